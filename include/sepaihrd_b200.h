@@ -1,0 +1,183 @@
+/*
+ * sepaihrd_b200.h -- C ABI of the B200-native batched SEPAIHRD likelihood evaluator.
+ *
+ * This is the drop-in boundary for ONE hot path of
+ * adjo0043/Mathematical-Modeling-Of-Infectious-Diseases-V1:
+ *
+ *     parameters -> AgeSEPAIHRDModel RHS -> adaptive Dopri5 (Boost.Odeint semantics)
+ *                -> daily incidence -> Poisson log-likelihood
+ *
+ * evaluated for B parameter vectors per call on one GPU.  The reference has no C ABI today:
+ * its boundary is the C++ virtual interface
+ *     double IObjectiveFunction::calculate(const Eigen::VectorXd&) const
+ *         (reference include/sir_age_structured/interfaces/IObjectiveFunction.hpp:24)
+ * implemented by SEPAIHRDObjectiveFunction::calculate
+ *         (reference src/model/objectives/SEPAIHRDObjectiveFunction.cpp:62-235).
+ * Every entry point below states which reference function(s) it replaces.  INTEGRATION.md
+ * shows the adapter a reference maintainer would add on their side.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no exceptions cross this boundary; every call returns a
+ *     sepaihrd_rc (0 = OK).  sepaihrd_last_error() gives a thread-local message.
+ *   - per-set failures are NOT call failures: the set's logL is -DBL_MAX
+ *     (std::numeric_limits<double>::lowest(), SEPAIHRDObjectiveFunction.cpp:111,119,161,227) and
+ *     the reason is in out_status[b] (SEPAIHRD_ST_* bits).
+ *   - all floating point is IEEE binary64.
+ *   - there is NO CPU fallback: if no CUDA device is usable, sepaihrd_create fails.
+ */
+#ifndef SEPAIHRD_B200_H
+#define SEPAIHRD_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SEPAIHRD_ABI_VERSION 1
+
+/* Number of compartments: S,E,P,A,I,H,ICU,R,D,CumH,CumICU
+ * (reference include/model/ModelConstants.hpp:18). State layout is compartment-major:
+ * state[c*n_ages + age]  (reference src/model/AgeSEPAIHRDModel.cpp:116-134). */
+#define SEPAIHRD_NUM_COMPARTMENTS 11
+#define SEPAIHRD_MAX_AGES 16
+#define SEPAIHRD_MAX_SEGMENTS 32
+
+/* ---- return codes ------------------------------------------------------------------------ */
+typedef enum sepaihrd_rc {
+    SEPAIHRD_OK = 0,
+    SEPAIHRD_ERR_INVALID_ARGUMENT = 1, /* reference: InvalidParameterException */
+    SEPAIHRD_ERR_NO_DEVICE = 2,        /* CUDA extension / device missing: fail loudly */
+    SEPAIHRD_ERR_CUDA = 3,
+    SEPAIHRD_ERR_UNSUPPORTED = 4,
+    SEPAIHRD_ERR_OUT_OF_MEMORY = 5
+} sepaihrd_rc;
+
+/* ---- per-set status bits (out_status) ------------------------------------------------------ */
+#define SEPAIHRD_ST_OK             0u
+#define SEPAIHRD_ST_S_OVERFLOW     1u  /* sum of non-S compartments > N_i: calculate() returns lowest() (ObjectiveFunction.cpp:161) */
+#define SEPAIHRD_ST_STEP_FAILURE   2u  /* >500 consecutive rejected steps: Boost failed_step_checker; reference throws SimulationException (Dopri5SolverStrategy.cpp:38-42) */
+#define SEPAIHRD_ST_NONFINITE      4u  /* total logL NaN/Inf -> lowest() (ObjectiveFunction.cpp:227) */
+#define SEPAIHRD_ST_INVALID_PARAM  8u  /* negative kappa: setCalibratableValues throws, caught at ObjectiveFunction.cpp:117-122 -> lowest() */
+
+/* ---- parameter-slot layout ----------------------------------------------------------------
+ * A "slot vector" is the flat image of reference struct SEPAIHRDParameters
+ * (include/model/parameters/SEPAIHRDParameters.hpp) restricted to what the hot path reads.
+ * For n = n_ages, nb = n_beta, nk = n_kappa the slots are, in order:
+ *   beta_values[nb] | kappa_values[nk] (kappa_values[0] = fixed baseline kappa_1) |
+ *   theta sigma gamma_p gamma_A gamma_I gamma_H gamma_ICU |
+ *   a[n] h_infec[n] p[n] h[n] icu[n] d_H[n] d_ICU[n] d_community[n] |
+ *   E0 P0 A0 I0 H0 ICU0 R0 D0 multipliers | seed_exposed runup_days | beta (scalar, quirk Q1)
+ */
+int32_t sepaihrd_slot_count(int32_t n_ages, int32_t n_beta, int32_t n_kappa);
+
+/* Resolve a reference parameter name ("beta_3", "kappa_2", "h_infec_1", "gamma_ICU", ...) to
+ * its slot index, with the same prefix-dispatch order as
+ * SEPAIHRDParameterManager::updateModelParameters (src/model/parameters/SEPAIHRDParameterManager.cpp:197-267).
+ * Returns -1 for an unknown name, -2 for a name that the reference rejects at construction
+ * (kappa_1 / kappa_baseline with a fixed baseline, out-of-range index; .cpp:45-88). */
+int32_t sepaihrd_slot_for_name(int32_t n_ages, int32_t n_beta, int32_t n_kappa, const char* name);
+
+/* ---- problem description (everything that is constant across parameter sets) ------------- */
+typedef struct sepaihrd_problem {
+    int32_t abi_version;          /* = SEPAIHRD_ABI_VERSION */
+    int32_t n_ages;               /* n: 4 (Spain-2020) or 16 (synthetic variant) on the GPU; any <=16 */
+    int32_t n_times;              /* K output times, strictly increasing (Simulator.cpp:82-90)          */
+    int32_t n_obs;                /* rows of each observation matrix; must equal K - runup_offset       */
+    const double* times;          /* [K]   (src/model/main.cpp:244-253: integers -int(runup)..num_days-1) */
+    const double* obs_hosp;       /* [n_obs*n] row-major (day, age): CalibrationData::getNewHospitalizations */
+    const double* obs_icu;        /* [n_obs*n] getNewICU                                                */
+    const double* obs_deaths;     /* [n_obs*n] getNewDeaths                                             */
+    const double* population;     /* [n]  N                                                             */
+    const double* contact_matrix; /* [n*n] COLUMN-major M(i,j) = data[j*n+i] (Eigen default; AgeSEPAIHRDModel.cpp:145,168) */
+    int32_t n_beta;               /* length of beta_end_times / beta_values (element 0 = baseline period) */
+    int32_t n_kappa;              /* length of kappa_end_times / kappa_values (element 0 = fixed baseline) */
+    const double* beta_end_times; /* [n_beta]  (initial_guess.txt:6)                                    */
+    const double* kappa_end_times;/* [n_kappa] (initial_guess.txt:7)                                    */
+    const double* base_slots;     /* [sepaihrd_slot_count] values of every slot for non-calibrated parameters */
+    const double* data_initial_state; /* [11*n] CalibrationData::getInitialSEPAIHRDState (multiplier mode, a6) */
+    int32_t n_params;             /* P: length of each parameter vector handed to eval                  */
+    int32_t constraint_mode;      /* 0 = OPTIMIZATION_CLAMP, 1 = MCMC_REFLECT (SEPAIHRDParameterManager.hpp:22-25) */
+    const int32_t* param_slot;    /* [P] slot of calibrated parameter i (from sepaihrd_slot_for_name)   */
+    const double* lower_bound;    /* [P] (param_bounds.txt); NaN = parameter has no bounds entry        */
+    const double* upper_bound;    /* [P]                                                                */
+    double abs_tol;               /* 1e-6 (main.cpp:260)                                                */
+    double rel_tol;               /* 1e-6 (main.cpp:261)                                                */
+    double dt_hint;               /* 1.0: objective builds its simulator with time_step 1.0 (ObjectiveFunction.cpp:113) */
+} sepaihrd_problem;
+
+typedef struct sepaihrd_ctx sepaihrd_ctx; /* opaque: owns device copies of the problem, a stream, scratch */
+
+/* Arithmetic flavour of the kernels.
+ *   SEPAIHRD_MATH_FAST   : FMA-contracted, likelihood accumulated per lane (default; production)
+ *   SEPAIHRD_MATH_STRICT : unfused IEEE mul/add in the reference's source order, likelihood summed
+ *                          row-by-row like calculateSingleLogLikelihood; bit-comparable with the
+ *                          CPU oracle up to libm (log/pow) differences. */
+#define SEPAIHRD_MATH_FAST   0
+#define SEPAIHRD_MATH_STRICT 1
+
+/* Replaces: construction of AgeSEPAIHRDModel + PiecewiseConstantNpiStrategy + SEPAIHRDParameterManager
+ * + SEPAIHRDObjectiveFunction + AgeSEPAIHRDSimulator + Dopri5SolverStrategy
+ * (src/model/SEPAIHRDModelCalibration.cpp:73-132; ObjectiveFunction.cpp:22-50).
+ * device < 0 means "current CUDA device". The problem is deep-copied. */
+sepaihrd_rc sepaihrd_create(const sepaihrd_problem* problem, int32_t device, sepaihrd_ctx** out_ctx);
+void        sepaihrd_destroy(sepaihrd_ctx* ctx);
+
+/* Replaces SEPAIHRDParameterManager::setConstraintMode (SEPAIHRDParameterManager.hpp:138). */
+sepaihrd_rc sepaihrd_set_constraint_mode(sepaihrd_ctx* ctx, int32_t mode);
+sepaihrd_rc sepaihrd_set_math_mode(sepaihrd_ctx* ctx, int32_t mode);
+/* Work on a caller-provided CUDA stream (cudaStream_t cast to void*); NULL = ctx-owned stream. */
+sepaihrd_rc sepaihrd_set_stream(sepaihrd_ctx* ctx, void* cuda_stream);
+
+/* Replaces B calls of SEPAIHRDObjectiveFunction::calculate (ObjectiveFunction.cpp:62-235) with a
+ * NullSimulationCache (benchmark_main.cpp:229-238).  HOST buffers:
+ *   params     [B][ld] row-major, ld >= P: one Eigen::VectorXd per row, unconstrained (constraints
+ *              are applied on the device like updateModelParameters -> applyConstraints, .cpp:173)
+ *   out_ll     [B]   log-likelihood or -DBL_MAX
+ *   out_status [B]   SEPAIHRD_ST_* bits, may be NULL
+ *   out_steps  [B][2] accepted / rejected Dopri5 step attempts, may be NULL (parity diagnostics)
+ * Copies H2D, runs the fused kernel, copies D2H, synchronises. */
+sepaihrd_rc sepaihrd_eval_batch(sepaihrd_ctx* ctx, const double* params, int64_t B, int64_t ld,
+                                double* out_ll, uint32_t* out_status, int32_t* out_steps);
+
+/* Same, with DEVICE pointers and no synchronisation: work is enqueued on the ctx stream. */
+sepaihrd_rc sepaihrd_eval_batch_device(sepaihrd_ctx* ctx, const double* d_params, int64_t B, int64_t ld,
+                                       double* d_out_ll, uint32_t* d_out_status, int32_t* d_out_steps);
+
+/* Trajectory output selector for sepaihrd_simulate_batch. */
+#define SEPAIHRD_TRAJ_FULL      0  /* all 11*n state components per output time                     */
+#define SEPAIHRD_TRAJ_OBSERVED  1  /* D, CumH, CumICU only (3*n per output time), the streams that
+                                      SimulationResultProcessor::getCompartmentData extracts
+                                      (ObjectiveFunction.cpp:172-174)                                */
+
+/* Replaces B calls of AgeSEPAIHRDSimulator::run / Simulator::run (src/sir_age_structured/Simulator.cpp:60-150)
+ * on models updated by updateModelParameters, with the initial-state rule of calculate()
+ * (ObjectiveFunction.cpp:124-163).  HOST buffers.
+ *   what       SEPAIHRD_TRAJ_*
+ *   stride     keep every stride-th output time starting at index 0 (1 = all K times)
+ *   out        [B][ceil(K/stride)][W] with W = 11*n or 3*n; rows of failed sets are NaN-filled
+ *   out_status [B] may be NULL */
+sepaihrd_rc sepaihrd_simulate_batch(sepaihrd_ctx* ctx, const double* params, int64_t B, int64_t ld,
+                                    int32_t what, int32_t stride, double* out, uint32_t* out_status);
+sepaihrd_rc sepaihrd_simulate_batch_device(sepaihrd_ctx* ctx, const double* d_params, int64_t B, int64_t ld,
+                                           int32_t what, int32_t stride, double* d_out, uint32_t* d_out_status);
+
+/* Block until everything enqueued on the ctx stream has finished. */
+sepaihrd_rc sepaihrd_synchronize(sepaihrd_ctx* ctx);
+
+/* Counters since creation: kernel launches issued by this ctx, parameter sets evaluated. */
+sepaihrd_rc sepaihrd_get_counters(const sepaihrd_ctx* ctx, int64_t* launches, int64_t* sets);
+
+/* Device-side FP64 pipe microbenchmark (dependent DFMA chains on every SM): returns the measured
+ * peak in FP64 instructions/s (x2 for FMA-counted FLOP/s).  Used as the roofline denominator,
+ * because MEASURED_PEAKS.json has no FP64 entry. */
+sepaihrd_rc sepaihrd_measure_fp64_peak(int32_t device, double* out_dfma_per_second);
+
+const char* sepaihrd_last_error(void);
+const char* sepaihrd_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEPAIHRD_B200_H */
