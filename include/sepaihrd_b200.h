@@ -127,7 +127,10 @@ void        sepaihrd_destroy(sepaihrd_ctx* ctx);
 /* Replaces SEPAIHRDParameterManager::setConstraintMode (SEPAIHRDParameterManager.hpp:138). */
 sepaihrd_rc sepaihrd_set_constraint_mode(sepaihrd_ctx* ctx, int32_t mode);
 sepaihrd_rc sepaihrd_set_math_mode(sepaihrd_ctx* ctx, int32_t mode);
-/* Work on a caller-provided CUDA stream (cudaStream_t cast to void*); NULL = ctx-owned stream. */
+/* Work on a caller-provided CUDA stream (cudaStream_t cast to void*).  NULL is the CUDA legacy default
+ * stream (what torch.cuda.current_stream().cuda_stream returns by default); SEPAIHRD_STREAM_OWN selects
+ * the non-blocking stream the ctx created for itself (the initial setting). */
+#define SEPAIHRD_STREAM_OWN ((void*)(intptr_t)-1)
 sepaihrd_rc sepaihrd_set_stream(sepaihrd_ctx* ctx, void* cuda_stream);
 
 /* Replaces B calls of SEPAIHRDObjectiveFunction::calculate (ObjectiveFunction.cpp:62-235) with a

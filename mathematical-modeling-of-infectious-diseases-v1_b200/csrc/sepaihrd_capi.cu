@@ -1,0 +1,494 @@
+// sepaihrd_capi.cu -- C ABI (include/sepaihrd_b200.h) over the fused CUDA kernels.
+// No torch types, no CPU fallback: every compute entry point needs a CUDA device.
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "sepaihrd_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+sepaihrd_rc fail(sepaihrd_rc rc, const std::string& msg) {
+    g_last_error = msg;
+    return rc;
+}
+
+#define CUDA_TRY(expr)                                                                                 \
+    do {                                                                                               \
+        cudaError_t _e = (expr);                                                                       \
+        if (_e != cudaSuccess)                                                                         \
+            return fail(_e == cudaErrorMemoryAllocation ? SEPAIHRD_ERR_OUT_OF_MEMORY : SEPAIHRD_ERR_CUDA, \
+                        std::string(#expr) + ": " + cudaGetErrorString(_e));                           \
+    } while (0)
+
+// ---- slot layout ------------------------------------------------------------------------------------
+struct Layout {
+    int n, nb, nk;
+    int scal0() const { return nb + nk; }
+    int age0() const { return scal0() + 7; }
+    int mult0() const { return age0() + 8 * n; }
+    int count() const { return mult0() + 11; }
+};
+
+bool has_prefix(const char* s, const char* prefix, size_t* len) {
+    size_t l = std::strlen(prefix);
+    *len = l;
+    return std::strncmp(s, prefix, l) == 0;
+}
+
+// decimal index after a prefix, as std::stoul would read it (digits required)
+bool read_index(const char* s, long* out) {
+    if (*s < '0' || *s > '9') return false;
+    char* end = nullptr;
+    *out = std::strtol(s, &end, 10);
+    return end != s;
+}
+
+}  // namespace
+
+struct sepaihrd_ctx {
+    int device = 0;
+    int n = 0, K = 0, n_obs = 0, nb = 0, nk = 0, P = 0, nslots = 0, nseg = 0, runup_offset = 0;
+    int constraint_mode = 0, math_mode = SEPAIHRD_MATH_FAST;
+    bool obs_mismatch = false;
+    double abs_tol = 1e-6, rel_tol = 1e-6, dt_hint = 1.0, hmax = 1.0;
+    std::vector<double> blob;   // host image
+    sepaihrd::KParams kp{};     // offsets etc. (I/O fields filled per call)
+    double* d_blob = nullptr;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    int num_sms = 0;
+    // scratch for the host-pointer entry points (grown on demand)
+    double* d_params = nullptr; size_t cap_params = 0;
+    double* d_out = nullptr; size_t cap_out = 0;
+    unsigned* d_status = nullptr; size_t cap_status = 0;
+    int* d_steps = nullptr; size_t cap_steps = 0;
+    long long launches = 0, sets = 0;
+};
+
+namespace {
+
+template <class T>
+sepaihrd_rc grow(T** ptr, size_t* cap, size_t need) {
+    if (need <= *cap) return SEPAIHRD_OK;
+    if (*ptr) cudaFree(*ptr);
+    *ptr = nullptr; *cap = 0;
+    CUDA_TRY(cudaMalloc((void**)ptr, need * sizeof(T)));
+    *cap = need;
+    return SEPAIHRD_OK;
+}
+
+struct LaunchCfg { int threads, minblocks; };
+
+template <int NA, bool STRICT, int MODE, int THREADS, int MINBLOCKS>
+sepaihrd_rc launch_t(sepaihrd_ctx* ctx, const sepaihrd::KParams& kp_in) {
+    using namespace sepaihrd;
+    KParams kp = kp_in;
+    constexpr int SETS = THREADS / NA;
+    kp.tiles = (kp.B + SETS - 1) / SETS;
+    auto kern = sepaihrd_batch_kernel<NA, STRICT, MODE, THREADS, MINBLOCKS>;
+    const size_t smem = (size_t)kp.blob_bytes + sizeof(double) * SETS * (size_t)(kp.slot_stride + kp.seg_stride) + 16;
+    static bool attr_set[64] = {};   // per device
+    if (!attr_set[ctx->device & 63]) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set[ctx->device & 63] = true;
+    }
+    if (smem > 200 * 1024) return fail(SEPAIHRD_ERR_UNSUPPORTED, "problem constants do not fit in shared memory");
+    int occ = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, smem));
+    if (occ < 1) return fail(SEPAIHRD_ERR_CUDA, "kernel does not fit on an SM");
+    long long grid = std::min<long long>(kp.tiles, (long long)ctx->num_sms * occ);
+    if (grid < 1) grid = 1;
+    kern<<<(unsigned)grid, THREADS, smem, ctx->stream>>>(kp);
+    CUDA_TRY(cudaGetLastError());
+    ctx->launches += 1;
+    ctx->sets += kp.B;
+    return SEPAIHRD_OK;
+}
+
+template <int NA, int THREADS, int MINBLOCKS>
+sepaihrd_rc launch_na(sepaihrd_ctx* ctx, const sepaihrd::KParams& kp, int mode) {
+    using namespace sepaihrd;
+    const bool strict = ctx->math_mode == SEPAIHRD_MATH_STRICT;
+    if (mode == MODE_LL)
+        return strict ? launch_t<NA, true, MODE_LL, THREADS, MINBLOCKS>(ctx, kp) : launch_t<NA, false, MODE_LL, THREADS, MINBLOCKS>(ctx, kp);
+    return strict ? launch_t<NA, true, MODE_TRAJ, THREADS, MINBLOCKS>(ctx, kp) : launch_t<NA, false, MODE_TRAJ, THREADS, MINBLOCKS>(ctx, kp);
+}
+
+sepaihrd_rc launch(sepaihrd_ctx* ctx, const sepaihrd::KParams& kp, int mode) {
+    switch (ctx->n) {
+        case 4: return launch_na<4, 128, 2>(ctx, kp, mode);
+        case 16: return launch_na<16, 128, 1>(ctx, kp, mode);
+        default: return fail(SEPAIHRD_ERR_UNSUPPORTED, "GPU kernels are instantiated for n_ages = 4 and 16");
+    }
+}
+
+__global__ void fill_kernel(double* ll, unsigned* st, int* steps, long long B, double v, unsigned s) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < B) {
+        ll[i] = v;
+        if (st) st[i] = s;
+        if (steps) { steps[2 * i] = 0; steps[2 * i + 1] = 0; }
+    }
+}
+
+// ---- FP64 pipe microbenchmark --------------------------------------------------------------------------
+constexpr int PEAK_CHAINS = 8, PEAK_ITERS = 4096;
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, double a, double b) {
+    double v[PEAK_CHAINS];
+#pragma unroll
+    for (int c = 0; c < PEAK_CHAINS; ++c) v[c] = a + c + threadIdx.x * 1e-9;
+#pragma unroll 1
+    for (int it = 0; it < PEAK_ITERS; ++it) {
+#pragma unroll
+        for (int c = 0; c < PEAK_CHAINS; ++c) v[c] = fma(v[c], b, a);
+    }
+    double s = 0;
+#pragma unroll
+    for (int c = 0; c < PEAK_CHAINS; ++c) s += v[c];
+    if (s == 123.456) out[0] = s;   // never true: keeps the chains alive
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t sepaihrd_slot_count(int32_t n, int32_t nb, int32_t nk) { return Layout{n, nb, nk}.count(); }
+
+int32_t sepaihrd_slot_for_name(int32_t n, int32_t nb, int32_t nk, const char* name) {
+    if (!name) return -1;
+    const Layout L{n, nb, nk};
+    size_t len = 0;
+    long idx = 0;
+    // exact scalar names first where the reference tests equality before prefixes
+    if (std::strcmp(name, "beta") == 0) return L.mult0() + 10;
+    if (has_prefix(name, "beta_", &len)) {
+        if (!read_index(name + len, &idx) || idx < 1 || idx > nb) return -2;
+        return (int)idx - 1;
+    }
+    static const char* scalars[7] = {"theta", "sigma", "gamma_p", "gamma_A", "gamma_I", "gamma_H", "gamma_ICU"};
+    for (int s = 0; s < 7; ++s)
+        if (std::strcmp(name, scalars[s]) == 0) return L.scal0() + s;
+    // per-age blocks, in the reference's if/else order (a_, h_infec_, p_, h_, icu_, d_H_, d_ICU_, d_community_)
+    static const char* blocks[8] = {"a_", "h_infec_", "p_", "h_", "icu_", "d_H_", "d_ICU_", "d_community_"};
+    for (int b = 0; b < 8; ++b)
+        if (has_prefix(name, blocks[b], &len)) {
+            if (!read_index(name + len, &idx) || idx >= n) return -2;
+            return L.age0() + b * n + (int)idx;
+        }
+    if (std::strcmp(name, "seed_exposed") == 0) return L.mult0() + 8;
+    if (std::strcmp(name, "runup_days") == 0) return L.mult0() + 9;
+    static const char* mult[8] = {"E0_multiplier", "P0_multiplier", "A0_multiplier", "I0_multiplier",
+                                  "H0_multiplier", "ICU0_multiplier", "R0_multiplier", "D0_multiplier"};
+    for (int m = 0; m < 8; ++m)
+        if (std::strcmp(name, mult[m]) == 0) return L.mult0() + m;
+    if (has_prefix(name, "kappa_", &len)) {
+        if (!read_index(name + len, &idx) || idx < 2 || idx > nk) return -2;   // kappa_1 is the fixed baseline
+        return nb + (int)idx - 1;
+    }
+    return -1;
+}
+
+const char* sepaihrd_last_error(void) { return g_last_error.c_str(); }
+const char* sepaihrd_version(void) { return "sepaihrd_b200 0.1.0 (sm_100a)"; }
+
+sepaihrd_rc sepaihrd_create(const sepaihrd_problem* pb, int32_t device, sepaihrd_ctx** out_ctx) {
+    if (!pb || !out_ctx) return fail(SEPAIHRD_ERR_INVALID_ARGUMENT, "null argument");
+    *out_ctx = nullptr;
+    if (pb->abi_version != SEPAIHRD_ABI_VERSION) return fail(SEPAIHRD_ERR_INVALID_ARGUMENT, "ABI version mismatch");
+    const int n = pb->n_ages, K = pb->n_times, nb = pb->n_beta, nk = pb->n_kappa, P = pb->n_params;
+    if (n < 1 || n > SEPAIHRD_MAX_AGES) return fail(SEPAIHRD_ERR_INVALID_ARGUMENT, "n_ages out of range");
+    if (K < 1) return fail(SEPAIHRD_ERR_INVALID_ARGUMENT, "Output time points vector cannot be empty.");   // Simulator.cpp:70-72
+    for (int i = 1; i < K; ++i)
+        if (!(pb->times[i] > pb->times[i - 1]))
+            return fail(SEPAIHRD_ERR_INVALID_ARGUMENT, "Output time points must be strictly increasing.");   // Simulator.cpp:82-90
+    if (nk < 1) return fail(SEPAIHRD_ERR_INVALID_ARGUMENT, "NPI strategy needs at least the baseline period");
+    if (pb->kappa_end_times[0] < 0.0)
+        return fail(SEPAIHRD_ERR_INVALID_ARGUMENT, "Baseline period end time must be non-negative.");   // NPI.cpp:24-26
+    for (int k = 1; k < nk; ++k)
+        if (!(pb->kappa_end_times[k] > pb->kappa_end_times[k - 1]))
+            return fail(SEPAIHRD_ERR_INVALID_ARGUMENT, "NPI end times must be strictly increasing.");   // NPI.cpp:36-46
+    for (int k = 1; k < nb; ++k)
+        if (!(pb->beta_end_times[k] > pb->beta_end_times[k - 1]))
+            return fail(SEPAIHRD_ERR_INVALID_ARGUMENT, "beta end times must be strictly increasing.");  // PiecewiseConstantParameterStrategy.cpp:22-34
+    if (P < 1) return fail(SEPAIHRD_ERR_INVALID_ARGUMENT, "Parameter names list cannot be empty.");      // ParameterManager.cpp:26-28
+    if (pb->abs_tol < 0 || pb->rel_tol < 0) return fail(SEPAIHRD_ERR_INVALID_ARGUMENT, "Error tolerances cannot be negative.");   // Simulator.cpp:46-52
+    if (!(pb->dt_hint > 0)) return fail(SEPAIHRD_ERR_INVALID_ARGUMENT, "Time step hint must be positive.");   // Simulator.cpp:39-41
+    const Layout L{n, nb, nk};
+    for (int i = 0; i < P; ++i)
+        if (pb->param_slot[i] < -1 || pb->param_slot[i] >= L.count())
+            return fail(SEPAIHRD_ERR_INVALID_ARGUMENT, "param_slot out of range (use sepaihrd_slot_for_name)");
+
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count < 1)
+        return fail(SEPAIHRD_ERR_NO_DEVICE, "no CUDA device: sepaihrd_b200 has no CPU fallback");
+    if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) device = 0; }
+    if (device >= count) return fail(SEPAIHRD_ERR_NO_DEVICE, "CUDA device index out of range");
+    CUDA_TRY(cudaSetDevice(device));
+
+    sepaihrd_ctx* ctx = new sepaihrd_ctx();
+    ctx->device = device;
+    ctx->n = n; ctx->K = K; ctx->n_obs = pb->n_obs; ctx->nb = nb; ctx->nk = nk; ctx->P = P; ctx->nslots = L.count();
+    ctx->constraint_mode = pb->constraint_mode; ctx->abs_tol = pb->abs_tol; ctx->rel_tol = pb->rel_tol; ctx->dt_hint = pb->dt_hint;
+    // runup_offset_ = first index with t >= 0 (ObjectiveFunction.cpp:39-46)
+    ctx->runup_offset = 0;
+    for (int i = 0; i < K; ++i) if (pb->times[i] >= 0.0) { ctx->runup_offset = i; break; }
+    ctx->obs_mismatch = (K - ctx->runup_offset) != pb->n_obs;   // calculate() then returns lowest() (.cpp:176-178)
+    ctx->hmax = 0.0;
+    for (int i = 1; i < K; ++i) ctx->hmax = std::max(ctx->hmax, pb->times[i] - pb->times[i - 1]);
+
+    // merged schedule segments: segment s = number of breakpoints strictly below t ("t <= end_k" picks k)
+    std::vector<double> bp;
+    for (int k = 0; k < nb; ++k) bp.push_back(pb->beta_end_times[k]);
+    for (int k = 0; k < nk; ++k) bp.push_back(pb->kappa_end_times[k]);
+    std::sort(bp.begin(), bp.end());
+    bp.erase(std::unique(bp.begin(), bp.end()), bp.end());
+    const int nseg = (int)bp.size();
+    if (nseg > SEPAIHRD_MAX_SEGMENTS) { delete ctx; return fail(SEPAIHRD_ERR_UNSUPPORTED, "too many schedule breakpoints"); }
+    ctx->nseg = nseg;
+    std::vector<int> segb(nseg + 1), segk(nseg + 1);
+    for (int s = 0; s <= nseg; ++s) {
+        const double tr = (s < nseg) ? bp[s] : bp[nseg - 1] + 1.0;
+        int ib = 0, ik = 0;
+        for (int k = 0; k < nb; ++k) if (tr > pb->beta_end_times[k]) ++ib;
+        for (int k = 0; k < nk; ++k) if (tr > pb->kappa_end_times[k]) ++ik;
+        segb[s] = std::min(ib, std::max(nb - 1, 0));
+        segk[s] = std::min(ik, nk - 1);
+    }
+
+    // later duplicates of a slot win in updateModelParameters' loop: disable the earlier ones
+    std::vector<int> pslot(P);
+    for (int i = 0; i < P; ++i) pslot[i] = pb->param_slot[i];
+    for (int i = 0; i < P; ++i)
+        for (int j = i + 1; j < P; ++j)
+            if (pslot[i] >= 0 && pslot[i] == pslot[j]) { pslot[i] = -1; break; }
+
+    // ---- pack the constants blob ---------------------------------------------------------------------
+    std::vector<double>& B = ctx->blob;
+    auto put = [&](const double* src, size_t cnt) { int off = (int)B.size(); B.insert(B.end(), src, src + cnt); return off; };
+    auto put_ints = [&](const int* src, size_t cnt) {
+        int off = (int)B.size();
+        B.resize(B.size() + (cnt + 1) / 2, 0.0);
+        std::memcpy(B.data() + off, src, cnt * sizeof(int));
+        return off;
+    };
+    sepaihrd::KParams& kp = ctx->kp;
+    kp.o_times = put(pb->times, K);
+    kp.o_obs_h = put(pb->obs_hosp, (size_t)pb->n_obs * n);
+    kp.o_obs_i = put(pb->obs_icu, (size_t)pb->n_obs * n);
+    kp.o_obs_d = put(pb->obs_deaths, (size_t)pb->n_obs * n);
+    kp.o_pop = put(pb->population, n);
+    {
+        // age_fraction = N / N.sum() (ObjectiveFunction.cpp:100-107); inv_N (AgeSEPAIHRDModel.cpp:46-49)
+        double total = 0.0;
+        for (int i = 0; i < n; ++i) total += pb->population[i];
+        std::vector<double> frac(n), inv(n);
+        for (int i = 0; i < n; ++i) {
+            frac[i] = (total > 0.0) ? pb->population[i] / total : 0.0;
+            inv[i] = (pb->population[i] > 1e-9) ? 1.0 / pb->population[i] : 0.0;
+        }
+        kp.o_agefrac = put(frac.data(), n);
+        kp.o_invN = put(inv.data(), n);
+    }
+    kp.o_M = put(pb->contact_matrix, (size_t)n * n);
+    kp.o_bp = put(bp.data(), nseg);
+    kp.o_base = put(pb->base_slots, L.count());
+    kp.o_init = put(pb->data_initial_state, (size_t)SEPAIHRD_NUM_COMPARTMENTS * n);
+    kp.o_lo = put(pb->lower_bound, P);
+    kp.o_hi = put(pb->upper_bound, P);
+    kp.o_pslot = put_ints(pslot.data(), P);
+    kp.o_segb = put_ints(segb.data(), nseg + 1);
+    kp.o_segk = put_ints(segk.data(), nseg + 1);
+    if (B.size() % 2) B.push_back(0.0);   // multiple of 16 bytes for cp.async.bulk
+    kp.blob_bytes = (int)(B.size() * sizeof(double));
+    kp.n = n; kp.K = K; kp.n_obs = pb->n_obs; kp.runup_offset = ctx->runup_offset; kp.nb = nb; kp.nk = nk;
+    kp.nseg = nseg; kp.P = P; kp.nslots = L.count();
+    kp.slot_stride = L.count() | 1;
+    kp.seg_stride = (nseg + 1) | 1;
+    kp.abs_tol = pb->abs_tol; kp.rel_tol = pb->rel_tol; kp.dt_hint = pb->dt_hint; kp.hmax = ctx->hmax;
+
+    cudaDeviceProp prop;
+    cudaError_t e = cudaGetDeviceProperties(&prop, device);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_blob, kp.blob_bytes);
+    if (e == cudaSuccess) e = cudaMemcpy(ctx->d_blob, B.data(), kp.blob_bytes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        std::string msg = std::string("CUDA setup failed: ") + cudaGetErrorString(e);
+        sepaihrd_destroy(ctx);
+        return fail(SEPAIHRD_ERR_CUDA, msg);
+    }
+    ctx->num_sms = prop.multiProcessorCount;
+    ctx->stream = ctx->own_stream;
+    kp.blob = ctx->d_blob;
+    if (pb->abs_tol <= 0.0) ctx->math_mode = SEPAIHRD_MATH_STRICT;   // FAST error norm needs a positive denominator
+    *out_ctx = ctx;
+    return SEPAIHRD_OK;
+}
+
+void sepaihrd_destroy(sepaihrd_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->d_blob) cudaFree(ctx->d_blob);
+    if (ctx->d_params) cudaFree(ctx->d_params);
+    if (ctx->d_out) cudaFree(ctx->d_out);
+    if (ctx->d_status) cudaFree(ctx->d_status);
+    if (ctx->d_steps) cudaFree(ctx->d_steps);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+sepaihrd_rc sepaihrd_set_constraint_mode(sepaihrd_ctx* ctx, int32_t mode) {
+    if (!ctx || (mode != 0 && mode != 1)) return fail(SEPAIHRD_ERR_INVALID_ARGUMENT, "bad constraint mode");
+    ctx->constraint_mode = mode;
+    return SEPAIHRD_OK;
+}
+
+sepaihrd_rc sepaihrd_set_math_mode(sepaihrd_ctx* ctx, int32_t mode) {
+    if (!ctx || (mode != SEPAIHRD_MATH_FAST && mode != SEPAIHRD_MATH_STRICT)) return fail(SEPAIHRD_ERR_INVALID_ARGUMENT, "bad math mode");
+    if (mode == SEPAIHRD_MATH_FAST && ctx->abs_tol <= 0.0) return fail(SEPAIHRD_ERR_UNSUPPORTED, "FAST math needs abs_tol > 0");
+    ctx->math_mode = mode;
+    return SEPAIHRD_OK;
+}
+
+sepaihrd_rc sepaihrd_set_stream(sepaihrd_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return fail(SEPAIHRD_ERR_INVALID_ARGUMENT, "null ctx");
+    ctx->stream = (cuda_stream == SEPAIHRD_STREAM_OWN) ? ctx->own_stream : (cudaStream_t)cuda_stream;
+    return SEPAIHRD_OK;
+}
+
+sepaihrd_rc sepaihrd_synchronize(sepaihrd_ctx* ctx) {
+    if (!ctx) return fail(SEPAIHRD_ERR_INVALID_ARGUMENT, "null ctx");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return SEPAIHRD_OK;
+}
+
+sepaihrd_rc sepaihrd_get_counters(const sepaihrd_ctx* ctx, int64_t* launches, int64_t* sets) {
+    if (!ctx) return fail(SEPAIHRD_ERR_INVALID_ARGUMENT, "null ctx");
+    if (launches) *launches = ctx->launches;
+    if (sets) *sets = ctx->sets;
+    return SEPAIHRD_OK;
+}
+
+sepaihrd_rc sepaihrd_eval_batch_device(sepaihrd_ctx* ctx, const double* d_params, int64_t B, int64_t ld,
+                                       double* d_out_ll, uint32_t* d_out_status, int32_t* d_out_steps) {
+    if (!ctx || !d_out_ll || (B > 0 && !d_params)) return fail(SEPAIHRD_ERR_INVALID_ARGUMENT, "null argument");
+    if (B < 0 || ld < ctx->P) return fail(SEPAIHRD_ERR_INVALID_ARGUMENT, "Parameter vector size mismatch.");   // ParameterManager.cpp:165-167
+    if (B == 0) return SEPAIHRD_OK;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    if (ctx->obs_mismatch) {
+        fill_kernel<<<(unsigned)((B + 255) / 256), 256, 0, ctx->stream>>>(d_out_ll, d_out_status, d_out_steps, B, -DBL_MAX,
+                                                                        SEPAIHRD_ST_INVALID_PARAM);
+        CUDA_TRY(cudaGetLastError());
+        ctx->launches += 1;
+        return SEPAIHRD_OK;
+    }
+    sepaihrd::KParams kp = ctx->kp;
+    kp.constraint_mode = ctx->constraint_mode;
+    kp.params = d_params; kp.B = B; kp.ld = ld;
+    kp.out_ll = d_out_ll; kp.out_status = d_out_status; kp.out_steps = d_out_steps;
+    kp.out_traj = nullptr; kp.traj_what = 0; kp.traj_stride = 1; kp.traj_rows = 0;
+    return launch(ctx, kp, sepaihrd::MODE_LL);
+}
+
+sepaihrd_rc sepaihrd_eval_batch(sepaihrd_ctx* ctx, const double* params, int64_t B, int64_t ld, double* out_ll,
+                                uint32_t* out_status, int32_t* out_steps) {
+    if (!ctx || !out_ll || (B > 0 && !params)) return fail(SEPAIHRD_ERR_INVALID_ARGUMENT, "null argument");
+    if (B < 0 || ld < ctx->P) return fail(SEPAIHRD_ERR_INVALID_ARGUMENT, "Parameter vector size mismatch.");
+    if (B == 0) return SEPAIHRD_OK;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    sepaihrd_rc rc;
+    if ((rc = grow(&ctx->d_params, &ctx->cap_params, (size_t)B * ld)) != SEPAIHRD_OK) return rc;
+    if ((rc = grow(&ctx->d_out, &ctx->cap_out, (size_t)B)) != SEPAIHRD_OK) return rc;
+    if ((rc = grow(&ctx->d_status, &ctx->cap_status, (size_t)B)) != SEPAIHRD_OK) return rc;
+    if (out_steps && (rc = grow(&ctx->d_steps, &ctx->cap_steps, (size_t)B * 2)) != SEPAIHRD_OK) return rc;
+    // chunked so the H2D copy of chunk c+1 overlaps the kernel of chunk c (two streams would be needed for
+    // full overlap with pageable memory; with pinned callers cudaMemcpyAsync already is asynchronous)
+    CUDA_TRY(cudaMemcpyAsync(ctx->d_params, params, sizeof(double) * (size_t)B * ld, cudaMemcpyHostToDevice, ctx->stream));
+    rc = sepaihrd_eval_batch_device(ctx, ctx->d_params, B, ld, ctx->d_out, ctx->d_status, out_steps ? ctx->d_steps : nullptr);
+    if (rc != SEPAIHRD_OK) return rc;
+    CUDA_TRY(cudaMemcpyAsync(out_ll, ctx->d_out, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_status) CUDA_TRY(cudaMemcpyAsync(out_status, ctx->d_status, sizeof(unsigned) * (size_t)B, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_steps) CUDA_TRY(cudaMemcpyAsync(out_steps, ctx->d_steps, sizeof(int) * (size_t)B * 2, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return SEPAIHRD_OK;
+}
+
+sepaihrd_rc sepaihrd_simulate_batch_device(sepaihrd_ctx* ctx, const double* d_params, int64_t B, int64_t ld,
+                                           int32_t what, int32_t stride, double* d_out, uint32_t* d_out_status) {
+    if (!ctx || !d_out || (B > 0 && !d_params)) return fail(SEPAIHRD_ERR_INVALID_ARGUMENT, "null argument");
+    if (B < 0 || ld < ctx->P) return fail(SEPAIHRD_ERR_INVALID_ARGUMENT, "Parameter vector size mismatch.");
+    if (what != SEPAIHRD_TRAJ_FULL && what != SEPAIHRD_TRAJ_OBSERVED) return fail(SEPAIHRD_ERR_INVALID_ARGUMENT, "bad trajectory selector");
+    if (stride < 1) return fail(SEPAIHRD_ERR_INVALID_ARGUMENT, "stride must be >= 1");
+    if (B == 0) return SEPAIHRD_OK;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    sepaihrd::KParams kp = ctx->kp;
+    kp.constraint_mode = ctx->constraint_mode;
+    kp.params = d_params; kp.B = B; kp.ld = ld;
+    kp.out_ll = nullptr; kp.out_status = d_out_status; kp.out_steps = nullptr;
+    kp.out_traj = d_out; kp.traj_what = what; kp.traj_stride = stride; kp.traj_rows = (ctx->K + stride - 1) / stride;
+    return launch(ctx, kp, sepaihrd::MODE_TRAJ);
+}
+
+sepaihrd_rc sepaihrd_simulate_batch(sepaihrd_ctx* ctx, const double* params, int64_t B, int64_t ld, int32_t what,
+                                    int32_t stride, double* out, uint32_t* out_status) {
+    if (!ctx || !out || (B > 0 && !params)) return fail(SEPAIHRD_ERR_INVALID_ARGUMENT, "null argument");
+    if (B < 0 || ld < ctx->P) return fail(SEPAIHRD_ERR_INVALID_ARGUMENT, "Parameter vector size mismatch.");
+    if (stride < 1) return fail(SEPAIHRD_ERR_INVALID_ARGUMENT, "stride must be >= 1");
+    if (B == 0) return SEPAIHRD_OK;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const int W = (what == SEPAIHRD_TRAJ_FULL) ? SEPAIHRD_NUM_COMPARTMENTS * ctx->n : 3 * ctx->n;
+    const size_t rows = (size_t)(ctx->K + stride - 1) / stride;
+    const size_t total = (size_t)B * rows * W;
+    sepaihrd_rc rc;
+    if ((rc = grow(&ctx->d_params, &ctx->cap_params, (size_t)B * ld)) != SEPAIHRD_OK) return rc;
+    if ((rc = grow(&ctx->d_out, &ctx->cap_out, total)) != SEPAIHRD_OK) return rc;
+    if ((rc = grow(&ctx->d_status, &ctx->cap_status, (size_t)B)) != SEPAIHRD_OK) return rc;
+    CUDA_TRY(cudaMemcpyAsync(ctx->d_params, params, sizeof(double) * (size_t)B * ld, cudaMemcpyHostToDevice, ctx->stream));
+    rc = sepaihrd_simulate_batch_device(ctx, ctx->d_params, B, ld, what, stride, ctx->d_out, ctx->d_status);
+    if (rc != SEPAIHRD_OK) return rc;
+    CUDA_TRY(cudaMemcpyAsync(out, ctx->d_out, sizeof(double) * total, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_status) CUDA_TRY(cudaMemcpyAsync(out_status, ctx->d_status, sizeof(unsigned) * (size_t)B, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return SEPAIHRD_OK;
+}
+
+sepaihrd_rc sepaihrd_measure_fp64_peak(int32_t device, double* out_dfma_per_second) {
+    if (!out_dfma_per_second) return fail(SEPAIHRD_ERR_INVALID_ARGUMENT, "null argument");
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count < 1) return fail(SEPAIHRD_ERR_NO_DEVICE, "no CUDA device");
+    if (device < 0) device = 0;
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    double* d_out = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&d_out, sizeof(double)));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256;
+    double best = 0.0;
+    for (int rep = 0; rep < 6; ++rep) {
+        CUDA_TRY(cudaEventRecord(e0));
+        dfma_peak_kernel<<<blocks, threads>>>(d_out, 1.0000001, 0.9999999);
+        CUDA_TRY(cudaEventRecord(e1));
+        CUDA_TRY(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        const double ops = (double)blocks * threads * PEAK_CHAINS * PEAK_ITERS;
+        if (rep > 0) best = std::max(best, ops / (ms * 1e-3));
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d_out);
+    *out_dfma_per_second = best;
+    return SEPAIHRD_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,346 @@
+"""CPU tests of the oracle (oracle/sepaihrd_oracle.cpp) against everything the reference pins for the
+hot path and against independent restatements.
+
+Reference tests mirrored here:
+  * ManualPoissonLikelihoodTest           tests/model/SEPAIHRDObjectivefunctionTest.cpp:688-752
+  * GetInitialSEPAIHRDState_*             tests/utils/GetCalibrationDataTests.cpp:163-227, 296-344
+  * property tests of the objective       tests/model/SEPAIHRDObjectivefunctionTest.cpp:330-508
+"""
+import math
+
+import numpy as np
+import pytest
+
+
+# ---------------------------------------------------------------------------------------------------
+# a7: Poisson log-likelihood -- the reference's only known-answer test
+def test_manual_poisson_likelihood_kat(orc):
+    obs = np.array([[5, 3], [2, 7], [4, 1], [6, 0], [3, 5]], dtype=float)
+    sim = np.array([[4.8, 3.2], [2.1, 6.9], [3.9, 1.1], [5.8, 0.2], [3.1, 4.9]])
+    manual = 0.0
+    for i in range(obs.shape[0]):
+        for j in range(obs.shape[1]):
+            s = sim[i, j] + 1e-10
+            manual += obs[i, j] * math.log(s) - s
+    assert abs(orc.poisson_ll(sim, obs) - manual) <= 1e-8          # EXPECT_NEAR(manual_ll, func_ll, 1e-8)
+
+
+def test_poisson_skips_negative_and_nonfinite_observations(orc):
+    # calculateSingleLogLikelihood: `if (obs >= 0.0 && std::isfinite(obs))` (ObjectiveFunction.cpp:267)
+    obs = np.array([[5.0, -1.0], [np.nan, 7.0], [np.inf, 1.0]])
+    sim = np.array([[4.8, 3.2], [2.1, 6.9], [3.9, 1.1]])
+    want = sum(o * math.log(s + 1e-10) - (s + 1e-10) for o, s in ((5.0, 4.8), (7.0, 6.9), (1.0, 1.1)))
+    assert orc.poisson_ll(sim, obs) == pytest.approx(want, rel=1e-15)
+    # negative simulated values are clamped to 0 before epsilon is added (.cpp:269-270)
+    assert orc.poisson_ll(np.array([[-3.0]]), np.array([[2.0]])) == pytest.approx(2.0 * math.log(1e-10) - 1e-10, rel=1e-15)
+
+
+# ---------------------------------------------------------------------------------------------------
+# a6 (multiplier mode): data-derived initial state
+def _initial_state_case(orc, pop, cum_c0, cum_d0, cum_h0, cum_i0, p_asym):
+    return orc.initial_state_from_data(pop, cum_c0, cum_d0, cum_h0, cum_i0, 1.0 / 5.2, 1.0 / 2.3, 1.0 / 7.0, 1.0 / 7.0, p_asym)
+
+
+def test_initial_state_correctly_calculates(orc):
+    n = 4
+    pop = [1000, 2000, 1500, 1000]
+    st = _initial_state_case(orc, pop, [5, 6, 7, 8], [0, 1, 1, 2], [2, 3, 4, 5], [1, 1, 2, 2], [0.5, 0.4, 0.3, 0.2])
+    assert st.shape == (11 * n,)
+    assert st[4 * n + 0] == 5 and st[5 * n + 0] == 2 and st[6 * n + 0] == 1 and st[8 * n + 0] == 0
+    assert st[9 * n + 0] == 2 and st[10 * n + 0] == 1
+    for age in range(n):
+        assert abs(sum(st[c * n + age] for c in range(9)) - pop[age]) <= 1e-6
+    assert (st >= 0).all()
+
+
+def test_initial_state_clamps_large_values(orc):
+    n = 4
+    pop = [100, 100, 100, 100]
+    st = _initial_state_case(orc, pop, [50, 10, 10, 10], [80, 10, 10, 10], [60, 10, 10, 10], [70, 10, 10, 10], [0.5] * 4)
+    assert st[8 * n + 0] == 80
+    assert 0 <= st[6 * n + 0] <= 20
+    for age in range(n):
+        assert abs(sum(st[c * n + age] for c in range(9)) - pop[age]) <= 1e-6
+
+
+def test_initial_state_oracle_equals_python_restatement(pkg, orc):
+    class D:  # minimal CalibrationData stand-in
+        pass
+    rng = np.random.default_rng(0)
+    for _ in range(20):
+        d = D()
+        d.population = rng.uniform(100, 1e6, 4).round()
+        d.cumulative_confirmed = rng.uniform(0, 500, (1, 4)).round()
+        d.cumulative_deaths = rng.uniform(0, 50, (1, 4)).round()
+        d.cumulative_hospitalizations = rng.uniform(0, 100, (1, 4)).round()
+        d.cumulative_icu = rng.uniform(0, 30, (1, 4)).round()
+        pa = rng.uniform(0, 1, 4)
+        a = pkg.config.initial_state_from_data(d, 0.3, 0.5, 0.25, 0.24, pa)
+        b = orc.initial_state_from_data(d.population, d.cumulative_confirmed[0], d.cumulative_deaths[0],
+                                        d.cumulative_hospitalizations[0], d.cumulative_icu[0], 0.3, 0.5, 0.25, 0.24, pa)
+        np.testing.assert_array_equal(a, b)
+
+
+def test_fixture_initial_state_matches_oracle(problem, orc):
+    # the committed problem's data_initial_state was produced by the Python reader; the oracle agrees
+    lay = problem.layout
+    s = problem.base_slots
+    # first row of the Spain window: all cumulative counts come from the CSV (not stored in the fixture),
+    # so check internal consistency instead: population balance and non-negativity
+    st = problem.data_initial_state.reshape(11, problem.n_ages)
+    assert (st >= 0).all()
+    np.testing.assert_allclose(st[:9].sum(0), problem.population, rtol=1e-12)
+    assert s[lay.runup_days] > 0 and s[lay.seed_exposed] > 0     # default config runs in run-up seeding mode (quirk Q4)
+
+
+# ---------------------------------------------------------------------------------------------------
+# a1-a3: RHS and schedules against a closed-form numpy restatement
+def _numpy_rhs(problem, slots, x, t):
+    lay = problem.layout
+    n = problem.n_ages
+    X = x.reshape(11, n)
+    S, E, P, A, I, H, U = X[:7]
+    g = lambda name: slots[lay.scalar(name)]
+    v = lambda blk: slots[lay.age(blk, 0):lay.age(blk, 0) + n]
+    be, ke = problem.beta_end_times, problem.kappa_end_times
+    ib = min(int(np.sum(t > be)), len(be) - 1)
+    ik = 0 if t < 0 else min(int(np.sum(t > ke)), len(ke) - 1)
+    beta_eff = slots[lay.beta0 + ib] * slots[lay.kappa0 + ik]
+    pressure = (P + A + g("theta") * I) * v("h_infec") / problem.population
+    lam = np.maximum(0.0, (problem.contact_matrix @ pressure) * beta_eff * v("a"))
+    d = np.empty_like(X)
+    d[0] = -lam * S
+    d[1] = lam * S - g("sigma") * E
+    d[2] = g("sigma") * E - g("gamma_p") * P
+    d[3] = v("p") * g("gamma_p") * P - g("gamma_A") * A
+    d[4] = (1 - v("p")) * g("gamma_p") * P - (g("gamma_I") + v("h") + v("d_community")) * I
+    d[5] = v("h") * I - (g("gamma_H") + v("d_H") + v("icu")) * H
+    d[6] = v("icu") * H - (g("gamma_ICU") + v("d_ICU")) * U
+    d[7] = g("gamma_A") * A + g("gamma_I") * I + g("gamma_H") * H + g("gamma_ICU") * U
+    d[8] = v("d_H") * H + v("d_ICU") * U + v("d_community") * I
+    d[9] = v("h") * I
+    d[10] = v("icu") * H
+    return d.reshape(-1)
+
+
+def test_rhs_matches_numpy_restatement(problem, oracle):
+    rng = np.random.default_rng(3)
+    for t in (-20.0, -0.5, 0.0, 12.9, 13.0, 13.0001, 63.0, 100.5, 305.0, 400.0):
+        x = rng.uniform(0, 1e5, problem.state_size)
+        got = oracle.rhs(problem.base_slots, x, t)
+        want = _numpy_rhs(problem, problem.base_slots, x, t)
+        np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-9)
+
+
+def test_rhs_conserves_population(problem, oracle):
+    x = np.random.default_rng(4).uniform(0, 1e5, problem.state_size)
+    d = oracle.rhs(problem.base_slots, x, 50.0).reshape(11, problem.n_ages)
+    np.testing.assert_allclose(d[:9].sum(0), 0.0, atol=1e-7)     # S..D flows cancel; CumH/CumICU are bookkeeping
+
+
+def test_schedule_breakpoint_belongs_to_old_segment(problem, oracle):
+    # quirk Q2: both schedules test `t <= end_k`, so t == breakpoint still uses the old segment
+    lay = problem.layout
+    x = np.random.default_rng(5).uniform(1, 1e4, problem.state_size)
+    s = problem.base_slots
+    for k, b in enumerate(problem.beta_end_times[:-1]):
+        at = oracle.rhs(s, x, float(b))
+        before = oracle.rhs(s, x, float(b) - 0.25)
+        after = oracle.rhs(s, x, float(b) + 1e-9)
+        np.testing.assert_array_equal(at, before)
+        if s[lay.beta0 + k] * s[lay.kappa0 + k] != s[lay.beta0 + k + 1] * s[lay.kappa0 + k + 1]:
+            assert not np.array_equal(at, after)
+    # past the last end time the last value is kept
+    np.testing.assert_array_equal(oracle.rhs(s, x, 1e6), oracle.rhs(s, x, float(problem.beta_end_times[-1]) + 1.0))
+
+
+# ---------------------------------------------------------------------------------------------------
+# a8: constraints
+def test_clamp_and_reflect(problem, oracle, pkg):
+    rng = np.random.default_rng(6)
+    lo, hi = problem.lower_bound, problem.upper_bound
+    for _ in range(50):
+        x = problem.base_params() + rng.normal(0, 1, problem.n_params) * (hi - lo) * 2
+        np.testing.assert_array_equal(oracle.apply_constraints(x, pkg.CLAMP), np.minimum(np.maximum(x, lo), hi))
+        r = oracle.apply_constraints(x, pkg.REFLECT)
+        w = hi - lo
+        y = np.fmod(x - lo, 2 * w)
+        y = np.where(y < 0, y + 2 * w, y)
+        want = np.where(y <= w, lo + y, hi - (y - w))
+        np.testing.assert_array_equal(r, want)
+        assert ((r >= lo - 1e-15) & (r <= hi + 1e-15)).all()
+    inside = lo + 0.3 * (hi - lo)
+    np.testing.assert_allclose(oracle.apply_constraints(inside, pkg.REFLECT), inside, rtol=1e-14)
+
+
+# ---------------------------------------------------------------------------------------------------
+# full evaluation: the survey's independent transcription is the only external anchor (parity unpinned)
+def test_default_evaluation_matches_survey_anchor(problem, oracle, golden):
+    a = golden["survey_anchor"]
+    r = oracle.eval_one(problem.base_params(), want_traj=True)
+    assert r["status"] == 0
+    assert r["ll"] == pytest.approx(a["logL"], rel=5e-13)
+    assert (r["accepted"], r["rejected"], r["rhs_calls"]) == (a["accepted"], a["rejected"], a["rhs_calls"])
+    n, t = problem.n_ages, problem.times
+    tr = r["traj"]
+    assert tr[np.where(t == 305)[0][0], 8 * n + 3] == pytest.approx(a["D_age3_t305"], rel=1e-9)
+    assert tr[np.where(t == 13)[0][0], 9 * n + 0] == pytest.approx(a["CumH_age0_t13"], rel=1e-9)
+    assert tr[np.where(t == 0)[0][0], 0] == pytest.approx(a["S_age0_t0"], rel=1e-9)
+
+
+def test_stream_likelihoods_match_survey_anchor(problem, oracle, orc, golden):
+    a = golden["survey_anchor"]
+    r = oracle.eval_one(problem.base_params(), want_traj=True)
+    n = problem.n_ages
+    tr = r["traj"].reshape(problem.n_times, 11, n)
+    off = problem.n_times - problem.n_obs
+    parts = []
+    for comp, obs in ((9, problem.obs_hosp), (10, problem.obs_icu), (8, problem.obs_deaths)):
+        inc = np.maximum(np.diff(tr[:, comp, :], axis=0, prepend=tr[:1, comp, :]), 0.0)
+        parts.append(orc.poisson_ll(inc[off:], obs))
+    assert parts[0] == pytest.approx(a["ll_H"], rel=1e-12)
+    assert parts[1] == pytest.approx(a["ll_ICU"], rel=1e-12)
+    assert parts[2] == pytest.approx(a["ll_D"], rel=1e-12)
+    assert (parts[0] + parts[1]) + parts[2] == r["ll"]
+
+
+def test_rejections_sit_at_schedule_breakpoints(problem, oracle):
+    # quirk Q2 as observed in the survey: all rejections are in the first interval and in the six
+    # intervals that start at a beta/kappa breakpoint
+    r = oracle.eval_one(problem.base_params(), want_interval_steps=True)
+    st = r["interval_steps"]
+    rej_days = set(problem.times[:-1][st[:, 1] > 0].tolist())
+    assert rej_days == {-20.0, 13.0, 63.0, 84.0, 111.0, 183.0, 237.0}
+    assert np.bincount(st.sum(1))[1] == 246
+
+
+def test_golden_vectors_reproduce(problem, oracle, orc, pkg, golden):
+    for key in ("jitter", "uniform"):
+        g = golden[key]
+        ll, st, steps, _ = oracle.eval_batch(np.array(g["params"]))
+        np.testing.assert_array_equal(ll, np.array(g["logL"]))
+        np.testing.assert_array_equal(steps, np.array(g["steps"]))
+        np.testing.assert_array_equal(st, np.array(g["status"]))
+    g = golden["reflect"]
+    ll, st, steps, _ = orc.Oracle(problem, constraint_mode=pkg.REFLECT).eval_batch(np.array(g["params"]))
+    np.testing.assert_array_equal(ll, np.array(g["logL"]))
+    # generators are deterministic functions of the seed (std::mt19937 + libstdc++ distributions)
+    np.testing.assert_array_equal(oracle.jitter_params(24, seed=1), np.array(golden["jitter"]["params"]))
+    np.testing.assert_array_equal(oracle.uniform_params(24, seed=2), np.array(golden["uniform"]["params"]))
+
+
+def test_trajectory_close_to_high_accuracy_solution(problem, oracle):
+    """Independent check of RHS + likelihood that does not share the step controller: scipy DOP853 at
+    1e-12.  The survey measured a 1.2e-4 max relative trajectory gap and -1.0e-5 relative in logL."""
+    from scipy.integrate import solve_ivp
+    base = problem.base_params()
+    r = oracle.eval_one(base, want_traj=True)
+    slots = problem.base_slots
+    x0 = r["traj"][0]
+    bps = sorted(set(problem.beta_end_times.tolist()) | set(problem.kappa_end_times.tolist()))
+    grid = problem.times
+    sol = [x0]
+    x = x0
+    # integrate segment by segment so the discontinuities are honoured exactly (left-closed segments, Q2)
+    edges = [grid[0]] + [b for b in bps if grid[0] < b < grid[-1]] + [grid[-1]]
+    out = {grid[0]: x0}
+    for a, b in zip(edges[:-1], edges[1:]):
+        tt = grid[(grid > a) & (grid <= b)]
+        mid = 0.5 * (a + b)
+        res = solve_ivp(lambda t, y: _numpy_rhs(problem, slots, y, mid), (a, b), x, method="DOP853", t_eval=tt,
+                        rtol=1e-12, atol=1e-12)
+        for ti, yi in zip(tt, res.y.T):
+            out[ti] = yi
+        x = res.y[:, -1]
+    ref = np.array([out[t] for t in grid])
+    scale = np.maximum(np.abs(ref), 1.0)
+    assert (np.abs(r["traj"] - ref) / scale).max() < 1e-3
+    rel = np.abs(r["traj"] - ref)[:, 8 * 4:] / np.maximum(np.abs(ref[:, 8 * 4:]), 1.0)
+    assert rel.max() < 5e-4
+
+
+# ---------------------------------------------------------------------------------------------------
+# properties the reference's own objective tests assert (SEPAIHRDObjectivefunctionTest.cpp:330-508)
+def test_objective_is_finite_repeatable_and_sensitive(problem, oracle):
+    base = problem.base_params()
+    vals = [oracle.eval_one(base)["ll"] for _ in range(5)]
+    assert all(math.isfinite(v) for v in vals) and len(set(vals)) == 1          # :344, :492-508
+    bumped = base.copy()
+    bumped[problem.param_names.index("beta_2")] += 0.02
+    assert oracle.eval_one(bumped)["ll"] != vals[0]                              # :380
+
+
+def test_nan_observations_are_tolerated(problem, orc, pkg):
+    p2 = pkg.Problem.from_json(problem.to_json())
+    p2.obs_hosp[10:20, 1] = np.nan
+    p2.obs_deaths[5, :] = -1.0
+    r = orc.Oracle(p2).eval_one(p2.base_params())
+    assert r["status"] == 0 and math.isfinite(r["ll"])                           # :454-489
+
+
+def test_failure_sentinels(problem, orc, pkg):
+    base = problem.base_params()
+    # NaN parameter -> NaN likelihood -> lowest() (ObjectiveFunction.cpp:227), quirk Q5: finite sentinel
+    bad = base.copy(); bad[problem.param_names.index("sigma")] = np.nan
+    r = orc.Oracle(problem).eval_one(bad)
+    assert r["ll"] == pkg.LOWEST and r["status"] & pkg.ST_NONFINITE
+    # ... but a NaN beta is swallowed by `std::max(0.0, lambda)` (AgeSEPAIHRDModel.cpp:196: (0.0 < NaN) is false ->
+    # lambda = 0): the evaluation stays finite.  Reproduced as is.
+    bad = base.copy(); bad[problem.param_names.index("beta_1")] = np.nan
+    r = orc.Oracle(problem).eval_one(bad)
+    assert r["status"] == 0 and math.isfinite(r["ll"])
+    # negative kappa -> setCalibratableValues throws -> lowest()
+    d = problem.to_json(); i = problem.param_names.index("kappa_3")
+    d["lower_bound"][i] = -5.0
+    p2 = pkg.Problem.from_json(d)
+    neg = p2.base_params(); neg[i] = -1.0
+    r = orc.Oracle(p2).eval_one(neg)
+    assert r["ll"] == pkg.LOWEST and r["status"] == pkg.ST_INVALID_PARAM
+    # multiplier mode with a huge E0 multiplier -> S overflow -> lowest()
+    d = problem.to_json()
+    iru, ie = problem.param_names.index("runup_days"), problem.param_names.index("E0_multiplier")
+    d["lower_bound"][iru] = -1.0; d["upper_bound"][ie] = 1e12
+    p3 = pkg.Problem.from_json(d)
+    x = p3.base_params(); x[iru] = -1.0; x[ie] = 1e12
+    r = orc.Oracle(p3).eval_one(x)
+    assert r["ll"] == pkg.LOWEST and r["status"] == pkg.ST_S_OVERFLOW
+    # ... and with sane multipliers the multiplier-mode path evaluates normally
+    x[ie] = 1.0
+    r = orc.Oracle(p3).eval_one(x)
+    assert r["status"] == 0 and math.isfinite(r["ll"])
+
+
+def test_dead_parameters_under_runup_seeding(problem, oracle):
+    # quirk Q4: with run-up seeding the eight multipliers and runup_days do not change logL
+    base = problem.base_params()
+    ll0 = oracle.eval_one(base)["ll"]
+    x = base.copy()
+    for nm in ("E0_multiplier", "I0_multiplier", "R0_multiplier", "runup_days"):
+        i = problem.param_names.index(nm)
+        x[i] = 0.5 * (problem.lower_bound[i] + problem.upper_bound[i])
+    assert oracle.eval_one(x)["ll"] == ll0
+
+
+def test_simulate_batch_selectors(problem, oracle, pkg):
+    P = oracle.jitter_params(3, seed=4)
+    full, st = oracle.simulate_batch(P, pkg.TRAJ_FULL, 1)
+    obs, _ = oracle.simulate_batch(P, pkg.TRAJ_OBSERVED, 7)
+    n = problem.n_ages
+    assert full.shape == (3, problem.n_times, 11 * n) and obs.shape == (3, (problem.n_times + 6) // 7, 3 * n)
+    np.testing.assert_array_equal(obs[:, :, 0:n], full[:, ::7, 8 * n:9 * n])
+    np.testing.assert_array_equal(obs[:, :, n:2 * n], full[:, ::7, 9 * n:10 * n])
+    np.testing.assert_array_equal(obs[:, :, 2 * n:3 * n], full[:, ::7, 10 * n:11 * n])
+
+
+def test_sixteen_age_variant_is_consistent_with_four(problem, orc):
+    """Splitting every age class into 4 identical sub-classes leaves the aggregated
+    epidemic unchanged up to rounding, so the 16-class trajectory summed over sub-classes equals the
+    4-class one closely (the step controller sees 4x smaller components, so only ~1e-5 agreement)."""
+    p16 = problem.expand_ages(4)
+    r4 = orc.Oracle(problem).eval_one(problem.base_params(), want_traj=True)
+    r16 = orc.Oracle(p16).eval_one(p16.base_params(), want_traj=True)
+    assert r16["status"] == 0
+    t4 = r4["traj"].reshape(problem.n_times, 11, 4)
+    t16 = r16["traj"].reshape(problem.n_times, 11, 4, 4).sum(-1)
+    rel = np.abs(t16 - t4) / np.maximum(np.abs(t4), 1.0)
+    assert rel.max() < 1e-3

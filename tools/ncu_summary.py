@@ -1,0 +1,55 @@
+#!/usr/bin/env python
+"""Summarise an .ncu-rep (one kernel) into the handful of numbers DESIGN.md / profiles/ cite.
+
+    python tools/ncu_summary.py gpurun_out/prof.ncu-rep [launch_index] > profiles/rNN_<name>.txt
+"""
+import csv
+import subprocess
+import sys
+
+rep = sys.argv[1]
+which = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(raw.splitlines()))
+hdr, units, vals = rows[0], rows[1], rows[2 + which]
+m = {h: (v, u) for h, u, v in zip(hdr, units, vals)}
+
+
+def show(key, label=None):
+    if key in m:
+        v, u = m[key]
+        print(f"{label or key:70s} {v} {u}")
+
+
+print("kernel:", m.get("Kernel Name", ("?",))[0][:120])
+for k in ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+          "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
+          "sm__warps_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.per_cycle_active",
+          "sm__cycles_elapsed.max", "sm__cycles_active.avg",
+          "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
+          "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
+          "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+          "sm__inst_executed_pipe_adu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+          "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_cbu.avg.pct_of_peak_sustained_active",
+          "sm__inst_executed_pipe_uniform.avg.pct_of_peak_sustained_active",
+          "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.avg.per_cycle_active", "smsp__inst_executed.sum",
+          "smsp__issue_inst0.avg.pct_of_peak_sustained_active",
+          "smsp__thread_inst_executed_per_inst_executed.ratio", "smsp__thread_inst_executed_per_inst_executed.pct",
+          "smsp__warps_eligible.avg.per_cycle_active", "smsp__warps_active.avg.per_cycle_active",
+          "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
+          "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+          "sass__inst_executed_shared_loads", "sass__inst_executed_shared_stores", "sass__inst_executed_global_loads",
+          "smsp__sass_thread_inst_executed_op_dfma_pred_on.sum", "smsp__sass_thread_inst_executed_op_dadd_pred_on.sum",
+          "smsp__sass_thread_inst_executed_op_dmul_pred_on.sum", "smsp__sass_thread_inst_executed_ops_dadd_dmul_dfma_pred_on.sum",
+          "smsp__sass_inst_executed_op_shared_ld.sum", "smsp__inst_executed_op_shuffle.sum" ]:
+    show(k)
+print("\n-- warp issue-stall reasons (smsp__average_warp*_issue_stalled_*_per_issue_active / pcsamp) --")
+st = [(h, v) for h, (v, u) in m.items() if "issue_stalled" in h and h.endswith("per_warp_active.pct")]
+if not st:
+    st = [(h, v) for h, (v, u) in m.items() if "smsp__average_warps_issue_stalled" in h and "per_issue_active" in h]
+for h, v in sorted(st, key=lambda kv: -float(kv[1].replace(",", "") or 0))[:14]:
+    print(f"{h:90s} {v}")
+print("\n-- pc sampling totals --")
+ps = [(h, v) for h, (v, u) in m.items() if h.startswith("smsp__pcsamp_warps_issue_stalled") and not h.endswith("not_issued")]
+for h, v in sorted(ps, key=lambda kv: -float(kv[1].replace(",", "") or 0))[:14]:
+    print(f"{h:90s} {v}")
