@@ -95,7 +95,7 @@ sepaihrd_rc launch_t(sepaihrd_ctx* ctx, const sepaihrd::KParams& kp_in) {
     constexpr int SETS = THREADS / NA;
     kp.tiles = (kp.B + SETS - 1) / SETS;
     auto kern = sepaihrd_batch_kernel<NA, STRICT, MODE, THREADS, MINBLOCKS>;
-    const size_t smem = (size_t)kp.blob_bytes + sizeof(double) * SETS * (size_t)(kp.slot_stride + kp.seg_stride) + 16;
+    const size_t smem = (size_t)kp.blob_bytes + sizeof(double) * (SETS * (size_t)(kp.slot_stride + ((kp.seg_stride + 1) & ~1)) + 2 * THREADS) + 16;
     static bool attr_set[64] = {};   // per device
     if (!attr_set[ctx->device & 63]) {
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));

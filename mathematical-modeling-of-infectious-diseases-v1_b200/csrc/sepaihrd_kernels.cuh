@@ -146,11 +146,30 @@ struct LaneParams {
     double M[NA];            // row `age` of the contact matrix: M(age, j)
 };
 
+// Infectious-pressure all-gather inside a lane group through shared memory: one STS.64 per lane, one
+// __syncwarp, then NA/2 LDS.128 (v2 profile: the 2*NA serialized SHFLs cost as much issue time as ~40
+// instructions per RHS).  `slot` alternates between two buffers so that consecutive exchanges never
+// race (write-after-read) without a second barrier.
+template <int NA>
+__device__ __forceinline__ void gather_pressure(double* spi, int slot_base, int lane_in_block, double pressure,
+                                                double (&pall)[NA]) {
+    spi[slot_base + lane_in_block] = pressure;
+    __syncwarp();
+    const double2* rp = reinterpret_cast<const double2*>(spi + slot_base + (lane_in_block & ~(NA - 1)));
+#pragma unroll
+    for (int j = 0; j < NA / 2; ++j) {
+        const double2 v = rp[j];
+        pall[2 * j] = v.x;
+        pall[2 * j + 1] = v.y;
+    }
+}
+
 // AgeSEPAIHRDModel::computeDerivatives for one age class (this lane), inputs y = S E P A I H ICU.
-// PASSIVE=false skips dR dD dCumH dCumICU (stage 2: Dopri5 has c2 = dc2 = 0).
+// Outputs: dyn = d(S E P A I H ICU), pas = d(R D CumH CumICU).
+// PASSIVE=false skips pas (stage 2: Dopri5 has c2 = dc2 = 0).
 template <int NA, bool STRICT, bool PASSIVE>
-__device__ __forceinline__ void rhs(const LaneParams<NA>& q, unsigned gmask, double ba, const double (&y)[NDYN],
-                                    double (&d)[NCOMP]) {
+__device__ __forceinline__ void rhs(const LaneParams<NA>& q, double ba, double* spi, int slot_base, int lane_in_block,
+                                    const double (&y)[NDYN], double (&dyn)[NDYN], double (&pas)[NPAS]) {
     using O = Ops<STRICT>;
     const double S = y[0], E = y[1], P = y[2], A = y[3], I = y[4], H = y[5], U = y[6];
     double pressure;
@@ -160,18 +179,24 @@ __device__ __forceinline__ void rhs(const LaneParams<NA>& q, unsigned gmask, dou
     } else {
         pressure = fma(q.theta, I, P + A) * q.hN;
     }
+    double pall[NA];
+    gather_pressure<NA>(spi, slot_base, lane_in_block, pressure, pall);
     double lam = 0.0;                                                        // :162-174 (j outer, in order)
 #pragma unroll
-    for (int j = 0; j < NA; ++j) {
-        const double pj = __shfl_sync(gmask, pressure, j, NA);
-        lam = O::mad(q.M[j], pj, lam);
-    }
+    for (int j = 0; j < NA; ++j) lam = O::mad(q.M[j], pall[j], lam);
     lam = O::mul(lam, ba);                                                   // :181-183, ba = (beta*kappa)*a_i
-    lam = (0.0 < lam) ? lam : 0.0;                                           // std::max(0.0, lambda) :196
+    if (STRICT) {
+        lam = (0.0 < lam) ? lam : 0.0;                                       // std::max(0.0, lambda) :196
+    } else {
+        // same selection with integer ops (off the FP64 pipe): negative, -0 and NaN (sign or quiet bit patterns
+        // above +inf) become +0; +inf and positive finite values pass.
+        const unsigned hi = (unsigned)__double2hiint(lam);
+        if (hi > 0x7ff00000u) lam = 0.0;
+    }
     const double flow_SE = O::mul(lam, S);
     const double flow_IH = O::mul(q.h, I);
     const double flow_H_ICU = O::mul(q.icu, H);
-    d[0] = -flow_SE;
+    dyn[0] = -flow_SE;
     if (STRICT) {
         const double flow_EP = O::mul(q.sigma, E);
         const double flow_P_out = O::mul(q.gamma_p, P);
@@ -184,69 +209,172 @@ __device__ __forceinline__ void rhs(const LaneParams<NA>& q, unsigned gmask, dou
         const double H_out = O::add(O::add(gH, dHH), flow_H_ICU);
         const double U_out = O::mul(O::add(q.gamma_ICU, q.dICU), U);
         const double gAA = O::mul(q.gamma_A, A);
-        d[1] = O::sub(flow_SE, flow_EP);
-        d[2] = O::sub(flow_EP, flow_P_out);
-        d[3] = O::sub(flow_PA, gAA);
-        d[4] = O::sub(flow_PI, I_out);
-        d[5] = O::sub(flow_IH, H_out);
-        d[6] = O::sub(flow_H_ICU, U_out);
+        dyn[1] = O::sub(flow_SE, flow_EP);
+        dyn[2] = O::sub(flow_EP, flow_P_out);
+        dyn[3] = O::sub(flow_PA, gAA);
+        dyn[4] = O::sub(flow_PI, I_out);
+        dyn[5] = O::sub(flow_IH, H_out);
+        dyn[6] = O::sub(flow_H_ICU, U_out);
         if (PASSIVE) {
             const double gUU = O::mul(q.gamma_ICU, U), dUU = O::mul(q.dICU, U);
-            d[7] = O::add(O::add(O::add(gAA, flow_IR), gH), gUU);            // :222
-            d[8] = O::add(O::add(dHH, dUU), flow_IDc);                      // :223
-            d[9] = flow_IH;
-            d[10] = flow_H_ICU;
+            pas[0] = O::add(O::add(O::add(gAA, flow_IR), gH), gUU);          // :222
+            pas[1] = O::add(O::add(dHH, dUU), flow_IDc);                    // :223
+            pas[2] = flow_IH;
+            pas[3] = flow_H_ICU;
         }
     } else {
         const double flow_P_out = q.gamma_p * P;
         const double flow_PA = q.p * flow_P_out;
-        d[1] = fma(-q.sigma, E, flow_SE);
-        d[2] = fma(q.sigma, E, -flow_P_out);
-        d[3] = fma(-q.gamma_A, A, flow_PA);
-        d[4] = fma(-q.kI, I, flow_P_out - flow_PA);
-        d[5] = fma(-q.kH, H, flow_IH);
-        d[6] = fma(-q.kU, U, flow_H_ICU);
+        dyn[1] = fma(-q.sigma, E, flow_SE);
+        dyn[2] = fma(q.sigma, E, -flow_P_out);
+        dyn[3] = fma(-q.gamma_A, A, flow_PA);
+        dyn[4] = fma(-q.kI, I, flow_P_out - flow_PA);
+        dyn[5] = fma(-q.kH, H, flow_IH);
+        dyn[6] = fma(-q.kU, U, flow_H_ICU);
         if (PASSIVE) {
-            d[7] = fma(q.gamma_ICU, U, fma(q.gamma_H, H, fma(q.gamma_I, I, q.gamma_A * A)));
-            d[8] = fma(q.dcomm, I, fma(q.dICU, U, q.dH * H));
-            d[9] = flow_IH;
-            d[10] = flow_H_ICU;
+            pas[0] = fma(q.gamma_ICU, U, fma(q.gamma_H, H, fma(q.gamma_I, I, q.gamma_A * A)));
+            pas[1] = fma(q.dcomm, I, fma(q.dICU, U, q.dH * H));
+            pas[2] = flow_IH;
+            pas[3] = flow_H_ICU;
         }
     }
 }
 
 // Dopri5 tableau as Boost writes it (runge_kutta_dopri5.hpp): integer ratios evaluated in double.
-struct Tab {
-    static constexpr double a2 = 1.0 / 5.0, a3 = 3.0 / 10.0, a4 = 4.0 / 5.0, a5 = 8.0 / 9.0;
-    static constexpr double b21 = 1.0 / 5.0;
-    static constexpr double b31 = 3.0 / 40.0, b32 = 9.0 / 40.0;
-    static constexpr double b41 = 44.0 / 45.0, b42 = -56.0 / 15.0, b43 = 32.0 / 9.0;
-    static constexpr double b51 = 19372.0 / 6561.0, b52 = -25360.0 / 2187.0, b53 = 64448.0 / 6561.0, b54 = -212.0 / 729.0;
-    static constexpr double b61 = 9017.0 / 3168.0, b62 = -355.0 / 33.0, b63 = 46732.0 / 5247.0, b64 = 49.0 / 176.0,
-                            b65 = -5103.0 / 18656.0;
-    static constexpr double c1 = 35.0 / 384.0, c3 = 500.0 / 1113.0, c4 = 125.0 / 192.0, c5 = -2187.0 / 6784.0,
-                            c6 = 11.0 / 84.0;
-    static constexpr double dc1 = c1 - 5179.0 / 57600.0, dc3 = c3 - 7571.0 / 16695.0, dc4 = c4 - 393.0 / 640.0;
-    static constexpr double dc5 = c5 - -92097.0 / 339200.0, dc6 = c6 - 187.0 / 2100.0, dc7 = -1.0 / 40.0;
+// Kept in __constant__ memory so that every use is a c[bank][offset] operand of the DMUL/DFMA itself
+// (as 64-bit immediates each use costs two UMOVs; v1 profile: 10% of all issued instructions).
+enum TabIdx {
+    T_A2, T_A3, T_A4, T_A5,
+    T_B21, T_B31, T_B32, T_B41, T_B42, T_B43, T_B51, T_B52, T_B53, T_B54, T_B61, T_B62, T_B63, T_B64, T_B65,
+    T_C1, T_C3, T_C4, T_C5, T_C6, T_DC1, T_DC3, T_DC4, T_DC5, T_DC6, T_DC7, T_COUNT
 };
+namespace tabv {
+constexpr double c1 = 35.0 / 384.0, c3 = 500.0 / 1113.0, c4 = 125.0 / 192.0, c5 = -2187.0 / 6784.0, c6 = 11.0 / 84.0;
+}
+__constant__ double c_tab[T_COUNT] = {
+    1.0 / 5.0, 3.0 / 10.0, 4.0 / 5.0, 8.0 / 9.0,
+    1.0 / 5.0, 3.0 / 40.0, 9.0 / 40.0, 44.0 / 45.0, -56.0 / 15.0, 32.0 / 9.0,
+    19372.0 / 6561.0, -25360.0 / 2187.0, 64448.0 / 6561.0, -212.0 / 729.0,
+    9017.0 / 3168.0, -355.0 / 33.0, 46732.0 / 5247.0, 49.0 / 176.0, -5103.0 / 18656.0,
+    tabv::c1, tabv::c3, tabv::c4, tabv::c5, tabv::c6,
+    tabv::c1 - 5179.0 / 57600.0, tabv::c3 - 7571.0 / 16695.0, tabv::c4 - 393.0 / 640.0,
+    tabv::c5 - -92097.0 / 339200.0, tabv::c6 - 187.0 / 2100.0, -1.0 / 40.0};
+
+constexpr unsigned FULL = 0xffffffffu;
 
 template <int NA>
-__device__ __forceinline__ double group_max(unsigned gmask, double v) {
+__device__ __forceinline__ double group_max(double v) {
 #pragma unroll
     for (int off = NA / 2; off >= 1; off >>= 1) {
-        const double o = __shfl_xor_sync(gmask, v, off, NA);
+        const double o = __shfl_xor_sync(FULL, v, off, NA);
         v = (v < o) ? o : v;
     }
     return v;
 }
 template <int NA>
-__device__ __forceinline__ double group_sum(unsigned gmask, double v) {
+__device__ __forceinline__ double group_sum(double v) {
 #pragma unroll
-    for (int off = NA / 2; off >= 1; off >>= 1) v += __shfl_xor_sync(gmask, v, off, NA);
+    for (int off = NA / 2; off >= 1; off >>= 1) v += __shfl_xor_sync(FULL, v, off, NA);
     return v;
 }
 
+// One Dopri5 step attempt (runge_kutta_dopri5::do_step_impl with error estimate) for this lane's age class.
+// MIXED=false: every stage of the step lies in one schedule segment (always true when the breakpoints sit
+// on output-grid points, e.g. the Spain-2020 configuration) and uses `ba_step`.  MIXED=true: the step
+// straddles a breakpoint; each stage looks its segment up from its own time.
+struct StepSched {
+    double ba_step;       // (beta*kappa)*a_i of the segment of the first stage time
+    int s_lo;             // segment of t + dt/5
+    const double* bp;     // merged breakpoints (shared memory)
+    const double* beff;   // this set's beta*kappa per segment (shared memory)
+    int nseg;
+    double a;
+};
+
+template <int NA, bool STRICT, bool MIXED>
+__device__ __forceinline__ void dopri5_attempt(const LaneParams<NA>& q, const StepSched& sc, double* spi, int& pi_slot,
+                                               int pi_stride, int lane_in_block, double t, double cur, double t_end,
+                                               const double (&x)[NCOMP], const double (&k1)[NCOMP], double (&xn)[NDYN],
+                                               double (&k7d)[NDYN], double (&k7p)[NPAS], double (&accN)[NPAS],
+                                               double (&xe)[NCOMP]) {
+    using O = Ops<STRICT>;
+    auto ba_at = [&](int tab_a) -> double {
+        if (!MIXED) return sc.ba_step;
+        const double ts = (tab_a < 0) ? t_end : O::add(t, O::mul(cur, c_tab[tab_a]));
+        int s = sc.s_lo;
+        while (s < sc.nseg && ts > sc.bp[s]) ++s;
+        return O::mul(sc.beff[s], sc.a);
+    };
+    auto next_slot = [&]() -> int { pi_slot ^= pi_stride; return pi_slot; };
+    double k2[NDYN], k3[NDYN], k4[NDYN], k5[NDYN], k6[NDYN];
+    double y[NDYN], kp_[NPAS], accE[NPAS];
+    // stage 2
+    { const double f1 = O::mul(cur, c_tab[T_B21]);
+#pragma unroll
+      for (int c = 0; c < NDYN; ++c) y[c] = O::mad(f1, k1[c], x[c]); }
+    rhs<NA, STRICT, false>(q, ba_at(T_A2), spi, next_slot(), lane_in_block, y, k2, kp_);
+    // stage 3
+    { const double f1 = O::mul(cur, c_tab[T_B31]), f2 = O::mul(cur, c_tab[T_B32]);
+#pragma unroll
+      for (int c = 0; c < NDYN; ++c) y[c] = O::mad(f2, k2[c], O::mad(f1, k1[c], x[c])); }
+    rhs<NA, STRICT, true>(q, ba_at(T_A3), spi, next_slot(), lane_in_block, y, k3, kp_);
+    { const double g1 = O::mul(cur, c_tab[T_C1]), g3 = O::mul(cur, c_tab[T_C3]);
+      const double e1 = O::mul(cur, c_tab[T_DC1]), e3 = O::mul(cur, c_tab[T_DC3]);
+#pragma unroll
+      for (int c = 0; c < NPAS; ++c) {
+          accN[c] = O::mad(g3, kp_[c], O::mad(g1, k1[NDYN + c], x[NDYN + c]));
+          accE[c] = O::mad(e3, kp_[c], O::mul(e1, k1[NDYN + c]));
+      } }
+    // stage 4
+    { const double f1 = O::mul(cur, c_tab[T_B41]), f2 = O::mul(cur, c_tab[T_B42]), f3 = O::mul(cur, c_tab[T_B43]);
+#pragma unroll
+      for (int c = 0; c < NDYN; ++c) y[c] = O::mad(f3, k3[c], O::mad(f2, k2[c], O::mad(f1, k1[c], x[c]))); }
+    rhs<NA, STRICT, true>(q, ba_at(T_A4), spi, next_slot(), lane_in_block, y, k4, kp_);
+    { const double g4 = O::mul(cur, c_tab[T_C4]), e4 = O::mul(cur, c_tab[T_DC4]);
+#pragma unroll
+      for (int c = 0; c < NPAS; ++c) { accN[c] = O::mad(g4, kp_[c], accN[c]); accE[c] = O::mad(e4, kp_[c], accE[c]); } }
+    // stage 5
+    { const double f1 = O::mul(cur, c_tab[T_B51]), f2 = O::mul(cur, c_tab[T_B52]), f3 = O::mul(cur, c_tab[T_B53]),
+                   f4 = O::mul(cur, c_tab[T_B54]);
+#pragma unroll
+      for (int c = 0; c < NDYN; ++c)
+          y[c] = O::mad(f4, k4[c], O::mad(f3, k3[c], O::mad(f2, k2[c], O::mad(f1, k1[c], x[c])))); }
+    rhs<NA, STRICT, true>(q, ba_at(T_A5), spi, next_slot(), lane_in_block, y, k5, kp_);
+    { const double g5 = O::mul(cur, c_tab[T_C5]), e5 = O::mul(cur, c_tab[T_DC5]);
+#pragma unroll
+      for (int c = 0; c < NPAS; ++c) { accN[c] = O::mad(g5, kp_[c], accN[c]); accE[c] = O::mad(e5, kp_[c], accE[c]); } }
+    // stage 6
+    { const double f1 = O::mul(cur, c_tab[T_B61]), f2 = O::mul(cur, c_tab[T_B62]), f3 = O::mul(cur, c_tab[T_B63]),
+                   f4 = O::mul(cur, c_tab[T_B64]), f5 = O::mul(cur, c_tab[T_B65]);
+#pragma unroll
+      for (int c = 0; c < NDYN; ++c)
+          y[c] = O::mad(f5, k5[c], O::mad(f4, k4[c], O::mad(f3, k3[c], O::mad(f2, k2[c], O::mad(f1, k1[c], x[c]))))); }
+    rhs<NA, STRICT, true>(q, ba_at(-1), spi, next_slot(), lane_in_block, y, k6, kp_);
+    { const double g6 = O::mul(cur, c_tab[T_C6]), e6 = O::mul(cur, c_tab[T_DC6]);
+#pragma unroll
+      for (int c = 0; c < NPAS; ++c) { accN[c] = O::mad(g6, kp_[c], accN[c]); accE[c] = O::mad(e6, kp_[c], accE[c]); } }
+    // solution (dynamic part) and the FSAL derivative
+    { const double g1 = O::mul(cur, c_tab[T_C1]), g3 = O::mul(cur, c_tab[T_C3]), g4 = O::mul(cur, c_tab[T_C4]),
+                   g5 = O::mul(cur, c_tab[T_C5]), g6 = O::mul(cur, c_tab[T_C6]);
+#pragma unroll
+      for (int c = 0; c < NDYN; ++c)
+          xn[c] = O::mad(g6, k6[c], O::mad(g5, k5[c], O::mad(g4, k4[c], O::mad(g3, k3[c], O::mad(g1, k1[c], x[c]))))); }
+    rhs<NA, STRICT, true>(q, ba_at(-1), spi, next_slot(), lane_in_block, xn, k7d, k7p);
+    // error estimate
+    { const double e1 = O::mul(cur, c_tab[T_DC1]), e3 = O::mul(cur, c_tab[T_DC3]), e4 = O::mul(cur, c_tab[T_DC4]),
+                   e5 = O::mul(cur, c_tab[T_DC5]), e6 = O::mul(cur, c_tab[T_DC6]), e7 = O::mul(cur, c_tab[T_DC7]);
+#pragma unroll
+      for (int c = 0; c < NDYN; ++c)
+          xe[c] = O::mad(e7, k7d[c], O::mad(e6, k6[c], O::mad(e5, k5[c], O::mad(e4, k4[c], O::mad(e3, k3[c], O::mul(e1, k1[c]))))));
+#pragma unroll
+      for (int c = 0; c < NPAS; ++c) xe[NDYN + c] = O::mad(e7, k7p[c], accE[c]); }
+}
+
 // ------------------------------------------------------------------------------------------------
+// The kernel is WARP-SYNCHRONOUS: all 32 lanes of a warp execute every step attempt together (lane
+// groups that have already reached the next output time run the attempt with a zero-length step and
+// discard it), so every shuffle is a plain full-mask SHFL.  This is the "regroup at output-day
+// boundaries" policy: a warp spends max-over-its-groups attempts per output interval.
 template <int NA, bool STRICT, int MODE, int THREADS, int MINBLOCKS>
 __global__ void __launch_bounds__(THREADS, MINBLOCKS) sepaihrd_batch_kernel(const KParams kp) {
     using O = Ops<STRICT>;
@@ -256,7 +384,8 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) sepaihrd_batch_kernel(cons
     const int blob_doubles = kp.blob_bytes >> 3;
     double* sslots = sblob + blob_doubles;
     double* sbeff = sslots + SETS * kp.slot_stride;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(sbeff + SETS * kp.seg_stride);
+    double* spi = sbeff + SETS * ((kp.seg_stride + 1) & ~1);            // 2 x THREADS doubles, 16-byte aligned
+    uint64_t* bar = reinterpret_cast<uint64_t*>(spi + 2 * THREADS);
 
     // ---- stage the constants blob once per block with one TMA bulk copy -----------------------------
     if (threadIdx.x == 0) {
@@ -275,13 +404,16 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) sepaihrd_batch_kernel(cons
     const int* s_pslot = reinterpret_cast<const int*>(sblob + kp.o_pslot);
     const int* s_segb = reinterpret_cast<const int*>(sblob + kp.o_segb);
     const int* s_segk = reinterpret_cast<const int*>(sblob + kp.o_segk);
+    int pi_slot = 0;   // toggles between 0 and THREADS before every pressure exchange
 
-    const int lane = threadIdx.x & 31;
     const int age = threadIdx.x % NA;
     const int grp = threadIdx.x / NA;
-    const unsigned gmask = (NA >= 32) ? 0xffffffffu : (((1u << NA) - 1u) << (lane - age));
-    const int n = NA;
+    constexpr int n = NA;
     const int nseg = kp.nseg;
+    const int K = kp.K;
+    const double hmax = kp.hmax;
+    const double f_abs = kp.abs_tol, f_rel = kp.rel_tol;
+    const double INF = __longlong_as_double(0x7ff0000000000000LL);
 
     double* my_slots = sslots + grp * kp.slot_stride;
     double* my_beff = sbeff + grp * kp.seg_stride;
@@ -291,13 +423,14 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) sepaihrd_batch_kernel(cons
     const int sl_mult0 = sl_age0 + 8 * n, sl_seed = sl_mult0 + 8, sl_runup = sl_mult0 + 9, sl_beta = sl_mult0 + 10;
 
     for (long long tile = blockIdx.x; tile < kp.tiles; tile += gridDim.x) {
-        const long long b = tile * SETS + grp;
-        if (b >= kp.B) continue;   // whole group idle (all group-scoped sync below uses gmask)
+        const long long b_raw = tile * SETS + grp;
+        const bool have = b_raw < kp.B;
+        const long long b = have ? b_raw : (kp.B - 1);   // idle groups shadow the last set; nothing is written for them
 
         // ---- updateModelParameters: base slots, then constrained calibrated values -------------------
-        __syncwarp(gmask);
+        __syncwarp();
         for (int s = age; s < kp.nslots; s += NA) my_slots[s] = sblob[kp.o_base + s];
-        __syncwarp(gmask);
+        __syncwarp();
         bool kappa_touched = false;
         {
             const double* prow = kp.params + b * kp.ld;
@@ -310,20 +443,23 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) sepaihrd_batch_kernel(cons
                 }
             }
         }
-        __syncwarp(gmask);
+        __syncwarp();
         unsigned status = 0;
-        kappa_touched = __any_sync(gmask, kappa_touched);
-        if (kappa_touched) {   // setCalibratableValues throws on a negative kappa (NPI.cpp:238-242)
+        {   // setCalibratableValues throws on a negative kappa (NPI.cpp:238-242) once any kappa is calibrated
             bool neg = false;
             for (int k = 1 + age; k < kp.nk; k += NA) neg |= (my_slots[sl_kappa0 + k] < 0.0);
-            if (__any_sync(gmask, neg)) status |= SEPAIHRD_ST_INVALID_PARAM;
+            const unsigned gsh = (threadIdx.x & 31) - age;
+            const unsigned gm = (NA >= 32) ? FULL : (((1u << NA) - 1u) << gsh);
+            const bool any_touch = (__ballot_sync(FULL, kappa_touched) & gm) != 0;
+            const bool any_neg = (__ballot_sync(FULL, neg) & gm) != 0;
+            if (any_touch && any_neg) status |= SEPAIHRD_ST_INVALID_PARAM;
         }
         // beta_eff per merged schedule segment: beta(t) * kappa(t)   (AgeSEPAIHRDModel.cpp:176-178)
         for (int s = age; s <= nseg; s += NA) {
             const double bv = (kp.nb > 0) ? my_slots[sl_beta0 + s_segb[s]] : my_slots[sl_beta];
             my_beff[s] = O::mul(bv, my_slots[sl_kappa0 + s_segk[s]]);
         }
-        __syncwarp(gmask);
+        __syncwarp();
 
         LaneParams<NA> q;
         q.theta = my_slots[sl_scal0 + 0]; q.sigma = my_slots[sl_scal0 + 1]; q.gamma_p = my_slots[sl_scal0 + 2];
@@ -357,9 +493,14 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) sepaihrd_batch_kernel(cons
             double sum = 0;
 #pragma unroll
             for (int j = 1; j < 9; ++j) sum = O::add(sum, x[j]);
-            if (__any_sync(gmask, sum > popN) && status == 0) status |= SEPAIHRD_ST_S_OVERFLOW;
+            const unsigned gsh = (threadIdx.x & 31) - age;
+            const unsigned gm = (NA >= 32) ? FULL : (((1u << NA) - 1u) << gsh);
+            const bool over = (__ballot_sync(FULL, sum > popN) & gm) != 0;
+            if (over && status == 0) status |= SEPAIHRD_ST_S_OVERFLOW;
             x[0] = O::sub(popN, sum);
         }
+        const unsigned gshift = (threadIdx.x & 31) - age;
+        const unsigned gmask = (NA >= 32) ? FULL : (((1u << NA) - 1u) << gshift);
 
         double ll_acc_h = 0.0, ll_acc_i = 0.0, ll_acc_d = 0.0;   // STRICT: per stream; FAST: ll_acc_h only
         int n_acc = 0, n_rej = 0;
@@ -370,194 +511,150 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) sepaihrd_batch_kernel(cons
             traj_out = kp.out_traj + (size_t)b * kp.traj_rows * W;
         }
 
-        if (status == 0) {
-            // ---- integrate_times: observer at every grid point, adaptive steps in between -----------------
-            double dt = kp.dt_hint;
-            double prev_h = x[9], prev_i = x[10], prev_d = x[8];   // row 0 is differenced against the initial state
-            int seg = 0;          // number of merged breakpoints strictly below the current time
-            int seg_ba = -1;      // segment for which `ba` is current
-            double ba = 0.0;
-            bool have_k1 = false;
-            const double f_abs = kp.abs_tol, f_rel = kp.rel_tol;
+        bool alive = (status == 0);
+        // ---- integrate_times: observer at every grid point, adaptive steps in between ---------------------
+        double dt = kp.dt_hint;
+        double prev_h = x[9], prev_i = x[10], prev_d = x[8];   // row 0 is differenced against the initial state
+        // schedule bookkeeping: seg = number of merged breakpoints strictly below t ("t <= end_k" picks k, so a
+        // step that STARTS on a breakpoint still has its FSAL k1 in the old segment: quirk Q2)
+        double t = s_times[0];
+        int seg = 0;
+        while (seg < nseg && t > s_bp[seg]) ++seg;
+        double bp_next = (seg < nseg) ? s_bp[seg] : INF;
+        double ba = O::mul(my_beff[seg], q.a);
+        {   // controlled stepper initialise(): dxdt = f(x, t0)
+            double y0[NDYN], d0[NDYN], p0[NPAS];
+#pragma unroll
+            for (int c = 0; c < NDYN; ++c) y0[c] = x[c];
+            pi_slot ^= THREADS;
+            rhs<NA, STRICT, true>(q, ba, spi, pi_slot, threadIdx.x, y0, d0, p0);
+#pragma unroll
+            for (int c = 0; c < NDYN; ++c) k1[c] = d0[c];
+#pragma unroll
+            for (int c = 0; c < NPAS; ++c) k1[NDYN + c] = p0[c];
+        }
 
-            for (int idx = 0; idx < kp.K; ++idx) {
-                double t = s_times[idx];
-                // ---- observer -----------------------------------------------------------------------------
-                if (MODE == MODE_TRAJ) {
-                    if (idx % kp.traj_stride == 0) {
-                        double* row = traj_out + (size_t)(idx / kp.traj_stride) * W;
-                        if (kp.traj_what == SEPAIHRD_TRAJ_FULL) {
+        for (int idx = 0; idx < K; ++idx) {
+            t = s_times[idx];
+            // ---- observer -----------------------------------------------------------------------------
+            if (MODE == MODE_TRAJ) {
+                if (have && alive && (idx % kp.traj_stride == 0)) {
+                    double* row = traj_out + (size_t)(idx / kp.traj_stride) * W;
+                    if (kp.traj_what == SEPAIHRD_TRAJ_FULL) {
 #pragma unroll
-                            for (int c = 0; c < NCOMP; ++c) row[c * n + age] = x[c];
-                        } else {
-                            row[0 * n + age] = x[8]; row[1 * n + age] = x[9]; row[2 * n + age] = x[10];
-                        }
-                    }
-                } else {
-                    // daily incidence + Poisson terms (ObjectiveFunction.cpp:191-225, 241-279)
-                    const double inc_h = std_max(O::sub(x[9], prev_h), 0.0);
-                    const double inc_i = std_max(O::sub(x[10], prev_i), 0.0);
-                    const double inc_d = std_max(O::sub(x[8], prev_d), 0.0);
-                    prev_h = x[9]; prev_i = x[10]; prev_d = x[8];
-                    const int r = idx - kp.runup_offset;
-                    if (r >= 0) {
-                        const double eps = 1e-10;
-                        double term_h = 0.0, term_i = 0.0, term_d = 0.0;
-                        const double oh = s_obs_h[r * n + age], oi = s_obs_i[r * n + age], od = s_obs_d[r * n + age];
-                        const bool vh = (oh >= 0.0) && isfinite(oh), vi = (oi >= 0.0) && isfinite(oi),
-                                   vd = (od >= 0.0) && isfinite(od);
-                        if (vh) { double sim = inc_h; if (sim < 0.0) sim = 0.0; sim = O::add(sim, eps); term_h = O::sub(O::mul(oh, log(sim)), sim); }
-                        if (vi) { double sim = inc_i; if (sim < 0.0) sim = 0.0; sim = O::add(sim, eps); term_i = O::sub(O::mul(oi, log(sim)), sim); }
-                        if (vd) { double sim = inc_d; if (sim < 0.0) sim = 0.0; sim = O::add(sim, eps); term_d = O::sub(O::mul(od, log(sim)), sim); }
-                        if (STRICT) {
-                            // row_sum over ages in order, then log_likelihood += row_sum (per stream)
-                            double rs_h = 0.0, rs_i = 0.0, rs_d = 0.0;
-#pragma unroll
-                            for (int j = 0; j < NA; ++j) {
-                                const double th = __shfl_sync(gmask, term_h, j, NA), ti = __shfl_sync(gmask, term_i, j, NA),
-                                             td = __shfl_sync(gmask, term_d, j, NA);
-                                const double ohj = s_obs_h[r * n + j], oij = s_obs_i[r * n + j], odj = s_obs_d[r * n + j];
-                                if ((ohj >= 0.0) && isfinite(ohj)) rs_h = O::add(rs_h, th);
-                                if ((oij >= 0.0) && isfinite(oij)) rs_i = O::add(rs_i, ti);
-                                if ((odj >= 0.0) && isfinite(odj)) rs_d = O::add(rs_d, td);
-                            }
-                            ll_acc_h = O::add(ll_acc_h, rs_h); ll_acc_i = O::add(ll_acc_i, rs_i); ll_acc_d = O::add(ll_acc_d, rs_d);
-                        } else {
-                            ll_acc_h += (term_h + term_i) + term_d;
-                        }
+                        for (int c = 0; c < NCOMP; ++c) row[c * n + age] = x[c];
+                    } else {
+                        row[0 * n + age] = x[8]; row[1 * n + age] = x[9]; row[2 * n + age] = x[10];
                     }
                 }
-                if (idx + 1 == kp.K) break;
-                const double t_next = s_times[idx + 1];
-                int fail_steps = 0;
-
-                // ---- adaptive steps up to t_next --------------------------------------------------------------
-                while ((t_next - t) > DBL_EPSILON) {
-                    double cur = std_min(dt, t_next - t);   // min_abs(dt, t_next - t)
-                    // schedule segment bookkeeping: stage times increase within a step
-                    int s_stage = seg;
-                    auto ba_at = [&](double ts) -> double {
-                        while (s_stage < nseg && ts > s_bp[s_stage]) ++s_stage;
-                        if (s_stage != seg_ba) { ba = O::mul(my_beff[s_stage], q.a); seg_ba = s_stage; }
-                        return ba;
-                    };
-                    if (!have_k1) {   // controlled stepper initialise(): dxdt = f(x, t0)
-                        double y0[NDYN];
+            } else {
+                // daily incidence + Poisson terms (ObjectiveFunction.cpp:191-225, 241-279)
+                const double inc_h = std_max(O::sub(x[9], prev_h), 0.0);
+                const double inc_i = std_max(O::sub(x[10], prev_i), 0.0);
+                const double inc_d = std_max(O::sub(x[8], prev_d), 0.0);
+                prev_h = x[9]; prev_i = x[10]; prev_d = x[8];
+                const int r = idx - kp.runup_offset;
+                if (r >= 0) {
+                    const double eps = 1e-10;
+                    double term_h = 0.0, term_i = 0.0, term_d = 0.0;
+                    const double oh = s_obs_h[r * n + age], oi = s_obs_i[r * n + age], od = s_obs_d[r * n + age];
+                    const bool vh = (oh >= 0.0) && isfinite(oh), vi = (oi >= 0.0) && isfinite(oi),
+                               vd = (od >= 0.0) && isfinite(od);
+                    if (vh) { double sim = inc_h; if (sim < 0.0) sim = 0.0; sim = O::add(sim, eps); term_h = O::sub(O::mul(oh, log(sim)), sim); }
+                    if (vi) { double sim = inc_i; if (sim < 0.0) sim = 0.0; sim = O::add(sim, eps); term_i = O::sub(O::mul(oi, log(sim)), sim); }
+                    if (vd) { double sim = inc_d; if (sim < 0.0) sim = 0.0; sim = O::add(sim, eps); term_d = O::sub(O::mul(od, log(sim)), sim); }
+                    if (STRICT) {
+                        // row_sum over ages in order, then log_likelihood += row_sum (per stream)
+                        double rs_h = 0.0, rs_i = 0.0, rs_d = 0.0;
 #pragma unroll
-                        for (int c = 0; c < NDYN; ++c) y0[c] = x[c];
-                        rhs<NA, STRICT, true>(q, gmask, ba_at(t), y0, k1);
-                        have_k1 = true;
-                    }
-                    double k2[NDYN], k3[NDYN], k4[NDYN], k5[NDYN], k6[NDYN];
-                    double kk[NCOMP], y[NDYN];
-                    double accN[NPAS], accE[NPAS];   // running solution / error sums of the passive compartments
-                    // stage 2
-                    { const double f1 = O::mul(cur, Tab::b21);
-#pragma unroll
-                      for (int c = 0; c < NDYN; ++c) y[c] = O::mad(f1, k1[c], x[c]); }
-                    rhs<NA, STRICT, false>(q, gmask, ba_at(O::add(t, O::mul(cur, Tab::a2))), y, kk);
-#pragma unroll
-                    for (int c = 0; c < NDYN; ++c) k2[c] = kk[c];
-                    // stage 3
-                    { const double f1 = O::mul(cur, Tab::b31), f2 = O::mul(cur, Tab::b32);
-#pragma unroll
-                      for (int c = 0; c < NDYN; ++c) y[c] = O::mad(f2, k2[c], O::mad(f1, k1[c], x[c])); }
-                    rhs<NA, STRICT, true>(q, gmask, ba_at(O::add(t, O::mul(cur, Tab::a3))), y, kk);
-                    { const double g1 = O::mul(cur, Tab::c1), g3 = O::mul(cur, Tab::c3);
-                      const double e1 = O::mul(cur, Tab::dc1), e3 = O::mul(cur, Tab::dc3);
-#pragma unroll
-                      for (int c = 0; c < NDYN; ++c) k3[c] = kk[c];
-#pragma unroll
-                      for (int c = 0; c < NPAS; ++c) {
-                          accN[c] = O::mad(g3, kk[NDYN + c], O::mad(g1, k1[NDYN + c], x[NDYN + c]));
-                          accE[c] = O::mad(e3, kk[NDYN + c], O::mul(e1, k1[NDYN + c]));
-                      } }
-                    // stage 4
-                    { const double f1 = O::mul(cur, Tab::b41), f2 = O::mul(cur, Tab::b42), f3 = O::mul(cur, Tab::b43);
-#pragma unroll
-                      for (int c = 0; c < NDYN; ++c) y[c] = O::mad(f3, k3[c], O::mad(f2, k2[c], O::mad(f1, k1[c], x[c]))); }
-                    rhs<NA, STRICT, true>(q, gmask, ba_at(O::add(t, O::mul(cur, Tab::a4))), y, kk);
-                    { const double g4 = O::mul(cur, Tab::c4), e4 = O::mul(cur, Tab::dc4);
-#pragma unroll
-                      for (int c = 0; c < NDYN; ++c) k4[c] = kk[c];
-#pragma unroll
-                      for (int c = 0; c < NPAS; ++c) { accN[c] = O::mad(g4, kk[NDYN + c], accN[c]); accE[c] = O::mad(e4, kk[NDYN + c], accE[c]); } }
-                    // stage 5
-                    { const double f1 = O::mul(cur, Tab::b51), f2 = O::mul(cur, Tab::b52), f3 = O::mul(cur, Tab::b53),
-                                   f4 = O::mul(cur, Tab::b54);
-#pragma unroll
-                      for (int c = 0; c < NDYN; ++c)
-                          y[c] = O::mad(f4, k4[c], O::mad(f3, k3[c], O::mad(f2, k2[c], O::mad(f1, k1[c], x[c])))); }
-                    rhs<NA, STRICT, true>(q, gmask, ba_at(O::add(t, O::mul(cur, Tab::a5))), y, kk);
-                    { const double g5 = O::mul(cur, Tab::c5), e5 = O::mul(cur, Tab::dc5);
-#pragma unroll
-                      for (int c = 0; c < NDYN; ++c) k5[c] = kk[c];
-#pragma unroll
-                      for (int c = 0; c < NPAS; ++c) { accN[c] = O::mad(g5, kk[NDYN + c], accN[c]); accE[c] = O::mad(e5, kk[NDYN + c], accE[c]); } }
-                    // stage 6
-                    { const double f1 = O::mul(cur, Tab::b61), f2 = O::mul(cur, Tab::b62), f3 = O::mul(cur, Tab::b63),
-                                   f4 = O::mul(cur, Tab::b64), f5 = O::mul(cur, Tab::b65);
-#pragma unroll
-                      for (int c = 0; c < NDYN; ++c)
-                          y[c] = O::mad(f5, k5[c], O::mad(f4, k4[c], O::mad(f3, k3[c], O::mad(f2, k2[c], O::mad(f1, k1[c], x[c]))))); }
-                    const double t_end = O::add(t, cur);
-                    rhs<NA, STRICT, true>(q, gmask, ba_at(t_end), y, kk);
-                    { const double g6 = O::mul(cur, Tab::c6), e6 = O::mul(cur, Tab::dc6);
-#pragma unroll
-                      for (int c = 0; c < NDYN; ++c) k6[c] = kk[c];
-#pragma unroll
-                      for (int c = 0; c < NPAS; ++c) { accN[c] = O::mad(g6, kk[NDYN + c], accN[c]); accE[c] = O::mad(e6, kk[NDYN + c], accE[c]); } }
-                    // solution (dynamic part) and the FSAL derivative
-                    double xn[NDYN];
-                    { const double g1 = O::mul(cur, Tab::c1), g3 = O::mul(cur, Tab::c3), g4 = O::mul(cur, Tab::c4),
-                                   g5 = O::mul(cur, Tab::c5), g6 = O::mul(cur, Tab::c6);
-#pragma unroll
-                      for (int c = 0; c < NDYN; ++c)
-                          xn[c] = O::mad(g6, k6[c], O::mad(g5, k5[c], O::mad(g4, k4[c], O::mad(g3, k3[c], O::mad(g1, k1[c], x[c]))))); }
-                    rhs<NA, STRICT, true>(q, gmask, ba_at(t_end), xn, kk);   // kk = k7 = dxdt_new
-                    const int seg_end = s_stage;                            // segment of t + dt (for the next step)
-                    // error estimate and its scaled max-norm (default_error_checker)
-                    double err;
-                    {
-                        const double e1 = O::mul(cur, Tab::dc1), e3 = O::mul(cur, Tab::dc3), e4 = O::mul(cur, Tab::dc4),
-                                     e5 = O::mul(cur, Tab::dc5), e6 = O::mul(cur, Tab::dc6), e7 = O::mul(cur, Tab::dc7);
-                        double xe[NCOMP];
-#pragma unroll
-                        for (int c = 0; c < NDYN; ++c)
-                            xe[c] = O::mad(e7, kk[c], O::mad(e6, k6[c], O::mad(e5, k5[c], O::mad(e4, k4[c], O::mad(e3, k3[c], O::mul(e1, k1[c]))))));
-#pragma unroll
-                        for (int c = 0; c < NPAS; ++c) xe[NDYN + c] = O::mad(e7, kk[NDYN + c], accE[c]);
-                        if (STRICT) {
-                            double m = 0.0;
-#pragma unroll
-                            for (int c = 0; c < NCOMP; ++c) {
-                                const double den = O::add(f_abs, O::mul(f_rel, O::add(fabs(x[c]), O::mul(cur, fabs(k1[c])))));
-                                const double v = fabs(__ddiv_rn(fabs(xe[c]), den));
-                                m = (m < v) ? v : m;
-                            }
-                            err = group_max<NA>(gmask, m);
-                        } else {
-                            // arg-max by cross multiplication, then ONE exact division per lane
-                            double bn = 0.0, bd = 1.0;
-#pragma unroll
-                            for (int c = 0; c < NCOMP; ++c) {
-                                const double den = fma(f_rel, fma(cur, fabs(k1[c]), fabs(x[c])), f_abs);
-                                const double num = fabs(xe[c]);
-                                if (num * bd > bn * den) { bn = num; bd = den; }
-                            }
-                            err = group_max<NA>(gmask, bn / bd);
+                        for (int j = 0; j < NA; ++j) {
+                            const double th = __shfl_sync(FULL, term_h, j, NA), ti = __shfl_sync(FULL, term_i, j, NA),
+                                         td = __shfl_sync(FULL, term_d, j, NA);
+                            const double ohj = s_obs_h[r * n + j], oij = s_obs_i[r * n + j], odj = s_obs_d[r * n + j];
+                            if ((ohj >= 0.0) && isfinite(ohj)) rs_h = O::add(rs_h, th);
+                            if ((oij >= 0.0) && isfinite(oij)) rs_i = O::add(rs_i, ti);
+                            if ((odj >= 0.0) && isfinite(odj)) rs_d = O::add(rs_d, td);
                         }
+                        ll_acc_h = O::add(ll_acc_h, rs_h); ll_acc_i = O::add(ll_acc_i, rs_i); ll_acc_d = O::add(ll_acc_d, rs_d);
+                    } else {
+                        ll_acc_h += (term_h + term_i) + term_d;
                     }
-                    if (err > 1.0) {
-                        // reject: decrease_step (error_order 4): dt *= max(0.9 * err^(-1/3), 1/5)
+                }
+            }
+            if (idx + 1 == K) break;
+            const double t_next = s_times[idx + 1];
+            int fail_steps = 0;
+            bool need = alive && ((t_next - t) > DBL_EPSILON);   // less_with_sign(t, t_next, dt)
+
+            // ---- adaptive steps up to t_next: one attempt per iteration for the WHOLE warp ------------------
+            while (__any_sync(FULL, need)) {
+                double cur = std_min(dt, t_next - t);   // min_abs(dt, t_next - t)
+                const double t_end = O::add(t, cur);
+                // Stage times lie in (t, t_end].  If t_end <= bp_next they all use segment `seg`; otherwise look
+                // the segments up (steps that start on a breakpoint, or that straddle one on a general grid).
+                StepSched sc;
+                sc.ba_step = ba; sc.s_lo = seg; sc.bp = s_bp; sc.beff = my_beff; sc.nseg = nseg; sc.a = q.a;
+                int s_hi = seg;
+                bool mixed = false;
+                if (!(t_end <= bp_next)) {
+                    const double t2 = O::add(t, O::mul(cur, c_tab[T_A2]));
+                    int s_lo = seg;
+                    while (s_lo < nseg && t2 > s_bp[s_lo]) ++s_lo;
+                    s_hi = s_lo;
+                    while (s_hi < nseg && t_end > s_bp[s_hi]) ++s_hi;
+                    mixed = (s_lo != s_hi);
+                    sc.s_lo = s_lo;
+                    sc.ba_step = O::mul(my_beff[s_lo], q.a);
+                }
+                double xn[NDYN], k7d[NDYN], k7p[NPAS], accN[NPAS], xe[NCOMP];
+                if (__any_sync(FULL, mixed))
+                    dopri5_attempt<NA, STRICT, true>(q, sc, spi, pi_slot, THREADS, threadIdx.x, t, cur, t_end, x, k1, xn, k7d, k7p, accN, xe);
+                else
+                    dopri5_attempt<NA, STRICT, false>(q, sc, spi, pi_slot, THREADS, threadIdx.x, t, cur, t_end, x, k1, xn, k7d, k7p, accN, xe);
+                double err = 0.0;
+                bool reject;
+                if (STRICT) {
+                    double m = 0.0;
+#pragma unroll
+                    for (int c = 0; c < NCOMP; ++c) {
+                        const double den = O::add(f_abs, O::mul(f_rel, O::add(fabs(x[c]), O::mul(cur, fabs(k1[c])))));
+                        const double v = fabs(__ddiv_rn(fabs(xe[c]), den));
+                        m = (m < v) ? v : m;
+                    }
+                    err = group_max<NA>(m);
+                    reject = err > 1.0;
+                } else {
+                    // fl(num/den) > 1  <=>  num > den, so the accept/reject decision needs no division; the VALUE of
+                    // the error norm is only needed to shrink a rejected step or to grow a step that is below hmax.
+                    double den[NCOMP];
+                    bool big = false;
+#pragma unroll
+                    for (int c = 0; c < NCOMP; ++c) {
+                        den[c] = fma(f_rel, fma(cur, fabs(k1[c]), fabs(x[c])), f_abs);
+                        big |= fabs(xe[c]) > den[c];
+                    }
+                    reject = (__ballot_sync(FULL, big) & gmask) != 0;
+                    if (__any_sync(FULL, need && (reject || dt < hmax))) {
+                        double bn = 0.0, bd = 1.0;   // arg-max by cross multiplication, then ONE exact division
+#pragma unroll
+                        for (int c = 0; c < NCOMP; ++c) {
+                            const double num = fabs(xe[c]);
+                            if (num * bd > bn * den[c]) { bn = num; bd = den[c]; }
+                        }
+                        err = group_max<NA>(bn / bd);
+                    }
+                }
+                if (need) {
+                    if (reject) {
+                        // decrease_step (error_order 4): dt *= max(0.9 * err^(-1/3), 1/5)
                         cur = O::mul(cur, std_max(O::mul(9.0 / 10.0, pow(err, -1.0 / 3.0)), 1.0 / 5.0));
                         ++n_rej;
                         dt = cur;
-                        if (fail_steps++ >= 500) { status |= SEPAIHRD_ST_STEP_FAILURE; break; }
+                        if (fail_steps++ >= 500) { status |= SEPAIHRD_ST_STEP_FAILURE; alive = false; }
                     } else {
                         // accept: t += dt; increase_step (stepper_order 5) when err < 0.5
                         t = t_end;
-                        if (STRICT || dt < kp.hmax) {
+                        if (STRICT || dt < hmax) {
                             if (err < 0.5) {
                                 const double e2 = std_max(3.2e-4 /* pow(5,-5) */, err);
                                 cur = O::mul(cur, O::mul(9.0 / 10.0, pow(e2, -1.0 / 5.0)));
@@ -566,36 +663,41 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) sepaihrd_batch_kernel(cons
                         }
                         ++n_acc;
                         fail_steps = 0;
-                        seg = seg_end;
+                        if (s_hi != seg) {
+                            seg = s_hi;
+                            bp_next = (seg < nseg) ? s_bp[seg] : INF;
+                            ba = O::mul(my_beff[seg], q.a);
+                        }
 #pragma unroll
-                        for (int c = 0; c < NDYN; ++c) { x[c] = xn[c]; k1[c] = kk[c]; }
+                        for (int c = 0; c < NDYN; ++c) { x[c] = xn[c]; k1[c] = k7d[c]; }
 #pragma unroll
-                        for (int c = 0; c < NPAS; ++c) { x[NDYN + c] = accN[c]; k1[NDYN + c] = kk[NDYN + c]; }
+                        for (int c = 0; c < NPAS; ++c) { x[NDYN + c] = accN[c]; k1[NDYN + c] = k7p[c]; }
                     }
                 }
-                if (status & SEPAIHRD_ST_STEP_FAILURE) break;
+                need = alive && ((t_next - t) > DBL_EPSILON);
             }
+            if (!__any_sync(FULL, alive)) break;
         }
 
         // ---- epilogue -------------------------------------------------------------------------------------
         if (MODE == MODE_LL) {
             double total;
             if (STRICT) total = O::add(O::add(ll_acc_h, ll_acc_i), ll_acc_d);   // ll_hosp + ll_icu + ll_deaths
-            else total = group_sum<NA>(gmask, ll_acc_h);
+            else total = group_sum<NA>(ll_acc_h);
             if (status != 0) total = -DBL_MAX;
             else if (isnan(total) || isinf(total)) { total = -DBL_MAX; status |= SEPAIHRD_ST_NONFINITE; }
-            if (age == 0) {
+            if (have && age == 0) {
                 kp.out_ll[b] = total;
                 if (kp.out_status) kp.out_status[b] = status;
                 if (kp.out_steps) { kp.out_steps[2 * b] = n_acc; kp.out_steps[2 * b + 1] = n_rej; }
             }
         } else {
-            if (status != 0) {   // failed sets: NaN-fill every row
+            if (have && status != 0) {   // failed sets: NaN-fill every row
                 const double qnan = __longlong_as_double(0x7ff8000000000000LL);
                 for (int r = 0; r < kp.traj_rows; ++r)
                     for (int w = age; w < W; w += NA) traj_out[(size_t)r * W + w] = qnan;
             }
-            if (age == 0) {
+            if (have && age == 0) {
                 if (kp.out_status) kp.out_status[b] = status;
                 if (kp.out_steps) { kp.out_steps[2 * b] = n_acc; kp.out_steps[2 * b + 1] = n_rej; }
             }
