@@ -314,6 +314,8 @@ sepaihrd_rc sepaihrd_create(const sepaihrd_problem* pb, int32_t device, sepaihrd
     kp.slot_stride = L.count() | 1;
     kp.seg_stride = (nseg + 1) | 1;
     kp.abs_tol = pb->abs_tol; kp.rel_tol = pb->rel_tol; kp.dt_hint = pb->dt_hint; kp.hmax = ctx->hmax;
+    kp.inv_rel = (pb->rel_tol > 0.0) ? 1.0 / pb->rel_tol : 0.0;
+    kp.abs_over_rel = (pb->rel_tol > 0.0) ? pb->abs_tol / pb->rel_tol : 0.0;
 
     cudaDeviceProp prop;
     cudaError_t e = cudaGetDeviceProperties(&prop, device);
@@ -328,7 +330,7 @@ sepaihrd_rc sepaihrd_create(const sepaihrd_problem* pb, int32_t device, sepaihrd
     ctx->num_sms = prop.multiProcessorCount;
     ctx->stream = ctx->own_stream;
     kp.blob = ctx->d_blob;
-    if (pb->abs_tol <= 0.0) ctx->math_mode = SEPAIHRD_MATH_STRICT;   // FAST error norm needs a positive denominator
+    if (pb->abs_tol <= 0.0 || pb->rel_tol <= 0.0) ctx->math_mode = SEPAIHRD_MATH_STRICT;   // FAST error norm works in units of rel_tol, positive denominator
     *out_ctx = ctx;
     return SEPAIHRD_OK;
 }
@@ -353,7 +355,7 @@ sepaihrd_rc sepaihrd_set_constraint_mode(sepaihrd_ctx* ctx, int32_t mode) {
 
 sepaihrd_rc sepaihrd_set_math_mode(sepaihrd_ctx* ctx, int32_t mode) {
     if (!ctx || (mode != SEPAIHRD_MATH_FAST && mode != SEPAIHRD_MATH_STRICT)) return fail(SEPAIHRD_ERR_INVALID_ARGUMENT, "bad math mode");
-    if (mode == SEPAIHRD_MATH_FAST && ctx->abs_tol <= 0.0) return fail(SEPAIHRD_ERR_UNSUPPORTED, "FAST math needs abs_tol > 0");
+    if (mode == SEPAIHRD_MATH_FAST && (ctx->abs_tol <= 0.0 || ctx->rel_tol <= 0.0)) return fail(SEPAIHRD_ERR_UNSUPPORTED, "FAST math needs abs_tol > 0 and rel_tol > 0");
     ctx->math_mode = mode;
     return SEPAIHRD_OK;
 }

@@ -55,6 +55,8 @@ struct KParams {
     int constraint_mode;       // 0 clamp, 1 reflect
     double abs_tol, rel_tol, dt_hint;
     double hmax;               // longest output interval: growing dt beyond it cannot change the result
+    double inv_rel;            // 1 / rel_tol          (FAST error norm is evaluated in units of rel_tol)
+    double abs_over_rel;       // abs_tol / rel_tol
     // I/O
     const double* params;      // [B][ld]
     long long B, ld;
@@ -135,6 +137,32 @@ __device__ __forceinline__ double constrain(double v, double lo, double hi, int 
         return (mode == 0) ? std_min(std_max(v, lo), hi) : reflect_bound(v, lo, hi);
     }
     return (mode == 0) ? std_max(0.0, v) : fabs(v);
+}
+
+// ---- step-size controller powers (FAST) ---------------------------------------------------------------
+// x^(-1/5) and x^(-1/3) by an FP32 MUFU seed (rel. error ~1e-6) and two Newton steps in FP64
+// (error constant 3 resp. 2: 1e-6 -> ~3e-12 -> rounding level, a few ulp).  The v3 profile showed the
+// two inlined CUDA pow() calls at ~260 instructions per step attempt.
+__device__ __forceinline__ double pow_m1_5(double x) {
+    double y = (double)__powf((float)x, -0.2f);
+    const double xs = x * 0.2;
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+        const double y2 = y * y;
+        const double y5 = y2 * y2 * y;
+        y = y * fma(-xs, y5, 1.2);            // y (6 - x y^5) / 5
+    }
+    return y;
+}
+__device__ __forceinline__ double pow_m1_3(double x) {
+    double y = (double)__powf((float)x, -0.33333334f);
+    const double xs = x * (1.0 / 3.0);
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+        const double y3 = y * y * y;
+        y = y * fma(-xs, y3, 4.0 / 3.0);      // y (4 - x y^3) / 3
+    }
+    return y;
 }
 
 // ---- per-lane model parameters (registers) ----------------------------------------------------------
@@ -296,7 +324,7 @@ __device__ __forceinline__ void dopri5_attempt(const LaneParams<NA>& q, const St
                                                int pi_stride, int lane_in_block, double t, double cur, double t_end,
                                                const double (&x)[NCOMP], const double (&k1)[NCOMP], double (&xn)[NDYN],
                                                double (&k7d)[NDYN], double (&k7p)[NPAS], double (&accN)[NPAS],
-                                               double (&xe)[NCOMP]) {
+                                               double (&xe)[NCOMP], double ecur) {
     using O = Ops<STRICT>;
     auto ba_at = [&](int tab_a) -> double {
         if (!MIXED) return sc.ba_step;
@@ -319,7 +347,7 @@ __device__ __forceinline__ void dopri5_attempt(const LaneParams<NA>& q, const St
       for (int c = 0; c < NDYN; ++c) y[c] = O::mad(f2, k2[c], O::mad(f1, k1[c], x[c])); }
     rhs<NA, STRICT, true>(q, ba_at(T_A3), spi, next_slot(), lane_in_block, y, k3, kp_);
     { const double g1 = O::mul(cur, c_tab[T_C1]), g3 = O::mul(cur, c_tab[T_C3]);
-      const double e1 = O::mul(cur, c_tab[T_DC1]), e3 = O::mul(cur, c_tab[T_DC3]);
+      const double e1 = O::mul(ecur, c_tab[T_DC1]), e3 = O::mul(ecur, c_tab[T_DC3]);
 #pragma unroll
       for (int c = 0; c < NPAS; ++c) {
           accN[c] = O::mad(g3, kp_[c], O::mad(g1, k1[NDYN + c], x[NDYN + c]));
@@ -330,7 +358,7 @@ __device__ __forceinline__ void dopri5_attempt(const LaneParams<NA>& q, const St
 #pragma unroll
       for (int c = 0; c < NDYN; ++c) y[c] = O::mad(f3, k3[c], O::mad(f2, k2[c], O::mad(f1, k1[c], x[c]))); }
     rhs<NA, STRICT, true>(q, ba_at(T_A4), spi, next_slot(), lane_in_block, y, k4, kp_);
-    { const double g4 = O::mul(cur, c_tab[T_C4]), e4 = O::mul(cur, c_tab[T_DC4]);
+    { const double g4 = O::mul(cur, c_tab[T_C4]), e4 = O::mul(ecur, c_tab[T_DC4]);
 #pragma unroll
       for (int c = 0; c < NPAS; ++c) { accN[c] = O::mad(g4, kp_[c], accN[c]); accE[c] = O::mad(e4, kp_[c], accE[c]); } }
     // stage 5
@@ -340,7 +368,7 @@ __device__ __forceinline__ void dopri5_attempt(const LaneParams<NA>& q, const St
       for (int c = 0; c < NDYN; ++c)
           y[c] = O::mad(f4, k4[c], O::mad(f3, k3[c], O::mad(f2, k2[c], O::mad(f1, k1[c], x[c])))); }
     rhs<NA, STRICT, true>(q, ba_at(T_A5), spi, next_slot(), lane_in_block, y, k5, kp_);
-    { const double g5 = O::mul(cur, c_tab[T_C5]), e5 = O::mul(cur, c_tab[T_DC5]);
+    { const double g5 = O::mul(cur, c_tab[T_C5]), e5 = O::mul(ecur, c_tab[T_DC5]);
 #pragma unroll
       for (int c = 0; c < NPAS; ++c) { accN[c] = O::mad(g5, kp_[c], accN[c]); accE[c] = O::mad(e5, kp_[c], accE[c]); } }
     // stage 6
@@ -350,7 +378,7 @@ __device__ __forceinline__ void dopri5_attempt(const LaneParams<NA>& q, const St
       for (int c = 0; c < NDYN; ++c)
           y[c] = O::mad(f5, k5[c], O::mad(f4, k4[c], O::mad(f3, k3[c], O::mad(f2, k2[c], O::mad(f1, k1[c], x[c]))))); }
     rhs<NA, STRICT, true>(q, ba_at(-1), spi, next_slot(), lane_in_block, y, k6, kp_);
-    { const double g6 = O::mul(cur, c_tab[T_C6]), e6 = O::mul(cur, c_tab[T_DC6]);
+    { const double g6 = O::mul(cur, c_tab[T_C6]), e6 = O::mul(ecur, c_tab[T_DC6]);
 #pragma unroll
       for (int c = 0; c < NPAS; ++c) { accN[c] = O::mad(g6, kp_[c], accN[c]); accE[c] = O::mad(e6, kp_[c], accE[c]); } }
     // solution (dynamic part) and the FSAL derivative
@@ -361,8 +389,8 @@ __device__ __forceinline__ void dopri5_attempt(const LaneParams<NA>& q, const St
           xn[c] = O::mad(g6, k6[c], O::mad(g5, k5[c], O::mad(g4, k4[c], O::mad(g3, k3[c], O::mad(g1, k1[c], x[c]))))); }
     rhs<NA, STRICT, true>(q, ba_at(-1), spi, next_slot(), lane_in_block, xn, k7d, k7p);
     // error estimate
-    { const double e1 = O::mul(cur, c_tab[T_DC1]), e3 = O::mul(cur, c_tab[T_DC3]), e4 = O::mul(cur, c_tab[T_DC4]),
-                   e5 = O::mul(cur, c_tab[T_DC5]), e6 = O::mul(cur, c_tab[T_DC6]), e7 = O::mul(cur, c_tab[T_DC7]);
+    { const double e1 = O::mul(ecur, c_tab[T_DC1]), e3 = O::mul(ecur, c_tab[T_DC3]), e4 = O::mul(ecur, c_tab[T_DC4]),
+                   e5 = O::mul(ecur, c_tab[T_DC5]), e6 = O::mul(ecur, c_tab[T_DC6]), e7 = O::mul(ecur, c_tab[T_DC7]);
 #pragma unroll
       for (int c = 0; c < NDYN; ++c)
           xe[c] = O::mad(e7, k7d[c], O::mad(e6, k6[c], O::mad(e5, k5[c], O::mad(e4, k4[c], O::mad(e3, k3[c], O::mul(e1, k1[c]))))));
@@ -587,30 +615,41 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) sepaihrd_batch_kernel(cons
             bool need = alive && ((t_next - t) > DBL_EPSILON);   // less_with_sign(t, t_next, dt)
 
             // ---- adaptive steps up to t_next: one attempt per iteration for the WHOLE warp ------------------
-            while (__any_sync(FULL, need)) {
+            while (true) {
+                const unsigned m_need = __ballot_sync(FULL, need);   // group-uniform, so whole groups are set
+                if (m_need == 0) break;
                 double cur = std_min(dt, t_next - t);   // min_abs(dt, t_next - t)
                 const double t_end = O::add(t, cur);
-                // Stage times lie in (t, t_end].  If t_end <= bp_next they all use segment `seg`; otherwise look
-                // the segments up (steps that start on a breakpoint, or that straddle one on a general grid).
+                // warp-level flags: bit0 = some stepping group carries dt < hmax (its error VALUE matters on accept),
+                //                   bit1 = some lane's stage times leave its current schedule segment
+                const unsigned flags = __reduce_or_sync(FULL, ((need && dt < hmax) ? 1u : 0u) | ((t_end <= bp_next) ? 0u : 2u));
                 StepSched sc;
                 sc.ba_step = ba; sc.s_lo = seg; sc.bp = s_bp; sc.beff = my_beff; sc.nseg = nseg; sc.a = q.a;
                 int s_hi = seg;
-                bool mixed = false;
-                if (!(t_end <= bp_next)) {
-                    const double t2 = O::add(t, O::mul(cur, c_tab[T_A2]));
-                    int s_lo = seg;
-                    while (s_lo < nseg && t2 > s_bp[s_lo]) ++s_lo;
-                    s_hi = s_lo;
-                    while (s_hi < nseg && t_end > s_bp[s_hi]) ++s_hi;
-                    mixed = (s_lo != s_hi);
-                    sc.s_lo = s_lo;
-                    sc.ba_step = O::mul(my_beff[s_lo], q.a);
+                bool run_mixed = false;
+                if (flags & 2u) {
+                    // Stage times lie in (t, t_end].  Steps that start on a breakpoint (quirk Q2) or straddle one on a
+                    // general grid look their segments up.
+                    bool mixed = false;
+                    if (!(t_end <= bp_next)) {
+                        const double t2 = O::add(t, O::mul(cur, c_tab[T_A2]));
+                        int s_lo = seg;
+                        while (s_lo < nseg && t2 > s_bp[s_lo]) ++s_lo;
+                        s_hi = s_lo;
+                        while (s_hi < nseg && t_end > s_bp[s_hi]) ++s_hi;
+                        mixed = (s_lo != s_hi);
+                        sc.s_lo = s_lo;
+                        sc.ba_step = O::mul(my_beff[s_lo], q.a);
+                    }
+                    run_mixed = __any_sync(FULL, mixed);
                 }
                 double xn[NDYN], k7d[NDYN], k7p[NPAS], accN[NPAS], xe[NCOMP];
-                if (__any_sync(FULL, mixed))
-                    dopri5_attempt<NA, STRICT, true>(q, sc, spi, pi_slot, THREADS, threadIdx.x, t, cur, t_end, x, k1, xn, k7d, k7p, accN, xe);
+                const double ecur = STRICT ? cur : cur * kp.inv_rel;
+                if (run_mixed)
+                    dopri5_attempt<NA, STRICT, true>(q, sc, spi, pi_slot, THREADS, threadIdx.x, t, cur, t_end, x, k1, xn, k7d, k7p, accN, xe, ecur);
                 else
-                    dopri5_attempt<NA, STRICT, false>(q, sc, spi, pi_slot, THREADS, threadIdx.x, t, cur, t_end, x, k1, xn, k7d, k7p, accN, xe);
+                    dopri5_attempt<NA, STRICT, false>(q, sc, spi, pi_slot, THREADS, threadIdx.x, t, cur, t_end, x, k1, xn, k7d, k7p, accN, xe, ecur);
+                // error norm (default_error_checker): max_c |xerr_c| / (abs + rel * (|x_c| + dt * |dxdt_c|))
                 double err = 0.0;
                 bool reject;
                 if (STRICT) {
@@ -624,30 +663,41 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) sepaihrd_batch_kernel(cons
                     err = group_max<NA>(m);
                     reject = err > 1.0;
                 } else {
-                    // fl(num/den) > 1  <=>  num > den, so the accept/reject decision needs no division; the VALUE of
-                    // the error norm is only needed to shrink a rejected step or to grow a step that is below hmax.
-                    double den[NCOMP];
-                    bool big = false;
+                    // xe and den are both in units of rel_tol.  fl(num/den) > 1 <=> num > den, so the accept/reject
+                    // decision needs no division; the VALUE of the norm is only needed to shrink a rejected step or
+                    // to grow a step that is below hmax.
+                    double num[NCOMP], den[NCOMP];
+                    bool big0 = false, big1 = false, big2 = false;
 #pragma unroll
                     for (int c = 0; c < NCOMP; ++c) {
-                        den[c] = fma(f_rel, fma(cur, fabs(k1[c]), fabs(x[c])), f_abs);
-                        big |= fabs(xe[c]) > den[c];
+                        num[c] = fabs(xe[c]);
+                        den[c] = fma(cur, fabs(k1[c]), fabs(x[c])) + kp.abs_over_rel;
+                        const bool g = num[c] > den[c];
+                        if (c % 3 == 0) big0 |= g; else if (c % 3 == 1) big1 |= g; else big2 |= g;
                     }
-                    reject = (__ballot_sync(FULL, big) & gmask) != 0;
-                    if (__any_sync(FULL, need && (reject || dt < hmax))) {
-                        double bn = 0.0, bd = 1.0;   // arg-max by cross multiplication, then ONE exact division
+                    const unsigned bal = __ballot_sync(FULL, big0 | big1 | big2);
+                    reject = (bal & gmask) != 0;
+                    if ((flags & 1u) || (bal & m_need)) {
+                        // arg-max of num/den by a cross-multiplication tournament, then ONE exact division per lane
 #pragma unroll
-                        for (int c = 0; c < NCOMP; ++c) {
-                            const double num = fabs(xe[c]);
-                            if (num * bd > bn * den[c]) { bn = num; bd = den[c]; }
+                        for (int stride = 1; stride < NCOMP; stride *= 2) {
+#pragma unroll
+                            for (int c = 0; c + stride < NCOMP; c += 2 * stride) {
+                                const bool other = num[c + stride] * den[c] > num[c] * den[c + stride];
+                                num[c] = other ? num[c + stride] : num[c];
+                                den[c] = other ? den[c + stride] : den[c];
+                            }
                         }
-                        err = group_max<NA>(bn / bd);
+                        err = group_max<NA>(num[0] / den[0]);
                     }
                 }
                 if (need) {
                     if (reject) {
                         // decrease_step (error_order 4): dt *= max(0.9 * err^(-1/3), 1/5)
-                        cur = O::mul(cur, std_max(O::mul(9.0 / 10.0, pow(err, -1.0 / 3.0)), 1.0 / 5.0));
+                        double shrink;
+                        if (STRICT) shrink = std_max(O::mul(9.0 / 10.0, pow(err, -1.0 / 3.0)), 1.0 / 5.0);
+                        else shrink = (err > 128.0) ? 0.2 : std_max(0.9 * pow_m1_3(err), 0.2);   // 0.9 err^(-1/3) < 0.2 beyond 91.2
+                        cur = O::mul(cur, shrink);
                         ++n_rej;
                         dt = cur;
                         if (fail_steps++ >= 500) { status |= SEPAIHRD_ST_STEP_FAILURE; alive = false; }
@@ -657,7 +707,8 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) sepaihrd_batch_kernel(cons
                         if (STRICT || dt < hmax) {
                             if (err < 0.5) {
                                 const double e2 = std_max(3.2e-4 /* pow(5,-5) */, err);
-                                cur = O::mul(cur, O::mul(9.0 / 10.0, pow(e2, -1.0 / 5.0)));
+                                if (STRICT) cur = O::mul(cur, O::mul(9.0 / 10.0, pow(e2, -1.0 / 5.0)));
+                                else cur = cur * (0.9 * pow_m1_5(e2));
                             }
                             dt = std_max(dt, cur);   // max_abs: keep the larger of the carried and the proposed step
                         }
