@@ -282,9 +282,15 @@ sepaihrd_rc sepaihrd_create(const sepaihrd_problem* pb, int32_t device, sepaihrd
     };
     sepaihrd::KParams& kp = ctx->kp;
     kp.o_times = put(pb->times, K);
-    kp.o_obs_h = put(pb->obs_hosp, (size_t)pb->n_obs * n);
-    kp.o_obs_i = put(pb->obs_icu, (size_t)pb->n_obs * n);
-    kp.o_obs_d = put(pb->obs_deaths, (size_t)pb->n_obs * n);
+    // observations: entries the likelihood skips (negative or non-finite, ObjectiveFunction.cpp:267) are stored as -1
+    auto put_obs = [&](const double* src) {
+        std::vector<double> v(src, src + (size_t)pb->n_obs * n);
+        for (double& o : v) if (!(o >= 0.0 && std::isfinite(o))) o = -1.0;
+        return put(v.data(), v.size());
+    };
+    kp.o_obs_h = put_obs(pb->obs_hosp);
+    kp.o_obs_i = put_obs(pb->obs_icu);
+    kp.o_obs_d = put_obs(pb->obs_deaths);
     kp.o_pop = put(pb->population, n);
     {
         // age_fraction = N / N.sum() (ObjectiveFunction.cpp:100-107); inv_N (AgeSEPAIHRDModel.cpp:46-49)
@@ -304,6 +310,17 @@ sepaihrd_rc sepaihrd_create(const sepaihrd_problem* pb, int32_t device, sepaihrd
     kp.o_init = put(pb->data_initial_state, (size_t)SEPAIHRD_NUM_COMPARTMENTS * n);
     kp.o_lo = put(pb->lower_bound, P);
     kp.o_hi = put(pb->upper_bound, P);
+    {
+        // FAST-mode logarithm table: c_i = 1 + (i + 1/2)/128; (1/c_i, -log(1/c_i)) with the SAME rounded 1/c_i
+        if (B.size() % 2) B.push_back(0.0);   // 16-byte alignment for LDS.128
+        std::vector<double> tab(256);
+        for (int i = 0; i < 128; ++i) {
+            const double invc = 1.0 / (1.0 + (i + 0.5) / 128.0);
+            tab[2 * i] = invc;
+            tab[2 * i + 1] = (double)(-std::log((long double)invc));
+        }
+        kp.o_logtab = put(tab.data(), tab.size());
+    }
     kp.o_pslot = put_ints(pslot.data(), P);
     kp.o_segb = put_ints(segb.data(), nseg + 1);
     kp.o_segk = put_ints(segk.data(), nseg + 1);

@@ -49,6 +49,7 @@ struct KParams {
     // offsets (in doubles) of the arrays inside the blob
     int o_times, o_obs_h, o_obs_i, o_obs_d, o_pop, o_agefrac, o_invN, o_M, o_bp, o_base, o_init, o_lo, o_hi;
     int o_pslot, o_segb, o_segk;   // int32 arrays, offsets still in doubles
+    int o_logtab;              // 128 x (1/c_i, log c_i): table of the FAST-mode logarithm
     int n, K, n_obs, runup_offset, nb, nk, nseg, P, nslots;
     int slot_stride;           // doubles per set in the shared slot table (odd -> conflict-free)
     int seg_stride;            // doubles per set in the shared beta_eff table
@@ -163,6 +164,27 @@ __device__ __forceinline__ double pow_m1_3(double x) {
         y = y * fma(-xs, y3, 4.0 / 3.0);      // y (4 - x y^3) / 3
     }
     return y;
+}
+
+// ---- logarithm for the Poisson terms (FAST) -----------------------------------------------------------
+// log(x) = e ln2 + log(c_i) + log1p(r),  r = m / c_i - 1 (one FMA, exact rounding), i = top 7 mantissa bits,
+// |r| <= 2^-8, log1p by a degree-5 polynomial (truncation 7e-16).  Absolute error ~1e-15: far inside what the
+// 1e-8 relative gate on logL needs, at ~9 FP64 instructions instead of ~35 for CUDA's log() (v4 profile: the three
+// log() calls per output day were 25% of the kernel time).  Non-finite and non-positive inputs go to log().
+__device__ __noinline__ double slow_log(double x) { return log(x); }
+__device__ __forceinline__ double fast_log(double x, const double2* __restrict__ tab) {
+    const int hi = __double2hiint(x);
+    if ((unsigned)(hi - 0x00100000) >= 0x7fe00000u) return slow_log(x);   // zero, subnormal, negative, inf, NaN
+    const int e = (hi >> 20) - 1023;
+    const int i = (hi >> 13) & 0x7f;
+    const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));   // [1, 2)
+    const double2 t = tab[i];
+    const double r = fma(m, t.x, -1.0);
+    double p = fma(r, 0.2, -0.25);
+    p = fma(p, r, 1.0 / 3.0);
+    p = fma(p, r, -0.5);
+    p = fma(p, r, 1.0);
+    return fma((double)e, 0.6931471805599453, fma(p, r, t.y));
 }
 
 // ---- per-lane model parameters (registers) ----------------------------------------------------------
@@ -432,6 +454,7 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) sepaihrd_batch_kernel(cons
     const int* s_pslot = reinterpret_cast<const int*>(sblob + kp.o_pslot);
     const int* s_segb = reinterpret_cast<const int*>(sblob + kp.o_segb);
     const int* s_segk = reinterpret_cast<const int*>(sblob + kp.o_segk);
+    const double2* s_logtab = reinterpret_cast<const double2*>(sblob + kp.o_logtab);
     int pi_slot = 0;   // toggles between 0 and THREADS before every pressure exchange
 
     const int age = threadIdx.x % NA;
@@ -586,11 +609,17 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) sepaihrd_batch_kernel(cons
                     const double eps = 1e-10;
                     double term_h = 0.0, term_i = 0.0, term_d = 0.0;
                     const double oh = s_obs_h[r * n + age], oi = s_obs_i[r * n + age], od = s_obs_d[r * n + age];
-                    const bool vh = (oh >= 0.0) && isfinite(oh), vi = (oi >= 0.0) && isfinite(oi),
-                               vd = (od >= 0.0) && isfinite(od);
-                    if (vh) { double sim = inc_h; if (sim < 0.0) sim = 0.0; sim = O::add(sim, eps); term_h = O::sub(O::mul(oh, log(sim)), sim); }
-                    if (vi) { double sim = inc_i; if (sim < 0.0) sim = 0.0; sim = O::add(sim, eps); term_i = O::sub(O::mul(oi, log(sim)), sim); }
-                    if (vd) { double sim = inc_d; if (sim < 0.0) sim = 0.0; sim = O::add(sim, eps); term_d = O::sub(O::mul(od, log(sim)), sim); }
+                    // the host stores every skipped observation (negative, NaN, inf: ObjectiveFunction.cpp:267) as -1
+                    const bool vh = (oh >= 0.0), vi = (oi >= 0.0), vd = (od >= 0.0);
+                    if (STRICT) {
+                        if (vh) { double sim = inc_h; if (sim < 0.0) sim = 0.0; sim = O::add(sim, eps); term_h = O::sub(O::mul(oh, log(sim)), sim); }
+                        if (vi) { double sim = inc_i; if (sim < 0.0) sim = 0.0; sim = O::add(sim, eps); term_i = O::sub(O::mul(oi, log(sim)), sim); }
+                        if (vd) { double sim = inc_d; if (sim < 0.0) sim = 0.0; sim = O::add(sim, eps); term_d = O::sub(O::mul(od, log(sim)), sim); }
+                    } else {
+                        if (vh) { const double sim = inc_h + eps; term_h = fma(oh, fast_log(sim, s_logtab), -sim); }
+                        if (vi) { const double sim = inc_i + eps; term_i = fma(oi, fast_log(sim, s_logtab), -sim); }
+                        if (vd) { const double sim = inc_d + eps; term_d = fma(od, fast_log(sim, s_logtab), -sim); }
+                    }
                     if (STRICT) {
                         // row_sum over ages in order, then log_likelihood += row_sum (per stream)
                         double rs_h = 0.0, rs_i = 0.0, rs_d = 0.0;
@@ -599,9 +628,9 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) sepaihrd_batch_kernel(cons
                             const double th = __shfl_sync(FULL, term_h, j, NA), ti = __shfl_sync(FULL, term_i, j, NA),
                                          td = __shfl_sync(FULL, term_d, j, NA);
                             const double ohj = s_obs_h[r * n + j], oij = s_obs_i[r * n + j], odj = s_obs_d[r * n + j];
-                            if ((ohj >= 0.0) && isfinite(ohj)) rs_h = O::add(rs_h, th);
-                            if ((oij >= 0.0) && isfinite(oij)) rs_i = O::add(rs_i, ti);
-                            if ((odj >= 0.0) && isfinite(odj)) rs_d = O::add(rs_d, td);
+                            if (ohj >= 0.0) rs_h = O::add(rs_h, th);
+                            if (oij >= 0.0) rs_i = O::add(rs_i, ti);
+                            if (odj >= 0.0) rs_d = O::add(rs_d, td);
                         }
                         ll_acc_h = O::add(ll_acc_h, rs_h); ll_acc_i = O::add(ll_acc_i, rs_i); ll_acc_d = O::add(ll_acc_d, rs_d);
                     } else {
