@@ -63,5 +63,6 @@ def golden():
 def cuda_lib():
     """Build (if stale) and load the product library; GPU tests call through the C ABI only."""
     entry.build_cuda()
+    entry.load_package()
     from sepaihrd_b200 import capi
     return capi.load_library()

@@ -1,0 +1,304 @@
+"""GPU parity tests: the CUDA path (through the C ABI, csrc/libsepaihrd_b200.so) against the CPU oracle
+on identical parameter sets, against the committed golden fixtures, and -- at BASELINE.json's full batch
+size -- through size-independent properties.
+
+Tolerances (BASELINE.json north_star): trajectories 1e-6 relative, log-likelihoods 1e-8 relative in FP64,
+identical accept/reject decisions (here: identical accepted/rejected Dopri5 step counts per set).
+Measured margins are ~1e-11 / ~1e-13, so the assertions use much tighter bounds than the gate and say so.
+"""
+import copy
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+LL_GATE = 1e-8          # north_star gate on logL
+TRAJ_GATE = 1e-6        # north_star gate on trajectories
+LL_TIGHT = 1e-9         # what we actually hold (observed <= 2e-11)
+TRAJ_TIGHT = 1e-10      # observed <= 1e-13
+
+
+@pytest.fixture(scope="module")
+def ev_mod(cuda_lib):
+    from sepaihrd_b200 import evaluator
+    return evaluator
+
+
+def _rel(a, b):
+    return np.abs(a - b) / np.maximum(np.abs(b), 1e-300)
+
+
+def _traj_rel(a, b):
+    return np.abs(a - b) / np.maximum(np.abs(b), 1.0)
+
+
+@pytest.mark.parametrize("dist", ["jitter", "uniform"])
+@pytest.mark.parametrize("math", ["strict", "fast"])
+def test_loglik_and_step_counts_match_oracle(problem, oracle, ev_mod, dist, math):
+    P = oracle.jitter_params(1024, seed=1) if dist == "jitter" else oracle.uniform_params(1024, seed=2)
+    if dist == "jitter":
+        P[0] = problem.base_params()
+    ll_ref, st_ref, steps_ref, _ = oracle.eval_batch(P)
+    with ev_mod.BatchEvaluator(problem, device=0, math=ev_mod.MATH_STRICT if math == "strict" else ev_mod.MATH_FAST) as ev:
+        ll, st, steps = ev.eval_batch(P, return_steps=True)
+    np.testing.assert_array_equal(st, st_ref)
+    assert _rel(ll, ll_ref).max() < LL_TIGHT < LL_GATE
+    np.testing.assert_array_equal(steps, steps_ref)          # identical accept/reject counts for every set
+
+
+@pytest.mark.parametrize("math", ["strict", "fast"])
+def test_golden_fixtures(problem, golden, ev_mod, pkg, math):
+    m = ev_mod.MATH_STRICT if math == "strict" else ev_mod.MATH_FAST
+    with ev_mod.BatchEvaluator(problem, device=0, math=m) as ev:
+        ll, st = ev.eval_batch(np.array([golden["default"]["params"]]))
+        assert st[0] == 0
+        assert abs(ll[0] - golden["survey_anchor"]["logL"]) / golden["survey_anchor"]["logL"] < 1e-12
+        for key in ("jitter", "uniform"):
+            g = golden[key]
+            ll, st, steps = ev.eval_batch(np.array(g["params"]), return_steps=True)
+            assert _rel(ll, np.array(g["logL"])).max() < LL_TIGHT
+            np.testing.assert_array_equal(steps, np.array(g["steps"]))
+            np.testing.assert_array_equal(st, np.array(g["status"]))
+        ev.set_constraint_mode(pkg.REFLECT)
+        g = golden["reflect"]
+        ll, st, steps = ev.eval_batch(np.array(g["params"]), return_steps=True)
+        assert _rel(ll, np.array(g["logL"])).max() < LL_TIGHT
+        np.testing.assert_array_equal(steps, np.array(g["steps"]))
+
+
+def test_default_trajectory_matches_golden_rows(problem, golden, ev_mod):
+    with ev_mod.BatchEvaluator(problem, device=0) as ev:
+        tr, st = ev.simulate_batch(np.array([golden["default"]["params"]]))
+    rows = golden["default"]["traj_rows"]
+    want = np.array(golden["default"]["traj"])
+    assert _traj_rel(tr[0][rows], want).max() < TRAJ_TIGHT < TRAJ_GATE
+
+
+@pytest.mark.parametrize("math", ["strict", "fast"])
+def test_trajectories_match_oracle(problem, oracle, ev_mod, pkg, math):
+    P = oracle.uniform_params(96, seed=5)
+    ref, st_ref = oracle.simulate_batch(P)
+    m = ev_mod.MATH_STRICT if math == "strict" else ev_mod.MATH_FAST
+    with ev_mod.BatchEvaluator(problem, device=0, math=m) as ev:
+        tr, st = ev.simulate_batch(P)
+        obs, _ = ev.simulate_batch(P, what=pkg.TRAJ_OBSERVED, stride=7)
+    np.testing.assert_array_equal(st, st_ref)
+    assert _traj_rel(tr, ref).max() < TRAJ_TIGHT
+    n = problem.n_ages
+    np.testing.assert_array_equal(obs[:, :, 0:n], tr[:, ::7, 8 * n:9 * n])        # D
+    np.testing.assert_array_equal(obs[:, :, n:2 * n], tr[:, ::7, 9 * n:10 * n])   # CumH
+    np.testing.assert_array_equal(obs[:, :, 2 * n:], tr[:, ::7, 10 * n:])         # CumICU
+
+
+def test_strict_math_is_bit_exact_when_the_controller_never_rejects(problem, orc, ev_mod):
+    """With loose tolerances every 1-day step is accepted and dt is always clipped to the grid, so the result
+    does not depend on pow(); STRICT mode then reproduces the oracle's trajectory BIT FOR BIT (the remaining
+    differences at 1e-6 tolerances are libm pow() rounding feeding the step size)."""
+    p2 = copy.deepcopy(problem)
+    p2.abs_tol = p2.rel_tol = 1.0e3
+    P = orc.Oracle(p2).uniform_params(64, seed=8)
+    ref, _ = orc.Oracle(p2).simulate_batch(P)
+    _, _, steps_ref, _ = orc.Oracle(p2).eval_batch(P)
+    assert (steps_ref[:, 1] == 0).all() and (steps_ref[:, 0] == problem.n_times - 1).all()
+    with ev_mod.BatchEvaluator(p2, device=0, math=ev_mod.MATH_STRICT) as ev:
+        tr, _ = ev.simulate_batch(P)
+    np.testing.assert_array_equal(tr, ref)
+
+
+def test_likelihood_recomputed_from_device_trajectories(problem, oracle, orc, ev_mod):
+    """eval_batch is consistent with simulate_batch + the oracle's Poisson sum (fused vs unfused path)."""
+    P = oracle.jitter_params(16, seed=3)
+    with ev_mod.BatchEvaluator(problem, device=0) as ev:
+        ll, _ = ev.eval_batch(P)
+        tr, _ = ev.simulate_batch(P)
+    n = problem.n_ages
+    off = problem.n_times - problem.n_obs
+    for b in range(len(P)):
+        t = tr[b].reshape(problem.n_times, 11, n)
+        tot = 0.0
+        parts = []
+        for comp, obs in ((9, problem.obs_hosp), (10, problem.obs_icu), (8, problem.obs_deaths)):
+            inc = np.maximum(np.diff(t[:, comp, :], axis=0, prepend=t[:1, comp, :]), 0.0)
+            parts.append(orc.poisson_ll(inc[off:], obs))
+        tot = (parts[0] + parts[1]) + parts[2]
+        assert abs(tot - ll[b]) / abs(tot) < 1e-12
+
+
+def test_edge_cases_empty_single_ragged_and_padded_rows(problem, oracle, ev_mod):
+    P = oracle.jitter_params(77, seed=12)                  # 77 is not a multiple of the 32 sets per block
+    ll_ref, _, steps_ref, _ = oracle.eval_batch(P)
+    with ev_mod.BatchEvaluator(problem, device=0) as ev:
+        ll0, st0 = ev.eval_batch(np.empty((0, problem.n_params)))
+        assert ll0.shape == (0,)
+        ll1, _ = ev.eval_batch(P[:1])
+        assert _rel(ll1, ll_ref[:1]).max() < LL_TIGHT
+        ll, st, steps = ev.eval_batch(P, return_steps=True)
+        assert _rel(ll, ll_ref).max() < LL_TIGHT
+        np.testing.assert_array_equal(steps, steps_ref)
+        # leading dimension larger than P (rows padded with garbage)
+        wide = np.full((77, problem.n_params + 5), np.nan)
+        wide[:, :problem.n_params] = P
+        llw, _ = ev.eval_batch(wide)
+        np.testing.assert_array_equal(llw, ll)
+        with pytest.raises(Exception):
+            ev.eval_batch(P[:, :10])                        # "Parameter vector size mismatch."
+
+
+def test_failure_sentinels_match_oracle(problem, orc, pkg, ev_mod):
+    """Per-set failures give -DBL_MAX (quirk Q5) with the same status word as the oracle."""
+    d = problem.to_json()
+    names = problem.param_names
+    ik, iru, ie, isg = names.index("kappa_3"), names.index("runup_days"), names.index("E0_multiplier"), names.index("sigma")
+    d["lower_bound"][ik] = -5.0
+    d["lower_bound"][iru] = -1.0
+    d["upper_bound"][ie] = 1e12
+    p2 = pkg.Problem.from_json(d)
+    base = p2.base_params()
+    P = np.tile(base, (6, 1))
+    P[1, ik] = -1.0                                  # negative kappa -> INVALID_PARAM
+    P[2, iru] = -1.0; P[2, ie] = 1e12                # multiplier mode, S overflow
+    P[3, iru] = -1.0                                 # multiplier mode, fine
+    P[4, isg] = np.nan                               # NaN state -> NONFINITE
+    P[5, names.index("beta_1")] = np.nan             # swallowed by max(0, lambda): finite
+    ll_ref, st_ref, steps_ref, _ = orc.Oracle(p2).eval_batch(P)
+    assert list(st_ref) == [0, pkg.ST_INVALID_PARAM, pkg.ST_S_OVERFLOW, 0, pkg.ST_NONFINITE, 0]
+    for m in (ev_mod.MATH_STRICT, ev_mod.MATH_FAST):
+        with ev_mod.BatchEvaluator(p2, device=0, math=m) as ev:
+            ll, st = ev.eval_batch(P)
+            tr, st_tr = ev.simulate_batch(P)
+        np.testing.assert_array_equal(st, st_ref)
+        good = st_ref == 0
+        assert _rel(ll[good], ll_ref[good]).max() < LL_TIGHT
+        assert (ll[~good] == pkg.LOWEST).all() and (ll_ref[~good] == pkg.LOWEST).all()
+        assert np.isnan(tr[1]).all() and np.isnan(tr[2]).all() and np.isfinite(tr[3]).all()
+
+
+def test_nan_and_negative_observations_are_skipped(problem, orc, pkg, ev_mod):
+    p2 = copy.deepcopy(problem)
+    p2.obs_hosp[10:20, 1] = np.nan
+    p2.obs_deaths[5, :] = -1.0
+    p2.obs_icu[7, 2] = np.inf
+    P = orc.Oracle(p2).jitter_params(8, seed=2)
+    ll_ref, st_ref, _, _ = orc.Oracle(p2).eval_batch(P)
+    for m in (ev_mod.MATH_STRICT, ev_mod.MATH_FAST):
+        with ev_mod.BatchEvaluator(p2, device=0, math=m) as ev:
+            ll, st = ev.eval_batch(P)
+        assert (st == 0).all() and _rel(ll, ll_ref).max() < LL_TIGHT
+
+
+def test_sixteen_age_variant(problem, orc, pkg, ev_mod):
+    """BASELINE configs[4]: synthetic 16-age-group contact matrix, full trajectories."""
+    p16 = problem.expand_ages(4)
+    o16 = orc.Oracle(p16)
+    P = o16.jitter_params(24, seed=4)
+    ll_ref, st_ref, steps_ref, _ = o16.eval_batch(P)
+    tr_ref, _ = o16.simulate_batch(P[:6])
+    for m in (ev_mod.MATH_STRICT, ev_mod.MATH_FAST):
+        with ev_mod.BatchEvaluator(p16, device=0, math=m) as ev:
+            ll, st, steps = ev.eval_batch(P, return_steps=True)
+            tr, _ = ev.simulate_batch(P[:6])
+        np.testing.assert_array_equal(st, st_ref)
+        assert _rel(ll, ll_ref).max() < LL_TIGHT
+        np.testing.assert_array_equal(steps, steps_ref)
+        assert _traj_rel(tr, tr_ref).max() < TRAJ_TIGHT
+
+
+def test_general_time_grid_and_off_grid_breakpoints(problem, orc, ev_mod):
+    """Breakpoints that do not sit on output times exercise the per-stage schedule lookup (steps that
+    straddle a discontinuity), on a non-uniform output grid (1-day then 2-day spacing, dt_hint < hmax)."""
+    p2 = copy.deepcopy(problem)
+    p2.beta_end_times = np.array([13.4, 63.0, 84.25, 111.0, 183.7, 237.0, 305.0])
+    p2.kappa_end_times = np.array([12.9, 63.0, 85.5, 111.0, 183.7, 240.1, 305.0])
+    keep = np.r_[0:40, 40:326:2]
+    p2.times = p2.times[keep] * 1.0
+    off = int(np.argmax(p2.times >= 0))
+    sel = keep[off:] - 20
+    p2.obs_hosp, p2.obs_icu, p2.obs_deaths = p2.obs_hosp[sel], p2.obs_icu[sel], p2.obs_deaths[sel]
+    o2 = orc.Oracle(p2)
+    P = o2.uniform_params(48, seed=6)
+    ll_ref, st_ref, steps_ref, _ = o2.eval_batch(P)
+    for m in (ev_mod.MATH_STRICT, ev_mod.MATH_FAST):
+        with ev_mod.BatchEvaluator(p2, device=0, math=m) as ev:
+            ll, st, steps = ev.eval_batch(P, return_steps=True)
+        np.testing.assert_array_equal(st, st_ref)
+        assert _rel(ll, ll_ref).max() < LL_TIGHT
+        assert (steps != steps_ref).any(axis=1).mean() <= 0.05   # a straddled discontinuity makes err hug 1.0
+
+
+def test_grid_without_runup_puts_row_zero_into_the_likelihood(problem, orc, ev_mod):
+    """times start at 0: runup_offset_ = 0, so the first likelihood row is the zero incidence of the initial
+    state against itself, obs*log(1e-10) - 1e-10 (ObjectiveFunction.cpp:191-194, 218-220)."""
+    p2 = copy.deepcopy(problem)
+    p2.times = p2.times[20:].copy()
+    o2 = orc.Oracle(p2)
+    P = o2.jitter_params(32, seed=9)
+    ll_ref, st_ref, steps_ref, _ = o2.eval_batch(P)
+    for m in (ev_mod.MATH_STRICT, ev_mod.MATH_FAST):
+        with ev_mod.BatchEvaluator(p2, device=0, math=m) as ev:
+            ll, st, steps = ev.eval_batch(P, return_steps=True)
+        np.testing.assert_array_equal(st, st_ref)
+        assert _rel(ll, ll_ref).max() < LL_TIGHT
+        np.testing.assert_array_equal(steps, steps_ref)
+
+
+def test_observation_row_mismatch_returns_lowest(problem, orc, pkg, ev_mod):
+    """num_obs_points_ != observed rows -> calculate() returns lowest() (ObjectiveFunction.cpp:176-178)."""
+    p2 = copy.deepcopy(problem)
+    p2.times = p2.times[:-3].copy()
+    P = orc.Oracle(p2).jitter_params(5, seed=1)
+    ll_ref, _, _, _ = orc.Oracle(p2).eval_batch(P)
+    with ev_mod.BatchEvaluator(p2, device=0) as ev:
+        ll, st = ev.eval_batch(P)
+    assert (ll == pkg.LOWEST).all() and (ll_ref == pkg.LOWEST).all()
+
+
+def test_device_pointer_path_matches_host_path(problem, oracle, ev_mod):
+    import torch
+    P = oracle.jitter_params(300, seed=21)
+    with ev_mod.BatchEvaluator(problem, device=0) as ev:
+        ll_h, st_h, steps_h = ev.eval_batch(P, return_steps=True)
+        d = torch.from_numpy(P).cuda()
+        ll_d, st_d, steps_d = ev.eval_batch(d, return_steps=True)
+        torch.cuda.synchronize()
+        np.testing.assert_array_equal(ll_d.cpu().numpy(), ll_h)
+        np.testing.assert_array_equal(steps_d.cpu().numpy(), steps_h)
+        launches, sets = ev.counters()
+        assert launches == 2 and sets == 600
+
+
+def test_full_size_properties_one_million_sets(problem, oracle, ev_mod):
+    """BASELINE configs[1] size (B = 1,048,576) through size-independent properties: a permuted batch gives
+    the permuted result bit for bit, duplicated sets give duplicated values, a checksum over the batch equals
+    the checksum of its tiles evaluated separately, and a random subsample agrees with the CPU oracle."""
+    import torch
+    B = 1 << 20
+    distinct = oracle.jitter_params(4096, seed=1)
+    rng = np.random.default_rng(0)
+    idx = rng.integers(0, len(distinct), B)
+    d_distinct = torch.from_numpy(distinct).cuda()
+    d_idx = torch.from_numpy(idx).cuda()
+    d_P = d_distinct[d_idx].contiguous()
+    with ev_mod.BatchEvaluator(problem, device=0) as ev:
+        ll, st, steps = ev.eval_batch(d_P, return_steps=True)
+        ll_small, _ = ev.eval_batch(d_distinct)
+        perm = torch.randperm(B, device="cuda")
+        ll_perm, _ = ev.eval_batch(d_P[perm].contiguous())
+        torch.cuda.synchronize()
+        assert int((st != 0).sum()) == 0
+        # duplicates / tiling: every copy of a distinct set has the value it has in the small batch
+        assert torch.equal(ll, ll_small[d_idx])
+        # permutation equivariance, bit for bit
+        assert torch.equal(ll_perm, ll[perm])
+        # checksum of checksums
+        chunks = [ev.eval_batch(d_P[i:i + (1 << 18)].contiguous())[0].sum() for i in range(0, B, 1 << 18)]
+        assert abs(float(torch.stack(chunks).sum()) - float(ll.sum())) <= 1e-9 * abs(float(ll.sum()))
+    sub = rng.integers(0, B, 256)
+    ll_ref, _, steps_ref, _ = oracle.eval_batch(distinct[idx[sub]])
+    assert _rel(ll[torch.from_numpy(sub).cuda()].cpu().numpy(), ll_ref).max() < LL_TIGHT
+    np.testing.assert_array_equal(steps[torch.from_numpy(sub).cuda()].cpu().numpy(), steps_ref)
+
+
+def test_fp64_peak_probe_is_plausible(ev_mod):
+    peak = ev_mod.measure_fp64_peak(0)
+    assert 5e12 < peak < 4e13        # B200: 148 SMs x 64 DFMA/clk x ~1.9 GHz = 1.8e13
