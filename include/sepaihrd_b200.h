@@ -166,6 +166,19 @@ sepaihrd_rc sepaihrd_simulate_batch(sepaihrd_ctx* ctx, const double* params, int
 sepaihrd_rc sepaihrd_simulate_batch_device(sepaihrd_ctx* ctx, const double* d_params, int64_t B, int64_t ld,
                                            int32_t what, int32_t stride, double* d_out, uint32_t* d_out_status);
 
+/* Replaces B calls of Simulator::run(initial_state, times) (Simulator.cpp:60-150) where the CALLER supplies the
+ * initial state, integrated as given (no seeding / multiplier / S-remainder rule): what
+ * PostCalibrationAnalyser and ResultAggregator do with one fixed initial state for every posterior draw
+ * (PostCalibrationAnalyser.cpp:156,221; ResultAggregator.cpp:289 -- quirk Q9).
+ *   initial_states [B][state_stride] compartment-major states, or ONE state shared by all sets when
+ *                  state_stride == 0.  Other arguments as sepaihrd_simulate_batch. */
+sepaihrd_rc sepaihrd_simulate_from_state(sepaihrd_ctx* ctx, const double* params, int64_t B, int64_t ld,
+                                         const double* initial_states, int64_t state_stride, int32_t what, int32_t stride,
+                                         double* out, uint32_t* out_status);
+sepaihrd_rc sepaihrd_simulate_from_state_device(sepaihrd_ctx* ctx, const double* d_params, int64_t B, int64_t ld,
+                                                const double* d_initial_states, int64_t state_stride, int32_t what,
+                                                int32_t stride, double* d_out, uint32_t* d_out_status);
+
 /* Block until everything enqueued on the ctx stream has finished. */
 sepaihrd_rc sepaihrd_synchronize(sepaihrd_ctx* ctx);
 

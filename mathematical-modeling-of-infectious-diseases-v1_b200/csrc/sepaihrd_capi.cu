@@ -415,6 +415,7 @@ sepaihrd_rc sepaihrd_eval_batch_device(sepaihrd_ctx* ctx, const double* d_params
     kp.params = d_params; kp.B = B; kp.ld = ld;
     kp.out_ll = d_out_ll; kp.out_status = d_out_status; kp.out_steps = d_out_steps;
     kp.out_traj = nullptr; kp.traj_what = 0; kp.traj_stride = 1; kp.traj_rows = 0;
+    kp.init_states = nullptr; kp.init_stride = 0;
     return launch(ctx, kp, sepaihrd::MODE_LL);
 }
 
@@ -441,8 +442,9 @@ sepaihrd_rc sepaihrd_eval_batch(sepaihrd_ctx* ctx, const double* params, int64_t
     return SEPAIHRD_OK;
 }
 
-sepaihrd_rc sepaihrd_simulate_batch_device(sepaihrd_ctx* ctx, const double* d_params, int64_t B, int64_t ld,
-                                           int32_t what, int32_t stride, double* d_out, uint32_t* d_out_status) {
+static sepaihrd_rc simulate_device_impl(sepaihrd_ctx* ctx, const double* d_params, int64_t B, int64_t ld,
+                                        const double* d_init, int64_t init_stride,
+                                        int32_t what, int32_t stride, double* d_out, uint32_t* d_out_status) {
     if (!ctx || !d_out || (B > 0 && !d_params)) return fail(SEPAIHRD_ERR_INVALID_ARGUMENT, "null argument");
     if (B < 0 || ld < ctx->P) return fail(SEPAIHRD_ERR_INVALID_ARGUMENT, "Parameter vector size mismatch.");
     if (what != SEPAIHRD_TRAJ_FULL && what != SEPAIHRD_TRAJ_OBSERVED) return fail(SEPAIHRD_ERR_INVALID_ARGUMENT, "bad trajectory selector");
@@ -454,7 +456,20 @@ sepaihrd_rc sepaihrd_simulate_batch_device(sepaihrd_ctx* ctx, const double* d_pa
     kp.params = d_params; kp.B = B; kp.ld = ld;
     kp.out_ll = nullptr; kp.out_status = d_out_status; kp.out_steps = nullptr;
     kp.out_traj = d_out; kp.traj_what = what; kp.traj_stride = stride; kp.traj_rows = (ctx->K + stride - 1) / stride;
+    kp.init_states = d_init; kp.init_stride = init_stride;
     return launch(ctx, kp, sepaihrd::MODE_TRAJ);
+}
+
+sepaihrd_rc sepaihrd_simulate_batch_device(sepaihrd_ctx* ctx, const double* d_params, int64_t B, int64_t ld,
+                                           int32_t what, int32_t stride, double* d_out, uint32_t* d_out_status) {
+    return simulate_device_impl(ctx, d_params, B, ld, nullptr, 0, what, stride, d_out, d_out_status);
+}
+
+sepaihrd_rc sepaihrd_simulate_from_state_device(sepaihrd_ctx* ctx, const double* d_params, int64_t B, int64_t ld,
+                                                const double* d_initial_states, int64_t state_stride, int32_t what,
+                                                int32_t stride, double* d_out, uint32_t* d_out_status) {
+    if (!d_initial_states) return fail(SEPAIHRD_ERR_INVALID_ARGUMENT, "null initial state");
+    return simulate_device_impl(ctx, d_params, B, ld, d_initial_states, state_stride, what, stride, d_out, d_out_status);
 }
 
 sepaihrd_rc sepaihrd_simulate_batch(sepaihrd_ctx* ctx, const double* params, int64_t B, int64_t ld, int32_t what,
@@ -473,6 +488,35 @@ sepaihrd_rc sepaihrd_simulate_batch(sepaihrd_ctx* ctx, const double* params, int
     if ((rc = grow(&ctx->d_status, &ctx->cap_status, (size_t)B)) != SEPAIHRD_OK) return rc;
     CUDA_TRY(cudaMemcpyAsync(ctx->d_params, params, sizeof(double) * (size_t)B * ld, cudaMemcpyHostToDevice, ctx->stream));
     rc = sepaihrd_simulate_batch_device(ctx, ctx->d_params, B, ld, what, stride, ctx->d_out, ctx->d_status);
+    if (rc != SEPAIHRD_OK) return rc;
+    CUDA_TRY(cudaMemcpyAsync(out, ctx->d_out, sizeof(double) * total, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_status) CUDA_TRY(cudaMemcpyAsync(out_status, ctx->d_status, sizeof(unsigned) * (size_t)B, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return SEPAIHRD_OK;
+}
+
+sepaihrd_rc sepaihrd_simulate_from_state(sepaihrd_ctx* ctx, const double* params, int64_t B, int64_t ld,
+                                         const double* initial_states, int64_t state_stride, int32_t what, int32_t stride,
+                                         double* out, uint32_t* out_status) {
+    if (!ctx || !out || !initial_states || (B > 0 && !params)) return fail(SEPAIHRD_ERR_INVALID_ARGUMENT, "null argument");
+    if (B < 0 || ld < ctx->P) return fail(SEPAIHRD_ERR_INVALID_ARGUMENT, "Parameter vector size mismatch.");
+    if (stride < 1) return fail(SEPAIHRD_ERR_INVALID_ARGUMENT, "stride must be >= 1");
+    if (state_stride != 0 && state_stride < (int64_t)SEPAIHRD_NUM_COMPARTMENTS * ctx->n)
+        return fail(SEPAIHRD_ERR_INVALID_ARGUMENT, "Initial state size does not match model state size.");   // Simulator.cpp:64-69
+    if (B == 0) return SEPAIHRD_OK;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const int W = (what == SEPAIHRD_TRAJ_FULL) ? SEPAIHRD_NUM_COMPARTMENTS * ctx->n : 3 * ctx->n;
+    const size_t rows = (size_t)(ctx->K + stride - 1) / stride;
+    const size_t total = (size_t)B * rows * W;
+    const size_t n_init = (state_stride == 0) ? (size_t)SEPAIHRD_NUM_COMPARTMENTS * ctx->n : (size_t)B * state_stride;
+    sepaihrd_rc rc;
+    if ((rc = grow(&ctx->d_params, &ctx->cap_params, (size_t)B * ld + n_init)) != SEPAIHRD_OK) return rc;
+    if ((rc = grow(&ctx->d_out, &ctx->cap_out, total)) != SEPAIHRD_OK) return rc;
+    if ((rc = grow(&ctx->d_status, &ctx->cap_status, (size_t)B)) != SEPAIHRD_OK) return rc;
+    double* d_init = ctx->d_params + (size_t)B * ld;
+    CUDA_TRY(cudaMemcpyAsync(ctx->d_params, params, sizeof(double) * (size_t)B * ld, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(d_init, initial_states, sizeof(double) * n_init, cudaMemcpyHostToDevice, ctx->stream));
+    rc = simulate_device_impl(ctx, ctx->d_params, B, ld, d_init, state_stride, what, stride, ctx->d_out, ctx->d_status);
     if (rc != SEPAIHRD_OK) return rc;
     CUDA_TRY(cudaMemcpyAsync(out, ctx->d_out, sizeof(double) * total, cudaMemcpyDeviceToHost, ctx->stream));
     if (out_status) CUDA_TRY(cudaMemcpyAsync(out_status, ctx->d_status, sizeof(unsigned) * (size_t)B, cudaMemcpyDeviceToHost, ctx->stream));

@@ -66,6 +66,8 @@ struct KParams {
     int* out_steps;            // [B][2] or null
     double* out_traj;          // MODE_TRAJ: [B][traj_rows][W]
     int traj_what, traj_stride, traj_rows;
+    const double* init_states; // optional [B][11n] (or one shared state when init_stride == 0): Simulator::run semantics
+    long long init_stride;
     long long tiles;           // ceil(B / sets_per_block)
 };
 
@@ -529,7 +531,12 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) sepaihrd_batch_kernel(cons
         // ---- initial state (ObjectiveFunction.cpp:124-163) -------------------------------------------
         double x[NCOMP], k1[NCOMP];
         const double popN = sblob[kp.o_pop + age];
-        {
+        if (kp.init_states != nullptr) {
+            // Simulator::run(initial_state, times): the caller's state is integrated as given (Simulator.cpp:60-150)
+            const double* st0 = kp.init_states + b * kp.init_stride;
+#pragma unroll
+            for (int c = 0; c < NCOMP; ++c) x[c] = st0[c * n + age];
+        } else {
             const double runup_days = my_slots[sl_runup], seed_exposed = my_slots[sl_seed];
             if (runup_days > 0 && seed_exposed > 0) {
                 x[1] = O::mul(seed_exposed, sblob[kp.o_agefrac + age]);

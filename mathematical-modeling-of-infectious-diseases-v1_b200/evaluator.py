@@ -133,6 +133,32 @@ class BatchEvaluator:
         return out, st
 
 
+def _simulate_from_state(self, params, initial_states, what: int = TRAJ_FULL, stride: int = 1):
+    """Batched Simulator::run(initial_state, times): ``initial_states`` is [11n] (shared) or [B, 11n]."""
+    p = self.problem
+    x = np.ascontiguousarray(params, dtype=np.float64)
+    s0 = np.ascontiguousarray(initial_states, dtype=np.float64)
+    B, ld = x.shape
+    if s0.ndim == 1:
+        sstride = 0
+    else:
+        if s0.shape[0] != B:
+            raise ValueError("one initial state per parameter set (or a single shared state)")
+        sstride = s0.shape[1]
+    if s0.shape[-1] != p.state_size:
+        raise ValueError("Initial state size does not match model state size.")
+    W = p.state_size if what == TRAJ_FULL else 3 * p.n_ages
+    rows = (p.n_times + stride - 1) // stride
+    out = np.empty((B, rows, W))
+    st = np.zeros(B, dtype=np.uint32)
+    capi.check(self._lib.sepaihrd_simulate_from_state(self._h, x.ctypes.data, B, ld, s0.ctypes.data, sstride, int(what),
+                                                      int(stride), out.ctypes.data, st.ctypes.data))
+    return out, st
+
+
+BatchEvaluator.simulate_from_state = _simulate_from_state
+
+
 def measure_fp64_peak(device: int = 0) -> float:
     """Measured FP64 pipe peak in DFMA instructions per second (lane-ops): roofline denominator."""
     v = C.c_double()

@@ -52,6 +52,9 @@ def lib():
         L.sepaihrd_oracle_simulate_batch.restype = C.c_int32
         L.sepaihrd_oracle_simulate_batch.argtypes = [C.c_void_p, _dp, C.c_int64, C.c_int64, C.c_int32, C.c_int32,
                                                      _dp, C.POINTER(C.c_uint32), C.c_int32]
+        L.sepaihrd_oracle_simulate_from_state.restype = C.c_int32
+        L.sepaihrd_oracle_simulate_from_state.argtypes = [C.c_void_p, _dp, C.c_int64, C.c_int64, _dp, C.c_int64, C.c_int32,
+                                                          C.c_int32, _dp, C.POINTER(C.c_uint32), C.c_int32]
         L.sepaihrd_oracle_jitter_params.restype = None
         L.sepaihrd_oracle_jitter_params.argtypes = [C.c_void_p, _dp, _dp, C.c_uint32, C.c_int64, _dp]
         L.sepaihrd_oracle_uniform_params.restype = None
@@ -127,6 +130,18 @@ class Oracle:
         out = np.empty((B, Kout, W)); st = np.zeros(B, dtype=np.uint32)
         self.L.sepaihrd_oracle_simulate_batch(self._ref, _p(x), B, ld, int(what), int(stride), _p(out),
                                               st.ctypes.data_as(C.POINTER(C.c_uint32)), int(nthreads))
+        return out, st
+
+    def simulate_from_state(self, params, initial_states, what: int = 0, stride: int = 1, nthreads: int = 0):
+        p = self.problem
+        x = _c64(params); s0 = _c64(initial_states)
+        B, ld = x.shape
+        sstride = 0 if s0.ndim == 1 else s0.shape[1]
+        W = p.state_size if what == 0 else 3 * p.n_ages
+        Kout = (p.n_times + stride - 1) // stride
+        out = np.empty((B, Kout, W)); st = np.zeros(B, dtype=np.uint32)
+        self.L.sepaihrd_oracle_simulate_from_state(self._ref, _p(x), B, ld, _p(s0), sstride, int(what), int(stride),
+                                                   _p(out), st.ctypes.data_as(C.POINTER(C.c_uint32)), int(nthreads))
         return out, st
 
     def jitter_params(self, B: int, seed: int = 1, base=None, sigmas=None) -> np.ndarray:

@@ -375,7 +375,7 @@ struct EvalScratch {
 
 // calculate() (.cpp:62-235) with a null cache. traj_out: [K][11n] (optional).
 double eval_one(const sepaihrd_problem* pb, const double* params, uint32_t* status_out, double* traj_out,
-                int32_t* interval_steps, int64_t* counts, EvalScratch& sc) {
+                int32_t* interval_steps, int64_t* counts, EvalScratch& sc, const double* given_state = nullptr) {
     const double LOWEST = std::numeric_limits<double>::lowest();
     const Slots L = slots_of(pb);
     const int n = L.n, K = pb->n_times, dim = NC * n;
@@ -384,7 +384,8 @@ double eval_one(const sepaihrd_problem* pb, const double* params, uint32_t* stat
     sc.slots.resize(L.count());
     if (!build_slots(pb, params, sc.slots.data())) { if (status_out) *status_out = SEPAIHRD_ST_INVALID_PARAM; return LOWEST; }
     double x[MAXS];
-    if (!initial_state(pb, sc.slots.data(), x)) { if (status_out) *status_out = SEPAIHRD_ST_S_OVERFLOW; return LOWEST; }
+    if (given_state) std::memcpy(x, given_state, sizeof(double) * dim);   // Simulator::run(initial_state, ...) (Simulator.cpp:60-150)
+    else if (!initial_state(pb, sc.slots.data(), x)) { if (status_out) *status_out = SEPAIHRD_ST_S_OVERFLOW; return LOWEST; }
     double x0[MAXS];
     std::memcpy(x0, x, sizeof(double) * dim);
 
@@ -572,9 +573,10 @@ int32_t sepaihrd_oracle_eval_batch(const sepaihrd_problem* pb, const double* par
     return used;
 }
 
-int32_t sepaihrd_oracle_simulate_batch(const sepaihrd_problem* pb, const double* params, int64_t B, int64_t ld,
-                                       int32_t what, int32_t stride, double* out, uint32_t* out_status,
-                                       int32_t nthreads) {
+static int32_t simulate_impl(const sepaihrd_problem* pb, const double* params, int64_t B, int64_t ld,
+                             const double* init_states, int64_t init_stride,
+                             int32_t what, int32_t stride, double* out, uint32_t* out_status,
+                             int32_t nthreads) {
     const int n = pb->n_ages, K = pb->n_times, dim = NC * n;
     const int W = (what == SEPAIHRD_TRAJ_FULL) ? dim : 3 * n;
     if (stride < 1) stride = 1;
@@ -593,7 +595,7 @@ int32_t sepaihrd_oracle_simulate_batch(const sepaihrd_problem* pb, const double*
 #pragma omp for schedule(dynamic, 4)
         for (int64_t b = 0; b < B; ++b) {
             uint32_t st = 0;
-            eval_one(pb, params + b * ld, &st, traj.data(), nullptr, nullptr, sc);
+            eval_one(pb, params + b * ld, &st, traj.data(), nullptr, nullptr, sc, init_states ? init_states + b * init_stride : nullptr);
             double* o = out + (size_t)b * Kout * W;
             const bool bad = (st & (SEPAIHRD_ST_S_OVERFLOW | SEPAIHRD_ST_INVALID_PARAM | SEPAIHRD_ST_STEP_FAILURE)) != 0;
             for (int r = 0; r < Kout; ++r) {
@@ -610,6 +612,18 @@ int32_t sepaihrd_oracle_simulate_batch(const sepaihrd_problem* pb, const double*
         }
     }
     return used;
+}
+
+int32_t sepaihrd_oracle_simulate_batch(const sepaihrd_problem* pb, const double* params, int64_t B, int64_t ld,
+                                       int32_t what, int32_t stride, double* out, uint32_t* out_status,
+                                       int32_t nthreads) {
+    return simulate_impl(pb, params, B, ld, nullptr, 0, what, stride, out, out_status, nthreads);
+}
+
+int32_t sepaihrd_oracle_simulate_from_state(const sepaihrd_problem* pb, const double* params, int64_t B, int64_t ld,
+                                            const double* initial_states, int64_t state_stride, int32_t what,
+                                            int32_t stride, double* out, uint32_t* out_status, int32_t nthreads) {
+    return simulate_impl(pb, params, B, ld, initial_states, state_stride, what, stride, out, out_status, nthreads);
 }
 
 void sepaihrd_oracle_jitter_params(const sepaihrd_problem* pb, const double* base, const double* sigmas,

@@ -78,6 +78,12 @@ int32_t sepaihrd_oracle_simulate_batch(const sepaihrd_problem* pb, const double*
                                        int32_t what, int32_t stride, double* out, uint32_t* out_status,
                                        int32_t nthreads);
 
+/* B simulations from caller-supplied initial states (Simulator::run semantics; quirk Q9).
+ * state_stride == 0: one state shared by all sets. */
+int32_t sepaihrd_oracle_simulate_from_state(const sepaihrd_problem* pb, const double* params, int64_t B, int64_t ld,
+                                            const double* initial_states, int64_t state_stride, int32_t what,
+                                            int32_t stride, double* out, uint32_t* out_status, int32_t nthreads);
+
 /* The reference benchmark's jitter recipe (sepaihrd_objective_benchmark_main.cpp:452-460):
  * candidate_i = base_i + sigma_i * N(0,1) from std::mt19937(seed) + std::normal_distribution,
  * then applyConstraints in the problem's mode. out: [B][P]. */

@@ -302,3 +302,20 @@ def test_full_size_properties_one_million_sets(problem, oracle, ev_mod):
 def test_fp64_peak_probe_is_plausible(ev_mod):
     peak = ev_mod.measure_fp64_peak(0)
     assert 5e12 < peak < 4e13        # B200: 148 SMs x 64 DFMA/clk x ~1.9 GHz = 1.8e13
+
+
+def test_simulate_from_caller_supplied_state(problem, oracle, ev_mod):
+    """Simulator::run(initial_state, times): the state is integrated as given (quirk Q9: posterior-predictive and
+    scenario runs share ONE fixed initial state)."""
+    P = oracle.jitter_params(20, seed=31)
+    shared = problem.data_initial_state.copy()
+    per_set = np.tile(shared, (20, 1)) * np.linspace(0.9, 1.1, 20)[:, None]
+    with ev_mod.BatchEvaluator(problem, device=0) as ev:
+        for s0 in (shared, per_set):
+            tr, st = ev.simulate_from_state(P, s0)
+            ref, st_ref = oracle.simulate_from_state(P, s0)
+            np.testing.assert_array_equal(st, st_ref)
+            assert _traj_rel(tr, ref).max() < TRAJ_TIGHT
+            np.testing.assert_array_equal(tr[:, 0, :], np.broadcast_to(s0, (20, problem.state_size)))
+        with pytest.raises(ValueError):
+            ev.simulate_from_state(P, shared[:-1])
