@@ -2,6 +2,7 @@
 // No torch types, no CPU fallback: every compute entry point needs a CUDA device.
 
 #include <algorithm>
+#include <climits>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -88,14 +89,14 @@ sepaihrd_rc grow(T** ptr, size_t* cap, size_t need) {
 
 struct LaunchCfg { int threads, minblocks; };
 
-template <int NA, bool STRICT, int MODE, int THREADS, int MINBLOCKS>
+template <int NA, bool STRICT, int MODE, int THREADS, int MINBLOCKS, int LOOP>
 sepaihrd_rc launch_t(sepaihrd_ctx* ctx, const sepaihrd::KParams& kp_in) {
     using namespace sepaihrd;
     KParams kp = kp_in;
     constexpr int SETS = THREADS / NA;
     kp.tiles = (kp.B + SETS - 1) / SETS;
-    auto kern = sepaihrd_batch_kernel<NA, STRICT, MODE, THREADS, MINBLOCKS>;
-    const size_t smem = (size_t)kp.blob_bytes + sizeof(double) * (SETS * (size_t)(kp.slot_stride + ((kp.seg_stride + 1) & ~1)) + 2 * THREADS) + 16;
+    auto kern = sepaihrd_batch_kernel<NA, STRICT, MODE, THREADS, MINBLOCKS, LOOP>;
+    const size_t smem = (size_t)kp.blob_bytes + sizeof(double) * (SETS * (size_t)(kp.slot_stride + ((kp.seg_stride + 1) & ~1)) + 2 * THREADS + (size_t)NA * THREADS) + 16;
     static bool attr_set[64] = {};   // per device
     if (!attr_set[ctx->device & 63]) {
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -118,9 +119,11 @@ template <int NA, int THREADS, int MINBLOCKS>
 sepaihrd_rc launch_na(sepaihrd_ctx* ctx, const sepaihrd::KParams& kp, int mode) {
     using namespace sepaihrd;
     const bool strict = ctx->math_mode == SEPAIHRD_MATH_STRICT;
-    if (mode == MODE_LL)
-        return strict ? launch_t<NA, true, MODE_LL, THREADS, MINBLOCKS>(ctx, kp) : launch_t<NA, false, MODE_LL, THREADS, MINBLOCKS>(ctx, kp);
-    return strict ? launch_t<NA, true, MODE_TRAJ, THREADS, MINBLOCKS>(ctx, kp) : launch_t<NA, false, MODE_TRAJ, THREADS, MINBLOCKS>(ctx, kp);
+    if (strict)   // STRICT keeps the reference-order loop
+        return (mode == MODE_LL) ? launch_t<NA, true, MODE_LL, THREADS, MINBLOCKS, 5>(ctx, kp)
+                                 : launch_t<NA, true, MODE_TRAJ, THREADS, MINBLOCKS, 5>(ctx, kp);
+    return (mode == MODE_LL) ? launch_t<NA, false, MODE_LL, THREADS, MINBLOCKS, 6>(ctx, kp)
+                             : launch_t<NA, false, MODE_TRAJ, THREADS, MINBLOCKS, 6>(ctx, kp);
 }
 
 sepaihrd_rc launch(sepaihrd_ctx* ctx, const sepaihrd::KParams& kp, int mode) {
@@ -333,6 +336,15 @@ sepaihrd_rc sepaihrd_create(const sepaihrd_problem* pb, int32_t device, sepaihrd
     kp.abs_tol = pb->abs_tol; kp.rel_tol = pb->rel_tol; kp.dt_hint = pb->dt_hint; kp.hmax = ctx->hmax;
     kp.inv_rel = (pb->rel_tol > 0.0) ? 1.0 / pb->rel_tol : 0.0;
     kp.abs_over_rel = (pb->rel_tol > 0.0) ? pb->abs_tol / pb->rel_tol : 0.0;
+    kp.grow_max = 9.0 / 10.0 * std::pow(std::pow(5.0, -5.0), -1.0 / 5);
+    // hi(num) - hi(den) equals log2(num/den) within +-0.0862 (units 2^-20) for normal den; margins on top of that
+    if (kp.abs_over_rel >= 1e-150) {
+        kp.thr_small = (int)std::lround(-11.75 * 1048576.0);    // ratio < 2^-11.66 = 3.09e-4 < 5^-5
+        kp.thr_nogrow = (int)std::lround(-0.90 * 1048576.0);    // ratio > 2^-0.987 = 0.5046 > 1/2
+        kp.thr_big = (int)std::lround(6.65 * 1048576.0);        // ratio > 2^6.56 = 94.6 > (0.9/0.2)^3 = 91.125
+    } else {   // the denominators may be zero/denormal: never trust the coarse classification
+        kp.thr_small = INT_MIN; kp.thr_nogrow = INT_MAX; kp.thr_big = INT_MAX;
+    }
 
     cudaDeviceProp prop;
     cudaError_t e = cudaGetDeviceProperties(&prop, device);

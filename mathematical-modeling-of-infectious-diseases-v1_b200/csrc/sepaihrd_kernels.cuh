@@ -29,6 +29,7 @@
 #pragma once
 
 #include <cfloat>
+#include <climits>
 #include <cstdint>
 #include <cuda_runtime.h>
 
@@ -58,6 +59,9 @@ struct KParams {
     double hmax;               // longest output interval: growing dt beyond it cannot change the result
     double inv_rel;            // 1 / rel_tol          (FAST error norm is evaluated in units of rel_tol)
     double abs_over_rel;       // abs_tol / rel_tol
+    double grow_max;           // 0.9 * pow(pow(5,-5), -1/5): the step-growth factor once err <= 5^-5 (libm, host)
+    // LOOP 6: coarse classification of the error norm from the high words of num/den (units: 2^-20 of a log2)
+    int thr_small, thr_nogrow, thr_big;
     // I/O
     const double* params;      // [B][ld]
     long long B, ld;
@@ -189,6 +193,66 @@ __device__ __forceinline__ double fast_log(double x, const double2* __restrict__
     return fma((double)e, 0.6931471805599453, fma(p, r, t.y));
 }
 
+
+// x^(-1/3) (cubic) or x^(-1/5) in ONE instruction stream: lanes of a warp that shrink a rejected step and lanes
+// that grow an accepted one share the chain instead of diverging into pow_m1_3 / pow_m1_5 back to back.
+__device__ __forceinline__ double pow_neg_inv(double x, bool cubic) {
+    double y = (double)__powf((float)x, cubic ? -0.33333334f : -0.2f);
+    const double xs = x * (cubic ? (1.0 / 3.0) : 0.2);
+    const double cst = cubic ? (4.0 / 3.0) : 1.2;
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+        const double y2 = y * y;
+        const double yn = (cubic ? y2 : (y2 * y2)) * y;
+        y = y * fma(-xs, yn, cst);
+    }
+    return y;
+}
+
+// fast_log without the special-case branch, so that the three Poisson streams of an output day interleave
+// in one basic block.  Inputs outside the positive normal range (the incidence went NaN/inf) raise `bad`;
+// the caller turns that into the reference's non-finite sentinel.
+__device__ __forceinline__ double fast_log_nb(double x, const double2* __restrict__ tab, bool valid, bool& bad) {
+    const int hi = __double2hiint(x);
+    bad |= valid && ((unsigned)(hi - 0x00100000) >= 0x7fe00000u);
+    const int e = (hi >> 20) - 1023;
+    const int i = (hi >> 13) & 0x7f;
+    const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));   // [1, 2)
+    const double2 t = tab[i];
+    const double r = fma(m, t.x, -1.0);
+    double p = fma(r, 0.2, -0.25);
+    p = fma(p, r, 1.0 / 3.0);
+    p = fma(p, r, -0.5);
+    p = fma(p, r, 1.0);
+    return fma((double)e, 0.6931471805599453, fma(p, r, t.y));
+}
+
+// a / b for a normal, positive b: MUFU.RCP64H seed (20 bits), two Newton steps, one residual correction.  Replaces
+// the IEEE division (slow-path check + call) on the error-norm VALUE, which only sizes the next step.
+__device__ __forceinline__ double fast_div_pos(double a, double b) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+    double e = fma(-b, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-b, r, 1.0);
+    r = fma(r, e, r);
+    const double q = a * r;
+    return fma(fma(-b, q, a), r, q);
+}
+
+// OR of every lane group's bits, replicated to all lanes of the group (ballot mask -> group mask).
+template <int NA>
+__device__ __forceinline__ unsigned expand_groups(unsigned m) {
+    if (NA >= 32) return m ? 0xffffffffu : 0u;
+    unsigned y = m;
+#pragma unroll
+    for (int s = 1; s < NA; s *= 2) y |= y >> s;
+    unsigned first = 0;
+#pragma unroll
+    for (int g = 0; g < 32; g += NA) first |= 1u << g;
+    return (y & first) * ((NA >= 32) ? 1u : ((1u << NA) - 1u));
+}
+
 // ---- per-lane model parameters (registers) ----------------------------------------------------------
 template <int NA>
 struct LaneParams {
@@ -219,9 +283,14 @@ __device__ __forceinline__ void gather_pressure(double* spi, int slot_base, int 
 // AgeSEPAIHRDModel::computeDerivatives for one age class (this lane), inputs y = S E P A I H ICU.
 // Outputs: dyn = d(S E P A I H ICU), pas = d(R D CumH CumICU).
 // PASSIVE=false skips pas (stage 2: Dopri5 has c2 = dc2 = 0).
-template <int NA, bool STRICT, bool PASSIVE>
+// FAST: q.M is the FOLDED row M(age, j) * h_infec_j / N_j * (beta*kappa*a_age) of the schedule segment the step
+// runs in, so the lanes exchange u_j = P_j + A_j + theta I_j and lambda is one short dot product (two partial sums).
+// FOLDED=false (a step whose stages sit in different segments; never on the Spain-2020 grid) takes the unfolded
+// row M(age, j) h_infec_j / N_j from shared memory (`mb`, thread-strided) and multiplies by `ba`.
+template <int NA, bool STRICT, bool PASSIVE, bool FOLDED = true>
 __device__ __forceinline__ void rhs(const LaneParams<NA>& q, double ba, double* spi, int slot_base, int lane_in_block,
-                                    const double (&y)[NDYN], double (&dyn)[NDYN], double (&pas)[NPAS]) {
+                                    const double (&y)[NDYN], double (&dyn)[NDYN], double (&pas)[NPAS],
+                                    const double* mb = nullptr, int mb_stride = 0) {
     using O = Ops<STRICT>;
     const double S = y[0], E = y[1], P = y[2], A = y[3], I = y[4], H = y[5], U = y[6];
     double pressure;
@@ -229,14 +298,27 @@ __device__ __forceinline__ void rhs(const LaneParams<NA>& q, double ba, double* 
         const double total_inf = O::add(O::add(P, A), O::mul(q.theta, I));   // :155
         pressure = O::mul(O::mul(total_inf, q.hinf), q.invN);                // :156
     } else {
-        pressure = fma(q.theta, I, P + A) * q.hN;
+        pressure = fma(q.theta, I, P + A);
     }
     double pall[NA];
     gather_pressure<NA>(spi, slot_base, lane_in_block, pressure, pall);
-    double lam = 0.0;                                                        // :162-174 (j outer, in order)
+    double lam;
+    if (STRICT) {
+        lam = 0.0;                                                           // :162-174 (j outer, in order)
 #pragma unroll
-    for (int j = 0; j < NA; ++j) lam = O::mad(q.M[j], pall[j], lam);
-    lam = O::mul(lam, ba);                                                   // :181-183, ba = (beta*kappa)*a_i
+        for (int j = 0; j < NA; ++j) lam = O::mad(q.M[j], pall[j], lam);
+        lam = O::mul(lam, ba);                                               // :181-183, ba = (beta*kappa)*a_i
+    } else {
+        constexpr int NACC = (NA >= 16) ? 4 : 2;
+        double acc[NACC];
+#pragma unroll
+        for (int j = 0; j < NA; ++j) {
+            const double m = FOLDED ? q.M[j] : mb[j * mb_stride];
+            acc[j % NACC] = (j < NACC) ? m * pall[j] : fma(m, pall[j], acc[j % NACC]);
+        }
+        lam = (NACC == 4) ? (acc[0] + acc[1]) + (acc[2] + acc[3]) : acc[0] + acc[1];
+        if (!FOLDED) lam *= ba;
+    }
     if (STRICT) {
         lam = (0.0 < lam) ? lam : 0.0;                                       // std::max(0.0, lambda) :196
     } else {
@@ -341,6 +423,8 @@ struct StepSched {
     const double* beff;   // this set's beta*kappa per segment (shared memory)
     int nseg;
     double a;
+    const double* mb;     // FAST: this lane's unfolded row M(age, j) h_infec_j / N_j in shared memory, stride mb_stride
+    int mb_stride;
 };
 
 template <int NA, bool STRICT, bool MIXED>
@@ -364,12 +448,12 @@ __device__ __forceinline__ void dopri5_attempt(const LaneParams<NA>& q, const St
     { const double f1 = O::mul(cur, c_tab[T_B21]);
 #pragma unroll
       for (int c = 0; c < NDYN; ++c) y[c] = O::mad(f1, k1[c], x[c]); }
-    rhs<NA, STRICT, false>(q, ba_at(T_A2), spi, next_slot(), lane_in_block, y, k2, kp_);
+    rhs<NA, STRICT, false, !MIXED>(q, ba_at(T_A2), spi, next_slot(), lane_in_block, y, k2, kp_, sc.mb, sc.mb_stride);
     // stage 3
     { const double f1 = O::mul(cur, c_tab[T_B31]), f2 = O::mul(cur, c_tab[T_B32]);
 #pragma unroll
       for (int c = 0; c < NDYN; ++c) y[c] = O::mad(f2, k2[c], O::mad(f1, k1[c], x[c])); }
-    rhs<NA, STRICT, true>(q, ba_at(T_A3), spi, next_slot(), lane_in_block, y, k3, kp_);
+    rhs<NA, STRICT, true, !MIXED>(q, ba_at(T_A3), spi, next_slot(), lane_in_block, y, k3, kp_, sc.mb, sc.mb_stride);
     { const double g1 = O::mul(cur, c_tab[T_C1]), g3 = O::mul(cur, c_tab[T_C3]);
       const double e1 = O::mul(ecur, c_tab[T_DC1]), e3 = O::mul(ecur, c_tab[T_DC3]);
 #pragma unroll
@@ -381,7 +465,7 @@ __device__ __forceinline__ void dopri5_attempt(const LaneParams<NA>& q, const St
     { const double f1 = O::mul(cur, c_tab[T_B41]), f2 = O::mul(cur, c_tab[T_B42]), f3 = O::mul(cur, c_tab[T_B43]);
 #pragma unroll
       for (int c = 0; c < NDYN; ++c) y[c] = O::mad(f3, k3[c], O::mad(f2, k2[c], O::mad(f1, k1[c], x[c]))); }
-    rhs<NA, STRICT, true>(q, ba_at(T_A4), spi, next_slot(), lane_in_block, y, k4, kp_);
+    rhs<NA, STRICT, true, !MIXED>(q, ba_at(T_A4), spi, next_slot(), lane_in_block, y, k4, kp_, sc.mb, sc.mb_stride);
     { const double g4 = O::mul(cur, c_tab[T_C4]), e4 = O::mul(ecur, c_tab[T_DC4]);
 #pragma unroll
       for (int c = 0; c < NPAS; ++c) { accN[c] = O::mad(g4, kp_[c], accN[c]); accE[c] = O::mad(e4, kp_[c], accE[c]); } }
@@ -391,7 +475,7 @@ __device__ __forceinline__ void dopri5_attempt(const LaneParams<NA>& q, const St
 #pragma unroll
       for (int c = 0; c < NDYN; ++c)
           y[c] = O::mad(f4, k4[c], O::mad(f3, k3[c], O::mad(f2, k2[c], O::mad(f1, k1[c], x[c])))); }
-    rhs<NA, STRICT, true>(q, ba_at(T_A5), spi, next_slot(), lane_in_block, y, k5, kp_);
+    rhs<NA, STRICT, true, !MIXED>(q, ba_at(T_A5), spi, next_slot(), lane_in_block, y, k5, kp_, sc.mb, sc.mb_stride);
     { const double g5 = O::mul(cur, c_tab[T_C5]), e5 = O::mul(ecur, c_tab[T_DC5]);
 #pragma unroll
       for (int c = 0; c < NPAS; ++c) { accN[c] = O::mad(g5, kp_[c], accN[c]); accE[c] = O::mad(e5, kp_[c], accE[c]); } }
@@ -401,7 +485,7 @@ __device__ __forceinline__ void dopri5_attempt(const LaneParams<NA>& q, const St
 #pragma unroll
       for (int c = 0; c < NDYN; ++c)
           y[c] = O::mad(f5, k5[c], O::mad(f4, k4[c], O::mad(f3, k3[c], O::mad(f2, k2[c], O::mad(f1, k1[c], x[c]))))); }
-    rhs<NA, STRICT, true>(q, ba_at(-1), spi, next_slot(), lane_in_block, y, k6, kp_);
+    rhs<NA, STRICT, true, !MIXED>(q, ba_at(-1), spi, next_slot(), lane_in_block, y, k6, kp_, sc.mb, sc.mb_stride);
     { const double g6 = O::mul(cur, c_tab[T_C6]), e6 = O::mul(ecur, c_tab[T_DC6]);
 #pragma unroll
       for (int c = 0; c < NPAS; ++c) { accN[c] = O::mad(g6, kp_[c], accN[c]); accE[c] = O::mad(e6, kp_[c], accE[c]); } }
@@ -411,7 +495,7 @@ __device__ __forceinline__ void dopri5_attempt(const LaneParams<NA>& q, const St
 #pragma unroll
       for (int c = 0; c < NDYN; ++c)
           xn[c] = O::mad(g6, k6[c], O::mad(g5, k5[c], O::mad(g4, k4[c], O::mad(g3, k3[c], O::mad(g1, k1[c], x[c]))))); }
-    rhs<NA, STRICT, true>(q, ba_at(-1), spi, next_slot(), lane_in_block, xn, k7d, k7p);
+    rhs<NA, STRICT, true, !MIXED>(q, ba_at(-1), spi, next_slot(), lane_in_block, xn, k7d, k7p, sc.mb, sc.mb_stride);
     // error estimate
     { const double e1 = O::mul(ecur, c_tab[T_DC1]), e3 = O::mul(ecur, c_tab[T_DC3]), e4 = O::mul(ecur, c_tab[T_DC4]),
                    e5 = O::mul(ecur, c_tab[T_DC5]), e6 = O::mul(ecur, c_tab[T_DC6]), e7 = O::mul(ecur, c_tab[T_DC7]);
@@ -427,8 +511,9 @@ __device__ __forceinline__ void dopri5_attempt(const LaneParams<NA>& q, const St
 // groups that have already reached the next output time run the attempt with a zero-length step and
 // discard it), so every shuffle is a plain full-mask SHFL.  This is the "regroup at output-day
 // boundaries" policy: a warp spends max-over-its-groups attempts per output interval.
-template <int NA, bool STRICT, int MODE, int THREADS, int MINBLOCKS>
+template <int NA, bool STRICT, int MODE, int THREADS, int MINBLOCKS, int LOOP>
 __global__ void __launch_bounds__(THREADS, MINBLOCKS) sepaihrd_batch_kernel(const KParams kp) {
+    static_assert(STRICT ? LOOP == 5 : LOOP == 6, "STRICT keeps the reference-order loop 5; FAST runs loop 6");
     using O = Ops<STRICT>;
     constexpr int SETS = THREADS / NA;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -437,7 +522,8 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) sepaihrd_batch_kernel(cons
     double* sslots = sblob + blob_doubles;
     double* sbeff = sslots + SETS * kp.slot_stride;
     double* spi = sbeff + SETS * ((kp.seg_stride + 1) & ~1);            // 2 x THREADS doubles, 16-byte aligned
-    uint64_t* bar = reinterpret_cast<uint64_t*>(spi + 2 * THREADS);
+    double* smb = spi + 2 * THREADS;                                    // NA x THREADS doubles: unfolded contact rows (FAST)
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smb + NA * THREADS);
 
     // ---- stage the constants blob once per block with one TMA bulk copy -----------------------------
     if (threadIdx.x == 0) {
@@ -527,6 +613,17 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) sepaihrd_batch_kernel(cons
         q.kU = q.gamma_ICU + q.dICU;
 #pragma unroll
         for (int j = 0; j < NA; ++j) q.M[j] = sblob[kp.o_M + j * n + age];   // column-major M(age, j)
+        int mseg = -1;                 // FAST: schedule segment q.M is currently folded for
+        if (!STRICT) {
+#pragma unroll
+            for (int j = 0; j < NA; ++j) smb[j * THREADS + threadIdx.x] = q.M[j] * __shfl_sync(FULL, q.hN, j, NA);
+        }
+        auto refold = [&](int s) {     // q.M[j] = M(age, j) h_infec_j / N_j * (beta*kappa)(segment s) * a_age
+            const double f = my_beff[s] * q.a;
+#pragma unroll
+            for (int j = 0; j < NA; ++j) q.M[j] = smb[j * THREADS + threadIdx.x] * f;
+            mseg = s;
+        };
 
         // ---- initial state (ObjectiveFunction.cpp:124-163) -------------------------------------------
         double x[NCOMP], k1[NCOMP];
@@ -585,6 +682,7 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) sepaihrd_batch_kernel(cons
 #pragma unroll
             for (int c = 0; c < NDYN; ++c) y0[c] = x[c];
             pi_slot ^= THREADS;
+            if (!STRICT) refold(seg);
             rhs<NA, STRICT, true>(q, ba, spi, pi_slot, threadIdx.x, y0, d0, p0);
 #pragma unroll
             for (int c = 0; c < NDYN; ++c) k1[c] = d0[c];
@@ -592,6 +690,169 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) sepaihrd_batch_kernel(cons
             for (int c = 0; c < NPAS; ++c) k1[NDYN + c] = p0[c];
         }
 
+        if constexpr (LOOP == 6 && !STRICT) {
+        // ================= LOOP 6 (FAST): one short decision section per attempt ============================
+        // Same arithmetic as the loop below; what changes is the control flow around the attempt body:
+        //  * a finished lane group idles with a ZERO-length step (cur = 0), so nothing in the body is predicated;
+        //  * accept/reject is decided by exact compares (num > den); the VALUE of the error norm is needed only to
+        //    size the next step, and three cases need no value at all.  They are recognised from the high words of
+        //    num and den (hi(num) - hi(den) = log2(num/den) within +-0.0862, in units of 2^-20):
+        //       every ratio surely <= 5^-5   -> growth factor is the constant 0.9 * (5^-5)^(-1/5)
+        //       some ratio surely  >= 0.5    -> accepted step does not grow
+        //       some ratio surely  >= 91.2   -> rejected step shrinks by exactly 1/5
+        //    only the remaining groups run the tournament + division + power (one shared instruction stream);
+        //  * all votes of an attempt are independent of each other (issued back to back), the loop-continuation
+        //    mask is derived from them with uniform integer arithmetic;
+        //  * the three Poisson streams of an output day are evaluated branch-free in one basic block.
+        bool bad = false;                                   // a scored likelihood term saw a NaN/inf incidence
+        int fail_steps = 0;
+        const unsigned lane_bit = 1u << (threadIdx.x & 31);
+        for (int idx = 0; idx < K; ++idx) {
+            t = s_times[idx];
+            if (MODE == MODE_TRAJ) {
+                if (have && alive && (idx % kp.traj_stride == 0)) {
+                    double* row = traj_out + (size_t)(idx / kp.traj_stride) * W;
+                    if (kp.traj_what == SEPAIHRD_TRAJ_FULL) {
+#pragma unroll
+                        for (int c = 0; c < NCOMP; ++c) row[c * n + age] = x[c];
+                    } else {
+                        row[0 * n + age] = x[8]; row[1 * n + age] = x[9]; row[2 * n + age] = x[10];
+                    }
+                }
+            } else {
+                const double inc_h = std_max(x[9] - prev_h, 0.0);
+                const double inc_i = std_max(x[10] - prev_i, 0.0);
+                const double inc_d = std_max(x[8] - prev_d, 0.0);
+                prev_h = x[9]; prev_i = x[10]; prev_d = x[8];
+                const int r = idx - kp.runup_offset;
+                if (r >= 0) {
+                    const double oh = s_obs_h[r * n + age], oi = s_obs_i[r * n + age], od = s_obs_d[r * n + age];
+                    const bool vh = (oh >= 0.0), vi = (oi >= 0.0), vd = (od >= 0.0);   // skipped observations are stored as -1
+                    const double sh = inc_h + 1e-10, si = inc_i + 1e-10, sd = inc_d + 1e-10;
+                    const double th = fma(oh, fast_log_nb(sh, s_logtab, vh, bad), -sh);
+                    const double ti = fma(oi, fast_log_nb(si, s_logtab, vi, bad), -si);
+                    const double td = fma(od, fast_log_nb(sd, s_logtab, vd, bad), -sd);
+                    ll_acc_h += ((vh ? th : 0.0) + (vi ? ti : 0.0)) + (vd ? td : 0.0);
+                }
+            }
+            if (idx + 1 == K) break;
+            const double t_next = s_times[idx + 1];
+            double rem = t_next - t;
+            bool active = alive && (rem > DBL_EPSILON);            // less_with_sign(t, t_next, dt)
+            unsigned m_active = __ballot_sync(FULL, active);
+            if (m_active == 0) {
+                if (!__any_sync(FULL, alive)) break;
+                continue;
+            }
+            // a breakpoint inside [t, t_next): attempts of this day may leave their schedule segment
+            const bool day_bp = __any_sync(FULL, bp_next < t_next);
+            while (true) {
+                const double cur = active ? std_min(dt, rem) : 0.0;   // min_abs(dt, t_next - t)
+                const double t_end = t + cur;
+                const unsigned m_more = __ballot_sync(FULL, active && ((t_next - t_end) > DBL_EPSILON));
+                const unsigned m_low = __ballot_sync(FULL, dt < hmax);
+                StepSched sc;
+                sc.ba_step = ba; sc.s_lo = seg; sc.bp = s_bp; sc.beff = my_beff; sc.nseg = nseg; sc.a = q.a;
+                sc.mb = smb + threadIdx.x; sc.mb_stride = THREADS;
+                int s_hi = seg;
+                bool run_mixed = false;
+                if (day_bp) {
+                    if (__any_sync(FULL, !(t_end <= bp_next))) {
+                        bool mixed = false;
+                        if (!(t_end <= bp_next)) {
+                            const double t2 = fma(cur, c_tab[T_A2], t);
+                            int s_lo = seg;
+                            while (s_lo < nseg && t2 > s_bp[s_lo]) ++s_lo;
+                            s_hi = s_lo;
+                            while (s_hi < nseg && t_end > s_bp[s_hi]) ++s_hi;
+                            mixed = (s_lo != s_hi);
+                            sc.s_lo = s_lo;
+                            sc.ba_step = my_beff[s_lo] * q.a;
+                            if (s_lo != mseg) refold(s_lo);   // stages 2..7 of a step that starts ON a breakpoint (quirk Q2)
+                        }
+                        run_mixed = __any_sync(FULL, mixed);
+                    }
+                }
+                double xn[NDYN], k7d[NDYN], k7p[NPAS], accN[NPAS], xe[NCOMP];
+                const double ecur = cur * kp.inv_rel;
+                if (run_mixed)
+                    dopri5_attempt<NA, false, true>(q, sc, spi, pi_slot, THREADS, threadIdx.x, t, cur, t_end, x, k1, xn, k7d, k7p, accN, xe, ecur);
+                else
+                    dopri5_attempt<NA, false, false>(q, sc, spi, pi_slot, THREADS, threadIdx.x, t, cur, t_end, x, k1, xn, k7d, k7p, accN, xe, ecur);
+                // ---- decision: exact compares; coarse magnitude of the worst ratio from the high words ---------
+                double num[NCOMP], den[NCOMP];
+                bool big0 = false, big1 = false, big2 = false;
+                int lm0 = INT_MIN, lm1 = INT_MIN;
+#pragma unroll
+                for (int c = 0; c < NCOMP; ++c) {
+                    num[c] = fabs(xe[c]);
+                    den[c] = fma(cur, fabs(k1[c]), fabs(x[c])) + kp.abs_over_rel;
+                    const bool g = num[c] > den[c];
+                    if (c % 3 == 0) big0 |= g; else if (c % 3 == 1) big1 |= g; else big2 |= g;
+                    const int l = __double2hiint(num[c]) - __double2hiint(den[c]);
+                    if (c & 1) lm1 = max(lm1, l); else lm0 = max(lm0, l);
+                }
+                const int lmax = max(lm0, lm1);
+                const unsigned bal_big = __ballot_sync(FULL, big0 | big1 | big2);
+                const unsigned bal_ng = __ballot_sync(FULL, lmax > kp.thr_nogrow);
+                const unsigned bal_ns = __ballot_sync(FULL, !(lmax < kp.thr_small));
+                const unsigned bal_sb = __ballot_sync(FULL, lmax > kp.thr_big);
+                const unsigned g_rej = expand_groups<NA>(bal_big) & m_active;
+                const unsigned g_ng = expand_groups<NA>(bal_ng), g_ns = expand_groups<NA>(bal_ns), g_sb = expand_groups<NA>(bal_sb);
+                const unsigned m_val = (g_rej & ~g_sb) | (m_active & ~g_rej & m_low & g_ns & ~g_ng);
+                const bool reject = (g_rej & lane_bit) != 0;
+                double err = 0.0, facv = 0.0;
+                if (m_val != 0) {
+                    // arg-max of num/den by a cross-multiplication tournament, then ONE exact division per lane
+#pragma unroll
+                    for (int stride = 1; stride < NCOMP; stride *= 2) {
+#pragma unroll
+                        for (int c = 0; c + stride < NCOMP; c += 2 * stride) {
+                            const bool other = num[c + stride] * den[c] > num[c] * den[c + stride];
+                            num[c] = other ? num[c + stride] : num[c];
+                            den[c] = other ? den[c + stride] : den[c];
+                        }
+                    }
+                    err = group_max<NA>(fast_div_pos(num[0], den[0]));
+                    // decrease_step: 0.9 err^(-1/3) (error_order 4);  increase_step: 0.9 max(5^-5, err)^(-1/5) (stepper_order 5)
+                    facv = 0.9 * pow_neg_inv(reject ? err : std_max(3.2e-4 /* pow(5,-5) */, err), reject);
+                }
+                unsigned m_dead = 0;
+                if (reject) {
+                    const double shrink = ((g_sb & lane_bit) || err > 128.0) ? 0.2 : std_max(facv, 0.2);   // 0.9 err^(-1/3) < 0.2 beyond 91.2
+                    dt = cur * shrink;
+                    ++n_rej;
+                    if (fail_steps++ >= 500) { status |= SEPAIHRD_ST_STEP_FAILURE; alive = false; }
+                } else if (active) {
+                    t = t_end;
+                    rem = t_next - t;
+                    if (dt < hmax) {
+                        double g = 0.0;                                  // err >= 0.5: the step is kept
+                        if (!(g_ns & lane_bit)) g = kp.grow_max;          // err <= 5^-5
+                        else if (!(g_ng & lane_bit) && err < 0.5) g = facv;
+                        dt = std_max(dt, cur * g);                       // max_abs(carried, proposed)
+                    }
+                    ++n_acc;
+                    fail_steps = 0;
+                    if (s_hi != seg) {
+                        seg = s_hi;
+                        bp_next = (seg < nseg) ? s_bp[seg] : INF;
+                        ba = my_beff[seg] * q.a;
+                        if (seg != mseg) refold(seg);
+                    }
+#pragma unroll
+                    for (int c = 0; c < NDYN; ++c) { x[c] = xn[c]; k1[c] = k7d[c]; }
+#pragma unroll
+                    for (int c = 0; c < NPAS; ++c) { x[NDYN + c] = accN[c]; k1[NDYN + c] = k7p[c]; }
+                }
+                if (g_rej != 0) m_dead = __ballot_sync(FULL, !alive);   // only a rejection can exhaust the failed-step budget
+                m_active = (m_more | g_rej) & ~m_dead;
+                if (m_active == 0) break;
+                active = (m_active & lane_bit) != 0;
+            }
+        }
+        if (bad) ll_acc_h = __longlong_as_double(0x7ff8000000000000LL);
+        } else {
         for (int idx = 0; idx < K; ++idx) {
             t = s_times[idx];
             // ---- observer -----------------------------------------------------------------------------
@@ -661,6 +922,7 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) sepaihrd_batch_kernel(cons
                 const unsigned flags = __reduce_or_sync(FULL, ((need && dt < hmax) ? 1u : 0u) | ((t_end <= bp_next) ? 0u : 2u));
                 StepSched sc;
                 sc.ba_step = ba; sc.s_lo = seg; sc.bp = s_bp; sc.beff = my_beff; sc.nseg = nseg; sc.a = q.a;
+                sc.mb = nullptr; sc.mb_stride = 0;
                 int s_hi = seg;
                 bool run_mixed = false;
                 if (flags & 2u) {
@@ -765,6 +1027,8 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) sepaihrd_batch_kernel(cons
             }
             if (!__any_sync(FULL, alive)) break;
         }
+
+        }   // LOOP
 
         // ---- epilogue -------------------------------------------------------------------------------------
         if (MODE == MODE_LL) {
