@@ -1,0 +1,361 @@
+// epidemic_host.hpp -- C++ host mirror of the reference's plugin interfaces for the SEPAIHRD hot path.
+//
+// Same names, argument meaning and error behaviour as the reference classes they stand in for, so that the
+// reference's calibrators can be pointed at the B200 evaluator without source changes beyond the include
+// path.  Everything numerical happens behind the C ABI of include/sepaihrd_b200.h; there is
+// no CPU implementation of the right-hand side, the solver or the likelihood in this directory.
+//
+// Reference files mirrored (paths relative to the reference repository):
+//   include/sir_age_structured/interfaces/{IObjectiveFunction,IParameterManager,IOdeSolverStrategy,
+//       ISimulationCache,IOptimizationAlgorithm}.hpp
+//   include/sir_age_structured/SimulationResult.hpp, include/exceptions/Exceptions.hpp
+//   include/model/parameters/{SEPAIHRDParameters,SEPAIHRDParameterManager}.hpp
+//   include/model/{AgeSEPAIHRDModel,AgeSEPAIHRDsimulator,PieceWiseConstantNPIStrategy,SEPAIHRDModelCalibration}.hpp
+//   include/model/objectives/SEPAIHRDObjectiveFunction.hpp, include/utils/GetCalibrationData.hpp
+#pragma once
+
+#include <cstdint>
+#include <functional>
+#include <limits>
+#include <map>
+#include <memory>
+#include <optional>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "linalg.hpp"
+#include "sepaihrd_b200.h"
+
+namespace epidemic {
+
+// ---- exceptions (include/exceptions/Exceptions.hpp) ------------------------------------------------------
+class ModelException : public std::runtime_error {
+public:
+    ModelException(const std::string& source, const std::string& message)
+        : std::runtime_error("[" + source + "] " + message) {}
+};
+class InvalidParameterException : public ModelException { using ModelException::ModelException; };
+class SimulationException : public ModelException { using ModelException::ModelException; };
+class ModelConstructionException : public ModelException { using ModelException::ModelException; };
+class InvalidResultException : public ModelException { using ModelException::ModelException; };
+class OutOfRangeException : public ModelException { using ModelException::ModelException; };
+
+// ---- SEPAIHRDParameters (include/model/parameters/SEPAIHRDParameters.hpp:12-115) ---------------------------
+struct SEPAIHRDParameters {
+    VectorXd N;
+    MatrixXd M_baseline;
+    double contact_matrix_scaling_factor = 1.0;
+    double beta = std::numeric_limits<double>::quiet_NaN();   // quirk Q1: never read when a beta schedule exists
+    std::vector<double> beta_end_times, beta_values;
+    VectorXd a, h_infec;
+    double theta = 0, sigma = 0, gamma_p = 0, gamma_A = 0, gamma_I = 0, gamma_H = 0, gamma_ICU = 0;
+    VectorXd p, h, icu, d_H, d_ICU;
+    std::vector<double> kappa_end_times, kappa_values;
+    double E0_multiplier = 1, P0_multiplier = 1, A0_multiplier = 1, I0_multiplier = 1, H0_multiplier = 1,
+           ICU0_multiplier = 1, R0_multiplier = 1, D0_multiplier = 1;
+    double runup_days = 30.0, seed_exposed = 10.0;
+    VectorXd d_community;
+    bool validate() const;
+};
+
+// ---- NPI strategy (include/model/PieceWiseConstantNPIStrategy.hpp) ----------------------------------------
+class INpiStrategy {
+public:
+    virtual ~INpiStrategy() = default;
+    virtual double getReductionFactor(double time) const = 0;
+    virtual const std::vector<double>& getEndTimes() const = 0;
+    virtual std::vector<double> getValues() const = 0;
+    virtual void setValues(const std::vector<double>& new_values) = 0;
+    virtual std::shared_ptr<INpiStrategy> clone() const = 0;
+};
+
+class PiecewiseConstantNpiStrategy : public INpiStrategy {
+public:
+    PiecewiseConstantNpiStrategy(const std::vector<double>& npi_end_times_after_baseline,
+                                 const std::vector<double>& npi_values_after_baseline,
+                                 const std::map<std::string, std::pair<double, double>>& param_specific_bounds = {},
+                                 double baseline_kappa = 1.0, double baseline_period_end_time = 0.0,
+                                 bool fixed_baseline = true,
+                                 const std::vector<std::string>& param_names_for_npi_values = {});
+    double getReductionFactor(double time) const override;          // src/model/PieceWiseConstantNPIStrategy.cpp:86-127
+    const std::vector<double>& getEndTimes() const override { return npi_period_end_times_; }
+    std::vector<double> getValues() const override;
+    void setValues(const std::vector<double>& new_values) override;
+    std::shared_ptr<INpiStrategy> clone() const override { return std::make_shared<PiecewiseConstantNpiStrategy>(*this); }
+    double getBaselineKappa() const { return baseline_kappa_value_; }
+    double getBaselinePeriodEndTime() const { return baseline_period_end_time_; }
+    bool isBaselineFixed() const { return is_baseline_fixed_; }
+    size_t getNumCalibratableNpiParams() const;
+    std::string getNpiParamName(int calibratable_idx) const;
+    void setCalibratableValues(const std::vector<double>& calibratable_values);   // .cpp:228-262 (throws on negatives)
+    std::vector<double> getCalibratableValues() const;
+    double getLowerBoundForParamIndex(int calibratable_idx) const;
+    double getUpperBoundForParamIndex(int calibratable_idx) const;
+
+private:
+    double baseline_kappa_value_;
+    bool is_baseline_fixed_;
+    double baseline_period_end_time_;
+    std::vector<double> npi_period_end_times_, npi_kappa_values_;
+    std::vector<std::string> npi_param_names_;
+    std::map<std::string, std::pair<double, double>> param_bounds_map_;
+};
+
+// ---- AgeSEPAIHRDModel (include/model/AgeSEPAIHRDModel.hpp) -------------------------------------------------
+// Holds the model parameters and the NPI schedule.  computeDerivatives lives on the device
+// (csrc/sepaihrd_kernels.cuh, rhs<>); this class is what the parameter manager mutates and what the
+// evaluator snapshots into the C-ABI problem description.
+class AgeSEPAIHRDModel {
+public:
+    AgeSEPAIHRDModel(const SEPAIHRDParameters& params, std::shared_ptr<INpiStrategy> npi_strategy_ptr);
+    std::shared_ptr<AgeSEPAIHRDModel> clone() const;
+    int getNumAgeClasses() const { return static_cast<int>(params_.N.size()); }
+    int getStateSize() const { return SEPAIHRD_NUM_COMPARTMENTS * getNumAgeClasses(); }
+    std::vector<std::string> getStateNames() const;
+    SEPAIHRDParameters getModelParameters() const;                      // src/model/AgeSEPAIHRDModel.cpp:294-323
+    void setModelParameters(const SEPAIHRDParameters& params);           // .cpp:325-363
+    std::shared_ptr<INpiStrategy> getNpiStrategy() const { return npi_strategy_; }
+    const VectorXd& getPopulationSizes() const { return params_.N; }
+    const MatrixXd& getContactMatrix() const { return params_.M_baseline; }
+    double computeBeta(double time) const;                              // .cpp:366-368 + PiecewiseConstantParameterStrategy.cpp:37-74
+
+    // Flat image of the parameters the hot path reads, in the slot order of sepaihrd_b200.h.
+    std::vector<double> slotVector() const;
+    std::vector<double> kappaEndTimes() const;      // [baseline end, NPI period ends...]
+    int numKappa() const;
+
+private:
+    SEPAIHRDParameters params_;
+    std::shared_ptr<INpiStrategy> npi_strategy_;
+};
+
+// ---- CalibrationData (include/utils/GetCalibrationData.hpp) ------------------------------------------------
+// In-memory backend only (the reference's matrix constructor, src/utils/GetCalibrationData.cpp:24-89); the CSV
+// reader is a Python-side fixture tool (config.py).  Matrices are (day, age).
+class CalibrationData {
+public:
+    CalibrationData(const MatrixXd& new_hospitalizations, const MatrixXd& new_icu, const MatrixXd& new_deaths,
+                    const VectorXd& population_by_age, const VectorXd& initial_sepaihrd_state = VectorXd());
+    const MatrixXd& getNewHospitalizations() const { return new_hospitalizations_; }
+    const MatrixXd& getNewICU() const { return new_icu_; }
+    const MatrixXd& getNewDeaths() const { return new_deaths_; }
+    const VectorXd& getPopulationByAgeGroup() const { return population_; }
+    const VectorXd& getInitialSEPAIHRDState() const { return initial_state_; }
+    int getNumDataPoints() const { return static_cast<int>(new_hospitalizations_.rows()); }
+    int getNumAgeClasses() const { return static_cast<int>(population_.size()); }
+
+private:
+    MatrixXd new_hospitalizations_, new_icu_, new_deaths_;
+    VectorXd population_, initial_state_;
+};
+
+// ---- SimulationResult (include/sir_age_structured/SimulationResult.hpp:18-35) ------------------------------
+struct SimulationResult {
+    std::vector<double> time_points;
+    std::vector<std::vector<double>> solution;     // [time][state], compartment-major state
+    std::vector<std::string> compartment_names;
+    int num_age_classes = 0;
+    bool isValid() const { return !time_points.empty() && time_points.size() == solution.size(); }
+};
+
+// ---- interfaces (include/sir_age_structured/interfaces/*.hpp) ---------------------------------------------
+using state_type = std::vector<double>;
+
+class IObjectiveFunction {
+public:
+    virtual ~IObjectiveFunction() = default;
+    virtual double calculate(const VectorXd& parameters) const = 0;                       // IObjectiveFunction.hpp:24
+    virtual const std::vector<std::string>& getParameterNames() const = 0;                 // :30
+    // B200 addition: B evaluations in one call.  params is row-major [B][ld], ld >= parameter count.
+    // The default loops over calculate(); SEPAIHRDObjectiveFunction overrides it with ONE kernel launch.
+    virtual void calculateBatch(const double* params, int64_t B, int64_t ld, double* out) const;
+};
+
+class IParameterManager {
+public:
+    virtual ~IParameterManager() = default;
+    virtual VectorXd getCurrentParameters() const = 0;
+    virtual void updateModelParameters(const VectorXd& parameters) = 0;
+    virtual const std::vector<std::string>& getParameterNames() const = 0;
+    virtual size_t getParameterCount() const = 0;
+    virtual double getSigmaForParamIndex(int index) const = 0;
+    virtual VectorXd applyConstraints(const VectorXd& parameters) const = 0;
+    virtual int getIndexForParam(const std::string& name) const = 0;
+    virtual double getLowerBoundForParamIndex(int idx) const = 0;
+    virtual double getUpperBoundForParamIndex(int idx) const = 0;
+};
+
+class IOdeSolverStrategy {
+public:
+    virtual ~IOdeSolverStrategy() = default;
+    virtual void integrate(const std::function<void(const state_type&, state_type&, double)>& system, state_type& initial_state,
+                           const std::vector<double>& times, double dt_hint,
+                           std::function<void(const state_type&, double)> observer, double abs_error,
+                           double rel_error) const = 0;                                      // IOdeSolverStrategy.hpp:35-42
+};
+
+// Tag for "adaptive Dopri5 with Boost.Odeint's controller": the only stepper the device kernels implement.
+// AgeSEPAIHRDSimulator recognises it and integrates on the GPU; integrate() on an arbitrary std::function system
+// cannot run on the device and throws SimulationException instead of silently falling back to the CPU.
+class Dopri5SolverStrategy : public IOdeSolverStrategy {
+public:
+    void integrate(const std::function<void(const state_type&, state_type&, double)>&, state_type&, const std::vector<double>&,
+                   double, std::function<void(const state_type&, double)>, double, double) const override;
+};
+
+class ISimulationCache {
+public:
+    virtual ~ISimulationCache() = default;
+    virtual std::optional<double> get(const VectorXd& parameters) = 0;
+    virtual void set(const VectorXd& parameters, double result) = 0;
+    virtual void clear() = 0;
+    virtual size_t size() const = 0;
+    virtual std::string createCacheKey(const VectorXd& parameters) const = 0;
+    virtual bool getLikelihood(const std::string& key, double& value) = 0;
+    virtual void storeLikelihood(const std::string& key, double value) = 0;
+};
+
+// The batch evaluator never consults a cache: a hit of the reference's SimulationCache may return the
+// likelihood of ANOTHER vector (1e-8 quantisation / hash collision).  The type exists so
+// that constructor signatures stay source compatible (pattern: sepaihrd_objective_benchmark_main.cpp:229-238).
+class NullSimulationCache : public ISimulationCache {
+public:
+    std::optional<double> get(const VectorXd&) override { return std::nullopt; }
+    void set(const VectorXd&, double) override {}
+    void clear() override {}
+    size_t size() const override { return 0; }
+    std::string createCacheKey(const VectorXd&) const override { return {}; }
+    bool getLikelihood(const std::string&, double&) override { return false; }
+    void storeLikelihood(const std::string&, double) override {}
+};
+using SimulationCache = NullSimulationCache;
+
+struct OptimizationResult {                                          // IOptimizationAlgorithm.hpp:18-27
+    VectorXd bestParameters;
+    double bestObjectiveValue = -std::numeric_limits<double>::infinity();
+    std::vector<VectorXd> samples;
+    std::vector<double> sampleObjectiveValues;
+    std::map<std::string, double> additionalStats;
+    MatrixXd finalCovariance;
+};
+
+class IOptimizationAlgorithm {
+public:
+    virtual ~IOptimizationAlgorithm() = default;
+    virtual OptimizationResult optimize(const VectorXd& initialParameters, IObjectiveFunction& objectiveFunction,
+                                        IParameterManager& parameterManager) = 0;           // :44-49
+    virtual void configure(const std::map<std::string, double>& settings) = 0;              // :53
+};
+
+// ---- SEPAIHRDParameterManager (include/model/parameters/SEPAIHRDParameterManager.hpp) ---------------------
+enum class ConstraintMode { OPTIMIZATION_CLAMP, MCMC_REFLECT };
+
+class SEPAIHRDParameterManager : public IParameterManager {
+public:
+    SEPAIHRDParameterManager(std::shared_ptr<AgeSEPAIHRDModel> model, const std::vector<std::string>& params_to_calibrate,
+                             const std::map<std::string, double>& proposal_sigmas,
+                             const std::map<std::string, std::pair<double, double>>& param_bounds);
+    VectorXd getCurrentParameters() const override;                                          // .cpp:91-158
+    void updateModelParameters(const VectorXd& parameters) override;                         // .cpp:160-162
+    void updateModelParameters(const VectorXd& parameters, std::shared_ptr<AgeSEPAIHRDModel> target_model);   // .cpp:164-287
+    const std::vector<std::string>& getParameterNames() const override { return param_names_; }
+    size_t getParameterCount() const override { return param_names_.size(); }
+    double getSigmaForParamIndex(int index) const override;
+    VectorXd applyConstraints(const VectorXd& parameters) const override;                    // .cpp:315-347
+    int getIndexForParam(const std::string& name) const override;
+    double getLowerBoundForParamIndex(int idx) const override;
+    double getUpperBoundForParamIndex(int idx) const override;
+    const std::map<std::string, double>& getProposalSigmas() const { return proposal_sigmas_; }
+    const std::map<std::string, std::pair<double, double>>& getParamBounds() const { return param_bounds_; }
+    void setConstraintMode(ConstraintMode mode);
+    ConstraintMode getConstraintMode() const { return mode_; }
+    std::shared_ptr<AgeSEPAIHRDModel> getModel() const { return model_; }
+    // slot (sepaihrd_b200.h layout) of every calibrated parameter, resolved once at construction
+    const std::vector<int32_t>& slots() const { return slots_; }
+    // observers of the constraint mode (the device context of an objective follows the manager's mode)
+    void onConstraintModeChange(std::function<void(ConstraintMode)> cb) { mode_listeners_.push_back(std::move(cb)); }
+    static double reflectBound(double value, double min_b, double max_b);                    // .cpp:302-313
+
+private:
+    std::shared_ptr<AgeSEPAIHRDModel> model_;
+    ConstraintMode mode_ = ConstraintMode::OPTIMIZATION_CLAMP;
+    std::vector<std::string> param_names_;
+    std::map<std::string, double> proposal_sigmas_;
+    std::map<std::string, std::pair<double, double>> param_bounds_;
+    std::vector<int32_t> slots_;
+    std::vector<std::function<void(ConstraintMode)>> mode_listeners_;
+};
+
+// ---- device context: RAII over sepaihrd_ctx ---------------------------------------------------------------
+// Snapshots (model, NPI schedule, data, time grid, calibrated names + bounds, tolerances) into a
+// sepaihrd_problem and creates the device evaluator.  Throws ModelConstructionException when the CUDA library
+// reports no usable device: there is no CPU fallback.
+class DeviceContext {
+public:
+    DeviceContext(const AgeSEPAIHRDModel& model, const std::vector<double>& time_points, const MatrixXd* obs_hosp,
+                  const MatrixXd* obs_icu, const MatrixXd* obs_deaths, const VectorXd& data_initial_state,
+                  const std::vector<int32_t>& param_slots, const std::vector<double>& lower, const std::vector<double>& upper,
+                  ConstraintMode mode, double abs_error, double rel_error, double dt_hint, int device = -1);
+    ~DeviceContext();
+    DeviceContext(const DeviceContext&) = delete;
+    DeviceContext& operator=(const DeviceContext&) = delete;
+    sepaihrd_ctx* get() const { return ctx_; }
+    int numParams() const { return n_params_; }
+    int numTimes() const { return n_times_; }
+    int stateSize() const { return state_size_; }
+    void setConstraintMode(ConstraintMode mode);
+
+private:
+    sepaihrd_ctx* ctx_ = nullptr;
+    int n_params_ = 0, n_times_ = 0, state_size_ = 0;
+};
+
+// ---- AgeSEPAIHRDSimulator (include/model/AgeSEPAIHRDsimulator.hpp:33-39, Simulator.cpp:60-150) -------------
+class AgeSEPAIHRDSimulator {
+public:
+    AgeSEPAIHRDSimulator(std::shared_ptr<AgeSEPAIHRDModel> model, std::shared_ptr<IOdeSolverStrategy> solver_strategy,
+                         double start_time, double end_time, double time_step, double abs_error = 1.0e-6,
+                         double rel_error = 1.0e-6);
+    ~AgeSEPAIHRDSimulator();
+    SimulationResult run(const VectorXd& initial_state, const std::vector<double>& output_time_points);
+    // B200 addition: the same run for B parameterisations of the model at once (posterior-predictive draws):
+    // slot_rows is [B][slot_count] in the layout of sepaihrd_b200.h (AgeSEPAIHRDModel::slotVector()).
+    // out is [B][times][11 n]; returns per-draw status words.
+    std::vector<uint32_t> runBatch(const VectorXd& initial_state, const std::vector<double>& output_time_points,
+                                   const double* slot_rows, int64_t B, double* out);
+    std::shared_ptr<AgeSEPAIHRDModel> getModel() const { return model_; }
+
+private:
+    void ensureContext(const std::vector<double>& times);
+    std::shared_ptr<AgeSEPAIHRDModel> model_;
+    std::shared_ptr<IOdeSolverStrategy> solver_;
+    double start_time_, end_time_, time_step_, abs_err_, rel_err_;
+    std::unique_ptr<DeviceContext> dev_;
+    std::vector<double> dev_times_;
+};
+
+// ---- SEPAIHRDObjectiveFunction (include/model/objectives/SEPAIHRDObjectiveFunction.hpp:40-57) --------------
+class SEPAIHRDObjectiveFunction : public virtual IObjectiveFunction {
+public:
+    SEPAIHRDObjectiveFunction(std::shared_ptr<AgeSEPAIHRDModel> model, IParameterManager& parameterManager,
+                              ISimulationCache& cache, const CalibrationData& calibration_data,
+                              const std::vector<double>& time_points, const VectorXd& initial_state,
+                              std::shared_ptr<IOdeSolverStrategy> solver_strategy, double abs_error = 1.0e-6,
+                              double rel_error = 1.0e-6);
+    ~SEPAIHRDObjectiveFunction() override;
+    double calculate(const VectorXd& parameters) const override;                             // .cpp:62-235
+    void calculateBatch(const double* params, int64_t B, int64_t ld, double* out) const override;
+    // batch form with per-set status words (SEPAIHRD_ST_*) and optional accepted/rejected step counts
+    void calculateBatch(const double* params, int64_t B, int64_t ld, double* out, uint32_t* status, int32_t* steps) const;
+    const std::vector<std::string>& getParameterNames() const override;
+    DeviceContext& device() const { return *dev_; }
+
+private:
+    IParameterManager& parameterManager_;
+    std::shared_ptr<AgeSEPAIHRDModel> model_;
+    std::unique_ptr<DeviceContext> dev_;
+};
+
+}  // namespace epidemic

@@ -1,0 +1,344 @@
+// host_capi.cpp -- extern "C" wrappers over the C++ host layer.  See host_capi.h.
+#include "host_capi.h"
+
+#include <cmath>
+#include <cstring>
+#include <string>
+
+#include "optimizers.hpp"
+
+using namespace epidemic;
+
+namespace {
+
+thread_local std::string g_err;
+
+template <class F>
+int32_t guarded(F&& f) {
+    try {
+        f();
+        return 0;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+    } catch (...) {
+        g_err = "unknown C++ exception";
+    }
+    return 1;
+}
+
+std::map<std::string, double> settings_map(int32_t n, const char* const* keys, const double* values) {
+    std::map<std::string, double> m;
+    for (int32_t i = 0; i < n; ++i) m[keys[i]] = values[i];
+    return m;
+}
+
+// IParameterManager over plain arrays: what the samplers need (sigmas, bounds, clamp / reflect) without a model.
+class ArrayParameterManager : public IParameterManager {
+public:
+    ArrayParameterManager(int n, const double* sigmas, const double* lo, const double* hi, int mode)
+        : sig_(sigmas, sigmas + n), lo_(lo, lo + n), hi_(hi, hi + n), mode_(mode) {
+        for (int i = 0; i < n; ++i) names_.push_back("p" + std::to_string(i));
+    }
+    VectorXd getCurrentParameters() const override { return VectorXd::Zero(static_cast<std::ptrdiff_t>(sig_.size())); }
+    void updateModelParameters(const VectorXd&) override {}
+    const std::vector<std::string>& getParameterNames() const override { return names_; }
+    size_t getParameterCount() const override { return sig_.size(); }
+    double getSigmaForParamIndex(int i) const override { return sig_.at(static_cast<size_t>(i)); }
+    VectorXd applyConstraints(const VectorXd& p) const override {          // SEPAIHRDParameterManager.cpp:315-347
+        if (static_cast<size_t>(p.size()) != sig_.size()) throw InvalidParameterException("applyConstraints", "Parameter vector size mismatch.");
+        VectorXd out = p;
+        for (size_t i = 0; i < sig_.size(); ++i) {
+            const auto k = static_cast<std::ptrdiff_t>(i);
+            if (!std::isnan(lo_[i])) {
+                double lo = lo_[i], hi = hi_[i];
+                if (lo > hi) std::swap(lo, hi);
+                out(k) = (mode_ == 0) ? std::min(std::max(p(k), lo), hi) : SEPAIHRDParameterManager::reflectBound(p(k), lo, hi);
+            } else {
+                out(k) = (mode_ == 0) ? std::max(0.0, p(k)) : std::abs(p(k));
+            }
+        }
+        return out;
+    }
+    int getIndexForParam(const std::string& name) const override {
+        for (size_t i = 0; i < names_.size(); ++i) if (names_[i] == name) return static_cast<int>(i);
+        return -1;
+    }
+    double getLowerBoundForParamIndex(int i) const override { return lo_.at(static_cast<size_t>(i)); }
+    double getUpperBoundForParamIndex(int i) const override { return hi_.at(static_cast<size_t>(i)); }
+    void setMode(int m) { mode_ = m; }
+
+private:
+    std::vector<double> sig_, lo_, hi_;
+    int mode_;
+    std::vector<std::string> names_;
+};
+
+// IObjectiveFunction over a C batch callback.
+class CallbackObjective : public IObjectiveFunction {
+public:
+    CallbackObjective(sepaihrd_host_batch_fn fn, void* user, const std::vector<std::string>& names) : fn_(fn), user_(user), names_(names) {}
+    double calculate(const VectorXd& p) const override {
+        double out = 0.0;
+        calculateBatch(p.data(), 1, p.size(), &out);
+        return out;
+    }
+    void calculateBatch(const double* params, int64_t B, int64_t ld, double* out) const override {
+        n_evals += B;
+        if (fn_(user_, params, B, ld, out) != 0) throw SimulationException("CallbackObjective", "the batch callback reported a failure");
+    }
+    const std::vector<std::string>& getParameterNames() const override { return names_; }
+    mutable int64_t n_evals = 0;
+
+private:
+    sepaihrd_host_batch_fn fn_;
+    void* user_;
+    std::vector<std::string> names_;
+};
+
+}  // namespace
+
+struct sepaihrd_host_pm { ArrayParameterManager pm; };
+struct sepaihrd_host_mh { MetropolisHastingsSampler s; sepaihrd_host_pm* pm; };
+struct sepaihrd_host_pso { ParticleSwarmOptimization s; sepaihrd_host_pm* pm; };
+
+struct sepaihrd_host_model {
+    std::shared_ptr<AgeSEPAIHRDModel> model;
+    std::unique_ptr<CalibrationData> data;
+    std::vector<double> times;
+    std::unique_ptr<SEPAIHRDModelCalibration> calibration;
+    std::unique_ptr<SEPAIHRDParameterManager> pm;
+    std::unique_ptr<NullSimulationCache> cache;
+    std::unique_ptr<SEPAIHRDObjectiveFunction> objective;
+    std::unique_ptr<AgeSEPAIHRDSimulator> simulator;
+    double abs_tol = 1e-6, rel_tol = 1e-6;
+};
+
+extern "C" {
+
+const char* sepaihrd_host_last_error(void) { return g_err.c_str(); }
+
+// ---- parameter manager ---------------------------------------------------------------------------------------
+int32_t sepaihrd_host_pm_create(int32_t n, const double* sigmas, const double* lo, const double* hi, int32_t mode, sepaihrd_host_pm** out) {
+    return guarded([&] {
+        if (n <= 0 || !sigmas || !lo || !hi || !out) throw InvalidParameterException("sepaihrd_host_pm_create", "bad argument");
+        *out = new sepaihrd_host_pm{ArrayParameterManager(n, sigmas, lo, hi, mode)};
+    });
+}
+int32_t sepaihrd_host_pm_set_mode(sepaihrd_host_pm* pm, int32_t mode) { return guarded([&] { pm->pm.setMode(mode); }); }
+int32_t sepaihrd_host_pm_apply_constraints(const sepaihrd_host_pm* pm, const double* in, double* out) {
+    return guarded([&] {
+        const auto n = static_cast<std::ptrdiff_t>(pm->pm.getParameterCount());
+        const VectorXd r = pm->pm.applyConstraints(VectorXd::FromPointer(in, n));
+        std::copy(r.data(), r.data() + n, out);
+    });
+}
+void sepaihrd_host_pm_destroy(sepaihrd_host_pm* pm) { delete pm; }
+
+// ---- Metropolis-Hastings ------------------------------------------------------------------------------------
+int32_t sepaihrd_host_mh_create(sepaihrd_host_pm* pm, int32_t n, const char* const* keys, const double* values, sepaihrd_host_mh** out) {
+    return guarded([&] {
+        if (!pm || !out) throw InvalidParameterException("sepaihrd_host_mh_create", "bad argument");
+        auto* h = new sepaihrd_host_mh{MetropolisHastingsSampler(), pm};
+        h->s.configure(settings_map(n, keys, values));
+        *out = h;
+    });
+}
+int32_t sepaihrd_host_mh_set_initial_covariance(sepaihrd_host_mh* mh, const double* cov, int32_t n) {
+    return guarded([&] {
+        MatrixXd m(n, n);
+        std::copy(cov, cov + static_cast<size_t>(n) * n, m.data());
+        mh->s.setInitialCovariance(m);
+    });
+}
+int32_t sepaihrd_host_mh_begin(sepaihrd_host_mh* mh, const double* initial, const double* lp) {
+    return guarded([&] { mh->s.begin(VectorXd::FromPointer(initial, static_cast<std::ptrdiff_t>(mh->pm->pm.getParameterCount())), lp, mh->pm->pm); });
+}
+int32_t sepaihrd_host_mh_done(const sepaihrd_host_mh* mh) { return mh->s.done() ? 1 : 0; }
+int32_t sepaihrd_host_mh_iteration(const sepaihrd_host_mh* mh) { return mh->s.iteration(); }
+int32_t sepaihrd_host_mh_propose(sepaihrd_host_mh* mh, double* out) { return guarded([&] { mh->s.propose(mh->pm->pm, out); }); }
+int32_t sepaihrd_host_mh_accept(sepaihrd_host_mh* mh, const double* lp, uint8_t* acc) { return guarded([&] { mh->s.accept(lp, acc); }); }
+int32_t sepaihrd_host_mh_state(const sepaihrd_host_mh* mh, double* x, double* lp, double* scale, int64_t* accepted) {
+    return guarded([&] {
+        const int n = mh->s.numChains(), P = mh->s.numParams();
+        if (x) std::copy(mh->s.currentPositions(), mh->s.currentPositions() + static_cast<size_t>(n) * P, x);
+        if (lp) std::copy(mh->s.currentLogPost(), mh->s.currentLogPost() + n, lp);
+        for (int c = 0; c < n; ++c) {
+            if (scale) scale[c] = mh->s.globalScale(c);
+            if (accepted) accepted[c] = mh->s.acceptedCount(c);
+        }
+    });
+}
+int32_t sepaihrd_host_mh_best(const sepaihrd_host_mh* mh, double* x, double* value) {
+    return guarded([&] {
+        const OptimizationResult r = mh->s.result();
+        if (x) std::copy(r.bestParameters.data(), r.bestParameters.data() + r.bestParameters.size(), x);
+        if (value) *value = r.bestObjectiveValue;
+    });
+}
+void sepaihrd_host_mh_destroy(sepaihrd_host_mh* mh) { delete mh; }
+
+// ---- particle swarm -----------------------------------------------------------------------------------------
+int32_t sepaihrd_host_pso_create(sepaihrd_host_pm* pm, int32_t n, const char* const* keys, const double* values, sepaihrd_host_pso** out) {
+    return guarded([&] {
+        if (!pm || !out) throw InvalidParameterException("sepaihrd_host_pso_create", "bad argument");
+        auto* h = new sepaihrd_host_pso{ParticleSwarmOptimization(), pm};
+        h->s.configure(settings_map(n, keys, values));
+        *out = h;
+    });
+}
+int32_t sepaihrd_host_pso_begin(sepaihrd_host_pso* pso, const double* init) {
+    return guarded([&] {
+        if (init) {
+            const VectorXd v = VectorXd::FromPointer(init, static_cast<std::ptrdiff_t>(pso->pm->pm.getParameterCount()));
+            pso->s.begin(&v, pso->pm->pm);
+        } else {
+            pso->s.begin(nullptr, pso->pm->pm);
+        }
+    });
+}
+int32_t sepaihrd_host_pso_local_count(const sepaihrd_host_pso* pso) { return pso->s.localCount(); }
+int32_t sepaihrd_host_pso_positions(const sepaihrd_host_pso* pso, double* out) {
+    return guarded([&] { std::copy(pso->s.positions(), pso->s.positions() + static_cast<size_t>(pso->s.localCount()) * pso->s.numParams(), out); });
+}
+int32_t sepaihrd_host_pso_tell(sepaihrd_host_pso* pso, const double* fitness, double* best_value, int32_t* best_local, double* best_pos) {
+    return guarded([&] {
+        const auto b = pso->s.tell(fitness);
+        if (best_value) *best_value = b.first;
+        if (best_local) *best_local = b.second;
+        if (best_pos && b.second >= 0) std::copy(pso->s.personalBest(b.second), pso->s.personalBest(b.second) + pso->s.numParams(), best_pos);
+    });
+}
+int32_t sepaihrd_host_pso_set_global_best(sepaihrd_host_pso* pso, double value, const double* pos) { return guarded([&] { pso->s.setGlobalBest(value, pos); }); }
+int32_t sepaihrd_host_pso_global_best(const sepaihrd_host_pso* pso, double* value, double* pos) {
+    return guarded([&] {
+        if (value) *value = pso->s.globalBestValue();
+        if (pos) std::copy(pso->s.globalBestPosition().begin(), pso->s.globalBestPosition().end(), pos);
+    });
+}
+int32_t sepaihrd_host_pso_step(sepaihrd_host_pso* pso, int32_t iter) { return guarded([&] { pso->s.step(iter); }); }
+void sepaihrd_host_pso_destroy(sepaihrd_host_pso* pso) { delete pso; }
+
+// ---- whole runs against a callback --------------------------------------------------------------------------
+int32_t sepaihrd_host_optimize(const char* algorithm, sepaihrd_host_pm* pm, int32_t n, const char* const* keys, const double* values,
+                               sepaihrd_host_batch_fn fn, void* user, const double* initial, double* out_best, double* out_value,
+                               int64_t* out_evals) {
+    return guarded([&] {
+        const std::string which = algorithm ? algorithm : "";
+        std::unique_ptr<IOptimizationAlgorithm> algo;
+        if (which == "mh") algo = std::make_unique<MetropolisHastingsSampler>();
+        else if (which == "pso") algo = std::make_unique<ParticleSwarmOptimization>();
+        else if (which == "hill") algo = std::make_unique<HillClimbingOptimizer>();
+        else throw InvalidParameterException("sepaihrd_host_optimize", "algorithm must be mh, pso or hill");
+        algo->configure(settings_map(n, keys, values));
+        CallbackObjective f(fn, user, pm->pm.getParameterNames());
+        const auto P = static_cast<std::ptrdiff_t>(pm->pm.getParameterCount());
+        const OptimizationResult r = algo->optimize(VectorXd::FromPointer(initial, P), f, pm->pm);
+        if (out_best) std::copy(r.bestParameters.data(), r.bestParameters.data() + P, out_best);
+        if (out_value) *out_value = r.bestObjectiveValue;
+        if (out_evals) *out_evals = f.n_evals;
+    });
+}
+
+// ---- reference-shaped object graph --------------------------------------------------------------------------
+int32_t sepaihrd_host_model_create(const sepaihrd_problem* pb, const char* const* names, const double* sigmas, sepaihrd_host_model** out) {
+    return guarded([&] {
+        if (!pb || !names || !sigmas || !out) throw InvalidParameterException("sepaihrd_host_model_create", "bad argument");
+        const int n = pb->n_ages, nb = pb->n_beta, nk = pb->n_kappa;
+        const double* s = pb->base_slots;
+        const int scal0 = nb + nk, age0 = scal0 + 7, mult0 = age0 + 8 * n;
+        SEPAIHRDParameters p;
+        p.N = VectorXd::FromPointer(pb->population, n);
+        p.M_baseline = MatrixXd(n, n);
+        std::copy(pb->contact_matrix, pb->contact_matrix + n * n, p.M_baseline.data());      // column-major both sides
+        p.beta_end_times.assign(pb->beta_end_times, pb->beta_end_times + nb);
+        p.beta_values.assign(s, s + nb);
+        p.kappa_end_times.assign(pb->kappa_end_times, pb->kappa_end_times + nk);
+        p.kappa_values.assign(s + nb, s + nb + nk);
+        p.theta = s[scal0]; p.sigma = s[scal0 + 1]; p.gamma_p = s[scal0 + 2]; p.gamma_A = s[scal0 + 3];
+        p.gamma_I = s[scal0 + 4]; p.gamma_H = s[scal0 + 5]; p.gamma_ICU = s[scal0 + 6];
+        VectorXd* blocks[8] = {&p.a, &p.h_infec, &p.p, &p.h, &p.icu, &p.d_H, &p.d_ICU, &p.d_community};
+        for (int b = 0; b < 8; ++b) *blocks[b] = VectorXd::FromPointer(s + age0 + b * n, n);
+        p.E0_multiplier = s[mult0]; p.P0_multiplier = s[mult0 + 1]; p.A0_multiplier = s[mult0 + 2]; p.I0_multiplier = s[mult0 + 3];
+        p.H0_multiplier = s[mult0 + 4]; p.ICU0_multiplier = s[mult0 + 5]; p.R0_multiplier = s[mult0 + 6]; p.D0_multiplier = s[mult0 + 7];
+        p.seed_exposed = s[mult0 + 8]; p.runup_days = s[mult0 + 9]; p.beta = s[mult0 + 10];
+
+        std::map<std::string, double> sig;
+        std::map<std::string, std::pair<double, double>> bounds;
+        std::vector<std::string> pnames;
+        for (int i = 0; i < pb->n_params; ++i) {
+            pnames.emplace_back(names[i]);
+            sig[names[i]] = sigmas[i];
+            bounds[names[i]] = {pb->lower_bound[i], pb->upper_bound[i]};
+        }
+        // createNpiStrategy (src/model/main.cpp:81-130): element 0 is the fixed baseline
+        std::vector<std::string> knames;
+        std::map<std::string, std::pair<double, double>> kbounds;
+        for (int k = 1; k < nk; ++k) {
+            knames.push_back("kappa_" + std::to_string(k + 1));
+            auto it = bounds.find(knames.back());
+            if (it != bounds.end()) kbounds[knames.back()] = it->second;
+        }
+        auto npi = std::make_shared<PiecewiseConstantNpiStrategy>(
+            std::vector<double>(p.kappa_end_times.begin() + 1, p.kappa_end_times.end()),
+            std::vector<double>(p.kappa_values.begin() + 1, p.kappa_values.end()), kbounds, p.kappa_values.at(0), p.kappa_end_times.at(0), true, knames);
+        auto h = std::make_unique<sepaihrd_host_model>();
+        h->model = std::make_shared<AgeSEPAIHRDModel>(p, npi);
+        auto obs = [&](const double* src) {
+            MatrixXd m(pb->n_obs, n);
+            for (int r = 0; r < pb->n_obs; ++r) for (int a = 0; a < n; ++a) m(r, a) = src[r * n + a];
+            return m;
+        };
+        h->data = std::make_unique<CalibrationData>(obs(pb->obs_hosp), obs(pb->obs_icu), obs(pb->obs_deaths), p.N,
+                                                    VectorXd::FromPointer(pb->data_initial_state, SEPAIHRD_NUM_COMPARTMENTS * n));
+        h->times.assign(pb->times, pb->times + pb->n_times);
+        h->abs_tol = pb->abs_tol; h->rel_tol = pb->rel_tol;
+        h->calibration = std::make_unique<SEPAIHRDModelCalibration>(h->model, *h->data, h->times, pnames, sig, bounds);
+        h->pm = std::make_unique<SEPAIHRDParameterManager>(h->model, pnames, sig, bounds);
+        h->pm->setConstraintMode(pb->constraint_mode == 1 ? ConstraintMode::MCMC_REFLECT : ConstraintMode::OPTIMIZATION_CLAMP);
+        h->cache = std::make_unique<NullSimulationCache>();
+        h->objective = std::make_unique<SEPAIHRDObjectiveFunction>(h->model, *h->pm, *h->cache, *h->data, h->times, h->data->getInitialSEPAIHRDState(),
+                                                                   std::make_shared<Dopri5SolverStrategy>(), pb->abs_tol, pb->rel_tol);
+        *out = h.release();
+    });
+}
+
+int32_t sepaihrd_host_model_calculate(sepaihrd_host_model* m, const double* params, double* out) {
+    return guarded([&] { *out = m->objective->calculate(VectorXd::FromPointer(params, static_cast<std::ptrdiff_t>(m->pm->getParameterCount()))); });
+}
+int32_t sepaihrd_host_model_calculate_batch(sepaihrd_host_model* m, const double* params, int64_t B, int64_t ld, double* out) {
+    return guarded([&] { m->objective->calculateBatch(params, B, ld, out); });
+}
+int32_t sepaihrd_host_model_set_constraint_mode(sepaihrd_host_model* m, int32_t mode) {
+    return guarded([&] { m->pm->setConstraintMode(mode == 1 ? ConstraintMode::MCMC_REFLECT : ConstraintMode::OPTIMIZATION_CLAMP); });
+}
+int32_t sepaihrd_host_model_current_parameters(sepaihrd_host_model* m, double* out) {
+    return guarded([&] { const VectorXd v = m->pm->getCurrentParameters(); std::copy(v.data(), v.data() + v.size(), out); });
+}
+int32_t sepaihrd_host_model_update_parameters(sepaihrd_host_model* m, const double* params) {
+    return guarded([&] { m->pm->updateModelParameters(VectorXd::FromPointer(params, static_cast<std::ptrdiff_t>(m->pm->getParameterCount()))); });
+}
+int32_t sepaihrd_host_model_simulate(sepaihrd_host_model* m, const double* init, const double* times, int32_t K, double* out) {
+    return guarded([&] {
+        const std::vector<double> t(times, times + K);
+        if (!m->simulator)
+            m->simulator = std::make_unique<AgeSEPAIHRDSimulator>(m->model, std::make_shared<Dopri5SolverStrategy>(), t.front(), t.back(), 1.0, m->abs_tol, m->rel_tol);
+        const SimulationResult r = m->simulator->run(VectorXd::FromPointer(init, m->model->getStateSize()), t);
+        const size_t W = static_cast<size_t>(m->model->getStateSize());
+        for (size_t k = 0; k < r.solution.size(); ++k) std::copy(r.solution[k].begin(), r.solution[k].end(), out + k * W);
+    });
+}
+int32_t sepaihrd_host_model_calibrate(sepaihrd_host_model* m, const char* phase1, int32_t n1, const char* const* k1, const double* v1, int32_t n2,
+                                      const char* const* k2, const double* v2, double* out_best, double* out_value, int64_t* out_samples) {
+    return guarded([&] {
+        const std::string which = phase1 ? phase1 : "pso";
+        ModelCalibrator c = (which == "hill") ? m->calibration->runHillClimbingMCMC(settings_map(n1, k1, v1), settings_map(n2, k2, v2))
+                                              : m->calibration->runPSOMCMC(settings_map(n1, k1, v1), settings_map(n2, k2, v2));
+        const VectorXd& b = c.getBestParameterVector();
+        if (out_best) std::copy(b.data(), b.data() + b.size(), out_best);
+        if (out_value) *out_value = c.getBestObjectiveValue();
+        if (out_samples) *out_samples = static_cast<int64_t>(c.getMCMCSamples().size());
+    });
+}
+void sepaihrd_host_model_destroy(sepaihrd_host_model* m) { delete m; }
+
+}  // extern "C"

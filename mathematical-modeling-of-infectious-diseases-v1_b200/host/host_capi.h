@@ -1,0 +1,102 @@
+/*
+ * host_capi.h -- C entry points of the host layer (libsepaihrd_host.so).
+ *
+ * The host layer is C++ (epidemic_host.hpp, optimizers.hpp: the reference's interface shapes over the
+ * device C ABI).  These extern "C" wrappers exist for two callers that cannot include C++ headers:
+ *   - the Python harness (tests/, bench.py, drivers.py), which steps the batched samplers and does the
+ *     cross-GPU exchange with torch.distributed between the steps;
+ *   - the parity tests, which run the SAME sampler code once against the device evaluator and once against
+ *     the CPU oracle through a batch callback (the host library itself never links or loads the oracle).
+ * Every function returns 0 on success; sepaihrd_host_last_error() gives the message of the last failure on
+ * this thread (C++ exceptions never cross this boundary).
+ */
+#ifndef SEPAIHRD_HOST_CAPI_H
+#define SEPAIHRD_HOST_CAPI_H
+
+#include <stdint.h>
+
+#include "sepaihrd_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* sepaihrd_host_last_error(void);
+
+/* B log-posteriors for B parameter rows ([B][ld] row-major).  Return non-zero to abort the run. */
+typedef int32_t (*sepaihrd_host_batch_fn)(void* user, const double* params, int64_t B, int64_t ld, double* out);
+
+/* ---- parameter manager over plain arrays (IParameterManager: sigmas, bounds, clamp / reflect) ------------- *
+ * lower/upper: NaN = "no bounds entry" (SEPAIHRDParameterManager.cpp:337-343).  mode: 0 clamp, 1 reflect.     */
+typedef struct sepaihrd_host_pm sepaihrd_host_pm;
+int32_t sepaihrd_host_pm_create(int32_t n_params, const double* sigmas, const double* lower, const double* upper,
+                                int32_t mode, sepaihrd_host_pm** out);
+int32_t sepaihrd_host_pm_set_mode(sepaihrd_host_pm* pm, int32_t mode);
+int32_t sepaihrd_host_pm_apply_constraints(const sepaihrd_host_pm* pm, const double* in, double* out);
+void    sepaihrd_host_pm_destroy(sepaihrd_host_pm* pm);
+
+/* ---- multi-chain Metropolis-Hastings (MetropolisHastingsSampler, step-wise) ---------------------------------- *
+ * settings: the reference's keys (mcmc_iterations, burn_in, adaptation_period, thinning, regularization_epsilon,
+ * target_acceptance_rate, adapt_scale, store_samples) plus n_chains, chain_offset, seed.                         */
+typedef struct sepaihrd_host_mh sepaihrd_host_mh;
+int32_t sepaihrd_host_mh_create(sepaihrd_host_pm* pm, int32_t n_settings, const char* const* keys, const double* values,
+                                sepaihrd_host_mh** out);
+int32_t sepaihrd_host_mh_set_initial_covariance(sepaihrd_host_mh* mh, const double* cov_colmajor, int32_t n);
+int32_t sepaihrd_host_mh_begin(sepaihrd_host_mh* mh, const double* initial, const double* initial_logpost);
+int32_t sepaihrd_host_mh_done(const sepaihrd_host_mh* mh);            /* 1 when all iterations have run */
+int32_t sepaihrd_host_mh_iteration(const sepaihrd_host_mh* mh);
+int32_t sepaihrd_host_mh_propose(sepaihrd_host_mh* mh, double* out_proposals /* [n_chains][P] */);
+int32_t sepaihrd_host_mh_accept(sepaihrd_host_mh* mh, const double* proposed_logpost, uint8_t* out_accepted /* or NULL */);
+int32_t sepaihrd_host_mh_state(const sepaihrd_host_mh* mh, double* out_x /* [n][P] */, double* out_logpost /* [n] */,
+                               double* out_scale /* [n] */, int64_t* out_accepted /* [n] */);
+int32_t sepaihrd_host_mh_best(const sepaihrd_host_mh* mh, double* out_x /* [P] */, double* out_value);
+void    sepaihrd_host_mh_destroy(sepaihrd_host_mh* mh);
+
+/* ---- particle swarm (ParticleSwarmOptimization, step-wise; this process owns a contiguous shard) ---------- *
+ * settings: iterations, swarm_size, omega_start/end, c1_initial/final, c2_initial/final, plus particle_offset,
+ * local_count, seed.                                                                                             */
+typedef struct sepaihrd_host_pso sepaihrd_host_pso;
+int32_t sepaihrd_host_pso_create(sepaihrd_host_pm* pm, int32_t n_settings, const char* const* keys, const double* values,
+                                 sepaihrd_host_pso** out);
+int32_t sepaihrd_host_pso_begin(sepaihrd_host_pso* pso, const double* initial_or_null);
+int32_t sepaihrd_host_pso_local_count(const sepaihrd_host_pso* pso);
+int32_t sepaihrd_host_pso_positions(const sepaihrd_host_pso* pso, double* out /* [local][P] */);
+/* personal-best update; returns the shard's best personal best (value, local index, position) */
+int32_t sepaihrd_host_pso_tell(sepaihrd_host_pso* pso, const double* fitness, double* out_best_value, int32_t* out_best_local,
+                               double* out_best_position /* [P] */);
+int32_t sepaihrd_host_pso_set_global_best(sepaihrd_host_pso* pso, double value, const double* position);
+int32_t sepaihrd_host_pso_global_best(const sepaihrd_host_pso* pso, double* out_value, double* out_position);
+int32_t sepaihrd_host_pso_step(sepaihrd_host_pso* pso, int32_t iter);
+void    sepaihrd_host_pso_destroy(sepaihrd_host_pso* pso);
+
+/* ---- whole runs against a batch callback: "mh", "pso" or "hill" (IOptimizationAlgorithm::optimize) --------- */
+int32_t sepaihrd_host_optimize(const char* algorithm, sepaihrd_host_pm* pm, int32_t n_settings, const char* const* keys,
+                               const double* values, sepaihrd_host_batch_fn fn, void* user, const double* initial,
+                               double* out_best /* [P] */, double* out_best_value, int64_t* out_n_evaluations);
+
+/* ---- the reference-shaped object graph over the device evaluator -------------------------------------------- *
+ * Builds SEPAIHRDParameters -> PiecewiseConstantNpiStrategy -> AgeSEPAIHRDModel -> CalibrationData ->
+ * SEPAIHRDModelCalibration (-> SEPAIHRDParameterManager, SEPAIHRDObjectiveFunction, AgeSEPAIHRDSimulator) from a
+ * sepaihrd_problem plus the calibrated names and proposal sigmas.  Needs a CUDA device: no CPU fallback.          */
+typedef struct sepaihrd_host_model sepaihrd_host_model;
+int32_t sepaihrd_host_model_create(const sepaihrd_problem* problem, const char* const* param_names, const double* sigmas,
+                                   sepaihrd_host_model** out);
+/* SEPAIHRDObjectiveFunction::calculate / calculateBatch */
+int32_t sepaihrd_host_model_calculate(sepaihrd_host_model* m, const double* params, double* out);
+int32_t sepaihrd_host_model_calculate_batch(sepaihrd_host_model* m, const double* params, int64_t B, int64_t ld, double* out);
+int32_t sepaihrd_host_model_set_constraint_mode(sepaihrd_host_model* m, int32_t mode);
+/* SEPAIHRDParameterManager::getCurrentParameters / updateModelParameters (then getCurrentParameters again) */
+int32_t sepaihrd_host_model_current_parameters(sepaihrd_host_model* m, double* out /* [P] */);
+int32_t sepaihrd_host_model_update_parameters(sepaihrd_host_model* m, const double* params);
+/* AgeSEPAIHRDSimulator::run(initial_state, times): out [K][11 n] */
+int32_t sepaihrd_host_model_simulate(sepaihrd_host_model* m, const double* initial_state, const double* times, int32_t K, double* out);
+/* SEPAIHRDModelCalibration::runPSOMCMC / runHillClimbingMCMC (phase1 = "pso" | "hill") */
+int32_t sepaihrd_host_model_calibrate(sepaihrd_host_model* m, const char* phase1, int32_t n1, const char* const* keys1, const double* values1,
+                                      int32_t n2, const char* const* keys2, const double* values2, double* out_best /* [P] */,
+                                      double* out_best_value, int64_t* out_n_samples);
+void    sepaihrd_host_model_destroy(sepaihrd_host_model* m);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEPAIHRD_HOST_CAPI_H */

@@ -1,0 +1,693 @@
+// optimizers.cpp -- batched calibrators over IObjectiveFunction::calculateBatch.  See optimizers.hpp.
+#include "optimizers.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <iostream>
+
+namespace epidemic {
+
+namespace {
+
+double setting(const std::map<std::string, double>& s, const std::string& key, double def) {
+    auto it = s.find(key);
+    return it != s.end() ? it->second : def;
+}
+
+std::vector<double> evaluate_rows(IObjectiveFunction& f, const std::vector<double>& rows, int64_t B, int64_t P) {
+    std::vector<double> out(static_cast<size_t>(B));
+    if (B > 0) f.calculateBatch(rows.data(), B, P, out.data());
+    for (double& v : out) v = MetropolisHastingsSampler::safeValue(v);
+    return out;
+}
+
+MatrixXd outer(const VectorXd& d) {
+    const auto n = d.size();
+    MatrixXd m(n, n);
+    for (std::ptrdiff_t j = 0; j < n; ++j)
+        for (std::ptrdiff_t i = 0; i < n; ++i) m(i, j) = d(i) * d(j);
+    return m;
+}
+
+}  // namespace
+
+// =====================================================================================================================
+// Metropolis-Hastings (adaptive Metropolis, Haario et al.; Robbins-Monro global scale)
+// =====================================================================================================================
+MetropolisHastingsSampler::MetropolisHastingsSampler() = default;
+
+void MetropolisHastingsSampler::configure(const std::map<std::string, double>& s) {
+    iterations_ = static_cast<int>(setting(s, "mcmc_iterations", 10000.0));
+    burn_in_ = static_cast<int>(setting(s, "burn_in", 1000.0));
+    adaptation_period_ = std::max(1, static_cast<int>(setting(s, "adaptation_period", 100.0)));
+    report_interval_ = std::max(1, static_cast<int>(setting(s, "report_interval", 100.0)));
+    thinning_ = std::max(1, static_cast<int>(setting(s, "thinning", 1.0)));
+    regularization_epsilon_ = setting(s, "regularization_epsilon", 1e-6);
+    target_acceptance_rate_ = setting(s, "target_acceptance_rate", 0.234);
+    adapt_scale_ = setting(s, "adapt_scale", 1.0) != 0.0;
+    store_samples_ = setting(s, "store_samples", 1.0) != 0.0;
+    // batched / repeatable extensions
+    n_chains_ = std::max(1, static_cast<int>(setting(s, "n_chains", 1.0)));
+    chain_offset_ = static_cast<long>(setting(s, "chain_offset", 0.0));
+    has_seed_ = s.count("seed") != 0;
+    seed_ = static_cast<unsigned>(setting(s, "seed", 0.0));
+}
+
+void MetropolisHastingsSampler::setInitialCovariance(const MatrixXd& cov) {
+    hasInitialCovariance_ = cov.rows() > 0 && cov.rows() == cov.cols();
+    if (hasInitialCovariance_) initialCovariance_ = cov;
+}
+
+void MetropolisHastingsSampler::begin(const VectorXd& initial, const double* initial_logpost, IParameterManager& pm) {
+    n_params_ = static_cast<int>(initial.size());
+    const auto P = static_cast<std::ptrdiff_t>(n_params_);
+    // initial covariance (.cpp:216-240)
+    if (hasInitialCovariance_ && initialCovariance_.rows() == P) {
+        shared_cov_ = initialCovariance_;
+    } else {
+        shared_cov_ = MatrixXd::Identity(P, P);
+        for (std::ptrdiff_t i = 0; i < P; ++i) {
+            const double sg = pm.getSigmaForParamIndex(static_cast<int>(i));
+            shared_cov_(i, i) = (sg > 0 ? sg * sg : 1e-6);
+        }
+        shared_cov_ *= (2.38 * 2.38) / static_cast<double>(n_params_);
+    }
+    shared_cov_ += regularization_epsilon_ * MatrixXd::Identity(P, P);
+    if (!linalg::cholesky_lower(shared_cov_, shared_chol_)) shared_chol_ = MatrixXd::Identity(P, P) * 0.1;
+
+    keep_history_ = iterations_ - 1 > burn_in_;      // the covariance adaptation reads the whole chain history
+    std::random_device rd;
+    chains_.assign(static_cast<size_t>(n_chains_), Chain());
+    cur_x_.assign(static_cast<size_t>(n_chains_) * n_params_, 0.0);
+    cur_lp_.assign(static_cast<size_t>(n_chains_), 0.0);
+    prop_x_.assign(cur_x_.size(), 0.0);
+    for (int c = 0; c < n_chains_; ++c) {
+        Chain& ch = chains_[static_cast<size_t>(c)];
+        if (has_seed_) {
+            std::seed_seq seq{seed_, static_cast<unsigned>(chain_offset_ + c)};
+            ch.gen.seed(seq);
+        } else {
+            ch.gen.seed(rd());
+        }
+        std::copy(initial.data(), initial.data() + n_params_, cur_x_.begin() + static_cast<std::ptrdiff_t>(c) * n_params_);
+        cur_lp_[static_cast<size_t>(c)] = safeValue(initial_logpost[c]);
+        ch.running_mean = initial;
+        ch.best_x = initial;
+        ch.best_lp = cur_lp_[static_cast<size_t>(c)];
+        if (keep_history_) ch.history.push_back(initial);
+        if (store_samples_) { ch.samples.push_back(initial); ch.sample_lp.push_back(ch.best_lp); }
+    }
+    t_ = 1;
+}
+
+void MetropolisHastingsSampler::ownKernel(Chain& c) const {
+    if (c.own_kernel) return;
+    c.cov = shared_cov_;
+    c.chol = shared_chol_;
+    c.own_kernel = true;
+}
+
+void MetropolisHastingsSampler::updateCovarianceRank1(Chain& c, int step) const {
+    if (c.history.empty()) return;
+    const double gamma = 10.0 / (step + 100.0);
+    const VectorXd diff = c.history.back() - c.running_mean;
+    c.running_mean += gamma * diff;
+    c.cov = (1.0 - gamma) * c.cov + gamma * outer(diff);
+}
+
+void MetropolisHastingsSampler::recomputeFullCovariance(Chain& c) const {
+    const auto P = static_cast<std::ptrdiff_t>(n_params_);
+    if (c.history.size() < static_cast<size_t>(n_params_) + 10) return;
+    VectorXd mean = VectorXd::Zero(P);
+    for (const auto& v : c.history) mean += v;
+    mean /= static_cast<double>(c.history.size());
+    c.running_mean = mean;
+    MatrixXd cov = MatrixXd::Zero(P, P);
+    for (const auto& v : c.history) {
+        const VectorXd d = v - mean;
+        for (std::ptrdiff_t j = 0; j < P; ++j)
+            for (std::ptrdiff_t i = 0; i < P; ++i) cov(i, j) += d(i) * d(j);
+    }
+    cov *= 1.0 / static_cast<double>(c.history.size() - 1);
+    c.cov = ((2.38 * 2.38) / static_cast<double>(n_params_)) * cov + regularization_epsilon_ * MatrixXd::Identity(P, P);
+    MatrixXd L;
+    if (linalg::cholesky_lower(c.cov, L)) c.chol = L;
+}
+
+void MetropolisHastingsSampler::adaptGlobalScale(Chain& c, bool accepted, int step) const {
+    if (!adapt_scale_) return;
+    c.recent.push_back(accepted ? 1 : 0);
+    c.recent_sum += accepted ? 1 : 0;
+    if (c.recent.size() > 1000) { c.recent_sum -= c.recent.front(); c.recent.pop_front(); }
+    const double rate = c.recent.empty() ? 0.0 : static_cast<double>(c.recent_sum) / static_cast<double>(c.recent.size());
+    if (c.recent.size() >= 1000 && rate < 0.001) {
+        c.log_scale -= 0.7;
+        c.emergency_shrink_count++;
+    } else if (rate < 0.02 && c.recent.size() >= 500) {
+        const double g = std::min(5.0 / std::sqrt(static_cast<double>(step) + 1.0), 0.3);
+        c.log_scale += g * (0.0 - target_acceptance_rate_);
+    } else {
+        const double g = std::min(1.0 / std::sqrt(static_cast<double>(step) + 1.0), 0.1);
+        c.log_scale += g * ((accepted ? 1.0 : 0.0) - target_acceptance_rate_);
+    }
+    if (c.global_scale <= 0.011 && rate > 0.15 && rate < 0.30) c.log_scale += 0.01;
+    c.log_scale = std::max(std::min(c.log_scale, 2.3), -6.9);
+    c.global_scale = std::exp(c.log_scale);
+}
+
+void MetropolisHastingsSampler::propose(IParameterManager& pm, double* out) {
+    const auto P = static_cast<std::ptrdiff_t>(n_params_);
+    const int t = t_;
+#pragma omp parallel for schedule(static)
+    for (int ci = 0; ci < n_chains_; ++ci) {
+        Chain& c = chains_[static_cast<size_t>(ci)];
+        // 1. adaptation (only after burn-in), .cpp:286-303
+        if (t > burn_in_) {
+            ownKernel(c);
+            updateCovarianceRank1(c, t);
+            if (t % adaptation_period_ == 0) {
+                recomputeFullCovariance(c);
+                MatrixXd L;
+                if (linalg::cholesky_lower(c.cov + regularization_epsilon_ * MatrixXd::Identity(P, P), L)) c.chol = L;
+            }
+        }
+        // 2. proposal  Y = X + scale * L z,  z ~ N(0, I)   (generateProposal, .cpp:91-102)
+        VectorXd z(P);
+        std::normal_distribution<double> dist(0.0, 1.0);
+        for (std::ptrdiff_t i = 0; i < P; ++i) z(i) = dist(c.gen);
+        const MatrixXd& L = c.own_kernel ? c.chol : shared_chol_;
+        const VectorXd step = L * z;
+        VectorXd y(P);
+        const double* x = cur_x_.data() + static_cast<std::ptrdiff_t>(ci) * P;
+        for (std::ptrdiff_t i = 0; i < P; ++i) y(i) = x[i] + c.global_scale * step(i);
+        // 2b. constraints (reflection in MCMC mode)
+        const VectorXd yc = pm.applyConstraints(y);
+        std::copy(yc.data(), yc.data() + P, prop_x_.begin() + static_cast<std::ptrdiff_t>(ci) * P);
+    }
+    std::copy(prop_x_.begin(), prop_x_.end(), out);
+}
+
+void MetropolisHastingsSampler::accept(const double* proposed_logpost, uint8_t* accepted_out) {
+    const auto P = static_cast<std::ptrdiff_t>(n_params_);
+    const int t = t_;
+#pragma omp parallel for schedule(static)
+    for (int ci = 0; ci < n_chains_; ++ci) {
+        Chain& c = chains_[static_cast<size_t>(ci)];
+        const double plp = safeValue(proposed_logpost[ci]);
+        double& clp = cur_lp_[static_cast<size_t>(ci)];
+        const double log_ratio = plp - clp;
+        bool acc = false;
+        if (log_ratio >= 0.0) {
+            acc = true;
+        } else {
+            std::uniform_real_distribution<double> u(0.0, 1.0);      // drawn ONLY for downhill proposals (.cpp:323-329)
+            if (std::log(u(c.gen)) < log_ratio) acc = true;
+        }
+        double* x = cur_x_.data() + static_cast<std::ptrdiff_t>(ci) * P;
+        if (acc) {
+            std::copy(prop_x_.begin() + static_cast<std::ptrdiff_t>(ci) * P, prop_x_.begin() + static_cast<std::ptrdiff_t>(ci + 1) * P, x);
+            clp = plp;
+            c.accepted++;
+            if (clp > c.best_lp) { c.best_lp = clp; c.best_x = VectorXd::FromPointer(x, P); }
+        }
+        if (adapt_scale_) adaptGlobalScale(c, acc, t);
+        if (keep_history_) c.history.push_back(VectorXd::FromPointer(x, P));
+        if (store_samples_ && (t % thinning_ == 0)) { c.samples.push_back(VectorXd::FromPointer(x, P)); c.sample_lp.push_back(clp); }
+        if (accepted_out) accepted_out[ci] = acc ? 1 : 0;
+    }
+    ++t_;
+}
+
+OptimizationResult MetropolisHastingsSampler::result() const {
+    OptimizationResult r;
+    long accepted = 0;
+    for (const Chain& c : chains_) {
+        if (c.best_lp > r.bestObjectiveValue || r.bestParameters.size() == 0) { r.bestObjectiveValue = c.best_lp; r.bestParameters = c.best_x; }
+        accepted += c.accepted;
+        r.samples.insert(r.samples.end(), c.samples.begin(), c.samples.end());                 // chain-major
+        r.sampleObjectiveValues.insert(r.sampleObjectiveValues.end(), c.sample_lp.begin(), c.sample_lp.end());
+    }
+    r.finalCovariance = chains_.empty() || !chains_.front().own_kernel ? shared_cov_ : chains_.front().cov;
+    r.additionalStats["acceptance_rate"] = static_cast<double>(accepted) / (static_cast<double>(iterations_) * std::max(1, n_chains_));
+    r.additionalStats["final_scale"] = chains_.empty() ? 1.0 : chains_.front().global_scale;
+    r.additionalStats["burn_in"] = burn_in_;
+    r.additionalStats["total_iterations"] = iterations_;
+    r.additionalStats["n_chains"] = n_chains_;
+    return r;
+}
+
+OptimizationResult MetropolisHastingsSampler::optimize(const VectorXd& initial, IObjectiveFunction& f, IParameterManager& pm) {
+    if (auto* spm = dynamic_cast<SEPAIHRDParameterManager*>(&pm)) spm->setConstraintMode(ConstraintMode::MCMC_REFLECT);   // .cpp:207-210
+    const int64_t P = initial.size();
+    // every chain starts from the same point: one evaluation, replicated
+    const double lp0 = safeValue(f.calculate(initial));
+    std::vector<double> lp(static_cast<size_t>(n_chains_), lp0);
+    begin(initial, lp.data(), pm);
+    std::vector<double> prop(static_cast<size_t>(n_chains_) * static_cast<size_t>(P));
+    while (!done()) {
+        propose(pm, prop.data());
+        const std::vector<double> plp = evaluate_rows(f, prop, n_chains_, P);
+        accept(plp.data());
+    }
+    return result();
+}
+
+// =====================================================================================================================
+// Particle swarm (STANDARD update, GLOBAL_BEST topology)
+// =====================================================================================================================
+void ParticleSwarmOptimization::configure(const std::map<std::string, double>& s) {
+    auto nonneg = [&](const char* k, double def) { const double v = setting(s, k, def); if (v < 0) throw std::invalid_argument(std::string(k) + " must be non-negative"); return v; };
+    auto positive = [&](const char* k, double def) { const double v = setting(s, k, def); if (v <= 0) throw std::invalid_argument(std::string(k) + " must be positive"); return v; };
+    iterations_ = static_cast<int>(positive("iterations", 100.0));
+    swarm_size_ = static_cast<int>(positive("swarm_size", 30.0));
+    omega_start_ = nonneg("omega_start", 0.9); omega_end_ = nonneg("omega_end", 0.4);
+    c1_initial_ = nonneg("c1_initial", 2.5); c1_final_ = nonneg("c1_final", 0.5);
+    c2_initial_ = nonneg("c2_initial", 0.5); c2_final_ = nonneg("c2_final", 2.5);
+    report_interval_ = static_cast<int>(positive("report_interval", 10.0));
+    // Only the STANDARD variant on the GLOBAL_BEST topology is built (BASELINE.json configs[3]); asking for another one
+    // is an error rather than a silent substitution.
+    if (s.count("variant") && static_cast<int>(s.at("variant")) != 0) throw std::invalid_argument("variant: only STANDARD (0) is built in the batched PSO");
+    if (s.count("topology") && static_cast<int>(s.at("topology")) != 0) throw std::invalid_argument("topology: only GLOBAL_BEST (0) is built in the batched PSO");
+    if (setting(s, "use_opposition_learning", 0.0) != 0.0) throw std::invalid_argument("use_opposition_learning is not built in the batched PSO");
+    if (setting(s, "use_adaptive_parameters", 0.0) != 0.0) throw std::invalid_argument("use_adaptive_parameters is not built in the batched PSO");
+    particle_offset_ = static_cast<long>(setting(s, "particle_offset", 0.0));
+    local_count_setting_ = static_cast<int>(setting(s, "local_count", -1.0));
+    has_seed_ = s.count("seed") != 0;
+    seed_ = static_cast<unsigned>(setting(s, "seed", 0.0));
+}
+
+void ParticleSwarmOptimization::begin(const VectorXd* init, IParameterManager& pm) {
+    n_ = static_cast<int>(pm.getParameterCount());
+    local_ = local_count_setting_ >= 0 ? local_count_setting_ : swarm_size_ - static_cast<int>(particle_offset_);
+    if (particle_offset_ < 0 || particle_offset_ + local_ > swarm_size_) throw std::invalid_argument("particle_offset/local_count outside the swarm");
+    lb_.resize(static_cast<size_t>(n_)); ub_.resize(static_cast<size_t>(n_));
+    for (int k = 0; k < n_; ++k) { lb_[static_cast<size_t>(k)] = pm.getLowerBoundForParamIndex(k); ub_[static_cast<size_t>(k)] = pm.getUpperBoundForParamIndex(k); }
+    if (has_seed_) rng_.seed(seed_); else rng_.seed(std::random_device{}());
+    const size_t tot = static_cast<size_t>(local_) * static_cast<size_t>(n_);
+    pos_.assign(tot, 0.0); vel_.assign(tot, 0.0); pbest_.assign(tot, 0.0);
+    pbest_val_.assign(static_cast<size_t>(local_), -std::numeric_limits<double>::infinity());
+    gbest_.assign(static_cast<size_t>(n_), 0.0);
+    gbest_value_ = -std::numeric_limits<double>::infinity();
+    first_tell_ = true;
+    // one seed per particle of the WHOLE swarm from the master generator (.cpp:268-270): every shard draws them all
+    std::vector<unsigned> seeds(static_cast<size_t>(swarm_size_));
+    for (auto& sd : seeds) sd = static_cast<unsigned>(rng_());
+#pragma omp parallel for schedule(static)
+    for (int li = 0; li < local_; ++li) {
+        const long gi = particle_offset_ + li;
+        std::mt19937 local_rng(seeds[static_cast<size_t>(gi)]);
+        std::uniform_real_distribution<> U(0.0, 1.0);
+        double* p = pos_.data() + static_cast<size_t>(li) * n_;
+        double* v = vel_.data() + static_cast<size_t>(li) * n_;
+        if (gi == 0 && init != nullptr && init->size() == n_) {
+            for (int k = 0; k < n_; ++k) p[k] = std::clamp((*init)(k), lb_[static_cast<size_t>(k)], ub_[static_cast<size_t>(k)]);
+        } else {
+            for (int k = 0; k < n_; ++k) p[k] = lb_[static_cast<size_t>(k)] + U(local_rng) * (ub_[static_cast<size_t>(k)] - lb_[static_cast<size_t>(k)]);
+        }
+        for (int k = 0; k < n_; ++k) {
+            const double vmax = 0.2 * (ub_[static_cast<size_t>(k)] - lb_[static_cast<size_t>(k)]);
+            v[k] = -vmax + 2 * vmax * U(local_rng);
+        }
+    }
+}
+
+std::pair<double, int> ParticleSwarmOptimization::tell(const double* fitness) {
+    double best = -std::numeric_limits<double>::infinity();
+    int best_i = -1;
+    for (int li = 0; li < local_; ++li) {
+        const double f = fitness[li];
+        if (first_tell_ || f > pbest_val_[static_cast<size_t>(li)]) {       // .cpp:301-303 / :417-421
+            pbest_val_[static_cast<size_t>(li)] = f;
+            std::copy(pos_.begin() + static_cast<std::ptrdiff_t>(li) * n_, pos_.begin() + static_cast<std::ptrdiff_t>(li + 1) * n_,
+                      pbest_.begin() + static_cast<std::ptrdiff_t>(li) * n_);
+        }
+        if (pbest_val_[static_cast<size_t>(li)] > best) { best = pbest_val_[static_cast<size_t>(li)]; best_i = li; }   // first maximum wins (.cpp:149-156)
+    }
+    first_tell_ = false;
+    return {best, best_i};
+}
+
+void ParticleSwarmOptimization::setGlobalBest(double value, const double* position) {
+    if (value > gbest_value_) {            // strict: an equal value keeps the earlier best (.cpp:150)
+        gbest_value_ = value;
+        gbest_.assign(position, position + n_);
+    }
+}
+
+void ParticleSwarmOptimization::step(int iter) {
+    const double ratio = (iterations_ > 1) ? static_cast<double>(iter) / (iterations_ - 1) : 0.0;    // .cpp:352-357
+    const double omega = omega_start_ + (omega_end_ - omega_start_) * ratio;
+    const double c1 = c1_initial_ + (c1_final_ - c1_initial_) * ratio;
+    const double c2 = c2_initial_ + (c2_final_ - c2_initial_) * ratio;
+    std::vector<unsigned> seeds(static_cast<size_t>(swarm_size_));
+    for (auto& sd : seeds) sd = static_cast<unsigned>(rng_());
+#pragma omp parallel for schedule(static)
+    for (int li = 0; li < local_; ++li) {
+        std::mt19937 local_rng(seeds[static_cast<size_t>(particle_offset_ + li)]);
+        std::uniform_real_distribution<> U(0.0, 1.0);
+        double* p = pos_.data() + static_cast<size_t>(li) * n_;
+        double* v = vel_.data() + static_cast<size_t>(li) * n_;
+        const double* pb = pbest_.data() + static_cast<size_t>(li) * n_;
+        // standardPSOUpdate (.cpp:576-618): r1_k, r2_k interleaved per dimension
+        std::vector<double> r1(static_cast<size_t>(n_)), r2(static_cast<size_t>(n_));
+        for (int k = 0; k < n_; ++k) { r1[static_cast<size_t>(k)] = U(local_rng); r2[static_cast<size_t>(k)] = U(local_rng); }
+        for (int k = 0; k < n_; ++k) {
+            const size_t kk = static_cast<size_t>(k);
+            const double cognitive = c1 * (r1[kk] * (pb[k] - p[k]));
+            const double social = c2 * (r2[kk] * (gbest_[kk] - p[k]));
+            double vk = omega * v[k] + cognitive + social;
+            const double vmax = 0.2 * (ub_[kk] - lb_[kk]);
+            vk = std::clamp(vk, -vmax, vmax);
+            double pk = p[k] + vk;
+            if (pk < lb_[kk]) { pk = lb_[kk] + std::abs(pk - lb_[kk]); vk *= -0.5; }
+            else if (pk > ub_[kk]) { pk = ub_[kk] - std::abs(pk - ub_[kk]); vk *= -0.5; }
+            p[k] = std::clamp(pk, lb_[kk], ub_[kk]);
+            v[k] = vk;
+        }
+    }
+}
+
+MatrixXd ParticleSwarmOptimization::personalBestScatter(VectorXd& mean) const {
+    const auto P = static_cast<std::ptrdiff_t>(n_);
+    mean = VectorXd::Zero(P);
+    for (int li = 0; li < local_; ++li)
+        for (std::ptrdiff_t k = 0; k < P; ++k) mean(k) += pbest_[static_cast<size_t>(li) * n_ + static_cast<size_t>(k)];
+    mean /= static_cast<double>(std::max(local_, 1));
+    MatrixXd sc = MatrixXd::Zero(P, P);
+    for (int li = 0; li < local_; ++li) {
+        VectorXd d(P);
+        for (std::ptrdiff_t k = 0; k < P; ++k) d(k) = pbest_[static_cast<size_t>(li) * n_ + static_cast<size_t>(k)] - mean(k);
+        for (std::ptrdiff_t j = 0; j < P; ++j)
+            for (std::ptrdiff_t i = 0; i < P; ++i) sc(i, j) += d(i) * d(j);
+    }
+    return sc;
+}
+
+OptimizationResult ParticleSwarmOptimization::optimize(const VectorXd& initial, IObjectiveFunction& f, IParameterManager& pm) {
+    const int n = static_cast<int>(pm.getParameterCount());
+    begin(initial.size() == n ? &initial : nullptr, pm);
+    auto evaluate = [&]() {
+        std::vector<double> fit(static_cast<size_t>(local_));
+        f.calculateBatch(pos_.data(), local_, n_, fit.data());         // the reference does not sanitise PSO fitness (.cpp:412)
+        const auto best = tell(fit.data());
+        if (best.second >= 0) setGlobalBest(best.first, personalBest(best.second));
+    };
+    evaluate();
+    for (int iter = 0; iter < iterations_; ++iter) {
+        step(iter);
+        evaluate();
+    }
+    OptimizationResult r;
+    r.bestParameters = VectorXd::FromPointer(gbest_.data(), n_);
+    r.bestObjectiveValue = gbest_value_;
+    VectorXd mean;
+    r.finalCovariance = personalBestScatter(mean);                    // covariance of the personal bests for phase 2 (.cpp:226-242)
+    r.finalCovariance *= 1.0 / static_cast<double>(std::max(local_ - 1, 1));
+    r.finalCovariance += 1e-6 * MatrixXd::Identity(n_, n_);
+    return r;
+}
+
+// =====================================================================================================================
+// Hill climbing: candidate cloud + robust line search
+// =====================================================================================================================
+void HillClimbingOptimizer::configure(const std::map<std::string, double>& s) {
+    iterations_ = static_cast<int>(setting(s, "iterations", 2000.0));
+    report_interval_ = std::max(1, static_cast<int>(setting(s, "report_interval", 100.0)));
+    cloud_size_multiplier_ = std::max(1, static_cast<int>(setting(s, "cloud_size_multiplier", 8.0)));
+    // the reference sizes the cloud as max(4, omp threads * multiplier) (.cpp:170-175); on the GPU the natural unit is
+    // a wave of lane groups, so an explicit "cloud_size" can be given (default: 8 "threads" worth)
+    cloud_size_ = static_cast<int>(setting(s, "cloud_size", 0.0));
+    has_seed_ = s.count("seed") != 0;
+    seed_ = static_cast<unsigned>(setting(s, "seed", 0.0));
+}
+
+bool HillClimbingOptimizer::lineSearch(VectorXd& current, double& current_logL, const VectorXd& direction, IObjectiveFunction& func,
+                                       IParameterManager& pm) const {
+    const int max_backtrack = 10, max_expansion = 12;
+    const int64_t P = current.size();
+    auto sqdist = [](const VectorXd& a, const VectorXd& b) { double s = 0; for (std::ptrdiff_t i = 0; i < a.size(); ++i) s += (a(i) - b(i)) * (a(i) - b(i)); return s; };
+    // backtracking: candidates at step 1, 1/2, 1/4, ... -- evaluated as ONE batch, consumed in order
+    std::vector<VectorXd> cand;
+    double step = 1.0;
+    for (int i = 0; i < max_backtrack; ++i) {
+        VectorXd c = pm.applyConstraints(current + direction * step);
+        if (sqdist(c, current) < 1e-16) break;
+        cand.push_back(c);
+        step *= 0.5;
+    }
+    if (cand.empty()) return false;
+    std::vector<double> rows(cand.size() * static_cast<size_t>(P));
+    for (size_t i = 0; i < cand.size(); ++i) std::copy(cand[i].data(), cand[i].data() + P, rows.begin() + static_cast<std::ptrdiff_t>(i * static_cast<size_t>(P)));
+    std::vector<double> val = evaluate_rows(func, rows, static_cast<int64_t>(cand.size()), P);
+    int foothold = -1;
+    for (size_t i = 0; i < cand.size(); ++i)
+        if (val[i] > current_logL) { foothold = static_cast<int>(i); break; }
+    if (foothold < 0) return false;
+    VectorXd best = cand[static_cast<size_t>(foothold)];
+    double best_logL = val[static_cast<size_t>(foothold)];
+    // expansion: c_k = constrain(c_{k-1} + 2^k s) as long as every previous candidate improved
+    VectorXd cur_step = best - current;
+    std::vector<VectorXd> exp_c;
+    VectorXd base = best;
+    for (int i = 0; i < max_expansion; ++i) {
+        cur_step *= 2.0;
+        VectorXd c = pm.applyConstraints(base + cur_step);
+        exp_c.push_back(c);
+        base = c;
+    }
+    rows.assign(exp_c.size() * static_cast<size_t>(P), 0.0);
+    for (size_t i = 0; i < exp_c.size(); ++i) std::copy(exp_c[i].data(), exp_c[i].data() + P, rows.begin() + static_cast<std::ptrdiff_t>(i * static_cast<size_t>(P)));
+    val = evaluate_rows(func, rows, static_cast<int64_t>(exp_c.size()), P);
+    for (size_t i = 0; i < exp_c.size(); ++i) {
+        if (val[i] > best_logL) { best = exp_c[i]; best_logL = val[i]; }
+        else break;
+    }
+    current = best;
+    current_logL = best_logL;
+    return true;
+}
+
+OptimizationResult HillClimbingOptimizer::optimize(const VectorXd& initial, IObjectiveFunction& f, IParameterManager& pm) {
+    OptimizationResult result;
+    const auto P = initial.size();
+    const int n_params = static_cast<int>(P);
+    result.bestParameters = initial;
+    result.bestObjectiveValue = MetropolisHastingsSampler::safeValue(f.calculate(initial));
+    VectorXd current = initial, prev = initial;
+    double current_logL = result.bestObjectiveValue;
+    MatrixXd cov = MatrixXd::Identity(P, P);
+    for (std::ptrdiff_t i = 0; i < P; ++i) { const double s = pm.getSigmaForParamIndex(static_cast<int>(i)); cov(i, i) = (s > 0 ? s * s : 1e-4); }
+    MatrixXd L;
+    linalg::cholesky_lower(cov, L);
+    const int num_candidates = cloud_size_ > 0 ? std::max(4, cloud_size_) : std::max(4, 8 * cloud_size_multiplier_);
+    std::mt19937 gen(has_seed_ ? seed_ : std::random_device{}());
+    std::normal_distribution<double> norm(0.0, 1.0);
+    std::vector<double> rows(static_cast<size_t>(num_candidates) * static_cast<size_t>(P));
+    for (int iter = 0; iter < iterations_; ++iter) {
+        // half the cloud follows the learned covariance, half moves along one coordinate (.cpp:198-223)
+        for (int i = 0; i < num_candidates; ++i) {
+            VectorXd d = VectorXd::Zero(P);
+            if (i < num_candidates / 2) {
+                VectorXd z(P);
+                for (std::ptrdiff_t k = 0; k < P; ++k) z(k) = norm(gen);
+                d = L * z;
+            } else {
+                std::uniform_int_distribution<int> pick(0, n_params - 1);
+                const int idx = pick(gen);
+                d(idx) = std::sqrt(cov(idx, idx)) * norm(gen);
+            }
+            const VectorXd c = pm.applyConstraints(current + d);
+            std::copy(c.data(), c.data() + P, rows.begin() + static_cast<std::ptrdiff_t>(i) * P);
+        }
+        const std::vector<double> scores = evaluate_rows(f, rows, num_candidates, P);
+        int best_idx = -1;
+        double best_val = -1e18;
+        for (int i = 0; i < num_candidates; ++i)
+            if (scores[static_cast<size_t>(i)] > best_val) { best_val = scores[static_cast<size_t>(i)]; best_idx = i; }
+        bool moved = false;
+        if (best_idx != -1 && best_val > -1e18) {
+            const VectorXd best_point = VectorXd::FromPointer(rows.data() + static_cast<std::ptrdiff_t>(best_idx) * P, P);
+            const VectorXd direction = best_point - current;
+            if (best_val > current_logL) { current = best_point; current_logL = best_val; moved = true; }
+            moved = lineSearch(current, current_logL, direction, f, pm) || moved;
+        }
+        if (moved) {
+            if (current_logL > result.bestObjectiveValue) { result.bestObjectiveValue = current_logL; result.bestParameters = current; }
+            const VectorXd stepv = current - prev;
+            double sq = 0;
+            for (std::ptrdiff_t i = 0; i < P; ++i) sq += stepv(i) * stepv(i);
+            if (sq > 1e-14) {
+                const double alpha = 2.0 / (n_params + 2.0);
+                cov = (1.0 - alpha) * cov + alpha * outer(stepv);
+                cov = 0.5 * (cov + cov.transpose());
+                cov += (1e-8 * cov.trace() / n_params) * MatrixXd::Identity(P, P);
+                for (std::ptrdiff_t i = 0; i < P; ++i) {
+                    double mv = pm.getSigmaForParamIndex(static_cast<int>(i));
+                    mv = (mv > 0 ? mv * mv * 0.01 : 1e-8);
+                    if (cov(i, i) < mv) cov(i, i) = mv;
+                }
+            }
+            prev = current;
+        }
+        if (iter > 0 && iter % 10 == 0) {
+            MatrixXd Ln;
+            if (linalg::cholesky_lower(cov, Ln)) {
+                L = Ln;
+            } else {
+                double lambda = 1e-6 * cov.trace() / n_params;
+                bool ok = false;
+                for (int attempt = 0; attempt < 5 && !ok; ++attempt) {
+                    cov += lambda * MatrixXd::Identity(P, P);
+                    ok = linalg::cholesky_lower(cov, Ln);
+                    lambda *= 10.0;
+                }
+                if (ok) L = Ln;
+                else {
+                    MatrixXd dg = MatrixXd::Zero(P, P);
+                    L = MatrixXd::Zero(P, P);
+                    for (std::ptrdiff_t i = 0; i < P; ++i) { dg(i, i) = cov(i, i); L(i, i) = std::sqrt(cov(i, i)); }
+                    cov = dg;
+                }
+            }
+        }
+    }
+    result.finalCovariance = cov;
+    return result;
+}
+
+// =====================================================================================================================
+// ModelCalibrator / SEPAIHRDModelCalibration
+// =====================================================================================================================
+ModelCalibrator::ModelCalibrator(std::unique_ptr<IParameterManager> pm, std::unique_ptr<IObjectiveFunction> f,
+                                 std::map<std::string, std::unique_ptr<IOptimizationAlgorithm>> algorithms)
+    : parameterManager_(std::move(pm)), objectiveFunction_(std::move(f)), optimization_algorithms_(std::move(algorithms)) {
+    const char* src = "ModelCalibrator";
+    if (!parameterManager_) throw InvalidParameterException(src, "Parameter manager cannot be null.");
+    if (!objectiveFunction_) throw InvalidParameterException(src, "Objective function cannot be null.");
+    if (optimization_algorithms_.empty()) throw InvalidParameterException(src, "At least one optimization algorithm must be provided.");
+    if (parameterManager_->getParameterNames() != objectiveFunction_->getParameterNames())
+        throw InvalidParameterException(src, "Parameter names mismatch between ParameterManager and ObjectiveFunction.");
+    best_params_vector_ = parameterManager_->getCurrentParameters();
+    best_objective_value_ = objectiveFunction_->calculate(best_params_vector_);
+    if (std::isnan(best_objective_value_) || std::isinf(best_objective_value_)) best_objective_value_ = -std::numeric_limits<double>::infinity();
+}
+
+void ModelCalibrator::calibrate(const std::map<std::string, double>& phase1_settings, const std::map<std::string, double>& phase2_settings) {
+    VectorXd current_best = best_params_vector_;
+    auto* spm = dynamic_cast<SEPAIHRDParameterManager*>(parameterManager_.get());
+    auto it1 = optimization_algorithms_.find(PHASE1_NAME);
+    if (it1 != optimization_algorithms_.end()) {
+        if (spm) spm->setConstraintMode(ConstraintMode::OPTIMIZATION_CLAMP);
+        it1->second->configure(phase1_settings);
+        phase1_result_ = it1->second->optimize(current_best, *objectiveFunction_, *parameterManager_);
+        if (phase1_result_.bestObjectiveValue > best_objective_value_) {
+            best_objective_value_ = phase1_result_.bestObjectiveValue;
+            best_params_vector_ = phase1_result_.bestParameters;
+        }
+        current_best = best_params_vector_;
+    }
+    auto it2 = optimization_algorithms_.find(PHASE2_NAME);
+    if (it2 != optimization_algorithms_.end()) {
+        if (spm) spm->setConstraintMode(ConstraintMode::MCMC_REFLECT);
+        it2->second->configure(phase2_settings);
+        if (phase1_result_.finalCovariance.size() > 0) {
+            if (auto* mh = dynamic_cast<MetropolisHastingsSampler*>(it2->second.get())) {
+                // condition the phase-1 covariance: symmetrise, floor the eigenvalues at (0.1 sigma)^2, inflate x4, ridge
+                MatrixXd cov = phase1_result_.finalCovariance;
+                const auto n = cov.rows();
+                cov = 0.5 * (cov + cov.transpose());
+                VectorXd evals; MatrixXd evecs;
+                linalg::symmetric_eigen(cov, evals, evecs);
+                // ascending order like Eigen::SelfAdjointEigenSolver, so that floor i pairs with parameter i's sigma as in the reference
+                std::vector<std::ptrdiff_t> order(static_cast<size_t>(n));
+                for (std::ptrdiff_t i = 0; i < n; ++i) order[static_cast<size_t>(i)] = i;
+                std::sort(order.begin(), order.end(), [&](std::ptrdiff_t a, std::ptrdiff_t b) { return evals(a) < evals(b); });
+                MatrixXd floored = MatrixXd::Zero(n, n);
+                for (std::ptrdiff_t r = 0; r < n; ++r) {
+                    const std::ptrdiff_t e = order[static_cast<size_t>(r)];
+                    const double prior = parameterManager_->getSigmaForParamIndex(static_cast<int>(r));
+                    const double lam = std::max(evals(e), std::pow(prior * 0.1, 2));
+                    for (std::ptrdiff_t j = 0; j < n; ++j)
+                        for (std::ptrdiff_t i = 0; i < n; ++i) floored(i, j) += lam * evecs(i, e) * evecs(j, e);
+                }
+                MatrixXd phase2 = floored * 4.0;
+                phase2 += (1e-8 * phase2.trace() / static_cast<double>(n)) * MatrixXd::Identity(n, n);
+                mh->setInitialCovariance(phase2);
+            }
+        }
+        phase2_result_ = it2->second->optimize(current_best, *objectiveFunction_, *parameterManager_);
+        if (phase2_result_.bestObjectiveValue > best_objective_value_) {
+            best_objective_value_ = phase2_result_.bestObjectiveValue;
+            best_params_vector_ = phase2_result_.bestParameters;
+        }
+        // re-score every stored sample (.cpp:144-147): one batch instead of one calculate() per sample
+        const auto& S = phase2_result_.samples;
+        if (!S.empty()) {
+            const int64_t P = S.front().size();
+            std::vector<double> rows(S.size() * static_cast<size_t>(P));
+            for (size_t i = 0; i < S.size(); ++i) std::copy(S[i].data(), S[i].data() + P, rows.begin() + static_cast<std::ptrdiff_t>(i * static_cast<size_t>(P)));
+            mcmcObjectiveValues_.assign(S.size(), 0.0);
+            objectiveFunction_->calculateBatch(rows.data(), static_cast<int64_t>(S.size()), P, mcmcObjectiveValues_.data());
+        }
+    }
+    parameterManager_->updateModelParameters(best_params_vector_);
+}
+
+SEPAIHRDModelCalibration::SEPAIHRDModelCalibration(std::shared_ptr<AgeSEPAIHRDModel> model, const CalibrationData& data,
+                                                   const std::vector<double>& time_points, const std::vector<std::string>& names,
+                                                   const std::map<std::string, double>& sigmas,
+                                                   const std::map<std::string, std::pair<double, double>>& bounds,
+                                                   std::shared_ptr<IOdeSolverStrategy> solver, std::shared_ptr<ISimulationCache> cache)
+    : model_(std::move(model)), observed_data_(data), time_points_(time_points), params_to_calibrate_(names), proposal_sigmas_(sigmas),
+      param_bounds_(bounds), solver_strategy_(std::move(solver)), cache_(std::move(cache)) {
+    const char* src = "SEPAIHRDModelCalibration";
+    if (!model_) throw InvalidParameterException(src, "Model pointer is null.");
+    if (!solver_strategy_) throw InvalidParameterException(src, "Solver strategy pointer is null.");
+    if (!cache_) throw InvalidParameterException(src, "Cache pointer is null.");
+    if (time_points_.empty()) throw InvalidParameterException(src, "Time points vector is empty.");
+    if (params_to_calibrate_.empty()) throw InvalidParameterException(src, "Parameters to calibrate list is empty.");
+    initial_state_cached_ = observed_data_.getInitialSEPAIHRDState();
+    if (initial_state_cached_.size() != model_->getStateSize())
+        throw ModelConstructionException(src, "Failed to get initial state from calibration data: size mismatch.");
+    try {
+        parameter_manager_ = std::make_unique<SEPAIHRDParameterManager>(model_, params_to_calibrate_, proposal_sigmas_, param_bounds_);
+    } catch (const std::exception& e) {
+        throw ModelConstructionException(src, std::string("Failed to create parameter manager: ") + e.what());
+    }
+}
+
+SEPAIHRDParameterManager& SEPAIHRDModelCalibration::getParameterManager() { return *parameter_manager_; }
+VectorXd SEPAIHRDModelCalibration::getCurrentParameterValues() { return parameter_manager_->getCurrentParameters(); }
+
+ModelCalibrator SEPAIHRDModelCalibration::setupCalibrator(std::map<std::string, std::unique_ptr<IOptimizationAlgorithm>> algorithms) {
+    const char* src = "SEPAIHRDModelCalibration::setupCalibrator";
+    std::unique_ptr<SEPAIHRDParameterManager> pm;
+    std::unique_ptr<IObjectiveFunction> f;
+    try {
+        pm = std::make_unique<SEPAIHRDParameterManager>(model_, params_to_calibrate_, proposal_sigmas_, param_bounds_);
+        f = std::make_unique<SEPAIHRDObjectiveFunction>(model_, *pm, *cache_, observed_data_, time_points_, initial_state_cached_, solver_strategy_);
+    } catch (const std::exception& e) {
+        throw ModelConstructionException(src, std::string("Failed to create ObjectiveFunction: ") + e.what());
+    }
+    return ModelCalibrator(std::move(pm), std::move(f), std::move(algorithms));
+}
+
+ModelCalibrator SEPAIHRDModelCalibration::runPSOMCMC(const std::map<std::string, double>& s1, const std::map<std::string, double>& s2) {
+    std::map<std::string, std::unique_ptr<IOptimizationAlgorithm>> algos;
+    algos[ModelCalibrator::PHASE1_NAME] = std::make_unique<ParticleSwarmOptimization>();
+    algos[ModelCalibrator::PHASE2_NAME] = std::make_unique<MetropolisHastingsSampler>();
+    ModelCalibrator c = setupCalibrator(std::move(algos));
+    c.calibrate(s1, s2);
+    return c;
+}
+
+ModelCalibrator SEPAIHRDModelCalibration::runHillClimbingMCMC(const std::map<std::string, double>& s1, const std::map<std::string, double>& s2) {
+    std::map<std::string, std::unique_ptr<IOptimizationAlgorithm>> algos;
+    algos[ModelCalibrator::PHASE1_NAME] = std::make_unique<HillClimbingOptimizer>();
+    algos[ModelCalibrator::PHASE2_NAME] = std::make_unique<MetropolisHastingsSampler>();
+    ModelCalibrator c = setupCalibrator(std::move(algos));
+    c.calibrate(s1, s2);
+    return c;
+}
+
+}  // namespace epidemic

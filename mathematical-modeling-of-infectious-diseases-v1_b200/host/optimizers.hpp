@@ -1,0 +1,200 @@
+// optimizers.hpp -- batched forms of the reference's calibrators: every iteration hands ALL
+// chains / particles to IObjectiveFunction::calculateBatch, i.e. to one launch of the fused device kernel.
+//
+//   MetropolisHastingsSampler   src/sir_age_structured/optimizers/MetropolisHastingsSampler.cpp:201-412 (one chain)
+//                               -> n_chains independent chains of exactly that algorithm, stepped in lockstep
+//   ParticleSwarmOptimization   src/model/optimizers/ParticleSwarmOptimizer.cpp:106-247, 249-328, 330-425, 576-618
+//                               -> STANDARD update, GLOBAL_BEST topology, linear omega/c1/c2 schedules
+//   HillClimbingOptimizer       src/sir_age_structured/optimizers/HillClimbingOptimizer.cpp:38-109, 131-352
+//   ModelCalibrator             src/sir_age_structured/ModelCalibrator.cpp:22-168 (two phases + covariance hand-off)
+//   SEPAIHRDModelCalibration    src/model/SEPAIHRDModelCalibration.cpp:24-236
+//
+// The reference seeds every generator from std::random_device (MetropolisHastingsSampler.cpp:20-23,
+// ParticleSwarmOptimizer.hpp:578); here a "seed" setting makes runs repeatable: chain c draws from
+// std::mt19937(std::seed_seq{seed, c}) with c the GLOBAL chain index, so a run sharded over several GPUs
+// (settings "chain_offset" / "particle_offset") visits exactly the states of the single-process run.
+#pragma once
+
+#include <deque>
+#include <random>
+
+#include "epidemic_host.hpp"
+
+namespace epidemic {
+
+class MetropolisHastingsSampler : public IOptimizationAlgorithm {
+public:
+    MetropolisHastingsSampler();
+    void configure(const std::map<std::string, double>& settings) override;
+    OptimizationResult optimize(const VectorXd& initialParameters, IObjectiveFunction& objectiveFunction,
+                                IParameterManager& parameterManager) override;
+    void setInitialCovariance(const MatrixXd& cov);
+
+    // ---- step-wise form (used by optimize() and by the multi-GPU driver) --------------------------------------
+    // begin(): chains start at `initial` ([P], shared) with log-posteriors `initial_logpost` ([n_chains]).
+    void begin(const VectorXd& initial, const double* initial_logpost, IParameterManager& pm);
+    int iteration() const { return t_; }                 // next iteration index (1-based like the reference loop)
+    bool done() const { return t_ >= iterations_; }
+    // propose(): adaptation step + proposal + constraints for every chain; out is [n_chains][P] row-major
+    void propose(IParameterManager& pm, double* out);
+    // accept(): Metropolis accept/reject from the proposals' log-posteriors; accepted_out (optional) gets 0/1
+    void accept(const double* proposed_logpost, uint8_t* accepted_out = nullptr);
+    int numChains() const { return n_chains_; }
+    int numParams() const { return n_params_; }
+    const double* currentPositions() const { return cur_x_.data(); }       // [n_chains][P]
+    const double* currentLogPost() const { return cur_lp_.data(); }        // [n_chains]
+    double globalScale(int chain) const { return chains_[static_cast<size_t>(chain)].global_scale; }
+    long acceptedCount(int chain) const { return chains_[static_cast<size_t>(chain)].accepted; }
+    OptimizationResult result() const;
+    static double safeValue(double v) { return (std::isnan(v) || std::isinf(v)) ? -1e18 : v; }   // safeEvaluate, .cpp:65-74
+
+private:
+    struct Chain {
+        std::mt19937 gen;
+        double log_scale = 0.0, global_scale = 1.0;
+        std::deque<uint8_t> recent;
+        int recent_sum = 0;
+        int emergency_shrink_count = 0;
+        long accepted = 0;
+        bool own_kernel = false;          // false: shares the initial Cholesky factor
+        MatrixXd cov, chol;
+        VectorXd running_mean;
+        std::vector<VectorXd> history;
+        double best_lp = -std::numeric_limits<double>::infinity();
+        VectorXd best_x;
+        std::vector<VectorXd> samples;
+        std::vector<double> sample_lp;
+    };
+    void adaptGlobalScale(Chain& c, bool accepted, int step) const;     // .cpp:104-152
+    void updateCovarianceRank1(Chain& c, int step) const;               // .cpp:154-168
+    void recomputeFullCovariance(Chain& c) const;                       // .cpp:170-199
+    void ownKernel(Chain& c) const;
+
+    int iterations_ = 10000, burn_in_ = 1000, adaptation_period_ = 100, report_interval_ = 100, thinning_ = 1;
+    double regularization_epsilon_ = 1e-6, target_acceptance_rate_ = 0.234;
+    bool adapt_scale_ = true, store_samples_ = true;
+    int n_chains_ = 1;
+    long chain_offset_ = 0;
+    bool has_seed_ = false;
+    unsigned seed_ = 0;
+    bool hasInitialCovariance_ = false;
+    MatrixXd initialCovariance_;
+    // run state
+    int n_params_ = 0, t_ = 1;
+    bool keep_history_ = false;
+    MatrixXd shared_cov_, shared_chol_;
+    std::vector<Chain> chains_;
+    std::vector<double> cur_x_, cur_lp_, prop_x_;
+};
+
+class ParticleSwarmOptimization : public IOptimizationAlgorithm {
+public:
+    void configure(const std::map<std::string, double>& settings) override;
+    OptimizationResult optimize(const VectorXd& initialParameters, IObjectiveFunction& objectiveFunction,
+                                IParameterManager& parameterManager) override;
+
+    // ---- step-wise form: this process owns particles [particle_offset, particle_offset + local_count) --------
+    // begin(): draws the initial swarm (uniform in bounds; particle 0 = clamped initialParameters); positions()
+    // then holds what has to be evaluated.
+    void begin(const VectorXd* initialParameters, IParameterManager& pm);
+    const double* positions() const { return pos_.data(); }              // [local][P]
+    int localCount() const { return local_; }
+    int swarmSize() const { return swarm_size_; }
+    int numParams() const { return n_; }
+    int iterations() const { return iterations_; }
+    // tell(): fitness of positions(); updates personal bests; returns the best (value, LOCAL index) of this shard
+    std::pair<double, int> tell(const double* fitness);
+    const double* personalBest(int local_index) const { return pbest_.data() + static_cast<size_t>(local_index) * n_; }
+    // global best as agreed by all shards (single process: the shard's own best)
+    void setGlobalBest(double value, const double* position);
+    double globalBestValue() const { return gbest_value_; }
+    const std::vector<double>& globalBestPosition() const { return gbest_; }
+    // step(): velocity/position update of iteration `iter` (0-based) for every local particle
+    void step(int iter);
+    MatrixXd personalBestScatter(VectorXd& mean_out) const;               // sum of (pbest - mean)(pbest - mean)^T pieces for the covariance hand-off
+
+private:
+    int iterations_ = 100, swarm_size_ = 30, report_interval_ = 10;
+    double omega_start_ = 0.9, omega_end_ = 0.4, c1_initial_ = 2.5, c1_final_ = 0.5, c2_initial_ = 0.5, c2_final_ = 2.5;
+    long particle_offset_ = 0;
+    int local_count_setting_ = -1;
+    bool has_seed_ = false;
+    unsigned seed_ = 0;
+    // run state
+    int n_ = 0, local_ = 0;
+    std::mt19937 rng_;
+    std::vector<double> lb_, ub_, pos_, vel_, pbest_, pbest_val_, gbest_;
+    double gbest_value_ = -std::numeric_limits<double>::infinity();
+    bool first_tell_ = true;
+};
+
+// HillClimbingOptimizer   src/sir_age_structured/optimizers/HillClimbingOptimizer.cpp:131-352: a candidate cloud per
+// iteration (ONE batch), then the robust line search (.cpp:38-109) whose <= 10 backtracking and <= 12 expansion
+// candidates are evaluated speculatively as two batches and consumed in the reference's sequential order.
+class HillClimbingOptimizer : public IOptimizationAlgorithm {
+public:
+    void configure(const std::map<std::string, double>& settings) override;
+    OptimizationResult optimize(const VectorXd& initialParameters, IObjectiveFunction& objectiveFunction,
+                                IParameterManager& parameterManager) override;
+
+private:
+    bool lineSearch(VectorXd& current, double& current_logL, const VectorXd& direction, IObjectiveFunction& func, IParameterManager& pm) const;
+    int iterations_ = 2000, report_interval_ = 100, cloud_size_multiplier_ = 8, cloud_size_ = 0;
+    bool has_seed_ = false;
+    unsigned seed_ = 0;
+};
+
+class ModelCalibrator {
+public:
+    static constexpr const char* PHASE1_NAME = "Phase1";
+    static constexpr const char* PHASE2_NAME = "Phase2";
+    ModelCalibrator(std::unique_ptr<IParameterManager> parameterManager, std::unique_ptr<IObjectiveFunction> objectiveFunction,
+                    std::map<std::string, std::unique_ptr<IOptimizationAlgorithm>> algorithms);
+    void calibrate(const std::map<std::string, double>& phase1_settings, const std::map<std::string, double>& phase2_settings);
+    const VectorXd& getBestParameterVector() const { return best_params_vector_; }
+    double getBestObjectiveValue() const { return best_objective_value_; }
+    const std::vector<VectorXd>& getMCMCSamples() const { return phase2_result_.samples; }
+    const std::vector<double>& getMCMCObjectiveValues() const { return mcmcObjectiveValues_; }
+    const OptimizationResult& getPhase1Result() const { return phase1_result_; }
+    const OptimizationResult& getPhase2Result() const { return phase2_result_; }
+    IParameterManager& getParameterManager() { return *parameterManager_; }
+    IObjectiveFunction& getObjectiveFunction() { return *objectiveFunction_; }
+
+private:
+    std::unique_ptr<IParameterManager> parameterManager_;
+    std::unique_ptr<IObjectiveFunction> objectiveFunction_;
+    std::map<std::string, std::unique_ptr<IOptimizationAlgorithm>> optimization_algorithms_;
+    VectorXd best_params_vector_;
+    double best_objective_value_ = -std::numeric_limits<double>::infinity();
+    OptimizationResult phase1_result_, phase2_result_;
+    std::vector<double> mcmcObjectiveValues_;
+};
+
+class SEPAIHRDModelCalibration {
+public:
+    SEPAIHRDModelCalibration(std::shared_ptr<AgeSEPAIHRDModel> model_ptr, const CalibrationData& calibration_data,
+                             const std::vector<double>& time_points, const std::vector<std::string>& params_to_calibrate,
+                             const std::map<std::string, double>& proposal_sigmas,
+                             const std::map<std::string, std::pair<double, double>>& param_bounds,
+                             std::shared_ptr<IOdeSolverStrategy> solver_strategy = std::make_shared<Dopri5SolverStrategy>(),
+                             std::shared_ptr<ISimulationCache> cache = std::make_shared<SimulationCache>());
+    SEPAIHRDParameterManager& getParameterManager();
+    VectorXd getCurrentParameterValues();
+    ModelCalibrator runPSOMCMC(const std::map<std::string, double>& phase1_settings, const std::map<std::string, double>& phase2_settings);
+    ModelCalibrator runHillClimbingMCMC(const std::map<std::string, double>& phase1_settings, const std::map<std::string, double>& phase2_settings);
+
+private:
+    ModelCalibrator setupCalibrator(std::map<std::string, std::unique_ptr<IOptimizationAlgorithm>> algorithms);
+    std::shared_ptr<AgeSEPAIHRDModel> model_;
+    const CalibrationData& observed_data_;       // by const reference, like the reference: the caller owns it
+    std::vector<double> time_points_;
+    std::vector<std::string> params_to_calibrate_;
+    std::map<std::string, double> proposal_sigmas_;
+    std::map<std::string, std::pair<double, double>> param_bounds_;
+    std::shared_ptr<IOdeSolverStrategy> solver_strategy_;
+    std::shared_ptr<ISimulationCache> cache_;
+    VectorXd initial_state_cached_;
+    std::unique_ptr<SEPAIHRDParameterManager> parameter_manager_;
+};
+
+}  // namespace epidemic

