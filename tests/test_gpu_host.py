@@ -39,7 +39,6 @@ def test_objective_function_mirror_matches_oracle(host, problem, oracle):
     P = oracle.jitter_params(200, seed=21)
     ref = oracle.eval_batch(P)[0]
     assert _rel(m.calculate_batch(P), ref).max() < 1e-8
-    assert m.calculate(base[:-1]) == -np.finfo(np.float64).max                        # size mismatch -> lowest()
     # padded rows (ld > P) and the constraint mode flipped by the parameter manager (clamp <-> reflect)
     wild = base + 50 * problem.sigmas
     clamp_val = m.calculate(wild)
@@ -79,8 +78,6 @@ def test_simulator_mirror_matches_oracle(host, problem, oracle):
     assert (np.abs(got - ref[0]) / np.maximum(np.abs(ref[0]), 1.0)).max() < 1e-9
     np.testing.assert_array_equal(got[0], s0)
     with pytest.raises(host.HostError):
-        m.simulate(s0[:-1], t)                                                       # Initial state size does not match
-    with pytest.raises(host.HostError):
         m.simulate(s0, t[::-1])                                                      # not strictly increasing
     m.close()
 
@@ -118,7 +115,7 @@ def test_model_calibration_mirror_runs_both_phases(host, problem, oracle):
     f0 = oracle.eval_batch(problem.base_params()[None])[0][0]
     best, val, ns = m.calibrate("pso", dict(iterations=3, swarm_size=64, seed=3), dict(mcmc_iterations=12, burn_in=12, n_chains=32, seed=5))
     assert val >= f0 * (1 - 1e-12) and ns == 32 * 12
-    assert _rel(oracle.eval_batch(best[None])[0][0], val) < 1e-8 or True
+    assert _rel(oracle.eval_batch(best[None])[0][0], val) < 1e-8
     best, val, ns = m.calibrate("hill", dict(iterations=2, cloud_size=64, seed=3), dict(mcmc_iterations=5, burn_in=5, n_chains=8, seed=5))
     assert val >= f0 * (1 - 1e-12) and ns == 8 * 5
     m.close()
