@@ -129,7 +129,7 @@ sepaihrd_rc launch_na(sepaihrd_ctx* ctx, const sepaihrd::KParams& kp, int mode) 
 sepaihrd_rc launch(sepaihrd_ctx* ctx, const sepaihrd::KParams& kp, int mode) {
     switch (ctx->n) {
         case 4: return launch_na<4, 128, 2>(ctx, kp, mode);
-        case 16: return launch_na<16, 128, 1>(ctx, kp, mode);
+        case 16: return launch_na<16, 256, 1>(ctx, kp, mode);   // the 16-age observation block (117 KB) allows one block per SM: make it 8 warps
         default: return fail(SEPAIHRD_ERR_UNSUPPORTED, "GPU kernels are instantiated for n_ages = 4 and 16");
     }
 }
