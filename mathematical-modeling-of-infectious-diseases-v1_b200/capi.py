@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libsepaihrd_b200.so")
+# SEPAIHRD_LIB: A/B timing of an experimental build of the same C ABI (tools/ only; tests and bench use the default)
+LIB_PATH = os.environ.get("SEPAIHRD_LIB") or os.path.join(_HERE, "csrc", "libsepaihrd_b200.so")
 _lib = None
 
 _dp = C.POINTER(C.c_double)

@@ -64,7 +64,10 @@ struct sepaihrd_ctx {
     std::vector<double> blob;   // host image
     sepaihrd::KParams kp{};     // offsets etc. (I/O fields filled per call)
     double* d_blob = nullptr;
+    unsigned* d_tile_counter = nullptr;
     cudaStream_t own_stream = nullptr;
+    cudaStream_t copy_stream = nullptr;   // host-pointer entry points: H2D / early D2H next to the compute stream
+    cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_kernel = nullptr;
     cudaStream_t stream = nullptr;
     int num_sms = 0;
     // scratch for the host-pointer entry points (grown on demand)
@@ -94,7 +97,11 @@ sepaihrd_rc launch_t(sepaihrd_ctx* ctx, const sepaihrd::KParams& kp_in) {
     using namespace sepaihrd;
     KParams kp = kp_in;
     constexpr int SETS = THREADS / NA;
-    kp.tiles = (kp.B + SETS - 1) / SETS;
+    constexpr int WSETS = (32 / NA) > 0 ? (32 / NA) : 1;
+    kp.tiles = (kp.B + WSETS - 1) / WSETS;
+    if (kp.tiles > 0xffff0000LL) return fail(SEPAIHRD_ERR_UNSUPPORTED, "batch too large for one launch");
+    kp.tile_counter = ctx->d_tile_counter;
+    CUDA_TRY(cudaMemsetAsync(ctx->d_tile_counter, 0, sizeof(unsigned), ctx->stream));
     auto kern = sepaihrd_batch_kernel<NA, STRICT, MODE, THREADS, MINBLOCKS, LOOP>;
     const size_t smem = (size_t)kp.blob_bytes + sizeof(double) * (SETS * (size_t)(kp.slot_stride + ((kp.seg_stride + 1) & ~1)) + 2 * THREADS + (size_t)NA * THREADS) + 16;
     static bool attr_set[64] = {};   // per device
@@ -106,7 +113,7 @@ sepaihrd_rc launch_t(sepaihrd_ctx* ctx, const sepaihrd::KParams& kp_in) {
     int occ = 0;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, smem));
     if (occ < 1) return fail(SEPAIHRD_ERR_CUDA, "kernel does not fit on an SM");
-    long long grid = std::min<long long>(kp.tiles, (long long)ctx->num_sms * occ);
+    long long grid = std::min<long long>((kp.tiles * 32 + THREADS - 1) / THREADS, (long long)ctx->num_sms * occ);
     if (grid < 1) grid = 1;
     kern<<<(unsigned)grid, THREADS, smem, ctx->stream>>>(kp);
     CUDA_TRY(cudaGetLastError());
@@ -350,7 +357,11 @@ sepaihrd_rc sepaihrd_create(const sepaihrd_problem* pb, int32_t device, sepaihrd
     cudaError_t e = cudaGetDeviceProperties(&prop, device);
     if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_blob, kp.blob_bytes);
     if (e == cudaSuccess) e = cudaMemcpy(ctx->d_blob, B.data(), kp.blob_bytes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_tile_counter, sizeof(unsigned));
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&ctx->ev_copy[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_kernel, cudaEventDisableTiming);
     if (e != cudaSuccess) {
         std::string msg = std::string("CUDA setup failed: ") + cudaGetErrorString(e);
         sepaihrd_destroy(ctx);
@@ -368,11 +379,15 @@ void sepaihrd_destroy(sepaihrd_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->d_blob) cudaFree(ctx->d_blob);
+    if (ctx->d_tile_counter) cudaFree(ctx->d_tile_counter);
     if (ctx->d_params) cudaFree(ctx->d_params);
     if (ctx->d_out) cudaFree(ctx->d_out);
     if (ctx->d_status) cudaFree(ctx->d_status);
     if (ctx->d_steps) cudaFree(ctx->d_steps);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    for (int i = 0; i < 2; ++i) if (ctx->ev_copy[i]) cudaEventDestroy(ctx->ev_copy[i]);
+    if (ctx->ev_kernel) cudaEventDestroy(ctx->ev_kernel);
     delete ctx;
 }
 
@@ -442,14 +457,36 @@ sepaihrd_rc sepaihrd_eval_batch(sepaihrd_ctx* ctx, const double* params, int64_t
     if ((rc = grow(&ctx->d_out, &ctx->cap_out, (size_t)B)) != SEPAIHRD_OK) return rc;
     if ((rc = grow(&ctx->d_status, &ctx->cap_status, (size_t)B)) != SEPAIHRD_OK) return rc;
     if (out_steps && (rc = grow(&ctx->d_steps, &ctx->cap_steps, (size_t)B * 2)) != SEPAIHRD_OK) return rc;
-    // chunked so the H2D copy of chunk c+1 overlaps the kernel of chunk c (two streams would be needed for
-    // full overlap with pageable memory; with pinned callers cudaMemcpyAsync already is asynchronous)
-    CUDA_TRY(cudaMemcpyAsync(ctx->d_params, params, sizeof(double) * (size_t)B * ld, cudaMemcpyHostToDevice, ctx->stream));
-    rc = sepaihrd_eval_batch_device(ctx, ctx->d_params, B, ld, ctx->d_out, ctx->d_status, out_steps ? ctx->d_steps : nullptr);
-    if (rc != SEPAIHRD_OK) return rc;
-    CUDA_TRY(cudaMemcpyAsync(out_ll, ctx->d_out, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost, ctx->stream));
-    if (out_status) CUDA_TRY(cudaMemcpyAsync(out_status, ctx->d_status, sizeof(unsigned) * (size_t)B, cudaMemcpyDeviceToHost, ctx->stream));
-    if (out_steps) CUDA_TRY(cudaMemcpyAsync(out_steps, ctx->d_steps, sizeof(int) * (size_t)B * 2, cudaMemcpyDeviceToHost, ctx->stream));
+    // Two chunks on two streams: while the kernel works on the first ~1/12 of the batch, the copy stream brings the
+    // rest over (H2D moves ~10x more sets per second than the kernel consumes), so only the first chunk's copy and the
+    // 12-byte-per-set results are exposed.  Small batches go as one piece.
+    const int64_t first = (B >= (1 << 16)) ? ((B / 12 + 255) / 256) * 256 : B;
+    const int64_t off[3] = {0, first, B};
+    const int n_chunks = (first < B) ? 2 : 1;
+    for (int c = 0; c < n_chunks; ++c) {
+        const int64_t b0 = off[c], nb = off[c + 1] - off[c];
+        CUDA_TRY(cudaMemcpyAsync(ctx->d_params + b0 * ld, params + b0 * ld, sizeof(double) * (size_t)nb * ld, cudaMemcpyHostToDevice, ctx->copy_stream));
+        CUDA_TRY(cudaEventRecord(ctx->ev_copy[c], ctx->copy_stream));
+    }
+    for (int c = 0; c < n_chunks; ++c) {
+        const int64_t b0 = off[c], nb = off[c + 1] - off[c];
+        CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[c], 0));
+        rc = sepaihrd_eval_batch_device(ctx, ctx->d_params + b0 * ld, nb, ld, ctx->d_out + b0, ctx->d_status + b0,
+                                        out_steps ? ctx->d_steps + 2 * b0 : nullptr);
+        if (rc != SEPAIHRD_OK) return rc;
+        if (c + 1 < n_chunks) {      // results of the first chunk go back under the second kernel
+            CUDA_TRY(cudaEventRecord(ctx->ev_kernel, ctx->stream));
+            CUDA_TRY(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_kernel, 0));
+            CUDA_TRY(cudaMemcpyAsync(out_ll + b0, ctx->d_out + b0, sizeof(double) * (size_t)nb, cudaMemcpyDeviceToHost, ctx->copy_stream));
+            if (out_status) CUDA_TRY(cudaMemcpyAsync(out_status + b0, ctx->d_status + b0, sizeof(unsigned) * (size_t)nb, cudaMemcpyDeviceToHost, ctx->copy_stream));
+            if (out_steps) CUDA_TRY(cudaMemcpyAsync(out_steps + 2 * b0, ctx->d_steps + 2 * b0, sizeof(int) * (size_t)nb * 2, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        } else {
+            CUDA_TRY(cudaMemcpyAsync(out_ll + b0, ctx->d_out + b0, sizeof(double) * (size_t)nb, cudaMemcpyDeviceToHost, ctx->stream));
+            if (out_status) CUDA_TRY(cudaMemcpyAsync(out_status + b0, ctx->d_status + b0, sizeof(unsigned) * (size_t)nb, cudaMemcpyDeviceToHost, ctx->stream));
+            if (out_steps) CUDA_TRY(cudaMemcpyAsync(out_steps + 2 * b0, ctx->d_steps + 2 * b0, sizeof(int) * (size_t)nb * 2, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+    }
+    CUDA_TRY(cudaStreamSynchronize(ctx->copy_stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return SEPAIHRD_OK;
 }

@@ -72,7 +72,8 @@ struct KParams {
     int traj_what, traj_stride, traj_rows;
     const double* init_states; // optional [B][11n] (or one shared state when init_stride == 0): Simulator::run semantics
     long long init_stride;
-    long long tiles;           // ceil(B / sets_per_block)
+    long long tiles;           // ceil(B / sets_per_warp)
+    unsigned* tile_counter;    // zeroed before every launch (tiles < 2^32 - grid warps)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -561,8 +562,16 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) sepaihrd_batch_kernel(cons
     const int sl_beta0 = 0, sl_kappa0 = kp.nb, sl_scal0 = kp.nb + kp.nk, sl_age0 = sl_scal0 + 7;
     const int sl_mult0 = sl_age0 + 8 * n, sl_seed = sl_mult0 + 8, sl_runup = sl_mult0 + 9, sl_beta = sl_mult0 + 10;
 
-    for (long long tile = blockIdx.x; tile < kp.tiles; tile += gridDim.x) {
-        const long long b_raw = tile * SETS + grp;
+    // Work is handed out per WARP (32 / NA sets at a time) from a global counter: warps never wait for the other
+    // warps of their block and the tail of a launch is one warp-tile long.
+    constexpr int WSETS = (32 / NA) > 0 ? (32 / NA) : 1;
+    const int grp_in_warp = (threadIdx.x & 31) / NA;
+    while (true) {
+        unsigned wt = 0;
+        if ((threadIdx.x & 31) == 0) wt = atomicAdd(kp.tile_counter, 1u);
+        wt = __shfl_sync(FULL, wt, 0);
+        if ((long long)wt >= kp.tiles) break;
+        const long long b_raw = (long long)wt * WSETS + grp_in_warp;
         const bool have = b_raw < kp.B;
         const long long b = have ? b_raw : (kp.B - 1);   // idle groups shadow the last set; nothing is written for them
 
@@ -750,7 +759,10 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) sepaihrd_batch_kernel(cons
                 const double cur = active ? std_min(dt, rem) : 0.0;   // min_abs(dt, t_next - t)
                 const double t_end = t + cur;
                 const unsigned m_more = __ballot_sync(FULL, active && ((t_next - t_end) > DBL_EPSILON));
-                const unsigned m_low = __ballot_sync(FULL, dt < hmax);
+                // growth can matter only if the largest possible proposal, cur * 0.9 (5^-5)^(-1/5), exceeds the carried dt
+                // (dt' = max(dt, cur * g), g <= that factor); the 1e-12 covers the few-ulp error of the fast power
+                const bool can_grow = (dt < hmax) && (cur * (kp.grow_max * (1.0 + 1e-12)) > dt);
+                const unsigned m_low = __ballot_sync(FULL, can_grow);
                 StepSched sc;
                 sc.ba_step = ba; sc.s_lo = seg; sc.bp = s_bp; sc.beff = my_beff; sc.nseg = nseg; sc.a = q.a;
                 sc.mb = smb + threadIdx.x; sc.mb_stride = THREADS;
@@ -803,7 +815,8 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) sepaihrd_batch_kernel(cons
                 const bool reject = (g_rej & lane_bit) != 0;
                 double err = 0.0, facv = 0.0;
                 if (m_val != 0) {
-                    // arg-max of num/den by a cross-multiplication tournament, then ONE exact division per lane
+                    // arg-max of num/den by a cross-multiplication tournament, then ONE division per lane (eleven parallel
+                    // reciprocal chains instead were measured: no faster, and their 11 extra live doubles spill)
 #pragma unroll
                     for (int stride = 1; stride < NCOMP; stride *= 2) {
 #pragma unroll
@@ -826,7 +839,7 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) sepaihrd_batch_kernel(cons
                 } else if (active) {
                     t = t_end;
                     rem = t_next - t;
-                    if (dt < hmax) {
+                    if (can_grow) {
                         double g = 0.0;                                  // err >= 0.5: the step is kept
                         if (!(g_ns & lane_bit)) g = kp.grow_max;          // err <= 5^-5
                         else if (!(g_ng & lane_bit) && err < 0.5) g = facv;
@@ -976,7 +989,8 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) sepaihrd_batch_kernel(cons
                     const unsigned bal = __ballot_sync(FULL, big0 | big1 | big2);
                     reject = (bal & gmask) != 0;
                     if ((flags & 1u) || (bal & m_need)) {
-                        // arg-max of num/den by a cross-multiplication tournament, then ONE exact division per lane
+                        // arg-max of num/den by a cross-multiplication tournament, then ONE division per lane (eleven parallel
+                    // reciprocal chains instead were measured: no faster, and their 11 extra live doubles spill)
 #pragma unroll
                         for (int stride = 1; stride < NCOMP; stride *= 2) {
 #pragma unroll
