@@ -43,6 +43,9 @@ B_PER_GPU = 1 << 20
 DISTINCT = 1 << 16
 FLOP_PER_ATTEMPT = 3750.0      # 6 RHS + stage/solution/error combinations + error norm, n = 4
 FLOP_PER_SET_FIXED = 22000.0   # 3672 likelihood terms * ~6
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch at B = 2^20 (ncu --set full, profiles/r01_v8_ncu_full_summary.txt):
+# 529.3 MB + 17.1 MB, i.e. the algorithmic 532.7 MB (62 doubles in, 12 bytes out per set) -- no re-reads.
+NCU_DRAM_BYTES_PER_LAUNCH_1M = 529.328384e6 + 17.067520e6
 
 
 def workload_config(n_gpus: int, batch: int) -> dict:
@@ -269,7 +272,8 @@ def main():
                "gpu_launches": int(launches1 - launches0),
                "gpu_launches_e2e": int(launches2 - launches1),
                "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                            "traffic": None, "kernel": "sepaihrd_batch_kernel<4,fast,LL>",
+                            "traffic": NCU_DRAM_BYTES_PER_LAUNCH_1M if B == (1 << 20) else None,
+                            "kernel": "sepaihrd_batch_kernel<4,fast,LL>",
                             "flop_per_launch": flop_per_launch, "attempts_per_set": attempts_total / B,
                             "launch_ms": launch_s * 1e3,
                             "peak_source": "measured live: sepaihrd_measure_fp64_peak (dependent DFMA chains), x2 FLOP per DFMA; "

@@ -70,11 +70,9 @@ else:
         launch(a.chunk); torch.cuda.synchronize()
         comm.barrier(); t0 = time.perf_counter()
         done = 0
-        acc = torch.zeros((K, W), dtype=torch.float64, device=f"cuda:{dev}")
-        while done < n_local:
+        while done < n_local:                      # the trajectories stay on the device (a consumer would read d_out here)
             nb = min(a.chunk, n_local - done)
             launch(nb)
-            acc += d_out[:nb].sum(dim=0)            # stand-in consumer: the trajectories stay on the device
             done += nb
         torch.cuda.synchronize(); comm.barrier(); dt = time.perf_counter() - t0
         # parity on a small subsample against the oracle
