@@ -22,6 +22,15 @@ from .distributed import Comm, shard_range
 Evaluate = Callable[[np.ndarray], np.ndarray]
 
 
+def _host_threads(comm: Comm) -> None:
+    """Give the C++ sampler loops this rank's share of the host cores (torchrun exports OMP_NUM_THREADS=1)."""
+    import os
+    if os.environ.get("SEPAIHRD_HOST_THREADS"):
+        hostlib.set_threads(int(os.environ["SEPAIHRD_HOST_THREADS"]))
+    elif comm.world > 1:
+        hostlib.set_threads(max(1, (os.cpu_count() or 1) // comm.world))
+
+
 def _loglik(evaluate: Evaluate, x: np.ndarray) -> np.ndarray:
     out = evaluate(x)
     if isinstance(out, tuple):          # BatchEvaluator.eval_batch returns (ll, status)
@@ -35,6 +44,7 @@ def run_multichain_mh(evaluate: Evaluate, sigmas, lower, upper, initial, n_chain
     the ranks of ``comm``; one batch evaluation per iteration per rank; all_gather of the log-likelihoods per
     iteration.  Returns a dict with the gathered final state, the accept matrix of the local shard and timings."""
     comm = comm or Comm()
+    _host_threads(comm)
     lo, hi = shard_range(n_chains, comm.rank, comm.world)
     counts = [shard_range(n_chains, r, comm.world)[1] - shard_range(n_chains, r, comm.world)[0] for r in range(comm.world)]
     pm = hostlib.ParameterManager(sigmas, lower, upper, mode=1)        # MCMC_REFLECT (MetropolisHastingsSampler.cpp:207-210)
@@ -76,6 +86,7 @@ def run_pso(evaluate: Evaluate, sigmas, lower, upper, swarm_size: int, iteration
     """Particle swarm with the global-best topology (ParticleSwarmOptimizer.cpp:106-247, 330-425, 576-618), particles
     sharded over the ranks; per iteration one batch evaluation per rank, then the global-best reduction."""
     comm = comm or Comm()
+    _host_threads(comm)
     lo, hi = shard_range(swarm_size, comm.rank, comm.world)
     pm = hostlib.ParameterManager(sigmas, lower, upper, mode=0)        # OPTIMIZATION_CLAMP (ModelCalibrator.cpp:62-66)
     st = dict(iterations=iterations, swarm_size=swarm_size, particle_offset=lo, local_count=hi - lo, seed=seed)

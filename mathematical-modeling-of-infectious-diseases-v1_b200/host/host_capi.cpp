@@ -2,6 +2,7 @@
 #include "host_capi.h"
 
 #include <cmath>
+#include <omp.h>
 #include <cstring>
 #include <string>
 
@@ -116,6 +117,11 @@ struct sepaihrd_host_model {
 extern "C" {
 
 const char* sepaihrd_host_last_error(void) { return g_err.c_str(); }
+
+int32_t sepaihrd_host_set_threads(int32_t n) {
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+}
 
 // ---- parameter manager ---------------------------------------------------------------------------------------
 int32_t sepaihrd_host_pm_create(int32_t n, const double* sigmas, const double* lo, const double* hi, int32_t mode, sepaihrd_host_pm** out) {

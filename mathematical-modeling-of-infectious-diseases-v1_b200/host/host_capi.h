@@ -23,6 +23,11 @@ extern "C" {
 
 const char* sepaihrd_host_last_error(void);
 
+/* OpenMP threads of the host-side sampler loops (proposal / particle updates).  torchrun exports OMP_NUM_THREADS=1 to
+ * every rank; the drivers call this with (host cores / ranks per node).  n <= 0 leaves the setting alone; returns the
+ * number of threads now in use. */
+int32_t sepaihrd_host_set_threads(int32_t n);
+
 /* B log-posteriors for B parameter rows ([B][ld] row-major).  Return non-zero to abort the run. */
 typedef int32_t (*sepaihrd_host_batch_fn)(void* user, const double* params, int64_t B, int64_t ld, double* out);
 

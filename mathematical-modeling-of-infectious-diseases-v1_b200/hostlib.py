@@ -29,6 +29,7 @@ BATCH_FN = C.CFUNCTYPE(C.c_int32, C.c_void_p, _dp, C.c_int64, C.c_int64, _dp)
 # every symbol host/host_capi.h declares
 SIGNATURES = {
     "sepaihrd_host_last_error": (C.c_char_p, []),
+    "sepaihrd_host_set_threads": (C.c_int32, [C.c_int32]),
     "sepaihrd_host_pm_create": (C.c_int32, [C.c_int32, _vp, _vp, _vp, C.c_int32, _vpp]),
     "sepaihrd_host_pm_set_mode": (C.c_int32, [_vp, C.c_int32]),
     "sepaihrd_host_pm_apply_constraints": (C.c_int32, [_vp, _vp, _vp]),
@@ -86,6 +87,11 @@ def load_library():
 def check(rc: int):
     if rc != 0:
         raise HostError((load_library().sepaihrd_host_last_error() or b"").decode())
+
+
+def set_threads(n: int) -> int:
+    """OpenMP threads of the C++ sampler loops (torchrun pins OMP_NUM_THREADS=1 per rank)."""
+    return int(load_library().sepaihrd_host_set_threads(int(n)))
 
 
 def _c64(a) -> np.ndarray:
