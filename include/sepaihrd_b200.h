@@ -179,6 +179,19 @@ sepaihrd_rc sepaihrd_simulate_from_state_device(sepaihrd_ctx* ctx, const double*
                                                 const double* d_initial_states, int64_t state_stride, int32_t what,
                                                 int32_t stride, double* d_out, uint32_t* d_out_status);
 
+/* Replaces ResultAggregator::aggregatePosteriorPredictives (src/model/ResultAggregator.cpp:174-412): B posterior draws are
+ * simulated from ONE fixed initial state (quirk Q9) and reduced on the device to quantiles of six series on the output
+ * days t >= 0 (T of them): daily hospitalisations, ICU admissions, deaths (first differences, clamped at 0, .cpp:292-335)
+ * and their running sums (.cpp:337-351).
+ *   probs          [n_probs] in [0, 1]  (the reference uses 0.025, 0.05, 0.5, 0.95, 0.975, .cpp:233)
+ *   out_quantiles  [6][T][n_ages][n_probs]; NaN where no valid draw exists
+ *   out_valid_draws (optional) draws whose simulation succeeded (failed ones are skipped like .cpp:290)
+ * Difference from the reference (documented in DESIGN.md): exact sample quantiles with linear interpolation from a full
+ * sort, not Boost's order-dependent extended P-square estimate. */
+sepaihrd_rc sepaihrd_posterior_predictive(sepaihrd_ctx* ctx, const double* params, int64_t B, int64_t ld,
+                                          const double* initial_state, int32_t n_probs, const double* probs,
+                                          double* out_quantiles, int64_t* out_valid_draws);
+
 /* Block until everything enqueued on the ctx stream has finished. */
 sepaihrd_rc sepaihrd_synchronize(sepaihrd_ctx* ctx);
 

@@ -11,6 +11,7 @@
 #include <string>
 #include <vector>
 
+#include "sepaihrd_internal.h"
 #include "sepaihrd_kernels.cuh"
 
 namespace {
@@ -57,7 +58,7 @@ bool read_index(const char* s, long* out) {
 
 struct sepaihrd_ctx {
     int device = 0;
-    int n = 0, K = 0, n_obs = 0, nb = 0, nk = 0, P = 0, nslots = 0, nseg = 0, runup_offset = 0;
+    int n = 0, K = 0, n_obs = 0, nb = 0, nk = 0, P = 0, nslots = 0, nseg = 0, runup_offset = 0, n_nonneg = 0;
     int constraint_mode = 0, math_mode = SEPAIHRD_MATH_FAST;
     bool obs_mismatch = false;
     double abs_tol = 1e-6, rel_tol = 1e-6, dt_hint = 1.0, hmax = 1.0;
@@ -251,6 +252,8 @@ sepaihrd_rc sepaihrd_create(const sepaihrd_problem* pb, int32_t device, sepaihrd
     // runup_offset_ = first index with t >= 0 (ObjectiveFunction.cpp:39-46)
     ctx->runup_offset = 0;
     for (int i = 0; i < K; ++i) if (pb->times[i] >= 0.0) { ctx->runup_offset = i; break; }
+    ctx->n_nonneg = 0;
+    for (int i = 0; i < K; ++i) ctx->n_nonneg += (pb->times[i] >= 0.0) ? 1 : 0;
     ctx->obs_mismatch = (K - ctx->runup_offset) != pb->n_obs;   // calculate() then returns lowest() (.cpp:176-178)
     ctx->hmax = 0.0;
     for (int i = 1; i < K; ++i) ctx->hmax = std::max(ctx->hmax, pb->times[i] - pb->times[i - 1]);
@@ -441,7 +444,7 @@ sepaihrd_rc sepaihrd_eval_batch_device(sepaihrd_ctx* ctx, const double* d_params
     kp.constraint_mode = ctx->constraint_mode;
     kp.params = d_params; kp.B = B; kp.ld = ld;
     kp.out_ll = d_out_ll; kp.out_status = d_out_status; kp.out_steps = d_out_steps;
-    kp.out_traj = nullptr; kp.traj_what = 0; kp.traj_stride = 1; kp.traj_rows = 0;
+    kp.out_traj = nullptr; kp.traj_what = 0; kp.traj_stride = 1; kp.traj_rows = 0; kp.traj_draw_minor = 0;
     kp.init_states = nullptr; kp.init_stride = 0;
     return launch(ctx, kp, sepaihrd::MODE_LL);
 }
@@ -493,7 +496,7 @@ sepaihrd_rc sepaihrd_eval_batch(sepaihrd_ctx* ctx, const double* params, int64_t
 
 static sepaihrd_rc simulate_device_impl(sepaihrd_ctx* ctx, const double* d_params, int64_t B, int64_t ld,
                                         const double* d_init, int64_t init_stride,
-                                        int32_t what, int32_t stride, double* d_out, uint32_t* d_out_status) {
+                                        int32_t what, int32_t stride, double* d_out, uint32_t* d_out_status, bool draw_minor = false) {
     if (!ctx || !d_out || (B > 0 && !d_params)) return fail(SEPAIHRD_ERR_INVALID_ARGUMENT, "null argument");
     if (B < 0 || ld < ctx->P) return fail(SEPAIHRD_ERR_INVALID_ARGUMENT, "Parameter vector size mismatch.");
     if (what != SEPAIHRD_TRAJ_FULL && what != SEPAIHRD_TRAJ_OBSERVED) return fail(SEPAIHRD_ERR_INVALID_ARGUMENT, "bad trajectory selector");
@@ -505,6 +508,7 @@ static sepaihrd_rc simulate_device_impl(sepaihrd_ctx* ctx, const double* d_param
     kp.params = d_params; kp.B = B; kp.ld = ld;
     kp.out_ll = nullptr; kp.out_status = d_out_status; kp.out_steps = nullptr;
     kp.out_traj = d_out; kp.traj_what = what; kp.traj_stride = stride; kp.traj_rows = (ctx->K + stride - 1) / stride;
+    kp.traj_draw_minor = draw_minor ? 1 : 0;
     kp.init_states = d_init; kp.init_stride = init_stride;
     return launch(ctx, kp, sepaihrd::MODE_TRAJ);
 }
@@ -604,3 +608,14 @@ sepaihrd_rc sepaihrd_measure_fp64_peak(int32_t device, double* out_dfma_per_seco
 }
 
 }  // extern "C"
+
+// ---- accessors for the other translation units of the library (sepaihrd_internal.h) -----------------------------
+namespace sepaihrd_internal {
+Dims dims(const sepaihrd_ctx* ctx) { return Dims{ctx->n, ctx->K, ctx->runup_offset, ctx->n_nonneg, ctx->P, ctx->device}; }
+cudaStream_t stream(const sepaihrd_ctx* ctx) { return ctx->stream; }
+sepaihrd_rc fail_with(sepaihrd_rc rc, const char* msg) { return fail(rc, msg); }
+sepaihrd_rc simulate_observed_draw_minor(sepaihrd_ctx* ctx, const double* d_params, long long B, long long ld, const double* d_init,
+                                         double* d_out, unsigned* d_status) {
+    return simulate_device_impl(ctx, d_params, B, ld, d_init, 0, SEPAIHRD_TRAJ_OBSERVED, 1, d_out, d_status, true);
+}
+}  // namespace sepaihrd_internal

@@ -1,0 +1,18 @@
+// sepaihrd_internal.h -- the few ctx accessors other translation units of the library need (not part of the ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include "sepaihrd_b200.h"
+
+namespace sepaihrd_internal {
+
+struct Dims { int n, K, runup_offset, n_nonneg, P, device; };   // n_nonneg: output times >= 0 (they are the last ones)
+Dims dims(const sepaihrd_ctx* ctx);
+cudaStream_t stream(const sepaihrd_ctx* ctx);
+sepaihrd_rc fail_with(sepaihrd_rc rc, const char* msg);
+// D, CumH, CumICU of B draws in the DRAW-MINOR layout [K][3n][B] (device pointers); d_init: one shared state or null
+sepaihrd_rc simulate_observed_draw_minor(sepaihrd_ctx* ctx, const double* d_params, long long B, long long ld, const double* d_init,
+                                         double* d_out, unsigned* d_status);
+
+}  // namespace sepaihrd_internal

@@ -68,8 +68,9 @@ struct KParams {
     double* out_ll;            // [B]
     unsigned* out_status;      // [B] or null
     int* out_steps;            // [B][2] or null
-    double* out_traj;          // MODE_TRAJ: [B][traj_rows][W]
+    double* out_traj;          // MODE_TRAJ: [B][traj_rows][W], or [traj_rows][W][B] when traj_draw_minor
     int traj_what, traj_stride, traj_rows;
+    int traj_draw_minor;       // draws fastest: the layout the posterior-predictive quantile pass reads column by column
     const double* init_states; // optional [B][11n] (or one shared state when init_stride == 0): Simulator::run semantics
     long long init_stride;
     long long tiles;           // ceil(B / sets_per_warp)
@@ -669,10 +670,13 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) sepaihrd_batch_kernel(cons
         double ll_acc_h = 0.0, ll_acc_i = 0.0, ll_acc_d = 0.0;   // STRICT: per stream; FAST: ll_acc_h only
         int n_acc = 0, n_rej = 0;
         double* traj_out = nullptr;
+        size_t t_rs = 0, t_cs = 1;     // row / column strides of this set's trajectory block
         int W = 0;
         if (MODE == MODE_TRAJ) {
             W = (kp.traj_what == SEPAIHRD_TRAJ_FULL) ? NCOMP * n : 3 * n;
-            traj_out = kp.out_traj + (size_t)b * kp.traj_rows * W;
+            traj_out = kp.traj_draw_minor ? kp.out_traj + (size_t)b : kp.out_traj + (size_t)b * kp.traj_rows * W;
+            t_rs = kp.traj_draw_minor ? (size_t)W * (size_t)kp.B : (size_t)W;
+            t_cs = kp.traj_draw_minor ? (size_t)kp.B : (size_t)1;
         }
 
         bool alive = (status == 0);
@@ -720,12 +724,12 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) sepaihrd_batch_kernel(cons
             t = s_times[idx];
             if (MODE == MODE_TRAJ) {
                 if (have && alive && (idx % kp.traj_stride == 0)) {
-                    double* row = traj_out + (size_t)(idx / kp.traj_stride) * W;
+                    double* row = traj_out + (size_t)(idx / kp.traj_stride) * t_rs;
                     if (kp.traj_what == SEPAIHRD_TRAJ_FULL) {
 #pragma unroll
-                        for (int c = 0; c < NCOMP; ++c) row[c * n + age] = x[c];
+                        for (int c = 0; c < NCOMP; ++c) row[(size_t)(c * n + age) * t_cs] = x[c];
                     } else {
-                        row[0 * n + age] = x[8]; row[1 * n + age] = x[9]; row[2 * n + age] = x[10];
+                        row[(size_t)(0 * n + age) * t_cs] = x[8]; row[(size_t)(1 * n + age) * t_cs] = x[9]; row[(size_t)(2 * n + age) * t_cs] = x[10];
                     }
                 }
             } else {
@@ -869,12 +873,12 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) sepaihrd_batch_kernel(cons
             // ---- observer -----------------------------------------------------------------------------
             if (MODE == MODE_TRAJ) {
                 if (have && alive && (idx % kp.traj_stride == 0)) {
-                    double* row = traj_out + (size_t)(idx / kp.traj_stride) * W;
+                    double* row = traj_out + (size_t)(idx / kp.traj_stride) * t_rs;
                     if (kp.traj_what == SEPAIHRD_TRAJ_FULL) {
 #pragma unroll
-                        for (int c = 0; c < NCOMP; ++c) row[c * n + age] = x[c];
+                        for (int c = 0; c < NCOMP; ++c) row[(size_t)(c * n + age) * t_cs] = x[c];
                     } else {
-                        row[0 * n + age] = x[8]; row[1 * n + age] = x[9]; row[2 * n + age] = x[10];
+                        row[(size_t)(0 * n + age) * t_cs] = x[8]; row[(size_t)(1 * n + age) * t_cs] = x[9]; row[(size_t)(2 * n + age) * t_cs] = x[10];
                     }
                 }
             } else {
@@ -1058,7 +1062,7 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) sepaihrd_batch_kernel(cons
             if (have && status != 0) {   // failed sets: NaN-fill every row
                 const double qnan = __longlong_as_double(0x7ff8000000000000LL);
                 for (int r = 0; r < kp.traj_rows; ++r)
-                    for (int w = age; w < W; w += NA) traj_out[(size_t)r * W + w] = qnan;
+                    for (int w = age; w < W; w += NA) traj_out[(size_t)r * t_rs + (size_t)w * t_cs] = qnan;
             }
             if (have && age == 0) {
                 if (kp.out_status) kp.out_status[b] = status;

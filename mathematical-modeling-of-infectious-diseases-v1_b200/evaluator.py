@@ -159,6 +159,31 @@ def _simulate_from_state(self, params, initial_states, what: int = TRAJ_FULL, st
 BatchEvaluator.simulate_from_state = _simulate_from_state
 
 
+PPC_PROBS = (0.025, 0.05, 0.5, 0.95, 0.975)     # ResultAggregator.cpp:233
+PPC_SERIES = ("daily_hospitalizations", "daily_icu_admissions", "daily_deaths",
+              "cumulative_hospitalizations", "cumulative_icu_admissions", "cumulative_deaths")
+
+
+def _posterior_predictive(self, params, initial_state, probs=PPC_PROBS):
+    """ResultAggregator::aggregatePosteriorPredictives on the device: quantiles [6, T, n_ages, len(probs)] of the six
+    PPC_SERIES over the draws (rows of ``params``), all simulated from ``initial_state``; also the number of valid draws."""
+    p = self.problem
+    x = np.ascontiguousarray(params, dtype=np.float64)
+    s0 = np.ascontiguousarray(initial_state, dtype=np.float64)
+    if s0.shape != (p.state_size,):
+        raise ValueError("Initial state size does not match model state size.")
+    pr = np.ascontiguousarray(probs, dtype=np.float64)
+    T = int((p.times >= 0).sum())
+    out = np.empty((6, T, p.n_ages, len(pr)))
+    valid = C.c_int64()
+    capi.check(self._lib.sepaihrd_posterior_predictive(self._h, x.ctypes.data, x.shape[0], x.shape[1], s0.ctypes.data, len(pr), pr.ctypes.data,
+                                                       out.ctypes.data, C.byref(valid)))
+    return out, valid.value
+
+
+BatchEvaluator.posterior_predictive = _posterior_predictive
+
+
 def measure_fp64_peak(device: int = 0) -> float:
     """Measured FP64 pipe peak in DFMA instructions per second (lane-ops): roofline denominator."""
     v = C.c_double()

@@ -319,3 +319,52 @@ def test_simulate_from_caller_supplied_state(problem, oracle, ev_mod):
             np.testing.assert_array_equal(tr[:, 0, :], np.broadcast_to(s0, (20, problem.state_size)))
         with pytest.raises(ValueError):
             ev.simulate_from_state(P, shared[:-1])
+
+
+def _ppc_reference(problem, oracle_obj, P, s0, probs):
+    """numpy restatement of ResultAggregator::aggregatePosteriorPredictives (.cpp:276-371) on oracle trajectories, with exact
+    linear-interpolation sample quantiles."""
+    tr, st = oracle_obj.simulate_from_state(P, s0, what=1)          # [B][K][3n]: D | CumH | CumICU
+    n = problem.n_ages
+    T = int((problem.times >= 0).sum()); first = problem.n_times - T
+    ok = st == 0
+    tr = tr[ok]
+    blocks = {"hosp": tr[:, :, n:2 * n], "icu": tr[:, :, 2 * n:3 * n], "deaths": tr[:, :, 0:n]}
+    init = {"hosp": s0[9 * n:10 * n], "icu": s0[10 * n:11 * n], "deaths": s0[8 * n:9 * n]}
+    out = []
+    daily_all = []
+    for key in ("hosp", "icu", "deaths"):
+        X = blocks[key]
+        prev = X[:, first - 1] if first > 0 else np.broadcast_to(init[key], X[:, 0].shape)
+        full = np.concatenate([prev[:, None, :], X[:, first:]], axis=1)
+        daily_all.append(np.maximum(0.0, np.diff(full, axis=1)))
+    series = daily_all + [np.cumsum(d, axis=1) for d in daily_all]
+    for S in series:
+        out.append(np.moveaxis(np.quantile(S, probs, axis=0), 0, -1))          # [T][n][Q]
+    return np.stack(out), int(ok.sum())
+
+
+def test_posterior_predictive_quantiles_match_numpy_on_oracle_trajectories(problem, orc, ev_mod, pkg):
+    """Device posterior-predictive aggregation (trajectory kernel -> series -> segmented sort -> quantiles) against the
+    reference's incidence rule applied to oracle trajectories; two draws are invalid (negative kappa) and must be skipped."""
+    loose = problem.__class__.from_json(dict(problem.to_json()))
+    k2 = loose.param_names.index("kappa_2")
+    loose.lower_bound[k2] = -1.0
+    o = orc.Oracle(loose)
+    P = o.jitter_params(301, seed=41)
+    P[7, k2] = -0.5; P[123, k2] = -0.25
+    s0 = problem.data_initial_state
+    probs = (0.025, 0.05, 0.5, 0.95, 0.975)
+    ref, n_ok = _ppc_reference(loose, o, P, s0, probs)
+    with ev_mod.BatchEvaluator(loose, device=0) as ev:
+        got, valid = ev.posterior_predictive(P, s0, probs)
+    assert valid == n_ok == 299
+    assert got.shape == ref.shape == (6, int((problem.times >= 0).sum()), problem.n_ages, 5)
+    err = np.abs(got - ref) / np.maximum(np.abs(ref), 1e-6)
+    assert err.max() < 1e-8, err.max()
+    assert np.all(np.diff(got, axis=-1) >= 0)                                       # quantiles are ordered
+    assert np.all(np.diff(got[3:], axis=1) >= -1e-9)                                # cumulative series are non-decreasing in time
+    # a single draw: every quantile is that draw's value
+    with ev_mod.BatchEvaluator(loose, device=0) as ev:
+        one, v1 = ev.posterior_predictive(P[:1], s0, (0.0, 0.5, 1.0))
+    assert v1 == 1 and np.all(one[..., 0] == one[..., 2])
