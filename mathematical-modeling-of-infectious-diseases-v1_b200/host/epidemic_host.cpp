@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <random>
 
 namespace epidemic {
 
@@ -515,6 +516,54 @@ void SEPAIHRDObjectiveFunction::calculateBatch(const double* params, int64_t B, 
 void SEPAIHRDObjectiveFunction::calculateBatch(const double* params, int64_t B, int64_t ld, double* out, uint32_t* status, int32_t* steps) const {
     if (sepaihrd_eval_batch(dev_->get(), params, B, ld, out, status, steps) != SEPAIHRD_OK)
         throw SimulationException("SEPAIHRDObjectiveFunction::calculateBatch", std::string("device evaluation failed: ") + sepaihrd_last_error());
+}
+
+// ---- ResultAggregator ---------------------------------------------------------------------------------------------
+PosteriorPredictiveData ResultAggregator::aggregatePosteriorPredictives(const std::vector<VectorXd>& samples, SEPAIHRDParameterManager& pm,
+                                                                        int num_samples_for_ppc, const std::vector<double>& time_points,
+                                                                        const VectorXd& initial_state, const CalibrationData& observed,
+                                                                        std::shared_ptr<AgeSEPAIHRDModel> model, unsigned int random_seed) const {
+    PosteriorPredictiveData ppd;
+    for (double t : time_points) if (t >= 0.0) ppd.time_points.push_back(t);
+    ppd.daily_hospitalizations.observed = observed.getNewHospitalizations();
+    ppd.daily_icu_admissions.observed = observed.getNewICU();
+    ppd.daily_deaths.observed = observed.getNewDeaths();
+    if (ppd.time_points.empty() || samples.empty()) return ppd;                    // .cpp:197-200, 218-221
+    if (!model) throw InvalidParameterException("ResultAggregator", "model template is null");
+    std::vector<size_t> pick;
+    if (num_samples_for_ppc > 0 && static_cast<size_t>(num_samples_for_ppc) < samples.size()) {
+        std::mt19937 gen(random_seed != 0 ? random_seed : std::random_device{}());
+        std::uniform_int_distribution<> distrib(0, static_cast<int>(samples.size()) - 1);
+        for (int i = 0; i < num_samples_for_ppc; ++i) pick.push_back(static_cast<size_t>(distrib(gen)));
+    } else {
+        for (size_t i = 0; i < samples.size(); ++i) pick.push_back(i);
+    }
+    const int64_t P = static_cast<int64_t>(pm.getParameterCount());
+    std::vector<double> rows(pick.size() * static_cast<size_t>(P));
+    for (size_t i = 0; i < pick.size(); ++i) {
+        if (samples[pick[i]].size() != P) throw InvalidParameterException("ResultAggregator", "Parameter vector size mismatch.");
+        std::copy(samples[pick[i]].data(), samples[pick[i]].data() + P, rows.begin() + static_cast<std::ptrdiff_t>(i * static_cast<size_t>(P)));
+    }
+    std::vector<double> lo, hi;
+    for (int i = 0; i < static_cast<int>(P); ++i) { lo.push_back(pm.getLowerBoundForParamIndex(i)); hi.push_back(pm.getUpperBoundForParamIndex(i)); }
+    DeviceContext dev(*model, time_points, nullptr, nullptr, nullptr, initial_state, pm.slots(), lo, hi, pm.getConstraintMode(), 1e-6, 1e-6, 1.0);
+    const double probs[5] = {0.025, 0.05, 0.5, 0.95, 0.975};                        // .cpp:233
+    const int n = model->getNumAgeClasses();
+    const std::ptrdiff_t T = static_cast<std::ptrdiff_t>(ppd.time_points.size());
+    std::vector<double> q(static_cast<size_t>(6 * T * n * 5));
+    if (sepaihrd_posterior_predictive(dev.get(), rows.data(), static_cast<int64_t>(pick.size()), P, initial_state.data(), 5, probs, q.data(),
+                                      &ppd.samples_used) != SEPAIHRD_OK)
+        throw SimulationException("ResultAggregator", std::string("device aggregation failed: ") + sepaihrd_last_error());
+    PosteriorPredictiveData::IncidenceData* series[6] = {&ppd.daily_hospitalizations, &ppd.daily_icu_admissions, &ppd.daily_deaths,
+                                                         &ppd.cumulative_hospitalizations, &ppd.cumulative_icu_admissions, &ppd.cumulative_deaths};
+    for (int s = 0; s < 6; ++s) {
+        MatrixXd* out[5] = {&series[s]->lower_95, &series[s]->lower_90, &series[s]->median, &series[s]->upper_90, &series[s]->upper_95};
+        for (MatrixXd* m : out) m->resize(T, n);
+        for (std::ptrdiff_t t = 0; t < T; ++t)
+            for (int a = 0; a < n; ++a)
+                for (int k = 0; k < 5; ++k) (*out[k])(t, a) = q[static_cast<size_t>(((s * T + t) * n + a) * 5 + k)];
+    }
+    return ppd;
 }
 
 }  // namespace epidemic

@@ -358,4 +358,26 @@ private:
     std::unique_ptr<DeviceContext> dev_;
 };
 
+// ---- posterior-predictive aggregation (include/model/ResultAggregator.hpp, PostCalibrationAnalyser) ---------------
+struct PosteriorPredictiveData {
+    struct IncidenceData { MatrixXd median, lower_90, upper_90, lower_95, upper_95, observed; };    // (day, age)
+    std::vector<double> time_points;                       // the output days t >= 0
+    IncidenceData daily_hospitalizations, daily_icu_admissions, daily_deaths;
+    IncidenceData cumulative_hospitalizations, cumulative_icu_admissions, cumulative_deaths;
+    int64_t samples_used = 0;
+};
+
+class ResultAggregator {
+public:
+    // ResultAggregator::aggregatePosteriorPredictives (src/model/ResultAggregator.cpp:174-412) without the runner /
+    // metrics-calculator indirection: the selected samples go to the device in ONE call (sepaihrd_posterior_predictive).
+    // num_samples_for_ppc > 0 and < samples: that many draws WITH replacement from std::mt19937(random_seed) +
+    // uniform_int_distribution, like the reference (.cpp:262-272); otherwise every sample once.  Quantiles are exact
+    // sample quantiles, not Boost's P-square estimates (known deviations).
+    PosteriorPredictiveData aggregatePosteriorPredictives(const std::vector<VectorXd>& param_samples, SEPAIHRDParameterManager& param_manager,
+                                                          int num_samples_for_ppc, const std::vector<double>& time_points,
+                                                          const VectorXd& initial_state, const CalibrationData& observed_data,
+                                                          std::shared_ptr<AgeSEPAIHRDModel> model_template, unsigned int random_seed = 0) const;
+};
+
 }  // namespace epidemic

@@ -345,6 +345,27 @@ int32_t sepaihrd_host_model_calibrate(sepaihrd_host_model* m, const char* phase1
         if (out_samples) *out_samples = static_cast<int64_t>(c.getMCMCSamples().size());
     });
 }
+int32_t sepaihrd_host_model_posterior_predictive(sepaihrd_host_model* m, const double* samples, int64_t S, int32_t num_samples, uint32_t seed,
+                                                 const double* init, double* out, int64_t* out_used) {
+    return guarded([&] {
+        const auto P = static_cast<std::ptrdiff_t>(m->pm->getParameterCount());
+        std::vector<VectorXd> sv;
+        for (int64_t i = 0; i < S; ++i) sv.push_back(VectorXd::FromPointer(samples + i * P, P));
+        const PosteriorPredictiveData d = ResultAggregator().aggregatePosteriorPredictives(
+            sv, *m->pm, num_samples, m->times, VectorXd::FromPointer(init, m->model->getStateSize()), *m->data, m->model, seed);
+        const PosteriorPredictiveData::IncidenceData* series[6] = {&d.daily_hospitalizations, &d.daily_icu_admissions, &d.daily_deaths,
+                                                                   &d.cumulative_hospitalizations, &d.cumulative_icu_admissions, &d.cumulative_deaths};
+        const std::ptrdiff_t T = static_cast<std::ptrdiff_t>(d.time_points.size());
+        const int n = m->model->getNumAgeClasses();
+        for (int s = 0; s < 6; ++s) {
+            const MatrixXd* q[5] = {&series[s]->lower_95, &series[s]->lower_90, &series[s]->median, &series[s]->upper_90, &series[s]->upper_95};
+            for (std::ptrdiff_t t = 0; t < T; ++t)
+                for (int a = 0; a < n; ++a)
+                    for (int k = 0; k < 5; ++k) out[((s * T + t) * n + a) * 5 + k] = (*q[k])(t, a);
+        }
+        if (out_used) *out_used = d.samples_used;
+    });
+}
 void sepaihrd_host_model_destroy(sepaihrd_host_model* m) { delete m; }
 
 }  // extern "C"

@@ -99,6 +99,10 @@ int32_t sepaihrd_host_model_simulate(sepaihrd_host_model* m, const double* initi
 int32_t sepaihrd_host_model_calibrate(sepaihrd_host_model* m, const char* phase1, int32_t n1, const char* const* keys1, const double* values1,
                                       int32_t n2, const char* const* keys2, const double* values2, double* out_best /* [P] */,
                                       double* out_best_value, int64_t* out_n_samples);
+/* ResultAggregator::aggregatePosteriorPredictives over `samples` ([S][P]); out [6][T][n][5] in the order
+ * lower_95, lower_90, median, upper_90, upper_95 (probabilities 0.025, 0.05, 0.5, 0.95, 0.975) */
+int32_t sepaihrd_host_model_posterior_predictive(sepaihrd_host_model* m, const double* samples, int64_t S, int32_t num_samples_for_ppc,
+                                                 uint32_t random_seed, const double* initial_state, double* out, int64_t* out_samples_used);
 void    sepaihrd_host_model_destroy(sepaihrd_host_model* m);
 
 #ifdef __cplusplus

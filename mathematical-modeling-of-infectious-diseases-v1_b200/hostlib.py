@@ -62,6 +62,7 @@ SIGNATURES = {
     "sepaihrd_host_model_update_parameters": (C.c_int32, [_vp, _vp]),
     "sepaihrd_host_model_simulate": (C.c_int32, [_vp, _vp, _vp, C.c_int32, _vp]),
     "sepaihrd_host_model_calibrate": (C.c_int32, [_vp, C.c_char_p, C.c_int32, _keys, _vp, C.c_int32, _keys, _vp, _vp, _dp, _i64p]),
+    "sepaihrd_host_model_posterior_predictive": (C.c_int32, [_vp, _vp, C.c_int64, C.c_int32, C.c_uint32, _vp, _vp, _i64p]),
     "sepaihrd_host_model_destroy": (None, [_vp]),
 }
 
@@ -303,6 +304,15 @@ class HostModel:
         check(self.L.sepaihrd_host_model_calibrate(self._h, phase1.encode(), n1, k1, v1.ctypes.data, n2, k2, v2.ctypes.data,
                                                    best.ctypes.data, C.byref(val), C.byref(ns)))
         return best, val.value, ns.value
+
+    def posterior_predictive(self, samples, initial_state, num_samples: int = 0, seed: int = 0):
+        """ResultAggregator::aggregatePosteriorPredictives: [6, T, n, 5] (lower_95, lower_90, median, upper_90, upper_95)."""
+        x = _c64(samples); s0 = _c64(initial_state)
+        T = int((self.problem.times >= 0).sum())
+        out = np.empty((6, T, self.problem.n_ages, 5)); used = C.c_int64()
+        check(self.L.sepaihrd_host_model_posterior_predictive(self._h, x.ctypes.data, x.shape[0], int(num_samples), int(seed), s0.ctypes.data,
+                                                              out.ctypes.data, C.byref(used)))
+        return out, used.value
 
     def close(self):
         if getattr(self, "_h", None):

@@ -119,3 +119,21 @@ def test_model_calibration_mirror_runs_both_phases(host, problem, oracle):
     best, val, ns = m.calibrate("hill", dict(iterations=2, cloud_size=64, seed=3), dict(mcmc_iterations=5, burn_in=5, n_chains=8, seed=5))
     assert val >= f0 * (1 - 1e-12) and ns == 8 * 5
     m.close()
+
+
+def test_result_aggregator_mirror_matches_the_evaluator(host, problem, oracle, ev_mod):
+    """ResultAggregator::aggregatePosteriorPredictives through the C++ mirror == the C-ABI call on the same draws; the
+    with-replacement subsampling follows std::mt19937(seed) + uniform_int_distribution."""
+    P = oracle.jitter_params(120, seed=8)
+    s0 = problem.data_initial_state
+    m = host.HostModel(problem)
+    got, used = m.posterior_predictive(P, s0)
+    with ev_mod.BatchEvaluator(problem, device=0) as ev:
+        ref, valid = ev.posterior_predictive(P, s0)
+    assert used == valid == 120
+    np.testing.assert_array_equal(got, ref)
+    sub, used = m.posterior_predictive(P, s0, num_samples=40, seed=99)
+    assert used == 40 and sub.shape == got.shape and not np.array_equal(sub, got)
+    sub2, _ = m.posterior_predictive(P, s0, num_samples=40, seed=99)
+    np.testing.assert_array_equal(sub, sub2)
+    m.close()
