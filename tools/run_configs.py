@@ -13,7 +13,7 @@ import torch
 import __graft_entry__ as g
 
 ap = argparse.ArgumentParser()
-ap.add_argument("what", choices=["mh", "pso", "ppc16"])
+ap.add_argument("what", choices=["mh", "pso", "ppc16", "ppcq"])
 ap.add_argument("--chains", type=int, default=4096)
 ap.add_argument("--particles", type=int, default=65536)
 ap.add_argument("--iterations", type=int, default=30)
@@ -52,6 +52,17 @@ elif a.what == "pso":
         comm.barrier(); dt = time.perf_counter() - t0
     out.update(particles=a.particles, iterations=a.iterations, seconds=dt, evals_per_s=a.particles * (a.iterations + 1) / dt,
                eval_seconds=r["eval_seconds"], comm_seconds=r["comm_seconds"], best_first=float(r["trace"][0]), best_last=float(r["trace"][-1]))
+elif a.what == "ppcq":
+    # posterior-predictive QUANTILES (ResultAggregator): draws -> trajectories -> series -> sort -> quantiles, one C-ABI call
+    o = orc.Oracle(p)
+    draws = o.jitter_params(4096, seed=11)
+    draws = np.tile(draws, ((a.draws + 4095) // 4096, 1))[:a.draws]
+    with BatchEvaluator(p, device=dev) as ev:
+        ev.posterior_predictive(draws[:1024], p.data_initial_state)
+        t0 = time.perf_counter()
+        q, valid = ev.posterior_predictive(draws, p.data_initial_state)
+        dt = time.perf_counter() - t0
+    out.update(draws=a.draws, ages=4, seconds=dt, draws_per_s=a.draws / dt, valid=valid, median_deaths_last_day=[float(x) for x in q[2, -1, :, 2]])
 else:
     p16 = p.expand_ages(4)
     o16 = orc.Oracle(p16)
