@@ -149,55 +149,9 @@ __device__ __forceinline__ double constrain(double v, double lo, double hi, int 
 }
 
 // ---- step-size controller powers (FAST) ---------------------------------------------------------------
-// x^(-1/5) and x^(-1/3) by an FP32 MUFU seed (rel. error ~1e-6) and two Newton steps in FP64
-// (error constant 3 resp. 2: 1e-6 -> ~3e-12 -> rounding level, a few ulp).  The v3 profile showed the
-// two inlined CUDA pow() calls at ~260 instructions per step attempt.
-__device__ __forceinline__ double pow_m1_5(double x) {
-    double y = (double)__powf((float)x, -0.2f);
-    const double xs = x * 0.2;
-#pragma unroll
-    for (int it = 0; it < 2; ++it) {
-        const double y2 = y * y;
-        const double y5 = y2 * y2 * y;
-        y = y * fma(-xs, y5, 1.2);            // y (6 - x y^5) / 5
-    }
-    return y;
-}
-__device__ __forceinline__ double pow_m1_3(double x) {
-    double y = (double)__powf((float)x, -0.33333334f);
-    const double xs = x * (1.0 / 3.0);
-#pragma unroll
-    for (int it = 0; it < 2; ++it) {
-        const double y3 = y * y * y;
-        y = y * fma(-xs, y3, 4.0 / 3.0);      // y (4 - x y^3) / 3
-    }
-    return y;
-}
-
-// ---- logarithm for the Poisson terms (FAST) -----------------------------------------------------------
-// log(x) = e ln2 + log(c_i) + log1p(r),  r = m / c_i - 1 (one FMA, exact rounding), i = top 7 mantissa bits,
-// |r| <= 2^-8, log1p by a degree-5 polynomial (truncation 7e-16).  Absolute error ~1e-15: far inside what the
-// 1e-8 relative gate on logL needs, at ~9 FP64 instructions instead of ~35 for CUDA's log() (v4 profile: the three
-// log() calls per output day were 25% of the kernel time).  Non-finite and non-positive inputs go to log().
-__device__ __noinline__ double slow_log(double x) { return log(x); }
-__device__ __forceinline__ double fast_log(double x, const double2* __restrict__ tab) {
-    const int hi = __double2hiint(x);
-    if ((unsigned)(hi - 0x00100000) >= 0x7fe00000u) return slow_log(x);   // zero, subnormal, negative, inf, NaN
-    const int e = (hi >> 20) - 1023;
-    const int i = (hi >> 13) & 0x7f;
-    const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));   // [1, 2)
-    const double2 t = tab[i];
-    const double r = fma(m, t.x, -1.0);
-    double p = fma(r, 0.2, -0.25);
-    p = fma(p, r, 1.0 / 3.0);
-    p = fma(p, r, -0.5);
-    p = fma(p, r, 1.0);
-    return fma((double)e, 0.6931471805599453, fma(p, r, t.y));
-}
-
-
-// x^(-1/3) (cubic) or x^(-1/5) in ONE instruction stream: lanes of a warp that shrink a rejected step and lanes
-// that grow an accepted one share the chain instead of diverging into pow_m1_3 / pow_m1_5 back to back.
+// x^(-1/3) (cubic) or x^(-1/5) by an FP32 MUFU seed (rel. error ~1e-6) and two Newton steps in FP64 (error constant 2
+// resp. 3: 1e-6 -> ~3e-12 -> rounding level, a few ulp; ~14 FP64 instructions against ~130 for pow()), in ONE
+// instruction stream: lanes that shrink a rejected step and lanes that grow an accepted one share the chain.
 __device__ __forceinline__ double pow_neg_inv(double x, bool cubic) {
     double y = (double)__powf((float)x, cubic ? -0.33333334f : -0.2f);
     const double xs = x * (cubic ? (1.0 / 3.0) : 0.2);
@@ -211,9 +165,14 @@ __device__ __forceinline__ double pow_neg_inv(double x, bool cubic) {
     return y;
 }
 
-// fast_log without the special-case branch, so that the three Poisson streams of an output day interleave
-// in one basic block.  Inputs outside the positive normal range (the incidence went NaN/inf) raise `bad`;
-// the caller turns that into the reference's non-finite sentinel.
+// ---- logarithm for the Poisson terms (FAST) -----------------------------------------------------------
+// log(x) = e ln2 + log(c_i) + log1p(r),  r = m / c_i - 1 (one FMA, exact rounding), i = top 7 mantissa bits,
+// |r| <= 2^-8, log1p by a degree-5 polynomial (truncation 7e-16).  Absolute error ~1e-15: far inside what the
+// 1e-8 relative gate on logL needs, at ~9 FP64 instructions instead of ~35 for CUDA's log() (v4 profile: the three
+// log() calls per output day were 25% of the kernel time).
+// No special-case branch, so that the three Poisson streams of an output day interleave in one basic block.  Inputs
+// outside the positive normal range (the incidence went NaN/inf) raise `bad`; the caller turns that into the
+// reference's non-finite sentinel.
 __device__ __forceinline__ double fast_log_nb(double x, const double2* __restrict__ tab, bool valid, bool& bad) {
     const int hi = __double2hiint(x);
     bad |= valid && ((unsigned)(hi - 0x00100000) >= 0x7fe00000u);
@@ -664,8 +623,6 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) sepaihrd_batch_kernel(cons
             if (over && status == 0) status |= SEPAIHRD_ST_S_OVERFLOW;
             x[0] = O::sub(popN, sum);
         }
-        const unsigned gshift = (threadIdx.x & 31) - age;
-        const unsigned gmask = (NA >= 32) ? FULL : (((1u << NA) - 1u) << gshift);
 
         double ll_acc_h = 0.0, ll_acc_i = 0.0, ll_acc_d = 0.0;   // STRICT: per stream; FAST: ll_acc_h only
         int n_acc = 0, n_rej = 0;
@@ -868,6 +825,8 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) sepaihrd_batch_kernel(cons
         }
         if (bad) ll_acc_h = __longlong_as_double(0x7ff8000000000000LL);
         } else {
+        // ================= LOOP 5 (STRICT): the reference's arithmetic, operation by operation ====================
+        // Unfused IEEE mul/add in source order, libm pow/log, true divisions, likelihood summed row by row per stream.
         for (int idx = 0; idx < K; ++idx) {
             t = s_times[idx];
             // ---- observer -----------------------------------------------------------------------------
@@ -893,32 +852,21 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) sepaihrd_batch_kernel(cons
                     double term_h = 0.0, term_i = 0.0, term_d = 0.0;
                     const double oh = s_obs_h[r * n + age], oi = s_obs_i[r * n + age], od = s_obs_d[r * n + age];
                     // the host stores every skipped observation (negative, NaN, inf: ObjectiveFunction.cpp:267) as -1
-                    const bool vh = (oh >= 0.0), vi = (oi >= 0.0), vd = (od >= 0.0);
-                    if (STRICT) {
-                        if (vh) { double sim = inc_h; if (sim < 0.0) sim = 0.0; sim = O::add(sim, eps); term_h = O::sub(O::mul(oh, log(sim)), sim); }
-                        if (vi) { double sim = inc_i; if (sim < 0.0) sim = 0.0; sim = O::add(sim, eps); term_i = O::sub(O::mul(oi, log(sim)), sim); }
-                        if (vd) { double sim = inc_d; if (sim < 0.0) sim = 0.0; sim = O::add(sim, eps); term_d = O::sub(O::mul(od, log(sim)), sim); }
-                    } else {
-                        if (vh) { const double sim = inc_h + eps; term_h = fma(oh, fast_log(sim, s_logtab), -sim); }
-                        if (vi) { const double sim = inc_i + eps; term_i = fma(oi, fast_log(sim, s_logtab), -sim); }
-                        if (vd) { const double sim = inc_d + eps; term_d = fma(od, fast_log(sim, s_logtab), -sim); }
-                    }
-                    if (STRICT) {
-                        // row_sum over ages in order, then log_likelihood += row_sum (per stream)
-                        double rs_h = 0.0, rs_i = 0.0, rs_d = 0.0;
+                    if (oh >= 0.0) { double sim = inc_h; if (sim < 0.0) sim = 0.0; sim = O::add(sim, eps); term_h = O::sub(O::mul(oh, log(sim)), sim); }
+                    if (oi >= 0.0) { double sim = inc_i; if (sim < 0.0) sim = 0.0; sim = O::add(sim, eps); term_i = O::sub(O::mul(oi, log(sim)), sim); }
+                    if (od >= 0.0) { double sim = inc_d; if (sim < 0.0) sim = 0.0; sim = O::add(sim, eps); term_d = O::sub(O::mul(od, log(sim)), sim); }
+                    // row_sum over ages in order, then log_likelihood += row_sum (per stream)
+                    double rs_h = 0.0, rs_i = 0.0, rs_d = 0.0;
 #pragma unroll
-                        for (int j = 0; j < NA; ++j) {
-                            const double th = __shfl_sync(FULL, term_h, j, NA), ti = __shfl_sync(FULL, term_i, j, NA),
-                                         td = __shfl_sync(FULL, term_d, j, NA);
-                            const double ohj = s_obs_h[r * n + j], oij = s_obs_i[r * n + j], odj = s_obs_d[r * n + j];
-                            if (ohj >= 0.0) rs_h = O::add(rs_h, th);
-                            if (oij >= 0.0) rs_i = O::add(rs_i, ti);
-                            if (odj >= 0.0) rs_d = O::add(rs_d, td);
-                        }
-                        ll_acc_h = O::add(ll_acc_h, rs_h); ll_acc_i = O::add(ll_acc_i, rs_i); ll_acc_d = O::add(ll_acc_d, rs_d);
-                    } else {
-                        ll_acc_h += (term_h + term_i) + term_d;
+                    for (int j = 0; j < NA; ++j) {
+                        const double th = __shfl_sync(FULL, term_h, j, NA), ti = __shfl_sync(FULL, term_i, j, NA),
+                                     td = __shfl_sync(FULL, term_d, j, NA);
+                        const double ohj = s_obs_h[r * n + j], oij = s_obs_i[r * n + j], odj = s_obs_d[r * n + j];
+                        if (ohj >= 0.0) rs_h = O::add(rs_h, th);
+                        if (oij >= 0.0) rs_i = O::add(rs_i, ti);
+                        if (odj >= 0.0) rs_d = O::add(rs_d, td);
                     }
+                    ll_acc_h = O::add(ll_acc_h, rs_h); ll_acc_i = O::add(ll_acc_i, rs_i); ll_acc_d = O::add(ll_acc_d, rs_d);
                 }
             }
             if (idx + 1 == K) break;
@@ -932,15 +880,12 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) sepaihrd_batch_kernel(cons
                 if (m_need == 0) break;
                 double cur = std_min(dt, t_next - t);   // min_abs(dt, t_next - t)
                 const double t_end = O::add(t, cur);
-                // warp-level flags: bit0 = some stepping group carries dt < hmax (its error VALUE matters on accept),
-                //                   bit1 = some lane's stage times leave its current schedule segment
-                const unsigned flags = __reduce_or_sync(FULL, ((need && dt < hmax) ? 1u : 0u) | ((t_end <= bp_next) ? 0u : 2u));
                 StepSched sc;
                 sc.ba_step = ba; sc.s_lo = seg; sc.bp = s_bp; sc.beff = my_beff; sc.nseg = nseg; sc.a = q.a;
                 sc.mb = nullptr; sc.mb_stride = 0;
                 int s_hi = seg;
                 bool run_mixed = false;
-                if (flags & 2u) {
+                if (__any_sync(FULL, !(t_end <= bp_next))) {
                     // Stage times lie in (t, t_end].  Steps that start on a breakpoint (quirk Q2) or straddle one on a
                     // general grid look their segments up.
                     bool mixed = false;
@@ -957,75 +902,34 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) sepaihrd_batch_kernel(cons
                     run_mixed = __any_sync(FULL, mixed);
                 }
                 double xn[NDYN], k7d[NDYN], k7p[NPAS], accN[NPAS], xe[NCOMP];
-                const double ecur = STRICT ? cur : cur * kp.inv_rel;
                 if (run_mixed)
-                    dopri5_attempt<NA, STRICT, true>(q, sc, spi, pi_slot, THREADS, threadIdx.x, t, cur, t_end, x, k1, xn, k7d, k7p, accN, xe, ecur);
+                    dopri5_attempt<NA, STRICT, true>(q, sc, spi, pi_slot, THREADS, threadIdx.x, t, cur, t_end, x, k1, xn, k7d, k7p, accN, xe, cur);
                 else
-                    dopri5_attempt<NA, STRICT, false>(q, sc, spi, pi_slot, THREADS, threadIdx.x, t, cur, t_end, x, k1, xn, k7d, k7p, accN, xe, ecur);
+                    dopri5_attempt<NA, STRICT, false>(q, sc, spi, pi_slot, THREADS, threadIdx.x, t, cur, t_end, x, k1, xn, k7d, k7p, accN, xe, cur);
                 // error norm (default_error_checker): max_c |xerr_c| / (abs + rel * (|x_c| + dt * |dxdt_c|))
-                double err = 0.0;
-                bool reject;
-                if (STRICT) {
-                    double m = 0.0;
+                double m = 0.0;
 #pragma unroll
-                    for (int c = 0; c < NCOMP; ++c) {
-                        const double den = O::add(f_abs, O::mul(f_rel, O::add(fabs(x[c]), O::mul(cur, fabs(k1[c])))));
-                        const double v = fabs(__ddiv_rn(fabs(xe[c]), den));
-                        m = (m < v) ? v : m;
-                    }
-                    err = group_max<NA>(m);
-                    reject = err > 1.0;
-                } else {
-                    // xe and den are both in units of rel_tol.  fl(num/den) > 1 <=> num > den, so the accept/reject
-                    // decision needs no division; the VALUE of the norm is only needed to shrink a rejected step or
-                    // to grow a step that is below hmax.
-                    double num[NCOMP], den[NCOMP];
-                    bool big0 = false, big1 = false, big2 = false;
-#pragma unroll
-                    for (int c = 0; c < NCOMP; ++c) {
-                        num[c] = fabs(xe[c]);
-                        den[c] = fma(cur, fabs(k1[c]), fabs(x[c])) + kp.abs_over_rel;
-                        const bool g = num[c] > den[c];
-                        if (c % 3 == 0) big0 |= g; else if (c % 3 == 1) big1 |= g; else big2 |= g;
-                    }
-                    const unsigned bal = __ballot_sync(FULL, big0 | big1 | big2);
-                    reject = (bal & gmask) != 0;
-                    if ((flags & 1u) || (bal & m_need)) {
-                        // arg-max of num/den by a cross-multiplication tournament, then ONE division per lane (eleven parallel
-                    // reciprocal chains instead were measured: no faster, and their 11 extra live doubles spill)
-#pragma unroll
-                        for (int stride = 1; stride < NCOMP; stride *= 2) {
-#pragma unroll
-                            for (int c = 0; c + stride < NCOMP; c += 2 * stride) {
-                                const bool other = num[c + stride] * den[c] > num[c] * den[c + stride];
-                                num[c] = other ? num[c + stride] : num[c];
-                                den[c] = other ? den[c + stride] : den[c];
-                            }
-                        }
-                        err = group_max<NA>(num[0] / den[0]);
-                    }
+                for (int c = 0; c < NCOMP; ++c) {
+                    const double den = O::add(f_abs, O::mul(f_rel, O::add(fabs(x[c]), O::mul(cur, fabs(k1[c])))));
+                    const double v = fabs(__ddiv_rn(fabs(xe[c]), den));
+                    m = (m < v) ? v : m;
                 }
+                const double err = group_max<NA>(m);
                 if (need) {
-                    if (reject) {
+                    if (err > 1.0) {
                         // decrease_step (error_order 4): dt *= max(0.9 * err^(-1/3), 1/5)
-                        double shrink;
-                        if (STRICT) shrink = std_max(O::mul(9.0 / 10.0, pow(err, -1.0 / 3.0)), 1.0 / 5.0);
-                        else shrink = (err > 128.0) ? 0.2 : std_max(0.9 * pow_m1_3(err), 0.2);   // 0.9 err^(-1/3) < 0.2 beyond 91.2
-                        cur = O::mul(cur, shrink);
+                        cur = O::mul(cur, std_max(O::mul(9.0 / 10.0, pow(err, -1.0 / 3.0)), 1.0 / 5.0));
                         ++n_rej;
                         dt = cur;
                         if (fail_steps++ >= 500) { status |= SEPAIHRD_ST_STEP_FAILURE; alive = false; }
                     } else {
                         // accept: t += dt; increase_step (stepper_order 5) when err < 0.5
                         t = t_end;
-                        if (STRICT || dt < hmax) {
-                            if (err < 0.5) {
-                                const double e2 = std_max(3.2e-4 /* pow(5,-5) */, err);
-                                if (STRICT) cur = O::mul(cur, O::mul(9.0 / 10.0, pow(e2, -1.0 / 5.0)));
-                                else cur = cur * (0.9 * pow_m1_5(e2));
-                            }
-                            dt = std_max(dt, cur);   // max_abs: keep the larger of the carried and the proposed step
+                        if (err < 0.5) {
+                            const double e2 = std_max(3.2e-4 /* pow(5,-5) */, err);
+                            cur = O::mul(cur, O::mul(9.0 / 10.0, pow(e2, -1.0 / 5.0)));
                         }
+                        dt = std_max(dt, cur);   // max_abs: keep the larger of the carried and the proposed step
                         ++n_acc;
                         fail_steps = 0;
                         if (s_hi != seg) {

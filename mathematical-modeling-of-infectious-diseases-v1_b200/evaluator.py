@@ -17,6 +17,9 @@ from . import capi
 from .problem import Problem, TRAJ_FULL
 
 MATH_FAST, MATH_STRICT = 0, 1
+PPC_PROBS = (0.025, 0.05, 0.5, 0.95, 0.975)     # ResultAggregator.cpp:233
+PPC_SERIES = ("daily_hospitalizations", "daily_icu_admissions", "daily_deaths",
+              "cumulative_hospitalizations", "cumulative_icu_admissions", "cumulative_deaths")
 
 
 def _is_tensor(x) -> bool:
@@ -132,56 +135,45 @@ class BatchEvaluator:
                                                      out.ctypes.data, st.ctypes.data))
         return out, st
 
-
-def _simulate_from_state(self, params, initial_states, what: int = TRAJ_FULL, stride: int = 1):
-    """Batched Simulator::run(initial_state, times): ``initial_states`` is [11n] (shared) or [B, 11n]."""
-    p = self.problem
-    x = np.ascontiguousarray(params, dtype=np.float64)
-    s0 = np.ascontiguousarray(initial_states, dtype=np.float64)
-    B, ld = x.shape
-    if s0.ndim == 1:
-        sstride = 0
-    else:
-        if s0.shape[0] != B:
-            raise ValueError("one initial state per parameter set (or a single shared state)")
-        sstride = s0.shape[1]
-    if s0.shape[-1] != p.state_size:
-        raise ValueError("Initial state size does not match model state size.")
-    W = p.state_size if what == TRAJ_FULL else 3 * p.n_ages
-    rows = (p.n_times + stride - 1) // stride
-    out = np.empty((B, rows, W))
-    st = np.zeros(B, dtype=np.uint32)
-    capi.check(self._lib.sepaihrd_simulate_from_state(self._h, x.ctypes.data, B, ld, s0.ctypes.data, sstride, int(what),
-                                                      int(stride), out.ctypes.data, st.ctypes.data))
-    return out, st
-
-
-BatchEvaluator.simulate_from_state = _simulate_from_state
+    def simulate_from_state(self, params, initial_states, what: int = TRAJ_FULL, stride: int = 1):
+        """Batched Simulator::run(initial_state, times): ``initial_states`` is [11n] (shared) or [B, 11n]."""
+        p = self.problem
+        x = np.ascontiguousarray(params, dtype=np.float64)
+        s0 = np.ascontiguousarray(initial_states, dtype=np.float64)
+        B, ld = x.shape
+        if s0.ndim == 1:
+            sstride = 0
+        else:
+            if s0.shape[0] != B:
+                raise ValueError("one initial state per parameter set (or a single shared state)")
+            sstride = s0.shape[1]
+        if s0.shape[-1] != p.state_size:
+            raise ValueError("Initial state size does not match model state size.")
+        W = p.state_size if what == TRAJ_FULL else 3 * p.n_ages
+        rows = (p.n_times + stride - 1) // stride
+        out = np.empty((B, rows, W))
+        st = np.zeros(B, dtype=np.uint32)
+        capi.check(self._lib.sepaihrd_simulate_from_state(self._h, x.ctypes.data, B, ld, s0.ctypes.data, sstride, int(what),
+                                                          int(stride), out.ctypes.data, st.ctypes.data))
+        return out, st
 
 
-PPC_PROBS = (0.025, 0.05, 0.5, 0.95, 0.975)     # ResultAggregator.cpp:233
-PPC_SERIES = ("daily_hospitalizations", "daily_icu_admissions", "daily_deaths",
-              "cumulative_hospitalizations", "cumulative_icu_admissions", "cumulative_deaths")
 
-
-def _posterior_predictive(self, params, initial_state, probs=PPC_PROBS):
-    """ResultAggregator::aggregatePosteriorPredictives on the device: quantiles [6, T, n_ages, len(probs)] of the six
-    PPC_SERIES over the draws (rows of ``params``), all simulated from ``initial_state``; also the number of valid draws."""
-    p = self.problem
-    x = np.ascontiguousarray(params, dtype=np.float64)
-    s0 = np.ascontiguousarray(initial_state, dtype=np.float64)
-    if s0.shape != (p.state_size,):
-        raise ValueError("Initial state size does not match model state size.")
-    pr = np.ascontiguousarray(probs, dtype=np.float64)
-    T = int((p.times >= 0).sum())
-    out = np.empty((6, T, p.n_ages, len(pr)))
-    valid = C.c_int64()
-    capi.check(self._lib.sepaihrd_posterior_predictive(self._h, x.ctypes.data, x.shape[0], x.shape[1], s0.ctypes.data, len(pr), pr.ctypes.data,
-                                                       out.ctypes.data, C.byref(valid)))
-    return out, valid.value
-
-
-BatchEvaluator.posterior_predictive = _posterior_predictive
+    def posterior_predictive(self, params, initial_state, probs=PPC_PROBS):
+        """ResultAggregator::aggregatePosteriorPredictives on the device: quantiles [6, T, n_ages, len(probs)] of the six
+        PPC_SERIES over the draws (rows of ``params``), all simulated from ``initial_state``; also the number of valid draws."""
+        p = self.problem
+        x = np.ascontiguousarray(params, dtype=np.float64)
+        s0 = np.ascontiguousarray(initial_state, dtype=np.float64)
+        if s0.shape != (p.state_size,):
+            raise ValueError("Initial state size does not match model state size.")
+        pr = np.ascontiguousarray(probs, dtype=np.float64)
+        T = int((p.times >= 0).sum())
+        out = np.empty((6, T, p.n_ages, len(pr)))
+        valid = C.c_int64()
+        capi.check(self._lib.sepaihrd_posterior_predictive(self._h, x.ctypes.data, x.shape[0], x.shape[1], s0.ctypes.data, len(pr), pr.ctypes.data,
+                                                           out.ctypes.data, C.byref(valid)))
+        return out, valid.value
 
 
 def measure_fp64_peak(device: int = 0) -> float:
