@@ -368,3 +368,67 @@ def test_posterior_predictive_quantiles_match_numpy_on_oracle_trajectories(probl
     with ev_mod.BatchEvaluator(loose, device=0) as ev:
         one, v1 = ev.posterior_predictive(P[:1], s0, (0.0, 0.5, 1.0))
     assert v1 == 1 and np.all(one[..., 0] == one[..., 2])
+
+
+def test_every_distinct_set_of_the_bench_batch_matches_the_oracle(problem, oracle, ev_mod):
+    """The bench batch is 65,536 distinct jittered sets tiled 16 times (bench.py).  ALL distinct sets against the CPU oracle:
+    logL within 1e-8 relative (north_star gate), identical status words, identical accepted/rejected step counts."""
+    P = oracle.jitter_params(1 << 16, seed=1)
+    ll_ref, st_ref, steps_ref, _ = oracle.eval_batch(P)
+    with ev_mod.BatchEvaluator(problem, device=0) as ev:
+        ll, st, steps = ev.eval_batch(P, return_steps=True)
+    np.testing.assert_array_equal(st, st_ref)
+    rel = _rel(ll, ll_ref)
+    assert rel.max() < 1e-8, rel.max()
+    mism = int((steps != steps_ref).any(axis=1).sum())
+    assert mism == 0, f"{mism} of {len(P)} sets took a different accept/reject path"
+    assert np.percentile(rel, 99.9) < 1e-10
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_randomised_problems_match_the_oracle(problem, orc, ev_mod, seed):
+    """Fuzz over the problem description: random output grid (integer and fractional spacing, with / without run-up), random
+    schedule breakpoints (on and off the grid), random missing observations, clamp or reflect, tolerances, 4 and 16 ages."""
+    rng = np.random.default_rng(100 + seed)
+    p2 = copy.deepcopy(problem)
+    n_days = int(rng.integers(40, 120))
+    start = float(rng.choice([-20.0, -7.5, 0.0]))
+    steps_ = rng.choice([1.0, 1.0, 0.5, 2.0], size=n_days)
+    times = start + np.concatenate([[0.0], np.cumsum(steps_)])
+    p2.times = times
+    T = int((times >= 0).sum())
+    pick = rng.integers(0, problem.obs_hosp.shape[0] - 1, T)
+    p2.obs_hosp, p2.obs_icu, p2.obs_deaths = problem.obs_hosp[pick].copy(), problem.obs_icu[pick].copy(), problem.obs_deaths[pick].copy()
+    for arr in (p2.obs_hosp, p2.obs_icu, p2.obs_deaths):
+        arr[rng.random(arr.shape) < 0.05] = np.nan
+        arr[rng.random(arr.shape) < 0.03] = -1.0
+    span = times[-1]
+    nb, nk = len(problem.beta_end_times), len(problem.kappa_end_times)
+    def breakpoints(k):
+        pts = np.sort(rng.uniform(0.05 * span, 0.95 * span, k - 1))
+        on_grid = rng.random(k - 1) < 0.5
+        pts = np.where(on_grid, np.round(pts), pts)
+        pts = np.maximum.accumulate(pts + 1e-3 * np.arange(k - 1))
+        return np.concatenate([pts, [span + 10.0]])
+    p2.beta_end_times, p2.kappa_end_times = breakpoints(nb), breakpoints(nk)
+    p2.constraint_mode = int(rng.integers(0, 2))
+    p2.abs_tol, p2.rel_tol = float(rng.choice([1e-6, 1e-7])), float(rng.choice([1e-6, 1e-5]))
+    if seed % 2 == 1:
+        p2 = p2.expand_ages(4)
+    o2 = orc.Oracle(p2)
+    P = np.vstack([o2.jitter_params(40, seed=seed + 50), o2.uniform_params(24, seed=seed + 60)])
+    P += rng.standard_normal(P.shape) * p2.sigmas * (rng.random(P.shape) < 0.1) * 30      # some far outside the bounds
+    ll_ref, st_ref, steps_ref, _ = o2.eval_batch(P)
+    for m in (ev_mod.MATH_STRICT, ev_mod.MATH_FAST):
+        with ev_mod.BatchEvaluator(p2, device=0, math=m) as ev:
+            ll, st, steps = ev.eval_batch(P, return_steps=True)
+        np.testing.assert_array_equal(st, st_ref)
+        ok = st_ref == 0
+        assert _rel(ll[ok], ll_ref[ok]).max() < 1e-8
+        np.testing.assert_array_equal(ll[~ok], ll_ref[~ok])
+        assert (steps[ok] != steps_ref[ok]).any(axis=1).mean() <= 0.05   # off-grid breakpoints: err can hug 1.0 (see test above)
+    tr_ref, _ = o2.simulate_batch(P[:6])
+    with ev_mod.BatchEvaluator(p2, device=0) as ev:
+        tr, _ = ev.simulate_batch(P[:6])
+    good = np.isfinite(tr_ref).all(axis=(1, 2))
+    assert (np.abs(tr[good] - tr_ref[good]) / np.maximum(np.abs(tr_ref[good]), 1.0)).max() < 1e-6
