@@ -347,6 +347,16 @@ sepaihrd_rc sepaihrd_create(const sepaihrd_problem* pb, int32_t device, sepaihrd
     kp.inv_rel = (pb->rel_tol > 0.0) ? 1.0 / pb->rel_tol : 0.0;
     kp.abs_over_rel = (pb->rel_tol > 0.0) ? pb->abs_tol / pb->rel_tol : 0.0;
     kp.grow_max = 9.0 / 10.0 * std::pow(std::pow(5.0, -5.0), -1.0 / 5);
+    {   // hmax * coefficient with the device's single rounding (the kernel would compute cur * c_tab[i], cur == hmax)
+        const double* tab = sepaihrd::h_tab;
+        static_assert(sepaihrd::T_COUNT <= 32, "hc table too small");
+        for (int i = 0; i < sepaihrd::T_COUNT; ++i) {
+            const bool is_dc = i >= sepaihrd::T_DC1;
+            const volatile double step = is_dc ? ctx->hmax * kp.inv_rel : ctx->hmax;   // volatile: no FMA contraction / reassociation on the host
+            const volatile double prod = step * tab[i];
+            kp.hc[i] = prod;
+        }
+    }
     // hi(num) - hi(den) equals log2(num/den) within +-0.0862 (units 2^-20) for normal den; margins on top of that
     if (kp.abs_over_rel >= 1e-150) {
         kp.thr_small = (int)std::lround(-11.75 * 1048576.0);    // ratio < 2^-11.66 = 3.09e-4 < 5^-5

@@ -59,6 +59,8 @@ struct KParams {
     double hmax;               // longest output interval: growing dt beyond it cannot change the result
     double inv_rel;            // 1 / rel_tol          (FAST error norm is evaluated in units of rel_tol)
     double abs_over_rel;       // abs_tol / rel_tol
+    double hc[32];             // Dopri5 coefficients pre-multiplied by hmax (b, c rows) resp. hmax / rel_tol (dc row): the attempt
+                               // body of a full-length step reads them straight from the constant bank (T_* indices)
     double grow_max;           // 0.9 * pow(pow(5,-5), -1/5): the step-growth factor once err <= 5^-5 (libm, host)
     // LOOP 6: coarse classification of the error norm from the high words of num/den (units: 2^-20 of a log2)
     int thr_small, thr_nogrow, thr_big;
@@ -346,14 +348,16 @@ enum TabIdx {
 namespace tabv {
 constexpr double c1 = 35.0 / 384.0, c3 = 500.0 / 1113.0, c4 = 125.0 / 192.0, c5 = -2187.0 / 6784.0, c6 = 11.0 / 84.0;
 }
-__constant__ double c_tab[T_COUNT] = {
-    1.0 / 5.0, 3.0 / 10.0, 4.0 / 5.0, 8.0 / 9.0,
-    1.0 / 5.0, 3.0 / 40.0, 9.0 / 40.0, 44.0 / 45.0, -56.0 / 15.0, 32.0 / 9.0,
-    19372.0 / 6561.0, -25360.0 / 2187.0, 64448.0 / 6561.0, -212.0 / 729.0,
-    9017.0 / 3168.0, -355.0 / 33.0, 46732.0 / 5247.0, 49.0 / 176.0, -5103.0 / 18656.0,
-    tabv::c1, tabv::c3, tabv::c4, tabv::c5, tabv::c6,
-    tabv::c1 - 5179.0 / 57600.0, tabv::c3 - 7571.0 / 16695.0, tabv::c4 - 393.0 / 640.0,
-    tabv::c5 - -92097.0 / 339200.0, tabv::c6 - 187.0 / 2100.0, -1.0 / 40.0};
+#define SEPAIHRD_TABLEAU_VALUES { \
+    1.0 / 5.0, 3.0 / 10.0, 4.0 / 5.0, 8.0 / 9.0, \
+    1.0 / 5.0, 3.0 / 40.0, 9.0 / 40.0, 44.0 / 45.0, -56.0 / 15.0, 32.0 / 9.0, \
+    19372.0 / 6561.0, -25360.0 / 2187.0, 64448.0 / 6561.0, -212.0 / 729.0, \
+    9017.0 / 3168.0, -355.0 / 33.0, 46732.0 / 5247.0, 49.0 / 176.0, -5103.0 / 18656.0, \
+    tabv::c1, tabv::c3, tabv::c4, tabv::c5, tabv::c6, \
+    tabv::c1 - 5179.0 / 57600.0, tabv::c3 - 7571.0 / 16695.0, tabv::c4 - 393.0 / 640.0, \
+    tabv::c5 - -92097.0 / 339200.0, tabv::c6 - 187.0 / 2100.0, -1.0 / 40.0}
+__constant__ double c_tab[T_COUNT] = SEPAIHRD_TABLEAU_VALUES;
+static const double h_tab[T_COUNT] = SEPAIHRD_TABLEAU_VALUES;   // host image of c_tab (same constant expressions)
 
 constexpr unsigned FULL = 0xffffffffu;
 
@@ -388,13 +392,19 @@ struct StepSched {
     int mb_stride;
 };
 
-template <int NA, bool STRICT, bool MIXED>
+// UNIT=true: every stepping lane group of the warp takes a step of exactly hmax (the usual case on a uniform output
+// grid: 48 % of the warp-attempts of the Spain-2020 jitter batch), so the 27 products step x coefficient are the
+// launch constants `hc` instead of 27 DMULs per lane.  hc[i] is computed on the host with the same single rounding.
+template <int NA, bool STRICT, bool MIXED, bool UNIT = false>
 __device__ __forceinline__ void dopri5_attempt(const LaneParams<NA>& q, const StepSched& sc, double* spi, int& pi_slot,
                                                int pi_stride, int lane_in_block, double t, double cur, double t_end,
                                                const double (&x)[NCOMP], const double (&k1)[NCOMP], double (&xn)[NDYN],
                                                double (&k7d)[NDYN], double (&k7p)[NPAS], double (&accN)[NPAS],
-                                               double (&xe)[NCOMP], double ecur) {
+                                               double (&xe)[NCOMP], double ecur, const double* hc = nullptr) {
     using O = Ops<STRICT>;
+    static_assert(!(UNIT && MIXED), "a full-length step on a breakpoint-free day never mixes segments");
+    auto cf = [&](int i) -> double { return UNIT ? hc[i] : O::mul(cur, c_tab[i]); };     // step * b_ij, step * c_j
+    auto ef = [&](int i) -> double { return UNIT ? hc[i] : O::mul(ecur, c_tab[i]); };    // step / rel_tol * dc_j
     auto ba_at = [&](int tab_a) -> double {
         if (!MIXED) return sc.ba_step;
         const double ts = (tab_a < 0) ? t_end : O::add(t, O::mul(cur, c_tab[tab_a]));
@@ -406,60 +416,60 @@ __device__ __forceinline__ void dopri5_attempt(const LaneParams<NA>& q, const St
     double k2[NDYN], k3[NDYN], k4[NDYN], k5[NDYN], k6[NDYN];
     double y[NDYN], kp_[NPAS], accE[NPAS];
     // stage 2
-    { const double f1 = O::mul(cur, c_tab[T_B21]);
+    { const double f1 = cf(T_B21);
 #pragma unroll
       for (int c = 0; c < NDYN; ++c) y[c] = O::mad(f1, k1[c], x[c]); }
     rhs<NA, STRICT, false, !MIXED>(q, ba_at(T_A2), spi, next_slot(), lane_in_block, y, k2, kp_, sc.mb, sc.mb_stride);
     // stage 3
-    { const double f1 = O::mul(cur, c_tab[T_B31]), f2 = O::mul(cur, c_tab[T_B32]);
+    { const double f1 = cf(T_B31), f2 = cf(T_B32);
 #pragma unroll
       for (int c = 0; c < NDYN; ++c) y[c] = O::mad(f2, k2[c], O::mad(f1, k1[c], x[c])); }
     rhs<NA, STRICT, true, !MIXED>(q, ba_at(T_A3), spi, next_slot(), lane_in_block, y, k3, kp_, sc.mb, sc.mb_stride);
-    { const double g1 = O::mul(cur, c_tab[T_C1]), g3 = O::mul(cur, c_tab[T_C3]);
-      const double e1 = O::mul(ecur, c_tab[T_DC1]), e3 = O::mul(ecur, c_tab[T_DC3]);
+    { const double g1 = cf(T_C1), g3 = cf(T_C3);
+      const double e1 = ef(T_DC1), e3 = ef(T_DC3);
 #pragma unroll
       for (int c = 0; c < NPAS; ++c) {
           accN[c] = O::mad(g3, kp_[c], O::mad(g1, k1[NDYN + c], x[NDYN + c]));
           accE[c] = O::mad(e3, kp_[c], O::mul(e1, k1[NDYN + c]));
       } }
     // stage 4
-    { const double f1 = O::mul(cur, c_tab[T_B41]), f2 = O::mul(cur, c_tab[T_B42]), f3 = O::mul(cur, c_tab[T_B43]);
+    { const double f1 = cf(T_B41), f2 = cf(T_B42), f3 = cf(T_B43);
 #pragma unroll
       for (int c = 0; c < NDYN; ++c) y[c] = O::mad(f3, k3[c], O::mad(f2, k2[c], O::mad(f1, k1[c], x[c]))); }
     rhs<NA, STRICT, true, !MIXED>(q, ba_at(T_A4), spi, next_slot(), lane_in_block, y, k4, kp_, sc.mb, sc.mb_stride);
-    { const double g4 = O::mul(cur, c_tab[T_C4]), e4 = O::mul(ecur, c_tab[T_DC4]);
+    { const double g4 = cf(T_C4), e4 = ef(T_DC4);
 #pragma unroll
       for (int c = 0; c < NPAS; ++c) { accN[c] = O::mad(g4, kp_[c], accN[c]); accE[c] = O::mad(e4, kp_[c], accE[c]); } }
     // stage 5
-    { const double f1 = O::mul(cur, c_tab[T_B51]), f2 = O::mul(cur, c_tab[T_B52]), f3 = O::mul(cur, c_tab[T_B53]),
-                   f4 = O::mul(cur, c_tab[T_B54]);
+    { const double f1 = cf(T_B51), f2 = cf(T_B52), f3 = cf(T_B53),
+                   f4 = cf(T_B54);
 #pragma unroll
       for (int c = 0; c < NDYN; ++c)
           y[c] = O::mad(f4, k4[c], O::mad(f3, k3[c], O::mad(f2, k2[c], O::mad(f1, k1[c], x[c])))); }
     rhs<NA, STRICT, true, !MIXED>(q, ba_at(T_A5), spi, next_slot(), lane_in_block, y, k5, kp_, sc.mb, sc.mb_stride);
-    { const double g5 = O::mul(cur, c_tab[T_C5]), e5 = O::mul(ecur, c_tab[T_DC5]);
+    { const double g5 = cf(T_C5), e5 = ef(T_DC5);
 #pragma unroll
       for (int c = 0; c < NPAS; ++c) { accN[c] = O::mad(g5, kp_[c], accN[c]); accE[c] = O::mad(e5, kp_[c], accE[c]); } }
     // stage 6
-    { const double f1 = O::mul(cur, c_tab[T_B61]), f2 = O::mul(cur, c_tab[T_B62]), f3 = O::mul(cur, c_tab[T_B63]),
-                   f4 = O::mul(cur, c_tab[T_B64]), f5 = O::mul(cur, c_tab[T_B65]);
+    { const double f1 = cf(T_B61), f2 = cf(T_B62), f3 = cf(T_B63),
+                   f4 = cf(T_B64), f5 = cf(T_B65);
 #pragma unroll
       for (int c = 0; c < NDYN; ++c)
           y[c] = O::mad(f5, k5[c], O::mad(f4, k4[c], O::mad(f3, k3[c], O::mad(f2, k2[c], O::mad(f1, k1[c], x[c]))))); }
     rhs<NA, STRICT, true, !MIXED>(q, ba_at(-1), spi, next_slot(), lane_in_block, y, k6, kp_, sc.mb, sc.mb_stride);
-    { const double g6 = O::mul(cur, c_tab[T_C6]), e6 = O::mul(ecur, c_tab[T_DC6]);
+    { const double g6 = cf(T_C6), e6 = ef(T_DC6);
 #pragma unroll
       for (int c = 0; c < NPAS; ++c) { accN[c] = O::mad(g6, kp_[c], accN[c]); accE[c] = O::mad(e6, kp_[c], accE[c]); } }
     // solution (dynamic part) and the FSAL derivative
-    { const double g1 = O::mul(cur, c_tab[T_C1]), g3 = O::mul(cur, c_tab[T_C3]), g4 = O::mul(cur, c_tab[T_C4]),
-                   g5 = O::mul(cur, c_tab[T_C5]), g6 = O::mul(cur, c_tab[T_C6]);
+    { const double g1 = cf(T_C1), g3 = cf(T_C3), g4 = cf(T_C4),
+                   g5 = cf(T_C5), g6 = cf(T_C6);
 #pragma unroll
       for (int c = 0; c < NDYN; ++c)
           xn[c] = O::mad(g6, k6[c], O::mad(g5, k5[c], O::mad(g4, k4[c], O::mad(g3, k3[c], O::mad(g1, k1[c], x[c]))))); }
     rhs<NA, STRICT, true, !MIXED>(q, ba_at(-1), spi, next_slot(), lane_in_block, xn, k7d, k7p, sc.mb, sc.mb_stride);
     // error estimate
-    { const double e1 = O::mul(ecur, c_tab[T_DC1]), e3 = O::mul(ecur, c_tab[T_DC3]), e4 = O::mul(ecur, c_tab[T_DC4]),
-                   e5 = O::mul(ecur, c_tab[T_DC5]), e6 = O::mul(ecur, c_tab[T_DC6]), e7 = O::mul(ecur, c_tab[T_DC7]);
+    { const double e1 = ef(T_DC1), e3 = ef(T_DC3), e4 = ef(T_DC4),
+                   e5 = ef(T_DC5), e6 = ef(T_DC6), e7 = ef(T_DC7);
 #pragma unroll
       for (int c = 0; c < NDYN; ++c)
           xe[c] = O::mad(e7, k7d[c], O::mad(e6, k6[c], O::mad(e5, k5[c], O::mad(e4, k4[c], O::mad(e3, k3[c], O::mul(e1, k1[c]))))));
@@ -716,6 +726,7 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) sepaihrd_batch_kernel(cons
             }
             // a breakpoint inside [t, t_next): attempts of this day may leave their schedule segment
             const bool day_bp = __any_sync(FULL, bp_next < t_next);
+            bool first_of_day = true;
             while (true) {
                 const double cur = active ? std_min(dt, rem) : 0.0;   // min_abs(dt, t_next - t)
                 const double t_end = t + cur;
@@ -743,7 +754,12 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) sepaihrd_batch_kernel(cons
                 }
                 double xn[NDYN], k7d[NDYN], k7p[NPAS], accN[NPAS], xe[NCOMP];
                 const double ecur = cur * kp.inv_rel;
-                if (run_mixed)
+                // first attempt of a breakpoint-free day with every stepping group at the full step hmax: constant coefficients
+                const bool unit = first_of_day && !day_bp && __all_sync(FULL, !active || cur == hmax);
+                first_of_day = false;
+                if (unit)
+                    dopri5_attempt<NA, false, false, true>(q, sc, spi, pi_slot, THREADS, threadIdx.x, t, cur, t_end, x, k1, xn, k7d, k7p, accN, xe, ecur, kp.hc);
+                else if (run_mixed)
                     dopri5_attempt<NA, false, true>(q, sc, spi, pi_slot, THREADS, threadIdx.x, t, cur, t_end, x, k1, xn, k7d, k7p, accN, xe, ecur);
                 else
                     dopri5_attempt<NA, false, false>(q, sc, spi, pi_slot, THREADS, threadIdx.x, t, cur, t_end, x, k1, xn, k7d, k7p, accN, xe, ecur);
