@@ -345,7 +345,7 @@ double SEPAIHRDParameterManager::getUpperBoundForParamIndex(int idx) const {
 
 void SEPAIHRDParameterManager::setConstraintMode(ConstraintMode mode) {
     mode_ = mode;
-    for (auto& cb : mode_listeners_) cb(mode);
+    for (auto& cb : mode_listeners_) if (cb) cb(mode);
 }
 
 // ---- DeviceContext ----------------------------------------------------------------------------------------------
@@ -495,10 +495,13 @@ SEPAIHRDObjectiveFunction::SEPAIHRDObjectiveFunction(std::shared_ptr<AgeSEPAIHRD
                                            initial_state, spm->slots(), lo, hi, spm->getConstraintMode(), abs_error, rel_error,
                                            1.0 /* the objective builds its simulator with time_step 1.0, .cpp:113 */);
     DeviceContext* dev = dev_.get();
-    spm->onConstraintModeChange([dev](ConstraintMode m) { dev->setConstraintMode(m); });
+    mode_listener_id_ = spm->onConstraintModeChange([dev](ConstraintMode m) { dev->setConstraintMode(m); });
 }
 
-SEPAIHRDObjectiveFunction::~SEPAIHRDObjectiveFunction() = default;
+SEPAIHRDObjectiveFunction::~SEPAIHRDObjectiveFunction() {
+    // the parameter manager may outlive this objective: stop forwarding its constraint mode to a dead device context
+    if (auto* spm = dynamic_cast<SEPAIHRDParameterManager*>(&parameterManager_)) spm->removeConstraintModeListener(mode_listener_id_);
+}
 
 const std::vector<std::string>& SEPAIHRDObjectiveFunction::getParameterNames() const { return parameterManager_.getParameterNames(); }
 

@@ -275,7 +275,8 @@ public:
     // slot (sepaihrd_b200.h layout) of every calibrated parameter, resolved once at construction
     const std::vector<int32_t>& slots() const { return slots_; }
     // observers of the constraint mode (the device context of an objective follows the manager's mode)
-    void onConstraintModeChange(std::function<void(ConstraintMode)> cb) { mode_listeners_.push_back(std::move(cb)); }
+    int onConstraintModeChange(std::function<void(ConstraintMode)> cb) { mode_listeners_.push_back(std::move(cb)); return static_cast<int>(mode_listeners_.size()) - 1; }
+    void removeConstraintModeListener(int id) { if (id >= 0 && static_cast<size_t>(id) < mode_listeners_.size()) mode_listeners_[static_cast<size_t>(id)] = nullptr; }
     static double reflectBound(double value, double min_b, double max_b);                    // .cpp:302-313
 
 private:
@@ -356,6 +357,7 @@ private:
     IParameterManager& parameterManager_;
     std::shared_ptr<AgeSEPAIHRDModel> model_;
     std::unique_ptr<DeviceContext> dev_;
+    int mode_listener_id_ = -1;
 };
 
 // ---- posterior-predictive aggregation (include/model/ResultAggregator.hpp, PostCalibrationAnalyser) ---------------
