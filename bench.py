@@ -125,7 +125,7 @@ def cpu_baseline(oracle, params, target_seconds: float = 12.0):
                       "dependency-free restatement of the reference path (the reference needs Boost/Eigen, absent here)"}, ll
 
 
-def run_reference(args):
+def run_reference(args, json_out):
     """--impl reference: the reference's CPU path (oracle port) on the host cores, same config/metric."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -147,16 +147,27 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     value = args.steps * m / dt
     sample = f"{m} sets per step (bounded sample of the 1M-set batch), {used} OpenMP threads"
-    print(json.dumps({"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+    json_out.write(json.dumps({"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
                       "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
                       "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                       "data": "synthetic", "config": workload_config(args.gpus, B_PER_GPU),
                       "cpu_baseline": {"value": value, "unit": UNIT, "cores": int(used), "kind": "port", "sample": sample},
                       "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                      "gpu_launches": 0}))
+                      "gpu_launches": 0}) + "\n")
+    json_out.flush()
+
+
+def _claim_stdout():
+    """Keep file descriptor 1 for the ONE JSON line: everything else that writes to stdout while the benchmark runs
+    (NCCL prints its version banner there, libraries may log) is sent to stderr.  Returns the stream for the JSON line."""
+    sys.stdout.flush()
+    out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return out
 
 
 def main():
+    json_out = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -166,7 +177,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
-        return run_reference(args)
+        return run_reference(args, json_out)
     args.warmup = max(args.warmup, 3)
 
     import torch
@@ -286,7 +297,8 @@ def main():
             rel = np.abs(h_ll.numpy()[:m] - ll_cpu) / np.abs(ll_cpu)
             base["max_rel_logl_diff_vs_gpu"] = float(rel.max())
             out["cpu_baseline"] = base
-        print(json.dumps(out))
+        json_out.write(json.dumps(out) + "\n")
+        json_out.flush()
     ev.close()
     if world > 1:
         dist.barrier()
