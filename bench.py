@@ -110,15 +110,25 @@ class ClockSampler:
                 "reasons": reasons}
 
 
+def host_cores() -> int:
+    """Host threads the CPU arm may use: every core this process is allowed on.  Passed to the oracle EXPLICITLY because
+    torchrun exports OMP_NUM_THREADS=1 to its ranks, which would silently shrink the CPU baseline to one core."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_baseline(oracle, params, target_seconds: float = 12.0):
     """The oracle (restated reference path, kind = "port") on all host cores, on a bounded sample."""
+    nt = host_cores()
     probe = params[:256]
     t0 = time.perf_counter()
-    _, _, _, used = oracle.eval_batch(probe)
+    _, _, _, used = oracle.eval_batch(probe, nthreads=nt)
     rate = len(probe) / (time.perf_counter() - t0)
     m = int(min(len(params), max(1024, rate * target_seconds)))
     t0 = time.perf_counter()
-    ll, _, _, used = oracle.eval_batch(params[:m])
+    ll, _, _, used = oracle.eval_batch(params[:m], nthreads=nt)
     dt = time.perf_counter() - t0
     return {"value": m / dt, "unit": UNIT, "cores": int(used), "kind": "port",
             "sample": f"first {m} sets of the same batch, OpenMP schedule(dynamic) over sets, {dt:.1f} s; the oracle is the "
@@ -134,16 +144,17 @@ def run_reference(args, json_out):
     orc.build()
     prob, oracle, params = make_params(pkg, orc, B_PER_GPU)
     probe = params[:256]
-    t0 = time.perf_counter(); oracle.eval_batch(probe); rate = 256 / (time.perf_counter() - t0)
+    nt = host_cores()
+    t0 = time.perf_counter(); oracle.eval_batch(probe, nthreads=nt); rate = 256 / (time.perf_counter() - t0)
     budget = 150.0 / max(1, args.steps + args.warmup)          # whole run within a few minutes
     m = int(min(len(params), max(512, rate * min(20.0, budget))))
     for _ in range(args.warmup):
-        oracle.eval_batch(params[:m])
+        oracle.eval_batch(params[:m], nthreads=nt)
     t0 = time.perf_counter()
     used = 1
     for s in range(args.steps):
         off = (s * m) % (len(params) - m + 1)
-        _, _, _, used = oracle.eval_batch(params[off:off + m])
+        _, _, _, used = oracle.eval_batch(params[off:off + m], nthreads=nt)
     dt = time.perf_counter() - t0
     value = args.steps * m / dt
     sample = f"{m} sets per step (bounded sample of the 1M-set batch), {used} OpenMP threads"
