@@ -245,6 +245,52 @@ int32_t sepaihrd_host_optimize(const char* algorithm, sepaihrd_host_pm* pm, int3
     });
 }
 
+int32_t sepaihrd_host_calibrate(const char* phase1, sepaihrd_host_pm* pm, int32_t n1, const char* const* k1, const double* v1, int32_t n2,
+                                const char* const* k2, const double* v2, sepaihrd_host_batch_fn fn, void* user, const double* initial,
+                                double* out_best, double* out_value, int64_t* out_samples, double* out_phase1) {
+    return guarded([&] {
+        // ModelCalibrator owns its parameter manager and objective: hand it copies that forward to the caller's objects
+        struct ForwardPM : IParameterManager {
+            ArrayParameterManager& p; VectorXd current;
+            ForwardPM(ArrayParameterManager& p_, const VectorXd& c) : p(p_), current(c) {}
+            VectorXd getCurrentParameters() const override { return current; }
+            void updateModelParameters(const VectorXd& v) override { current = v; }
+            const std::vector<std::string>& getParameterNames() const override { return p.getParameterNames(); }
+            size_t getParameterCount() const override { return p.getParameterCount(); }
+            double getSigmaForParamIndex(int i) const override { return p.getSigmaForParamIndex(i); }
+            VectorXd applyConstraints(const VectorXd& v) const override { return p.applyConstraints(v); }
+            int getIndexForParam(const std::string& n) const override { return p.getIndexForParam(n); }
+            double getLowerBoundForParamIndex(int i) const override { return p.getLowerBoundForParamIndex(i); }
+            double getUpperBoundForParamIndex(int i) const override { return p.getUpperBoundForParamIndex(i); }
+        };
+        const auto P = static_cast<std::ptrdiff_t>(pm->pm.getParameterCount());
+        std::map<std::string, std::unique_ptr<IOptimizationAlgorithm>> algos;
+        const std::string which = phase1 ? phase1 : "pso";
+        if (which == "hill") algos[ModelCalibrator::PHASE1_NAME] = std::make_unique<HillClimbingOptimizer>();
+        else if (which == "pso") algos[ModelCalibrator::PHASE1_NAME] = std::make_unique<ParticleSwarmOptimization>();
+        else throw InvalidParameterException("sepaihrd_host_calibrate", "phase1 must be pso or hill");
+        // the sampler of phase 2 flips the SEPAIHRD manager to reflection itself; an array manager is flipped here
+        struct ReflectingMH : MetropolisHastingsSampler {
+            ArrayParameterManager& p;
+            explicit ReflectingMH(ArrayParameterManager& p_) : p(p_) {}
+            OptimizationResult optimize(const VectorXd& x0, IObjectiveFunction& f, IParameterManager& m) override {
+                p.setMode(1);
+                return MetropolisHastingsSampler::optimize(x0, f, m);
+            }
+        };
+        algos[ModelCalibrator::PHASE2_NAME] = std::make_unique<ReflectingMH>(pm->pm);
+        pm->pm.setMode(0);
+        auto objective = std::make_unique<CallbackObjective>(fn, user, pm->pm.getParameterNames());
+        ModelCalibrator c(std::make_unique<ForwardPM>(pm->pm, VectorXd::FromPointer(initial, P)), std::move(objective), std::move(algos));
+        c.calibrate(settings_map(n1, k1, v1), settings_map(n2, k2, v2));
+        const VectorXd& b = c.getBestParameterVector();
+        if (out_best) std::copy(b.data(), b.data() + P, out_best);
+        if (out_value) *out_value = c.getBestObjectiveValue();
+        if (out_samples) *out_samples = static_cast<int64_t>(c.getMCMCObjectiveValues().size());
+        if (out_phase1) *out_phase1 = c.getPhase1Result().bestObjectiveValue;
+    });
+}
+
 // ---- reference-shaped object graph --------------------------------------------------------------------------
 int32_t sepaihrd_host_model_create(const sepaihrd_problem* pb, const char* const* names, const double* sigmas, sepaihrd_host_model** out) {
     return guarded([&] {

@@ -79,6 +79,14 @@ int32_t sepaihrd_host_optimize(const char* algorithm, sepaihrd_host_pm* pm, int3
                                const double* values, sepaihrd_host_batch_fn fn, void* user, const double* initial,
                                double* out_best /* [P] */, double* out_best_value, int64_t* out_n_evaluations);
 
+/* ModelCalibrator::calibrate (two phases, covariance hand-off, batched re-scoring of the samples) against a batch callback:
+ * phase 1 = "pso" | "hill", phase 2 = Metropolis-Hastings.  The parameter manager's mode is switched clamp -> reflect between
+ * the phases exactly like ModelCalibrator.cpp:62-66, 88-92. */
+int32_t sepaihrd_host_calibrate(const char* phase1, sepaihrd_host_pm* pm, int32_t n1, const char* const* keys1, const double* values1,
+                                int32_t n2, const char* const* keys2, const double* values2, sepaihrd_host_batch_fn fn, void* user,
+                                const double* initial, double* out_best /* [P] */, double* out_best_value, int64_t* out_n_samples,
+                                double* out_phase1_value);
+
 /* ---- the reference-shaped object graph over the device evaluator -------------------------------------------- *
  * Builds SEPAIHRDParameters -> PiecewiseConstantNpiStrategy -> AgeSEPAIHRDModel -> CalibrationData ->
  * SEPAIHRDModelCalibration (-> SEPAIHRDParameterManager, SEPAIHRDObjectiveFunction, AgeSEPAIHRDSimulator) from a

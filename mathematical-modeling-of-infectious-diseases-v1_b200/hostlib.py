@@ -54,6 +54,7 @@ SIGNATURES = {
     "sepaihrd_host_pso_step": (C.c_int32, [_vp, C.c_int32]),
     "sepaihrd_host_pso_destroy": (None, [_vp]),
     "sepaihrd_host_optimize": (C.c_int32, [C.c_char_p, _vp, C.c_int32, _keys, _vp, BATCH_FN, _vp, _vp, _vp, _dp, _i64p]),
+    "sepaihrd_host_calibrate": (C.c_int32, [C.c_char_p, _vp, C.c_int32, _keys, _vp, C.c_int32, _keys, _vp, BATCH_FN, _vp, _vp, _vp, _dp, _i64p, _dp]),
     "sepaihrd_host_model_create": (C.c_int32, [_vp, _keys, _vp, _vpp]),
     "sepaihrd_host_model_calculate": (C.c_int32, [_vp, _vp, _dp]),
     "sepaihrd_host_model_calculate_batch": (C.c_int32, [_vp, _vp, C.c_int64, C.c_int64, _vp]),
@@ -254,6 +255,31 @@ def optimize(algorithm: str, pm: ParameterManager, settings: Dict[str, float], e
     check(L.sepaihrd_host_optimize(algorithm.encode(), pm._h, n, keys, vals.ctypes.data, cb, None, x0.ctypes.data, best.ctypes.data,
                                    C.byref(val), C.byref(nev)))
     return best, val.value, nev.value
+
+
+def calibrate(phase1: str, pm: ParameterManager, settings1: Dict[str, float], settings2: Dict[str, float],
+              evaluate: Callable[[np.ndarray], np.ndarray], initial):
+    """ModelCalibrator::calibrate (phase 1 "pso" | "hill", phase 2 Metropolis-Hastings) with ``evaluate`` as the objective.
+    Returns (best vector, best value, number of re-scored MCMC samples, best value of phase 1)."""
+    L, P = pm.L, pm.n
+
+    def _cb(_user, params, B, ld, out):
+        try:
+            x = np.ctypeslib.as_array(params, shape=(B, ld))[:, :P]
+            np.ctypeslib.as_array(out, shape=(B,))[:] = evaluate(np.ascontiguousarray(x))
+            return 0
+        except Exception:
+            import traceback
+            traceback.print_exc()
+            return 1
+
+    cb = BATCH_FN(_cb)
+    n1, k1, v1 = _settings(settings1); n2, k2, v2 = _settings(settings2)
+    x0 = _c64(initial)
+    best = np.empty(P); val = C.c_double(); ns = C.c_int64(); p1 = C.c_double()
+    check(L.sepaihrd_host_calibrate(phase1.encode(), pm._h, n1, k1, v1.ctypes.data, n2, k2, v2.ctypes.data, cb, None, x0.ctypes.data,
+                                    best.ctypes.data, C.byref(val), C.byref(ns), C.byref(p1)))
+    return best, val.value, ns.value, p1.value
 
 
 class HostModel:

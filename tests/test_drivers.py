@@ -205,3 +205,21 @@ def test_world_size_two_gloo_matches_single_process(tmp_path, host, problem):
     for r in two:
         np.testing.assert_array_equal(r["trace"], one[0]["trace"])
         np.testing.assert_array_equal(r["best_position"], one[0]["best_position"])
+
+
+def test_two_phase_model_calibrator_on_a_synthetic_posterior(host, problem):
+    """ModelCalibrator::calibrate on the CPU with a synthetic Gaussian log-posterior: phase 1 (PSO or hill climbing, clamp mode)
+    hands its covariance to phase 2 (Metropolis-Hastings, reflect mode, eigenvalues floored at (0.1 sigma)^2, x4 inflation), and
+    every stored MCMC sample is re-scored in one batch."""
+    mid = 0.5 * (problem.lower_bound + problem.upper_bound)
+    width = problem.upper_bound - problem.lower_bound
+    target = mid + 0.1 * width
+    ev = lambda x: -0.5 * (((x - target) / (0.05 * width)) ** 2).sum(axis=1)
+    pm = host.ParameterManager(problem.sigmas, problem.lower_bound, problem.upper_bound, mode=0)
+    f0 = ev(mid[None])[0]
+    for phase1, s1 in (("pso", dict(iterations=25, swarm_size=40, seed=2)), ("hill", dict(iterations=15, cloud_size=32, seed=2))):
+        best, val, n_samples, p1 = host.calibrate(phase1, pm, s1, dict(mcmc_iterations=40, burn_in=40, n_chains=4, seed=3, thinning=2), ev, mid)
+        assert p1 > f0 and val >= p1                      # phase 1 improves on the start, the overall best is at least that
+        assert n_samples == 4 * (1 + 39 // 2)             # initial state + every 2nd iteration, per chain
+        np.testing.assert_allclose(ev(best[None])[0], val, rtol=1e-12)
+        assert np.all(best >= problem.lower_bound) and np.all(best <= problem.upper_bound)
