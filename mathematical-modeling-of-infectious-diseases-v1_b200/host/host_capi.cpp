@@ -415,3 +415,156 @@ int32_t sepaihrd_host_model_posterior_predictive(sepaihrd_host_model* m, const d
 void sepaihrd_host_model_destroy(sepaihrd_host_model* m) { delete m; }
 
 }  // extern "C"
+
+// ---- the reference's on-disk formats ----------------------------------------------------------------------------
+#include "config_io.hpp"
+
+#include <cstdio>
+
+namespace {
+
+thread_local std::string g_json;
+
+struct Json {
+    std::string s;
+    static std::string num(double v) {
+        if (!std::isfinite(v)) return "null";
+        char buf[40];
+        std::snprintf(buf, sizeof buf, "%.17g", v);
+        return buf;
+    }
+    static std::string str(const std::string& v) {
+        std::string o = "\"";
+        for (char c : v) {
+            if (c == '"' || c == '\\') { o += '\\'; o += c; }
+            else if (static_cast<unsigned char>(c) < 0x20) { char b[8]; std::snprintf(b, sizeof b, "\\u%04x", c); o += b; }
+            else o += c;
+        }
+        return o + "\"";
+    }
+    template <class It> static std::string nums(It b, It e) {
+        std::string o = "[";
+        for (It i = b; i != e; ++i) { if (i != b) o += ','; o += num(*i); }
+        return o + "]";
+    }
+    static std::string nums(const VectorXd& v) { return nums(v.data(), v.data() + v.size()); }
+    static std::string nums(const std::vector<double>& v) { return nums(v.begin(), v.end()); }
+    static std::string rowmajor(const MatrixXd& m) {
+        std::vector<double> f;
+        for (std::ptrdiff_t i = 0; i < m.rows(); ++i) for (std::ptrdiff_t j = 0; j < m.cols(); ++j) f.push_back(m(i, j));
+        return nums(f);
+    }
+    static std::string strs(const std::vector<std::string>& v) {
+        std::string o = "[";
+        for (size_t i = 0; i < v.size(); ++i) { if (i) o += ','; o += str(v[i]); }
+        return o + "]";
+    }
+    void field(const char* key, const std::string& value) { s += (s.empty() ? "{" : ",") + str(key) + ":" + value; }
+    std::string done() { return s.empty() ? "{}" : s + "}"; }
+};
+
+std::string parameters_json(const SEPAIHRDParameters& p) {
+    Json j;
+    j.field("beta", Json::num(p.beta)); j.field("theta", Json::num(p.theta)); j.field("sigma", Json::num(p.sigma));
+    j.field("gamma_p", Json::num(p.gamma_p)); j.field("gamma_A", Json::num(p.gamma_A)); j.field("gamma_I", Json::num(p.gamma_I));
+    j.field("gamma_H", Json::num(p.gamma_H)); j.field("gamma_ICU", Json::num(p.gamma_ICU));
+    j.field("E0_multiplier", Json::num(p.E0_multiplier)); j.field("P0_multiplier", Json::num(p.P0_multiplier));
+    j.field("A0_multiplier", Json::num(p.A0_multiplier)); j.field("I0_multiplier", Json::num(p.I0_multiplier));
+    j.field("H0_multiplier", Json::num(p.H0_multiplier)); j.field("ICU0_multiplier", Json::num(p.ICU0_multiplier));
+    j.field("R0_multiplier", Json::num(p.R0_multiplier)); j.field("D0_multiplier", Json::num(p.D0_multiplier));
+    j.field("runup_days", Json::num(p.runup_days)); j.field("seed_exposed", Json::num(p.seed_exposed));
+    j.field("a", Json::nums(p.a)); j.field("h_infec", Json::nums(p.h_infec)); j.field("p", Json::nums(p.p)); j.field("h", Json::nums(p.h));
+    j.field("icu", Json::nums(p.icu)); j.field("d_H", Json::nums(p.d_H)); j.field("d_ICU", Json::nums(p.d_ICU));
+    j.field("d_community", Json::nums(p.d_community));
+    j.field("beta_end_times", Json::nums(p.beta_end_times)); j.field("beta_values", Json::nums(p.beta_values));
+    j.field("kappa_end_times", Json::nums(p.kappa_end_times)); j.field("kappa_values", Json::nums(p.kappa_values));
+    return j.done();
+}
+
+}  // namespace
+
+extern "C" const char* sepaihrd_host_read_file_json(const char* kind, const char* filename, int32_t a, int32_t b, const char* start_date,
+                                                    const char* end_date) {
+    const int32_t rc = guarded([&] {
+        const std::string k = kind ? kind : "", f = filename ? filename : "";
+        Json j;
+        if (k == "parameters") {
+            g_json = parameters_json(readSEPAIHRDParameters(f, a));
+            return;
+        } else if (k == "bounds") {
+            for (const auto& [name, lh] : readParamBounds(f)) j.field(name.c_str(), "[" + Json::num(lh.first) + "," + Json::num(lh.second) + "]");
+        } else if (k == "sigmas") {
+            for (const auto& [name, v] : readProposalSigmas(f)) j.field(name.c_str(), Json::num(v));
+        } else if (k == "settings") {
+            for (const auto& [name, v] : readMetropolisHastingsSettings(f)) j.field(name.c_str(), Json::num(v));
+        } else if (k == "names") {
+            j.field("names", Json::strs(readParamsToCalibrate(f)));
+        } else if (k == "matrix") {
+            j.field("rowmajor", Json::rowmajor(readMatrixFromCSV(f, a, b)));
+        } else if (k == "data") {
+            const CalibrationDataFile d(f, start_date ? start_date : "", end_date ? end_date : "");
+            j.field("dates", Json::strs(d.getDates()));
+            j.field("population", Json::nums(d.getPopulationByAgeGroup()));
+            j.field("new_confirmed", Json::rowmajor(d.getNewConfirmedCases()));
+            j.field("new_hospitalizations", Json::rowmajor(d.getNewHospitalizations()));
+            j.field("new_icu", Json::rowmajor(d.getNewICU()));
+            j.field("new_deaths", Json::rowmajor(d.getNewDeaths()));
+            j.field("cumulative_confirmed", Json::rowmajor(d.getCumulativeConfirmedCases()));
+            j.field("cumulative_deaths", Json::rowmajor(d.getCumulativeDeaths()));
+            j.field("cumulative_hospitalizations", Json::rowmajor(d.getCumulativeHospitalizations()));
+            j.field("cumulative_icu", Json::rowmajor(d.getCumulativeICU()));
+        } else {
+            throw InvalidParameterException("sepaihrd_host_read_file_json", "unknown kind: " + k);
+        }
+        g_json = j.done();
+    });
+    return rc == 0 ? g_json.c_str() : nullptr;
+}
+
+extern "C" const char* sepaihrd_host_project_json(const char* project_root, const char* start_date, const char* end_date, int32_t n_ages) {
+    const int32_t rc = guarded([&] {
+        const ReferenceProject prj = loadReferenceProject(project_root ? project_root : "", start_date ? start_date : "",
+                                                          end_date ? end_date : "", n_ages);
+        SEPAIHRDParameterManager pm(prj.model, prj.params_to_calibrate, prj.proposal_sigmas, prj.param_bounds);   // validates names / sigmas / bounds
+        std::vector<double> lo, hi, sg;
+        for (size_t i = 0; i < prj.params_to_calibrate.size(); ++i) {
+            lo.push_back(pm.getLowerBoundForParamIndex(static_cast<int>(i)));
+            hi.push_back(pm.getUpperBoundForParamIndex(static_cast<int>(i)));
+            sg.push_back(pm.getSigmaForParamIndex(static_cast<int>(i)));
+        }
+        Json j;
+        j.field("format", Json::str("sepaihrd_problem/1"));
+        j.field("n_ages", std::to_string(n_ages));
+        j.field("times", Json::nums(prj.time_points));
+        j.field("obs_hosp", Json::rowmajor(prj.data->getNewHospitalizations()));
+        j.field("obs_icu", Json::rowmajor(prj.data->getNewICU()));
+        j.field("obs_deaths", Json::rowmajor(prj.data->getNewDeaths()));
+        j.field("population", Json::nums(prj.data->getPopulationByAgeGroup()));
+        j.field("contact_matrix_rowmajor", Json::rowmajor(prj.model->getContactMatrix()));
+        j.field("beta_end_times", Json::nums(prj.params.beta_end_times));
+        j.field("kappa_end_times", Json::nums(prj.model->kappaEndTimes()));
+        j.field("base_slots", Json::nums(prj.model->slotVector()));
+        j.field("data_initial_state", Json::nums(prj.data_initial_state));
+        j.field("initial_state", Json::nums(prj.initial_state));
+        j.field("param_names", Json::strs(prj.params_to_calibrate));
+        j.field("lower_bound", Json::nums(lo));
+        j.field("upper_bound", Json::nums(hi));
+        j.field("sigmas", Json::nums(sg));
+        j.field("constraint_mode", "0");
+        j.field("abs_tol", Json::num(prj.abs_error));
+        j.field("rel_tol", Json::num(prj.rel_error));
+        j.field("dt_hint", Json::num(prj.dt_hint));
+        g_json = j.done();
+    });
+    return rc == 0 ? g_json.c_str() : nullptr;
+}
+
+extern "C" int32_t sepaihrd_host_resave_parameters(const char* in_file, int32_t n_ages, const char* out_file, int32_t n_calibrated,
+                                                   const char* const* calibrated_names, double obj_value, const char* timestamp) {
+    return guarded([&] {
+        const SEPAIHRDParameters p = readSEPAIHRDParameters(in_file ? in_file : "", n_ages);
+        std::vector<std::string> names;
+        for (int32_t i = 0; i < n_calibrated; ++i) names.emplace_back(calibrated_names[i]);
+        saveCalibrationResults(out_file ? out_file : "", p, names, obj_value, timestamp ? timestamp : "");
+    });
+}

@@ -113,6 +113,20 @@ int32_t sepaihrd_host_model_posterior_predictive(sepaihrd_host_model* m, const d
                                                  uint32_t random_seed, const double* initial_state, double* out, int64_t* out_samples_used);
 void    sepaihrd_host_model_destroy(sepaihrd_host_model* m);
 
+/* ---- the reference's on-disk formats (config_io.hpp: C++ readers / writer) ------------- *
+ * Both return JSON text owned by the library (valid until the next call on this thread), or NULL with the message in
+ * sepaihrd_host_last_error().  Non-finite numbers are written as null.
+ *   kind = "parameters" (a = number of age classes), "bounds", "sigmas", "names", "settings", "matrix" (a rows, b cols),
+ *          "data" (start / end date window; empty string = open)                                                       */
+const char* sepaihrd_host_read_file_json(const char* kind, const char* filename, int32_t a, int32_t b, const char* start_date,
+                                         const char* end_date);
+/* loadReferenceProject(root, start, end): the problem main() assembles, with the keys of the Python Problem JSON
+ * (format "sepaihrd_problem/1") plus "initial_state" (the state main() integrates from).                               */
+const char* sepaihrd_host_project_json(const char* project_root, const char* start_date, const char* end_date, int32_t n_ages);
+/* readSEPAIHRDParameters(in_file) -> saveCalibrationResults(out_file, ...): the writer's round trip */
+int32_t sepaihrd_host_resave_parameters(const char* in_file, int32_t n_ages, const char* out_file, int32_t n_calibrated,
+                                        const char* const* calibrated_names, double obj_value, const char* timestamp);
+
 #ifdef __cplusplus
 }
 #endif

@@ -9,7 +9,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
-from typing import Callable, Dict, Optional, Sequence
+from typing import Callable, Dict, List, Optional, Sequence
 
 import numpy as np
 
@@ -65,6 +65,9 @@ SIGNATURES = {
     "sepaihrd_host_model_calibrate": (C.c_int32, [_vp, C.c_char_p, C.c_int32, _keys, _vp, C.c_int32, _keys, _vp, _vp, _dp, _i64p]),
     "sepaihrd_host_model_posterior_predictive": (C.c_int32, [_vp, _vp, C.c_int64, C.c_int32, C.c_uint32, _vp, _vp, _i64p]),
     "sepaihrd_host_model_destroy": (None, [_vp]),
+    "sepaihrd_host_read_file_json": (C.c_char_p, [C.c_char_p, C.c_char_p, C.c_int32, C.c_int32, C.c_char_p, C.c_char_p]),
+    "sepaihrd_host_project_json": (C.c_char_p, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int32]),
+    "sepaihrd_host_resave_parameters": (C.c_int32, [C.c_char_p, C.c_int32, C.c_char_p, C.c_int32, _keys, C.c_double, C.c_char_p]),
 }
 
 
@@ -347,3 +350,30 @@ class HostModel:
 
     def __del__(self):
         self.close()
+
+
+# ---- the reference's on-disk formats through the C++ readers (host/config_io.hpp) ---------------------------------
+def read_file(kind: str, path: str, a: int = 0, b: int = 0, start_date: str = "", end_date: str = "") -> dict:
+    """kind: parameters (a = ages) | bounds | sigmas | names | settings | matrix (a x b) | data (date window).
+    Raises HostError with the C++ exception text (FileIOException / DataFormatException / CSVReadException)."""
+    import json
+    txt = load_library().sepaihrd_host_read_file_json(kind.encode(), os.fsencode(path), int(a), int(b), start_date.encode(), end_date.encode())
+    if txt is None:
+        check(1)
+    return json.loads(txt.decode())
+
+
+def load_reference_project(root: str, start_date: str = "2020-03-01", end_date: str = "2020-12-31", n_ages: int = 4) -> dict:
+    """loadReferenceProject (main.cpp:188-316) in C++; the dict has the keys of Problem.to_json() plus initial_state."""
+    import json
+    txt = load_library().sepaihrd_host_project_json(os.fsencode(root), start_date.encode(), end_date.encode(), int(n_ages))
+    if txt is None:
+        check(1)
+    return json.loads(txt.decode())
+
+
+def resave_parameters(in_file: str, n_ages: int, out_file: str, calibrated: List[str], obj_value: float, timestamp: str = "") -> None:
+    """readSEPAIHRDParameters -> saveCalibrationResults."""
+    names = (C.c_char_p * max(len(calibrated), 1))(*[c.encode() for c in calibrated])
+    check(load_library().sepaihrd_host_resave_parameters(os.fsencode(in_file), int(n_ages), os.fsencode(out_file), len(calibrated), names,
+                                                         float(obj_value), timestamp.encode()))
