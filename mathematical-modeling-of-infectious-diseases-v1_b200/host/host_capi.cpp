@@ -6,6 +6,7 @@
 #include <cstring>
 #include <string>
 
+#include "analysis.hpp"
 #include "optimizers.hpp"
 
 using namespace epidemic;
@@ -113,6 +114,42 @@ struct sepaihrd_host_model {
     std::unique_ptr<AgeSEPAIHRDSimulator> simulator;
     double abs_tol = 1e-6, rel_tol = 1e-6;
 };
+
+// SEPAIHRDParameters -> PiecewiseConstantNpiStrategy -> AgeSEPAIHRDModel from the flat problem description (host only: no
+// device is touched).  createNpiStrategy (src/model/main.cpp:81-130): element 0 of the kappa schedule is the fixed baseline.
+static std::shared_ptr<AgeSEPAIHRDModel> model_from_problem(const sepaihrd_problem* pb, const std::map<std::string, std::pair<double, double>>& bounds,
+                                                     SEPAIHRDParameters* params_out = nullptr) {
+    const int n = pb->n_ages, nb = pb->n_beta, nk = pb->n_kappa;
+    const double* s = pb->base_slots;
+    const int scal0 = nb + nk, age0 = scal0 + 7, mult0 = age0 + 8 * n;
+    SEPAIHRDParameters p;
+    p.N = VectorXd::FromPointer(pb->population, n);
+    p.M_baseline = MatrixXd(n, n);
+    std::copy(pb->contact_matrix, pb->contact_matrix + n * n, p.M_baseline.data());      // column-major both sides
+    p.beta_end_times.assign(pb->beta_end_times, pb->beta_end_times + nb);
+    p.beta_values.assign(s, s + nb);
+    p.kappa_end_times.assign(pb->kappa_end_times, pb->kappa_end_times + nk);
+    p.kappa_values.assign(s + nb, s + nb + nk);
+    p.theta = s[scal0]; p.sigma = s[scal0 + 1]; p.gamma_p = s[scal0 + 2]; p.gamma_A = s[scal0 + 3];
+    p.gamma_I = s[scal0 + 4]; p.gamma_H = s[scal0 + 5]; p.gamma_ICU = s[scal0 + 6];
+    VectorXd* blocks[8] = {&p.a, &p.h_infec, &p.p, &p.h, &p.icu, &p.d_H, &p.d_ICU, &p.d_community};
+    for (int b = 0; b < 8; ++b) *blocks[b] = VectorXd::FromPointer(s + age0 + b * n, n);
+    p.E0_multiplier = s[mult0]; p.P0_multiplier = s[mult0 + 1]; p.A0_multiplier = s[mult0 + 2]; p.I0_multiplier = s[mult0 + 3];
+    p.H0_multiplier = s[mult0 + 4]; p.ICU0_multiplier = s[mult0 + 5]; p.R0_multiplier = s[mult0 + 6]; p.D0_multiplier = s[mult0 + 7];
+    p.seed_exposed = s[mult0 + 8]; p.runup_days = s[mult0 + 9]; p.beta = s[mult0 + 10];
+    std::vector<std::string> knames;
+    std::map<std::string, std::pair<double, double>> kbounds;
+    for (int k = 1; k < nk; ++k) {
+        knames.push_back("kappa_" + std::to_string(k + 1));
+        auto it = bounds.find(knames.back());
+        if (it != bounds.end()) kbounds[knames.back()] = it->second;
+    }
+    auto npi = std::make_shared<PiecewiseConstantNpiStrategy>(
+        std::vector<double>(p.kappa_end_times.begin() + 1, p.kappa_end_times.end()),
+        std::vector<double>(p.kappa_values.begin() + 1, p.kappa_values.end()), kbounds, p.kappa_values.at(0), p.kappa_end_times.at(0), true, knames);
+    if (params_out) *params_out = p;
+    return std::make_shared<AgeSEPAIHRDModel>(p, npi);
+}
 
 extern "C" {
 
@@ -295,25 +332,7 @@ int32_t sepaihrd_host_calibrate(const char* phase1, sepaihrd_host_pm* pm, int32_
 int32_t sepaihrd_host_model_create(const sepaihrd_problem* pb, const char* const* names, const double* sigmas, sepaihrd_host_model** out) {
     return guarded([&] {
         if (!pb || !names || !sigmas || !out) throw InvalidParameterException("sepaihrd_host_model_create", "bad argument");
-        const int n = pb->n_ages, nb = pb->n_beta, nk = pb->n_kappa;
-        const double* s = pb->base_slots;
-        const int scal0 = nb + nk, age0 = scal0 + 7, mult0 = age0 + 8 * n;
-        SEPAIHRDParameters p;
-        p.N = VectorXd::FromPointer(pb->population, n);
-        p.M_baseline = MatrixXd(n, n);
-        std::copy(pb->contact_matrix, pb->contact_matrix + n * n, p.M_baseline.data());      // column-major both sides
-        p.beta_end_times.assign(pb->beta_end_times, pb->beta_end_times + nb);
-        p.beta_values.assign(s, s + nb);
-        p.kappa_end_times.assign(pb->kappa_end_times, pb->kappa_end_times + nk);
-        p.kappa_values.assign(s + nb, s + nb + nk);
-        p.theta = s[scal0]; p.sigma = s[scal0 + 1]; p.gamma_p = s[scal0 + 2]; p.gamma_A = s[scal0 + 3];
-        p.gamma_I = s[scal0 + 4]; p.gamma_H = s[scal0 + 5]; p.gamma_ICU = s[scal0 + 6];
-        VectorXd* blocks[8] = {&p.a, &p.h_infec, &p.p, &p.h, &p.icu, &p.d_H, &p.d_ICU, &p.d_community};
-        for (int b = 0; b < 8; ++b) *blocks[b] = VectorXd::FromPointer(s + age0 + b * n, n);
-        p.E0_multiplier = s[mult0]; p.P0_multiplier = s[mult0 + 1]; p.A0_multiplier = s[mult0 + 2]; p.I0_multiplier = s[mult0 + 3];
-        p.H0_multiplier = s[mult0 + 4]; p.ICU0_multiplier = s[mult0 + 5]; p.R0_multiplier = s[mult0 + 6]; p.D0_multiplier = s[mult0 + 7];
-        p.seed_exposed = s[mult0 + 8]; p.runup_days = s[mult0 + 9]; p.beta = s[mult0 + 10];
-
+        const int n = pb->n_ages;
         std::map<std::string, double> sig;
         std::map<std::string, std::pair<double, double>> bounds;
         std::vector<std::string> pnames;
@@ -322,19 +341,9 @@ int32_t sepaihrd_host_model_create(const sepaihrd_problem* pb, const char* const
             sig[names[i]] = sigmas[i];
             bounds[names[i]] = {pb->lower_bound[i], pb->upper_bound[i]};
         }
-        // createNpiStrategy (src/model/main.cpp:81-130): element 0 is the fixed baseline
-        std::vector<std::string> knames;
-        std::map<std::string, std::pair<double, double>> kbounds;
-        for (int k = 1; k < nk; ++k) {
-            knames.push_back("kappa_" + std::to_string(k + 1));
-            auto it = bounds.find(knames.back());
-            if (it != bounds.end()) kbounds[knames.back()] = it->second;
-        }
-        auto npi = std::make_shared<PiecewiseConstantNpiStrategy>(
-            std::vector<double>(p.kappa_end_times.begin() + 1, p.kappa_end_times.end()),
-            std::vector<double>(p.kappa_values.begin() + 1, p.kappa_values.end()), kbounds, p.kappa_values.at(0), p.kappa_end_times.at(0), true, knames);
+        SEPAIHRDParameters p;
         auto h = std::make_unique<sepaihrd_host_model>();
-        h->model = std::make_shared<AgeSEPAIHRDModel>(p, npi);
+        h->model = model_from_problem(pb, bounds, &p);
         auto obs = [&](const double* src) {
             MatrixXd m(pb->n_obs, n);
             for (int r = 0; r < pb->n_obs; ++r) for (int a = 0; a < n; ++a) m(r, a) = src[r * n + a];
@@ -566,5 +575,100 @@ extern "C" int32_t sepaihrd_host_resave_parameters(const char* in_file, int32_t 
         std::vector<std::string> names;
         for (int32_t i = 0; i < n_calibrated; ++i) names.emplace_back(calibrated_names[i]);
         saveCalibrationResults(out_file ? out_file : "", p, names, obj_value, timestamp ? timestamp : "");
+    });
+}
+
+
+// ---- post-calibration analysis: essential metrics and NPI scenarios -------------------------------------------------
+namespace {
+
+void store_metrics(const EssentialMetrics& m, int n, int nk, double* scalars, double* age, double* kappa) {
+    if (scalars) {
+        const double v[SEPAIHRD_HOST_NUM_METRICS] = {m.R0, m.overall_IFR, m.overall_attack_rate, m.peak_hospital_occupancy, m.peak_ICU_occupancy,
+                                                     m.time_to_peak_hospital, m.time_to_peak_ICU, m.total_cumulative_deaths, m.max_Rt, m.min_Rt,
+                                                     m.final_Rt, m.seroprevalence_at_target_day};
+        std::copy(v, v + SEPAIHRD_HOST_NUM_METRICS, scalars);
+    }
+    if (age) {
+        const std::vector<double>* blocks[4] = {&m.age_specific_IFR, &m.age_specific_IHR, &m.age_specific_IICUR, &m.age_specific_attack_rate};
+        for (int b = 0; b < 4; ++b) std::copy(blocks[b]->begin(), blocks[b]->begin() + n, age + b * n);
+    }
+    if (kappa)
+        for (int k = 0; k < nk; ++k) {
+            const auto it = m.kappa_values.find("kappa_" + std::to_string(k + 1));
+            kappa[k] = (it != m.kappa_values.end()) ? it->second : std::nan("");
+        }
+}
+
+}  // namespace
+
+extern "C" int32_t sepaihrd_host_metrics(const sepaihrd_problem* pb, const double* times, int32_t K, const double* trajectory,
+                                         const double* initial_state, double* out_scalars, double* out_age, double* out_rt, double* out_sero) {
+    return guarded([&] {
+        if (!pb || !times || K <= 0 || !trajectory || !initial_state) throw InvalidParameterException("sepaihrd_host_metrics", "bad argument");
+        SEPAIHRDParameters p;
+        auto model = model_from_problem(pb, {}, &p);
+        const int n = pb->n_ages, W = SEPAIHRD_NUM_COMPARTMENTS * n;
+        SimulationResult sim;
+        sim.time_points.assign(times, times + K);
+        sim.num_age_classes = n;
+        sim.solution.resize(static_cast<size_t>(K));
+        for (int k = 0; k < K; ++k) sim.solution[static_cast<size_t>(k)].assign(trajectory + static_cast<size_t>(k) * W, trajectory + static_cast<size_t>(k + 1) * W);
+        const VectorXd x0 = VectorXd::FromPointer(initial_state, W);
+        const SEPAIHRDParameters params = model->getModelParameters();
+        MetricsCalculator mc;
+        store_metrics(mc.calculateEssentialMetrics(sim, model, params, x0, sim.time_points), n, 0, out_scalars, out_age, nullptr);
+        if (out_rt) { const auto rt = mc.calculateRtTrajectory(sim, model, sim.time_points); std::copy(rt.begin(), rt.end(), out_rt); }
+        if (out_sero) { const auto se = mc.calculateSeroprevalenceTrajectory(sim, params, sim.time_points); std::copy(se.begin(), se.end(), out_sero); }
+    });
+}
+
+extern "C" int32_t sepaihrd_host_model_scenarios(sepaihrd_host_model* m, const double* samples, int64_t S, int32_t burn_in, int32_t thinning,
+                                                 const double* initial_state, double* out_scalars, double* out_age, double* out_kappa,
+                                                 double* out_trajectories, const char* csv_path) {
+    return guarded([&] {
+        if (!m || !samples || S <= 0 || !initial_state) throw InvalidParameterException("sepaihrd_host_model_scenarios", "bad argument");
+        const auto P = static_cast<std::ptrdiff_t>(m->pm->getParameterCount());
+        const int n = m->model->getNumAgeClasses(), nk = m->model->numKappa(), W = m->model->getStateSize();
+        std::vector<VectorXd> smp;
+        for (int64_t i = 0; i < S; ++i) smp.push_back(VectorXd::FromPointer(samples + i * P, P));
+        PostCalibrationAnalyser analyser(m->model, std::make_shared<Dopri5SolverStrategy>(), m->times, VectorXd::FromPointer(initial_state, W),
+                                         m->abs_tol, m->rel_tol);
+        std::vector<SimulationResult> runs;
+        const auto results = analyser.scenarioAnalysisFromSamples(smp, *m->pm, burn_in, thinning, &runs);
+        for (size_t r = 0; r < results.size(); ++r) {
+            store_metrics(results[r].second, n, nk, out_scalars ? out_scalars + r * SEPAIHRD_HOST_NUM_METRICS : nullptr,
+                          out_age ? out_age + r * 4 * static_cast<size_t>(n) : nullptr, out_kappa ? out_kappa + r * static_cast<size_t>(nk) : nullptr);
+            if (out_trajectories)
+                for (size_t k = 0; k < runs[r].solution.size(); ++k)
+                    std::copy(runs[r].solution[k].begin(), runs[r].solution[k].end(), out_trajectories + (r * runs[r].solution.size() + k) * static_cast<size_t>(W));
+        }
+        if (csv_path && *csv_path) PostCalibrationAnalyser::writeScenarioComparison(csv_path, results);
+    });
+}
+
+extern "C" int32_t sepaihrd_host_model_analyze_runs(sepaihrd_host_model* m, const double* samples, int64_t S, int32_t burn_in, int32_t thinning,
+                                                    const double* initial_state, double* out_scalars, double* out_rt_quantiles,
+                                                    double* out_sero_quantiles, int64_t* out_runs) {
+    return guarded([&] {
+        if (!m || !samples || S <= 0 || !initial_state) throw InvalidParameterException("sepaihrd_host_model_analyze_runs", "bad argument");
+        const auto P = static_cast<std::ptrdiff_t>(m->pm->getParameterCount());
+        const int W = m->model->getStateSize();
+        std::vector<VectorXd> smp;
+        for (int64_t i = 0; i < S; ++i) smp.push_back(VectorXd::FromPointer(samples + i * P, P));
+        PostCalibrationAnalyser analyser(m->model, std::make_shared<Dopri5SolverStrategy>(), m->times, VectorXd::FromPointer(initial_state, W),
+                                         m->abs_tol, m->rel_tol);
+        const auto res = analyser.analyzeMCMCRuns(smp, *m->pm, burn_in, thinning);
+        if (out_runs) *out_runs = static_cast<int64_t>(res.metrics.size());
+        for (size_t r = 0; r < res.metrics.size(); ++r)
+            store_metrics(res.metrics[r], 0, 0, out_scalars ? out_scalars + r * SEPAIHRD_HOST_NUM_METRICS : nullptr, nullptr, nullptr);
+        auto put = [&](const AggregatedTrajectory& a, double* out) {
+            if (!out) return;
+            const size_t K = a.median.size();
+            const std::vector<double>* q[5] = {&a.q025, &a.q05, &a.median, &a.q95, &a.q975};
+            for (int j = 0; j < 5; ++j) std::copy(q[j]->begin(), q[j]->end(), out + static_cast<size_t>(j) * K);
+        };
+        put(res.rt, out_rt_quantiles);
+        put(res.seroprevalence, out_sero_quantiles);
     });
 }

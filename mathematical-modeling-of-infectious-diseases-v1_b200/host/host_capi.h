@@ -127,6 +127,29 @@ const char* sepaihrd_host_project_json(const char* project_root, const char* sta
 int32_t sepaihrd_host_resave_parameters(const char* in_file, int32_t n_ages, const char* out_file, int32_t n_calibrated,
                                         const char* const* calibrated_names, double obj_value, const char* timestamp);
 
+/* ---- post-calibration analysis (analysis.hpp: MetricsCalculator, ReproductionNumberCalculator, PostCalibrationAnalyser) *
+ * Scalar metrics of one run, in this order: R0, overall_IFR, overall_attack_rate, peak_hospital_occupancy,
+ * peak_ICU_occupancy, time_to_peak_hospital, time_to_peak_ICU, total_cumulative_deaths, max_Rt, min_Rt, final_Rt,
+ * seroprevalence_at_target_day.  Per-age metrics: [4][n] = IFR, IHR, IICUR, attack rate.                                */
+#define SEPAIHRD_HOST_NUM_METRICS 12
+/* MetricsCalculator on a GIVEN trajectory ([K][11 n]) of the model described by `problem` (its base slots): host arithmetic
+ * only, no device call.  out_rt / out_sero: [K] Rt and seroprevalence trajectories, or NULL.                            */
+int32_t sepaihrd_host_metrics(const sepaihrd_problem* problem, const double* times, int32_t K, const double* trajectory,
+                              const double* initial_state, double* out_scalars, double* out_age /* [4][n] or NULL */,
+                              double* out_rt, double* out_sero);
+/* PostCalibrationAnalyser, scenario step of generateFullReport: mean of the kept samples -> "baseline", "stricter_lockdown"
+ * (first calibratable kappa x 0.9), "weaker_lockdown" (x 1.1), integrated as ONE device batch from `initial_state`.
+ * out_scalars [3][12], out_age [3][4][n], out_kappa [3][n_kappa], out_trajectories [3][K][11 n] (each may be NULL);
+ * csv_path non-empty: scenario_comparison.csv in the reference's format.                                                */
+int32_t sepaihrd_host_model_scenarios(sepaihrd_host_model* m, const double* samples, int64_t S, int32_t burn_in, int32_t thinning,
+                                      const double* initial_state, double* out_scalars, double* out_age, double* out_kappa,
+                                      double* out_trajectories, const char* csv_path);
+/* analyzeMCMCRunsInBatches without the files: one run per kept sample (one device batch); out_scalars [runs][12];
+ * out_*_quantiles [5][K] in the order 0.025, 0.05, 0.5, 0.95, 0.975.                                                    */
+int32_t sepaihrd_host_model_analyze_runs(sepaihrd_host_model* m, const double* samples, int64_t S, int32_t burn_in, int32_t thinning,
+                                         const double* initial_state, double* out_scalars, double* out_rt_quantiles,
+                                         double* out_sero_quantiles, int64_t* out_runs);
+
 #ifdef __cplusplus
 }
 #endif

@@ -65,6 +65,9 @@ SIGNATURES = {
     "sepaihrd_host_model_calibrate": (C.c_int32, [_vp, C.c_char_p, C.c_int32, _keys, _vp, C.c_int32, _keys, _vp, _vp, _dp, _i64p]),
     "sepaihrd_host_model_posterior_predictive": (C.c_int32, [_vp, _vp, C.c_int64, C.c_int32, C.c_uint32, _vp, _vp, _i64p]),
     "sepaihrd_host_model_destroy": (None, [_vp]),
+    "sepaihrd_host_metrics": (C.c_int32, [_vp, _vp, C.c_int32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "sepaihrd_host_model_scenarios": (C.c_int32, [_vp, _vp, C.c_int64, C.c_int32, C.c_int32, _vp, _vp, _vp, _vp, _vp, C.c_char_p]),
+    "sepaihrd_host_model_analyze_runs": (C.c_int32, [_vp, _vp, C.c_int64, C.c_int32, C.c_int32, _vp, _vp, _vp, _vp, _i64p]),
     "sepaihrd_host_read_file_json": (C.c_char_p, [C.c_char_p, C.c_char_p, C.c_int32, C.c_int32, C.c_char_p, C.c_char_p]),
     "sepaihrd_host_project_json": (C.c_char_p, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int32]),
     "sepaihrd_host_resave_parameters": (C.c_int32, [C.c_char_p, C.c_int32, C.c_char_p, C.c_int32, _keys, C.c_double, C.c_char_p]),
@@ -285,6 +288,23 @@ def calibrate(phase1: str, pm: ParameterManager, settings1: Dict[str, float], se
     return best, val.value, ns.value, p1.value
 
 
+NUM_METRICS = 12
+METRIC_NAMES = ["R0", "overall_IFR", "overall_attack_rate", "peak_hospital_occupancy", "peak_ICU_occupancy", "time_to_peak_hospital",
+                "time_to_peak_ICU", "total_cumulative_deaths", "max_Rt", "min_Rt", "final_Rt", "seroprevalence_at_target_day"]
+
+
+def essential_metrics(problem, times, trajectory, initial_state, trajectories: bool = False):
+    """MetricsCalculator::calculateEssentialMetrics on a given trajectory [K, 11 n] of the problem's base model (host
+    arithmetic only).  Returns (scalars[12], age[4, n]) or, with trajectories=True, also (Rt[K], seroprevalence[K])."""
+    L = load_library()
+    cp = problem.as_c()
+    t = _c64(times); tr = _c64(trajectory); s0 = _c64(initial_state)
+    sc = np.empty(NUM_METRICS); age = np.empty((4, problem.n_ages)); rt = np.empty(len(t)); se = np.empty(len(t))
+    check(L.sepaihrd_host_metrics(C.addressof(cp), t.ctypes.data, len(t), tr.ctypes.data, s0.ctypes.data, sc.ctypes.data, age.ctypes.data,
+                                  rt.ctypes.data if trajectories else None, se.ctypes.data if trajectories else None))
+    return (sc, age, rt, se) if trajectories else (sc, age)
+
+
 class HostModel:
     """The reference-shaped C++ object graph (AgeSEPAIHRDModel, SEPAIHRDParameterManager, SEPAIHRDObjectiveFunction,
     AgeSEPAIHRDSimulator, SEPAIHRDModelCalibration) over the device evaluator.  Needs a CUDA device."""
@@ -342,6 +362,31 @@ class HostModel:
         check(self.L.sepaihrd_host_model_posterior_predictive(self._h, x.ctypes.data, x.shape[0], int(num_samples), int(seed), s0.ctypes.data,
                                                               out.ctypes.data, C.byref(used)))
         return out, used.value
+
+    def scenarios(self, samples, initial_state, burn_in: int = 0, thinning: int = 1, csv_path: str = "", trajectories: bool = False):
+        """PostCalibrationAnalyser scenario analysis (baseline / stricter_lockdown / weaker_lockdown) as one device batch.
+        Returns dict(names, scalars [3, 12], age [3, 4, n], kappa [3, nk][, trajectories [3, K, 11 n]])."""
+        x = _c64(samples); s0 = _c64(initial_state)
+        n, nk, K = self.problem.n_ages, len(self.problem.kappa_end_times), self.problem.n_times
+        sc = np.empty((3, NUM_METRICS)); age = np.empty((3, 4, n)); kap = np.empty((3, nk))
+        traj = np.empty((3, K, self.problem.state_size)) if trajectories else None
+        check(self.L.sepaihrd_host_model_scenarios(self._h, x.ctypes.data, x.shape[0], int(burn_in), int(thinning), s0.ctypes.data,
+                                                   sc.ctypes.data, age.ctypes.data, kap.ctypes.data,
+                                                   traj.ctypes.data if trajectories else None, os.fsencode(csv_path)))
+        out = dict(names=["baseline", "stricter_lockdown", "weaker_lockdown"], scalars=sc, age=age, kappa=kap)
+        if trajectories:
+            out["trajectories"] = traj
+        return out
+
+    def analyze_runs(self, samples, initial_state, burn_in: int = 0, thinning: int = 1):
+        """analyzeMCMCRunsInBatches without the files: metrics [runs, 12], Rt and seroprevalence quantiles [5, K]."""
+        x = _c64(samples); s0 = _c64(initial_state)
+        runs = len(range(int(burn_in), x.shape[0], max(int(thinning), 1)))
+        K = self.problem.n_times
+        sc = np.empty((max(runs, 1), NUM_METRICS)); rt = np.empty((5, K)); se = np.empty((5, K)); got = C.c_int64()
+        check(self.L.sepaihrd_host_model_analyze_runs(self._h, x.ctypes.data, x.shape[0], int(burn_in), int(thinning), s0.ctypes.data,
+                                                      sc.ctypes.data, rt.ctypes.data, se.ctypes.data, C.byref(got)))
+        return sc[:got.value], rt, se
 
     def close(self):
         if getattr(self, "_h", None):

@@ -137,3 +137,82 @@ def test_result_aggregator_mirror_matches_the_evaluator(host, problem, oracle, e
     sub2, _ = m.posterior_predictive(P, s0, num_samples=40, seed=99)
     np.testing.assert_array_equal(sub, sub2)
     m.close()
+
+
+def _slots_for(problem, vec):
+    s = np.array(problem.base_slots, dtype=float)
+    for i, sl in enumerate(problem.param_slot):
+        if sl >= 0:
+            s[sl] = vec[i]
+    return s
+
+
+def test_npi_scenario_analysis_matches_oracle(host, problem, orc, oracle, tmp_path):
+    """PostCalibrationAnalyser scenario step (BASELINE.json configs[4]): mean of the kept samples -> baseline, first calibratable
+    kappa x0.9 / x1.1, three runs as one device batch.  Trajectories against the CPU oracle (1e-6 gate, observed ~1e-13), metrics
+    against the numpy restatement; the scenario runs' metrics model keeps the BASELINE kappa schedule like the reference."""
+    from _metrics_ref import essential_metrics, unpack
+    d = problem.to_json()
+    d["base_slots"] = list(d["base_slots"]); d["base_slots"][problem.layout.beta_scalar] = None      # quirk Q1: no scalar beta
+    prob = problem.__class__.from_json(d)
+    samples = oracle.jitter_params(40, seed=33)
+    burn_in, thinning = 4, 3
+    mean = np.clip(samples[burn_in::thinning].sum(axis=0) / len(samples[burn_in::thinning]), prob.lower_bound, prob.upper_bound)
+    s0 = oracle.simulate_batch(problem.base_params()[None])[0][0][0]          # the run-up seeded state of calculate()
+    m = host.HostModel(prob)
+    csv = str(tmp_path / "scenario_comparison.csv")
+    out = m.scenarios(samples, s0, burn_in, thinning, csv_path=csv, trajectories=True)
+    k2 = prob.param_names.index("kappa_2")
+    vecs = np.stack([mean, mean, mean]); vecs[1, k2] *= 0.9; vecs[2, k2] *= 1.1
+    lay = prob.layout
+    np.testing.assert_allclose(out["kappa"][:, 1], vecs[:, k2], rtol=1e-15)
+    np.testing.assert_array_equal(out["kappa"][:, 0], [1.0, 1.0, 1.0])
+    # oracle reference with the kappa_2 bounds opened (the scenario values are set on the model directly, unconstrained)
+    wide = dict(prob.to_json()); wide["lower_bound"] = list(wide["lower_bound"]); wide["upper_bound"] = list(wide["upper_bound"])
+    wide["lower_bound"][k2] = 0.0; wide["upper_bound"][k2] = 10.0
+    ref, st = orc.Oracle(prob.__class__.from_json(wide)).simulate_from_state(vecs, s0)
+    assert (st == 0).all()
+    assert (np.abs(out["trajectories"] - ref) / np.maximum(np.abs(ref), 1.0)).max() < 1e-9
+    base_kappa = _slots_for(prob, mean)[lay.kappa0:lay.kappa0 + lay.nk]
+    for r in range(3):
+        q = unpack(prob, _slots_for(prob, vecs[r]))
+        sc, age, _, _ = essential_metrics(q, prob.times, out["trajectories"][r], s0, npi_kappa_values=base_kappa)
+        np.testing.assert_allclose(out["scalars"][r], sc, rtol=1e-10)
+        np.testing.assert_allclose(out["age"][r], age, rtol=1e-10)
+    names = host.METRIC_NAMES
+    deaths = out["scalars"][:, names.index("total_cumulative_deaths")]
+    assert deaths[1] < deaths[0] < deaths[2]                                  # stricter < baseline < weaker lockdown
+    lines = open(csv).read().strip().split("\n")
+    assert lines[0].startswith("scenario,R0,overall_IFR,overall_attack_rate,peak_hospital,peak_ICU,") and lines[0].endswith("kappa_7")
+    assert [ln.split(",")[0] for ln in lines[1:]] == ["baseline", "stricter_lockdown", "weaker_lockdown"]
+    m.close()
+
+
+def test_mcmc_run_analysis_matches_oracle(host, problem, oracle):
+    """analyzeMCMCRunsInBatches: one run per kept sample in one device batch, metrics per run, Rt / seroprevalence quantiles."""
+    from _metrics_ref import essential_metrics, unpack
+    samples = oracle.jitter_params(30, seed=35)
+    s0 = problem.data_initial_state
+    m = host.HostModel(problem)
+    sc, rt_q, se_q = m.analyze_runs(samples, s0, burn_in=5, thinning=4)
+    kept = samples[5::4]
+    assert sc.shape == (len(kept), 12)
+    ref, st = oracle.simulate_from_state(kept, s0)
+    rts, ses = [], []
+    for r, vec in enumerate(kept):
+        q = unpack(problem, _slots_for(problem, np.clip(vec, problem.lower_bound, problem.upper_bound)))
+        s, _, rt, se = essential_metrics(q, problem.times, ref[r], s0)
+        np.testing.assert_allclose(sc[r], s, rtol=1e-8)
+        rts.append(rt); ses.append(se)
+    probs = [0.025, 0.05, 0.5, 0.95, 0.975]
+
+    def quant(cols):
+        v = np.sort(np.array(cols), axis=0); n = len(v)
+        out = []
+        for p in probs:
+            pos = p * (n - 1); i = int(pos); f = pos - i
+            out.append(v[i] * (1 - f) + v[i + 1] * f if i + 1 < n else v[i])
+        return np.array(out)
+    np.testing.assert_allclose(rt_q, quant(rts), rtol=1e-8)
+    np.testing.assert_allclose(se_q, quant(ses), rtol=1e-8, atol=1e-16)
+    m.close()
