@@ -192,6 +192,33 @@ sepaihrd_rc sepaihrd_posterior_predictive(sepaihrd_ctx* ctx, const double* param
                                           const double* initial_state, int32_t n_probs, const double* probs,
                                           double* out_quantiles, int64_t* out_valid_draws);
 
+/* ---- device-resident particle swarm ---------------------------------------------------------------------------------
+ * Replaces the per-iteration host work of ParticleSwarmOptimization for swarms scored by this evaluator
+ * (src/model/optimizers/ParticleSwarmOptimizer.cpp: initializeSwarm :249-328, updateParticles :330-425, standardPSOUpdate
+ * :576-618, personal / global best :301-303, :417-421, :149-156).  Positions, velocities and personal bests stay in HBM;
+ * per iteration the caller supplies one 32-bit seed per particle of the WHOLE swarm (the reference draws them from its
+ * master std::mt19937, :365-371) and the global best position, and reads back the shard's best (value, index, position).
+ * The device runs std::mt19937 + std::uniform_real_distribution<double> and the update in unfused FP64, so the swarm
+ * visits exactly the positions the host implementation visits.  Bounds are the ctx's parameter bounds (all finite).
+ * This process owns particles [particle_offset, particle_offset + local_count) of a swarm of swarm_size.               */
+typedef struct sepaihrd_swarm sepaihrd_swarm;
+enum { SEPAIHRD_SWARM_POSITIONS = 0, SEPAIHRD_SWARM_VELOCITIES = 1, SEPAIHRD_SWARM_PERSONAL_BEST = 2,
+       SEPAIHRD_SWARM_PERSONAL_BEST_VALUES = 3, SEPAIHRD_SWARM_FITNESS = 4 };
+sepaihrd_rc sepaihrd_swarm_create(sepaihrd_ctx* ctx, int64_t swarm_size, int64_t particle_offset, int64_t local_count,
+                                  sepaihrd_swarm** out);
+void sepaihrd_swarm_destroy(sepaihrd_swarm* swarm);
+/* seeds [swarm_size]; initial (or NULL): global particle 0 starts at clamp(initial) instead of a uniform draw (:283-288) */
+sepaihrd_rc sepaihrd_swarm_init(sepaihrd_swarm* swarm, const uint32_t* seeds, const double* initial);
+/* One objective launch over the shard's positions, personal-best update, arg-max of the personal bests (first maximum
+ * wins).  out_best_local_index = -1 (and value -inf) for an empty shard.  out_best_position [P] may be NULL.            */
+sepaihrd_rc sepaihrd_swarm_evaluate(sepaihrd_swarm* swarm, double* out_best_value, int64_t* out_best_local_index,
+                                    double* out_best_position);
+/* Velocity / position update with inertia omega and acceleration coefficients c1, c2 towards global_best [P].          */
+sepaihrd_rc sepaihrd_swarm_step(sepaihrd_swarm* swarm, const uint32_t* seeds, double omega, double c1, double c2,
+                                const double* global_best);
+/* Copy one of the swarm's arrays to the host: [local][P] or [local] (SEPAIHRD_SWARM_*).                                */
+sepaihrd_rc sepaihrd_swarm_read(sepaihrd_swarm* swarm, int32_t what, double* out);
+
 /* Block until everything enqueued on the ctx stream has finished. */
 sepaihrd_rc sepaihrd_synchronize(sepaihrd_ctx* ctx);
 

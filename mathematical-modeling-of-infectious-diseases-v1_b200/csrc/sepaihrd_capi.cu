@@ -624,6 +624,9 @@ namespace sepaihrd_internal {
 Dims dims(const sepaihrd_ctx* ctx) { return Dims{ctx->n, ctx->K, ctx->runup_offset, ctx->n_nonneg, ctx->P, ctx->device}; }
 cudaStream_t stream(const sepaihrd_ctx* ctx) { return ctx->stream; }
 sepaihrd_rc fail_with(sepaihrd_rc rc, const char* msg) { return fail(rc, msg); }
+const double* lower_bounds(const sepaihrd_ctx* ctx) { return ctx->blob.data() + ctx->kp.o_lo; }
+const double* upper_bounds(const sepaihrd_ctx* ctx) { return ctx->blob.data() + ctx->kp.o_hi; }
+void count_launches(sepaihrd_ctx* ctx, int n) { ctx->launches += n; }
 sepaihrd_rc simulate_observed_draw_minor(sepaihrd_ctx* ctx, const double* d_params, long long B, long long ld, const double* d_init,
                                          double* d_out, unsigned* d_status) {
     return simulate_device_impl(ctx, d_params, B, ld, d_init, 0, SEPAIHRD_TRAJ_OBSERVED, 1, d_out, d_status, true);

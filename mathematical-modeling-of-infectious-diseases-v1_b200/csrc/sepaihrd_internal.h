@@ -11,6 +11,9 @@ struct Dims { int n, K, runup_offset, n_nonneg, P, device; };   // n_nonneg: out
 Dims dims(const sepaihrd_ctx* ctx);
 cudaStream_t stream(const sepaihrd_ctx* ctx);
 sepaihrd_rc fail_with(sepaihrd_rc rc, const char* msg);
+const double* lower_bounds(const sepaihrd_ctx* ctx);   // host copies, [P], as given at creation
+const double* upper_bounds(const sepaihrd_ctx* ctx);
+void count_launches(sepaihrd_ctx* ctx, int n);          // kernels another translation unit enqueued on the ctx stream
 // D, CumH, CumICU of B draws in the DRAW-MINOR layout [K][3n][B] (device pointers); d_init: one shared state or null
 sepaihrd_rc simulate_observed_draw_minor(sepaihrd_ctx* ctx, const double* d_params, long long B, long long ld, const double* d_init,
                                          double* d_out, unsigned* d_status);

@@ -82,10 +82,16 @@ def run_multichain_mh(evaluate: Evaluate, sigmas, lower, upper, initial, n_chain
 
 
 def run_pso(evaluate: Evaluate, sigmas, lower, upper, swarm_size: int, iterations: int, seed: int, initial=None,
-            comm: Optional[Comm] = None, settings: Optional[Dict[str, float]] = None):
+            comm: Optional[Comm] = None, settings: Optional[Dict[str, float]] = None, device_ctx=None):
     """Particle swarm with the global-best topology (ParticleSwarmOptimizer.cpp:106-247, 330-425, 576-618), particles
-    sharded over the ranks; per iteration one batch evaluation per rank, then the global-best reduction."""
+    sharded over the ranks; per iteration one batch evaluation per rank, then the global-best reduction.
+
+    device_ctx (BatchEvaluator.handle): keep this rank's shard in the HBM of that evaluator's GPU (sepaihrd_swarm_*):
+    per iteration one seed per particle goes down and one (value, index, position) triple comes back; `evaluate` is not
+    called.  The visited positions are identical to the host-resident run."""
     comm = comm or Comm()
+    if device_ctx is not None:
+        return _run_pso_device(device_ctx, sigmas, lower, upper, swarm_size, iterations, seed, initial, comm, settings)
     _host_threads(comm)
     lo, hi = shard_range(swarm_size, comm.rank, comm.world)
     pm = hostlib.ParameterManager(sigmas, lower, upper, mode=0)        # OPTIMIZATION_CLAMP (ModelCalibrator.cpp:62-66)
@@ -117,3 +123,37 @@ def run_pso(evaluate: Evaluate, sigmas, lower, upper, swarm_size: int, iteration
     val, pos = sw.global_best()
     return dict(rank=comm.rank, world=comm.world, particles=(lo, hi), best_value=val, best_position=pos, trace=np.array(trace),
                 eval_seconds=t_eval, comm_seconds=t_comm, evaluations=(iterations + 1) * (hi - lo))
+
+
+def _run_pso_device(device_ctx, sigmas, lower, upper, swarm_size, iterations, seed, initial, comm, settings):
+    _host_threads(comm)
+    lo, hi = shard_range(swarm_size, comm.rank, comm.world)
+    pm = hostlib.ParameterManager(sigmas, lower, upper, mode=0)
+    st = dict(iterations=iterations, swarm_size=swarm_size, seed=seed)
+    st.update(settings or {})
+    st["particle_offset"], st["local_count"] = lo, hi - lo
+    sw = hostlib.Swarm(pm, st)
+    sw.begin_device(device_ctx, initial)
+    t_eval = t_comm = 0.0
+    trace = []
+
+    def evaluate_and_reduce():
+        nonlocal t_eval, t_comm
+        t0 = time.perf_counter()
+        v, i, pos = sw.evaluate_device()
+        t1 = time.perf_counter()
+        gv, gi, gpos = comm.argmax_and_fetch(v, lo + i if i >= 0 else -1, pos)
+        sw.set_global_best(gv, gpos)
+        t2 = time.perf_counter()
+        t_eval += t1 - t0
+        t_comm += t2 - t1
+        trace.append(sw.global_best()[0])
+
+    evaluate_and_reduce()
+    for it in range(iterations):
+        sw.step_device(it)
+        evaluate_and_reduce()
+    val, pos = sw.global_best()
+    sw.fetch()
+    return dict(rank=comm.rank, world=comm.world, particles=(lo, hi), best_value=val, best_position=pos, trace=np.array(trace),
+                eval_seconds=t_eval, comm_seconds=t_comm, evaluations=(iterations + 1) * (hi - lo), final_positions=sw.positions())

@@ -58,6 +58,11 @@ class BatchEvaluator:
             pass
 
     # -- configuration ----------------------------------------------------------------------------
+    @property
+    def handle(self):
+        """The sepaihrd_ctx* (for C-ABI calls that take the context, e.g. the device-resident swarm)."""
+        return self._h
+
     def set_constraint_mode(self, mode: int):
         """SEPAIHRDParameterManager::setConstraintMode."""
         capi.check(self._lib.sepaihrd_set_constraint_mode(self._h, int(mode)))

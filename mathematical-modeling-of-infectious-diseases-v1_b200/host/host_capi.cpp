@@ -259,6 +259,25 @@ int32_t sepaihrd_host_pso_global_best(const sepaihrd_host_pso* pso, double* valu
     });
 }
 int32_t sepaihrd_host_pso_step(sepaihrd_host_pso* pso, int32_t iter) { return guarded([&] { pso->s.step(iter); }); }
+int32_t sepaihrd_host_pso_begin_device(sepaihrd_host_pso* pso, const double* init, sepaihrd_ctx* ctx) {
+    return guarded([&] {
+        if (init) {
+            const VectorXd v = VectorXd::FromPointer(init, static_cast<std::ptrdiff_t>(pso->pm->pm.getParameterCount()));
+            pso->s.beginDevice(&v, pso->pm->pm, ctx);
+        } else {
+            pso->s.beginDevice(nullptr, pso->pm->pm, ctx);
+        }
+    });
+}
+int32_t sepaihrd_host_pso_evaluate_device(sepaihrd_host_pso* pso, double* best_value, int32_t* best_local, double* best_pos) {
+    return guarded([&] {
+        const auto b = pso->s.evaluateDevice(best_pos);
+        if (best_value) *best_value = b.first;
+        if (best_local) *best_local = b.second;
+    });
+}
+int32_t sepaihrd_host_pso_step_device(sepaihrd_host_pso* pso, int32_t iter) { return guarded([&] { pso->s.stepDevice(iter); }); }
+int32_t sepaihrd_host_pso_fetch(sepaihrd_host_pso* pso) { return guarded([&] { pso->s.fetchPersonalBests(); }); }
 void sepaihrd_host_pso_destroy(sepaihrd_host_pso* pso) { delete pso; }
 
 // ---- whole runs against a callback --------------------------------------------------------------------------

@@ -72,6 +72,14 @@ int32_t sepaihrd_host_pso_tell(sepaihrd_host_pso* pso, const double* fitness, do
 int32_t sepaihrd_host_pso_set_global_best(sepaihrd_host_pso* pso, double value, const double* position);
 int32_t sepaihrd_host_pso_global_best(const sepaihrd_host_pso* pso, double* out_value, double* out_position);
 int32_t sepaihrd_host_pso_step(sepaihrd_host_pso* pso, int32_t iter);
+/* Device-resident form of the same swarm (sepaihrd_swarm_*): the shard's particles stay in HBM of `ctx`'s GPU; the same seeds
+ * and arithmetic, hence the same positions, as begin / tell / step.  evaluate_device = objective launch + tell.  fetch copies
+ * positions, velocities and personal bests back so that sepaihrd_host_pso_positions() can be read.                             */
+int32_t sepaihrd_host_pso_begin_device(sepaihrd_host_pso* pso, const double* initial /* [P] or NULL */, sepaihrd_ctx* ctx);
+int32_t sepaihrd_host_pso_evaluate_device(sepaihrd_host_pso* pso, double* out_best_value, int32_t* out_best_local_index,
+                                          double* out_best_position /* [P] or NULL */);
+int32_t sepaihrd_host_pso_step_device(sepaihrd_host_pso* pso, int32_t iter);
+int32_t sepaihrd_host_pso_fetch(sepaihrd_host_pso* pso);
 void    sepaihrd_host_pso_destroy(sepaihrd_host_pso* pso);
 
 /* ---- whole runs against a batch callback: "mh", "pso" or "hill" (IOptimizationAlgorithm::optimize) --------- */

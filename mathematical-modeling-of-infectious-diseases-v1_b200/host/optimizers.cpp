@@ -274,9 +274,14 @@ void ParticleSwarmOptimization::configure(const std::map<std::string, double>& s
     local_count_setting_ = static_cast<int>(setting(s, "local_count", -1.0));
     has_seed_ = s.count("seed") != 0;
     seed_ = static_cast<unsigned>(setting(s, "seed", 0.0));
+    device_resident_ = setting(s, "device_resident", 1.0) != 0.0;
 }
 
-void ParticleSwarmOptimization::begin(const VectorXd* init, IParameterManager& pm) {
+ParticleSwarmOptimization::~ParticleSwarmOptimization() {
+    if (dev_swarm_) sepaihrd_swarm_destroy(dev_swarm_);
+}
+
+void ParticleSwarmOptimization::setupRun(IParameterManager& pm) {
     n_ = static_cast<int>(pm.getParameterCount());
     local_ = local_count_setting_ >= 0 ? local_count_setting_ : swarm_size_ - static_cast<int>(particle_offset_);
     if (particle_offset_ < 0 || particle_offset_ + local_ > swarm_size_) throw std::invalid_argument("particle_offset/local_count outside the swarm");
@@ -289,9 +294,65 @@ void ParticleSwarmOptimization::begin(const VectorXd* init, IParameterManager& p
     gbest_.assign(static_cast<size_t>(n_), 0.0);
     gbest_value_ = -std::numeric_limits<double>::infinity();
     first_tell_ = true;
-    // one seed per particle of the WHOLE swarm from the master generator (.cpp:268-270): every shard draws them all
-    std::vector<unsigned> seeds(static_cast<size_t>(swarm_size_));
-    for (auto& sd : seeds) sd = static_cast<unsigned>(rng_());
+    if (dev_swarm_) { sepaihrd_swarm_destroy(dev_swarm_); dev_swarm_ = nullptr; }
+}
+
+// one seed per particle of the WHOLE swarm from the master generator (.cpp:268-270, :365-371): every shard draws them all
+std::vector<uint32_t> ParticleSwarmOptimization::drawSeeds() {
+    std::vector<uint32_t> seeds(static_cast<size_t>(swarm_size_));
+    for (auto& sd : seeds) sd = static_cast<uint32_t>(rng_());
+    return seeds;
+}
+
+void ParticleSwarmOptimization::coefficients(int iter, double& omega, double& c1, double& c2) const {
+    const double ratio = (iterations_ > 1) ? static_cast<double>(iter) / (iterations_ - 1) : 0.0;    // .cpp:352-357
+    omega = omega_start_ + (omega_end_ - omega_start_) * ratio;
+    c1 = c1_initial_ + (c1_final_ - c1_initial_) * ratio;
+    c2 = c2_initial_ + (c2_final_ - c2_initial_) * ratio;
+}
+
+void ParticleSwarmOptimization::beginDevice(const VectorXd* init, IParameterManager& pm, sepaihrd_ctx* ctx) {
+    if (!ctx) throw std::invalid_argument("beginDevice: null device context");
+    setupRun(pm);
+    if (sepaihrd_swarm_create(ctx, swarm_size_, particle_offset_, local_, &dev_swarm_) != SEPAIHRD_OK)
+        throw std::runtime_error(std::string("sepaihrd_swarm_create: ") + sepaihrd_last_error());
+    const std::vector<uint32_t> seeds = drawSeeds();
+    const bool use_init = init != nullptr && init->size() == n_;
+    if (sepaihrd_swarm_init(dev_swarm_, seeds.data(), use_init ? init->data() : nullptr) != SEPAIHRD_OK)
+        throw std::runtime_error(std::string("sepaihrd_swarm_init: ") + sepaihrd_last_error());
+}
+
+std::pair<double, int> ParticleSwarmOptimization::evaluateDevice(double* best_position) {
+    if (!dev_swarm_) throw std::logic_error("evaluateDevice before beginDevice");
+    double value = 0.0;
+    int64_t index = -1;
+    if (sepaihrd_swarm_evaluate(dev_swarm_, &value, &index, best_position) != SEPAIHRD_OK)
+        throw std::runtime_error(std::string("sepaihrd_swarm_evaluate: ") + sepaihrd_last_error());
+    first_tell_ = false;
+    return {value, static_cast<int>(index)};
+}
+
+void ParticleSwarmOptimization::stepDevice(int iter) {
+    if (!dev_swarm_) throw std::logic_error("stepDevice before beginDevice");
+    double omega, c1, c2;
+    coefficients(iter, omega, c1, c2);
+    const std::vector<uint32_t> seeds = drawSeeds();
+    if (sepaihrd_swarm_step(dev_swarm_, seeds.data(), omega, c1, c2, gbest_.data()) != SEPAIHRD_OK)
+        throw std::runtime_error(std::string("sepaihrd_swarm_step: ") + sepaihrd_last_error());
+}
+
+void ParticleSwarmOptimization::fetchPersonalBests() {
+    if (!dev_swarm_ || local_ == 0) return;
+    if (sepaihrd_swarm_read(dev_swarm_, SEPAIHRD_SWARM_PERSONAL_BEST, pbest_.data()) != SEPAIHRD_OK ||
+        sepaihrd_swarm_read(dev_swarm_, SEPAIHRD_SWARM_PERSONAL_BEST_VALUES, pbest_val_.data()) != SEPAIHRD_OK ||
+        sepaihrd_swarm_read(dev_swarm_, SEPAIHRD_SWARM_POSITIONS, pos_.data()) != SEPAIHRD_OK ||
+        sepaihrd_swarm_read(dev_swarm_, SEPAIHRD_SWARM_VELOCITIES, vel_.data()) != SEPAIHRD_OK)
+        throw std::runtime_error(std::string("sepaihrd_swarm_read: ") + sepaihrd_last_error());
+}
+
+void ParticleSwarmOptimization::begin(const VectorXd* init, IParameterManager& pm) {
+    setupRun(pm);
+    const std::vector<uint32_t> seeds = drawSeeds();
 #pragma omp parallel for schedule(static)
     for (int li = 0; li < local_; ++li) {
         const long gi = particle_offset_ + li;
@@ -335,12 +396,9 @@ void ParticleSwarmOptimization::setGlobalBest(double value, const double* positi
 }
 
 void ParticleSwarmOptimization::step(int iter) {
-    const double ratio = (iterations_ > 1) ? static_cast<double>(iter) / (iterations_ - 1) : 0.0;    // .cpp:352-357
-    const double omega = omega_start_ + (omega_end_ - omega_start_) * ratio;
-    const double c1 = c1_initial_ + (c1_final_ - c1_initial_) * ratio;
-    const double c2 = c2_initial_ + (c2_final_ - c2_initial_) * ratio;
-    std::vector<unsigned> seeds(static_cast<size_t>(swarm_size_));
-    for (auto& sd : seeds) sd = static_cast<unsigned>(rng_());
+    double omega, c1, c2;
+    coefficients(iter, omega, c1, c2);
+    const std::vector<uint32_t> seeds = drawSeeds();
 #pragma omp parallel for schedule(static)
     for (int li = 0; li < local_; ++li) {
         std::mt19937 local_rng(seeds[static_cast<size_t>(particle_offset_ + li)]);
@@ -385,17 +443,34 @@ MatrixXd ParticleSwarmOptimization::personalBestScatter(VectorXd& mean) const {
 
 OptimizationResult ParticleSwarmOptimization::optimize(const VectorXd& initial, IObjectiveFunction& f, IParameterManager& pm) {
     const int n = static_cast<int>(pm.getParameterCount());
-    begin(initial.size() == n ? &initial : nullptr, pm);
-    auto evaluate = [&]() {
-        std::vector<double> fit(static_cast<size_t>(local_));
-        f.calculateBatch(pos_.data(), local_, n_, fit.data());         // the reference does not sanitise PSO fitness (.cpp:412)
-        const auto best = tell(fit.data());
-        if (best.second >= 0) setGlobalBest(best.first, personalBest(best.second));
-    };
-    evaluate();
-    for (int iter = 0; iter < iterations_; ++iter) {
-        step(iter);
+    auto* device_objective = dynamic_cast<SEPAIHRDObjectiveFunction*>(&f);
+    if (device_objective != nullptr && device_resident_) {
+        // the swarm stays in HBM: per iteration one seed per particle goes down, one (value, index, position) triple comes back
+        beginDevice(initial.size() == n ? &initial : nullptr, pm, device_objective->device().get());
+        std::vector<double> best_pos(static_cast<size_t>(n));
+        auto evaluate = [&]() {
+            const auto best = evaluateDevice(best_pos.data());
+            if (best.second >= 0) setGlobalBest(best.first, best_pos.data());
+        };
         evaluate();
+        for (int iter = 0; iter < iterations_; ++iter) {
+            stepDevice(iter);
+            evaluate();
+        }
+        fetchPersonalBests();
+    } else {
+        begin(initial.size() == n ? &initial : nullptr, pm);
+        auto evaluate = [&]() {
+            std::vector<double> fit(static_cast<size_t>(local_));
+            f.calculateBatch(pos_.data(), local_, n_, fit.data());         // the reference does not sanitise PSO fitness (.cpp:412)
+            const auto best = tell(fit.data());
+            if (best.second >= 0) setGlobalBest(best.first, personalBest(best.second));
+        };
+        evaluate();
+        for (int iter = 0; iter < iterations_; ++iter) {
+            step(iter);
+            evaluate();
+        }
     }
     OptimizationResult r;
     r.bestParameters = VectorXd::FromPointer(gbest_.data(), n_);

@@ -113,6 +113,21 @@ public:
     void step(int iter);
     MatrixXd personalBestScatter(VectorXd& mean_out) const;               // sum of (pbest - mean)(pbest - mean)^T pieces for the covariance hand-off
 
+    // ---- device-resident form (sepaihrd_swarm_*, csrc/sepaihrd_swarm.cu): the shard's particles live in HBM ----------
+    // Same seeds, same generator, same unfused arithmetic as begin()/tell()/step(): the swarm visits exactly the same
+    // positions, but an iteration moves one seed per particle and the global best instead of the whole swarm.
+    // optimize() takes this path by itself when the objective is a SEPAIHRDObjectiveFunction (setting
+    // "device_resident", default 1).  `ctx` must have been created with the parameter manager's bounds.
+    void beginDevice(const VectorXd* initialParameters, IParameterManager& pm, sepaihrd_ctx* ctx);
+    std::pair<double, int> evaluateDevice(double* best_position /* [P] or null */);   // objective launch + tell on the device
+    void stepDevice(int iter);
+    void fetchPersonalBests();                                            // device -> pbest_ / pbest_val_ / pos_ (for the covariance hand-off)
+    bool onDevice() const { return dev_swarm_ != nullptr; }
+    ~ParticleSwarmOptimization() override;
+    ParticleSwarmOptimization() = default;
+    ParticleSwarmOptimization(const ParticleSwarmOptimization&) = delete;
+    ParticleSwarmOptimization& operator=(const ParticleSwarmOptimization&) = delete;
+
 private:
     int iterations_ = 100, swarm_size_ = 30, report_interval_ = 10;
     double omega_start_ = 0.9, omega_end_ = 0.4, c1_initial_ = 2.5, c1_final_ = 0.5, c2_initial_ = 0.5, c2_final_ = 2.5;
@@ -126,6 +141,11 @@ private:
     std::vector<double> lb_, ub_, pos_, vel_, pbest_, pbest_val_, gbest_;
     double gbest_value_ = -std::numeric_limits<double>::infinity();
     bool first_tell_ = true;
+    bool device_resident_ = true;
+    sepaihrd_swarm* dev_swarm_ = nullptr;
+    void setupRun(IParameterManager& pm);
+    std::vector<uint32_t> drawSeeds();
+    void coefficients(int iter, double& omega, double& c1, double& c2) const;
 };
 
 // HillClimbingOptimizer   src/sir_age_structured/optimizers/HillClimbingOptimizer.cpp:131-352: a candidate cloud per

@@ -52,6 +52,10 @@ SIGNATURES = {
     "sepaihrd_host_pso_set_global_best": (C.c_int32, [_vp, C.c_double, _vp]),
     "sepaihrd_host_pso_global_best": (C.c_int32, [_vp, _dp, _vp]),
     "sepaihrd_host_pso_step": (C.c_int32, [_vp, C.c_int32]),
+    "sepaihrd_host_pso_begin_device": (C.c_int32, [_vp, _vp, _vp]),
+    "sepaihrd_host_pso_evaluate_device": (C.c_int32, [_vp, _dp, _i32p, _vp]),
+    "sepaihrd_host_pso_step_device": (C.c_int32, [_vp, C.c_int32]),
+    "sepaihrd_host_pso_fetch": (C.c_int32, [_vp]),
     "sepaihrd_host_pso_destroy": (None, [_vp]),
     "sepaihrd_host_optimize": (C.c_int32, [C.c_char_p, _vp, C.c_int32, _keys, _vp, BATCH_FN, _vp, _vp, _vp, _dp, _i64p]),
     "sepaihrd_host_calibrate": (C.c_int32, [C.c_char_p, _vp, C.c_int32, _keys, _vp, C.c_int32, _keys, _vp, BATCH_FN, _vp, _vp, _vp, _dp, _i64p, _dp]),
@@ -232,6 +236,26 @@ class Swarm:
 
     def step(self, it: int):
         check(self.L.sepaihrd_host_pso_step(self._h, int(it)))
+
+    # ---- device-resident form: the shard lives in the HBM of the evaluator's GPU (csrc/sepaihrd_swarm.cu) --------
+    def begin_device(self, ctx_handle, initial=None):
+        """ctx_handle: the sepaihrd_ctx* of the evaluator that scores the particles (BatchEvaluator.handle)."""
+        x = None if initial is None else _c64(initial)
+        check(self.L.sepaihrd_host_pso_begin_device(self._h, None if x is None else x.ctypes.data, ctx_handle))
+        self.local = int(self.L.sepaihrd_host_pso_local_count(self._h))
+
+    def evaluate_device(self):
+        """Objective launch over the shard + personal-best update + arg-max: (best value, local index, position)."""
+        v = C.c_double(); i = C.c_int32(); pos = np.empty(self.pm.n)
+        check(self.L.sepaihrd_host_pso_evaluate_device(self._h, C.byref(v), C.byref(i), pos.ctypes.data))
+        return v.value, i.value, pos
+
+    def step_device(self, it: int):
+        check(self.L.sepaihrd_host_pso_step_device(self._h, int(it)))
+
+    def fetch(self):
+        """Copy positions / velocities / personal bests back from the device (positions() is then current)."""
+        check(self.L.sepaihrd_host_pso_fetch(self._h))
 
     def __del__(self):
         if getattr(self, "_h", None):

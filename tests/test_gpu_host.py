@@ -216,3 +216,62 @@ def test_mcmc_run_analysis_matches_oracle(host, problem, oracle):
     np.testing.assert_allclose(rt_q, quant(rts), rtol=1e-8)
     np.testing.assert_allclose(se_q, quant(ses), rtol=1e-8, atol=1e-16)
     m.close()
+
+
+def test_device_resident_swarm_visits_the_host_swarms_positions(host, problem, ev_mod):
+    """sepaihrd_swarm_* (csrc/sepaihrd_swarm.cu): std::mt19937 + uniform_real_distribution and the unfused PSO update on the
+    device reproduce the host implementation bit for bit -- same positions, same global-best trace."""
+    from sepaihrd_b200 import drivers
+    kw = dict(sigmas=problem.sigmas, lower=problem.lower_bound, upper=problem.upper_bound, swarm_size=333, iterations=5, seed=7,
+              initial=problem.base_params())
+    with ev_mod.BatchEvaluator(problem, device=0) as ev:
+        ref = drivers.run_pso(ev.eval_batch, **kw)
+        launches0 = ev.counters()[0]
+        got = drivers.run_pso(None, device_ctx=ev.handle, **kw)
+        launches = ev.counters()[0] - launches0
+    np.testing.assert_array_equal(got["trace"], ref["trace"])
+    np.testing.assert_array_equal(got["best_position"], ref["best_position"])
+    assert got["best_value"] == ref["best_value"] and got["trace"][-1] >= got["trace"][0]
+    assert launches == 1 + 6 * 3 + 5          # init, (objective + tell + best) per evaluation, one update per iteration
+    # without a starting point every particle is drawn; no-seed runs differ
+    kw2 = dict(kw, initial=None, iterations=2)
+    with ev_mod.BatchEvaluator(problem, device=0) as ev:
+        a = drivers.run_pso(ev.eval_batch, **kw2)
+        b = drivers.run_pso(None, device_ctx=ev.handle, **kw2)
+    np.testing.assert_array_equal(a["trace"], b["trace"])
+
+
+def test_device_resident_swarm_shard_matches_host_shard(host, problem, ev_mod):
+    """A shard (particle_offset, local_count) of a larger swarm: initial draw, one evaluation, one update towards a given
+    global best -- positions identical to the host shard's."""
+    pm = host.ParameterManager(problem.sigmas, problem.lower_bound, problem.upper_bound, mode=0)
+    st = dict(iterations=9, swarm_size=500, seed=11, particle_offset=137, local_count=91)
+    h = host.Swarm(pm, st); d = host.Swarm(pm, st)
+    with ev_mod.BatchEvaluator(problem, device=0) as ev:
+        h.begin(problem.base_params()); d.begin_device(ev.handle, problem.base_params())
+        d.fetch()
+        x0 = h.positions()
+        np.testing.assert_array_equal(d.positions(), x0)
+        assert ((x0 >= problem.lower_bound) & (x0 <= problem.upper_bound)).all() and len(np.unique(x0[:, 0])) == 91
+        fit = ev.eval_batch(x0)[0]
+        v, i, pos = h.tell(fit)
+        dv, di, dpos = d.evaluate_device()
+        assert (dv, di) == (v, i)
+        np.testing.assert_array_equal(dpos, pos)
+        g = np.clip(pos + 0.5 * problem.sigmas, problem.lower_bound, problem.upper_bound)
+        h.set_global_best(v + 1.0, g); d.set_global_best(v + 1.0, g)
+        for it in (0, 1):
+            h.step(it); d.step_device(it)
+            d.fetch()
+            np.testing.assert_array_equal(d.positions(), h.positions())
+            v, i, pos = h.tell(ev.eval_batch(h.positions())[0])
+            dv, di, dpos = d.evaluate_device()
+            assert (dv, di) == (v, i)
+            np.testing.assert_array_equal(dpos, pos)
+    # an empty shard and a shard outside the swarm
+    with ev_mod.BatchEvaluator(problem, device=0) as ev:
+        e = host.Swarm(pm, dict(st, particle_offset=500, local_count=0))
+        e.begin_device(ev.handle)
+        assert e.evaluate_device()[1] == -1
+        with pytest.raises(host.HostError):
+            host.Swarm(pm, dict(st, particle_offset=450, local_count=91)).begin_device(ev.handle)

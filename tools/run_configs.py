@@ -19,6 +19,7 @@ ap.add_argument("--particles", type=int, default=65536)
 ap.add_argument("--iterations", type=int, default=30)
 ap.add_argument("--draws", type=int, default=100000)
 ap.add_argument("--chunk", type=int, default=8192)
+ap.add_argument("--host-swarm", action="store_true", help="pso: keep the swarm on the host (the pre-device-resident path)")
 a = ap.parse_args()
 pkg = g.load_package(); orc = g.load_oracle()
 from sepaihrd_b200 import drivers
@@ -48,9 +49,9 @@ elif a.what == "pso":
         ev.eval_batch(np.tile(p.base_params(), (64, 1)))
         comm.barrier(); t0 = time.perf_counter()
         r = drivers.run_pso(ev.eval_batch, p.sigmas, p.lower_bound, p.upper_bound, a.particles, a.iterations, seed=7,
-                            initial=p.base_params(), comm=comm)
+                            initial=p.base_params(), comm=comm, device_ctx=None if a.host_swarm else ev.handle)
         comm.barrier(); dt = time.perf_counter() - t0
-    out.update(particles=a.particles, iterations=a.iterations, seconds=dt, evals_per_s=a.particles * (a.iterations + 1) / dt,
+    out.update(swarm="host" if a.host_swarm else "device", particles=a.particles, iterations=a.iterations, seconds=dt, evals_per_s=a.particles * (a.iterations + 1) / dt,
                eval_seconds=r["eval_seconds"], comm_seconds=r["comm_seconds"], best_first=float(r["trace"][0]), best_last=float(r["trace"][-1]))
 elif a.what == "ppcq":
     # posterior-predictive QUANTILES (ResultAggregator): draws -> trajectories -> series -> sort -> quantiles, one C-ABI call
