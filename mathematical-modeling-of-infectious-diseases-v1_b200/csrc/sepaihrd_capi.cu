@@ -62,6 +62,7 @@ struct sepaihrd_ctx {
     int constraint_mode = 0, math_mode = SEPAIHRD_MATH_FAST;
     bool obs_mismatch = false;
     double abs_tol = 1e-6, rel_tol = 1e-6, dt_hint = 1.0, hmax = 1.0;
+    bool bp_on_grid = false;       // no schedule breakpoint strictly inside an output interval
     std::vector<double> blob;   // host image
     sepaihrd::KParams kp{};     // offsets etc. (I/O fields filled per call)
     double* d_blob = nullptr;
@@ -93,7 +94,7 @@ sepaihrd_rc grow(T** ptr, size_t* cap, size_t need) {
 
 struct LaunchCfg { int threads, minblocks; };
 
-template <int NA, bool STRICT, int MODE, int THREADS, int MINBLOCKS, int LOOP>
+template <int NA, bool STRICT, int MODE, int THREADS, int MINBLOCKS, int LOOP, bool ONGRID = false>
 sepaihrd_rc launch_t(sepaihrd_ctx* ctx, const sepaihrd::KParams& kp_in) {
     using namespace sepaihrd;
     KParams kp = kp_in;
@@ -103,7 +104,7 @@ sepaihrd_rc launch_t(sepaihrd_ctx* ctx, const sepaihrd::KParams& kp_in) {
     if (kp.tiles > 0xffff0000LL) return fail(SEPAIHRD_ERR_UNSUPPORTED, "batch too large for one launch");
     kp.tile_counter = ctx->d_tile_counter;
     CUDA_TRY(cudaMemsetAsync(ctx->d_tile_counter, 0, sizeof(unsigned), ctx->stream));
-    auto kern = sepaihrd_batch_kernel<NA, STRICT, MODE, THREADS, MINBLOCKS, LOOP>;
+    auto kern = sepaihrd_batch_kernel<NA, STRICT, MODE, THREADS, MINBLOCKS, LOOP, ONGRID>;
     const size_t smem = (size_t)kp.blob_bytes + sizeof(double) * (SETS * (size_t)(kp.slot_stride + ((kp.seg_stride + 1) & ~1)) + 2 * THREADS + (size_t)NA * THREADS) + 16;
     static bool attr_set[64] = {};   // per device
     if (!attr_set[ctx->device & 63]) {
@@ -130,6 +131,11 @@ sepaihrd_rc launch_na(sepaihrd_ctx* ctx, const sepaihrd::KParams& kp, int mode) 
     if (strict)   // STRICT keeps the reference-order loop
         return (mode == MODE_LL) ? launch_t<NA, true, MODE_LL, THREADS, MINBLOCKS, 5>(ctx, kp)
                                  : launch_t<NA, true, MODE_TRAJ, THREADS, MINBLOCKS, 5>(ctx, kp);
+#ifndef SEPAIHRD_EXP_NO_ONGRID
+    if (ctx->bp_on_grid)   // breakpoints on output-grid points (e.g. Spain 2020): the build without the mixed-segment attempt body
+        return (mode == MODE_LL) ? launch_t<NA, false, MODE_LL, THREADS, MINBLOCKS, 6, true>(ctx, kp)
+                                 : launch_t<NA, false, MODE_TRAJ, THREADS, MINBLOCKS, 6, true>(ctx, kp);
+#endif
     return (mode == MODE_LL) ? launch_t<NA, false, MODE_LL, THREADS, MINBLOCKS, 6>(ctx, kp)
                              : launch_t<NA, false, MODE_TRAJ, THREADS, MINBLOCKS, 6>(ctx, kp);
 }
@@ -267,6 +273,12 @@ sepaihrd_rc sepaihrd_create(const sepaihrd_problem* pb, int32_t device, sepaihrd
     const int nseg = (int)bp.size();
     if (nseg > SEPAIHRD_MAX_SEGMENTS) { delete ctx; return fail(SEPAIHRD_ERR_UNSUPPORTED, "too many schedule breakpoints"); }
     ctx->nseg = nseg;
+    // a breakpoint strictly inside an output interval can split the stages of a step over two segments; one on a grid
+    // point (or outside the window) cannot, because no step crosses a grid point
+    ctx->bp_on_grid = true;
+    for (double b : bp)
+        for (int i = 0; i + 1 < K; ++i)
+            if (b > pb->times[i] && b < pb->times[i + 1]) ctx->bp_on_grid = false;
     std::vector<int> segb(nseg + 1), segk(nseg + 1);
     for (int s = 0; s <= nseg; ++s) {
         const double tr = (s < nseg) ? bp[s] : bp[nseg - 1] + 1.0;

@@ -482,7 +482,10 @@ __device__ __forceinline__ void dopri5_attempt(const LaneParams<NA>& q, const St
 // groups that have already reached the next output time run the attempt with a zero-length step and
 // discard it), so every shuffle is a plain full-mask SHFL.  This is the "regroup at output-day
 // boundaries" policy: a warp spends max-over-its-groups attempts per output interval.
-template <int NA, bool STRICT, int MODE, int THREADS, int MINBLOCKS, int LOOP>
+// ONGRID (FAST only): every schedule breakpoint inside the integration window sits on an output-grid point, so no step can
+// have its stages in two segments and the mixed-segment attempt body is not instantiated (668 SASS instructions less to
+// keep in the instruction cache).  The host decides per problem (sepaihrd_create).
+template <int NA, bool STRICT, int MODE, int THREADS, int MINBLOCKS, int LOOP, bool ONGRID = false>
 __global__ void __launch_bounds__(THREADS, MINBLOCKS) sepaihrd_batch_kernel(const KParams kp) {
     static_assert(STRICT ? LOOP == 5 : LOOP == 6, "STRICT keeps the reference-order loop 5; FAST runs loop 6");
     using O = Ops<STRICT>;
@@ -749,7 +752,7 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) sepaihrd_batch_kernel(cons
                             sc.ba_step = my_beff[s_lo] * q.a;
                             if (s_lo != mseg) refold(s_lo);   // stages 2..7 of a step that starts ON a breakpoint (quirk Q2)
                         }
-                        run_mixed = __any_sync(FULL, mixed);
+                        if (!ONGRID) run_mixed = __any_sync(FULL, mixed);
                     }
                 }
                 double xn[NDYN], k7d[NDYN], k7p[NPAS], accN[NPAS], xe[NCOMP];
@@ -759,7 +762,7 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) sepaihrd_batch_kernel(cons
                 first_of_day = false;
                 if (unit)
                     dopri5_attempt<NA, false, false, true>(q, sc, spi, pi_slot, THREADS, threadIdx.x, t, cur, t_end, x, k1, xn, k7d, k7p, accN, xe, ecur, kp.hc);
-                else if (run_mixed)
+                else if (!ONGRID && run_mixed)
                     dopri5_attempt<NA, false, true>(q, sc, spi, pi_slot, THREADS, threadIdx.x, t, cur, t_end, x, k1, xn, k7d, k7p, accN, xe, ecur);
                 else
                     dopri5_attempt<NA, false, false>(q, sc, spi, pi_slot, THREADS, threadIdx.x, t, cur, t_end, x, k1, xn, k7d, k7p, accN, xe, ecur);
