@@ -274,3 +274,68 @@ def problem_from_reference_tree(root: str, start_date: str = "2020-03-01", end_d
         upper_bound=[bounds[nm][1] for nm in names], sigmas=[sigmas[nm] for nm in names],
         meta=dict(source="adjo0043/Mathematical-Modeling-Of-Infectious-Diseases-V1 data/ tree",
                   window=[start_date, end_date], dates=[data.dates[0], data.dates[-1]]))
+
+
+def write_reference_tree(problem: Problem, root: str, start_date: str = "2020-03-01") -> None:
+    """Write ``problem`` as a reference-style project tree (data/processed/processed_data.csv, data/contacts.csv,
+    data/configuration/{initial_guess,params_to_calibrate,param_bounds,proposal_sigmas}.txt) that the readers above --
+    and the C++ ones of host/config_io.hpp, e.g. through host/sepaihrd_objective_benchmark -- load back into the same
+    problem.  Numbers are written with 17 significant digits, so the round trip is exact for everything the hot path
+    reads; the cumulative columns of the first day are chosen such that the data-derived initial state is reproduced
+    (to rounding), later cumulative rows are running sums.  4 age classes (the CSV format has 4 fixed bands)."""
+    if problem.n_ages != 4:
+        raise ValueError("the reference's data format has 4 fixed age bands")
+    n, lay = 4, problem.layout
+    os.makedirs(os.path.join(root, "data", "processed"), exist_ok=True)
+    os.makedirs(os.path.join(root, "data", "configuration"), exist_ok=True)
+    r = lambda v: repr(float(v))
+    st = problem.data_initial_state.reshape(NUM_COMPARTMENTS, n)
+    cum = dict(cumulative_deceased=st[8].copy(), cumulative_hospitalized_patients=st[9].copy(),
+               cumulative_intensive_care_patients=st[10].copy(), cumulative_confirmed=st[4] + st[8])
+    new = dict(new_confirmed=np.zeros((problem.n_obs, n)), new_deceased=problem.obs_deaths,
+               new_hospitalized_patients=problem.obs_hosp, new_intensive_care_patients=problem.obs_icu)
+    series = list(new) + list(cum) + ["population"]
+    header = ["date"] + [f"{s}_{b}" for s in series for b in _AGE_SUFFIXES]
+    day0 = np.datetime64(start_date)
+    with open(os.path.join(root, "data", "processed", "processed_data.csv"), "w") as f:
+        f.write(",".join(header) + "\n")
+        for d in range(problem.n_obs):
+            if d > 0:
+                for s in cum:
+                    cum[s] = cum[s] + np.nan_to_num(np.maximum(new["new" + s[len("cumulative"):]][d], 0.0))
+            cells = [str(day0 + d)]
+            for s in series:
+                row = problem.population if s == "population" else (new[s][d] if s in new else cum[s])
+                cells += [r(v) if np.isfinite(v) else "-1.0" for v in row]
+            f.write(",".join(cells) + "\n")
+    with open(os.path.join(root, "data", "contacts.csv"), "w") as f:
+        f.write("// contact matrix M(i, j), row i = contacted age class\n")
+        for i in range(n):
+            f.write(",".join(r(v) for v in problem.contact_matrix[i]) + "\n")
+    s = problem.base_slots
+    with open(os.path.join(root, "data", "configuration", "initial_guess.txt"), "w") as f:
+        f.write("# written by sepaihrd_b200.config.write_reference_tree\n")
+        f.write("beta_end_times " + " ".join(r(v) for v in problem.beta_end_times) + "\n")
+        for k in range(lay.nb):
+            f.write(f"beta_{k + 1} {r(s[lay.beta0 + k])}\n")
+        if np.isfinite(s[lay.beta_scalar]):
+            f.write(f"beta {r(s[lay.beta_scalar])}\n")
+        for nm in _SCALARS:
+            f.write(f"{nm} {r(s[lay.scalar(nm)])}\n")
+        for blk in _AGE_BLOCKS:
+            f.write(blk + " " + " ".join(r(v) for v in s[lay.age(blk, 0):lay.age(blk, 0) + n]) + "\n")
+        for m, nm in enumerate(_MULTIPLIERS):
+            f.write(f"{nm} {r(s[lay.mult0 + m])}\n")
+        f.write(f"runup_days {r(s[lay.runup_days])}\nseed_exposed {r(s[lay.seed_exposed])}\n")
+        f.write("kappa_end_times " + " ".join(r(v) for v in problem.kappa_end_times) + "\n")
+        for k in range(lay.nk):
+            f.write(f"kappa_{k + 1} {r(s[lay.kappa0 + k])}\n")
+    cfg = os.path.join(root, "data", "configuration")
+    with open(os.path.join(cfg, "params_to_calibrate.txt"), "w") as f:
+        f.write("\n".join(problem.param_names) + "\n")
+    with open(os.path.join(cfg, "param_bounds.txt"), "w") as f:
+        for nm, lo, hi in zip(problem.param_names, problem.lower_bound, problem.upper_bound):
+            f.write(f"{nm} {r(lo)} {r(hi)}\n")
+    with open(os.path.join(cfg, "proposal_sigmas.txt"), "w") as f:
+        for nm, sg in zip(problem.param_names, problem.sigmas):
+            f.write(f"{nm} {r(sg)}\n")

@@ -319,3 +319,18 @@ def test_reference_tree_reproduces_the_committed_problem(host, problem):
     both = ~(np.isnan(g) | np.isnan(w))
     assert both.sum() >= len(g) - 1 and (g[both] == w[both]).all()
     assert len(got["times"]) == 326 and got["times"][0] == -20.0 and got["times"][-1] == 305.0
+
+
+def test_written_tree_round_trips_through_both_readers(tmp_path, host, cfg, problem):
+    """config.write_reference_tree -> the Python readers and the C++ readers give back the committed Spain-2020 problem
+    exactly (this is the tree host/sepaihrd_objective_benchmark is run on where the reference tree is absent)."""
+    cfg.write_reference_tree(problem, str(tmp_path))
+    py = cfg.problem_from_reference_tree(str(tmp_path)).to_json()
+    cc = host.load_reference_project(str(tmp_path))
+    want = problem.to_json()
+    assert py["param_names"] == cc["param_names"] == want["param_names"]
+    for key in ("times", "obs_hosp", "obs_icu", "obs_deaths", "population", "contact_matrix_rowmajor", "beta_end_times",
+                "kappa_end_times", "data_initial_state", "lower_bound", "upper_bound", "sigmas"):
+        assert py[key] == want[key], key
+        assert cc[key] == want[key], key
+    assert py["base_slots"] == want["base_slots"] and cc["base_slots"] == want["base_slots"]

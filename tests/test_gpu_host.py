@@ -275,3 +275,32 @@ def test_device_resident_swarm_shard_matches_host_shard(host, problem, ev_mod):
         assert e.evaluate_device()[1] == -1
         with pytest.raises(host.HostError):
             host.Swarm(pm, dict(st, particle_offset=450, local_count=91)).begin_device(ev.handle)
+
+
+def test_objective_benchmark_harness_runs_from_a_project_tree(host, problem, oracle, tmp_path):
+    """host/sepaihrd_objective_benchmark (the reference's timing harness, C++ end to end: tree -> readers -> mirrored objects
+    -> device batches): warm-up value and the sum over the harness's own jittered sets against the oracle."""
+    import json, os, subprocess
+    from sepaihrd_b200 import config
+    config.write_reference_tree(problem, str(tmp_path))
+    exe = os.path.join(os.path.dirname(host.LIB_PATH), "sepaihrd_objective_benchmark")
+    assert os.path.exists(exe), "run `python __graft_entry__.py` (make -C host builds the harness)"
+    run = subprocess.run([exe, "--project-root", str(tmp_path), "--repeats", "16", "--jitters", "512", "--seed", "1", "--json"],
+                         capture_output=True, text=True, timeout=300)
+    assert run.returncode == 0, run.stderr
+    rep = json.loads(next(ln for ln in run.stdout.splitlines() if ln.startswith("JSON "))[5:])
+    base_ll = oracle.eval_batch(problem.base_params()[None])[0][0]
+    jit = oracle.eval_batch(oracle.jitter_params(512, seed=1))[0]
+    assert _rel(rep["warmup_value"], base_ll) < 1e-8
+    assert _rel(rep["repeat_sum"], 16 * base_ll) < 1e-8
+    assert _rel(rep["jitter_sum"], jit.sum()) < 1e-8
+    assert "Jitter: 512 evals" in run.stdout and "Objective calls: 529" in run.stdout
+    # the batched callers through the same binary: seeded multi-chain MCMC and the device-resident swarm improve on the start
+    run = subprocess.run([exe, "--project-root", str(tmp_path), "--mode", "all", "--repeats", "0", "--jitters", "0", "--hill-iters", "3",
+                          "--mcmc-iters", "12", "--chains", "64", "--pso-iters", "4", "--swarm", "256", "--json"],
+                         capture_output=True, text=True, timeout=600)
+    assert run.returncode == 0, run.stderr
+    rep = json.loads(next(ln for ln in run.stdout.splitlines() if ln.startswith("JSON "))[5:])
+    assert rep["hill_best"] >= base_ll * (1 - 1e-12) and rep["mcmc_best"] >= rep["hill_best"] * (1 - 1e-12) and rep["pso_best"] >= base_ll * (1 - 1e-12)
+    bad = subprocess.run([exe, "--project-root", str(tmp_path / "nowhere")], capture_output=True, text=True)
+    assert bad.returncode == 1 and "unable to open" in bad.stderr
