@@ -435,6 +435,19 @@ sepaihrd_rc sepaihrd_set_stream(sepaihrd_ctx* ctx, void* cuda_stream) {
     return SEPAIHRD_OK;
 }
 
+sepaihrd_rc sepaihrd_alloc_pinned(size_t bytes, void** out) {
+    if (!out) return fail(SEPAIHRD_ERR_INVALID_ARGUMENT, "null argument");
+    *out = nullptr;
+    const cudaError_t e = cudaMallocHost(out, bytes ? bytes : 1);
+    if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) return fail(SEPAIHRD_ERR_NO_DEVICE, cudaGetErrorString(e));
+    if (e != cudaSuccess) return fail(e == cudaErrorMemoryAllocation ? SEPAIHRD_ERR_OUT_OF_MEMORY : SEPAIHRD_ERR_CUDA, cudaGetErrorString(e));
+    return SEPAIHRD_OK;
+}
+
+void sepaihrd_free_pinned(void* ptr) {
+    if (ptr) cudaFreeHost(ptr);
+}
+
 sepaihrd_rc sepaihrd_synchronize(sepaihrd_ctx* ctx) {
     if (!ctx) return fail(SEPAIHRD_ERR_INVALID_ARGUMENT, "null ctx");
     CUDA_TRY(cudaSetDevice(ctx->device));

@@ -11,6 +11,7 @@
 //     `--cache-size` are accepted and ignored;
 //   * `--project-root PATH` names the tree (the reference finds it by walking up from the working directory);
 //   * `--mode pso` and `--chains N` exist in addition (batched callers), and `--json` prints one machine-readable line.
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -98,6 +99,22 @@ std::map<std::string, double> settings_or_empty(const std::string& path, std::ma
     return reader(path);
 }
 
+// page-locked buffer of doubles (sepaihrd_alloc_pinned)
+class PinnedDoubles {
+public:
+    explicit PinnedDoubles(size_t count) {
+        void* p = nullptr;
+        if (sepaihrd_alloc_pinned(count * sizeof(double), &p) != SEPAIHRD_OK) throw std::runtime_error(std::string("sepaihrd_alloc_pinned: ") + sepaihrd_last_error());
+        p_ = static_cast<double*>(p);
+    }
+    ~PinnedDoubles() { sepaihrd_free_pinned(p_); }
+    PinnedDoubles(const PinnedDoubles&) = delete;
+    PinnedDoubles& operator=(const PinnedDoubles&) = delete;
+    double* data() { return p_; }
+private:
+    double* p_ = nullptr;
+};
+
 // counts what goes through it, like the reference's CountingObjective
 class CountingObjective : public IObjectiveFunction {
 public:
@@ -142,31 +159,37 @@ int main(int argc, char** argv) {
             const double warmup_val = counting.calculate(base);
             const double warmup_ms = ms_since(t0);
 
-            std::vector<double> rows, out;
+            // parameter rows and results in page-locked memory: the host-buffer call then overlaps its copies with the kernel
+            const size_t most = static_cast<size_t>(std::max(std::max(args.repeats, args.jitters), 1));
+            PinnedDoubles rows(most * static_cast<size_t>(P)), out(most);
             auto batch = [&](int n, double& sum) {
-                out.assign(static_cast<size_t>(n), 0.0);
                 const auto t = Clock::now();
                 if (n > 0) counting.calculateBatch(rows.data(), n, P, out.data());
                 const double took = ms_since(t);
                 sum = 0.0;
-                for (double v : out) sum += v;
+                for (int i = 0; i < n; ++i) sum += out.data()[i];
                 return took;
             };
-            rows.clear();
-            for (int i = 0; i < args.repeats; ++i) rows.insert(rows.end(), base.data(), base.data() + P);
+            for (int i = 0; i < args.repeats; ++i) std::copy(base.data(), base.data() + P, rows.data() + static_cast<size_t>(i) * P);
             double repeat_sum = 0.0;
             const double repeats_ms = batch(args.repeats, repeat_sum);
 
-            // the reference's recipe, set by set (draw order included)
+            // the reference's recipe, set by set (draw order included): one generator, drawn sequentially; the constraints
+            // are applied afterwards, row-parallel
             std::mt19937 rng(static_cast<unsigned>(args.seed));
             std::normal_distribution<double> normal(0.0, 1.0);
-            rows.clear();
             t0 = Clock::now();
-            VectorXd candidate = base;
+            std::vector<double> sigma(static_cast<size_t>(P));
+            for (std::ptrdiff_t i = 0; i < P; ++i) sigma[static_cast<size_t>(i)] = pm.getSigmaForParamIndex(static_cast<int>(i));
             for (int k = 0; k < args.jitters; ++k) {
-                for (std::ptrdiff_t i = 0; i < P; ++i) candidate[i] = base[i] + pm.getSigmaForParamIndex(static_cast<int>(i)) * normal(rng);
-                candidate = pm.applyConstraints(candidate);
-                rows.insert(rows.end(), candidate.data(), candidate.data() + P);
+                double* row = rows.data() + static_cast<size_t>(k) * P;
+                for (std::ptrdiff_t i = 0; i < P; ++i) row[i] = base[i] + sigma[static_cast<size_t>(i)] * normal(rng);
+            }
+#pragma omp parallel for schedule(static)
+            for (int k = 0; k < args.jitters; ++k) {
+                double* row = rows.data() + static_cast<size_t>(k) * P;
+                const VectorXd c = pm.applyConstraints(VectorXd::FromPointer(row, P));
+                std::copy(c.data(), c.data() + P, row);
             }
             const double gen_ms = ms_since(t0);
             double jitter_sum = 0.0;
