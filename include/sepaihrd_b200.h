@@ -219,6 +219,10 @@ sepaihrd_rc sepaihrd_swarm_step(sepaihrd_swarm* swarm, const uint32_t* seeds, do
 /* Copy one of the swarm's arrays to the host: [local][P] or [local] (SEPAIHRD_SWARM_*).                                */
 sepaihrd_rc sepaihrd_swarm_read(sepaihrd_swarm* swarm, int32_t what, double* out);
 
+/* The aggregation passes (sepaihrd_posterior_predictive) keep their device work buffers in the ctx and reuse them across
+ * calls; this frees them (they are also freed by sepaihrd_destroy). */
+sepaihrd_rc sepaihrd_release_scratch(sepaihrd_ctx* ctx);
+
 /* Page-locked host memory for the host-buffer entry points (sepaihrd_eval_batch, sepaihrd_simulate_batch, ...): parameter
  * and result buffers allocated here move at full PCIe / C2C rate and let the call overlap its copies with the kernel; any
  * other host pointer works too, through the driver's staging copies.  Free with sepaihrd_free_pinned.               */

@@ -39,6 +39,7 @@ SIGNATURES = {
     "sepaihrd_swarm_evaluate": (C.c_int, [C.c_void_p, _dp, C.POINTER(C.c_int64), C.c_void_p]),
     "sepaihrd_swarm_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_void_p]),
     "sepaihrd_swarm_read": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
+    "sepaihrd_release_scratch": (C.c_int, [C.c_void_p]),
     "sepaihrd_alloc_pinned": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
     "sepaihrd_free_pinned": (None, [C.c_void_p]),
     "sepaihrd_synchronize": (C.c_int, [C.c_void_p]),

@@ -63,6 +63,9 @@ struct sepaihrd_ctx {
     bool obs_mismatch = false;
     double abs_tol = 1e-6, rel_tol = 1e-6, dt_hint = 1.0, hmax = 1.0;
     bool bp_on_grid = false;       // no schedule breakpoint strictly inside an output interval
+    static constexpr int N_SCRATCH = 16;
+    void* scratch[N_SCRATCH] = {};        // grow-only work buffers of the aggregation passes (sepaihrd_internal::scratch)
+    size_t scratch_bytes[N_SCRATCH] = {};
     std::vector<double> blob;   // host image
     sepaihrd::KParams kp{};     // offsets etc. (I/O fields filled per call)
     double* d_blob = nullptr;
@@ -409,6 +412,7 @@ void sepaihrd_destroy(sepaihrd_ctx* ctx) {
     if (ctx->d_out) cudaFree(ctx->d_out);
     if (ctx->d_status) cudaFree(ctx->d_status);
     if (ctx->d_steps) cudaFree(ctx->d_steps);
+    for (void* p : ctx->scratch) if (p) cudaFree(p);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     for (int i = 0; i < 2; ++i) if (ctx->ev_copy[i]) cudaEventDestroy(ctx->ev_copy[i]);
@@ -432,6 +436,13 @@ sepaihrd_rc sepaihrd_set_math_mode(sepaihrd_ctx* ctx, int32_t mode) {
 sepaihrd_rc sepaihrd_set_stream(sepaihrd_ctx* ctx, void* cuda_stream) {
     if (!ctx) return fail(SEPAIHRD_ERR_INVALID_ARGUMENT, "null ctx");
     ctx->stream = (cuda_stream == SEPAIHRD_STREAM_OWN) ? ctx->own_stream : (cudaStream_t)cuda_stream;
+    return SEPAIHRD_OK;
+}
+
+sepaihrd_rc sepaihrd_release_scratch(sepaihrd_ctx* ctx) {
+    if (!ctx) return fail(SEPAIHRD_ERR_INVALID_ARGUMENT, "null argument");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    sepaihrd_internal::release_scratch(ctx);
     return SEPAIHRD_OK;
 }
 
@@ -652,6 +663,24 @@ sepaihrd_rc fail_with(sepaihrd_rc rc, const char* msg) { return fail(rc, msg); }
 const double* lower_bounds(const sepaihrd_ctx* ctx) { return ctx->blob.data() + ctx->kp.o_lo; }
 const double* upper_bounds(const sepaihrd_ctx* ctx) { return ctx->blob.data() + ctx->kp.o_hi; }
 void count_launches(sepaihrd_ctx* ctx, int n) { ctx->launches += n; }
+void* scratch(sepaihrd_ctx* ctx, int slot, size_t bytes) {
+    if (slot < 0 || slot >= sepaihrd_ctx::N_SCRATCH) return nullptr;
+    if (ctx->scratch_bytes[slot] >= bytes && ctx->scratch[slot]) return ctx->scratch[slot];
+    cudaStreamSynchronize(ctx->stream);             // nothing in flight may still use the buffer that is replaced
+    if (ctx->scratch[slot]) cudaFree(ctx->scratch[slot]);
+    ctx->scratch[slot] = nullptr; ctx->scratch_bytes[slot] = 0;
+    void* p = nullptr;
+    if (cudaMalloc(&p, bytes ? bytes : 16) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    ctx->scratch[slot] = p; ctx->scratch_bytes[slot] = bytes;
+    return p;
+}
+void release_scratch(sepaihrd_ctx* ctx) {
+    cudaStreamSynchronize(ctx->stream);
+    for (int i = 0; i < sepaihrd_ctx::N_SCRATCH; ++i) {
+        if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
+        ctx->scratch[i] = nullptr; ctx->scratch_bytes[i] = 0;
+    }
+}
 sepaihrd_rc simulate_observed_draw_minor(sepaihrd_ctx* ctx, const double* d_params, long long B, long long ld, const double* d_init,
                                          double* d_out, unsigned* d_status) {
     return simulate_device_impl(ctx, d_params, B, ld, d_init, 0, SEPAIHRD_TRAJ_OBSERVED, 1, d_out, d_status, true);

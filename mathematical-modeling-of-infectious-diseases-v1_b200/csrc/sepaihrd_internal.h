@@ -13,7 +13,11 @@ cudaStream_t stream(const sepaihrd_ctx* ctx);
 sepaihrd_rc fail_with(sepaihrd_rc rc, const char* msg);
 const double* lower_bounds(const sepaihrd_ctx* ctx);   // host copies, [P], as given at creation
 const double* upper_bounds(const sepaihrd_ctx* ctx);
-void count_launches(sepaihrd_ctx* ctx, int n);          // kernels another translation unit enqueued on the ctx stream
+void count_launches(sepaihrd_ctx* ctx, int n);
+// Grow-only device work buffer `slot` (0..15) of at least `bytes`, owned by the ctx and reused across calls; nullptr when the
+// allocation fails.  sepaihrd_release_scratch() drops them all.
+void* scratch(sepaihrd_ctx* ctx, int slot, size_t bytes);
+void release_scratch(sepaihrd_ctx* ctx);          // kernels another translation unit enqueued on the ctx stream
 // D, CumH, CumICU of B draws in the DRAW-MINOR layout [K][3n][B] (device pointers); d_init: one shared state or null
 sepaihrd_rc simulate_observed_draw_minor(sepaihrd_ctx* ctx, const double* d_params, long long B, long long ld, const double* d_init,
                                          double* d_out, unsigned* d_status);

@@ -115,27 +115,24 @@ extern "C" sepaihrd_rc sepaihrd_posterior_predictive(sepaihrd_ctx* ctx, const do
 
     cudaSetDevice(d.device);
     cudaStream_t s = stream(ctx);
-    double *d_params = nullptr, *d_init = nullptr, *d_traj = nullptr, *d_series = nullptr, *d_sorted = nullptr, *d_probs = nullptr, *d_q = nullptr;
-    unsigned* d_status = nullptr;
-    long long* d_off = nullptr;
-    unsigned long long* d_cnt = nullptr;
-    void* d_tmp = nullptr;
-    auto cleanup = [&]() {
-        for (void* p : {(void*)d_params, (void*)d_init, (void*)d_traj, (void*)d_series, (void*)d_sorted, (void*)d_probs, (void*)d_q, (void*)d_status,
-                        (void*)d_off, (void*)d_cnt, d_tmp})
-            if (p) cudaFree(p);
-    };
+    // work buffers live in the ctx (grow-only scratch slots): repeated aggregations of the same size allocate nothing
+    auto cleanup = [] {};
     const size_t traj_elems = (size_t)K * 3 * n * (size_t)B, col_elems = (size_t)n_cols * (size_t)B;
-    PPC_TRY(cudaMalloc(&d_params, sizeof(double) * (size_t)B * ld));
-    PPC_TRY(cudaMalloc(&d_init, sizeof(double) * SEPAIHRD_NUM_COMPARTMENTS * n));
-    PPC_TRY(cudaMalloc(&d_traj, sizeof(double) * traj_elems));
-    PPC_TRY(cudaMalloc(&d_series, sizeof(double) * 6 * col_elems));
-    PPC_TRY(cudaMalloc(&d_sorted, sizeof(double) * col_elems));
-    PPC_TRY(cudaMalloc(&d_probs, sizeof(double) * n_probs));
-    PPC_TRY(cudaMalloc(&d_q, sizeof(double) * 6 * (size_t)n_cols * n_probs));
-    PPC_TRY(cudaMalloc(&d_status, sizeof(unsigned) * (size_t)B));
-    PPC_TRY(cudaMalloc(&d_off, sizeof(long long) * (size_t)(n_cols + 1)));
-    PPC_TRY(cudaMalloc(&d_cnt, sizeof(unsigned long long)));
+    int slot = 0;
+    bool oom = false;
+    auto buf = [&](size_t bytes) { void* p = scratch(ctx, slot++, bytes); oom = oom || (p == nullptr); return p; };
+    double* d_params = (double*)buf(sizeof(double) * (size_t)B * ld);
+    double* d_init = (double*)buf(sizeof(double) * SEPAIHRD_NUM_COMPARTMENTS * n);
+    double* d_traj = (double*)buf(sizeof(double) * traj_elems);
+    double* d_series = (double*)buf(sizeof(double) * 6 * col_elems);
+    double* d_sorted = (double*)buf(sizeof(double) * col_elems);
+    double* d_probs = (double*)buf(sizeof(double) * n_probs);
+    double* d_q = (double*)buf(sizeof(double) * 6 * (size_t)n_cols * n_probs);
+    unsigned* d_status = (unsigned*)buf(sizeof(unsigned) * (size_t)B);
+    long long* d_off = (long long*)buf(sizeof(long long) * (size_t)(n_cols + 1));
+    unsigned long long* d_cnt = (unsigned long long*)buf(sizeof(unsigned long long));
+    if (oom) return fail_with(SEPAIHRD_ERR_OUT_OF_MEMORY, "posterior-predictive work buffers do not fit: split the draws");
+    void* d_tmp = nullptr;
     PPC_TRY(cudaMemcpyAsync(d_params, params, sizeof(double) * (size_t)B * ld, cudaMemcpyHostToDevice, s));
     PPC_TRY(cudaMemcpyAsync(d_init, initial_state, sizeof(double) * SEPAIHRD_NUM_COMPARTMENTS * n, cudaMemcpyHostToDevice, s));
     PPC_TRY(cudaMemcpyAsync(d_probs, probs, sizeof(double) * n_probs, cudaMemcpyHostToDevice, s));
@@ -158,7 +155,8 @@ extern "C" sepaihrd_rc sepaihrd_posterior_predictive(sepaihrd_ctx* ctx, const do
     size_t tmp_bytes = 0;
     PPC_TRY(cub::DeviceSegmentedRadixSort::SortKeys(nullptr, tmp_bytes, d_series, d_sorted, (long long)col_elems, (long long)n_cols, d_off, d_off + 1,
                                                      0, 64, s));
-    PPC_TRY(cudaMalloc(&d_tmp, tmp_bytes ? tmp_bytes : 16));
+    d_tmp = scratch(ctx, slot++, tmp_bytes ? tmp_bytes : 16);
+    if (!d_tmp) return fail_with(SEPAIHRD_ERR_OUT_OF_MEMORY, "posterior-predictive sort buffer does not fit: split the draws");
     for (int ser = 0; ser < 6; ++ser) {
         PPC_TRY(cub::DeviceSegmentedRadixSort::SortKeys(d_tmp, tmp_bytes, d_series + (size_t)ser * col_elems, d_sorted, (long long)col_elems,
                                                          (long long)n_cols, d_off, d_off + 1, 0, 64, s));

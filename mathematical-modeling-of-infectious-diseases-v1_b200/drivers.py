@@ -82,7 +82,7 @@ def run_multichain_mh(evaluate: Evaluate, sigmas, lower, upper, initial, n_chain
 
 
 def run_pso(evaluate: Evaluate, sigmas, lower, upper, swarm_size: int, iterations: int, seed: int, initial=None,
-            comm: Optional[Comm] = None, settings: Optional[Dict[str, float]] = None, device_ctx=None):
+            comm: Optional[Comm] = None, settings: Optional[Dict[str, float]] = None, device_ctx=None, return_positions: bool = False):
     """Particle swarm with the global-best topology (ParticleSwarmOptimizer.cpp:106-247, 330-425, 576-618), particles
     sharded over the ranks; per iteration one batch evaluation per rank, then the global-best reduction.
 
@@ -91,7 +91,7 @@ def run_pso(evaluate: Evaluate, sigmas, lower, upper, swarm_size: int, iteration
     called.  The visited positions are identical to the host-resident run."""
     comm = comm or Comm()
     if device_ctx is not None:
-        return _run_pso_device(device_ctx, sigmas, lower, upper, swarm_size, iterations, seed, initial, comm, settings)
+        return _run_pso_device(device_ctx, sigmas, lower, upper, swarm_size, iterations, seed, initial, comm, settings, return_positions)
     _host_threads(comm)
     lo, hi = shard_range(swarm_size, comm.rank, comm.world)
     pm = hostlib.ParameterManager(sigmas, lower, upper, mode=0)        # OPTIMIZATION_CLAMP (ModelCalibrator.cpp:62-66)
@@ -125,7 +125,7 @@ def run_pso(evaluate: Evaluate, sigmas, lower, upper, swarm_size: int, iteration
                 eval_seconds=t_eval, comm_seconds=t_comm, evaluations=(iterations + 1) * (hi - lo))
 
 
-def _run_pso_device(device_ctx, sigmas, lower, upper, swarm_size, iterations, seed, initial, comm, settings):
+def _run_pso_device(device_ctx, sigmas, lower, upper, swarm_size, iterations, seed, initial, comm, settings, return_positions):
     _host_threads(comm)
     lo, hi = shard_range(swarm_size, comm.rank, comm.world)
     pm = hostlib.ParameterManager(sigmas, lower, upper, mode=0)
@@ -154,6 +154,9 @@ def _run_pso_device(device_ctx, sigmas, lower, upper, swarm_size, iterations, se
         sw.step_device(it)
         evaluate_and_reduce()
     val, pos = sw.global_best()
-    sw.fetch()
-    return dict(rank=comm.rank, world=comm.world, particles=(lo, hi), best_value=val, best_position=pos, trace=np.array(trace),
-                eval_seconds=t_eval, comm_seconds=t_comm, evaluations=(iterations + 1) * (hi - lo), final_positions=sw.positions())
+    out = dict(rank=comm.rank, world=comm.world, particles=(lo, hi), best_value=val, best_position=pos, trace=np.array(trace),
+               eval_seconds=t_eval, comm_seconds=t_comm, evaluations=(iterations + 1) * (hi - lo))
+    if return_positions:            # the swarm itself stays on the device unless asked for
+        sw.fetch()
+        out["final_positions"] = sw.positions()
+    return out

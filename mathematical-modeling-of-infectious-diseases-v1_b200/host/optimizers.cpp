@@ -341,13 +341,14 @@ void ParticleSwarmOptimization::stepDevice(int iter) {
         throw std::runtime_error(std::string("sepaihrd_swarm_step: ") + sepaihrd_last_error());
 }
 
-void ParticleSwarmOptimization::fetchPersonalBests() {
+void ParticleSwarmOptimization::fetchPersonalBests(bool with_positions) {
     if (!dev_swarm_ || local_ == 0) return;
-    if (sepaihrd_swarm_read(dev_swarm_, SEPAIHRD_SWARM_PERSONAL_BEST, pbest_.data()) != SEPAIHRD_OK ||
-        sepaihrd_swarm_read(dev_swarm_, SEPAIHRD_SWARM_PERSONAL_BEST_VALUES, pbest_val_.data()) != SEPAIHRD_OK ||
-        sepaihrd_swarm_read(dev_swarm_, SEPAIHRD_SWARM_POSITIONS, pos_.data()) != SEPAIHRD_OK ||
-        sepaihrd_swarm_read(dev_swarm_, SEPAIHRD_SWARM_VELOCITIES, vel_.data()) != SEPAIHRD_OK)
-        throw std::runtime_error(std::string("sepaihrd_swarm_read: ") + sepaihrd_last_error());
+    bool ok = sepaihrd_swarm_read(dev_swarm_, SEPAIHRD_SWARM_PERSONAL_BEST, pbest_.data()) == SEPAIHRD_OK &&
+              sepaihrd_swarm_read(dev_swarm_, SEPAIHRD_SWARM_PERSONAL_BEST_VALUES, pbest_val_.data()) == SEPAIHRD_OK;
+    if (ok && with_positions)
+        ok = sepaihrd_swarm_read(dev_swarm_, SEPAIHRD_SWARM_POSITIONS, pos_.data()) == SEPAIHRD_OK &&
+             sepaihrd_swarm_read(dev_swarm_, SEPAIHRD_SWARM_VELOCITIES, vel_.data()) == SEPAIHRD_OK;
+    if (!ok) throw std::runtime_error(std::string("sepaihrd_swarm_read: ") + sepaihrd_last_error());
 }
 
 void ParticleSwarmOptimization::begin(const VectorXd* init, IParameterManager& pm) {
@@ -457,7 +458,7 @@ OptimizationResult ParticleSwarmOptimization::optimize(const VectorXd& initial, 
             stepDevice(iter);
             evaluate();
         }
-        fetchPersonalBests();
+        fetchPersonalBests(false);                 // the personal bests feed the covariance hand-off; positions stay on the device
     } else {
         begin(initial.size() == n ? &initial : nullptr, pm);
         auto evaluate = [&]() {

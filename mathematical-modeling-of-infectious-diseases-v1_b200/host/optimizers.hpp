@@ -121,7 +121,7 @@ public:
     void beginDevice(const VectorXd* initialParameters, IParameterManager& pm, sepaihrd_ctx* ctx);
     std::pair<double, int> evaluateDevice(double* best_position /* [P] or null */);   // objective launch + tell on the device
     void stepDevice(int iter);
-    void fetchPersonalBests();                                            // device -> pbest_ / pbest_val_ / pos_ (for the covariance hand-off)
+    void fetchPersonalBests(bool with_positions = true);                  // device -> pbest_ / pbest_val_ (covariance hand-off) [+ pos_ / vel_]
     bool onDevice() const { return dev_swarm_ != nullptr; }
     ~ParticleSwarmOptimization() override;
     ParticleSwarmOptimization() = default;

@@ -61,9 +61,12 @@ elif a.what == "ppcq":
     with BatchEvaluator(p, device=dev) as ev:
         ev.posterior_predictive(draws[:1024], p.data_initial_state)
         t0 = time.perf_counter()
-        q, valid = ev.posterior_predictive(draws, p.data_initial_state)
+        q, valid = ev.posterior_predictive(draws, p.data_initial_state)     # first call of this size: allocates ~10 GB of work buffers
+        first = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        q, valid = ev.posterior_predictive(draws, p.data_initial_state)     # steady state: the ctx reuses them
         dt = time.perf_counter() - t0
-    out.update(draws=a.draws, ages=4, seconds=dt, draws_per_s=a.draws / dt, valid=valid, median_deaths_last_day=[float(x) for x in q[2, -1, :, 2]])
+    out.update(draws=a.draws, ages=4, seconds=dt, first_call_seconds=first, draws_per_s=a.draws / dt, valid=valid, median_deaths_last_day=[float(x) for x in q[2, -1, :, 2]])
 else:
     p16 = p.expand_ages(4)
     o16 = orc.Oracle(p16)
