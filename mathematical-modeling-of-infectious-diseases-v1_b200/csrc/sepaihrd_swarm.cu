@@ -40,6 +40,8 @@ struct sepaihrd_swarm {
     double* h_gbest = nullptr;
     bool evaluated_once = false;
     int blocks_tell = 0;
+    char* d_arena = nullptr;            // the one device allocation all d_* pointers point into
+    char* h_arena = nullptr;            // the one pinned allocation all h_* pointers point into
 };
 
 namespace {
@@ -214,9 +216,6 @@ __global__ void __launch_bounds__(TELL_THREADS) swarm_best_kernel(int blocks, in
         for (int k = threadIdx.x; k < P; k += TELL_THREADS) best[2 + k] = pbest[bi * P + k];
 }
 
-template <class T>
-cudaError_t dalloc(T** p, size_t count) { return cudaMalloc((void**)p, sizeof(T) * (count ? count : 1)); }
-
 }  // namespace
 
 extern "C" {
@@ -236,17 +235,33 @@ sepaihrd_rc sepaihrd_swarm_create(sepaihrd_ctx* ctx, int64_t swarm_size, int64_t
     s->ctx = ctx; s->P = d.P; s->swarm_size = swarm_size; s->offset = particle_offset; s->local = local_count;
     const size_t tot = (size_t)local_count * d.P;
     s->blocks_tell = (int)((local_count + TELL_THREADS - 1) / TELL_THREADS);
+    // ONE device allocation and ONE pinned allocation, carved into the arrays (allocation and release cost far more than the
+    // arithmetic of an iteration; 256-byte aligned pieces)
     cudaError_t e = cudaSuccess;
-    auto ok = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
-    ok(dalloc(&s->d_pos, tot)); ok(dalloc(&s->d_vel, tot)); ok(dalloc(&s->d_pbest, tot));
-    ok(dalloc(&s->d_pbest_val, (size_t)local_count)); ok(dalloc(&s->d_fit, (size_t)local_count)); ok(dalloc(&s->d_status, (size_t)local_count));
-    ok(dalloc(&s->d_lb, (size_t)d.P)); ok(dalloc(&s->d_ub, (size_t)d.P)); ok(dalloc(&s->d_gbest, (size_t)d.P)); ok(dalloc(&s->d_init, (size_t)d.P));
-    ok(dalloc(&s->d_seeds, (size_t)swarm_size));
-    ok(dalloc(&s->d_block_val, (size_t)s->blocks_tell)); ok(dalloc(&s->d_block_idx, (size_t)s->blocks_tell));
-    ok(dalloc(&s->d_best, (size_t)d.P + 2));
-    ok(cudaMallocHost((void**)&s->h_best, sizeof(double) * ((size_t)d.P + 2)));
-    ok(cudaMallocHost((void**)&s->h_seeds, sizeof(unsigned) * (size_t)swarm_size));
-    ok(cudaMallocHost((void**)&s->h_gbest, sizeof(double) * (size_t)d.P));
+    size_t dev_bytes = 0, host_bytes = 0;
+    auto reserve = [](size_t& total, size_t bytes) { const size_t at = total; total += (bytes + 255) & ~(size_t)255; return at; };
+    const size_t o_pos = reserve(dev_bytes, sizeof(double) * tot), o_vel = reserve(dev_bytes, sizeof(double) * tot),
+                 o_pbest = reserve(dev_bytes, sizeof(double) * tot), o_pval = reserve(dev_bytes, sizeof(double) * (size_t)local_count),
+                 o_fit = reserve(dev_bytes, sizeof(double) * (size_t)local_count), o_status = reserve(dev_bytes, sizeof(unsigned) * (size_t)local_count),
+                 o_lb = reserve(dev_bytes, sizeof(double) * d.P), o_ub = reserve(dev_bytes, sizeof(double) * d.P),
+                 o_gbest = reserve(dev_bytes, sizeof(double) * d.P), o_init = reserve(dev_bytes, sizeof(double) * d.P),
+                 o_seeds = reserve(dev_bytes, sizeof(unsigned) * (size_t)swarm_size),
+                 o_bval = reserve(dev_bytes, sizeof(double) * (size_t)(s->blocks_tell + 1)),
+                 o_bidx = reserve(dev_bytes, sizeof(long long) * (size_t)(s->blocks_tell + 1)),
+                 o_best = reserve(dev_bytes, sizeof(double) * ((size_t)d.P + 2));
+    const size_t h_best = reserve(host_bytes, sizeof(double) * ((size_t)d.P + 2)), h_seeds = reserve(host_bytes, sizeof(unsigned) * (size_t)swarm_size),
+                 h_gbest = reserve(host_bytes, sizeof(double) * (size_t)d.P);
+    e = cudaMalloc((void**)&s->d_arena, dev_bytes);
+    if (e == cudaSuccess) e = cudaMallocHost((void**)&s->h_arena, host_bytes);
+    if (e == cudaSuccess) {
+        char* D = s->d_arena; char* H = s->h_arena;
+        s->d_pos = (double*)(D + o_pos); s->d_vel = (double*)(D + o_vel); s->d_pbest = (double*)(D + o_pbest);
+        s->d_pbest_val = (double*)(D + o_pval); s->d_fit = (double*)(D + o_fit); s->d_status = (unsigned*)(D + o_status);
+        s->d_lb = (double*)(D + o_lb); s->d_ub = (double*)(D + o_ub); s->d_gbest = (double*)(D + o_gbest); s->d_init = (double*)(D + o_init);
+        s->d_seeds = (unsigned*)(D + o_seeds); s->d_block_val = (double*)(D + o_bval); s->d_block_idx = (long long*)(D + o_bidx);
+        s->d_best = (double*)(D + o_best);
+        s->h_best = (double*)(H + h_best); s->h_seeds = (unsigned*)(H + h_seeds); s->h_gbest = (double*)(H + h_gbest);
+    }
     if (e == cudaSuccess) e = cudaMemcpy(s->d_lb, lo, sizeof(double) * d.P, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(s->d_ub, hi, sizeof(double) * d.P, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(swarm_init_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RNG_SMEM);
@@ -261,10 +276,8 @@ sepaihrd_rc sepaihrd_swarm_create(sepaihrd_ctx* ctx, int64_t swarm_size, int64_t
 
 void sepaihrd_swarm_destroy(sepaihrd_swarm* s) {
     if (!s) return;
-    cudaFree(s->d_pos); cudaFree(s->d_vel); cudaFree(s->d_pbest); cudaFree(s->d_pbest_val); cudaFree(s->d_fit); cudaFree(s->d_status);
-    cudaFree(s->d_lb); cudaFree(s->d_ub); cudaFree(s->d_gbest); cudaFree(s->d_init); cudaFree(s->d_seeds);
-    cudaFree(s->d_block_val); cudaFree(s->d_block_idx); cudaFree(s->d_best);
-    cudaFreeHost(s->h_best); cudaFreeHost(s->h_seeds); cudaFreeHost(s->h_gbest);
+    if (s->d_arena) cudaFree(s->d_arena);
+    if (s->h_arena) cudaFreeHost(s->h_arena);
     delete s;
 }
 

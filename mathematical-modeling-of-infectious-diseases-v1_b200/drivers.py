@@ -132,9 +132,11 @@ def _run_pso_device(device_ctx, sigmas, lower, upper, swarm_size, iterations, se
     st = dict(iterations=iterations, swarm_size=swarm_size, seed=seed)
     st.update(settings or {})
     st["particle_offset"], st["local_count"] = lo, hi - lo
+    t_start = time.perf_counter()
     sw = hostlib.Swarm(pm, st)
-    sw.begin_device(device_ctx, initial)
-    t_eval = t_comm = 0.0
+    sw.begin_device(device_ctx, initial)          # allocates the swarm in HBM (+ pinned staging) and draws it
+    t_setup = time.perf_counter() - t_start
+    t_eval = t_comm = t_step = 0.0
     trace = []
 
     def evaluate_and_reduce():
@@ -151,10 +153,12 @@ def _run_pso_device(device_ctx, sigmas, lower, upper, swarm_size, iterations, se
 
     evaluate_and_reduce()
     for it in range(iterations):
+        t0 = time.perf_counter()
         sw.step_device(it)
+        t_step += time.perf_counter() - t0
         evaluate_and_reduce()
     val, pos = sw.global_best()
-    out = dict(rank=comm.rank, world=comm.world, particles=(lo, hi), best_value=val, best_position=pos, trace=np.array(trace),
+    out = dict(setup_seconds=t_setup, step_seconds=t_step, rank=comm.rank, world=comm.world, particles=(lo, hi), best_value=val, best_position=pos, trace=np.array(trace),
                eval_seconds=t_eval, comm_seconds=t_comm, evaluations=(iterations + 1) * (hi - lo))
     if return_positions:            # the swarm itself stays on the device unless asked for
         sw.fetch()

@@ -51,6 +51,7 @@ elif a.what == "pso":
         r = drivers.run_pso(ev.eval_batch, p.sigmas, p.lower_bound, p.upper_bound, a.particles, a.iterations, seed=7,
                             initial=p.base_params(), comm=comm, device_ctx=None if a.host_swarm else ev.handle)
         comm.barrier(); dt = time.perf_counter() - t0
+    out.update(setup_seconds=r.get("setup_seconds"), step_seconds=r.get("step_seconds"))
     out.update(swarm="host" if a.host_swarm else "device", particles=a.particles, iterations=a.iterations, seconds=dt, evals_per_s=a.particles * (a.iterations + 1) / dt,
                eval_seconds=r["eval_seconds"], comm_seconds=r["comm_seconds"], best_first=float(r["trace"][0]), best_last=float(r["trace"][-1]))
 elif a.what == "ppcq":
