@@ -97,6 +97,24 @@ def test_seeded_mcmc_accept_sequences_are_identical_on_gpu_and_oracle(problem, r
     assert 0 < ref["accepts"].mean() < 1
 
 
+def test_seeded_mcmc_4096_chains_with_adaptation_matches_oracle(problem, reflect_problem, orc, ev_mod):
+    """BASELINE.json configs[2] at its own width: 4096 seeded chains, with the adaptive part switched on early (burn-in 3,
+    covariance recomputed + re-factorised every 2 iterations): identical accept matrix and identical visited states."""
+    from sepaihrd_b200 import drivers
+    o = orc.Oracle(reflect_problem)
+    kw = dict(sigmas=problem.sigmas, lower=problem.lower_bound, upper=problem.upper_bound, initial=problem.base_params(),
+              n_chains=4096, iterations=9, seed=1234, settings=dict(burn_in=3, adaptation_period=2))
+    ref = drivers.run_multichain_mh(lambda x: o.eval_batch(x)[0], **kw)
+    with ev_mod.BatchEvaluator(reflect_problem, device=0) as ev:
+        got = drivers.run_multichain_mh(ev.eval_batch, **kw)
+    assert got["accepts"].shape == (8, 4096)
+    np.testing.assert_array_equal(got["accepts"], ref["accepts"])
+    np.testing.assert_array_equal(got["x"], ref["x"])
+    np.testing.assert_array_equal(got["scale"], ref["scale"])
+    assert _rel(got["logpost"], ref["logpost"]).max() < 1e-8
+    assert 0.02 < ref["accepts"].mean() < 0.9
+
+
 def test_pso_swarm_reaches_the_same_global_best_on_gpu_and_oracle(problem, oracle, ev_mod):
     from sepaihrd_b200 import drivers
     kw = dict(sigmas=problem.sigmas, lower=problem.lower_bound, upper=problem.upper_bound, swarm_size=256, iterations=6, seed=7,
