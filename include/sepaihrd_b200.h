@@ -116,6 +116,9 @@ typedef struct sepaihrd_ctx sepaihrd_ctx; /* opaque: owns device copies of the p
  *                          CPU oracle up to libm (log/pow) differences. */
 #define SEPAIHRD_MATH_FAST   0
 #define SEPAIHRD_MATH_STRICT 1
+/* FAST arithmetic with the general kernel build even when every breakpoint sits on an output-grid point (the default then
+ * picks the build without the mixed-segment attempt body): a verification switch, results are bit-identical to FAST. */
+#define SEPAIHRD_MATH_FAST_GENERAL 2
 
 /* Replaces: construction of AgeSEPAIHRDModel + PiecewiseConstantNpiStrategy + SEPAIHRDParameterManager
  * + SEPAIHRDObjectiveFunction + AgeSEPAIHRDSimulator + Dopri5SolverStrategy

@@ -135,7 +135,7 @@ sepaihrd_rc launch_na(sepaihrd_ctx* ctx, const sepaihrd::KParams& kp, int mode) 
         return (mode == MODE_LL) ? launch_t<NA, true, MODE_LL, THREADS, MINBLOCKS, 5>(ctx, kp)
                                  : launch_t<NA, true, MODE_TRAJ, THREADS, MINBLOCKS, 5>(ctx, kp);
 #ifndef SEPAIHRD_EXP_NO_ONGRID
-    if (ctx->bp_on_grid)   // breakpoints on output-grid points (e.g. Spain 2020): the build without the mixed-segment attempt body
+    if (ctx->bp_on_grid && ctx->math_mode != SEPAIHRD_MATH_FAST_GENERAL)   // breakpoints on output-grid points (e.g. Spain 2020): the build without the mixed-segment attempt body
         return (mode == MODE_LL) ? launch_t<NA, false, MODE_LL, THREADS, MINBLOCKS, 6, true>(ctx, kp)
                                  : launch_t<NA, false, MODE_TRAJ, THREADS, MINBLOCKS, 6, true>(ctx, kp);
 #endif
@@ -427,8 +427,8 @@ sepaihrd_rc sepaihrd_set_constraint_mode(sepaihrd_ctx* ctx, int32_t mode) {
 }
 
 sepaihrd_rc sepaihrd_set_math_mode(sepaihrd_ctx* ctx, int32_t mode) {
-    if (!ctx || (mode != SEPAIHRD_MATH_FAST && mode != SEPAIHRD_MATH_STRICT)) return fail(SEPAIHRD_ERR_INVALID_ARGUMENT, "bad math mode");
-    if (mode == SEPAIHRD_MATH_FAST && (ctx->abs_tol <= 0.0 || ctx->rel_tol <= 0.0)) return fail(SEPAIHRD_ERR_UNSUPPORTED, "FAST math needs abs_tol > 0 and rel_tol > 0");
+    if (!ctx || (mode != SEPAIHRD_MATH_FAST && mode != SEPAIHRD_MATH_STRICT && mode != SEPAIHRD_MATH_FAST_GENERAL)) return fail(SEPAIHRD_ERR_INVALID_ARGUMENT, "bad math mode");
+    if (mode != SEPAIHRD_MATH_STRICT && (ctx->abs_tol <= 0.0 || ctx->rel_tol <= 0.0)) return fail(SEPAIHRD_ERR_UNSUPPORTED, "FAST math needs abs_tol > 0 and rel_tol > 0");
     ctx->math_mode = mode;
     return SEPAIHRD_OK;
 }

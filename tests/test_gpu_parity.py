@@ -432,3 +432,19 @@ def test_randomised_problems_match_the_oracle(problem, orc, ev_mod, seed):
         tr, _ = ev.simulate_batch(P[:6])
     good = np.isfinite(tr_ref).all(axis=(1, 2))
     assert (np.abs(tr[good] - tr_ref[good]) / np.maximum(np.abs(tr_ref[good]), 1.0)).max() < 1e-6
+
+
+def test_ongrid_build_is_bit_identical_to_the_general_build(problem, oracle, ev_mod):
+    """The Spain-2020 breakpoints sit on grid days, so FAST picks the kernel built without the mixed-segment attempt body;
+    SEPAIHRD_MATH_FAST_GENERAL forces the general build: same log-likelihoods, step counts and trajectories, bit for bit."""
+    P = np.vstack([oracle.jitter_params(3000, seed=41), oracle.uniform_params(1096, seed=42)])
+    with ev_mod.BatchEvaluator(problem, device=0, math=ev_mod.MATH_FAST) as a, \
+         ev_mod.BatchEvaluator(problem, device=0, math=ev_mod.MATH_FAST_GENERAL) as b:
+        ll_a, st_a, steps_a = a.eval_batch(P, return_steps=True)
+        ll_b, st_b, steps_b = b.eval_batch(P, return_steps=True)
+        np.testing.assert_array_equal(ll_a, ll_b)
+        np.testing.assert_array_equal(st_a, st_b)
+        np.testing.assert_array_equal(steps_a, steps_b)
+        tr_a, _ = a.simulate_batch(P[:64])
+        tr_b, _ = b.simulate_batch(P[:64])
+        np.testing.assert_array_equal(tr_a, tr_b)
