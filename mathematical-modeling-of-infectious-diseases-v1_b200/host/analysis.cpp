@@ -223,8 +223,11 @@ std::vector<SimulationResult> SimulationRunner::runSimulations(const std::vector
                                                                const std::vector<double>& times) {
     if (params.empty()) return {};
     if (times.empty()) throw InvalidParameterException("SimulationRunner", "Time points cannot be empty");
-    if (!simulator_)
+    if (!simulator_ || times.front() != sim_start_ || times.back() != sim_end_) {      // one simulator per time window
         simulator_ = std::make_unique<AgeSEPAIHRDSimulator>(model_template_, solver_, times.front(), times.back(), dt_hint_, abs_err_, rel_err_);
+        sim_start_ = times.front();
+        sim_end_ = times.back();
+    }
     std::vector<double> rows;
     size_t width = 0;
     for (const SEPAIHRDParameters& p : params) {

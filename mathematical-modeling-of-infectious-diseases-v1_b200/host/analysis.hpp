@@ -80,6 +80,7 @@ private:
     std::shared_ptr<IOdeSolverStrategy> solver_;
     double abs_err_, rel_err_, dt_hint_;
     std::unique_ptr<AgeSEPAIHRDSimulator> simulator_;
+    double sim_start_ = 0.0, sim_end_ = 0.0;
 };
 
 struct AggregatedTrajectory {                                   // per time point: sorted-sample quantiles
