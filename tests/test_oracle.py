@@ -344,3 +344,80 @@ def test_sixteen_age_variant_is_consistent_with_four(problem, orc):
     t16 = r16["traj"].reshape(problem.n_times, 11, 4, 4).sum(-1)
     rel = np.abs(t16 - t4) / np.maximum(np.abs(t4), 1.0)
     assert rel.max() < 1e-3
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The controller (row a4) once more, independently of oracle/sepaihrd_oracle.cpp: Boost.Odeint's integrate_times +
+# controlled_runge_kutta<runge_kutta_dopri5> + default_error_checker + default_step_adjuster written out in plain Python over
+# the numpy right-hand side above.  Different language, different author pass, vectorised RHS with another summation order
+# in the contact product: agreement of the accepted / rejected step pattern day by day and of the trajectory to ~1e-12 is
+# the strongest pin available without the Boost headers (parity unpinned by the reference itself).
+def _python_integrate_times(problem, slots, x0, times, dt, abs_tol=1e-6, rel_tol=1e-6):
+    eps = np.finfo(float).eps
+    a = (1 / 5, 3 / 10, 4 / 5, 8 / 9, 1.0, 1.0)
+    b = ((1 / 5,), (3 / 40, 9 / 40), (44 / 45, -56 / 15, 32 / 9), (19372 / 6561, -25360 / 2187, 64448 / 6561, -212 / 729),
+         (9017 / 3168, -355 / 33, 46732 / 5247, 49 / 176, -5103 / 18656))
+    c = (35 / 384, 0.0, 500 / 1113, 125 / 192, -2187 / 6784, 11 / 84)
+    dc = (c[0] - 5179 / 57600, 0.0, c[2] - 7571 / 16695, c[3] - 393 / 640, c[4] + 92097 / 339200, c[5] - 187 / 2100, -1 / 40)
+    f = lambda x, t: _numpy_rhs(problem, slots, x, t)
+    x = np.array(x0, dtype=float)
+    dxdt = None
+    rows, per_interval = [], []
+    for i, t in enumerate(times):
+        rows.append(x.copy())                                   # observer; t is reset to the grid value
+        if i + 1 == len(times):
+            break
+        t_next = times[i + 1]
+        acc = rej = fails = 0
+        while (t_next - t) > eps:                                # less_with_sign, dt > 0
+            cur = min(dt, t_next - t)
+            if dxdt is None:
+                dxdt = f(x, t)                                   # first call of a fresh controlled stepper
+            k = [dxdt]
+            for s in range(5):
+                y = x.copy()
+                for j in range(s + 1):
+                    y = y + (cur * b[s][j]) * k[j]
+                k.append(f(y, t + cur * a[s]))
+            xn = x.copy()
+            for j in range(6):
+                if c[j] != 0.0:
+                    xn = xn + (cur * c[j]) * k[j]
+            k7 = f(xn, t + cur)
+            k.append(k7)
+            xerr = np.zeros_like(x)
+            for j in range(7):
+                if dc[j] != 0.0:
+                    xerr = xerr + (cur * dc[j]) * k[j]
+            err = np.max(np.abs(xerr) / (abs_tol + rel_tol * (np.abs(x) + cur * np.abs(dxdt))))
+            if err > 1.0:                                        # reject: shrink with the ERROR order (4): exponent -1/3
+                cur *= max(0.9 * err ** (-1.0 / 3.0), 0.2)
+                rej += 1
+                fails += 1
+                assert fails < 500
+                dt = cur
+            else:                                                # accept: grow with the STEPPER order (5): exponent -1/5
+                t += cur
+                if err < 0.5:
+                    cur *= 0.9 * max(5.0 ** -5, err) ** (-1.0 / 5.0)
+                x, dxdt = xn, k7                                  # FSAL
+                fails = 0
+                acc += 1
+                dt = max(dt, cur)
+        per_interval.append((acc, rej))
+    return np.array(rows), np.array(per_interval)
+
+
+def test_controller_matches_an_independent_python_transcription(problem, oracle):
+    K = 60                                                       # through the breakpoint at t = 13 and 26 ordinary days
+    sub = problem.__class__.from_json(dict(problem.to_json(), times=[float(t) for t in problem.times[:K]],
+                                           obs_hosp=[float(v) for v in problem.obs_hosp[:K - 20].reshape(-1)],
+                                           obs_icu=[float(v) for v in problem.obs_icu[:K - 20].reshape(-1)],
+                                           obs_deaths=[float(v) for v in problem.obs_deaths[:K - 20].reshape(-1)]))
+    import __graft_entry__ as entry
+    o = entry.load_oracle().Oracle(sub)
+    r = o.eval_one(sub.base_params(), want_traj=True, want_interval_steps=True)
+    rows, steps = _python_integrate_times(sub, sub.base_slots, r["traj"][0], sub.times, sub.dt_hint)
+    np.testing.assert_array_equal(steps, r["interval_steps"])     # the same accepted / rejected attempts in every interval
+    assert steps[:, 1].sum() > 5 and steps[33, 1] > 0              # the rejections of day -20 and of the day after t = 13
+    np.testing.assert_allclose(rows, r["traj"], rtol=2e-11, atol=1e-9)
