@@ -771,9 +771,8 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) sepaihrd_batch_kernel(cons
                 bool big0 = false, big1 = false, big2 = false;
 #pragma unroll
                 for (int c = 0; c < NCOMP; ++c) {
-                    num[c] = fabs(xe[c]);
                     den[c] = fma(cur, fabs(k1[c]), fabs(x[c])) + kp.abs_over_rel;
-                    const bool g = num[c] > den[c];
+                    const bool g = fabs(xe[c]) > den[c];          // |.| is an operand modifier of the DSETP
                     if (c % 3 == 0) big0 |= g; else if (c % 3 == 1) big1 |= g; else big2 |= g;
                 }
                 // all votes of the attempt sit together after the body (measured: 1 % faster than voting before it)
@@ -794,6 +793,10 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) sepaihrd_batch_kernel(cons
                     break;
                 }
                 int lm0 = INT_MIN, lm1 = INT_MIN;
+                // |xe| as a value is needed only from here on (magnitude classes, tournament): clear the sign bit with an
+                // integer op instead of a DADD on the FP64 pipe (v10: +0.6 % A/B)
+#pragma unroll
+                for (int c = 0; c < NCOMP; ++c) num[c] = __hiloint2double(__double2hiint(xe[c]) & 0x7fffffff, __double2loint(xe[c]));
 #pragma unroll
                 for (int c = 0; c < NCOMP; ++c) {
                     const int l = __double2hiint(num[c]) - __double2hiint(den[c]);
