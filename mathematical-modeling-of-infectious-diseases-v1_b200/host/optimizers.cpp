@@ -76,18 +76,26 @@ void MetropolisHastingsSampler::begin(const VectorXd& initial, const double* ini
     if (!linalg::cholesky_lower(shared_cov_, shared_chol_)) shared_chol_ = MatrixXd::Identity(P, P) * 0.1;
 
     keep_history_ = iterations_ - 1 > burn_in_;      // the covariance adaptation reads the whole chain history
+    shared_diagonal_ = true;                          // the start kernel built from the sigmas is diagonal: L z is then P products
+    for (std::ptrdiff_t j = 0; j < P && shared_diagonal_; ++j)
+        for (std::ptrdiff_t i = 0; i < P; ++i)
+            if (i != j && shared_chol_(i, j) != 0.0) { shared_diagonal_ = false; break; }
     std::random_device rd;
-    chains_.assign(static_cast<size_t>(n_chains_), Chain());
+    chains_.clear();
+    chains_.resize(static_cast<size_t>(n_chains_));   // constructed in place (a chain carries a 2.5 KB generator)
     cur_x_.assign(static_cast<size_t>(n_chains_) * n_params_, 0.0);
     cur_lp_.assign(static_cast<size_t>(n_chains_), 0.0);
     prop_x_.assign(cur_x_.size(), 0.0);
+    std::vector<unsigned> fallback_seeds;
+    if (!has_seed_) { fallback_seeds.resize(static_cast<size_t>(n_chains_)); for (auto& v : fallback_seeds) v = rd(); }
+#pragma omp parallel for schedule(static)
     for (int c = 0; c < n_chains_; ++c) {
         Chain& ch = chains_[static_cast<size_t>(c)];
         if (has_seed_) {
             std::seed_seq seq{seed_, static_cast<unsigned>(chain_offset_ + c)};
             ch.gen.seed(seq);
         } else {
-            ch.gen.seed(rd());
+            ch.gen.seed(fallback_seeds[static_cast<size_t>(c)]);
         }
         std::copy(initial.data(), initial.data() + n_params_, cur_x_.begin() + static_cast<std::ptrdiff_t>(c) * n_params_);
         cur_lp_[static_cast<size_t>(c)] = safeValue(initial_logpost[c]);
@@ -175,8 +183,18 @@ void MetropolisHastingsSampler::propose(IParameterManager& pm, double* out) {
         VectorXd z(P);
         std::normal_distribution<double> dist(0.0, 1.0);
         for (std::ptrdiff_t i = 0; i < P; ++i) z(i) = dist(c.gen);
+        // L is a lower Cholesky factor (diagonal for the start kernel): the structural zeros are skipped, which leaves every
+        // sum unchanged (they would add +-0)
         const MatrixXd& L = c.own_kernel ? c.chol : shared_chol_;
-        const VectorXd step = L * z;
+        VectorXd step = VectorXd::Zero(P);
+        if (!c.own_kernel && shared_diagonal_) {
+            for (std::ptrdiff_t i = 0; i < P; ++i) step(i) = L(i, i) * z(i);
+        } else {
+            for (std::ptrdiff_t j = 0; j < P; ++j) {
+                const double zj = z(j);
+                for (std::ptrdiff_t i = j; i < P; ++i) step(i) += L(i, j) * zj;
+            }
+        }
         VectorXd y(P);
         const double* x = cur_x_.data() + static_cast<std::ptrdiff_t>(ci) * P;
         for (std::ptrdiff_t i = 0; i < P; ++i) y(i) = x[i] + c.global_scale * step(i);

@@ -75,6 +75,7 @@ private:
     bool adapt_scale_ = true, store_samples_ = true;
     int n_chains_ = 1;
     long chain_offset_ = 0;
+    bool shared_diagonal_ = false;
     bool has_seed_ = false;
     unsigned seed_ = 0;
     bool hasInitialCovariance_ = false;
