@@ -14,9 +14,9 @@
 // draws per double, low word first) -- and the same unfused FP64 operations in the same order, so a device-resident
 // swarm visits EXACTLY the positions of the host swarm (tests/test_gpu_host.py).
 //
-// Mapping: one thread per particle; the generator state (624 words) sits in shared memory, word-major so that the 64
-// threads of a block hit 64 different banks; the row-major [particle][P] arrays are read and written once per iteration
-// (HBM traffic 7 x 8 P bytes per particle, against ~1.8 MFLOP of evaluation: irrelevant to the iteration time).
+// Mapping: one thread per particle; the generator state (624 words) is a per-thread local-memory array (lane-interleaved,
+// hence coalesced, L1/L2-resident); the row-major [particle][P] arrays are read and written once per iteration (HBM traffic
+// 7 x 8 P bytes per particle, against ~1.8 MFLOP of evaluation: irrelevant to the iteration time).
 #include <cfloat>
 #include <cmath>
 #include <cstdint>
@@ -55,33 +55,41 @@ using sepaihrd_internal::fail_with;
     } while (0)
 
 constexpr int MT_N = 624, MT_M = 397;
-constexpr int RNG_THREADS = 64;                         // 64 generators x 624 words x 4 B = 156 KB of shared memory per block
-constexpr size_t RNG_SMEM = (size_t)MT_N * RNG_THREADS * sizeof(unsigned);
+constexpr int RNG_THREADS = 128;
 
-// std::mt19937 with its state in shared memory: word i of this thread's generator is st[i * RNG_THREADS + lane].
+// std::mt19937, one generator per thread.  The 624-word state is a per-thread array in LOCAL memory: the hardware interleaves
+// local memory by lane, so word i of the 32 generators of a warp is one coalesced 128-byte line, served from L1/L2.  (v10
+// kept the states in shared memory -- 156 KB for 64 generators -- which left 2 warps per SM to hide the latencies of the
+// seeding recurrence and of the row-major parameter traffic: 0.44 ms per update of 65 536 particles.)
+// The state is refilled lazily in blocks of 16 words, in increasing order: a step of 4 P = 248 draws twists 256 words, not 624.
 struct Mt19937 {
-    unsigned* st;
-    int idx;
-    __device__ void seed(unsigned* base, unsigned s) {
-        st = base + threadIdx.x;
+    unsigned st[MT_N];
+    int idx, filled;
+    __device__ void seed(unsigned s) {
         unsigned x = s;
         st[0] = x;
+#pragma unroll 4
         for (int i = 1; i < MT_N; ++i) {
             x = 1812433253u * (x ^ (x >> 30)) + (unsigned)i;
-            st[i * RNG_THREADS] = x;
+            st[i] = x;
         }
-        idx = MT_N;
+        idx = MT_N; filled = MT_N;
     }
-    __device__ void refill() {
-        for (int k = 0; k < MT_N; ++k) {
-            const unsigned y = (st[k * RNG_THREADS] & 0x80000000u) | (st[((k + 1) % MT_N) * RNG_THREADS] & 0x7fffffffu);
-            st[k * RNG_THREADS] = st[((k + MT_M) % MT_N) * RNG_THREADS] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+    // twist words [from, from + 16): word k needs the OLD k + 1 and the word k + 397 (mod 624), which for k >= 227 is the
+    // already twisted k - 227 -- exactly the order of the reference algorithm
+    __device__ void refill16(int from) {
+#pragma unroll 4
+        for (int k = from; k < from + 16; ++k) {
+            const int k1 = (k + 1 == MT_N) ? 0 : k + 1;
+            const int km = (k + MT_M >= MT_N) ? k + MT_M - MT_N : k + MT_M;
+            const unsigned y = (st[k] & 0x80000000u) | (st[k1] & 0x7fffffffu);
+            st[k] = st[km] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
         }
-        idx = 0;
     }
     __device__ unsigned next() {
-        if (idx >= MT_N) refill();
-        unsigned y = st[(idx++) * RNG_THREADS];
+        if (idx >= MT_N) { idx = 0; filled = 0; }
+        if (idx >= filled) { refill16(filled); filled += 16; }      // 624 = 39 x 16
+        unsigned y = st[idx++];
         y ^= (y >> 11);
         y ^= (y << 7) & 0x9d2c5680u;
         y ^= (y << 15) & 0xefc60000u;
@@ -105,12 +113,11 @@ __global__ void __launch_bounds__(RNG_THREADS) swarm_init_kernel(long long local
                                                                  const double* __restrict__ lb, const double* __restrict__ ub,
                                                                  const double* __restrict__ init, double* __restrict__ pos,
                                                                  double* __restrict__ vel) {
-    extern __shared__ unsigned smem_rng[];
     const long long li = blockIdx.x * (long long)RNG_THREADS + threadIdx.x;
     if (li >= local) return;
     const long long gi = offset + li;
     Mt19937 rng;
-    rng.seed(smem_rng, seeds[gi]);
+    rng.seed(seeds[gi]);
     double* p = pos + li * P;
     double* v = vel + li * P;
     if (gi == 0 && init != nullptr) {
@@ -130,11 +137,10 @@ __global__ void __launch_bounds__(RNG_THREADS) swarm_step_kernel(long long local
                                                                  const double* __restrict__ gbest, const double* __restrict__ pbest,
                                                                  double omega, double c1, double c2, double* __restrict__ pos,
                                                                  double* __restrict__ vel) {
-    extern __shared__ unsigned smem_rng[];
     const long long li = blockIdx.x * (long long)RNG_THREADS + threadIdx.x;
     if (li >= local) return;
     Mt19937 rng;
-    rng.seed(smem_rng, seeds[offset + li]);
+    rng.seed(seeds[offset + li]);
     double* p = pos + li * P;
     double* v = vel + li * P;
     const double* pb = pbest + li * P;
@@ -264,8 +270,6 @@ sepaihrd_rc sepaihrd_swarm_create(sepaihrd_ctx* ctx, int64_t swarm_size, int64_t
     }
     if (e == cudaSuccess) e = cudaMemcpy(s->d_lb, lo, sizeof(double) * d.P, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(s->d_ub, hi, sizeof(double) * d.P, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(swarm_init_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RNG_SMEM);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(swarm_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RNG_SMEM);
     if (e != cudaSuccess) {
         sepaihrd_swarm_destroy(s);
         return fail_with(e == cudaErrorMemoryAllocation ? SEPAIHRD_ERR_OUT_OF_MEMORY : SEPAIHRD_ERR_CUDA, cudaGetErrorString(e));
@@ -302,7 +306,7 @@ sepaihrd_rc sepaihrd_swarm_init(sepaihrd_swarm* s, const uint32_t* seeds, const 
     s->evaluated_once = false;
     if (s->local > 0) {
         const unsigned blocks = (unsigned)((s->local + RNG_THREADS - 1) / RNG_THREADS);
-        swarm_init_kernel<<<blocks, RNG_THREADS, RNG_SMEM, st>>>(s->local, s->offset, s->P, s->d_seeds, s->d_lb, s->d_ub,
+        swarm_init_kernel<<<blocks, RNG_THREADS, 0, st>>>(s->local, s->offset, s->P, s->d_seeds, s->d_lb, s->d_ub,
                                                                  initial ? s->d_init : nullptr, s->d_pos, s->d_vel);
         SW_TRY(cudaGetLastError());
         sepaihrd_internal::count_launches(s->ctx, 1);
@@ -352,7 +356,7 @@ sepaihrd_rc sepaihrd_swarm_step(sepaihrd_swarm* s, const uint32_t* seeds, double
     SW_TRY(cudaMemcpyAsync(s->d_gbest, s->h_gbest, sizeof(double) * s->P, cudaMemcpyHostToDevice, st));
     if (s->local > 0) {
         const unsigned blocks = (unsigned)((s->local + RNG_THREADS - 1) / RNG_THREADS);
-        swarm_step_kernel<<<blocks, RNG_THREADS, RNG_SMEM, st>>>(s->local, s->offset, s->P, s->d_seeds, s->d_lb, s->d_ub, s->d_gbest, s->d_pbest,
+        swarm_step_kernel<<<blocks, RNG_THREADS, 0, st>>>(s->local, s->offset, s->P, s->d_seeds, s->d_lb, s->d_ub, s->d_gbest, s->d_pbest,
                                                                  omega, c1, c2, s->d_pos, s->d_vel);
         SW_TRY(cudaGetLastError());
         sepaihrd_internal::count_launches(s->ctx, 1);
