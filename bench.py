@@ -9,7 +9,7 @@
 Workload (BASELINE.json configs[1]): a batched likelihood sweep of
 B = 1,048,576 parameter sets PER GPU (weak scaling), 4 age groups, Spain-2020 window; set b =
 clamp(base + sigma * N(0,1)) -- the reference benchmark's own jitter recipe
-(sepaihrd_objective_benchmark_main.cpp:452-460), std::mt19937(1), tiled from 65,536 distinct draws.
+(sepaihrd_objective_benchmark_main.cpp:452-460), std::mt19937(1); all 1,048,576 sets are distinct draws.
 One "step" = one pass of the hot path over the batch = ONE launch of the fused kernel.
 
 value   : whole-job evals/s with the parameter batch resident in HBM; CUDA events on the launching
@@ -40,7 +40,7 @@ import __graft_entry__ as entry  # noqa: E402
 METRIC = "SEPAIHRD Dopri5+Poisson likelihood evals/sec"
 UNIT = "evals/s"
 B_PER_GPU = 1 << 20
-DISTINCT = 1 << 16
+DISTINCT = 1 << 20              # every set of the batch is its own draw
 FLOP_PER_ATTEMPT = 3750.0      # 6 RHS + stage/solution/error combinations + error norm, n = 4
 FLOP_PER_SET_FIXED = 22000.0   # 3672 likelihood terms * ~6
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch at B = 2^20 (ncu --set full, profiles/r01_v9_ncu_full_summary.txt):

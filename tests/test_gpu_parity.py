@@ -371,8 +371,9 @@ def test_posterior_predictive_quantiles_match_numpy_on_oracle_trajectories(probl
 
 
 def test_every_distinct_set_of_the_bench_batch_matches_the_oracle(problem, oracle, ev_mod):
-    """The bench batch is 65,536 distinct jittered sets tiled 16 times (bench.py).  ALL distinct sets against the CPU oracle:
-    logL within 1e-8 relative (north_star gate), identical status words, identical accepted/rejected step counts."""
+    """The first 65,536 sets of the bench batch (bench.py draws 1,048,576 distinct jittered sets from mt19937(1); the whole
+    batch and a second distribution are covered by tools/full_parity.py) against the CPU oracle: logL within 1e-8 relative
+    (north_star gate), identical status words, identical accepted/rejected step counts."""
     P = oracle.jitter_params(1 << 16, seed=1)
     ll_ref, st_ref, steps_ref, _ = oracle.eval_batch(P)
     with ev_mod.BatchEvaluator(problem, device=0) as ev:

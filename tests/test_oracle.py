@@ -421,3 +421,37 @@ def test_controller_matches_an_independent_python_transcription(problem, oracle)
     np.testing.assert_array_equal(steps, r["interval_steps"])     # the same accepted / rejected attempts in every interval
     assert steps[:, 1].sum() > 5 and steps[33, 1] > 0              # the rejections of day -20 and of the day after t = 13
     np.testing.assert_allclose(rows, r["traj"], rtol=2e-11, atol=1e-9)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The Dopri5 STEPPER (tableau, solution weights, embedded error weights) against a published third-party implementation:
+# scipy.integrate's RK45 is the same Dormand-Prince 5(4) pair (its step CONTROLLER differs from Boost's, so only single
+# steps and coefficients are comparable).  One forced-accept step of the oracle (huge tolerances: the first attempt of
+# length t1 - t0 is taken as is) must equal scipy's rk_step, and the coefficient tuples of the Python transcription above
+# -- which the oracle's accept / reject pattern is checked against -- must equal scipy's A, B, C and E (E up to the sign
+# convention: Boost forms x5 - x4 with dc_i = c_i - c4_i, scipy K^T E with E = b4 - b5 ... the norm takes |.|).
+def test_dopri5_stepper_matches_scipy_rk45_tableau_and_one_step(problem, orc):
+    rk = pytest.importorskip("scipy.integrate._ivp.rk")
+    RK45, rk_step = rk.RK45, rk.rk_step
+    a = (1 / 5, 3 / 10, 4 / 5, 8 / 9, 1.0)
+    np.testing.assert_allclose(RK45.C[1:6], a, rtol=1e-15)
+    b = ((1 / 5,), (3 / 40, 9 / 40), (44 / 45, -56 / 15, 32 / 9), (19372 / 6561, -25360 / 2187, 64448 / 6561, -212 / 729),
+         (9017 / 3168, -355 / 33, 46732 / 5247, 49 / 176, -5103 / 18656))
+    for s, row in enumerate(b):
+        np.testing.assert_allclose(RK45.A[s + 1][:s + 1], row, rtol=1e-15)
+    c = (35 / 384, 0.0, 500 / 1113, 125 / 192, -2187 / 6784, 11 / 84)
+    np.testing.assert_allclose(RK45.B, c, rtol=1e-15)
+    dc = (c[0] - 5179 / 57600, 0.0, c[2] - 7571 / 16695, c[3] - 393 / 640, c[4] + 92097 / 339200, c[5] - 187 / 2100, -1 / 40)
+    np.testing.assert_allclose(-np.asarray(RK45.E), dc, rtol=2e-13, atol=1e-17)
+
+    for t0, h in ((-20.0, 1.0), (5.0, 0.5), (13.0, 1.0), (40.0, 1.0)):      # 13.0: step starting ON a breakpoint (quirk Q2)
+        sub = problem.__class__.from_json(dict(problem.to_json(), times=[t0, t0 + h], abs_tol=1e30, rel_tol=1e30,
+                                               dt_hint=h, obs_hosp=[], obs_icu=[], obs_deaths=[]))
+        o = orc.Oracle(sub)
+        r = o.eval_one(sub.base_params(), want_traj=True, want_interval_steps=True)
+        assert tuple(r["interval_steps"][0]) == (1, 0)
+        x0 = r["traj"][0]
+        f = lambda t, y: _numpy_rhs(sub, sub.base_slots, np.asarray(y, dtype=float), t)
+        K = np.empty((7, x0.size))
+        y_new, _ = rk_step(f, t0, x0, f(t0, x0), h, RK45.A, RK45.B, RK45.C, K)
+        np.testing.assert_allclose(r["traj"][1], y_new, rtol=1e-12, atol=1e-9)
