@@ -36,13 +36,14 @@ struct Args {
     std::string hillSettingsPath, mcmcSettingsPath, psoSettingsPath;
     bool useFileIters = false, json = false;
     int hillIters = 200, mcmcIters = 2000, psoIters = 30, chains = 1, swarm = 4096;
+    bool psoAsConfigured = false;
 };
 
 void usage(const char* prog) {
     std::cout << "Usage: " << prog << " --project-root PATH [--repeats N] [--jitters N] [--seed N] [--threads N]\n"
               << "       [--start YYYY-MM-DD] [--end YYYY-MM-DD] [--constraints opt|mcmc] [--no-cache] [--cache-size N]\n"
               << "       [--mode micro|hill|mcmc|hillmcmc|pso|all] [--hill-settings PATH] [--mcmc-settings PATH] [--pso-settings PATH]\n"
-              << "       [--hill-iters N] [--mcmc-iters N] [--pso-iters N] [--chains N] [--swarm N] [--use-file-iters] [--json]\n";
+              << "       [--hill-iters N] [--mcmc-iters N] [--pso-iters N] [--chains N] [--swarm N] [--pso-as-configured] [--use-file-iters] [--json]\n";
 }
 
 Args parse(int argc, char** argv) {
@@ -72,6 +73,7 @@ Args parse(int argc, char** argv) {
         else if (f == "--hill-iters") a.hillIters = std::stoi(value());
         else if (f == "--mcmc-iters") a.mcmcIters = std::stoi(value());
         else if (f == "--pso-iters") a.psoIters = std::stoi(value());
+        else if (f == "--pso-as-configured") a.psoAsConfigured = true;
         else if (f == "--chains") a.chains = std::stoi(value());
         else if (f == "--swarm") a.swarm = std::stoi(value());
         else if (f == "--json") a.json = true;
@@ -246,15 +248,18 @@ int main(int argc, char** argv) {
             std::map<std::string, double> st = settings_or_empty(args.psoSettingsPath, readParticleSwarmSettings);
             if (!args.useFileIters) { st["iterations"] = args.psoIters; st["swarm_size"] = args.swarm; }
             st["seed"] = args.seed;
-            for (const char* k : {"variant", "topology", "use_opposition_learning", "use_adaptive_parameters"}) st.erase(k);   // STANDARD / GLOBAL_BEST only
+            // default: the STANDARD / GLOBAL_BEST swarm of BASELINE.json configs[3] (device-resident); --pso-as-configured keeps the
+            // variant / topology / opposition / adaptation switches of the settings file (whole-swarm engine, one batch per evaluation)
+            if (!args.psoAsConfigured)
+                for (const char* k : {"variant", "topology", "use_opposition_learning", "use_adaptive_parameters"}) st[k] = 0.0;
             pm.setConstraintMode(ConstraintMode::OPTIMIZATION_CLAMP);
             ParticleSwarmOptimization pso;
             pso.configure(st);
             const auto t0 = Clock::now();
             const OptimizationResult res = pso.optimize(base, objective, pm);          // the device-resident swarm needs the device objective itself
             const double took = ms_since(t0);
-            const double evals = (st["iterations"] + 1.0) * st["swarm_size"];
-            std::printf("\n--- PSO (device-resident swarm) ---\nTime: %.3f ms\nObjective calls: %.0f (%.4e evals/s)\nBest logL: %.12e\n", took, evals,
+            const double evals = static_cast<double>(pso.evaluations());
+            std::printf("\n--- PSO (%s) ---\nTime: %.3f ms\nObjective calls: %.0f (%.4e evals/s)\nBest logL: %.12e\n", pso.onDevice() ? "device-resident swarm" : "host-resident swarm, batched evaluations", took, evals,
                         evals / took * 1e3, res.bestObjectiveValue);
             report["pso_ms"] = took; report["pso_best"] = res.bestObjectiveValue; report["pso_calls"] = evals;
         };

@@ -278,6 +278,38 @@ int32_t sepaihrd_host_pso_evaluate_device(sepaihrd_host_pso* pso, double* best_v
 }
 int32_t sepaihrd_host_pso_step_device(sepaihrd_host_pso* pso, int32_t iter) { return guarded([&] { pso->s.stepDevice(iter); }); }
 int32_t sepaihrd_host_pso_fetch(sepaihrd_host_pso* pso) { return guarded([&] { pso->s.fetchPersonalBests(); }); }
+int32_t sepaihrd_host_pso_run(sepaihrd_host_pso* pso, sepaihrd_host_batch_fn fn, void* user, const double* init, double* out_best,
+                              double* out_value, double* out_stats) {
+    return guarded([&] {
+        if (!pso || !fn) throw InvalidParameterException("sepaihrd_host_pso_run", "bad argument");
+        CallbackObjective f(fn, user, pso->pm->pm.getParameterNames());
+        const auto P = static_cast<std::ptrdiff_t>(pso->pm->pm.getParameterCount());
+        const VectorXd x0 = init ? VectorXd::FromPointer(init, P) : VectorXd();
+        const OptimizationResult r = pso->s.optimize(x0, f, pso->pm->pm);
+        if (out_best) std::copy(r.bestParameters.data(), r.bestParameters.data() + P, out_best);
+        if (out_value) *out_value = r.bestObjectiveValue;
+        if (out_stats) {
+            out_stats[0] = static_cast<double>(pso->s.evaluations()); out_stats[1] = pso->s.restartCount();
+            out_stats[2] = pso->s.elitistTrials(); out_stats[3] = pso->s.swarmDiversity();
+        }
+    });
+}
+int32_t sepaihrd_host_pso_values(const sepaihrd_host_pso* pso, double* out_pbest, double* out_fitness) {
+    return guarded([&] {
+        if (out_pbest) std::copy(pso->s.personalBestValues().begin(), pso->s.personalBestValues().end(), out_pbest);
+        if (out_fitness) std::copy(pso->s.currentFitness().begin(), pso->s.currentFitness().end(), out_fitness);
+    });
+}
+int32_t sepaihrd_host_pso_neighbors(sepaihrd_host_pso* pso, int32_t particle, int32_t* out, int32_t cap) {
+    int32_t count = -1;
+    const int32_t rc = guarded([&] {
+        if (!pso || particle < 0 || particle >= pso->s.swarmSize()) throw InvalidParameterException("sepaihrd_host_pso_neighbors", "particle outside the swarm");
+        const std::vector<int> nb = pso->s.getNeighbors(particle);
+        count = static_cast<int32_t>(nb.size());
+        for (int32_t i = 0; i < count && i < cap; ++i) out[i] = nb[static_cast<size_t>(i)];
+    });
+    return rc == 0 ? count : -1;
+}
 void sepaihrd_host_pso_destroy(sepaihrd_host_pso* pso) { delete pso; }
 
 // ---- whole runs against a callback --------------------------------------------------------------------------

@@ -57,9 +57,12 @@ int32_t sepaihrd_host_mh_state(const sepaihrd_host_mh* mh, double* out_x /* [n][
 int32_t sepaihrd_host_mh_best(const sepaihrd_host_mh* mh, double* out_x /* [P] */, double* out_value);
 void    sepaihrd_host_mh_destroy(sepaihrd_host_mh* mh);
 
-/* ---- particle swarm (ParticleSwarmOptimization, step-wise; this process owns a contiguous shard) ---------- *
- * settings: iterations, swarm_size, omega_start/end, c1_initial/final, c2_initial/final, plus particle_offset,
- * local_count, seed.                                                                                             */
+/* ---- particle swarm (ParticleSwarmOptimization) ----------------------------------------------------------------- *
+ * settings: every key of the reference's pso_settings.txt (iterations, swarm_size, omega_start/end, c1_initial/final,
+ * c2_initial/final, variant, topology, use_opposition_learning, use_adaptive_parameters, restart_threshold, max_stagnation,
+ * quantum_beta, levy_alpha, ...) with the reference class's defaults, plus particle_offset, local_count, seed,
+ * device_resident.  The step-wise calls (begin / tell / step, and their device forms) drive one contiguous shard of the
+ * STANDARD / GLOBAL_BEST swarm (variant 0, topology 0, no opposition learning, no adaptive parameters).               */
 typedef struct sepaihrd_host_pso sepaihrd_host_pso;
 int32_t sepaihrd_host_pso_create(sepaihrd_host_pm* pm, int32_t n_settings, const char* const* keys, const double* values,
                                  sepaihrd_host_pso** out);
@@ -80,6 +83,15 @@ int32_t sepaihrd_host_pso_evaluate_device(sepaihrd_host_pso* pso, double* out_be
                                           double* out_best_position /* [P] or NULL */);
 int32_t sepaihrd_host_pso_step_device(sepaihrd_host_pso* pso, int32_t iter);
 int32_t sepaihrd_host_pso_fetch(sepaihrd_host_pso* pso);
+/* Whole run of ParticleSwarmOptimization::optimize on this handle against a batch callback: every variant / topology /
+ * opposition / adaptation / restart / elitist-learning setting of the reference class (ParticleSwarmOptimizer.cpp:106-247).
+ * out_stats[4] = objective evaluations, stagnation restarts, elitist-learning trials consumed, final swarm diversity.        */
+int32_t sepaihrd_host_pso_run(sepaihrd_host_pso* pso, sepaihrd_host_batch_fn fn, void* user, const double* initial_or_null,
+                              double* out_best /* [P] */, double* out_best_value, double* out_stats /* [4] or NULL */);
+/* state of the swarm after sepaihrd_host_pso_run: personal-best values and current fitness, [swarm_size] each */
+int32_t sepaihrd_host_pso_values(const sepaihrd_host_pso* pso, double* out_pbest_values, double* out_current_fitness);
+/* getNeighbors (ParticleSwarmOptimizer.cpp:836-905) of the configured topology; returns the count, fills at most `cap`      */
+int32_t sepaihrd_host_pso_neighbors(sepaihrd_host_pso* pso, int32_t particle, int32_t* out, int32_t cap);
 void    sepaihrd_host_pso_destroy(sepaihrd_host_pso* pso);
 
 /* ---- whole runs against a batch callback: "mh", "pso" or "hill" (IOptimizationAlgorithm::optimize) --------- */

@@ -271,28 +271,63 @@ OptimizationResult MetropolisHastingsSampler::optimize(const VectorXd& initial, 
 }
 
 // =====================================================================================================================
-// Particle swarm (STANDARD update, GLOBAL_BEST topology)
+// Particle swarm (ParticleSwarmOptimizer.cpp, whole class).  optimize() is the reference's algorithm with every swarm
+// evaluation handed to calculateBatch as ONE batch; the STANDARD / GLOBAL_BEST swarm with linear schedules also exists
+// step-wise (begin / tell / step: shardable over processes) and device-resident (beginDevice / evaluateDevice / stepDevice).
+//
+// Where batching forces a choice the reference leaves open:
+//   * the reference's OpenMP loop lets particle i read personal bests its neighbours may or may not have updated yet in
+//     the same iteration (sequentially: always for j < i); here every neighbourhood best is taken from the personal bests
+//     at the START of the iteration -- the synchronous swarm;
+//   * RANDOM_DYNAMIC shuffles with the shared master generator inside that OpenMP loop (a data race in the reference);
+//     here the shuffles run in particle order before the updates, which is the reference's single-thread order;
+//   * HYBRID passes an empty mean-best vector into quantumPSOUpdate (it is only computed for QUANTUM, .cpp:359-362:
+//     out-of-bounds reads); here the mean of the personal bests is computed for HYBRID as well;
+//   * std::sort on equal fitness values (opposition selection, restart) is replaced by std::stable_sort, so ties keep
+//     the lower particle index;
+//   * the <= 3 sequential trial evaluations of the elitist learning strategy are generated ahead and evaluated as one
+//     batch of 3; the master generator is then rewound to where the reference would have stopped drawing.
 // =====================================================================================================================
 void ParticleSwarmOptimization::configure(const std::map<std::string, double>& s) {
-    auto nonneg = [&](const char* k, double def) { const double v = setting(s, k, def); if (v < 0) throw std::invalid_argument(std::string(k) + " must be non-negative"); return v; };
-    auto positive = [&](const char* k, double def) { const double v = setting(s, k, def); if (v <= 0) throw std::invalid_argument(std::string(k) + " must be positive"); return v; };
-    iterations_ = static_cast<int>(positive("iterations", 100.0));
-    swarm_size_ = static_cast<int>(positive("swarm_size", 30.0));
-    omega_start_ = nonneg("omega_start", 0.9); omega_end_ = nonneg("omega_end", 0.4);
-    c1_initial_ = nonneg("c1_initial", 2.5); c1_final_ = nonneg("c1_final", 0.5);
-    c2_initial_ = nonneg("c2_initial", 0.5); c2_final_ = nonneg("c2_final", 2.5);
-    report_interval_ = static_cast<int>(positive("report_interval", 10.0));
-    // Only the STANDARD variant on the GLOBAL_BEST topology is built (BASELINE.json configs[3]); asking for another one
-    // is an error rather than a silent substitution.
-    if (s.count("variant") && static_cast<int>(s.at("variant")) != 0) throw std::invalid_argument("variant: only STANDARD (0) is built in the batched PSO");
-    if (s.count("topology") && static_cast<int>(s.at("topology")) != 0) throw std::invalid_argument("topology: only GLOBAL_BEST (0) is built in the batched PSO");
-    if (setting(s, "use_opposition_learning", 0.0) != 0.0) throw std::invalid_argument("use_opposition_learning is not built in the batched PSO");
-    if (setting(s, "use_adaptive_parameters", 0.0) != 0.0) throw std::invalid_argument("use_adaptive_parameters is not built in the batched PSO");
-    particle_offset_ = static_cast<long>(setting(s, "particle_offset", 0.0));
-    local_count_setting_ = static_cast<int>(setting(s, "local_count", -1.0));
-    has_seed_ = s.count("seed") != 0;
-    seed_ = static_cast<unsigned>(setting(s, "seed", 0.0));
-    device_resident_ = setting(s, "device_resident", 1.0) != 0.0;
+    // .cpp:10-104: only the keys present are touched, each validated with the reference's message
+    for (const auto& [key, value] : s) {
+        if (key == "iterations") { if (value <= 0) throw std::invalid_argument("iterations must be positive"); iterations_ = static_cast<int>(value); }
+        else if (key == "swarm_size") { if (value <= 0) throw std::invalid_argument("swarm_size must be positive"); swarm_size_ = static_cast<int>(value); }
+        else if (key == "omega_start") { if (value < 0) throw std::invalid_argument("omega_start must be non-negative"); omega_start_ = value; }
+        else if (key == "omega_end") { if (value < 0) throw std::invalid_argument("omega_end must be non-negative"); omega_end_ = value; }
+        else if (key == "c1_initial") { if (value < 0) throw std::invalid_argument("c1_initial must be non-negative"); c1_initial_ = value; }
+        else if (key == "c1_final") { if (value < 0) throw std::invalid_argument("c1_final must be non-negative"); c1_final_ = value; }
+        else if (key == "c2_initial") { if (value < 0) throw std::invalid_argument("c2_initial must be non-negative"); c2_initial_ = value; }
+        else if (key == "c2_final") { if (value < 0) throw std::invalid_argument("c2_final must be non-negative"); c2_final_ = value; }
+        else if (key == "report_interval") { if (value <= 0) throw std::invalid_argument("report_interval must be positive"); report_interval_ = static_cast<int>(value); }
+        else if (key == "variant") {
+            const int v = static_cast<int>(value);
+            if (v < 0 || v > 4) throw std::invalid_argument("variant must be between 0 and 4");
+            variant_ = static_cast<PSOVariant>(v);
+        } else if (key == "topology") {
+            const int t = static_cast<int>(value);
+            if (t < 0 || t > 3) throw std::invalid_argument("topology must be between 0 and 3");
+            topology_ = static_cast<TopologyType>(t);
+        }
+        else if (key == "use_opposition_learning") use_opposition_learning_ = (value != 0.0);
+        else if (key == "use_parallel") use_parallel_ = (value != 0.0);           // kept for the settings file; the batch IS the parallel loop
+        else if (key == "use_adaptive_parameters") use_adaptive_parameters_ = (value != 0.0);
+        else if (key == "diversity_threshold") diversity_threshold_ = value;
+        else if (key == "restart_threshold") restart_threshold_ = value;
+        else if (key == "quantum_beta") quantum_beta_ = value;
+        else if (key == "levy_alpha") levy_alpha_ = value;
+        else if (key == "max_stagnation") { if (value <= 0) throw std::invalid_argument("max_stagnation must be positive"); max_stagnation_ = static_cast<int>(value); }
+        else if (key == "log_evolutionary_state") log_evolutionary_state_ = (value != 0.0);
+        // extensions of this build: sharding, repeatable runs, device-resident swarm
+        else if (key == "particle_offset") particle_offset_ = static_cast<long>(value);
+        else if (key == "local_count") local_count_setting_ = static_cast<int>(value);
+        else if (key == "seed") { has_seed_ = true; seed_ = static_cast<unsigned>(value); }
+        else if (key == "device_resident") device_resident_ = (value != 0.0);
+    }
+}
+
+bool ParticleSwarmOptimization::isBasicSwarm() const {
+    return variant_ == PSOVariant::STANDARD && topology_ == TopologyType::GLOBAL_BEST && !use_opposition_learning_ && !use_adaptive_parameters_;
 }
 
 ParticleSwarmOptimization::~ParticleSwarmOptimization() {
@@ -306,12 +341,17 @@ void ParticleSwarmOptimization::setupRun(IParameterManager& pm) {
     lb_.resize(static_cast<size_t>(n_)); ub_.resize(static_cast<size_t>(n_));
     for (int k = 0; k < n_; ++k) { lb_[static_cast<size_t>(k)] = pm.getLowerBoundForParamIndex(k); ub_[static_cast<size_t>(k)] = pm.getUpperBoundForParamIndex(k); }
     if (has_seed_) rng_.seed(seed_); else rng_.seed(std::random_device{}());
+    uniform_dist_.reset(); normal_dist_.reset();
     const size_t tot = static_cast<size_t>(local_) * static_cast<size_t>(n_);
     pos_.assign(tot, 0.0); vel_.assign(tot, 0.0); pbest_.assign(tot, 0.0);
     pbest_val_.assign(static_cast<size_t>(local_), -std::numeric_limits<double>::infinity());
+    cur_fit_.assign(static_cast<size_t>(local_), -std::numeric_limits<double>::infinity());
+    success_rate_.assign(static_cast<size_t>(local_), 0.0);
+    success_count_.assign(static_cast<size_t>(local_), 0); total_updates_.assign(static_cast<size_t>(local_), 0);
     gbest_.assign(static_cast<size_t>(n_), 0.0);
     gbest_value_ = -std::numeric_limits<double>::infinity();
     first_tell_ = true;
+    restarts_ = 0; els_trials_ = 0; evaluations_ = 0;
     if (dev_swarm_) { sepaihrd_swarm_destroy(dev_swarm_); dev_swarm_ = nullptr; }
 }
 
@@ -329,8 +369,17 @@ void ParticleSwarmOptimization::coefficients(int iter, double& omega, double& c1
     c2 = c2_initial_ + (c2_final_ - c2_initial_) * ratio;
 }
 
+namespace {
+void require_basic(const ParticleSwarmOptimization& s, const char* who) {
+    if (!s.isBasicSwarm())
+        throw std::invalid_argument(std::string(who) + ": the step-wise / device-resident swarm is the STANDARD variant on the GLOBAL_BEST topology "
+                                    "(settings variant 0, topology 0, use_opposition_learning 0, use_adaptive_parameters 0); optimize() runs every other configuration");
+}
+}  // namespace
+
 void ParticleSwarmOptimization::beginDevice(const VectorXd* init, IParameterManager& pm, sepaihrd_ctx* ctx) {
     if (!ctx) throw std::invalid_argument("beginDevice: null device context");
+    require_basic(*this, "beginDevice");
     setupRun(pm);
     if (sepaihrd_swarm_create(ctx, swarm_size_, particle_offset_, local_, &dev_swarm_) != SEPAIHRD_OK)
         throw std::runtime_error(std::string("sepaihrd_swarm_create: ") + sepaihrd_last_error());
@@ -347,6 +396,7 @@ std::pair<double, int> ParticleSwarmOptimization::evaluateDevice(double* best_po
     if (sepaihrd_swarm_evaluate(dev_swarm_, &value, &index, best_position) != SEPAIHRD_OK)
         throw std::runtime_error(std::string("sepaihrd_swarm_evaluate: ") + sepaihrd_last_error());
     first_tell_ = false;
+    evaluations_ += local_;
     return {value, static_cast<int>(index)};
 }
 
@@ -369,8 +419,8 @@ void ParticleSwarmOptimization::fetchPersonalBests(bool with_positions) {
     if (!ok) throw std::runtime_error(std::string("sepaihrd_swarm_read: ") + sepaihrd_last_error());
 }
 
-void ParticleSwarmOptimization::begin(const VectorXd* init, IParameterManager& pm) {
-    setupRun(pm);
+// the draws of initializeSwarm (.cpp:273-298) for the local particles: position, then velocity, from the particle's own generator
+void ParticleSwarmOptimization::drawInitialSwarm(const VectorXd* init) {
     const std::vector<uint32_t> seeds = drawSeeds();
 #pragma omp parallel for schedule(static)
     for (int li = 0; li < local_; ++li) {
@@ -391,6 +441,12 @@ void ParticleSwarmOptimization::begin(const VectorXd* init, IParameterManager& p
     }
 }
 
+void ParticleSwarmOptimization::begin(const VectorXd* init, IParameterManager& pm) {
+    require_basic(*this, "begin");
+    setupRun(pm);
+    drawInitialSwarm(init);
+}
+
 std::pair<double, int> ParticleSwarmOptimization::tell(const double* fitness) {
     double best = -std::numeric_limits<double>::infinity();
     int best_i = -1;
@@ -404,6 +460,7 @@ std::pair<double, int> ParticleSwarmOptimization::tell(const double* fitness) {
         if (pbest_val_[static_cast<size_t>(li)] > best) { best = pbest_val_[static_cast<size_t>(li)]; best_i = li; }   // first maximum wins (.cpp:149-156)
     }
     first_tell_ = false;
+    evaluations_ += local_;
     return {best, best_i};
 }
 
@@ -414,6 +471,29 @@ void ParticleSwarmOptimization::setGlobalBest(double value, const double* positi
     }
 }
 
+// standardPSOUpdate (.cpp:576-618) for local particle i towards `lbest`: r1_k, r2_k interleaved per dimension
+void ParticleSwarmOptimization::standardPSOUpdate(int i, const double* lbest, double omega, double c1, double c2, std::mt19937& rng) {
+    std::uniform_real_distribution<> U(0.0, 1.0);
+    double* p = pos_.data() + static_cast<size_t>(i) * n_;
+    double* v = vel_.data() + static_cast<size_t>(i) * n_;
+    const double* pb = pbest_.data() + static_cast<size_t>(i) * n_;
+    std::vector<double> r1(static_cast<size_t>(n_)), r2(static_cast<size_t>(n_));
+    for (int k = 0; k < n_; ++k) { r1[static_cast<size_t>(k)] = U(rng); r2[static_cast<size_t>(k)] = U(rng); }
+    for (int k = 0; k < n_; ++k) {
+        const size_t kk = static_cast<size_t>(k);
+        const double cognitive = c1 * (r1[kk] * (pb[k] - p[k]));
+        const double social = c2 * (r2[kk] * (lbest[k] - p[k]));
+        double vk = omega * v[k] + cognitive + social;
+        const double vmax = 0.2 * (ub_[kk] - lb_[kk]);
+        vk = std::clamp(vk, -vmax, vmax);
+        double pk = p[k] + vk;
+        if (pk < lb_[kk]) { pk = lb_[kk] + std::abs(pk - lb_[kk]); vk *= -0.5; }      // reflection with velocity dampening
+        else if (pk > ub_[kk]) { pk = ub_[kk] - std::abs(pk - ub_[kk]); vk *= -0.5; }
+        p[k] = std::clamp(pk, lb_[kk], ub_[kk]);
+        v[k] = vk;
+    }
+}
+
 void ParticleSwarmOptimization::step(int iter) {
     double omega, c1, c2;
     coefficients(iter, omega, c1, c2);
@@ -421,26 +501,7 @@ void ParticleSwarmOptimization::step(int iter) {
 #pragma omp parallel for schedule(static)
     for (int li = 0; li < local_; ++li) {
         std::mt19937 local_rng(seeds[static_cast<size_t>(particle_offset_ + li)]);
-        std::uniform_real_distribution<> U(0.0, 1.0);
-        double* p = pos_.data() + static_cast<size_t>(li) * n_;
-        double* v = vel_.data() + static_cast<size_t>(li) * n_;
-        const double* pb = pbest_.data() + static_cast<size_t>(li) * n_;
-        // standardPSOUpdate (.cpp:576-618): r1_k, r2_k interleaved per dimension
-        std::vector<double> r1(static_cast<size_t>(n_)), r2(static_cast<size_t>(n_));
-        for (int k = 0; k < n_; ++k) { r1[static_cast<size_t>(k)] = U(local_rng); r2[static_cast<size_t>(k)] = U(local_rng); }
-        for (int k = 0; k < n_; ++k) {
-            const size_t kk = static_cast<size_t>(k);
-            const double cognitive = c1 * (r1[kk] * (pb[k] - p[k]));
-            const double social = c2 * (r2[kk] * (gbest_[kk] - p[k]));
-            double vk = omega * v[k] + cognitive + social;
-            const double vmax = 0.2 * (ub_[kk] - lb_[kk]);
-            vk = std::clamp(vk, -vmax, vmax);
-            double pk = p[k] + vk;
-            if (pk < lb_[kk]) { pk = lb_[kk] + std::abs(pk - lb_[kk]); vk *= -0.5; }
-            else if (pk > ub_[kk]) { pk = ub_[kk] - std::abs(pk - ub_[kk]); vk *= -0.5; }
-            p[k] = std::clamp(pk, lb_[kk], ub_[kk]);
-            v[k] = vk;
-        }
+        standardPSOUpdate(li, gbest_.data(), omega, c1, c2, local_rng);
     }
 }
 
@@ -460,37 +521,409 @@ MatrixXd ParticleSwarmOptimization::personalBestScatter(VectorXd& mean) const {
     return sc;
 }
 
-OptimizationResult ParticleSwarmOptimization::optimize(const VectorXd& initial, IObjectiveFunction& f, IParameterManager& pm) {
-    const int n = static_cast<int>(pm.getParameterCount());
-    auto* device_objective = dynamic_cast<SEPAIHRDObjectiveFunction*>(&f);
-    if (device_objective != nullptr && device_resident_) {
-        // the swarm stays in HBM: per iteration one seed per particle goes down, one (value, index, position) triple comes back
-        beginDevice(initial.size() == n ? &initial : nullptr, pm, device_objective->device().get());
-        std::vector<double> best_pos(static_cast<size_t>(n));
-        auto evaluate = [&]() {
-            const auto best = evaluateDevice(best_pos.data());
-            if (best.second >= 0) setGlobalBest(best.first, best_pos.data());
-        };
-        evaluate();
-        for (int iter = 0; iter < iterations_; ++iter) {
-            stepDevice(iter);
-            evaluate();
+// ---- the whole-swarm engine ------------------------------------------------------------------------------------------
+void ParticleSwarmOptimization::evaluateSwarm(IObjectiveFunction& f, int first, std::vector<double>& fitness) {
+    if (first >= local_) return;
+    f.calculateBatch(pos_.data() + static_cast<size_t>(first) * n_, local_ - first, n_, fitness.data() + first);   // not sanitised (.cpp:298, :412)
+    evaluations_ += local_ - first;
+}
+
+void ParticleSwarmOptimization::rescanGlobalBest() {                       // .cpp:149-156, :316-321: strict >, index order
+    for (int i = 0; i < local_; ++i)
+        if (pbest_val_[static_cast<size_t>(i)] > gbest_value_) {
+            gbest_value_ = pbest_val_[static_cast<size_t>(i)];
+            gbest_.assign(pbest_.begin() + static_cast<std::ptrdiff_t>(i) * n_, pbest_.begin() + static_cast<std::ptrdiff_t>(i + 1) * n_);
         }
-        fetchPersonalBests(false);                 // the personal bests feed the covariance hand-off; positions stay on the device
-    } else {
-        begin(initial.size() == n ? &initial : nullptr, pm);
-        auto evaluate = [&]() {
-            std::vector<double> fit(static_cast<size_t>(local_));
-            f.calculateBatch(pos_.data(), local_, n_, fit.data());         // the reference does not sanitise PSO fitness (.cpp:412)
-            const auto best = tell(fit.data());
-            if (best.second >= 0) setGlobalBest(best.first, personalBest(best.second));
-        };
-        evaluate();
-        for (int iter = 0; iter < iterations_; ++iter) {
-            step(iter);
-            evaluate();
+}
+
+void ParticleSwarmOptimization::permuteSwarm(const std::vector<int>& order) {
+    auto rows = [&](std::vector<double>& a) {
+        std::vector<double> b(a.size());
+        for (int i = 0; i < local_; ++i)
+            std::copy(a.begin() + static_cast<std::ptrdiff_t>(order[static_cast<size_t>(i)]) * n_, a.begin() + static_cast<std::ptrdiff_t>(order[static_cast<size_t>(i)] + 1) * n_,
+                      b.begin() + static_cast<std::ptrdiff_t>(i) * n_);
+        a.swap(b);
+    };
+    auto scal = [&](auto& a) {
+        auto b = a;
+        for (int i = 0; i < local_; ++i) b[static_cast<size_t>(i)] = a[static_cast<size_t>(order[static_cast<size_t>(i)])];
+        a.swap(b);
+    };
+    rows(pos_); rows(vel_); rows(pbest_);
+    scal(pbest_val_); scal(cur_fit_); scal(success_rate_); scal(success_count_); scal(total_updates_);
+}
+
+// oppositionBasedInitialization (.cpp:507-560).  The opposite particles are built but never evaluated before the selection
+// (their pbest_value is the struct default -inf, ParticleSwarmOptimizer.hpp:258), so with finite fitness values the
+// selection keeps the original swarm, sorted by fitness; an opposite particle enters only where an original scored -inf.
+void ParticleSwarmOptimization::oppositionBasedInitialization() {
+    const int N = local_;
+    const double NEG_INF = -std::numeric_limits<double>::infinity();
+    std::vector<std::pair<double, int>> cand;
+    cand.reserve(static_cast<size_t>(2 * N));
+    for (int i = 0; i < N; ++i) { cand.push_back({pbest_val_[static_cast<size_t>(i)], i}); cand.push_back({NEG_INF, i + N}); }
+    std::stable_sort(cand.begin(), cand.end(), [](const auto& a, const auto& b) { return a.first > b.first; });
+    std::vector<double> pos(pos_.size()), vel(vel_.size()), pb(pbest_.size()), pbv(static_cast<size_t>(N)), cf(static_cast<size_t>(N)), sr(static_cast<size_t>(N));
+    std::vector<int> sc(static_cast<size_t>(N)), tu(static_cast<size_t>(N));
+    for (int i = 0; i < N; ++i) {
+        const int idx = cand[static_cast<size_t>(i)].second;
+        const size_t d = static_cast<size_t>(i) * n_;
+        if (idx < N) {
+            const size_t s = static_cast<size_t>(idx) * n_;
+            std::copy(pos_.begin() + s, pos_.begin() + s + n_, pos.begin() + d);
+            std::copy(vel_.begin() + s, vel_.begin() + s + n_, vel.begin() + d);
+            std::copy(pbest_.begin() + s, pbest_.begin() + s + n_, pb.begin() + d);
+            pbv[static_cast<size_t>(i)] = pbest_val_[static_cast<size_t>(idx)]; cf[static_cast<size_t>(i)] = cur_fit_[static_cast<size_t>(idx)];
+            sr[static_cast<size_t>(i)] = success_rate_[static_cast<size_t>(idx)]; sc[static_cast<size_t>(i)] = success_count_[static_cast<size_t>(idx)];
+            tu[static_cast<size_t>(i)] = total_updates_[static_cast<size_t>(idx)];
+        } else {
+            const size_t s = static_cast<size_t>(idx - N) * n_;
+            for (int k = 0; k < n_; ++k) {
+                pos[d + k] = lb_[static_cast<size_t>(k)] + ub_[static_cast<size_t>(k)] - pos_[s + k];
+                vel[d + k] = -vel_[s + k];
+                pb[d + k] = pos[d + k];
+            }
+            pbv[static_cast<size_t>(i)] = NEG_INF; cf[static_cast<size_t>(i)] = NEG_INF; sr[static_cast<size_t>(i)] = 0.0; sc[static_cast<size_t>(i)] = 0; tu[static_cast<size_t>(i)] = 0;
         }
     }
+    pos_.swap(pos); vel_.swap(vel); pbest_.swap(pb); pbest_val_.swap(pbv); cur_fit_.swap(cf); success_rate_.swap(sr); success_count_.swap(sc); total_updates_.swap(tu);
+}
+
+void ParticleSwarmOptimization::initializeSwarmFull(const VectorXd* init, IObjectiveFunction& f, IParameterManager& pm) {
+    setupRun(pm);
+    drawInitialSwarm(init);
+    evaluateSwarm(f, 0, cur_fit_);
+    pbest_ = pos_; pbest_val_ = cur_fit_;
+    if (use_opposition_learning_) {                                      // .cpp:306-315: select, then evaluate the whole swarm again
+        oppositionBasedInitialization();
+        evaluateSwarm(f, 0, cur_fit_);
+        pbest_ = pos_; pbest_val_ = cur_fit_;
+    }
+    gbest_value_ = -std::numeric_limits<double>::infinity();
+    rescanGlobalBest();
+    first_tell_ = false;
+}
+
+std::vector<int> ParticleSwarmOptimization::getNeighbors(int particle_idx) {
+    std::vector<int> nb;
+    const int N = swarm_size_;
+    switch (topology_) {
+        case TopologyType::GLOBAL_BEST:
+            nb.resize(static_cast<size_t>(N));
+            for (int i = 0; i < N; ++i) nb[static_cast<size_t>(i)] = i;
+            break;
+        case TopologyType::LOCAL_BEST:                                   // ring, two neighbours on each side
+            nb.push_back(particle_idx);
+            for (int j = 1; j <= 2; ++j) { nb.push_back((particle_idx - j + N) % N); nb.push_back((particle_idx + j) % N); }
+            break;
+        case TopologyType::VON_NEUMANN: {                                // ceil(sqrt(N))-wide grid, no wrap-around
+            const int g = static_cast<int>(std::ceil(std::sqrt(N)));
+            const int row = particle_idx / g, col = particle_idx % g;
+            nb.push_back(particle_idx);
+            if (row > 0) { const int idx = (row - 1) * g + col; if (idx < N) nb.push_back(idx); }
+            if (row < g - 1) { const int idx = (row + 1) * g + col; if (idx < N) nb.push_back(idx); }
+            if (col > 0) { const int idx = row * g + (col - 1); if (idx < N) nb.push_back(idx); }
+            if (col < g - 1) { const int idx = row * g + (col + 1); if (idx < N) nb.push_back(idx); }
+            break;
+        }
+        case TopologyType::RANDOM_DYNAMIC: {                             // four random others, redrawn on every call (master generator)
+            nb.push_back(particle_idx);
+            std::vector<int> cand;
+            cand.reserve(static_cast<size_t>(std::max(N - 1, 0)));
+            for (int i = 0; i < N; ++i) if (i != particle_idx) cand.push_back(i);
+            std::shuffle(cand.begin(), cand.end(), rng_);
+            const int k = std::min(4, static_cast<int>(cand.size()));
+            nb.insert(nb.end(), cand.begin(), cand.begin() + k);
+            break;
+        }
+    }
+    return nb;
+}
+
+double ParticleSwarmOptimization::calculateEvolutionaryFactor() const {   // .cpp:446-482
+    const double INF = std::numeric_limits<double>::infinity();
+    double mean_distance = 0.0, max_distance = 0.0, mean_fitness = 0.0, max_fitness = -INF, min_fitness = INF;
+    for (int i = 0; i < local_; ++i) {
+        double d2 = 0.0;
+        for (int k = 0; k < n_; ++k) { const double d = pos_[static_cast<size_t>(i) * n_ + static_cast<size_t>(k)] - gbest_[static_cast<size_t>(k)]; d2 += d * d; }
+        const double dist = std::sqrt(d2);
+        mean_distance += dist;
+        max_distance = std::max(max_distance, dist);
+        const double cf = cur_fit_[static_cast<size_t>(i)];
+        mean_fitness += cf;
+        max_fitness = std::max(max_fitness, cf);
+        min_fitness = std::min(min_fitness, cf);
+    }
+    mean_distance /= swarm_size_;
+    mean_fitness /= swarm_size_;
+    const double fitness_range = (max_fitness - min_fitness) > 1e-10 ? (max_fitness - min_fitness) : 1e-10;
+    const double distance_factor = (max_distance > 0) ? mean_distance / max_distance : 0.0;
+    const double fitness_factor = (max_fitness - mean_fitness) / fitness_range;
+    return 0.5 * distance_factor + 0.5 * (1.0 - fitness_factor);
+}
+
+ParticleSwarmOptimization::EvolutionaryState ParticleSwarmOptimization::estimateEvolutionaryState() const {   // .cpp:427-444
+    const double ef = calculateEvolutionaryFactor();
+    if (ef > 0.7) return EvolutionaryState::EXPLORATION;
+    if (ef > 0.4) return EvolutionaryState::EXPLOITATION;
+    if (ef > 0.2) return EvolutionaryState::CONVERGENCE;
+    return EvolutionaryState::JUMPING_OUT;
+}
+
+void ParticleSwarmOptimization::adaptParameters(EvolutionaryState state, int iter, double& omega, double& c1, double& c2) {   // .cpp:484-505
+    const double PI = 3.14159265358979323846;
+    const double ratio = (iterations_ > 1) ? static_cast<double>(iter) / (iterations_ - 1) : 0.0;
+    switch (state) {
+        case EvolutionaryState::EXPLORATION:
+            omega = 0.9 - 0.2 * ratio; c1 = 1.5 + 0.5 * std::sin(ratio * PI); c2 = 1.5 - 0.5 * std::sin(ratio * PI); break;
+        case EvolutionaryState::EXPLOITATION:
+            omega = 0.7 - 0.3 * ratio; c1 = 2.0 - ratio; c2 = 1.0 + ratio; break;
+        case EvolutionaryState::CONVERGENCE:
+            omega = 0.4 - 0.3 * ratio; c1 = 1.0 - 0.5 * ratio; c2 = 2.0 + 0.5 * ratio; break;
+        case EvolutionaryState::JUMPING_OUT:                              // three draws from the master generator, in this order
+            omega = 0.9 + 0.1 * uniform_dist_(rng_); c1 = 2.5 + uniform_dist_(rng_); c2 = 0.5 + uniform_dist_(rng_); break;
+    }
+    omega = std::clamp(omega, 0.1, 1.0);
+    c1 = std::clamp(c1, 0.0, 4.0);
+    c2 = std::clamp(c2, 0.0, 4.0);
+}
+
+// quantumPSOUpdate (.cpp:620-652): attractor between personal and global best, jump length from the mean-best distance
+void ParticleSwarmOptimization::quantumPSOUpdate(int i, const std::vector<double>& mean_best, int iter, std::mt19937& rng) {
+    std::uniform_real_distribution<> U(0.0, 1.0);
+    double* p = pos_.data() + static_cast<size_t>(i) * n_;
+    const double* pb = pbest_.data() + static_cast<size_t>(i) * n_;
+    const double phi = U(rng);
+    const double beta = quantum_beta_ * (1.0 - 0.5 * static_cast<double>(iter) / iterations_);
+    for (int k = 0; k < n_; ++k) {
+        const size_t kk = static_cast<size_t>(k);
+        const double attractor = phi * pb[k] + (1 - phi) * gbest_[kk];
+        const double u = U(rng);
+        const double L = 2.0 * beta * std::abs(mean_best[kk] - p[k]);
+        if (U(rng) < 0.5) p[k] = attractor + L * std::log(1.0 / u);
+        else p[k] = attractor - L * std::log(1.0 / u);
+        p[k] = std::clamp(p[k], lb_[kk], ub_[kk]);
+    }
+}
+
+// generateLevyNumber (.cpp:917-934): Mantegna's algorithm; a fresh normal_distribution per number, as in the reference
+double ParticleSwarmOptimization::generateLevyNumber(std::mt19937& rng) const {
+    const double PI = 3.14159265358979323846;
+    const double sigma_u = std::pow(std::tgamma(1 + levy_alpha_) * std::sin(PI * levy_alpha_ / 2) /
+                                        (std::tgamma((1 + levy_alpha_) / 2) * levy_alpha_ * std::pow(2, (levy_alpha_ - 1) / 2)),
+                                    1.0 / levy_alpha_);
+    std::normal_distribution<> local_normal(0.0, 1.0);
+    const double u = local_normal(rng) * sigma_u;
+    const double v = std::max(std::abs(local_normal(rng)), 1e-10);
+    const double levy_step = u / std::pow(v, 1.0 / levy_alpha_);
+    return std::clamp(levy_step, -100.0, 100.0);
+}
+
+// levyFlightUpdate (.cpp:654-677): standard update towards the GLOBAL best, then an occasional heavy-tailed jump
+void ParticleSwarmOptimization::levyFlightUpdate(int i, double omega, double c1, double c2, std::mt19937& rng) {
+    standardPSOUpdate(i, gbest_.data(), omega, c1, c2, rng);
+    std::uniform_real_distribution<> U(0.0, 1.0);
+    const double levy_prob = 0.1 * (1.0 + success_rate_[static_cast<size_t>(i)]);
+    if (U(rng) < levy_prob) {
+        std::vector<double> levy(static_cast<size_t>(n_));
+        for (auto& l : levy) l = generateLevyNumber(rng);
+        const double step_scale = 0.01 * (1.0 - stagnation_counter_ / static_cast<double>(max_stagnation_));
+        double* p = pos_.data() + static_cast<size_t>(i) * n_;
+        for (int k = 0; k < n_; ++k) {
+            const size_t kk = static_cast<size_t>(k);
+            const double scale = step_scale * (ub_[kk] - lb_[kk]);
+            p[k] += scale * levy[kk];
+            p[k] = std::clamp(p[k], lb_[kk], ub_[kk]);
+        }
+    }
+}
+
+void ParticleSwarmOptimization::updateParticles(int iter, IObjectiveFunction& f) {   // .cpp:330-425
+    double omega = omega_start_, c1 = c1_initial_, c2 = c2_initial_;
+    if (use_adaptive_parameters_) adaptParameters(estimateEvolutionaryState(), iter, omega, c1, c2);
+    else coefficients(iter, omega, c1, c2);
+    std::vector<double> mean_best;
+    if (variant_ == PSOVariant::QUANTUM || variant_ == PSOVariant::HYBRID) {          // calculateMeanBestPosition (.cpp:936-947)
+        mean_best.assign(static_cast<size_t>(n_), 0.0);
+        for (int i = 0; i < local_; ++i)
+            for (int k = 0; k < n_; ++k) mean_best[static_cast<size_t>(k)] += pbest_[static_cast<size_t>(i) * n_ + static_cast<size_t>(k)];
+        for (auto& m : mean_best) m /= swarm_size_;
+    }
+    const std::vector<uint32_t> seeds = drawSeeds();
+    // getNeighborhoodBest (.cpp:816-834) for every particle from the personal bests at the start of the iteration
+    std::vector<int> lbest_of;
+    std::vector<double> lbest_rows;
+    if (topology_ != TopologyType::GLOBAL_BEST) {
+        lbest_of.resize(static_cast<size_t>(local_));
+        for (int i = 0; i < local_; ++i) {
+            int best = i;
+            double best_value = pbest_val_[static_cast<size_t>(i)];
+            for (int nb : getNeighbors(i))
+                if (nb >= 0 && nb < swarm_size_ && pbest_val_[static_cast<size_t>(nb)] > best_value) { best_value = pbest_val_[static_cast<size_t>(nb)]; best = nb; }
+            lbest_of[static_cast<size_t>(i)] = best;
+        }
+        lbest_rows = pbest_;           // snapshot: an update below never changes pbest_, but keep the read side explicit
+    }
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < local_; ++i) {
+        std::mt19937 local_rng(seeds[static_cast<size_t>(i)]);
+        std::uniform_real_distribution<> local_uniform(0.0, 1.0);
+        const double* lbest = (topology_ == TopologyType::GLOBAL_BEST) ? gbest_.data()
+                                                                       : lbest_rows.data() + static_cast<size_t>(lbest_of[static_cast<size_t>(i)]) * n_;
+        switch (variant_) {
+            case PSOVariant::STANDARD:
+            case PSOVariant::ADAPTIVE:                                   // standard update with the adapted coefficients
+                standardPSOUpdate(i, lbest, omega, c1, c2, local_rng);
+                break;
+            case PSOVariant::QUANTUM:
+                quantumPSOUpdate(i, mean_best, iter, local_rng);
+                break;
+            case PSOVariant::LEVY_FLIGHT:
+                levyFlightUpdate(i, omega, c1, c2, local_rng);
+                break;
+            case PSOVariant::HYBRID: {                                   // by success rate; the uniform is drawn only when its test is reached
+                const double sr = success_rate_[static_cast<size_t>(i)];
+                if (sr < 0.3 && local_uniform(local_rng) < 0.5) levyFlightUpdate(i, omega, c1, c2, local_rng);
+                else if (sr > 0.7 && local_uniform(local_rng) < 0.3) quantumPSOUpdate(i, mean_best, iter, local_rng);
+                else standardPSOUpdate(i, lbest, omega, c1, c2, local_rng);
+                break;
+            }
+        }
+    }
+    evaluateSwarm(f, 0, cur_fit_);
+    for (int i = 0; i < local_; ++i) {
+        const size_t ii = static_cast<size_t>(i);
+        total_updates_[ii]++;
+        if (cur_fit_[ii] > pbest_val_[ii]) {
+            pbest_val_[ii] = cur_fit_[ii];
+            std::copy(pos_.begin() + static_cast<std::ptrdiff_t>(i) * n_, pos_.begin() + static_cast<std::ptrdiff_t>(i + 1) * n_, pbest_.begin() + static_cast<std::ptrdiff_t>(i) * n_);
+            success_count_[ii]++;
+        }
+        success_rate_[ii] = (total_updates_[ii] > 0) ? static_cast<double>(success_count_[ii]) / total_updates_[ii] : 0.0;
+    }
+}
+
+// applyElitistLearningStrategy (.cpp:705-742): up to three Gaussian trials around the best particle's POSITION with a
+// halving radius; the first improvement of its personal best is taken.
+void ParticleSwarmOptimization::applyElitistLearningStrategy(int best, IObjectiveFunction& f) {
+    const size_t b = static_cast<size_t>(best);
+    const double* p = pos_.data() + b * n_;
+    double sigma_scale = 0.1 * std::exp(-2.0 * success_rate_[b]);
+    std::vector<double> trials(static_cast<size_t>(3) * n_), fit(3);
+    std::mt19937 rng_after[3];
+    std::normal_distribution<> dist_after[3];
+    for (int a = 0; a < 3; ++a) {
+        for (int k = 0; k < n_; ++k) {
+            const size_t kk = static_cast<size_t>(k);
+            const double sigma = sigma_scale * (ub_[kk] - lb_[kk]);
+            trials[static_cast<size_t>(a) * n_ + kk] = std::clamp(p[k] + sigma * normal_dist_(rng_), lb_[kk], ub_[kk]);
+        }
+        rng_after[a] = rng_; dist_after[a] = normal_dist_;
+        sigma_scale *= 0.5;
+    }
+    f.calculateBatch(trials.data(), 3, n_, fit.data());
+    evaluations_ += 3;
+    for (int a = 0; a < 3; ++a) {
+        ++els_trials_;
+        if (fit[static_cast<size_t>(a)] > pbest_val_[b]) {
+            std::copy(trials.begin() + static_cast<std::ptrdiff_t>(a) * n_, trials.begin() + static_cast<std::ptrdiff_t>(a + 1) * n_, pos_.begin() + static_cast<std::ptrdiff_t>(best) * n_);
+            std::copy(trials.begin() + static_cast<std::ptrdiff_t>(a) * n_, trials.begin() + static_cast<std::ptrdiff_t>(a + 1) * n_, pbest_.begin() + static_cast<std::ptrdiff_t>(best) * n_);
+            pbest_val_[b] = fit[static_cast<size_t>(a)];
+            cur_fit_[b] = fit[static_cast<size_t>(a)];
+            rng_ = rng_after[a]; normal_dist_ = dist_after[a];          // the reference stops drawing here
+            break;
+        }
+    }
+}
+
+// restartSwarm (.cpp:744-814): keep the best `keep_best_count` particles, re-seed the others around the elites (70 % of the
+// coordinates) or uniformly in bounds (30 %)
+void ParticleSwarmOptimization::restartSwarm(IObjectiveFunction& f, int keep_best_count) {
+    ++restarts_;
+    std::vector<int> order(static_cast<size_t>(local_));
+    for (int i = 0; i < local_; ++i) order[static_cast<size_t>(i)] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return pbest_val_[static_cast<size_t>(a)] > pbest_val_[static_cast<size_t>(b)]; });
+    permuteSwarm(order);
+    const int n_elite = std::min(keep_best_count, swarm_size_);
+    const std::vector<double> elite(pos_.begin(), pos_.begin() + static_cast<std::ptrdiff_t>(n_elite) * n_);
+    const std::vector<uint32_t> seeds = drawSeeds();
+#pragma omp parallel for schedule(static)
+    for (int i = keep_best_count; i < local_; ++i) {
+        std::mt19937 local_rng(seeds[static_cast<size_t>(i)]);
+        std::uniform_real_distribution<> U(0.0, 1.0);
+        std::normal_distribution<> Nrm(0.0, 1.0);                        // one object per particle: its cached second value carries over
+        const double* el = elite.data() + static_cast<size_t>(i % n_elite) * n_;
+        double* p = pos_.data() + static_cast<size_t>(i) * n_;
+        double* v = vel_.data() + static_cast<size_t>(i) * n_;
+        for (int k = 0; k < n_; ++k) {
+            const size_t kk = static_cast<size_t>(k);
+            if (U(local_rng) < 0.7) {
+                const double range = ub_[kk] - lb_[kk];
+                const double sigma = 0.3 * range * (1.0 + 0.5 * U(local_rng));
+                p[k] = el[k] + sigma * Nrm(local_rng);
+            } else {
+                p[k] = lb_[kk] + U(local_rng) * (ub_[kk] - lb_[kk]);
+            }
+            p[k] = std::clamp(p[k], lb_[kk], ub_[kk]);
+            const double vmax = 0.2 * (ub_[kk] - lb_[kk]);
+            v[k] = -vmax + 2 * vmax * U(local_rng);
+        }
+    }
+    evaluateSwarm(f, keep_best_count, cur_fit_);
+    for (int i = keep_best_count; i < local_; ++i) {
+        const size_t ii = static_cast<size_t>(i);
+        std::copy(pos_.begin() + static_cast<std::ptrdiff_t>(i) * n_, pos_.begin() + static_cast<std::ptrdiff_t>(i + 1) * n_, pbest_.begin() + static_cast<std::ptrdiff_t>(i) * n_);
+        pbest_val_[ii] = cur_fit_[ii];
+        success_count_[ii] = 0; total_updates_[ii] = 0; success_rate_[ii] = 0.0;
+    }
+    gbest_value_ = pbest_val_[0];                                        // the sorted swarm's first particle, unconditionally (.cpp:806-807)
+    gbest_.assign(pbest_.begin(), pbest_.begin() + n_);
+}
+
+void ParticleSwarmOptimization::runHostLoop(int start_iter, double previous_gbest, IObjectiveFunction& f) {   // .cpp:131-182
+    for (int iter = start_iter; iter < iterations_; ++iter) {
+        if (std::abs(gbest_value_ - previous_gbest) < restart_threshold_) {
+            stagnation_counter_++;
+            if (stagnation_counter_ > max_stagnation_) {
+                restartSwarm(f);
+                stagnation_counter_ = 0;
+            }
+        } else {
+            stagnation_counter_ = 0;
+        }
+        previous_gbest = gbest_value_;
+        updateParticles(iter, f);
+        rescanGlobalBest();
+        if ((variant_ == PSOVariant::ADAPTIVE || variant_ == PSOVariant::HYBRID) && (iter % 5 == 0)) {
+            const int best = static_cast<int>(std::max_element(pbest_val_.begin(), pbest_val_.end()) - pbest_val_.begin());   // first maximum
+            applyElitistLearningStrategy(best, f);
+            if (pbest_val_[static_cast<size_t>(best)] > gbest_value_) {
+                gbest_value_ = pbest_val_[static_cast<size_t>(best)];
+                gbest_.assign(pbest_.begin() + static_cast<std::ptrdiff_t>(best) * n_, pbest_.begin() + static_cast<std::ptrdiff_t>(best + 1) * n_);
+            }
+        }
+    }
+}
+
+double ParticleSwarmOptimization::swarmDiversity() const {
+    if (local_ == 0) return 0.0;
+    std::vector<double> centroid(static_cast<size_t>(n_), 0.0);
+    for (int i = 0; i < local_; ++i)
+        for (int k = 0; k < n_; ++k) centroid[static_cast<size_t>(k)] += pos_[static_cast<size_t>(i) * n_ + static_cast<size_t>(k)];
+    for (auto& c : centroid) c /= swarm_size_;
+    double avg = 0.0, mx = 0.0;
+    for (int i = 0; i < local_; ++i) {
+        double d2 = 0.0;
+        for (int k = 0; k < n_; ++k) { const double d = pos_[static_cast<size_t>(i) * n_ + static_cast<size_t>(k)] - centroid[static_cast<size_t>(k)]; d2 += d * d; }
+        const double dist = std::sqrt(d2);
+        avg += dist;
+        mx = std::max(mx, dist);
+    }
+    avg /= swarm_size_;
+    return (mx > 0) ? avg / mx : 0.0;
+}
+
+OptimizationResult ParticleSwarmOptimization::finish() const {
     OptimizationResult r;
     r.bestParameters = VectorXd::FromPointer(gbest_.data(), n_);
     r.bestObjectiveValue = gbest_value_;
@@ -499,6 +932,60 @@ OptimizationResult ParticleSwarmOptimization::optimize(const VectorXd& initial, 
     r.finalCovariance *= 1.0 / static_cast<double>(std::max(local_ - 1, 1));
     r.finalCovariance += 1e-6 * MatrixXd::Identity(n_, n_);
     return r;
+}
+
+OptimizationResult ParticleSwarmOptimization::optimize(const VectorXd& initial, IObjectiveFunction& f, IParameterManager& pm) {
+    const int n = static_cast<int>(pm.getParameterCount());
+    const VectorXd* init = initial.size() == n ? &initial : nullptr;
+    const int local = local_count_setting_ >= 0 ? local_count_setting_ : swarm_size_ - static_cast<int>(particle_offset_);
+    const bool whole = particle_offset_ == 0 && local == swarm_size_;
+    auto* device_objective = dynamic_cast<SEPAIHRDObjectiveFunction*>(&f);
+    if (!whole) {
+        // one shard of a swarm run on its own (the sharded drivers exchange the global best between the calls of the
+        // step-wise form instead): STANDARD / GLOBAL_BEST only, no restart
+        begin(init, pm);
+        auto evaluate = [&]() {
+            std::vector<double> fit(static_cast<size_t>(local_));
+            f.calculateBatch(pos_.data(), local_, n_, fit.data());
+            const auto best = tell(fit.data());
+            if (best.second >= 0) setGlobalBest(best.first, personalBest(best.second));
+        };
+        evaluate();
+        for (int iter = 0; iter < iterations_; ++iter) { step(iter); evaluate(); }
+        return finish();
+    }
+    if (device_objective != nullptr && device_resident_ && isBasicSwarm()) {
+        // the swarm stays in HBM: per iteration one seed per particle goes down, one (value, index, position) triple comes
+        // back.  The stagnation test of the main loop (.cpp:133-146) runs here on the host; when it asks for a restart the
+        // swarm is read back once and the run continues in the host-resident engine.
+        beginDevice(init, pm, device_objective->device().get());
+        std::vector<double> best_pos(static_cast<size_t>(n));
+        auto evaluate = [&]() {
+            const auto best = evaluateDevice(best_pos.data());
+            if (best.second >= 0) setGlobalBest(best.first, best_pos.data());
+        };
+        evaluate();
+        double previous_gbest = -std::numeric_limits<double>::infinity();
+        for (int iter = 0; iter < iterations_; ++iter) {
+            const bool stagnant = std::abs(gbest_value_ - previous_gbest) < restart_threshold_;
+            if (stagnant && stagnation_counter_ + 1 > max_stagnation_) {
+                fetchPersonalBests(true);
+                cur_fit_ = pbest_val_;             // current fitness is only read by the adaptive variants, which never start on the device
+                sepaihrd_swarm_destroy(dev_swarm_); dev_swarm_ = nullptr;
+                runHostLoop(iter, previous_gbest, f);
+                return finish();
+            }
+            stagnation_counter_ = stagnant ? stagnation_counter_ + 1 : 0;
+            previous_gbest = gbest_value_;
+            stepDevice(iter);
+            evaluate();
+        }
+        fetchPersonalBests(false);                 // the personal bests feed the covariance hand-off; positions stay on the device
+        return finish();
+    }
+    initializeSwarmFull(init, f, pm);
+    runHostLoop(0, -std::numeric_limits<double>::infinity(), f);
+    return finish();
 }
 
 // =====================================================================================================================

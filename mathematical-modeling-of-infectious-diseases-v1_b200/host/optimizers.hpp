@@ -3,8 +3,12 @@
 //
 //   MetropolisHastingsSampler   src/sir_age_structured/optimizers/MetropolisHastingsSampler.cpp:201-412 (one chain)
 //                               -> n_chains independent chains of exactly that algorithm, stepped in lockstep
-//   ParticleSwarmOptimization   src/model/optimizers/ParticleSwarmOptimizer.cpp:106-247, 249-328, 330-425, 576-618
-//                               -> STANDARD update, GLOBAL_BEST topology, linear omega/c1/c2 schedules
+//   ParticleSwarmOptimization   src/model/optimizers/ParticleSwarmOptimizer.cpp:10-948 (whole class)
+//                               -> all five variants (STANDARD, QUANTUM, ADAPTIVE, LEVY_FLIGHT, HYBRID), all four topologies
+//                                  (GLOBAL_BEST, LOCAL_BEST ring, VON_NEUMANN grid, RANDOM_DYNAMIC), opposition-based
+//                                  initialisation, evolutionary-state parameter adaptation, stagnation restart, elitist
+//                                  learning; every swarm evaluation is ONE batch.  The STANDARD / GLOBAL_BEST swarm with
+//                                  linear schedules additionally has a step-wise (shardable) and a device-resident form
 //   HillClimbingOptimizer       src/sir_age_structured/optimizers/HillClimbingOptimizer.cpp:38-109, 131-352
 //   ModelCalibrator             src/sir_age_structured/ModelCalibrator.cpp:22-168 (two phases + covariance hand-off)
 //   SEPAIHRDModelCalibration    src/model/SEPAIHRDModelCalibration.cpp:24-236
@@ -129,9 +133,59 @@ public:
     ParticleSwarmOptimization(const ParticleSwarmOptimization&) = delete;
     ParticleSwarmOptimization& operator=(const ParticleSwarmOptimization&) = delete;
 
+
+    // ---- the reference's enums (ParticleSwarmOptimizer.hpp) and the state they drive ---------------------------------
+    enum class PSOVariant { STANDARD = 0, QUANTUM = 1, ADAPTIVE = 2, LEVY_FLIGHT = 3, HYBRID = 4 };
+    enum class TopologyType { GLOBAL_BEST = 0, LOCAL_BEST = 1, VON_NEUMANN = 2, RANDOM_DYNAMIC = 3 };
+    enum class EvolutionaryState { EXPLORATION, EXPLOITATION, CONVERGENCE, JUMPING_OUT };
+    PSOVariant variant() const { return variant_; }
+    TopologyType topology() const { return topology_; }
+    // true when the configured swarm is the STANDARD update on the GLOBAL_BEST topology with linear coefficient schedules
+    // and no opposition-based initialisation: the form the step-wise and the device-resident interfaces implement
+    bool isBasicSwarm() const;
+    int restartCount() const { return restarts_; }                        // stagnation restarts of the last optimize()
+    int elitistTrials() const { return els_trials_; }                     // elitist-learning trial evaluations of the last optimize()
+    long evaluations() const { return evaluations_; }                     // objective evaluations of the last optimize()
+    // getNeighbors (.cpp:836-905) for the configured topology; RANDOM_DYNAMIC draws from the master generator
+    std::vector<int> getNeighbors(int particle_idx);
+    // whole-swarm state of the last optimize() on the host path (tests, diagnostics)
+    const std::vector<double>& personalBestValues() const { return pbest_val_; }
+    const std::vector<double>& currentFitness() const { return cur_fit_; }
+    double swarmDiversity() const;                                        // calculateSwarmDiversity (.cpp:679-703)
+
 private:
     int iterations_ = 100, swarm_size_ = 30, report_interval_ = 10;
     double omega_start_ = 0.9, omega_end_ = 0.4, c1_initial_ = 2.5, c1_final_ = 0.5, c2_initial_ = 0.5, c2_final_ = 2.5;
+    // defaults of the reference class (ParticleSwarmOptimizer.hpp:201-236)
+    PSOVariant variant_ = PSOVariant::ADAPTIVE;
+    TopologyType topology_ = TopologyType::GLOBAL_BEST;
+    bool use_opposition_learning_ = true, use_parallel_ = false, use_adaptive_parameters_ = true, log_evolutionary_state_ = true;
+    double diversity_threshold_ = 0.1, restart_threshold_ = 1e-6, quantum_beta_ = 1.0, levy_alpha_ = 1.5;
+    int stagnation_counter_ = 0, max_stagnation_ = 50;
+    std::uniform_real_distribution<> uniform_dist_{0.0, 1.0};
+    std::normal_distribution<> normal_dist_{0.0, 1.0};
+    std::vector<double> cur_fit_, success_rate_;
+    std::vector<int> success_count_, total_updates_;
+    int restarts_ = 0, els_trials_ = 0;
+    long evaluations_ = 0;
+    // the whole-swarm engine behind optimize() (host-resident arrays, one calculateBatch per swarm evaluation)
+    void evaluateSwarm(IObjectiveFunction& f, int first, std::vector<double>& fitness);
+    void initializeSwarmFull(const VectorXd* init, IObjectiveFunction& f, IParameterManager& pm);
+    void oppositionBasedInitialization();
+    void permuteSwarm(const std::vector<int>& order);
+    void runHostLoop(int start_iter, double previous_gbest, IObjectiveFunction& f);
+    void restartSwarm(IObjectiveFunction& f, int keep_best_count = 3);
+    void updateParticles(int iter, IObjectiveFunction& f);
+    double calculateEvolutionaryFactor() const;
+    EvolutionaryState estimateEvolutionaryState() const;
+    void adaptParameters(EvolutionaryState state, int iter, double& omega, double& c1, double& c2);
+    void standardPSOUpdate(int i, const double* lbest, double omega, double c1, double c2, std::mt19937& rng);
+    void quantumPSOUpdate(int i, const std::vector<double>& mean_best, int iter, std::mt19937& rng);
+    void levyFlightUpdate(int i, double omega, double c1, double c2, std::mt19937& rng);
+    double generateLevyNumber(std::mt19937& rng) const;
+    void applyElitistLearningStrategy(int best, IObjectiveFunction& f);
+    void rescanGlobalBest();
+    OptimizationResult finish() const;
     long particle_offset_ = 0;
     int local_count_setting_ = -1;
     bool has_seed_ = false;
@@ -145,6 +199,7 @@ private:
     bool device_resident_ = true;
     sepaihrd_swarm* dev_swarm_ = nullptr;
     void setupRun(IParameterManager& pm);
+    void drawInitialSwarm(const VectorXd* initialParameters);
     std::vector<uint32_t> drawSeeds();
     void coefficients(int iter, double& omega, double& c1, double& c2) const;
 };

@@ -56,6 +56,9 @@ SIGNATURES = {
     "sepaihrd_host_pso_evaluate_device": (C.c_int32, [_vp, _dp, _i32p, _vp]),
     "sepaihrd_host_pso_step_device": (C.c_int32, [_vp, C.c_int32]),
     "sepaihrd_host_pso_fetch": (C.c_int32, [_vp]),
+    "sepaihrd_host_pso_run": (C.c_int32, [_vp, BATCH_FN, _vp, _vp, _vp, _dp, _vp]),
+    "sepaihrd_host_pso_values": (C.c_int32, [_vp, _vp, _vp]),
+    "sepaihrd_host_pso_neighbors": (C.c_int32, [_vp, C.c_int32, _vp, C.c_int32]),
     "sepaihrd_host_pso_destroy": (None, [_vp]),
     "sepaihrd_host_optimize": (C.c_int32, [C.c_char_p, _vp, C.c_int32, _keys, _vp, BATCH_FN, _vp, _vp, _vp, _dp, _i64p]),
     "sepaihrd_host_calibrate": (C.c_int32, [C.c_char_p, _vp, C.c_int32, _keys, _vp, C.c_int32, _keys, _vp, BATCH_FN, _vp, _vp, _vp, _dp, _i64p, _dp]),
@@ -198,11 +201,19 @@ class MultiChainMH:
             self._h = None
 
 
+# the swarm the step-wise (shardable) and device-resident interfaces implement; the class defaults are the reference's
+# (ADAPTIVE variant, opposition learning, adaptive parameters: ParticleSwarmOptimizer.hpp:201-213)
+BASIC_SWARM = dict(variant=0, topology=0, use_opposition_learning=0, use_adaptive_parameters=0)
+
+
 class Swarm:
-    """Step-wise handle on the batched ParticleSwarmOptimization; this process owns one shard of particles."""
+    """Handle on the batched ParticleSwarmOptimization.  Step-wise (begin / tell / step and the device forms): this process owns
+    one shard of the STANDARD / GLOBAL_BEST swarm -- BASIC_SWARM is the default of this wrapper.  run(): a whole optimize() with
+    any of the reference's variants, topologies and strategies (pass them in ``settings``)."""
 
     def __init__(self, pm: ParameterManager, settings: Dict[str, float]):
         self.L, self.pm = pm.L, pm
+        settings = {**BASIC_SWARM, **settings}
         n, keys, vals = _settings(settings)
         h = C.c_void_p()
         check(self.L.sepaihrd_host_pso_create(pm._h, n, keys, vals.ctypes.data, C.byref(h)))
@@ -257,17 +268,39 @@ class Swarm:
         """Copy positions / velocities / personal bests back from the device (positions() is then current)."""
         check(self.L.sepaihrd_host_pso_fetch(self._h))
 
+    # ---- whole runs: every variant / topology / strategy of the reference class ---------------------------------------
+    def run(self, evaluate: Callable[[np.ndarray], np.ndarray], initial=None):
+        """ParticleSwarmOptimization::optimize with ``evaluate`` ([B, P] -> [B]) as the objective.
+        Returns (best position, best value, dict(evaluations, restarts, elitist_trials, diversity))."""
+        P = self.pm.n
+        cb = BATCH_FN(_batch_callback(evaluate, P))
+        x0 = None if initial is None else _c64(initial)
+        best = np.empty(P); val = C.c_double(); stats = np.zeros(4)
+        check(self.L.sepaihrd_host_pso_run(self._h, cb, None, None if x0 is None else x0.ctypes.data, best.ctypes.data, C.byref(val),
+                                           stats.ctypes.data))
+        return best, val.value, dict(evaluations=int(stats[0]), restarts=int(stats[1]), elitist_trials=int(stats[2]), diversity=float(stats[3]))
+
+    def values(self, swarm_size: int):
+        """(personal-best values, current fitness) of the swarm after run()."""
+        pb = np.empty(swarm_size); cf = np.empty(swarm_size)
+        check(self.L.sepaihrd_host_pso_values(self._h, pb.ctypes.data, cf.ctypes.data))
+        return pb, cf
+
+    def neighbors(self, particle: int) -> List[int]:
+        """getNeighbors of the configured topology (RANDOM_DYNAMIC draws from the master generator on every call)."""
+        out = np.empty(64, dtype=np.int32)
+        k = self.L.sepaihrd_host_pso_neighbors(self._h, int(particle), out.ctypes.data, 64)
+        if k < 0:
+            raise HostError(self.L.sepaihrd_host_last_error().decode())
+        return [int(v) for v in out[:min(k, 64)]]
+
     def __del__(self):
         if getattr(self, "_h", None):
             self.L.sepaihrd_host_pso_destroy(self._h)
             self._h = None
 
 
-def optimize(algorithm: str, pm: ParameterManager, settings: Dict[str, float], evaluate: Callable[[np.ndarray], np.ndarray], initial):
-    """IOptimizationAlgorithm::optimize ("mh", "pso", "hill") with ``evaluate`` ([B, P] -> [B]) as the objective."""
-    L = pm.L
-    P = pm.n
-
+def _batch_callback(evaluate, P):
     def _cb(_user, params, B, ld, out):
         try:
             x = np.ctypeslib.as_array(params, shape=(B, ld))[:, :P]
@@ -277,8 +310,14 @@ def optimize(algorithm: str, pm: ParameterManager, settings: Dict[str, float], e
             import traceback
             traceback.print_exc()
             return 1
+    return _cb
 
-    cb = BATCH_FN(_cb)
+
+def optimize(algorithm: str, pm: ParameterManager, settings: Dict[str, float], evaluate: Callable[[np.ndarray], np.ndarray], initial):
+    """IOptimizationAlgorithm::optimize ("mh", "pso", "hill") with ``evaluate`` ([B, P] -> [B]) as the objective."""
+    L = pm.L
+    P = pm.n
+    cb = BATCH_FN(_batch_callback(evaluate, P))
     n, keys, vals = _settings(settings)
     x0 = _c64(initial)
     best = np.empty(P); val = C.c_double(); nev = C.c_int64()

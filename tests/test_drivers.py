@@ -166,13 +166,17 @@ def test_whole_run_optimizers_improve_the_oracle_likelihood(host, problem, oracl
     best, val, nev = host.optimize("hill", pm, dict(iterations=3, cloud_size=16, seed=4), ev, x0)
     assert val >= f0 and nev >= 1 + 3 * 16
     np.testing.assert_allclose(ev(best[None])[0], val, rtol=1e-13)
-    best, val, nev = host.optimize("pso", pm, dict(iterations=3, swarm_size=12, seed=4), ev, x0)
+    best, val, nev = host.optimize("pso", pm, dict(iterations=3, swarm_size=12, seed=4, **host.BASIC_SWARM), ev, x0)
     assert val >= f0 and nev == 12 * 4                                  # particle 0 starts at the initial point
+    # the class defaults are the reference's: ADAPTIVE variant, opposition-based initialisation (the swarm is scored twice),
+    # adaptive coefficients, elitist learning after iteration 0 (3 trials)
+    best, val, nev = host.optimize("pso", pm, dict(iterations=3, swarm_size=12, seed=4), ev, x0)
+    assert val >= f0 and nev == 12 * 2 + 3 * 12 + 3
     pm.set_mode(1)
     best, val, nev = host.optimize("mh", pm, dict(mcmc_iterations=6, burn_in=6, n_chains=3, seed=4), ev, x0)
     assert val >= f0 and nev == 1 + 5 * 3
     with pytest.raises(host.HostError):
-        host.optimize("pso", pm, dict(iterations=1, swarm_size=4, variant=2), ev, x0)      # only STANDARD is built
+        host.optimize("pso", pm, dict(iterations=1, swarm_size=4, variant=5), ev, x0)      # "variant must be between 0 and 4"
 
 
 def _spawn(what, tmp_path, world, port):

@@ -127,6 +127,34 @@ def test_pso_swarm_reaches_the_same_global_best_on_gpu_and_oracle(problem, oracl
     assert ref["trace"][-1] >= ref["trace"][0]
 
 
+def test_device_resident_swarm_hands_over_to_the_host_engine_on_a_stagnation_restart(host, problem):
+    """restart_threshold = 1e300 makes every iteration "stagnant", so with max_stagnation = 2 the main loop restarts the swarm at
+    iteration 3 (ParticleSwarmOptimizer.cpp:133-146).  The device-resident swarm is read back at that point and the run continues
+    in the host engine; started on the host it must visit the same states (the device swarm is bit-identical to the host swarm)."""
+    s1 = dict(iterations=6, swarm_size=96, seed=3, restart_threshold=1e300, max_stagnation=2, **host.BASIC_SWARM)
+    s2 = dict(mcmc_iterations=4, burn_in=4, n_chains=8, seed=5)
+    m = host.HostModel(problem)
+    on_device = m.calibrate("pso", dict(s1, device_resident=1), s2)
+    on_host = m.calibrate("pso", dict(s1, device_resident=0), s2)
+    no_restart = m.calibrate("pso", dict(s1, device_resident=1, max_stagnation=50), s2)
+    m.close()
+    assert on_device[1] == on_host[1]
+    np.testing.assert_array_equal(on_device[0], on_host[0])
+    assert not np.array_equal(no_restart[0], on_device[0])        # the restart did change the run
+
+
+def test_reference_default_swarm_configuration_runs_on_the_device_objective(host, problem, oracle):
+    """The shipped pso_settings.txt: von Neumann topology, opposition-based initialisation, adaptive coefficients -- the
+    whole-swarm engine with every evaluation as one device batch."""
+    m = host.HostModel(problem)
+    f0 = oracle.eval_batch(problem.base_params()[None])[0][0]
+    s1 = dict(iterations=4, swarm_size=128, seed=3, variant=0, topology=2, use_opposition_learning=1, use_adaptive_parameters=1, max_stagnation=20)
+    best, val, ns = m.calibrate("pso", s1, dict(mcmc_iterations=3, burn_in=3, n_chains=8, seed=5))
+    m.close()
+    assert val >= f0 * (1 - 1e-12)
+    assert _rel(oracle.eval_batch(best[None])[0][0], val) < 1e-8
+
+
 def test_model_calibration_mirror_runs_both_phases(host, problem, oracle):
     """SEPAIHRDModelCalibration::runPSOMCMC / runHillClimbingMCMC end to end on the device (small settings)."""
     m = host.HostModel(problem)
