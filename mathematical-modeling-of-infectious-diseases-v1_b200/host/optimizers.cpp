@@ -3,6 +3,8 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <iostream>
 
 namespace epidemic {
@@ -370,6 +372,12 @@ void ParticleSwarmOptimization::coefficients(int iter, double& omega, double& c1
 }
 
 namespace {
+// the reference's per-iteration progress line (.cpp:184-211) goes to its Logger; here it is printed to stderr when the
+// environment variable SEPAIHRD_PSO_REPORT is set (report_interval applies)
+bool report_enabled() {
+    static const bool on = std::getenv("SEPAIHRD_PSO_REPORT") != nullptr;
+    return on;
+}
 void require_basic(const ParticleSwarmOptimization& s, const char* who) {
     if (!s.isBasicSwarm())
         throw std::invalid_argument(std::string(who) + ": the step-wise / device-resident swarm is the STANDARD variant on the GLOBAL_BEST topology "
@@ -902,7 +910,14 @@ void ParticleSwarmOptimization::runHostLoop(int start_iter, double previous_gbes
                 gbest_.assign(pbest_.begin() + static_cast<std::ptrdiff_t>(best) * n_, pbest_.begin() + static_cast<std::ptrdiff_t>(best + 1) * n_);
             }
         }
+        reportProgress(iter, "host");
     }
+}
+
+void ParticleSwarmOptimization::reportProgress(int iter, const char* where) const {
+    if (!report_enabled() || !((iter + 1) % report_interval_ == 0 || iter == iterations_ - 1)) return;
+    std::fprintf(stderr, "[PSO %s] Iteration %d/%d | Best: %.17g | Stagnation: %d | Restarts: %d\n", where, iter + 1, iterations_, gbest_value_,
+                 stagnation_counter_, restarts_);
 }
 
 double ParticleSwarmOptimization::swarmDiversity() const {
@@ -979,6 +994,7 @@ OptimizationResult ParticleSwarmOptimization::optimize(const VectorXd& initial, 
             previous_gbest = gbest_value_;
             stepDevice(iter);
             evaluate();
+            reportProgress(iter, "device");
         }
         fetchPersonalBests(false);                 // the personal bests feed the covariance hand-off; positions stay on the device
         return finish();

@@ -186,6 +186,7 @@ private:
     void applyElitistLearningStrategy(int best, IObjectiveFunction& f);
     void rescanGlobalBest();
     OptimizationResult finish() const;
+    void reportProgress(int iter, const char* where) const;
     long particle_offset_ = 0;
     int local_count_setting_ = -1;
     bool has_seed_ = false;

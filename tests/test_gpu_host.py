@@ -133,11 +133,12 @@ def test_device_resident_swarm_hands_over_to_the_host_engine_on_a_stagnation_res
     in the host engine; started on the host it must visit the same states (the device swarm is bit-identical to the host swarm)."""
     s1 = dict(iterations=6, swarm_size=96, seed=3, restart_threshold=1e300, max_stagnation=2, **host.BASIC_SWARM)
     s2 = dict(mcmc_iterations=4, burn_in=4, n_chains=8, seed=5)
-    m = host.HostModel(problem)
-    on_device = m.calibrate("pso", dict(s1, device_resident=1), s2)
-    on_host = m.calibrate("pso", dict(s1, device_resident=0), s2)
-    no_restart = m.calibrate("pso", dict(s1, device_resident=1, max_stagnation=50), s2)
-    m.close()
+    def run(**kw):                      # a calibration leaves its result in the model: every run gets a fresh one
+        m = host.HostModel(problem)
+        out = m.calibrate("pso", dict(s1, **kw), s2)
+        m.close()
+        return out
+    on_device, on_host, no_restart = run(device_resident=1), run(device_resident=0), run(device_resident=1, max_stagnation=50)
     assert on_device[1] == on_host[1]
     np.testing.assert_array_equal(on_device[0], on_host[0])
     assert not np.array_equal(no_restart[0], on_device[0])        # the restart did change the run
