@@ -7,8 +7,10 @@
 //   * `--repeats N` and `--jitters N` are each ONE batch call of N parameter sets (calculateBatch) instead of N calls of
 //     calculate(); the jittered sets are the reference's: base_i + sigma_i N(0,1) from std::mt19937(seed) +
 //     std::normal_distribution, set by set, then applyConstraints (:452-460);
-//   * there is no likelihood cache to enable (quirk Q6: a hit may return another vector's value): `--no-cache` and
-//     `--cache-size` are accepted and ignored;
+//   * the likelihood cache is OFF unless `--cache-size N` is given (the reference defaults to a cache of 10000 entries and
+//     takes `--no-cache`; quirk Q6: a hit may return another vector's value, so measurements and parity runs go without).
+//     With a cache, calculate() and every batch of at most N sets consult it like the reference's calculate() does; the cache
+//     statistics line of the reference is printed after each mode;
 //   * `--project-root PATH` names the tree (the reference finds it by walking up from the working directory);
 //   * `--mode pso` and `--chains N` exist in addition (batched callers), and `--json` prints one machine-readable line.
 #include <algorithm>
@@ -37,6 +39,7 @@ struct Args {
     bool useFileIters = false, json = false;
     int hillIters = 200, mcmcIters = 2000, psoIters = 30, chains = 1, swarm = 4096;
     bool psoAsConfigured = false;
+    size_t cacheSize = 0;
 };
 
 void usage(const char* prog) {
@@ -55,8 +58,8 @@ Args parse(int argc, char** argv) {
             return argv[++i];
         };
         if (f == "--help" || f == "-h") { usage(argv[0]); std::exit(0); }
-        else if (f == "--no-cache") {}
-        else if (f == "--cache-size") (void)value();
+        else if (f == "--no-cache") a.cacheSize = 0;
+        else if (f == "--cache-size") a.cacheSize = static_cast<size_t>(std::stoull(value()));
         else if (f == "--repeats") a.repeats = std::stoi(value());
         else if (f == "--jitters") a.jitters = std::stoi(value());
         else if (f == "--seed") a.seed = std::stoi(value());
@@ -140,7 +143,18 @@ int main(int argc, char** argv) {
         const ReferenceProject prj = loadReferenceProject(args.root, args.startDate, args.endDate);
         SEPAIHRDParameterManager pm(prj.model, prj.params_to_calibrate, prj.proposal_sigmas, prj.param_bounds);
         pm.setConstraintMode(args.constraintMode == "mcmc" ? ConstraintMode::MCMC_REFLECT : ConstraintMode::OPTIMIZATION_CLAMP);
-        NullSimulationCache cache;
+        std::unique_ptr<ISimulationCache> cache_owner;
+        SimulationCache* sim_cache = nullptr;
+        if (args.cacheSize > 0) { auto c = std::make_unique<SimulationCache>(args.cacheSize); sim_cache = c.get(); cache_owner = std::move(c); }
+        else cache_owner = std::make_unique<NullSimulationCache>();
+        ISimulationCache& cache = *cache_owner;
+        auto print_cache_stats = [&]() {                                       // printCacheStats, reference harness :260-272
+            if (!sim_cache) return;
+            const size_t calls = sim_cache->getLikelihoodCalls(), hits = sim_cache->getLikelihoodHits();
+            std::printf("Cache stats: size=%zu, get_calls=%zu, hits=%zu (%.2f%%), store_calls=%zu\n", sim_cache->size(), calls, hits,
+                        calls ? 100.0 * static_cast<double>(hits) / static_cast<double>(calls) : 0.0, sim_cache->storeLikelihoodCalls());
+            sim_cache->resetLikelihoodStats();
+        };
         const CalibrationData data = prj.data->toCalibrationData(prj.data_initial_state);
         SEPAIHRDObjectiveFunction objective(prj.model, pm, cache, data, prj.time_points, prj.data_initial_state,
                                             std::make_shared<Dopri5SolverStrategy>(), prj.abs_error, prj.rel_error);
@@ -150,7 +164,7 @@ int main(int argc, char** argv) {
 
         std::cout << "SEPAIHRD objective benchmark (B200 evaluator)\n"
                   << "Parameters: " << P << ", output points: " << prj.time_points.size() << ", data days: " << prj.data->getNumDataPoints() << "\n"
-                  << "Cache enabled: no (batch evaluator; see quirk Q6)\n"
+                  << "Cache enabled: " << (sim_cache ? "yes, capacity " + std::to_string(args.cacheSize) : std::string("no (default here; --cache-size N enables it, quirk Q6)")) << "\n"
                   << "Mode: " << args.mode << "\nConstraint mode: " << args.constraintMode << "\n"
                   << "Data window: " << args.startDate << " .. " << args.endDate << "\n";
         std::map<std::string, double> report;
@@ -205,6 +219,7 @@ int main(int argc, char** argv) {
                 std::printf("Jitter: %d evals => %.3f ms (avg %.4f us/eval, %.4e evals/s; host generation of the sets %.3f ms; sum logL %.12e)\n",
                             args.jitters, jitters_ms, jitters_ms * 1000.0 / args.jitters, args.jitters / jitters_ms * 1e3, gen_ms, jitter_sum);
             std::printf("Objective calls: %lld\n", counting.calls());
+            print_cache_stats();
             report["warmup_value"] = warmup_val; report["repeat_ms"] = repeats_ms; report["jitter_ms"] = jitters_ms;
             report["jitter_sum"] = jitter_sum; report["repeat_sum"] = repeat_sum;
             report["jitter_evals_per_s"] = args.jitters > 0 ? args.jitters / jitters_ms * 1e3 : 0.0;
@@ -222,6 +237,7 @@ int main(int argc, char** argv) {
             const OptimizationResult res = hill.optimize(base, counting, pm);
             const double took = ms_since(t0);
             std::printf("\n--- Hill Climbing ---\nTime: %.3f ms\nObjective calls: %lld\nBest logL: %.12e\n", took, counting.calls(), res.bestObjectiveValue);
+            print_cache_stats();
             report["hill_ms"] = took; report["hill_best"] = res.bestObjectiveValue; report["hill_calls"] = static_cast<double>(counting.calls());
             return res.bestParameters;
         };
@@ -241,6 +257,7 @@ int main(int argc, char** argv) {
             const double took = ms_since(t0);
             std::printf("\n--- MCMC (SA-MH, %d chains) ---\nTime: %.3f ms\nObjective calls: %lld\nBest logL: %.12e\n", args.chains, took, counting.calls(),
                         res.bestObjectiveValue);
+            print_cache_stats();
             report["mcmc_ms"] = took; report["mcmc_best"] = res.bestObjectiveValue; report["mcmc_calls"] = static_cast<double>(counting.calls());
         };
 

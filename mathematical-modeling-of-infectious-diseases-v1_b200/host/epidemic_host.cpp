@@ -473,11 +473,11 @@ SimulationResult AgeSEPAIHRDSimulator::run(const VectorXd& initial_state, const 
 }
 
 // ---- SEPAIHRDObjectiveFunction ------------------------------------------------------------------------------------
-SEPAIHRDObjectiveFunction::SEPAIHRDObjectiveFunction(std::shared_ptr<AgeSEPAIHRDModel> model, IParameterManager& pm, ISimulationCache&,
+SEPAIHRDObjectiveFunction::SEPAIHRDObjectiveFunction(std::shared_ptr<AgeSEPAIHRDModel> model, IParameterManager& pm, ISimulationCache& cache,
                                                      const CalibrationData& data, const std::vector<double>& time_points,
                                                      const VectorXd& initial_state, std::shared_ptr<IOdeSolverStrategy> solver,
                                                      double abs_error, double rel_error)
-    : parameterManager_(pm), model_(std::move(model)) {
+    : parameterManager_(pm), cache_(cache), model_(std::move(model)) {
     const char* src = "SEPAIHRDObjectiveFunction";
     if (!model_) throw InvalidParameterException(src, "Model pointer is null.");
     if (!solver) throw InvalidParameterException(src, "Solver strategy pointer is null.");
@@ -512,13 +512,190 @@ double SEPAIHRDObjectiveFunction::calculate(const VectorXd& parameters) const {
     return out;
 }
 
-void SEPAIHRDObjectiveFunction::calculateBatch(const double* params, int64_t B, int64_t ld, double* out) const {
-    calculateBatch(params, B, ld, out, nullptr, nullptr);
+void SEPAIHRDObjectiveFunction::evaluateRows(const double* params, int64_t B, int64_t ld, double* out, uint32_t* status, int32_t* steps) const {
+    if (sepaihrd_eval_batch(dev_->get(), params, B, ld, out, status, steps) != SEPAIHRD_OK)
+        throw SimulationException("SEPAIHRDObjectiveFunction::calculateBatch", std::string("device evaluation failed: ") + sepaihrd_last_error());
 }
 
 void SEPAIHRDObjectiveFunction::calculateBatch(const double* params, int64_t B, int64_t ld, double* out, uint32_t* status, int32_t* steps) const {
-    if (sepaihrd_eval_batch(dev_->get(), params, B, ld, out, status, steps) != SEPAIHRD_OK)
-        throw SimulationException("SEPAIHRDObjectiveFunction::calculateBatch", std::string("device evaluation failed: ") + sepaihrd_last_error());
+    evaluateRows(params, B, ld, out, status, steps);
+}
+
+void SEPAIHRDObjectiveFunction::calculateBatch(const double* params, int64_t B, int64_t ld, double* out) const {
+    if (B <= 0) return;
+    auto* fast = dynamic_cast<SimulationCache*>(&cache_);
+    const bool uncached = dynamic_cast<NullSimulationCache*>(&cache_) != nullptr || (fast != nullptr && static_cast<size_t>(B) > fast->capacity());
+    if (uncached) return evaluateRows(params, B, ld, out, nullptr, nullptr);
+    // calculate() row by row as far as the cache is concerned (.cpp:63-77): probe, remember the misses, evaluate them as ONE
+    // batch, store what calculate() would have stored (.cpp:227-234).
+    const std::ptrdiff_t P = dev_->numParams();
+    std::vector<size_t> fkey(fast ? static_cast<size_t>(B) : 0);
+    std::vector<std::string> skey(fast ? 0 : static_cast<size_t>(B));
+    std::vector<int64_t> miss, first_of(static_cast<size_t>(B), -1);
+    std::map<std::string, int64_t> seen_s;
+    std::map<size_t, int64_t> seen_f;
+    for (int64_t i = 0; i < B; ++i) {
+        const double* row = params + i * ld;
+        double v = 0.0;
+        bool hit;
+        if (fast) { fkey[static_cast<size_t>(i)] = fast->computeHash(row, P); hit = fast->getLikelihood(fkey[static_cast<size_t>(i)], v); }
+        else { skey[static_cast<size_t>(i)] = cache_.createCacheKey(VectorXd::FromPointer(row, P)); hit = cache_.getLikelihood(skey[static_cast<size_t>(i)], v); }
+        if (hit) { out[i] = v; first_of[static_cast<size_t>(i)] = i; continue; }
+        const auto ins = fast ? seen_f.emplace(fkey[static_cast<size_t>(i)], i).first->second : seen_s.emplace(skey[static_cast<size_t>(i)], i).first->second;
+        if (ins != i) first_of[static_cast<size_t>(i)] = ins;      // the same key earlier in this batch: evaluated once
+        else miss.push_back(i);
+    }
+    if (!miss.empty()) {
+        const int64_t M = static_cast<int64_t>(miss.size());
+        std::vector<double> rows, vals(static_cast<size_t>(M));
+        std::vector<uint32_t> st(static_cast<size_t>(M));
+        const double* src = params;
+        int64_t src_ld = ld;
+        if (M != B) {                                              // gather the missing rows
+            rows.resize(static_cast<size_t>(M) * static_cast<size_t>(P));
+            for (int64_t j = 0; j < M; ++j) std::copy(params + miss[static_cast<size_t>(j)] * ld, params + miss[static_cast<size_t>(j)] * ld + P, rows.begin() + j * P);
+            src = rows.data(); src_ld = P;
+        }
+        evaluateRows(src, M, src_ld, vals.data(), st.data(), nullptr);
+        for (int64_t j = 0; j < M; ++j) {
+            const int64_t i = miss[static_cast<size_t>(j)];
+            out[i] = vals[static_cast<size_t>(j)];
+            // calculate() reaches its store only on the complete path; the early `return lowest()` exits (bad parameters, S
+            // overflow, invalid simulation result) leave the cache untouched
+            if ((st[static_cast<size_t>(j)] & ~static_cast<uint32_t>(SEPAIHRD_ST_NONFINITE)) == 0) {
+                if (fast) fast->storeLikelihood(fkey[static_cast<size_t>(i)], out[i]);
+                else cache_.storeLikelihood(skey[static_cast<size_t>(i)], out[i]);
+            }
+        }
+    }
+    for (int64_t i = 0; i < B; ++i) {
+        const int64_t f = first_of[static_cast<size_t>(i)];
+        if (f >= 0 && f != i) {                                    // the repeat would have been a hit in calculate(): count it as one
+            double v = 0.0;
+            const bool hit = fast ? fast->getLikelihood(fkey[static_cast<size_t>(i)], v) : cache_.getLikelihood(skey[static_cast<size_t>(i)], v);
+            out[i] = hit ? v : out[f];
+        }
+    }
+}
+
+// ---- SimulationCache (src/sir_age_structured/caching/SimulationCache.cpp) ---------------------------------------------
+namespace {
+inline size_t mix_hash(size_t k) {                                 // the 64-bit finaliser the reference mixes each coordinate with (.cpp:11-19)
+    k ^= k >> 33; k *= 0xff51afd7ed558ccdULL;
+    k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ULL;
+    k ^= k >> 33;
+    return k;
+}
+}  // namespace
+
+SimulationCache::SimulationCache(size_t max_size) : capacity_(max_size) {
+    if (max_size == 0) throw std::invalid_argument("SimulationCache: max_size must be > 0.");
+    keys_.assign(capacity_, 0); values_.assign(capacity_, 0.0); frequencies_.assign(capacity_, 0); timestamps_.assign(capacity_, 0);
+    occupied_.assign(capacity_, 0);
+}
+
+size_t SimulationCache::computeHash(const double* p, std::ptrdiff_t count) const {      // .cpp:35-52
+    size_t seed = 0;
+    for (std::ptrdiff_t i = 0; i < count; ++i) {
+        const long long quantized = static_cast<long long>(p[i] * 1e8 + 0.5);
+        seed ^= mix_hash(static_cast<size_t>(quantized)) + 0x9e3779b9 + (seed << 6) + (seed >> 2);
+    }
+    return seed;
+}
+size_t SimulationCache::computeHash(const VectorXd& parameters) const { return computeHash(parameters.data(), parameters.size()); }
+std::string SimulationCache::createCacheKey(const VectorXd& parameters) const { return std::to_string(computeHash(parameters)); }
+
+size_t SimulationCache::findIndex(size_t key) const {              // linear probing from key % capacity (.cpp:58-72)
+    size_t idx = key % capacity_;
+    const size_t start = idx;
+    while (occupied_[idx]) {
+        if (keys_[idx] == key) return idx;
+        if (++idx == capacity_) idx = 0;
+        if (idx == start) break;
+    }
+    return NOT_FOUND;
+}
+
+size_t SimulationCache::evict() {                                  // least frequently used, oldest among equals (.cpp:74-104)
+    size_t victim = 0;
+    uint32_t min_freq = std::numeric_limits<uint32_t>::max(), min_time = std::numeric_limits<uint32_t>::max();
+    for (size_t i = 0; i < capacity_; ++i) {
+        if (!occupied_[i]) continue;
+        if (frequencies_[i] < min_freq || (frequencies_[i] == min_freq && timestamps_[i] < min_time)) {
+            min_freq = frequencies_[i]; min_time = timestamps_[i]; victim = i;
+        }
+    }
+    occupied_[victim] = 0;
+    --count_;
+    return victim;
+}
+
+bool SimulationCache::lookupLocked(size_t key, double& value) {
+    const size_t idx = findIndex(key);
+    if (idx == NOT_FOUND) return false;
+    frequencies_[idx]++;
+    timestamps_[idx] = ++current_tick_;
+    value = values_[idx];
+    return true;
+}
+
+void SimulationCache::storeLocked(size_t key, double value) {
+    const size_t idx = findIndex(key);
+    if (idx != NOT_FOUND) {                                        // update in place
+        values_[idx] = value;
+        frequencies_[idx]++;
+        timestamps_[idx] = ++current_tick_;
+        return;
+    }
+    if (count_ >= capacity_) evict();
+    size_t at = key % capacity_;
+    while (occupied_[at]) if (++at == capacity_) at = 0;
+    keys_[at] = key; values_[at] = value; frequencies_[at] = 1; timestamps_[at] = ++current_tick_; occupied_[at] = 1;
+    ++count_;
+}
+
+std::optional<double> SimulationCache::get(const VectorXd& parameters) {
+    std::lock_guard<std::mutex> lock(mutex_);
+    double v = 0.0;
+    if (lookupLocked(computeHash(parameters), v)) return v;
+    return std::nullopt;
+}
+void SimulationCache::set(const VectorXd& parameters, double result) {
+    std::lock_guard<std::mutex> lock(mutex_);
+    storeLocked(computeHash(parameters), result);
+}
+void SimulationCache::clear() {
+    std::lock_guard<std::mutex> lock(mutex_);
+    std::fill(occupied_.begin(), occupied_.end(), 0);
+    std::fill(frequencies_.begin(), frequencies_.end(), 0);
+    count_ = 0;
+    current_tick_ = 0;
+}
+size_t SimulationCache::size() const {
+    std::lock_guard<std::mutex> lock(mutex_);
+    return count_;
+}
+bool SimulationCache::getLikelihood(size_t key, double& value) {
+    get_calls_.fetch_add(1, std::memory_order_relaxed);
+    std::lock_guard<std::mutex> lock(mutex_);
+    if (!lookupLocked(key, value)) return false;
+    get_hits_.fetch_add(1, std::memory_order_relaxed);
+    return true;
+}
+void SimulationCache::storeLikelihood(size_t key, double value) {
+    store_calls_.fetch_add(1, std::memory_order_relaxed);
+    std::lock_guard<std::mutex> lock(mutex_);
+    storeLocked(key, value);
+}
+bool SimulationCache::getLikelihood(const std::string& key, double& value) {            // a key that is not a number is a miss (.cpp:165-180)
+    size_t k = 0;
+    try { k = std::stoull(key); } catch (...) { get_calls_.fetch_add(1, std::memory_order_relaxed); return false; }
+    return getLikelihood(k, value);
+}
+void SimulationCache::storeLikelihood(const std::string& key, double value) {
+    size_t k = 0;
+    try { k = std::stoull(key); } catch (...) { store_calls_.fetch_add(1, std::memory_order_relaxed); return; }
+    storeLikelihood(k, value);
 }
 
 // ---- ResultAggregator ---------------------------------------------------------------------------------------------

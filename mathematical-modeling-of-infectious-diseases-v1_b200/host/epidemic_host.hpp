@@ -15,7 +15,9 @@
 #pragma once
 
 #include <cstdint>
+#include <atomic>
 #include <functional>
+#include <mutex>
 #include <limits>
 #include <map>
 #include <memory>
@@ -217,9 +219,9 @@ public:
     virtual void storeLikelihood(const std::string& key, double value) = 0;
 };
 
-// The batch evaluator never consults a cache: a hit of the reference's SimulationCache may return the
-// likelihood of ANOTHER vector (1e-8 quantisation / hash collision).  The type exists so
-// that constructor signatures stay source compatible (pattern: sepaihrd_objective_benchmark_main.cpp:229-238).
+// The cache that caches nothing (pattern: sepaihrd_objective_benchmark_main.cpp:229-238).  Parity runs use it: a hit of the
+// reference's SimulationCache may return the likelihood of ANOTHER vector (1e-8 quantisation / hash collision, SURVEY.md
+// quirk Q6).
 class NullSimulationCache : public ISimulationCache {
 public:
     std::optional<double> get(const VectorXd&) override { return std::nullopt; }
@@ -230,7 +232,46 @@ public:
     bool getLikelihood(const std::string&, double&) override { return false; }
     void storeLikelihood(const std::string&, double) override {}
 };
-using SimulationCache = NullSimulationCache;
+
+// SimulationCache (src/sir_age_structured/caching/SimulationCache.cpp): parameter vector -> log-likelihood, keyed by a 64-bit
+// hash of the vector quantised at 1e-8 (computeHash, .cpp:35-52), open addressing with linear probing over `max_size` slots,
+// least-frequently-used eviction with least-recently-used tie-break by a linear scan (.cpp:74-104), one mutex, hit counters.
+// SEPAIHRDObjectiveFunction consults it in calculate() and in calculateBatch() for batches that fit into it.
+class SimulationCache : public ISimulationCache {
+public:
+    explicit SimulationCache(size_t max_size = 1000);
+    std::optional<double> get(const VectorXd& parameters) override;
+    void set(const VectorXd& parameters, double result) override;
+    void clear() override;
+    size_t size() const override;
+    std::string createCacheKey(const VectorXd& parameters) const override;      // the hash as a decimal string
+    size_t computeHash(const VectorXd& parameters) const;
+    size_t computeHash(const double* parameters, std::ptrdiff_t count) const;
+    bool getLikelihood(const std::string& key, double& value) override;
+    void storeLikelihood(const std::string& key, double value) override;
+    bool getLikelihood(size_t key, double& value);                              // fast path: numeric key
+    void storeLikelihood(size_t key, double value);
+    size_t capacity() const { return capacity_; }
+    size_t getLikelihoodCalls() const { return get_calls_.load(std::memory_order_relaxed); }
+    size_t getLikelihoodHits() const { return get_hits_.load(std::memory_order_relaxed); }
+    size_t storeLikelihoodCalls() const { return store_calls_.load(std::memory_order_relaxed); }
+    void resetLikelihoodStats() { get_calls_ = 0; get_hits_ = 0; store_calls_ = 0; }
+
+private:
+    static constexpr size_t NOT_FOUND = static_cast<size_t>(-1);
+    size_t findIndex(size_t key) const;
+    size_t evict();
+    bool lookupLocked(size_t key, double& value);
+    void storeLocked(size_t key, double value);
+    size_t capacity_, count_ = 0;
+    uint32_t current_tick_ = 0;
+    std::vector<size_t> keys_;
+    std::vector<double> values_;
+    std::vector<uint32_t> frequencies_, timestamps_;
+    std::vector<uint8_t> occupied_;
+    mutable std::mutex mutex_;
+    mutable std::atomic<size_t> get_calls_{0}, get_hits_{0}, store_calls_{0};
+};
 
 struct OptimizationResult {                                          // IOptimizationAlgorithm.hpp:18-27
     VectorXd bestParameters;
@@ -347,14 +388,20 @@ public:
                               double rel_error = 1.0e-6);
     ~SEPAIHRDObjectiveFunction() override;
     double calculate(const VectorXd& parameters) const override;                             // .cpp:62-235
+    // B calls of calculate() in order.  The cache is consulted like calculate() does (.cpp:63-77, :227-234) when the batch fits
+    // into it (B <= capacity: a larger batch would evict its own entries; it goes to the device whole); a key that repeats
+    // inside the batch is evaluated once.  Failures that calculate() returns before its store (invalid parameters, S overflow,
+    // failed integration) are not stored here either.
     void calculateBatch(const double* params, int64_t B, int64_t ld, double* out) const override;
-    // batch form with per-set status words (SEPAIHRD_ST_*) and optional accepted/rejected step counts
+    // batch form with per-set status words (SEPAIHRD_ST_*) and optional accepted/rejected step counts; never cached
     void calculateBatch(const double* params, int64_t B, int64_t ld, double* out, uint32_t* status, int32_t* steps) const;
     const std::vector<std::string>& getParameterNames() const override;
     DeviceContext& device() const { return *dev_; }
 
 private:
+    void evaluateRows(const double* params, int64_t B, int64_t ld, double* out, uint32_t* status, int32_t* steps) const;
     IParameterManager& parameterManager_;
+    ISimulationCache& cache_;
     std::shared_ptr<AgeSEPAIHRDModel> model_;
     std::unique_ptr<DeviceContext> dev_;
     int mode_listener_id_ = -1;

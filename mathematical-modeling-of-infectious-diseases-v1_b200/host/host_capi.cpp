@@ -109,11 +109,23 @@ struct sepaihrd_host_model {
     std::vector<double> times;
     std::unique_ptr<SEPAIHRDModelCalibration> calibration;
     std::unique_ptr<SEPAIHRDParameterManager> pm;
-    std::unique_ptr<NullSimulationCache> cache;
+    std::shared_ptr<ISimulationCache> cache;
     std::unique_ptr<SEPAIHRDObjectiveFunction> objective;
     std::unique_ptr<AgeSEPAIHRDSimulator> simulator;
     double abs_tol = 1e-6, rel_tol = 1e-6;
+    std::vector<std::string> pnames;
+    std::map<std::string, double> sig;
+    std::map<std::string, std::pair<double, double>> bounds;
+    // the calibration and the objective hold the cache: (re)built whenever the cache changes
+    void build(std::shared_ptr<ISimulationCache> c) {
+        objective.reset(); calibration.reset();
+        cache = std::move(c);
+        calibration = std::make_unique<SEPAIHRDModelCalibration>(model, *data, times, pnames, sig, bounds, std::make_shared<Dopri5SolverStrategy>(), cache);
+        objective = std::make_unique<SEPAIHRDObjectiveFunction>(model, *pm, *cache, *data, times, data->getInitialSEPAIHRDState(),
+                                                                std::make_shared<Dopri5SolverStrategy>(), abs_tol, rel_tol);
+    }
 };
+struct sepaihrd_host_cache { SimulationCache c; explicit sepaihrd_host_cache(size_t n) : c(n) {} };
 
 // SEPAIHRDParameters -> PiecewiseConstantNpiStrategy -> AgeSEPAIHRDModel from the flat problem description (host only: no
 // device is touched).  createNpiStrategy (src/model/main.cpp:81-130): element 0 of the kappa schedule is the fixed baseline.
@@ -404,12 +416,10 @@ int32_t sepaihrd_host_model_create(const sepaihrd_problem* pb, const char* const
                                                     VectorXd::FromPointer(pb->data_initial_state, SEPAIHRD_NUM_COMPARTMENTS * n));
         h->times.assign(pb->times, pb->times + pb->n_times);
         h->abs_tol = pb->abs_tol; h->rel_tol = pb->rel_tol;
-        h->calibration = std::make_unique<SEPAIHRDModelCalibration>(h->model, *h->data, h->times, pnames, sig, bounds);
         h->pm = std::make_unique<SEPAIHRDParameterManager>(h->model, pnames, sig, bounds);
         h->pm->setConstraintMode(pb->constraint_mode == 1 ? ConstraintMode::MCMC_REFLECT : ConstraintMode::OPTIMIZATION_CLAMP);
-        h->cache = std::make_unique<NullSimulationCache>();
-        h->objective = std::make_unique<SEPAIHRDObjectiveFunction>(h->model, *h->pm, *h->cache, *h->data, h->times, h->data->getInitialSEPAIHRDState(),
-                                                                   std::make_shared<Dopri5SolverStrategy>(), pb->abs_tol, pb->rel_tol);
+        h->pnames = pnames; h->sig = sig; h->bounds = bounds;
+        h->build(std::make_shared<NullSimulationCache>());         // parity runs: no cache (quirk Q6); sepaihrd_host_model_set_cache switches
         *out = h.release();
     });
 }
@@ -472,7 +482,55 @@ int32_t sepaihrd_host_model_posterior_predictive(sepaihrd_host_model* m, const d
         if (out_used) *out_used = d.samples_used;
     });
 }
+int32_t sepaihrd_host_model_set_cache(sepaihrd_host_model* m, int64_t capacity) {
+    return guarded([&] {
+        if (!m || capacity < 0) throw InvalidParameterException("sepaihrd_host_model_set_cache", "bad argument");
+        if (capacity == 0) m->build(std::make_shared<NullSimulationCache>());
+        else m->build(std::make_shared<SimulationCache>(static_cast<size_t>(capacity)));
+    });
+}
+int32_t sepaihrd_host_model_cache_stats(const sepaihrd_host_model* m, int64_t* out) {
+    return guarded([&] {
+        if (!m || !out) throw InvalidParameterException("sepaihrd_host_model_cache_stats", "bad argument");
+        const auto* sc = dynamic_cast<const SimulationCache*>(m->cache.get());
+        out[0] = static_cast<int64_t>(m->cache->size());
+        out[1] = sc ? static_cast<int64_t>(sc->getLikelihoodCalls()) : 0;
+        out[2] = sc ? static_cast<int64_t>(sc->getLikelihoodHits()) : 0;
+        out[3] = sc ? static_cast<int64_t>(sc->storeLikelihoodCalls()) : 0;
+    });
+}
 void sepaihrd_host_model_destroy(sepaihrd_host_model* m) { delete m; }
+
+// ---- SimulationCache on its own (host only) -----------------------------------------------------------------------------
+int32_t sepaihrd_host_cache_create(int64_t capacity, sepaihrd_host_cache** out) {
+    return guarded([&] {
+        if (!out || capacity < 0) throw InvalidParameterException("sepaihrd_host_cache_create", "bad argument");
+        *out = new sepaihrd_host_cache(static_cast<size_t>(capacity));      // capacity 0: "SimulationCache: max_size must be > 0."
+    });
+}
+uint64_t sepaihrd_host_cache_hash(const sepaihrd_host_cache* c, const double* params, int32_t n) {
+    return static_cast<uint64_t>(c->c.computeHash(params, n));
+}
+int32_t sepaihrd_host_cache_get(sepaihrd_host_cache* c, uint64_t key, double* out_value) {
+    double v = 0.0;
+    const bool hit = c->c.getLikelihood(static_cast<size_t>(key), v);
+    if (hit && out_value) *out_value = v;
+    return hit ? 1 : 0;
+}
+void sepaihrd_host_cache_store(sepaihrd_host_cache* c, uint64_t key, double value) { c->c.storeLikelihood(static_cast<size_t>(key), value); }
+int32_t sepaihrd_host_cache_get_vector(sepaihrd_host_cache* c, const double* params, int32_t n, double* out_value) {
+    const auto v = c->c.get(VectorXd::FromPointer(params, n));
+    if (v && out_value) *out_value = *v;
+    return v ? 1 : 0;
+}
+void sepaihrd_host_cache_set_vector(sepaihrd_host_cache* c, const double* params, int32_t n, double value) { c->c.set(VectorXd::FromPointer(params, n), value); }
+int64_t sepaihrd_host_cache_size(const sepaihrd_host_cache* c) { return static_cast<int64_t>(c->c.size()); }
+void sepaihrd_host_cache_clear(sepaihrd_host_cache* c) { c->c.clear(); }
+void sepaihrd_host_cache_stats(const sepaihrd_host_cache* c, int64_t* out) {
+    out[0] = static_cast<int64_t>(c->c.getLikelihoodCalls()); out[1] = static_cast<int64_t>(c->c.getLikelihoodHits());
+    out[2] = static_cast<int64_t>(c->c.storeLikelihoodCalls());
+}
+void sepaihrd_host_cache_destroy(sepaihrd_host_cache* c) { delete c; }
 
 }  // extern "C"
 

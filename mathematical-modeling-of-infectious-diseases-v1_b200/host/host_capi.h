@@ -131,7 +131,27 @@ int32_t sepaihrd_host_model_calibrate(sepaihrd_host_model* m, const char* phase1
  * lower_95, lower_90, median, upper_90, upper_95 (probabilities 0.025, 0.05, 0.5, 0.95, 0.975) */
 int32_t sepaihrd_host_model_posterior_predictive(sepaihrd_host_model* m, const double* samples, int64_t S, int32_t num_samples_for_ppc,
                                                  uint32_t random_seed, const double* initial_state, double* out, int64_t* out_samples_used);
+/* The model is built with the cache that caches nothing (parity runs).  capacity > 0: the objective and the
+ * calibration are rebuilt over a SimulationCache of that capacity (src/model/main.cpp:371 uses 1000); 0: back to none.
+ * stats[4] = entries, getLikelihood calls, hits, storeLikelihood calls.                                                     */
+int32_t sepaihrd_host_model_set_cache(sepaihrd_host_model* m, int64_t capacity);
+int32_t sepaihrd_host_model_cache_stats(const sepaihrd_host_model* m, int64_t* out_stats /* [4] */);
 void    sepaihrd_host_model_destroy(sepaihrd_host_model* m);
+
+/* ---- SimulationCache (src/sir_age_structured/caching/SimulationCache.cpp) on its own, host only ---------------------- *
+ * hash = computeHash (1e-8 quantisation, .cpp:35-52); get / store = the numeric-key getLikelihood / storeLikelihood
+ * (.cpp:212-252); get_vector / set_vector = get / set (.cpp:106-150).  get returns 1 on a hit.                            */
+typedef struct sepaihrd_host_cache sepaihrd_host_cache;
+int32_t  sepaihrd_host_cache_create(int64_t capacity, sepaihrd_host_cache** out);
+uint64_t sepaihrd_host_cache_hash(const sepaihrd_host_cache* c, const double* params, int32_t n);
+int32_t  sepaihrd_host_cache_get(sepaihrd_host_cache* c, uint64_t key, double* out_value);
+void     sepaihrd_host_cache_store(sepaihrd_host_cache* c, uint64_t key, double value);
+int32_t  sepaihrd_host_cache_get_vector(sepaihrd_host_cache* c, const double* params, int32_t n, double* out_value);
+void     sepaihrd_host_cache_set_vector(sepaihrd_host_cache* c, const double* params, int32_t n, double value);
+int64_t  sepaihrd_host_cache_size(const sepaihrd_host_cache* c);
+void     sepaihrd_host_cache_clear(sepaihrd_host_cache* c);
+void     sepaihrd_host_cache_stats(const sepaihrd_host_cache* c, int64_t* out_stats /* [3]: get calls, hits, store calls */);
+void     sepaihrd_host_cache_destroy(sepaihrd_host_cache* c);
 
 /* ---- the reference's on-disk formats (config_io.hpp: C++ readers / writer) ------------- *
  * Both return JSON text owned by the library (valid until the next call on this thread), or NULL with the message in

@@ -71,7 +71,19 @@ SIGNATURES = {
     "sepaihrd_host_model_simulate": (C.c_int32, [_vp, _vp, _vp, C.c_int32, _vp]),
     "sepaihrd_host_model_calibrate": (C.c_int32, [_vp, C.c_char_p, C.c_int32, _keys, _vp, C.c_int32, _keys, _vp, _vp, _dp, _i64p]),
     "sepaihrd_host_model_posterior_predictive": (C.c_int32, [_vp, _vp, C.c_int64, C.c_int32, C.c_uint32, _vp, _vp, _i64p]),
+    "sepaihrd_host_model_set_cache": (C.c_int32, [_vp, C.c_int64]),
+    "sepaihrd_host_model_cache_stats": (C.c_int32, [_vp, _vp]),
     "sepaihrd_host_model_destroy": (None, [_vp]),
+    "sepaihrd_host_cache_create": (C.c_int32, [C.c_int64, _vpp]),
+    "sepaihrd_host_cache_hash": (C.c_uint64, [_vp, _vp, C.c_int32]),
+    "sepaihrd_host_cache_get": (C.c_int32, [_vp, C.c_uint64, _dp]),
+    "sepaihrd_host_cache_store": (None, [_vp, C.c_uint64, C.c_double]),
+    "sepaihrd_host_cache_get_vector": (C.c_int32, [_vp, _vp, C.c_int32, _dp]),
+    "sepaihrd_host_cache_set_vector": (None, [_vp, _vp, C.c_int32, C.c_double]),
+    "sepaihrd_host_cache_size": (C.c_int64, [_vp]),
+    "sepaihrd_host_cache_clear": (None, [_vp]),
+    "sepaihrd_host_cache_stats": (None, [_vp, _vp]),
+    "sepaihrd_host_cache_destroy": (None, [_vp]),
     "sepaihrd_host_metrics": (C.c_int32, [_vp, _vp, C.c_int32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sepaihrd_host_model_scenarios": (C.c_int32, [_vp, _vp, C.c_int64, C.c_int32, C.c_int32, _vp, _vp, _vp, _vp, _vp, C.c_char_p]),
     "sepaihrd_host_model_analyze_runs": (C.c_int32, [_vp, _vp, C.c_int64, C.c_int32, C.c_int32, _vp, _vp, _vp, _vp, _i64p]),
@@ -300,6 +312,51 @@ class Swarm:
             self._h = None
 
 
+class Cache:
+    """SimulationCache of the host mirror (LFU / LRU, open addressing, keys = hash of the vector quantised at 1e-8)."""
+
+    def __init__(self, capacity: int = 1000):
+        self.L = load_library()
+        h = C.c_void_p()
+        check(self.L.sepaihrd_host_cache_create(int(capacity), C.byref(h)))
+        self._h = h
+
+    def hash(self, params) -> int:
+        x = _c64(params)
+        return int(self.L.sepaihrd_host_cache_hash(self._h, x.ctypes.data, len(x)))
+
+    def get(self, key: int):
+        v = C.c_double()
+        return v.value if self.L.sepaihrd_host_cache_get(self._h, int(key), C.byref(v)) else None
+
+    def store(self, key: int, value: float):
+        self.L.sepaihrd_host_cache_store(self._h, int(key), float(value))
+
+    def get_vector(self, params):
+        x = _c64(params); v = C.c_double()
+        return v.value if self.L.sepaihrd_host_cache_get_vector(self._h, x.ctypes.data, len(x), C.byref(v)) else None
+
+    def set_vector(self, params, value: float):
+        x = _c64(params)
+        self.L.sepaihrd_host_cache_set_vector(self._h, x.ctypes.data, len(x), float(value))
+
+    def __len__(self) -> int:
+        return int(self.L.sepaihrd_host_cache_size(self._h))
+
+    def clear(self):
+        self.L.sepaihrd_host_cache_clear(self._h)
+
+    def stats(self):
+        out = np.zeros(3, dtype=np.int64)
+        self.L.sepaihrd_host_cache_stats(self._h, out.ctypes.data)
+        return dict(get_calls=int(out[0]), hits=int(out[1]), store_calls=int(out[2]))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self.L.sepaihrd_host_cache_destroy(self._h)
+            self._h = None
+
+
 def _batch_callback(evaluate, P):
     def _cb(_user, params, B, ld, out):
         try:
@@ -391,6 +448,15 @@ class HostModel:
         x = _c64(params); out = np.empty(x.shape[0])
         check(self.L.sepaihrd_host_model_calculate_batch(self._h, x.ctypes.data, x.shape[0], x.shape[1], out.ctypes.data))
         return out
+
+    def set_cache(self, capacity: int):
+        """capacity > 0: evaluate through a SimulationCache of that capacity (the reference's main() uses 1000); 0: no cache."""
+        check(self.L.sepaihrd_host_model_set_cache(self._h, int(capacity)))
+
+    def cache_stats(self):
+        out = np.zeros(4, dtype=np.int64)
+        check(self.L.sepaihrd_host_model_cache_stats(self._h, out.ctypes.data))
+        return dict(entries=int(out[0]), get_calls=int(out[1]), hits=int(out[2]), store_calls=int(out[3]))
 
     def set_constraint_mode(self, mode: int):
         check(self.L.sepaihrd_host_model_set_constraint_mode(self._h, int(mode)))

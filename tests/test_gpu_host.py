@@ -127,6 +127,35 @@ def test_pso_swarm_reaches_the_same_global_best_on_gpu_and_oracle(problem, oracl
     assert ref["trace"][-1] >= ref["trace"][0]
 
 
+def test_objective_consults_the_simulation_cache_like_calculate_does(host, problem, oracle):
+    """SimulationCache behind SEPAIHRDObjectiveFunction (ObjectiveFunction.cpp:63-77, 227-234): probe per vector, one device batch
+    for the misses, a key repeated inside the batch evaluated once, batches beyond the capacity evaluated whole."""
+    m = host.HostModel(problem)
+    x = oracle.jitter_params(40, seed=3)
+    plain = m.calculate_batch(x)
+    assert m.cache_stats() == dict(entries=0, get_calls=0, hits=0, store_calls=0)          # the default is the cache that caches nothing
+    m.set_cache(64)
+    a = m.calculate(x[0])
+    assert m.cache_stats() == dict(entries=1, get_calls=1, hits=0, store_calls=1)
+    b = m.calculate(x[0])
+    assert a == b == plain[0] and m.cache_stats() == dict(entries=1, get_calls=2, hits=1, store_calls=1)
+    rows = [1, 2, 1, 3, 0, 2]
+    got = m.calculate_batch(x[rows])
+    np.testing.assert_array_equal(got, plain[rows])
+    # 6 probes (x0 hits) + 2 re-probes for the repeated keys (hits); 3 distinct misses stored
+    assert m.cache_stats() == dict(entries=4, get_calls=2 + 6 + 2, hits=1 + 1 + 2, store_calls=1 + 3)
+    np.testing.assert_array_equal(m.calculate_batch(x[:4]), plain[:4])                    # all hits: no device call needed
+    assert m.cache_stats()["hits"] == 4 + 4
+    m.set_cache(16)                                                                        # 40 sets > 16 entries: evaluated whole
+    np.testing.assert_array_equal(m.calculate_batch(x), plain)
+    assert m.cache_stats() == dict(entries=0, get_calls=0, hits=0, store_calls=0)
+    # least-frequently-used eviction through the objective: 16 entries, then a 17th
+    for i in range(17):
+        m.calculate(x[i])
+    assert m.cache_stats()["entries"] == 16
+    m.close()
+
+
 def test_device_resident_swarm_hands_over_to_the_host_engine_on_a_stagnation_restart(host, problem):
     """restart_threshold = 1e300 makes every iteration "stagnant", so with max_stagnation = 2 the main loop restarts the swarm at
     iteration 3 (ParticleSwarmOptimizer.cpp:133-146).  The device-resident swarm is read back at that point and the run continues
