@@ -578,6 +578,59 @@ void SEPAIHRDObjectiveFunction::calculateBatch(const double* params, int64_t B, 
     }
 }
 
+// ---- finite-difference gradient ---------------------------------------------------------------------------------------------
+void ForwardDifferences::perturb(const VectorXd& params, double epsilon, std::vector<double>& rows, std::vector<double>& steps) {
+    const std::ptrdiff_t P = params.size();
+    rows.resize(static_cast<size_t>(P * P));
+    steps.resize(static_cast<size_t>(P));
+    for (std::ptrdiff_t i = 0; i < P; ++i) {
+        const double param_scale = std::max(std::abs(params(i)), epsilon);      // .cpp:35-36
+        steps[static_cast<size_t>(i)] = epsilon * param_scale;
+        double* row = rows.data() + i * P;
+        std::copy(params.data(), params.data() + P, row);
+        row[i] += steps[static_cast<size_t>(i)];
+    }
+}
+
+void ForwardDifferences::gradient(double f_center, const double* f_plus, const uint8_t* skip, const std::vector<double>& steps, VectorXd& grad) {
+    const std::ptrdiff_t P = static_cast<std::ptrdiff_t>(steps.size());
+    grad.resize(P);
+    for (std::ptrdiff_t i = 0; i < P; ++i) {
+        if ((skip && skip[i]) || !std::isfinite(f_plus[i])) grad(i) = 0.0;      // .cpp:50-53, 101-104, 163-167
+        else grad(i) = (f_plus[i] - f_center) / steps[static_cast<size_t>(i)];
+    }
+}
+
+double SEPAIHRDGradientObjectiveFunction::evaluate_with_gradient(const VectorXd& params, VectorXd& grad) const {
+    const std::ptrdiff_t P = params.size();
+    grad.resize(P);
+    const double f_center = SEPAIHRDObjectiveFunction::calculate(params);
+    if (!std::isfinite(f_center)) {                                             // .cpp:24-29
+        grad.setZero();
+        return f_center;
+    }
+    std::vector<double> rows, steps, f_plus(static_cast<size_t>(P));
+    std::vector<uint32_t> status(static_cast<size_t>(P));
+    ForwardDifferences::perturb(params, epsilon_, rows, steps);
+    auto* spm = dynamic_cast<SEPAIHRDParameterManager*>(&parameterManager_);
+    const ConstraintMode mode = spm ? spm->getConstraintMode() : ConstraintMode::OPTIMIZATION_CLAMP;
+    if (mode != ConstraintMode::OPTIMIZATION_CLAMP) device().setConstraintMode(ConstraintMode::OPTIMIZATION_CLAMP);
+    try {
+        evaluateRows(rows.data(), P, P, f_plus.data(), status.data(), nullptr);
+    } catch (...) {
+        if (mode != ConstraintMode::OPTIMIZATION_CLAMP) device().setConstraintMode(mode);
+        throw;
+    }
+    if (mode != ConstraintMode::OPTIMIZATION_CLAMP) device().setConstraintMode(mode);
+    ++gradient_batches_;
+    // a perturbed vector the parameter manager rejects (negative kappa) or whose initial state does not fit into the
+    // population contributes a zero component (.cpp:50-53, 93-104); every other failure is the finite sentinel lowest()
+    std::vector<uint8_t> skip(static_cast<size_t>(P));
+    for (std::ptrdiff_t i = 0; i < P; ++i) skip[static_cast<size_t>(i)] = (status[static_cast<size_t>(i)] & (SEPAIHRD_ST_INVALID_PARAM | SEPAIHRD_ST_S_OVERFLOW)) != 0;
+    ForwardDifferences::gradient(f_center, f_plus.data(), skip.data(), steps, grad);
+    return f_center;
+}
+
 // ---- SimulationCache (src/sir_age_structured/caching/SimulationCache.cpp) ---------------------------------------------
 namespace {
 inline size_t mix_hash(size_t k) {                                 // the 64-bit finaliser the reference mixes each coordinate with (.cpp:11-19)

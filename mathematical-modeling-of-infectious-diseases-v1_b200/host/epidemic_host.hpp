@@ -175,6 +175,22 @@ public:
     virtual void calculateBatch(const double* params, int64_t B, int64_t ld, double* out) const;
 };
 
+// include/model/interfaces/IGradientObjectiveFunction.hpp: objective + gradient in one call (the NUTS sampler needs it)
+class IGradientObjectiveFunction : public virtual IObjectiveFunction {
+public:
+    ~IGradientObjectiveFunction() override = default;
+    virtual double evaluate_with_gradient(const VectorXd& params, VectorXd& grad) const = 0;
+};
+
+// Forward finite differences the way SEPAIHRDGradientObjectiveFunction::evaluate_with_gradient forms them
+// (src/model/objectives/SEPAIHRDGradientObjectiveFunction.cpp:15-171): step eps_i = epsilon * max(|x_i|, epsilon),
+// grad_i = (f(x + eps_i e_i) - f(x)) / eps_i when f(x + eps_i e_i) is finite, else 0.  `rows` receives the P perturbed vectors
+// ([P][P] row-major) and is what a caller evaluates as ONE batch.
+struct ForwardDifferences {
+    static void perturb(const VectorXd& params, double epsilon, std::vector<double>& rows, std::vector<double>& steps);
+    static void gradient(double f_center, const double* f_plus, const uint8_t* skip /* or null */, const std::vector<double>& steps, VectorXd& grad);
+};
+
 class IParameterManager {
 public:
     virtual ~IParameterManager() = default;
@@ -398,13 +414,37 @@ public:
     const std::vector<std::string>& getParameterNames() const override;
     DeviceContext& device() const { return *dev_; }
 
-private:
+protected:
     void evaluateRows(const double* params, int64_t B, int64_t ld, double* out, uint32_t* status, int32_t* steps) const;
     IParameterManager& parameterManager_;
     ISimulationCache& cache_;
     std::shared_ptr<AgeSEPAIHRDModel> model_;
     std::unique_ptr<DeviceContext> dev_;
     int mode_listener_id_ = -1;
+};
+
+// SEPAIHRDGradientObjectiveFunction (include/model/objectives/SEPAIHRDGradientObjectiveFunction.hpp): the reference loops over
+// the P parameters with OpenMP, one simulation each; here the P perturbed vectors are ONE device batch (SURVEY.md section 2,
+// row 15: "P+1 batch").  Like the reference, the centre value goes through calculate() (and its cache) and the perturbed
+// vectors are constrained by CLAMPING whatever the manager's current mode is (the reference builds a fresh
+// SEPAIHRDParameterManager per component, whose mode is the default OPTIMIZATION_CLAMP, .cpp:40-43).
+// Deliberate difference: the reference builds the perturbed runs' initial state from the multipliers only
+// and ignores run-up seeding, so under the shipped configuration its differences compare two different initial conditions;
+// here every evaluation uses calculate()'s initial-state rule.
+class SEPAIHRDGradientObjectiveFunction : public virtual SEPAIHRDObjectiveFunction, public IGradientObjectiveFunction {
+public:
+    SEPAIHRDGradientObjectiveFunction(std::shared_ptr<AgeSEPAIHRDModel> model, IParameterManager& parameterManager, ISimulationCache& cache,
+                                      const CalibrationData& calibration_data, const std::vector<double>& time_points,
+                                      const VectorXd& initial_state, std::shared_ptr<IOdeSolverStrategy> solver_strategy,
+                                      double abs_error = 1.0e-6, double rel_error = 1.0e-6)
+        : SEPAIHRDObjectiveFunction(std::move(model), parameterManager, cache, calibration_data, time_points, initial_state,
+                                    std::move(solver_strategy), abs_error, rel_error) {}
+    double epsilon_ = 1e-4;
+    double evaluate_with_gradient(const VectorXd& params, VectorXd& grad) const override;
+    long gradientBatches() const { return gradient_batches_; }
+
+private:
+    mutable long gradient_batches_ = 0;
 };
 
 // ---- posterior-predictive aggregation (include/model/ResultAggregator.hpp, PostCalibrationAnalyser) ---------------

@@ -76,7 +76,7 @@ private:
 };
 
 // IObjectiveFunction over a C batch callback.
-class CallbackObjective : public IObjectiveFunction {
+class CallbackObjective : public virtual IObjectiveFunction {
 public:
     CallbackObjective(sepaihrd_host_batch_fn fn, void* user, const std::vector<std::string>& names) : fn_(fn), user_(user), names_(names) {}
     double calculate(const VectorXd& p) const override {
@@ -95,6 +95,24 @@ private:
     sepaihrd_host_batch_fn fn_;
     void* user_;
     std::vector<std::string> names_;
+};
+
+// the callback objective with the forward-difference gradient of SEPAIHRDGradientObjectiveFunction: centre value, then the P
+// perturbed vectors as ONE batch
+class CallbackGradientObjective : public CallbackObjective, public IGradientObjectiveFunction {
+public:
+    using CallbackObjective::CallbackObjective;
+    double epsilon_ = 1e-4;
+    double evaluate_with_gradient(const VectorXd& params, VectorXd& grad) const override {
+        const double f_center = calculate(params);
+        grad.resize(params.size());
+        if (!std::isfinite(f_center)) { grad.setZero(); return f_center; }
+        std::vector<double> rows, steps, f_plus(static_cast<size_t>(params.size()));
+        ForwardDifferences::perturb(params, epsilon_, rows, steps);
+        calculateBatch(rows.data(), params.size(), params.size(), f_plus.data());
+        ForwardDifferences::gradient(f_center, f_plus.data(), nullptr, steps, grad);
+        return f_center;
+    }
 };
 
 }  // namespace
@@ -334,9 +352,10 @@ int32_t sepaihrd_host_optimize(const char* algorithm, sepaihrd_host_pm* pm, int3
         if (which == "mh") algo = std::make_unique<MetropolisHastingsSampler>();
         else if (which == "pso") algo = std::make_unique<ParticleSwarmOptimization>();
         else if (which == "hill") algo = std::make_unique<HillClimbingOptimizer>();
-        else throw InvalidParameterException("sepaihrd_host_optimize", "algorithm must be mh, pso or hill");
+        else if (which == "nuts") algo = std::make_unique<NUTSSampler>();
+        else throw InvalidParameterException("sepaihrd_host_optimize", "algorithm must be mh, pso, hill or nuts");
         algo->configure(settings_map(n, keys, values));
-        CallbackObjective f(fn, user, pm->pm.getParameterNames());
+        CallbackGradientObjective f(fn, user, pm->pm.getParameterNames());
         const auto P = static_cast<std::ptrdiff_t>(pm->pm.getParameterCount());
         const OptimizationResult r = algo->optimize(VectorXd::FromPointer(initial, P), f, pm->pm);
         if (out_best) std::copy(r.bestParameters.data(), r.bestParameters.data() + P, out_best);
@@ -453,8 +472,10 @@ int32_t sepaihrd_host_model_calibrate(sepaihrd_host_model* m, const char* phase1
                                       const char* const* k2, const double* v2, double* out_best, double* out_value, int64_t* out_samples) {
     return guarded([&] {
         const std::string which = phase1 ? phase1 : "pso";
-        ModelCalibrator c = (which == "hill") ? m->calibration->runHillClimbingMCMC(settings_map(n1, k1, v1), settings_map(n2, k2, v2))
-                                              : m->calibration->runPSOMCMC(settings_map(n1, k1, v1), settings_map(n2, k2, v2));
+        if (which != "hill" && which != "pso" && which != "nuts") throw InvalidParameterException("sepaihrd_host_model_calibrate", "phase1 must be pso, hill or nuts");
+        ModelCalibrator c = (which == "hill")   ? m->calibration->runHillClimbingMCMC(settings_map(n1, k1, v1), settings_map(n2, k2, v2))
+                            : (which == "nuts") ? m->calibration->runNUTS(settings_map(n2, k2, v2))          // single phase: the second settings map
+                                                : m->calibration->runPSOMCMC(settings_map(n1, k1, v1), settings_map(n2, k2, v2));
         const VectorXd& b = c.getBestParameterVector();
         if (out_best) std::copy(b.data(), b.data() + b.size(), out_best);
         if (out_value) *out_value = c.getBestObjectiveValue();
@@ -480,6 +501,19 @@ int32_t sepaihrd_host_model_posterior_predictive(sepaihrd_host_model* m, const d
                     for (int k = 0; k < 5; ++k) out[((s * T + t) * n + a) * 5 + k] = (*q[k])(t, a);
         }
         if (out_used) *out_used = d.samples_used;
+    });
+}
+int32_t sepaihrd_host_model_gradient(sepaihrd_host_model* m, const double* params, double epsilon, double* out_value, double* out_grad) {
+    return guarded([&] {
+        if (!m || !params || !out_grad) throw InvalidParameterException("sepaihrd_host_model_gradient", "bad argument");
+        SEPAIHRDGradientObjectiveFunction g(m->model, *m->pm, *m->cache, *m->data, m->times, m->data->getInitialSEPAIHRDState(),
+                                            std::make_shared<Dopri5SolverStrategy>(), m->abs_tol, m->rel_tol);
+        if (epsilon > 0) g.epsilon_ = epsilon;
+        const auto P = static_cast<std::ptrdiff_t>(m->pm->getParameterCount());
+        VectorXd grad;
+        const double v = g.evaluate_with_gradient(VectorXd::FromPointer(params, P), grad);
+        if (out_value) *out_value = v;
+        std::copy(grad.data(), grad.data() + P, out_grad);
     });
 }
 int32_t sepaihrd_host_model_set_cache(sepaihrd_host_model* m, int64_t capacity) {

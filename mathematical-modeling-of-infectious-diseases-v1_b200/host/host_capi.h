@@ -94,7 +94,8 @@ int32_t sepaihrd_host_pso_values(const sepaihrd_host_pso* pso, double* out_pbest
 int32_t sepaihrd_host_pso_neighbors(sepaihrd_host_pso* pso, int32_t particle, int32_t* out, int32_t cap);
 void    sepaihrd_host_pso_destroy(sepaihrd_host_pso* pso);
 
-/* ---- whole runs against a batch callback: "mh", "pso" or "hill" (IOptimizationAlgorithm::optimize) --------- */
+/* ---- whole runs against a batch callback: "mh", "pso", "hill" or "nuts" (IOptimizationAlgorithm::optimize); "nuts" takes the
+ * forward-difference gradient of the callback (P perturbed vectors per gradient, one batch) ------------------------------- */
 int32_t sepaihrd_host_optimize(const char* algorithm, sepaihrd_host_pm* pm, int32_t n_settings, const char* const* keys,
                                const double* values, sepaihrd_host_batch_fn fn, void* user, const double* initial,
                                double* out_best /* [P] */, double* out_best_value, int64_t* out_n_evaluations);
@@ -131,6 +132,9 @@ int32_t sepaihrd_host_model_calibrate(sepaihrd_host_model* m, const char* phase1
  * lower_95, lower_90, median, upper_90, upper_95 (probabilities 0.025, 0.05, 0.5, 0.95, 0.975) */
 int32_t sepaihrd_host_model_posterior_predictive(sepaihrd_host_model* m, const double* samples, int64_t S, int32_t num_samples_for_ppc,
                                                  uint32_t random_seed, const double* initial_state, double* out, int64_t* out_samples_used);
+/* SEPAIHRDGradientObjectiveFunction::evaluate_with_gradient: the objective at params and its forward-difference gradient
+ * (step epsilon * max(|x_i|, epsilon), epsilon <= 0: the reference's 1e-4), the P perturbed vectors as one device batch.     */
+int32_t sepaihrd_host_model_gradient(sepaihrd_host_model* m, const double* params, double epsilon, double* out_value, double* out_grad /* [P] */);
 /* The model is built with the cache that caches nothing (parity runs).  capacity > 0: the objective and the
  * calibration are rebuilt over a SimulationCache of that capacity (src/model/main.cpp:371 uses 1000); 0: back to none.
  * stats[4] = entries, getLikelihood calls, hits, storeLikelihood calls.                                                     */

@@ -1005,6 +1005,222 @@ OptimizationResult ParticleSwarmOptimization::optimize(const VectorXd& initial, 
 }
 
 // =====================================================================================================================
+// NUTS (src/model/optimizers/NUTSSampler.cpp)
+// =====================================================================================================================
+namespace {
+double dot(const VectorXd& a, const VectorXd& b) {
+    double s = 0.0;
+    for (std::ptrdiff_t i = 0; i < a.size(); ++i) s += a(i) * b(i);
+    return s;
+}
+void clip_gradient(VectorXd& grad) {                                  // .cpp:80-88, 285-289, 296-299
+    const double norm = std::sqrt(dot(grad, grad));
+    if (norm > 1000.0) grad *= 1000.0 / norm;
+}
+}  // namespace
+
+NUTSSampler::NUTSSampler() : rng_(std::random_device{}()) {}
+
+void NUTSSampler::configure(const std::map<std::string, double>& s) {
+    num_iterations_ = static_cast<int>(setting(s, "nuts_iterations", 2000.0));
+    adaptation_window_ = static_cast<int>(setting(s, "nuts_adaptation_window", 500.0));
+    delta_target_ = setting(s, "nuts_delta_target", 0.8);
+    max_tree_depth_ = static_cast<int>(setting(s, "nuts_max_tree_depth", 10.0));
+    has_seed_ = s.count("seed") != 0;
+    seed_ = static_cast<unsigned>(setting(s, "seed", 0.0));
+}
+
+double NUTSSampler::gradientAt(IGradientObjectiveFunction& objective, const VectorXd& theta, VectorXd& grad) const {
+    if (memo_valid_ && memo_theta_ == theta) { grad = memo_grad_; return memo_value_; }
+    const double v = objective.evaluate_with_gradient(theta, grad);
+    ++gradient_evaluations_;
+    memo_theta_ = theta; memo_grad_ = grad; memo_value_ = v; memo_valid_ = true;
+    return v;
+}
+
+OptimizationResult NUTSSampler::optimize(const VectorXd& initialParameters, IObjectiveFunction& objectiveFunction, IParameterManager& pm) {
+    auto* grad_obj = dynamic_cast<IGradientObjectiveFunction*>(&objectiveFunction);
+    if (!grad_obj) throw InvalidParameterException("NUTSSampler", "Objective function must implement IGradientObjectiveFunction for NUTS.");
+    if (has_seed_) rng_.seed(seed_);
+    memo_valid_ = false; gradient_evaluations_ = 0; tree_depths_.clear();
+    OptimizationResult result;
+    result.samples.reserve(static_cast<size_t>(std::max(num_iterations_, 0)));
+    result.sampleObjectiveValues.reserve(static_cast<size_t>(std::max(num_iterations_, 0)));
+    VectorXd theta_m = initialParameters;
+    const std::ptrdiff_t P = theta_m.size();
+
+    double epsilon = findReasonableEpsilon(*grad_obj, theta_m, pm);
+    // dual averaging (.cpp:63-70)
+    const double mu = std::log(10.0 * epsilon);
+    double epsilon_bar = epsilon, H_bar = 0.0;
+    const double gamma = 0.05, t0 = 10.0, kappa = 0.75;
+
+    for (int m = 1; m <= num_iterations_; ++m) {
+        std::normal_distribution<> normal(0.0, 1.0);                     // a fresh distribution per iteration (.cpp:74)
+        VectorXd r0(P);
+        for (std::ptrdiff_t i = 0; i < P; ++i) r0(i) = normal(rng_);
+        VectorXd grad(P);
+        const double log_p = gradientAt(*grad_obj, theta_m, grad);
+        clip_gradient(grad);
+        if (!std::isfinite(log_p)) {                                     // .cpp:98-105: repeat the last sample, if there is one
+            if (!result.samples.empty()) {
+                result.samples.push_back(result.samples.back());
+                result.sampleObjectiveValues.push_back(result.sampleObjectiveValues.back());
+            }
+            continue;
+        }
+        const double H0 = log_p - 0.5 * dot(r0, r0);
+        const double log_u_slice = H0 - std::exponential_distribution<>(1.0)(rng_);
+        VectorXd theta_minus = theta_m, theta_plus = theta_m, r_minus = r0, r_plus = r0, theta_next = theta_m;
+        int j = 0, n = 1, n_alpha = 0;
+        bool s = true;
+        double alpha = 0.0;
+        while (s && j < max_tree_depth_) {
+            const int v = (std::uniform_int_distribution<>(0, 1)(rng_) * 2) - 1;
+            Tree subtree;
+            if (v == -1) {
+                buildTree(*grad_obj, theta_minus, r_minus, log_u_slice, v, j, epsilon, H0, pm, subtree);
+                theta_minus = subtree.theta_minus; r_minus = subtree.r_minus;
+            } else {
+                buildTree(*grad_obj, theta_plus, r_plus, log_u_slice, v, j, epsilon, H0, pm, subtree);
+                theta_plus = subtree.theta_plus; r_plus = subtree.r_plus;
+            }
+            if (subtree.s && checkNoUTurn(theta_minus, theta_plus, r_minus, r_plus)) {
+                const double acceptance_prob = static_cast<double>(subtree.n_valid) / static_cast<double>(n + subtree.n_valid);
+                if (std::uniform_real_distribution<>(0.0, 1.0)(rng_) < acceptance_prob) theta_next = subtree.theta_prime;
+                n += subtree.n_valid;
+                alpha += subtree.alpha;
+                n_alpha += subtree.n_alpha;
+                j++;
+            } else {
+                s = false;
+            }
+        }
+        theta_m = theta_next;
+        tree_depths_.push_back(j);
+        if (m <= adaptation_window_) {                                   // .cpp:165-179
+            const double avg_alpha = (n_alpha > 0) ? alpha / n_alpha : 0.0;
+            const double eta = 1.0 / (m + t0);
+            H_bar = (1.0 - eta) * H_bar + eta * (delta_target_ - avg_alpha);
+            const double log_epsilon = mu - (std::sqrt(m) / gamma) * H_bar;
+            epsilon = std::exp(log_epsilon);
+            const double m_kappa = std::pow(m, -kappa);
+            const double log_epsilon_bar = m_kappa * log_epsilon + (1.0 - m_kappa) * std::log(epsilon_bar);
+            epsilon_bar = std::exp(log_epsilon_bar);
+        } else {
+            epsilon = epsilon_bar;
+        }
+        const VectorXd constrained_theta = pm.applyConstraints(theta_m);
+        result.samples.push_back(constrained_theta);
+        const double final_obj = objectiveFunction.calculate(constrained_theta);
+        result.sampleObjectiveValues.push_back(final_obj);
+        if (final_obj > result.bestObjectiveValue) {
+            result.bestObjectiveValue = final_obj;
+            result.bestParameters = constrained_theta;
+        }
+    }
+    final_epsilon_ = epsilon;
+    return result;
+}
+
+// heuristic first step size (.cpp:213-279): a tenth of the mean proposal sigma, clipped to [1e-6, 0.1], then at most five
+// halvings / 1.5-fold increases steered by the acceptance probability of one leapfrog step
+double NUTSSampler::findReasonableEpsilon(IGradientObjectiveFunction& objective, const VectorXd& theta, IParameterManager& pm) const {
+    const std::ptrdiff_t P = theta.size();
+    double avg_scale = 0.0;
+    for (std::ptrdiff_t i = 0; i < P; ++i) avg_scale += pm.getSigmaForParamIndex(static_cast<int>(i));
+    avg_scale /= static_cast<double>(P);
+    double epsilon = std::max(1e-6, std::min(avg_scale * 0.1, 0.1));
+    std::normal_distribution<> normal(0.0, 1.0);
+    VectorXd r(P);
+    for (std::ptrdiff_t i = 0; i < P; ++i) r(i) = normal(rng_);
+    VectorXd grad(P);
+    const double log_p = gradientAt(objective, theta, grad);
+    if (!std::isfinite(log_p)) return epsilon;
+    const double H0 = log_p - 0.5 * dot(r, r);
+    VectorXd theta_prime = theta, r_prime = r;
+    leapfrog(objective, theta_prime, r_prime, epsilon, pm);
+    double log_p_prime = gradientAt(objective, theta_prime, grad);
+    double H_prime = log_p_prime - 0.5 * dot(r_prime, r_prime);
+    double accept_prob = std::exp(std::min(0.0, H_prime - H0));
+    for (int iter = 0; iter < 5; ++iter) {
+        if (accept_prob < 0.1 && epsilon > 1e-8) epsilon *= 0.5;
+        else if (accept_prob > 0.9 && epsilon < 1.0) epsilon *= 1.5;
+        else break;
+        theta_prime = theta; r_prime = r;
+        leapfrog(objective, theta_prime, r_prime, epsilon, pm);
+        log_p_prime = gradientAt(objective, theta_prime, grad);
+        if (!std::isfinite(log_p_prime)) { epsilon *= 0.5; continue; }
+        H_prime = log_p_prime - 0.5 * dot(r_prime, r_prime);
+        accept_prob = std::exp(std::min(0.0, H_prime - H0));
+    }
+    return epsilon;
+}
+
+void NUTSSampler::leapfrog(IGradientObjectiveFunction& objective, VectorXd& theta, VectorXd& r, double epsilon, IParameterManager& pm) const {   // .cpp:282-306
+    VectorXd grad(theta.size());
+    gradientAt(objective, theta, grad);
+    clip_gradient(grad);
+    r += (0.5 * epsilon) * grad;
+    theta += epsilon * r;
+    theta = pm.applyConstraints(theta);
+    gradientAt(objective, theta, grad);
+    clip_gradient(grad);
+    r += (0.5 * epsilon) * grad;
+}
+
+void NUTSSampler::buildTree(IGradientObjectiveFunction& objective, const VectorXd& theta, const VectorXd& r, double log_u_slice, int v, int j,
+                            double epsilon, double H0, IParameterManager& pm, Tree& tree) const {                                          // .cpp:309-407
+    if (j == 0) {
+        VectorXd theta_prime = theta, r_prime = r;
+        leapfrog(objective, theta_prime, r_prime, v * epsilon, pm);
+        VectorXd grad(theta_prime.size());
+        const double log_p = gradientAt(objective, theta_prime, grad);
+        const double H_prime = log_p - 0.5 * dot(r_prime, r_prime);
+        tree.n_valid = (log_u_slice <= H_prime) ? 1 : 0;
+        tree.s = (log_u_slice < H_prime + DELTA_MAX);
+        tree.theta_minus = theta_prime; tree.theta_plus = theta_prime;
+        tree.r_minus = r_prime; tree.r_plus = r_prime;
+        tree.theta_prime = theta_prime;
+        tree.alpha = std::min(1.0, std::exp(H_prime - H0));
+        tree.n_alpha = 1;
+        return;
+    }
+    Tree left;
+    buildTree(objective, theta, r, log_u_slice, v, j - 1, epsilon, H0, pm, left);
+    if (!left.s) { tree = left; return; }
+    Tree right;
+    if (v == -1) {
+        buildTree(objective, left.theta_minus, left.r_minus, log_u_slice, v, j - 1, epsilon, H0, pm, right);
+        tree.theta_minus = right.theta_minus; tree.r_minus = right.r_minus;
+        tree.theta_plus = left.theta_plus; tree.r_plus = left.r_plus;
+    } else {
+        buildTree(objective, left.theta_plus, left.r_plus, log_u_slice, v, j - 1, epsilon, H0, pm, right);
+        tree.theta_minus = left.theta_minus; tree.r_minus = left.r_minus;
+        tree.theta_plus = right.theta_plus; tree.r_plus = right.r_plus;
+    }
+    if (right.s) {
+        tree.n_valid = left.n_valid + right.n_valid;
+        const double prob = (tree.n_valid > 0) ? static_cast<double>(right.n_valid) / static_cast<double>(tree.n_valid) : 0.0;
+        tree.theta_prime = (std::uniform_real_distribution<>(0.0, 1.0)(rng_) < prob) ? right.theta_prime : left.theta_prime;
+        tree.alpha = left.alpha + right.alpha;
+        tree.n_alpha = left.n_alpha + right.n_alpha;
+        tree.s = left.s && right.s && checkNoUTurn(tree.theta_minus, tree.theta_plus, tree.r_minus, tree.r_plus);
+    } else {
+        tree.theta_prime = left.theta_prime;
+        tree.n_valid = left.n_valid;
+        tree.s = false;
+        tree.alpha = left.alpha;
+        tree.n_alpha = left.n_alpha;
+    }
+}
+
+bool NUTSSampler::checkNoUTurn(const VectorXd& theta_minus, const VectorXd& theta_plus, const VectorXd& r_minus, const VectorXd& r_plus) {   // .cpp:410-424
+    const VectorXd delta = theta_plus - theta_minus;
+    return dot(delta, r_minus) >= 0 && dot(delta, r_plus) >= 0;
+}
+
+// =====================================================================================================================
 // Hill climbing: candidate cloud + robust line search
 // =====================================================================================================================
 void HillClimbingOptimizer::configure(const std::map<std::string, double>& s) {
@@ -1262,7 +1478,12 @@ ModelCalibrator SEPAIHRDModelCalibration::setupCalibrator(std::map<std::string, 
     std::unique_ptr<IObjectiveFunction> f;
     try {
         pm = std::make_unique<SEPAIHRDParameterManager>(model_, params_to_calibrate_, proposal_sigmas_, param_bounds_);
-        f = std::make_unique<SEPAIHRDObjectiveFunction>(model_, *pm, *cache_, observed_data_, time_points_, initial_state_cached_, solver_strategy_);
+        bool needs_gradient = false;                              // .cpp:77-83: a NUTS sampler among the algorithms asks for the gradient objective
+        for (const auto& kv : algorithms) needs_gradient = needs_gradient || dynamic_cast<NUTSSampler*>(kv.second.get()) != nullptr;
+        if (needs_gradient)
+            f = std::make_unique<SEPAIHRDGradientObjectiveFunction>(model_, *pm, *cache_, observed_data_, time_points_, initial_state_cached_, solver_strategy_);
+        else
+            f = std::make_unique<SEPAIHRDObjectiveFunction>(model_, *pm, *cache_, observed_data_, time_points_, initial_state_cached_, solver_strategy_);
     } catch (const std::exception& e) {
         throw ModelConstructionException(src, std::string("Failed to create ObjectiveFunction: ") + e.what());
     }
@@ -1284,6 +1505,14 @@ ModelCalibrator SEPAIHRDModelCalibration::runHillClimbingMCMC(const std::map<std
     algos[ModelCalibrator::PHASE2_NAME] = std::make_unique<MetropolisHastingsSampler>();
     ModelCalibrator c = setupCalibrator(std::move(algos));
     c.calibrate(s1, s2);
+    return c;
+}
+
+ModelCalibrator SEPAIHRDModelCalibration::runNUTS(const std::map<std::string, double>& nuts_settings) {
+    std::map<std::string, std::unique_ptr<IOptimizationAlgorithm>> algos;
+    algos[ModelCalibrator::PHASE2_NAME] = std::make_unique<NUTSSampler>();
+    ModelCalibrator c = setupCalibrator(std::move(algos));
+    c.calibrate({}, nuts_settings);                                   // no phase 1
     return c;
 }
 

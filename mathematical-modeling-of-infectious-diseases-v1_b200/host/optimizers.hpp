@@ -221,6 +221,51 @@ private:
     unsigned seed_ = 0;
 };
 
+// NUTSSampler   src/model/optimizers/NUTSSampler.cpp:16-426: the No-U-Turn sampler with dual-averaging step-size adaptation
+// (Hoffman & Gelman 2014, algorithm 6 as the reference writes it: heuristic first step size, gradients rescaled to norm
+// <= 1000, constraints applied inside the leapfrog step, slice variable in log space, DELTA_MAX = 1000).  It needs an
+// IGradientObjectiveFunction; every gradient is one batch of P perturbed vectors on the device.  The reference evaluates the
+// gradient at a leapfrog end point and again, at the same point, when the next leapfrog starts or the tree leaf is scored:
+// the last (point, value, gradient) triple is remembered here, which changes no number.  Extra setting: `seed`.
+class NUTSSampler : public IOptimizationAlgorithm {
+public:
+    NUTSSampler();
+    void configure(const std::map<std::string, double>& settings) override;
+    OptimizationResult optimize(const VectorXd& initialParameters, IObjectiveFunction& objectiveFunction,
+                                IParameterManager& parameterManager) override;
+    long gradientEvaluations() const { return gradient_evaluations_; }      // distinct points whose gradient was computed
+    double finalEpsilon() const { return final_epsilon_; }
+    const std::vector<int>& treeDepths() const { return tree_depths_; }
+
+private:
+    struct Tree {
+        VectorXd theta_minus, theta_plus, r_minus, r_plus, theta_prime;
+        int n_valid = 0;
+        bool s = false;
+        double alpha = 0.0;
+        int n_alpha = 0;
+    };
+    double gradientAt(IGradientObjectiveFunction& objective, const VectorXd& theta, VectorXd& grad) const;
+    double findReasonableEpsilon(IGradientObjectiveFunction& objective, const VectorXd& theta, IParameterManager& pm) const;
+    void leapfrog(IGradientObjectiveFunction& objective, VectorXd& theta, VectorXd& r, double epsilon, IParameterManager& pm) const;
+    void buildTree(IGradientObjectiveFunction& objective, const VectorXd& theta, const VectorXd& r, double log_u_slice, int v, int j,
+                   double epsilon, double H0, IParameterManager& pm, Tree& tree) const;
+    static bool checkNoUTurn(const VectorXd& theta_minus, const VectorXd& theta_plus, const VectorXd& r_minus, const VectorXd& r_plus);
+    int num_iterations_ = 2000, adaptation_window_ = 500, max_tree_depth_ = 10;
+    double delta_target_ = 0.8;
+    static constexpr double DELTA_MAX = 1000.0;
+    bool has_seed_ = false;
+    unsigned seed_ = 0;
+    mutable std::mt19937 rng_;
+    // the last gradient evaluation (see above)
+    mutable bool memo_valid_ = false;
+    mutable VectorXd memo_theta_, memo_grad_;
+    mutable double memo_value_ = 0.0;
+    mutable long gradient_evaluations_ = 0;
+    double final_epsilon_ = 0.0;
+    std::vector<int> tree_depths_;
+};
+
 class ModelCalibrator {
 public:
     static constexpr const char* PHASE1_NAME = "Phase1";
@@ -259,6 +304,7 @@ public:
     VectorXd getCurrentParameterValues();
     ModelCalibrator runPSOMCMC(const std::map<std::string, double>& phase1_settings, const std::map<std::string, double>& phase2_settings);
     ModelCalibrator runHillClimbingMCMC(const std::map<std::string, double>& phase1_settings, const std::map<std::string, double>& phase2_settings);
+    ModelCalibrator runNUTS(const std::map<std::string, double>& nuts_settings);        // .cpp:210-236: NUTS as phase 2, no phase 1
 
 private:
     ModelCalibrator setupCalibrator(std::map<std::string, std::unique_ptr<IOptimizationAlgorithm>> algorithms);

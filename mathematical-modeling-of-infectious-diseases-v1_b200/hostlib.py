@@ -71,6 +71,7 @@ SIGNATURES = {
     "sepaihrd_host_model_simulate": (C.c_int32, [_vp, _vp, _vp, C.c_int32, _vp]),
     "sepaihrd_host_model_calibrate": (C.c_int32, [_vp, C.c_char_p, C.c_int32, _keys, _vp, C.c_int32, _keys, _vp, _vp, _dp, _i64p]),
     "sepaihrd_host_model_posterior_predictive": (C.c_int32, [_vp, _vp, C.c_int64, C.c_int32, C.c_uint32, _vp, _vp, _i64p]),
+    "sepaihrd_host_model_gradient": (C.c_int32, [_vp, _vp, C.c_double, _dp, _vp]),
     "sepaihrd_host_model_set_cache": (C.c_int32, [_vp, C.c_int64]),
     "sepaihrd_host_model_cache_stats": (C.c_int32, [_vp, _vp]),
     "sepaihrd_host_model_destroy": (None, [_vp]),
@@ -448,6 +449,12 @@ class HostModel:
         x = _c64(params); out = np.empty(x.shape[0])
         check(self.L.sepaihrd_host_model_calculate_batch(self._h, x.ctypes.data, x.shape[0], x.shape[1], out.ctypes.data))
         return out
+
+    def gradient(self, params, epsilon: float = 0.0):
+        """SEPAIHRDGradientObjectiveFunction::evaluate_with_gradient: (value, forward-difference gradient)."""
+        x = _c64(params); g = np.empty(len(x)); v = C.c_double()
+        check(self.L.sepaihrd_host_model_gradient(self._h, x.ctypes.data, float(epsilon), C.byref(v), g.ctypes.data))
+        return v.value, g
 
     def set_cache(self, capacity: int):
         """capacity > 0: evaluate through a SimulationCache of that capacity (the reference's main() uses 1000); 0: no cache."""

@@ -127,6 +127,39 @@ def test_pso_swarm_reaches_the_same_global_best_on_gpu_and_oracle(problem, oracl
     assert ref["trace"][-1] >= ref["trace"][0]
 
 
+def test_gradient_objective_is_one_device_batch_of_forward_differences(host, problem, oracle):
+    """SEPAIHRDGradientObjectiveFunction::evaluate_with_gradient: (f(x + eps_i e_i) - f(x)) / eps_i, eps_i = 1e-4 max(|x_i|, 1e-4),
+    the P perturbed vectors as one device batch, against the same differences of the CPU oracle."""
+    m = host.HostModel(problem)
+    x = oracle.jitter_params(3, seed=17)[2]
+    val, g = m.gradient(x)
+    P = len(x)
+    steps = 1e-4 * np.maximum(np.abs(x), 1e-4)
+    rows = np.tile(x, (P, 1)) + np.diag(steps)
+    fc = oracle.eval_batch(x[None])[0][0]
+    fp = oracle.eval_batch(rows)[0]
+    want = (fp - fc) / steps
+    assert _rel(val, fc) < 1e-8
+    # the differences amplify the 1e-11 relative agreement of the two evaluators by |f| / (eps_i |df|)
+    tol = 1e-7 * np.abs(want) + 4e-10 * abs(fc) / steps
+    assert np.all(np.abs(g - want) <= tol), np.max(np.abs(g - want) / tol)
+    assert np.count_nonzero(g) >= 50                               # the dead parameters of quirk Q4 have an exactly zero component
+    dead = [i for i, nme in enumerate(problem.param_names) if nme.endswith("_multiplier") or nme == "runup_days"]
+    assert dead and np.all(g[dead] == 0.0)
+    m.close()
+
+
+def test_nuts_calibration_runs_on_the_device_objective(host, problem, oracle):
+    """SEPAIHRDModelCalibration::runNUTS: NUTS as the only phase over the gradient objective (P-vector batches on the device)."""
+    m = host.HostModel(problem)
+    f0 = oracle.eval_batch(problem.base_params()[None])[0][0]
+    best, val, ns = m.calibrate("nuts", {}, dict(nuts_iterations=4, nuts_adaptation_window=2, nuts_max_tree_depth=2, seed=3))
+    m.close()
+    assert ns == 4 and np.isfinite(val)
+    assert _rel(oracle.eval_batch(best[None])[0][0], val) < 1e-8
+    assert np.all(best >= problem.lower_bound) and np.all(best <= problem.upper_bound)
+
+
 def test_objective_consults_the_simulation_cache_like_calculate_does(host, problem, oracle):
     """SimulationCache behind SEPAIHRDObjectiveFunction (ObjectiveFunction.cpp:63-77, 227-234): probe per vector, one device batch
     for the misses, a key repeated inside the batch evaluated once, batches beyond the capacity evaluated whole."""
