@@ -24,6 +24,8 @@
  *     the reason is in out_status[b] (SEPAIHRD_ST_* bits).
  *   - all floating point is IEEE binary64.
  *   - there is NO CPU fallback: if no CUDA device is usable, sepaihrd_create fails.
+ *   - a ctx may be used from several host threads: every entry point takes the ctx's lock for its duration.  The
+ *     `_device` variants only ENQUEUE on the ctx stream; ordering between threads that enqueue is the callers' business.
  */
 #ifndef SEPAIHRD_B200_H
 #define SEPAIHRD_B200_H
@@ -143,7 +145,11 @@ sepaihrd_rc sepaihrd_set_stream(sepaihrd_ctx* ctx, void* cuda_stream);
  *   out_ll     [B]   log-likelihood or -DBL_MAX
  *   out_status [B]   SEPAIHRD_ST_* bits, may be NULL
  *   out_steps  [B][2] accepted / rejected Dopri5 step attempts, may be NULL (parity diagnostics)
- * Copies H2D, runs the fused kernel, copies D2H, synchronises. */
+ * Copies H2D, runs the fused kernel, copies D2H, synchronises.
+ * Thread-safe like calculate() has to be (the reference calls it from OpenMP loops, ParticleSwarmOptimizer.cpp:368-424,
+ * HillClimbingOptimizer.cpp:228-234), and concurrent calls of at most 4096 sets each are MERGED: a caller that finds no
+ * launch in flight takes every request queued so far (its own included) to the device as one launch.  The reference's
+ * optimizers, unchanged, therefore cost one launch per round of their threads, not one per calculate(). */
 sepaihrd_rc sepaihrd_eval_batch(sepaihrd_ctx* ctx, const double* params, int64_t B, int64_t ld,
                                 double* out_ll, uint32_t* out_status, int32_t* out_steps);
 
@@ -237,6 +243,8 @@ sepaihrd_rc sepaihrd_synchronize(sepaihrd_ctx* ctx);
 
 /* Counters since creation: kernel launches issued by this ctx, parameter sets evaluated. */
 sepaihrd_rc sepaihrd_get_counters(const sepaihrd_ctx* ctx, int64_t* launches, int64_t* sets);
+/* Request merging of sepaihrd_eval_batch since creation: launches that served more than one call, and the calls they served. */
+sepaihrd_rc sepaihrd_get_merge_counters(const sepaihrd_ctx* ctx, int64_t* merged_launches, int64_t* merged_requests);
 
 /* Device-side FP64 pipe microbenchmark (dependent DFMA chains on every SM): returns the measured
  * peak in FP64 instructions/s (x2 for FMA-counted FLOP/s).  Used as the roofline denominator,

@@ -44,6 +44,7 @@ SIGNATURES = {
     "sepaihrd_free_pinned": (None, [C.c_void_p]),
     "sepaihrd_synchronize": (C.c_int, [C.c_void_p]),
     "sepaihrd_get_counters": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "sepaihrd_get_merge_counters": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "sepaihrd_measure_fp64_peak": (C.c_int, [C.c_int32, _dp]),
     "sepaihrd_last_error": (C.c_char_p, []),
     "sepaihrd_version": (C.c_char_p, []),

@@ -7,7 +7,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
 #include <limits>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -56,7 +58,28 @@ bool read_index(const char* s, long* out) {
 
 }  // namespace
 
+// One host-pointer evaluation request waiting to be served (sepaihrd_eval_batch): concurrent callers of one ctx are merged
+// into ONE launch by whichever of them currently leads.
+struct EvalRequest {
+    const double* params; int64_t B, ld;
+    double* out_ll; uint32_t* out_status; int32_t* out_steps;
+    sepaihrd_rc rc = SEPAIHRD_OK;
+    std::string error;
+    bool done = false, lead = false;     // served / told to lead the next round
+    std::condition_variable cv;          // its owner sleeps here: a round wakes exactly the owners it served and ONE next leader
+};
+
 struct sepaihrd_ctx {
+    // Every entry point that touches the ctx takes `mu` (recursive: the host-pointer calls go through the device-pointer ones):
+    // the reference's objective is called concurrently from OpenMP loops (ParticleSwarmOptimizer.cpp:368-424,
+    // HillClimbingOptimizer.cpp:228-234), so a drop-in behind calculate() has to tolerate that.
+    std::recursive_mutex mu;
+    // request coalescing of sepaihrd_eval_batch
+    std::mutex q_mu;
+    std::vector<EvalRequest*> queue;
+    bool leader = false;
+    double* h_stage = nullptr; size_t cap_stage = 0;          // pinned: packed rows | logL | status | steps of a merged launch
+    long long merged_launches = 0, merged_requests = 0;
     int device = 0;
     int n = 0, K = 0, n_obs = 0, nb = 0, nk = 0, P = 0, nslots = 0, nseg = 0, runup_offset = 0, n_nonneg = 0;
     int constraint_mode = 0, math_mode = SEPAIHRD_MATH_FAST;
@@ -413,6 +436,7 @@ void sepaihrd_destroy(sepaihrd_ctx* ctx) {
     if (ctx->d_status) cudaFree(ctx->d_status);
     if (ctx->d_steps) cudaFree(ctx->d_steps);
     for (void* p : ctx->scratch) if (p) cudaFree(p);
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     for (int i = 0; i < 2; ++i) if (ctx->ev_copy[i]) cudaEventDestroy(ctx->ev_copy[i]);
@@ -422,6 +446,7 @@ void sepaihrd_destroy(sepaihrd_ctx* ctx) {
 
 sepaihrd_rc sepaihrd_set_constraint_mode(sepaihrd_ctx* ctx, int32_t mode) {
     if (!ctx || (mode != 0 && mode != 1)) return fail(SEPAIHRD_ERR_INVALID_ARGUMENT, "bad constraint mode");
+    std::lock_guard<std::recursive_mutex> lock(ctx->mu);
     ctx->constraint_mode = mode;
     return SEPAIHRD_OK;
 }
@@ -429,18 +454,21 @@ sepaihrd_rc sepaihrd_set_constraint_mode(sepaihrd_ctx* ctx, int32_t mode) {
 sepaihrd_rc sepaihrd_set_math_mode(sepaihrd_ctx* ctx, int32_t mode) {
     if (!ctx || (mode != SEPAIHRD_MATH_FAST && mode != SEPAIHRD_MATH_STRICT && mode != SEPAIHRD_MATH_FAST_GENERAL)) return fail(SEPAIHRD_ERR_INVALID_ARGUMENT, "bad math mode");
     if (mode != SEPAIHRD_MATH_STRICT && (ctx->abs_tol <= 0.0 || ctx->rel_tol <= 0.0)) return fail(SEPAIHRD_ERR_UNSUPPORTED, "FAST math needs abs_tol > 0 and rel_tol > 0");
+    std::lock_guard<std::recursive_mutex> lock(ctx->mu);
     ctx->math_mode = mode;
     return SEPAIHRD_OK;
 }
 
 sepaihrd_rc sepaihrd_set_stream(sepaihrd_ctx* ctx, void* cuda_stream) {
     if (!ctx) return fail(SEPAIHRD_ERR_INVALID_ARGUMENT, "null ctx");
+    std::lock_guard<std::recursive_mutex> lock(ctx->mu);
     ctx->stream = (cuda_stream == SEPAIHRD_STREAM_OWN) ? ctx->own_stream : (cudaStream_t)cuda_stream;
     return SEPAIHRD_OK;
 }
 
 sepaihrd_rc sepaihrd_release_scratch(sepaihrd_ctx* ctx) {
     if (!ctx) return fail(SEPAIHRD_ERR_INVALID_ARGUMENT, "null argument");
+    std::lock_guard<std::recursive_mutex> lock(ctx->mu);
     CUDA_TRY(cudaSetDevice(ctx->device));
     sepaihrd_internal::release_scratch(ctx);
     return SEPAIHRD_OK;
@@ -461,6 +489,7 @@ void sepaihrd_free_pinned(void* ptr) {
 
 sepaihrd_rc sepaihrd_synchronize(sepaihrd_ctx* ctx) {
     if (!ctx) return fail(SEPAIHRD_ERR_INVALID_ARGUMENT, "null ctx");
+    std::lock_guard<std::recursive_mutex> lock(ctx->mu);
     CUDA_TRY(cudaSetDevice(ctx->device));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return SEPAIHRD_OK;
@@ -473,11 +502,19 @@ sepaihrd_rc sepaihrd_get_counters(const sepaihrd_ctx* ctx, int64_t* launches, in
     return SEPAIHRD_OK;
 }
 
+sepaihrd_rc sepaihrd_get_merge_counters(const sepaihrd_ctx* ctx, int64_t* merged_launches, int64_t* merged_requests) {
+    if (!ctx) return fail(SEPAIHRD_ERR_INVALID_ARGUMENT, "null ctx");
+    if (merged_launches) *merged_launches = ctx->merged_launches;
+    if (merged_requests) *merged_requests = ctx->merged_requests;
+    return SEPAIHRD_OK;
+}
+
 sepaihrd_rc sepaihrd_eval_batch_device(sepaihrd_ctx* ctx, const double* d_params, int64_t B, int64_t ld,
                                        double* d_out_ll, uint32_t* d_out_status, int32_t* d_out_steps) {
     if (!ctx || !d_out_ll || (B > 0 && !d_params)) return fail(SEPAIHRD_ERR_INVALID_ARGUMENT, "null argument");
     if (B < 0 || ld < ctx->P) return fail(SEPAIHRD_ERR_INVALID_ARGUMENT, "Parameter vector size mismatch.");   // ParameterManager.cpp:165-167
     if (B == 0) return SEPAIHRD_OK;
+    std::lock_guard<std::recursive_mutex> lock(ctx->mu);
     CUDA_TRY(cudaSetDevice(ctx->device));
     if (ctx->obs_mismatch) {
         fill_kernel<<<(unsigned)((B + 255) / 256), 256, 0, ctx->stream>>>(d_out_ll, d_out_status, d_out_steps, B, -DBL_MAX,
@@ -495,11 +532,14 @@ sepaihrd_rc sepaihrd_eval_batch_device(sepaihrd_ctx* ctx, const double* d_params
     return launch(ctx, kp, sepaihrd::MODE_LL);
 }
 
-sepaihrd_rc sepaihrd_eval_batch(sepaihrd_ctx* ctx, const double* params, int64_t B, int64_t ld, double* out_ll,
-                                uint32_t* out_status, int32_t* out_steps) {
-    if (!ctx || !out_ll || (B > 0 && !params)) return fail(SEPAIHRD_ERR_INVALID_ARGUMENT, "null argument");
-    if (B < 0 || ld < ctx->P) return fail(SEPAIHRD_ERR_INVALID_ARGUMENT, "Parameter vector size mismatch.");
-    if (B == 0) return SEPAIHRD_OK;
+}  // extern "C"
+
+namespace {
+
+// the host-pointer evaluation itself; the caller holds no lock
+sepaihrd_rc eval_batch_serial(sepaihrd_ctx* ctx, const double* params, int64_t B, int64_t ld, double* out_ll,
+                              uint32_t* out_status, int32_t* out_steps) {
+    std::lock_guard<std::recursive_mutex> lock(ctx->mu);
     CUDA_TRY(cudaSetDevice(ctx->device));
     sepaihrd_rc rc;
     if ((rc = grow(&ctx->d_params, &ctx->cap_params, (size_t)B * ld)) != SEPAIHRD_OK) return rc;
@@ -540,6 +580,92 @@ sepaihrd_rc sepaihrd_eval_batch(sepaihrd_ctx* ctx, const double* params, int64_t
     return SEPAIHRD_OK;
 }
 
+// Serve the requests of `batch` (>= 2) with ONE launch: rows packed into a page-locked staging buffer (leading dimension P),
+// results scattered back.
+sepaihrd_rc eval_merged(sepaihrd_ctx* ctx, const std::vector<EvalRequest*>& batch) {
+    const int P = ctx->P;
+    int64_t total = 0;
+    bool want_status = false, want_steps = false;
+    for (const EvalRequest* r : batch) { total += r->B; want_status |= r->out_status != nullptr; want_steps |= r->out_steps != nullptr; }
+    const size_t doubles = (size_t)total * P + (size_t)total /* logL */ + (size_t)(total + 1) / 2 /* status */ + (size_t)total /* steps */;
+    {
+        std::lock_guard<std::recursive_mutex> lock(ctx->mu);
+        if (doubles > ctx->cap_stage) {
+            CUDA_TRY(cudaSetDevice(ctx->device));
+            if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+            ctx->h_stage = nullptr; ctx->cap_stage = 0;
+            const size_t want = std::max<size_t>(doubles * 2, 1 << 16);
+            CUDA_TRY(cudaMallocHost((void**)&ctx->h_stage, want * sizeof(double)));
+            ctx->cap_stage = want;
+        }
+    }
+    double* rows = ctx->h_stage;
+    double* ll = rows + (size_t)total * P;
+    uint32_t* st = reinterpret_cast<uint32_t*>(ll + total);
+    int32_t* steps = reinterpret_cast<int32_t*>(ll + total + (total + 1) / 2);
+    int64_t at = 0;
+    for (const EvalRequest* r : batch)
+        for (int64_t b = 0; b < r->B; ++b, ++at) std::memcpy(rows + at * P, r->params + b * r->ld, sizeof(double) * (size_t)P);
+    const sepaihrd_rc rc = eval_batch_serial(ctx, rows, total, P, ll, want_status ? st : nullptr, want_steps ? steps : nullptr);
+    if (rc != SEPAIHRD_OK) return rc;
+    at = 0;
+    for (EvalRequest* r : batch) {
+        std::memcpy(r->out_ll, ll + at, sizeof(double) * (size_t)r->B);
+        if (r->out_status) std::memcpy(r->out_status, st + at, sizeof(uint32_t) * (size_t)r->B);
+        if (r->out_steps) std::memcpy(r->out_steps, steps + 2 * at, sizeof(int32_t) * 2 * (size_t)r->B);
+        at += r->B;
+    }
+    ctx->merged_launches += 1;
+    ctx->merged_requests += (long long)batch.size();
+    return SEPAIHRD_OK;
+}
+
+constexpr int64_t COALESCE_MAX_SETS = 4096;      // larger requests fill the machine on their own
+
+}  // namespace
+
+extern "C" {
+
+// B calls of calculate().  Thread-safe; small requests that arrive while another one is being served are MERGED: the caller
+// that finds no leader takes everything queued so far (its own request included) to the device as one launch, wakes the owners
+// and hands the lead on.  An OpenMP loop over calculate() -- the reference's optimizers, unchanged -- therefore costs one launch
+// per round of its threads instead of one launch per call.
+sepaihrd_rc sepaihrd_eval_batch(sepaihrd_ctx* ctx, const double* params, int64_t B, int64_t ld, double* out_ll,
+                                uint32_t* out_status, int32_t* out_steps) {
+    if (!ctx || !out_ll || (B > 0 && !params)) return fail(SEPAIHRD_ERR_INVALID_ARGUMENT, "null argument");
+    if (B < 0 || ld < ctx->P) return fail(SEPAIHRD_ERR_INVALID_ARGUMENT, "Parameter vector size mismatch.");
+    if (B == 0) return SEPAIHRD_OK;
+    if (B > COALESCE_MAX_SETS) return eval_batch_serial(ctx, params, B, ld, out_ll, out_status, out_steps);
+    EvalRequest me;
+    me.params = params; me.B = B; me.ld = ld; me.out_ll = out_ll; me.out_status = out_status; me.out_steps = out_steps;
+    std::unique_lock<std::mutex> ql(ctx->q_mu);
+    ctx->queue.push_back(&me);
+    if (ctx->leader) me.cv.wait(ql, [&] { return me.done || me.lead; });
+    if (!me.done) {
+        // lead ONE round: everything queued up to now, this request among it
+        ctx->leader = true;
+        std::vector<EvalRequest*> batch;
+        batch.swap(ctx->queue);
+        ql.unlock();
+        sepaihrd_rc rc;
+        if (batch.size() == 1) rc = eval_batch_serial(ctx, params, B, ld, out_ll, out_status, out_steps);   // nobody else: no staging copy
+        else rc = eval_merged(ctx, batch);
+        const std::string err = (rc != SEPAIHRD_OK) ? g_last_error : std::string();
+        ql.lock();
+        // hand the lead to the oldest request that arrived meanwhile (it starts its round while the owners below wake up)
+        EvalRequest* next = ctx->queue.empty() ? nullptr : ctx->queue.front();
+        if (next) next->lead = true; else ctx->leader = false;
+        for (EvalRequest* r : batch) { r->rc = rc; r->error = err; r->done = true; }
+        if (next) next->cv.notify_one();
+        for (EvalRequest* r : batch) if (r != &me) r->cv.notify_one();      // under the lock: a woken owner's request lives on its stack
+        ql.unlock();
+        return rc;
+    }
+    ql.unlock();
+    if (me.rc != SEPAIHRD_OK) g_last_error = me.error;
+    return me.rc;
+}
+
 static sepaihrd_rc simulate_device_impl(sepaihrd_ctx* ctx, const double* d_params, int64_t B, int64_t ld,
                                         const double* d_init, int64_t init_stride,
                                         int32_t what, int32_t stride, double* d_out, uint32_t* d_out_status, bool draw_minor = false) {
@@ -548,6 +674,7 @@ static sepaihrd_rc simulate_device_impl(sepaihrd_ctx* ctx, const double* d_param
     if (what != SEPAIHRD_TRAJ_FULL && what != SEPAIHRD_TRAJ_OBSERVED) return fail(SEPAIHRD_ERR_INVALID_ARGUMENT, "bad trajectory selector");
     if (stride < 1) return fail(SEPAIHRD_ERR_INVALID_ARGUMENT, "stride must be >= 1");
     if (B == 0) return SEPAIHRD_OK;
+    std::lock_guard<std::recursive_mutex> lock(ctx->mu);
     CUDA_TRY(cudaSetDevice(ctx->device));
     sepaihrd::KParams kp = ctx->kp;
     kp.constraint_mode = ctx->constraint_mode;
@@ -577,6 +704,7 @@ sepaihrd_rc sepaihrd_simulate_batch(sepaihrd_ctx* ctx, const double* params, int
     if (B < 0 || ld < ctx->P) return fail(SEPAIHRD_ERR_INVALID_ARGUMENT, "Parameter vector size mismatch.");
     if (stride < 1) return fail(SEPAIHRD_ERR_INVALID_ARGUMENT, "stride must be >= 1");
     if (B == 0) return SEPAIHRD_OK;
+    std::lock_guard<std::recursive_mutex> lock(ctx->mu);
     CUDA_TRY(cudaSetDevice(ctx->device));
     const int W = (what == SEPAIHRD_TRAJ_FULL) ? SEPAIHRD_NUM_COMPARTMENTS * ctx->n : 3 * ctx->n;
     const size_t rows = (size_t)(ctx->K + stride - 1) / stride;
@@ -603,6 +731,7 @@ sepaihrd_rc sepaihrd_simulate_from_state(sepaihrd_ctx* ctx, const double* params
     if (state_stride != 0 && state_stride < (int64_t)SEPAIHRD_NUM_COMPARTMENTS * ctx->n)
         return fail(SEPAIHRD_ERR_INVALID_ARGUMENT, "Initial state size does not match model state size.");   // Simulator.cpp:64-69
     if (B == 0) return SEPAIHRD_OK;
+    std::lock_guard<std::recursive_mutex> lock(ctx->mu);
     CUDA_TRY(cudaSetDevice(ctx->device));
     const int W = (what == SEPAIHRD_TRAJ_FULL) ? SEPAIHRD_NUM_COMPARTMENTS * ctx->n : 3 * ctx->n;
     const size_t rows = (size_t)(ctx->K + stride - 1) / stride;
@@ -663,6 +792,7 @@ sepaihrd_rc fail_with(sepaihrd_rc rc, const char* msg) { return fail(rc, msg); }
 const double* lower_bounds(const sepaihrd_ctx* ctx) { return ctx->blob.data() + ctx->kp.o_lo; }
 const double* upper_bounds(const sepaihrd_ctx* ctx) { return ctx->blob.data() + ctx->kp.o_hi; }
 void count_launches(sepaihrd_ctx* ctx, int n) { ctx->launches += n; }
+std::unique_lock<std::recursive_mutex> lock(sepaihrd_ctx* ctx) { return std::unique_lock<std::recursive_mutex>(ctx->mu); }
 void* scratch(sepaihrd_ctx* ctx, int slot, size_t bytes) {
     if (slot < 0 || slot >= sepaihrd_ctx::N_SCRATCH) return nullptr;
     if (ctx->scratch_bytes[slot] >= bytes && ctx->scratch[slot]) return ctx->scratch[slot];

@@ -1,6 +1,8 @@
 // sepaihrd_internal.h -- the few ctx accessors other translation units of the library need (not part of the ABI).
 #pragma once
 
+#include <mutex>
+
 #include <cuda_runtime.h>
 
 #include "sepaihrd_b200.h"
@@ -14,6 +16,8 @@ sepaihrd_rc fail_with(sepaihrd_rc rc, const char* msg);
 const double* lower_bounds(const sepaihrd_ctx* ctx);   // host copies, [P], as given at creation
 const double* upper_bounds(const sepaihrd_ctx* ctx);
 void count_launches(sepaihrd_ctx* ctx, int n);
+// the ctx mutex (recursive): every entry point of another translation unit that touches the ctx holds it for its duration
+std::unique_lock<std::recursive_mutex> lock(sepaihrd_ctx* ctx);
 // Grow-only device work buffer `slot` (0..15) of at least `bytes`, owned by the ctx and reused across calls; nullptr when the
 // allocation fails.  sepaihrd_release_scratch() drops them all.
 void* scratch(sepaihrd_ctx* ctx, int slot, size_t bytes);

@@ -113,6 +113,7 @@ extern "C" sepaihrd_rc sepaihrd_posterior_predictive(sepaihrd_ctx* ctx, const do
     const long long n_cols = (long long)T * n;            // columns per series
     if ((double)n_cols * (double)B > 2.0e9) return fail_with(SEPAIHRD_ERR_UNSUPPORTED, "more than 2e9 values per series: split the draws");
 
+    const auto ctx_lock = lock(ctx);
     cudaSetDevice(d.device);
     cudaStream_t s = stream(ctx);
     // work buffers live in the ctx (grow-only scratch slots): repeated aggregations of the same size allocate nothing

@@ -293,6 +293,7 @@ static sepaihrd_rc upload_seeds(sepaihrd_swarm* s, const uint32_t* seeds, cudaSt
 
 sepaihrd_rc sepaihrd_swarm_init(sepaihrd_swarm* s, const uint32_t* seeds, const double* initial) {
     if (!s || !seeds) return fail_with(SEPAIHRD_ERR_INVALID_ARGUMENT, "null argument");
+    const auto ctx_lock = sepaihrd_internal::lock(s->ctx);
     const sepaihrd_internal::Dims d = sepaihrd_internal::dims(s->ctx);
     SW_TRY(cudaSetDevice(d.device));
     cudaStream_t st = sepaihrd_internal::stream(s->ctx);
@@ -316,6 +317,7 @@ sepaihrd_rc sepaihrd_swarm_init(sepaihrd_swarm* s, const uint32_t* seeds, const 
 
 sepaihrd_rc sepaihrd_swarm_evaluate(sepaihrd_swarm* s, double* out_best_value, int64_t* out_best_local_index, double* out_best_position) {
     if (!s) return fail_with(SEPAIHRD_ERR_INVALID_ARGUMENT, "null argument");
+    const auto ctx_lock = sepaihrd_internal::lock(s->ctx);
     const sepaihrd_internal::Dims d = sepaihrd_internal::dims(s->ctx);
     SW_TRY(cudaSetDevice(d.device));
     cudaStream_t st = sepaihrd_internal::stream(s->ctx);
@@ -346,6 +348,7 @@ sepaihrd_rc sepaihrd_swarm_evaluate(sepaihrd_swarm* s, double* out_best_value, i
 sepaihrd_rc sepaihrd_swarm_step(sepaihrd_swarm* s, const uint32_t* seeds, double omega, double c1, double c2, const double* global_best) {
     if (!s || !seeds || !global_best) return fail_with(SEPAIHRD_ERR_INVALID_ARGUMENT, "null argument");
     if (!s->evaluated_once) return fail_with(SEPAIHRD_ERR_INVALID_ARGUMENT, "sepaihrd_swarm_step before the first sepaihrd_swarm_evaluate");
+    const auto ctx_lock = sepaihrd_internal::lock(s->ctx);
     const sepaihrd_internal::Dims d = sepaihrd_internal::dims(s->ctx);
     SW_TRY(cudaSetDevice(d.device));
     cudaStream_t st = sepaihrd_internal::stream(s->ctx);
@@ -366,6 +369,7 @@ sepaihrd_rc sepaihrd_swarm_step(sepaihrd_swarm* s, const uint32_t* seeds, double
 
 sepaihrd_rc sepaihrd_swarm_read(sepaihrd_swarm* s, int32_t what, double* out) {
     if (!s || !out) return fail_with(SEPAIHRD_ERR_INVALID_ARGUMENT, "null argument");
+    const auto ctx_lock = sepaihrd_internal::lock(s->ctx);
     const sepaihrd_internal::Dims d = sepaihrd_internal::dims(s->ctx);
     SW_TRY(cudaSetDevice(d.device));
     cudaStream_t st = sepaihrd_internal::stream(s->ctx);

@@ -81,6 +81,12 @@ class BatchEvaluator:
         capi.check(self._lib.sepaihrd_get_counters(self._h, C.byref(a), C.byref(b)))
         return a.value, b.value
 
+    def merge_counters(self):
+        """(launches that served more than one concurrent eval_batch call, calls served by them)."""
+        a, b = C.c_int64(), C.c_int64()
+        capi.check(self._lib.sepaihrd_get_merge_counters(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     # -- evaluation -------------------------------------------------------------------------------
     def eval_batch(self, params, return_steps: bool = False):
         """logL for each row of ``params`` ([B, P] float64).  numpy in -> numpy out (synchronous);

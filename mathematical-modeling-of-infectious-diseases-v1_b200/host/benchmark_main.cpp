@@ -12,7 +12,10 @@
 //     With a cache, calculate() and every batch of at most N sets consult it like the reference's calculate() does; the cache
 //     statistics line of the reference is printed after each mode;
 //   * `--project-root PATH` names the tree (the reference finds it by walking up from the working directory);
-//   * `--mode pso` and `--chains N` exist in addition (batched callers), and `--json` prints one machine-readable line.
+//   * `--mode pso` and `--chains N` exist in addition (batched callers), and `--json` prints one machine-readable line;
+//   * `--mode threads` is the UNCHANGED reference calling pattern: an OpenMP loop (`--threads N` of them, more than cores is
+//     the point) in which every thread calls calculate() for one jittered vector at a time, as ParticleSwarmOptimizer.cpp:368-424
+//     does.  The C ABI merges the calls that arrive while a launch is in flight into the next launch.
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
@@ -20,6 +23,7 @@
 #include <fstream>
 #include <iostream>
 #include <map>
+#include <omp.h>
 #include <random>
 #include <string>
 #include <vector>
@@ -45,7 +49,7 @@ struct Args {
 void usage(const char* prog) {
     std::cout << "Usage: " << prog << " --project-root PATH [--repeats N] [--jitters N] [--seed N] [--threads N]\n"
               << "       [--start YYYY-MM-DD] [--end YYYY-MM-DD] [--constraints opt|mcmc] [--no-cache] [--cache-size N]\n"
-              << "       [--mode micro|hill|mcmc|hillmcmc|pso|all] [--hill-settings PATH] [--mcmc-settings PATH] [--pso-settings PATH]\n"
+              << "       [--mode micro|hill|mcmc|hillmcmc|pso|threads|all] [--hill-settings PATH] [--mcmc-settings PATH] [--pso-settings PATH]\n"
               << "       [--hill-iters N] [--mcmc-iters N] [--pso-iters N] [--chains N] [--swarm N] [--pso-as-configured] [--use-file-iters] [--json]\n";
 }
 
@@ -84,10 +88,10 @@ Args parse(int argc, char** argv) {
     }
     if (a.repeats < 0 || a.jitters < 0) throw std::runtime_error("repeats/jitters must be non-negative");
     if (a.constraintMode != "opt" && a.constraintMode != "mcmc") throw std::runtime_error("--constraints must be 'opt' or 'mcmc'");
-    static const char* modes[] = {"micro", "hill", "mcmc", "hillmcmc", "pso", "all"};
+    static const char* modes[] = {"micro", "hill", "mcmc", "hillmcmc", "pso", "threads", "all"};
     bool ok = false;
     for (const char* m : modes) ok = ok || a.mode == m;
-    if (!ok) throw std::runtime_error("--mode must be one of: micro, hill, mcmc, hillmcmc, pso, all");
+    if (!ok) throw std::runtime_error("--mode must be one of: micro, hill, mcmc, hillmcmc, pso, threads, all");
     const std::string cfg = a.root + "/data/configuration/";
     if (a.hillSettingsPath.empty()) a.hillSettingsPath = cfg + "hill_climbing_settings.txt";
     if (a.mcmcSettingsPath.empty()) a.mcmcSettingsPath = cfg + "mcmc_settings.txt";
@@ -281,7 +285,41 @@ int main(int argc, char** argv) {
             report["pso_ms"] = took; report["pso_best"] = res.bestObjectiveValue; report["pso_calls"] = evals;
         };
 
+        auto run_threads = [&]() {
+            const int n = std::max(args.jitters, 1);
+            std::vector<double> rows(static_cast<size_t>(n) * static_cast<size_t>(P)), out(static_cast<size_t>(n));
+            std::mt19937 rng(static_cast<unsigned>(args.seed));
+            std::normal_distribution<double> normal(0.0, 1.0);
+            for (int k = 0; k < n; ++k) {
+                VectorXd v(P);
+                for (std::ptrdiff_t i = 0; i < P; ++i) v(i) = base[i] + pm.getSigmaForParamIndex(static_cast<int>(i)) * normal(rng);
+                const VectorXd c = pm.applyConstraints(v);
+                std::copy(c.data(), c.data() + P, rows.begin() + static_cast<std::ptrdiff_t>(k) * P);
+            }
+            (void)objective.calculate(base);                                   // warm-up
+            int64_t ml0 = 0, mr0 = 0, l0 = 0, s0 = 0;
+            sepaihrd_get_merge_counters(objective.device().get(), &ml0, &mr0);
+            sepaihrd_get_counters(objective.device().get(), &l0, &s0);
+            const int nthreads = args.threads > 0 ? args.threads : 0;
+            const auto t0 = Clock::now();
+#pragma omp parallel for schedule(static) num_threads(nthreads > 0 ? nthreads : omp_get_max_threads())
+            for (int k = 0; k < n; ++k) out[static_cast<size_t>(k)] = objective.calculate(VectorXd::FromPointer(rows.data() + static_cast<std::ptrdiff_t>(k) * P, P));
+            const double took = ms_since(t0);
+            int64_t ml1 = 0, mr1 = 0, l1 = 0, s1 = 0;
+            sepaihrd_get_merge_counters(objective.device().get(), &ml1, &mr1);
+            sepaihrd_get_counters(objective.device().get(), &l1, &s1);
+            double sum = 0.0;
+            for (double v : out) sum += v;
+            std::printf("\n--- calculate() from an OpenMP loop (%d threads) ---\n%d evals => %.3f ms (%.4e evals/s; sum logL %.12e)\n"
+                        "Kernel launches: %lld (%.1f calls per launch; %lld launches served more than one call)\n",
+                        nthreads > 0 ? nthreads : omp_get_max_threads(), n, took, n / took * 1e3, sum, static_cast<long long>(l1 - l0),
+                        static_cast<double>(n) / std::max<int64_t>(l1 - l0, 1), static_cast<long long>(ml1 - ml0));
+            report["threads_ms"] = took; report["threads_evals_per_s"] = n / took * 1e3; report["threads_launches"] = static_cast<double>(l1 - l0);
+            report["threads_sum"] = sum;
+        };
+
         if (args.mode == "micro") run_micro();
+        else if (args.mode == "threads") run_threads();
         else if (args.mode == "hill") (void)run_hill();
         else if (args.mode == "mcmc") run_mcmc(base);
         else if (args.mode == "pso") run_pso();

@@ -411,5 +411,13 @@ def test_objective_benchmark_harness_runs_from_a_project_tree(host, problem, ora
     assert run.returncode == 0, run.stderr
     rep = json.loads(next(ln for ln in run.stdout.splitlines() if ln.startswith("JSON "))[5:])
     assert rep["hill_best"] >= base_ll * (1 - 1e-12) and rep["mcmc_best"] >= rep["hill_best"] * (1 - 1e-12) and rep["pso_best"] >= base_ll * (1 - 1e-12)
+    # the unchanged reference calling pattern: calculate() from an OpenMP loop with more threads than cores; the C ABI merges
+    # concurrent calls into shared launches and every call still gets its own vector's value
+    run = subprocess.run([exe, "--project-root", str(tmp_path), "--mode", "threads", "--threads", "128", "--jitters", "2048", "--seed", "1", "--json"],
+                         capture_output=True, text=True, timeout=300)
+    assert run.returncode == 0, run.stderr
+    rep = json.loads(next(ln for ln in run.stdout.splitlines() if ln.startswith("JSON "))[5:])
+    assert _rel(rep["threads_sum"], oracle.eval_batch(oracle.jitter_params(2048, seed=1))[0].sum()) < 1e-8
+    assert rep["threads_launches"] < 2048 / 4
     bad = subprocess.run([exe, "--project-root", str(tmp_path / "nowhere")], capture_output=True, text=True)
     assert bad.returncode == 1 and "unable to open" in bad.stderr

@@ -370,6 +370,53 @@ def test_posterior_predictive_quantiles_match_numpy_on_oracle_trajectories(probl
     assert v1 == 1 and np.all(one[..., 0] == one[..., 2])
 
 
+def test_concurrent_callers_are_serialised_and_merged_into_shared_launches(problem, oracle, ev_mod):
+    """calculate() is called from OpenMP loops in the reference (ParticleSwarmOptimizer.cpp:368-424): many host threads on ONE ctx.
+    Every thread must get its own vector's value, and calls that arrive while a launch is in flight share the next launch."""
+    import threading
+    P = oracle.jitter_params(512, seed=9)
+    with ev_mod.BatchEvaluator(problem, device=0) as ev:
+        want, want_st = ev.eval_batch(P)
+        l0, _ = ev.counters()
+        got = np.full(len(P), np.nan)
+        n_threads, per = 64, len(P) // 64
+        start = threading.Barrier(n_threads)
+
+        def worker(t):
+            start.wait()
+            for k in range(per):                                  # one vector per call, like calculate()
+                i = t * per + k
+                got[i] = ev.eval_batch(P[i:i + 1])[0][0]
+        threads = [threading.Thread(target=worker, args=(t,)) for t in range(n_threads)]
+        for th in threads: th.start()
+        for th in threads: th.join()
+        l1, _ = ev.counters()
+        merged_launches, merged_calls = ev.merge_counters()
+        # mixed sizes with status / step-count outputs, concurrently with a big (unmerged) batch
+        big = oracle.jitter_params(6000, seed=10)
+        out = {}
+
+        def small(t):
+            out[t] = ev.eval_batch(P[t * 3:(t + 1) * 3 + (t % 2)], return_steps=True)
+
+        def large():
+            out["big"] = ev.eval_batch(big)
+        threads = [threading.Thread(target=small, args=(t,)) for t in range(24)] + [threading.Thread(target=large)]
+        for th in threads: th.start()
+        for th in threads: th.join()
+        ref_big = ev.eval_batch(big)
+        ref_steps = ev.eval_batch(P[:100], return_steps=True)
+    np.testing.assert_array_equal(got, want)                      # bit-identical: the arithmetic of a set does not depend on its neighbours
+    assert l1 - l0 < len(P)                                       # fewer launches than calls ...
+    assert merged_launches >= 1 and merged_calls > merged_launches   # ... because calls shared launches
+    np.testing.assert_array_equal(out["big"][0], ref_big[0])
+    for t in range(24):
+        lo, hi = t * 3, (t + 1) * 3 + (t % 2)
+        np.testing.assert_array_equal(out[t][0], ref_steps[0][lo:hi])
+        np.testing.assert_array_equal(out[t][1], ref_steps[1][lo:hi])
+        np.testing.assert_array_equal(out[t][2], ref_steps[2][lo:hi])
+
+
 def test_every_distinct_set_of_the_bench_batch_matches_the_oracle(problem, oracle, ev_mod):
     """The first 65,536 sets of the bench batch (bench.py draws 1,048,576 distinct jittered sets from mt19937(1); the whole
     batch and a second distribution are covered by tools/full_parity.py) against the CPU oracle: logL within 1e-8 relative
