@@ -344,3 +344,190 @@ def test_shipped_reference_settings_file_is_accepted(host, tmp_path):
     assert stats["evaluations"] == 3 and np.isfinite(val)
     best, val, stats = host.Swarm(pm, dict(st, seed=1, iterations=30, swarm_size=25)).run(ev)
     assert val > -0.02
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The configuration the reference ships and defaults to -- opposition-based initialisation, evolutionary-state parameter
+# adaptation, ADAPTIVE variant with elitist learning, stagnation restart -- restated in Python on top of the standard update
+# above, sequentially as the reference runs it (one trial evaluation at a time in the elitist strategy; the C++ mirror draws
+# the three trials ahead and rewinds the master generator).
+class _Normal:
+    """std::normal_distribution<double>(0, 1) of libstdc++ (polar method, second value saved)."""
+
+    def __init__(self):
+        self.saved = None
+
+    def __call__(self, g):
+        if self.saved is not None:
+            v, self.saved = self.saved, None
+            return v
+        while True:
+            x = 2.0 * g.uniform() - 1.0
+            y = 2.0 * g.uniform() - 1.0
+            r2 = x * x + y * y
+            if not (r2 > 1.0 or r2 == 0.0):
+                break
+        mult = math.sqrt(-2.0 * math.log(r2) / r2)
+        self.saved = x * mult
+        return y * mult
+
+
+def _python_full_pso(ev, lb, ub, N, iterations, seed, topology, variant, st, max_stagnation, restart_threshold):
+    n = len(lb)
+    master = StdMt19937(seed)
+    master_normal = _Normal()
+    swarm_batches = []
+
+    def evaluate(rows):
+        swarm_batches.append(np.array(rows))
+        return ev(np.array(rows))
+    # initializeSwarm
+    seeds = [master.raw() for _ in range(N)]
+    pos = np.empty((N, n)); vel = np.empty((N, n))
+    for i in range(N):
+        g = StdMt19937(seeds[i])
+        for k in range(n):
+            pos[i, k] = lb[k] + g.uniform() * (ub[k] - lb[k])
+        for k in range(n):
+            vmax = 0.2 * (ub[k] - lb[k])
+            vel[i, k] = -vmax + 2 * vmax * g.uniform()
+    fit = evaluate(pos)
+    # oppositionBasedInitialization: the opposites are never scored -> the originals, sorted by fitness (stable)
+    order = sorted(range(N), key=lambda i: -fit[i])
+    pos, vel = pos[order].copy(), vel[order].copy()
+    fit = evaluate(pos)
+    cur_fit = fit.copy()
+    pbest, pbest_val = pos.copy(), fit.copy()
+    succ_count = np.zeros(N, dtype=int); total = np.zeros(N, dtype=int); succ_rate = np.zeros(N)
+    gbest_val, gbest = -np.inf, None
+
+    def rescan():
+        nonlocal gbest_val, gbest
+        for i in range(N):
+            if pbest_val[i] > gbest_val:
+                gbest_val, gbest = pbest_val[i], pbest[i].copy()
+    rescan()
+    previous, stagnation, restarts, els_trials = -np.inf, 0, 0, 0
+    for it in range(iterations):
+        if abs(gbest_val - previous) < restart_threshold:
+            stagnation += 1
+            if stagnation > max_stagnation:                    # restartSwarm
+                restarts += 1
+                order = sorted(range(N), key=lambda i: -pbest_val[i])
+                pos, vel, pbest = pos[order].copy(), vel[order].copy(), pbest[order].copy()
+                pbest_val, cur_fit = pbest_val[order].copy(), cur_fit[order].copy()
+                succ_count, total, succ_rate = succ_count[order].copy(), total[order].copy(), succ_rate[order].copy()
+                elite = pos[:3].copy()
+                seeds = [master.raw() for _ in range(N)]
+                for i in range(3, N):
+                    g = StdMt19937(seeds[i]); nrm = _Normal()
+                    el = elite[i % 3]
+                    for k in range(n):
+                        if g.uniform() < 0.7:
+                            rng_ = ub[k] - lb[k]
+                            sigma = 0.3 * rng_ * (1.0 + 0.5 * g.uniform())
+                            pos[i, k] = el[k] + sigma * nrm(g)
+                        else:
+                            pos[i, k] = lb[k] + g.uniform() * (ub[k] - lb[k])
+                        pos[i, k] = min(max(pos[i, k], lb[k]), ub[k])
+                        vmax = 0.2 * (ub[k] - lb[k])
+                        vel[i, k] = -vmax + 2 * vmax * g.uniform()
+                f2 = evaluate(pos[3:])
+                for i in range(3, N):
+                    cur_fit[i] = f2[i - 3]; pbest[i] = pos[i]; pbest_val[i] = f2[i - 3]
+                    succ_count[i] = 0; total[i] = 0; succ_rate[i] = 0.0
+                gbest_val, gbest = pbest_val[0], pbest[0].copy()
+                stagnation = 0
+        else:
+            stagnation = 0
+        previous = gbest_val
+        # updateParticles: evolutionary state -> coefficients
+        md = mx = mf = 0.0; maxf, minf = -np.inf, np.inf
+        for i in range(N):
+            d2 = 0.0
+            for k in range(n):
+                d = pos[i, k] - gbest[k]
+                d2 += d * d
+            dist = math.sqrt(d2)
+            md += dist; mx = max(mx, dist)
+            mf += cur_fit[i]; maxf = max(maxf, cur_fit[i]); minf = min(minf, cur_fit[i])
+        md /= N; mf /= N
+        frange = (maxf - minf) if (maxf - minf) > 1e-10 else 1e-10
+        ef = 0.5 * ((md / mx) if mx > 0 else 0.0) + 0.5 * (1.0 - (maxf - mf) / frange)
+        ratio = it / (iterations - 1) if iterations > 1 else 0.0
+        if ef > 0.7:
+            omega = 0.9 - 0.2 * ratio; c1 = 1.5 + 0.5 * math.sin(ratio * math.pi); c2 = 1.5 - 0.5 * math.sin(ratio * math.pi)
+        elif ef > 0.4:
+            omega = 0.7 - 0.3 * ratio; c1 = 2.0 - ratio; c2 = 1.0 + ratio
+        elif ef > 0.2:
+            omega = 0.4 - 0.3 * ratio; c1 = 1.0 - 0.5 * ratio; c2 = 2.0 + 0.5 * ratio
+        else:
+            omega = 0.9 + 0.1 * master.uniform(); c1 = 2.5 + master.uniform(); c2 = 0.5 + master.uniform()
+        omega = min(max(omega, 0.1), 1.0); c1 = min(max(c1, 0.0), 4.0); c2 = min(max(c2, 0.0), 4.0)
+        seeds = [master.raw() for _ in range(N)]
+        snap, snap_val = pbest.copy(), pbest_val.copy()
+        for i in range(N):
+            g = StdMt19937(seeds[i])
+            if topology == 0:
+                lbest = gbest
+            else:
+                b, bv = i, snap_val[i]
+                for j in _neighbors(topology, i, N):
+                    if snap_val[j] > bv:
+                        b, bv = j, snap_val[j]
+                lbest = snap[b]
+            r = [(g.uniform(), g.uniform()) for _ in range(n)]
+            for k in range(n):
+                cognitive = c1 * (r[k][0] * (snap[i, k] - pos[i, k]))
+                social = c2 * (r[k][1] * (lbest[k] - pos[i, k]))
+                v = omega * vel[i, k] + cognitive + social
+                vmax = 0.2 * (ub[k] - lb[k])
+                v = min(max(v, -vmax), vmax)
+                p = pos[i, k] + v
+                if p < lb[k]:
+                    p = lb[k] + abs(p - lb[k]); v *= -0.5
+                elif p > ub[k]:
+                    p = ub[k] - abs(p - ub[k]); v *= -0.5
+                pos[i, k] = min(max(p, lb[k]), ub[k]); vel[i, k] = v
+        cur_fit = evaluate(pos).copy()
+        for i in range(N):
+            total[i] += 1
+            if cur_fit[i] > pbest_val[i]:
+                pbest_val[i] = cur_fit[i]; pbest[i] = pos[i]; succ_count[i] += 1
+            succ_rate[i] = succ_count[i] / total[i] if total[i] > 0 else 0.0
+        rescan()
+        if variant in (2, 4) and it % 5 == 0:                 # applyElitistLearningStrategy, one trial at a time
+            b = int(np.argmax(pbest_val))
+            sigma_scale = 0.1 * math.exp(-2.0 * succ_rate[b])
+            for _ in range(3):
+                trial = np.array([min(max(pos[b, k] + (sigma_scale * (ub[k] - lb[k])) * master_normal(master), lb[k]), ub[k]) for k in range(n)])
+                tf = float(ev(trial[None])[0])
+                els_trials += 1
+                if tf > pbest_val[b]:
+                    pos[b] = trial; pbest[b] = trial; pbest_val[b] = tf; cur_fit[b] = tf
+                    break
+                sigma_scale *= 0.5
+            if pbest_val[b] > gbest_val:
+                gbest_val, gbest = pbest_val[b], pbest[b].copy()
+    return swarm_batches, gbest_val, gbest, restarts, els_trials
+
+
+@pytest.mark.parametrize("variant,topology", [(0, 2), (2, 0), (2, 1)])
+def test_shipped_and_default_configurations_equal_the_python_restatement_bit_for_bit(host, variant, topology):
+    lb, ub, target = _box(5)
+    ev = lambda x: -(((x - target) / (ub - lb)) ** 2).sum(axis=1)
+    N, iters, seed = 13, 40, 99
+    st = dict(iterations=iters, swarm_size=N, seed=seed, variant=variant, topology=topology, use_opposition_learning=1,
+              use_adaptive_parameters=1, max_stagnation=2, restart_threshold=2e-3)
+    want, want_val, want_pos, restarts, els = _python_full_pso(ev, lb, ub, N, iters, seed, topology, variant, st, 2, 2e-3)
+    pm = host.ParameterManager(np.ones_like(lb), lb, ub, mode=0)
+    f, got = _recording(ev)
+    best, val, stats = host.Swarm(pm, st).run(f)
+    got_swarm = [b for b in got if len(b) != 3]               # the mirror scores the three elitist trials as one batch
+    assert len(got_swarm) == len(want)
+    for k, (a, b) in enumerate(zip(got_swarm, want)):
+        np.testing.assert_array_equal(a, b, err_msg=f"swarm batch {k} differs")
+    assert val == want_val
+    np.testing.assert_array_equal(best, want_pos)
+    assert stats["restarts"] == restarts and restarts >= 1     # the stagnation restart ran (batches of N - 3 positions)
+    assert stats["elitist_trials"] == els and (els > 0) == (variant == 2)
