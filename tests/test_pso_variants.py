@@ -372,6 +372,52 @@ class _Normal:
         return y * mult
 
 
+def _uniform_int(g, m):
+    """std::uniform_int_distribution<unsigned long>(0, m - 1) on std::mt19937 (libstdc++ >= 11, Lemire's method, 64-bit product)."""
+    M = 0xFFFFFFFF
+    product = g.raw() * m
+    low = product & M
+    if low < m:
+        threshold = ((M + 1) - m) % m
+        while low < threshold:
+            product = g.raw() * m
+            low = product & M
+    return product >> 32
+
+
+def _std_shuffle(a, g):
+    """std::shuffle of libstdc++ (bits/stl_algo.h): two swap positions from one draw while range^2 fits the engine's range."""
+    n = len(a)
+    if n == 0:
+        return
+    if (0xFFFFFFFF // n) >= n:
+        i = 1
+        if n % 2 == 0:
+            j = _uniform_int(g, 2)
+            a[i], a[j] = a[j], a[i]
+            i += 1
+        while i != n:
+            swap_range = i + 1
+            x = _uniform_int(g, swap_range * (swap_range + 1))
+            p0, p1 = x // (swap_range + 1), x % (swap_range + 1)
+            a[i], a[p0] = a[p0], a[i]
+            i += 1
+            a[i], a[p1] = a[p1], a[i]
+            i += 1
+        return
+    for i in range(1, n):
+        j = _uniform_int(g, i + 1)
+        a[i], a[j] = a[j], a[i]
+
+
+def _levy_sigma_u(alpha):
+    import ctypes
+    libm = ctypes.CDLL("libm.so.6")
+    libm.tgamma.restype = ctypes.c_double; libm.tgamma.argtypes = [ctypes.c_double]
+    tg = libm.tgamma                                            # std::tgamma of the C++ side is this function
+    return math.pow(tg(1 + alpha) * math.sin(math.pi * alpha / 2) / (tg((1 + alpha) / 2) * alpha * math.pow(2, (alpha - 1) / 2)), 1.0 / alpha)
+
+
 def _python_full_pso(ev, lb, ub, N, iterations, seed, topology, variant, st, max_stagnation, restart_threshold):
     n = len(lb)
     master = StdMt19937(seed)
@@ -464,18 +510,31 @@ def _python_full_pso(ev, lb, ub, N, iterations, seed, topology, variant, st, max
         else:
             omega = 0.9 + 0.1 * master.uniform(); c1 = 2.5 + master.uniform(); c2 = 0.5 + master.uniform()
         omega = min(max(omega, 0.1), 1.0); c1 = min(max(c1, 0.0), 4.0); c2 = min(max(c2, 0.0), 4.0)
+        mean_best = None
+        if variant in (1, 4):                                  # calculateMeanBestPosition (the mirror computes it for HYBRID too)
+            mean_best = np.zeros(n)
+            for i in range(N):
+                for k in range(n):
+                    mean_best[k] += pbest[i, k]
+            mean_best = mean_best / N
         seeds = [master.raw() for _ in range(N)]
         snap, snap_val = pbest.copy(), pbest_val.copy()
-        for i in range(N):
-            g = StdMt19937(seeds[i])
-            if topology == 0:
-                lbest = gbest
-            else:
+        lbest_of = list(range(N))
+        if topology != 0:                                      # neighbourhood bests from the snapshot, in particle order
+            for i in range(N):
+                if topology == 3:                              # RANDOM_DYNAMIC: four of the others, shuffled with the MASTER generator
+                    cand = [j for j in range(N) if j != i]
+                    _std_shuffle(cand, master)
+                    nb = [i] + cand[:min(4, len(cand))]
+                else:
+                    nb = _neighbors(topology, i, N)
                 b, bv = i, snap_val[i]
-                for j in _neighbors(topology, i, N):
+                for j in nb:
                     if snap_val[j] > bv:
                         b, bv = j, snap_val[j]
-                lbest = snap[b]
+                lbest_of[i] = b
+
+        def standard(i, g, lbest):
             r = [(g.uniform(), g.uniform()) for _ in range(n)]
             for k in range(n):
                 cognitive = c1 * (r[k][0] * (snap[i, k] - pos[i, k]))
@@ -489,6 +548,53 @@ def _python_full_pso(ev, lb, ub, N, iterations, seed, topology, variant, st, max
                 elif p > ub[k]:
                     p = ub[k] - abs(p - ub[k]); v *= -0.5
                 pos[i, k] = min(max(p, lb[k]), ub[k]); vel[i, k] = v
+
+        def quantum(i, g):                                     # quantumPSOUpdate
+            phi = g.uniform()
+            beta = st.get("quantum_beta", 1.0) * (1.0 - 0.5 * float(it) / iterations)
+            for k in range(n):
+                attractor = phi * snap[i, k] + (1 - phi) * gbest[k]
+                u = g.uniform()
+                Lq = 2.0 * beta * abs(mean_best[k] - pos[i, k])
+                if g.uniform() < 0.5:
+                    p = attractor + Lq * math.log(1.0 / u)
+                else:
+                    p = attractor - Lq * math.log(1.0 / u)
+                pos[i, k] = min(max(p, lb[k]), ub[k])
+
+        def levy(i, g):                                        # levyFlightUpdate: towards the GLOBAL best, then an occasional jump
+            standard(i, g, gbest)
+            if g.uniform() < 0.1 * (1.0 + succ_rate[i]):
+                alpha = st.get("levy_alpha", 1.5)
+                sigma_u = _levy_sigma_u(alpha)
+                steps = []
+                for _ in range(n):
+                    nrm = _Normal()                            # a fresh distribution per number
+                    u = nrm(g) * sigma_u
+                    v = max(abs(nrm(g)), 1e-10)
+                    steps.append(min(max(u / math.pow(v, 1.0 / alpha), -100.0), 100.0))
+                step_scale = 0.01 * (1.0 - stagnation / float(max_stagnation))
+                for k in range(n):
+                    scale = step_scale * (ub[k] - lb[k])
+                    p = pos[i, k] + scale * steps[k]
+                    pos[i, k] = min(max(p, lb[k]), ub[k])
+
+        for i in range(N):
+            g = StdMt19937(seeds[i])
+            lbest = gbest if topology == 0 else snap[lbest_of[i]]
+            if variant in (0, 2):
+                standard(i, g, lbest)
+            elif variant == 1:
+                quantum(i, g)
+            elif variant == 3:
+                levy(i, g)
+            else:                                              # HYBRID: the uniform is drawn only when its test is reached
+                if succ_rate[i] < 0.3 and g.uniform() < 0.5:
+                    levy(i, g)
+                elif succ_rate[i] > 0.7 and g.uniform() < 0.3:
+                    quantum(i, g)
+                else:
+                    standard(i, g, lbest)
         cur_fit = evaluate(pos).copy()
         for i in range(N):
             total[i] += 1
@@ -512,7 +618,7 @@ def _python_full_pso(ev, lb, ub, N, iterations, seed, topology, variant, st, max
     return swarm_batches, gbest_val, gbest, restarts, els_trials
 
 
-@pytest.mark.parametrize("variant,topology", [(0, 2), (2, 0), (2, 1)])
+@pytest.mark.parametrize("variant,topology", [(0, 2), (2, 0), (2, 1), (1, 0), (3, 1), (4, 2), (0, 3), (4, 3)])
 def test_shipped_and_default_configurations_equal_the_python_restatement_bit_for_bit(host, variant, topology):
     lb, ub, target = _box(5)
     ev = lambda x: -(((x - target) / (ub - lb)) ** 2).sum(axis=1)
@@ -530,4 +636,4 @@ def test_shipped_and_default_configurations_equal_the_python_restatement_bit_for
     assert val == want_val
     np.testing.assert_array_equal(best, want_pos)
     assert stats["restarts"] == restarts and restarts >= 1     # the stagnation restart ran (batches of N - 3 positions)
-    assert stats["elitist_trials"] == els and (els > 0) == (variant == 2)
+    assert stats["elitist_trials"] == els and (els > 0) == (variant in (2, 4))
