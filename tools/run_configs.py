@@ -20,6 +20,7 @@ ap.add_argument("--iterations", type=int, default=30)
 ap.add_argument("--draws", type=int, default=100000)
 ap.add_argument("--chunk", type=int, default=8192)
 ap.add_argument("--host-swarm", action="store_true", help="pso: keep the swarm on the host (the pre-device-resident path)")
+ap.add_argument("--ages", type=int, default=4, help="ppcq: 4, or 16 for the synthetic many-age-group variant of BASELINE configs[4]")
 a = ap.parse_args()
 pkg = g.load_package(); orc = g.load_oracle()
 from sepaihrd_b200 import drivers
@@ -57,17 +58,21 @@ elif a.what == "pso":
 elif a.what == "ppcq":
     # posterior-predictive QUANTILES (ResultAggregator): draws -> trajectories -> series -> sort -> quantiles, one C-ABI call
     o = orc.Oracle(p)
-    draws = o.jitter_params(4096, seed=11)
+    pq = p if a.ages == 4 else p.expand_ages(a.ages // 4)
+    oq = orc.Oracle(pq)
+    draws = oq.jitter_params(4096, seed=11)
     draws = np.tile(draws, ((a.draws + 4095) // 4096, 1))[:a.draws]
-    with BatchEvaluator(p, device=dev) as ev:
-        ev.posterior_predictive(draws[:1024], p.data_initial_state)
+    with BatchEvaluator(pq, device=dev) as ev:
+        ev.posterior_predictive(draws[:1024], pq.data_initial_state)
         t0 = time.perf_counter()
-        q, valid = ev.posterior_predictive(draws, p.data_initial_state)     # first call of this size: allocates ~10 GB of work buffers
+        q, valid = ev.posterior_predictive(draws, pq.data_initial_state)     # first call of this size: allocates the work buffers
         first = time.perf_counter() - t0
         t0 = time.perf_counter()
-        q, valid = ev.posterior_predictive(draws, p.data_initial_state)     # steady state: the ctx reuses them
+        q, valid = ev.posterior_predictive(draws, pq.data_initial_state)     # steady state: the ctx reuses them
         dt = time.perf_counter() - t0
-    out.update(draws=a.draws, ages=4, seconds=dt, first_call_seconds=first, draws_per_s=a.draws / dt, valid=valid, median_deaths_last_day=[float(x) for x in q[2, -1, :, 2]])
+        free_b, total_b = torch.cuda.mem_get_info(dev)
+    out.update(draws=a.draws, ages=a.ages, seconds=dt, first_call_seconds=first, draws_per_s=a.draws / dt, valid=valid,
+               device_gbytes_in_use=(total_b - free_b) / 1e9, median_deaths_last_day=[float(x) for x in q[2, -1, :, 2]])
 else:
     p16 = p.expand_ages(4)
     o16 = orc.Oracle(p16)
