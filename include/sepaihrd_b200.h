@@ -84,7 +84,9 @@ int32_t sepaihrd_slot_for_name(int32_t n_ages, int32_t n_beta, int32_t n_kappa, 
 /* ---- problem description (everything that is constant across parameter sets) ------------- */
 typedef struct sepaihrd_problem {
     int32_t abi_version;          /* = SEPAIHRD_ABI_VERSION */
-    int32_t n_ages;               /* n: 4 (Spain-2020) or 16 (synthetic variant) on the GPU; any <=16 */
+    int32_t n_ages;               /* n: 1..16.  4 (Spain-2020) and 16 (synthetic variant) run natively; any other count runs
+                                   * zero-padded to the next of the two (empty classes: population 0, no contacts, skipped
+                                   * observations), with every input and output in the caller's n                          */
     int32_t n_times;              /* K output times, strictly increasing (Simulator.cpp:82-90)          */
     int32_t n_obs;                /* rows of each observation matrix; must equal K - runup_offset       */
     const double* times;          /* [K]   (src/model/main.cpp:244-253: integers -int(runup)..num_days-1) */

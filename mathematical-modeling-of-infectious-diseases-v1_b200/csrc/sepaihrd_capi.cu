@@ -81,6 +81,7 @@ struct sepaihrd_ctx {
     double* h_stage = nullptr; size_t cap_stage = 0;          // pinned: packed rows | logL | status | steps of a merged launch
     long long merged_launches = 0, merged_requests = 0;
     int device = 0;
+    int n_user = 0;                // the caller's age-class count; n below is what the kernels run with (4 or 16, zero-padded classes)
     int n = 0, K = 0, n_obs = 0, nb = 0, nk = 0, P = 0, nslots = 0, nseg = 0, runup_offset = 0, n_nonneg = 0;
     int constraint_mode = 0, math_mode = SEPAIHRD_MATH_FAST;
     bool obs_mismatch = false;
@@ -170,7 +171,7 @@ sepaihrd_rc launch(sepaihrd_ctx* ctx, const sepaihrd::KParams& kp, int mode) {
     switch (ctx->n) {
         case 4: return launch_na<4, 128, 2>(ctx, kp, mode);
         case 16: return launch_na<16, 256, 1>(ctx, kp, mode);   // the 16-age observation block (117 KB) allows one block per SM: make it 8 warps
-        default: return fail(SEPAIHRD_ERR_UNSUPPORTED, "GPU kernels are instantiated for n_ages = 4 and 16");
+        default: return fail(SEPAIHRD_ERR_UNSUPPORTED, "GPU kernels are instantiated for 4 and 16 lanes per set (sepaihrd_create pads other age-class counts)");
     }
 }
 
@@ -198,6 +199,62 @@ __global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, double a, d
 #pragma unroll
     for (int c = 0; c < PEAK_CHAINS; ++c) s += v[c];
     if (s == 123.456) out[0] = s;   // never true: keeps the chains alive
+}
+
+}  // namespace
+
+namespace {
+
+// A copy of a problem description with its age classes padded to `np` (see sepaihrd_create).
+struct PaddedProblem {
+    sepaihrd_problem pb{};
+    std::vector<double> obs_h, obs_i, obs_d, pop, M, base, init;
+    std::vector<int32_t> slot;
+    static int map_slot(int s, const Layout& from, const Layout& to) {
+        if (s < from.age0()) return s;                                  // schedules and scalar rates: same place
+        if (s < from.mult0()) {                                          // per-age blocks a, h_infec, p, h, icu, d_H, d_ICU, d_community
+            const int k = (s - from.age0()) / from.n, age = (s - from.age0()) % from.n;
+            return to.age0() + k * to.n + age;
+        }
+        return to.mult0() + (s - from.mult0());                          // multipliers, seed_exposed, runup_days, beta
+    }
+    void build(const sepaihrd_problem& src, int np) {
+        pb = src;
+        const int n = src.n_ages;
+        const Layout from{n, src.n_beta, src.n_kappa}, to{np, src.n_beta, src.n_kappa};
+        auto pad_rows = [&](const double* a, std::vector<double>& out) {   // [n_obs][n] -> [n_obs][np], padding = skipped observation
+            out.assign((size_t)src.n_obs * np, -1.0);
+            for (int r = 0; r < src.n_obs; ++r) for (int j = 0; j < n; ++j) out[(size_t)r * np + j] = a[(size_t)r * n + j];
+        };
+        pad_rows(src.obs_hosp, obs_h); pad_rows(src.obs_icu, obs_i); pad_rows(src.obs_deaths, obs_d);
+        pop.assign(np, 0.0);
+        for (int j = 0; j < n; ++j) pop[j] = src.population[j];
+        M.assign((size_t)np * np, 0.0);                                    // column-major M(i, j) = M[j * n + i]
+        for (int j = 0; j < n; ++j) for (int i = 0; i < n; ++i) M[(size_t)j * np + i] = src.contact_matrix[(size_t)j * n + i];
+        base.assign(to.count(), 0.0);
+        for (int s = 0; s < from.count(); ++s) base[map_slot(s, from, to)] = src.base_slots[s];
+        init.assign((size_t)SEPAIHRD_NUM_COMPARTMENTS * np, 0.0);
+        for (int cpt = 0; cpt < SEPAIHRD_NUM_COMPARTMENTS; ++cpt) for (int j = 0; j < n; ++j) init[(size_t)cpt * np + j] = src.data_initial_state[(size_t)cpt * n + j];
+        slot.resize(src.n_params);
+        for (int i = 0; i < src.n_params; ++i) slot[i] = src.param_slot[i] < 0 ? src.param_slot[i] : map_slot(src.param_slot[i], from, to);
+        pb.n_ages = np;
+        pb.obs_hosp = obs_h.data(); pb.obs_icu = obs_i.data(); pb.obs_deaths = obs_d.data();
+        pb.population = pop.data(); pb.contact_matrix = M.data(); pb.base_slots = base.data();
+        pb.data_initial_state = init.data(); pb.param_slot = slot.data();
+    }
+};
+
+sepaihrd_rc create_impl(const sepaihrd_problem* pb, int n_user, int n, int32_t device, sepaihrd_ctx** out_ctx);
+
+// `count` compartment-major state vectors (C compartments) from n_in to n_out age classes: extra classes are dropped / zero-filled
+__global__ void repack_ages_kernel(const double* __restrict__ in, long long in_stride, double* __restrict__ out, long long out_stride,
+                                   long long count, int C, int n_in, int n_out) {
+    const long long per = (long long)C * n_out, total = count * per;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long v = i / per;
+        const int r = (int)(i % per), cpt = r / n_out, age = r % n_out;
+        out[v * out_stride + r] = (age < n_in) ? in[v * in_stride + (long long)cpt * n_in + age] : 0.0;
+    }
 }
 
 }  // namespace
@@ -265,10 +322,33 @@ sepaihrd_rc sepaihrd_create(const sepaihrd_problem* pb, int32_t device, sepaihrd
     if (P < 1) return fail(SEPAIHRD_ERR_INVALID_ARGUMENT, "Parameter names list cannot be empty.");      // ParameterManager.cpp:26-28
     if (pb->abs_tol < 0 || pb->rel_tol < 0) return fail(SEPAIHRD_ERR_INVALID_ARGUMENT, "Error tolerances cannot be negative.");   // Simulator.cpp:46-52
     if (!(pb->dt_hint > 0)) return fail(SEPAIHRD_ERR_INVALID_ARGUMENT, "Time step hint must be positive.");   // Simulator.cpp:39-41
+    {
+        const Layout Lu{n, nb, nk};
+        for (int i = 0; i < P; ++i)
+            if (pb->param_slot[i] < -1 || pb->param_slot[i] >= Lu.count())
+                return fail(SEPAIHRD_ERR_INVALID_ARGUMENT, "param_slot out of range (use sepaihrd_slot_for_name)");
+    }
+    // The kernels are instantiated for 4 and 16 lanes per parameter set.  Any other age-class count runs in the next larger one
+    // with EMPTY extra classes: population 0 (hence 1/N = 0 and age fraction 0, see below), zero contact rows and columns, zero
+    // rates, zero initial state, observations marked as skipped.  Such a class has zero derivatives, a zero error estimate (it
+    // never decides a step) and contributes no likelihood term, so the real classes compute exactly what they would alone.
+    const int n_user = n;
+    PaddedProblem padded;
+    if (n != 4 && n != 16) {
+        padded.build(*pb, n <= 4 ? 4 : 16);
+        pb = &padded.pb;
+    }
+    const int n_run = pb->n_ages;
+    return create_impl(pb, n_user, n_run, device, out_ctx);
+}
+
+}  // extern "C"
+
+namespace {
+
+sepaihrd_rc create_impl(const sepaihrd_problem* pb, int n_user, int n, int32_t device, sepaihrd_ctx** out_ctx) {
+    const int K = pb->n_times, nb = pb->n_beta, nk = pb->n_kappa, P = pb->n_params;
     const Layout L{n, nb, nk};
-    for (int i = 0; i < P; ++i)
-        if (pb->param_slot[i] < -1 || pb->param_slot[i] >= L.count())
-            return fail(SEPAIHRD_ERR_INVALID_ARGUMENT, "param_slot out of range (use sepaihrd_slot_for_name)");
 
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || count < 1)
@@ -279,6 +359,7 @@ sepaihrd_rc sepaihrd_create(const sepaihrd_problem* pb, int32_t device, sepaihrd
 
     sepaihrd_ctx* ctx = new sepaihrd_ctx();
     ctx->device = device;
+    ctx->n_user = n_user;
     ctx->n = n; ctx->K = K; ctx->n_obs = pb->n_obs; ctx->nb = nb; ctx->nk = nk; ctx->P = P; ctx->nslots = L.count();
     ctx->constraint_mode = pb->constraint_mode; ctx->abs_tol = pb->abs_tol; ctx->rel_tol = pb->rel_tol; ctx->dt_hint = pb->dt_hint;
     // runup_offset_ = first index with t >= 0 (ObjectiveFunction.cpp:39-46)
@@ -425,6 +506,10 @@ sepaihrd_rc sepaihrd_create(const sepaihrd_problem* pb, int32_t device, sepaihrd
     *out_ctx = ctx;
     return SEPAIHRD_OK;
 }
+
+}  // namespace
+
+extern "C" {
 
 void sepaihrd_destroy(sepaihrd_ctx* ctx) {
     if (!ctx) return;
@@ -676,14 +761,42 @@ static sepaihrd_rc simulate_device_impl(sepaihrd_ctx* ctx, const double* d_param
     if (B == 0) return SEPAIHRD_OK;
     std::lock_guard<std::recursive_mutex> lock(ctx->mu);
     CUDA_TRY(cudaSetDevice(ctx->device));
+    const int rows = (ctx->K + stride - 1) / stride;
+    // padded age classes (sepaihrd_create): the caller's states are widened on the way in, the trajectories narrowed on the way
+    // out; the draw-minor layout is internal (posterior-predictive pass) and stays padded
+    const bool repack = ctx->n != ctx->n_user && !draw_minor;
+    const int C = (what == SEPAIHRD_TRAJ_FULL) ? SEPAIHRD_NUM_COMPARTMENTS : 3;
+    double* d_kernel_out = d_out;
+    if (repack) {
+        if (d_init) {
+            const long long n_vec = (init_stride == 0) ? 1 : B;
+            const long long wide = (long long)SEPAIHRD_NUM_COMPARTMENTS * ctx->n;
+            double* d_wide = (double*)sepaihrd_internal::scratch(ctx, 14, sizeof(double) * (size_t)(n_vec * wide));
+            if (!d_wide) return fail(SEPAIHRD_ERR_OUT_OF_MEMORY, "no room for the padded initial states");
+            repack_ages_kernel<<<(unsigned)std::min<long long>((n_vec * wide + 255) / 256, 65535), 256, 0, ctx->stream>>>(
+                d_init, init_stride, d_wide, wide, n_vec, SEPAIHRD_NUM_COMPARTMENTS, ctx->n_user, ctx->n);
+            CUDA_TRY(cudaGetLastError());
+            d_init = d_wide;
+            if (init_stride != 0) init_stride = wide;
+        }
+        d_kernel_out = (double*)sepaihrd_internal::scratch(ctx, 15, sizeof(double) * (size_t)B * rows * C * ctx->n);
+        if (!d_kernel_out) return fail(SEPAIHRD_ERR_OUT_OF_MEMORY, "no room for the padded trajectories: split the batch");
+    }
     sepaihrd::KParams kp = ctx->kp;
     kp.constraint_mode = ctx->constraint_mode;
     kp.params = d_params; kp.B = B; kp.ld = ld;
     kp.out_ll = nullptr; kp.out_status = d_out_status; kp.out_steps = nullptr;
-    kp.out_traj = d_out; kp.traj_what = what; kp.traj_stride = stride; kp.traj_rows = (ctx->K + stride - 1) / stride;
+    kp.out_traj = d_kernel_out; kp.traj_what = what; kp.traj_stride = stride; kp.traj_rows = rows;
     kp.traj_draw_minor = draw_minor ? 1 : 0;
     kp.init_states = d_init; kp.init_stride = init_stride;
-    return launch(ctx, kp, sepaihrd::MODE_TRAJ);
+    const sepaihrd_rc rc = launch(ctx, kp, sepaihrd::MODE_TRAJ);
+    if (rc != SEPAIHRD_OK || !repack) return rc;
+    const long long n_vec = (long long)B * rows, narrow = (long long)C * ctx->n_user;
+    repack_ages_kernel<<<(unsigned)std::min<long long>((n_vec * narrow + 255) / 256, 148 * 32), 256, 0, ctx->stream>>>(
+        d_kernel_out, (long long)C * ctx->n, d_out, narrow, n_vec, C, ctx->n, ctx->n_user);
+    CUDA_TRY(cudaGetLastError());
+    ctx->launches += 1;
+    return SEPAIHRD_OK;
 }
 
 sepaihrd_rc sepaihrd_simulate_batch_device(sepaihrd_ctx* ctx, const double* d_params, int64_t B, int64_t ld,
@@ -706,7 +819,7 @@ sepaihrd_rc sepaihrd_simulate_batch(sepaihrd_ctx* ctx, const double* params, int
     if (B == 0) return SEPAIHRD_OK;
     std::lock_guard<std::recursive_mutex> lock(ctx->mu);
     CUDA_TRY(cudaSetDevice(ctx->device));
-    const int W = (what == SEPAIHRD_TRAJ_FULL) ? SEPAIHRD_NUM_COMPARTMENTS * ctx->n : 3 * ctx->n;
+    const int W = (what == SEPAIHRD_TRAJ_FULL) ? SEPAIHRD_NUM_COMPARTMENTS * ctx->n_user : 3 * ctx->n_user;
     const size_t rows = (size_t)(ctx->K + stride - 1) / stride;
     const size_t total = (size_t)B * rows * W;
     sepaihrd_rc rc;
@@ -728,15 +841,15 @@ sepaihrd_rc sepaihrd_simulate_from_state(sepaihrd_ctx* ctx, const double* params
     if (!ctx || !out || !initial_states || (B > 0 && !params)) return fail(SEPAIHRD_ERR_INVALID_ARGUMENT, "null argument");
     if (B < 0 || ld < ctx->P) return fail(SEPAIHRD_ERR_INVALID_ARGUMENT, "Parameter vector size mismatch.");
     if (stride < 1) return fail(SEPAIHRD_ERR_INVALID_ARGUMENT, "stride must be >= 1");
-    if (state_stride != 0 && state_stride < (int64_t)SEPAIHRD_NUM_COMPARTMENTS * ctx->n)
+    if (state_stride != 0 && state_stride < (int64_t)SEPAIHRD_NUM_COMPARTMENTS * ctx->n_user)
         return fail(SEPAIHRD_ERR_INVALID_ARGUMENT, "Initial state size does not match model state size.");   // Simulator.cpp:64-69
     if (B == 0) return SEPAIHRD_OK;
     std::lock_guard<std::recursive_mutex> lock(ctx->mu);
     CUDA_TRY(cudaSetDevice(ctx->device));
-    const int W = (what == SEPAIHRD_TRAJ_FULL) ? SEPAIHRD_NUM_COMPARTMENTS * ctx->n : 3 * ctx->n;
+    const int W = (what == SEPAIHRD_TRAJ_FULL) ? SEPAIHRD_NUM_COMPARTMENTS * ctx->n_user : 3 * ctx->n_user;
     const size_t rows = (size_t)(ctx->K + stride - 1) / stride;
     const size_t total = (size_t)B * rows * W;
-    const size_t n_init = (state_stride == 0) ? (size_t)SEPAIHRD_NUM_COMPARTMENTS * ctx->n : (size_t)B * state_stride;
+    const size_t n_init = (state_stride == 0) ? (size_t)SEPAIHRD_NUM_COMPARTMENTS * ctx->n_user : (size_t)B * state_stride;
     sepaihrd_rc rc;
     if ((rc = grow(&ctx->d_params, &ctx->cap_params, (size_t)B * ld + n_init)) != SEPAIHRD_OK) return rc;
     if ((rc = grow(&ctx->d_out, &ctx->cap_out, total)) != SEPAIHRD_OK) return rc;
@@ -786,7 +899,7 @@ sepaihrd_rc sepaihrd_measure_fp64_peak(int32_t device, double* out_dfma_per_seco
 
 // ---- accessors for the other translation units of the library (sepaihrd_internal.h) -----------------------------
 namespace sepaihrd_internal {
-Dims dims(const sepaihrd_ctx* ctx) { return Dims{ctx->n, ctx->K, ctx->runup_offset, ctx->n_nonneg, ctx->P, ctx->device}; }
+Dims dims(const sepaihrd_ctx* ctx) { return Dims{ctx->n, ctx->K, ctx->runup_offset, ctx->n_nonneg, ctx->P, ctx->device, ctx->n_user}; }
 cudaStream_t stream(const sepaihrd_ctx* ctx) { return ctx->stream; }
 sepaihrd_rc fail_with(sepaihrd_rc rc, const char* msg) { return fail(rc, msg); }
 const double* lower_bounds(const sepaihrd_ctx* ctx) { return ctx->blob.data() + ctx->kp.o_lo; }

@@ -9,7 +9,7 @@
 
 namespace sepaihrd_internal {
 
-struct Dims { int n, K, runup_offset, n_nonneg, P, device; };   // n_nonneg: output times >= 0 (they are the last ones)
+struct Dims { int n, K, runup_offset, n_nonneg, P, device, n_user; };   // n: age classes the kernels run with (n_user zero-padded to 4 or 16); n_nonneg: output times >= 0 (the last ones)
 Dims dims(const sepaihrd_ctx* ctx);
 cudaStream_t stream(const sepaihrd_ctx* ctx);
 sepaihrd_rc fail_with(sepaihrd_rc rc, const char* msg);

@@ -135,7 +135,16 @@ extern "C" sepaihrd_rc sepaihrd_posterior_predictive(sepaihrd_ctx* ctx, const do
     if (oom) return fail_with(SEPAIHRD_ERR_OUT_OF_MEMORY, "posterior-predictive work buffers do not fit: split the draws");
     void* d_tmp = nullptr;
     PPC_TRY(cudaMemcpyAsync(d_params, params, sizeof(double) * (size_t)B * ld, cudaMemcpyHostToDevice, s));
+    // padded age classes (sepaihrd_create): the caller's state has d.n_user classes per compartment, the pass runs with n
+    std::vector<double> wide_init;
+    if (n != d.n_user) {
+        wide_init.assign((size_t)SEPAIHRD_NUM_COMPARTMENTS * n, 0.0);
+        for (int cpt = 0; cpt < SEPAIHRD_NUM_COMPARTMENTS; ++cpt)
+            for (int a = 0; a < d.n_user; ++a) wide_init[(size_t)cpt * n + a] = initial_state[(size_t)cpt * d.n_user + a];
+        initial_state = wide_init.data();
+    }
     PPC_TRY(cudaMemcpyAsync(d_init, initial_state, sizeof(double) * SEPAIHRD_NUM_COMPARTMENTS * n, cudaMemcpyHostToDevice, s));
+    if (!wide_init.empty()) PPC_TRY(cudaStreamSynchronize(s));      // the staging vector is pageable and local
     PPC_TRY(cudaMemcpyAsync(d_probs, probs, sizeof(double) * n_probs, cudaMemcpyHostToDevice, s));
     PPC_TRY(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), s));
 
@@ -165,9 +174,16 @@ extern "C" sepaihrd_rc sepaihrd_posterior_predictive(sepaihrd_ctx* ctx, const do
         PPC_TRY(cudaGetLastError());
     }
     unsigned long long cnt = 0;
-    PPC_TRY(cudaMemcpyAsync(out_quantiles, d_q, sizeof(double) * 6 * (size_t)n_cols * n_probs, cudaMemcpyDeviceToHost, s));
+    std::vector<double> wide_q;
+    double* q_dst = out_quantiles;
+    if (n != d.n_user) { wide_q.resize(6 * (size_t)n_cols * n_probs); q_dst = wide_q.data(); }
+    PPC_TRY(cudaMemcpyAsync(q_dst, d_q, sizeof(double) * 6 * (size_t)n_cols * n_probs, cudaMemcpyDeviceToHost, s));
     PPC_TRY(cudaMemcpyAsync(&cnt, d_cnt, sizeof(cnt), cudaMemcpyDeviceToHost, s));
     PPC_TRY(cudaStreamSynchronize(s));
+    if (n != d.n_user)                                                  // [6][T][n][q] -> [6][T][n_user][q]
+        for (size_t st = 0; st < 6 * (size_t)T; ++st)
+            for (int a = 0; a < d.n_user; ++a)
+                for (int q = 0; q < n_probs; ++q) out_quantiles[(st * d.n_user + a) * n_probs + q] = wide_q[(st * n + a) * n_probs + q];
     if (out_valid_draws) *out_valid_draws = (int64_t)cnt;
     cleanup();
     return SEPAIHRD_OK;

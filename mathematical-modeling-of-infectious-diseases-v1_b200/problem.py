@@ -304,6 +304,40 @@ class Problem:
             meta=dict(self.meta, expanded_from=n, factor=f))
 
 
+    def select_ages(self, keep) -> "Problem":
+        """The sub-problem of the age classes ``keep`` (indices, in the order given): populations, contact sub-matrix, per-age
+        parameters, observations and initial state of those classes only.  Gives problems with any class count (3, 5, 7, ...)
+        for the tests of the zero-padded kernel path (sepaihrd_create)."""
+        keep = [int(i) for i in keep]
+        n, n2 = self.n_ages, len(keep)
+        if n2 < 1 or any(i < 0 or i >= n for i in keep):
+            raise ValueError("age indices out of range")
+        lay, lay2 = self.layout, SlotLayout(n2, len(self.beta_end_times), len(self.kappa_end_times))
+        base2 = np.empty(lay2.count)
+        base2[:lay.age0] = self.base_slots[:lay.age0]
+        for b in range(len(_AGE_BLOCKS)):
+            base2[lay2.age0 + b * n2: lay2.age0 + (b + 1) * n2] = self.base_slots[lay.age0 + b * n: lay.age0 + (b + 1) * n][keep]
+        base2[lay2.mult0:] = self.base_slots[lay.mult0:]
+        names2: List[str] = []
+        lo2: List[float] = []; hi2: List[float] = []; sg2: List[float] = []
+        for nm, lo, hi, sg in zip(self.param_names, self.lower_bound, self.upper_bound, self.sigmas):
+            blk = next((b for b in sorted(_AGE_BLOCKS, key=len, reverse=True) if nm.startswith(b + "_") and nm[len(b) + 1:].isdigit()), None)
+            if blk is None:
+                names2.append(nm); lo2.append(lo); hi2.append(hi); sg2.append(sg)
+            elif int(nm[len(blk) + 1:]) in keep:
+                names2.append(f"{blk}_{keep.index(int(nm[len(blk) + 1:]))}"); lo2.append(lo); hi2.append(hi); sg2.append(sg)
+        init2 = self.data_initial_state.reshape(NUM_COMPARTMENTS, n)[:, keep]
+        return Problem(
+            n_ages=n2, times=self.times.copy(),
+            obs_hosp=self.obs_hosp[:, keep].copy(), obs_icu=self.obs_icu[:, keep].copy(), obs_deaths=self.obs_deaths[:, keep].copy(),
+            population=self.population[keep].copy(), contact_matrix=self.contact_matrix[np.ix_(keep, keep)].copy(),
+            beta_end_times=self.beta_end_times.copy(), kappa_end_times=self.kappa_end_times.copy(),
+            base_slots=base2, data_initial_state=init2.reshape(-1).copy(), param_names=names2,
+            lower_bound=lo2, upper_bound=hi2, sigmas=sg2, constraint_mode=self.constraint_mode,
+            abs_tol=self.abs_tol, rel_tol=self.rel_tol, dt_hint=self.dt_hint,
+            meta=dict(self.meta, selected_from=n, ages=keep))
+
+
 def default_problem_path() -> str:
     return os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "spain2020_problem.json")
 

@@ -370,6 +370,45 @@ def test_posterior_predictive_quantiles_match_numpy_on_oracle_trajectories(probl
     assert v1 == 1 and np.all(one[..., 0] == one[..., 2])
 
 
+@pytest.mark.parametrize("ages", [[2], [1, 0], [0, 1, 3], "5 of 8", "7 of 8", "11 of 16"])
+def test_any_number_of_age_classes_runs_zero_padded(problem, orc, ev_mod, ages):
+    """The kernels run with 4 or 16 lanes per set; sepaihrd_create pads any other age-class count with empty classes
+    (population 0, zero contacts and rates, skipped observations).  logL, step counts, trajectories, caller-supplied initial
+    states and the posterior-predictive quantiles must be those of the unpadded problem (oracle)."""
+    if isinstance(ages, str):
+        k, of = int(ages.split()[0]), int(ages.split()[2])
+        p = problem.expand_ages(of // 4).select_ages(list(range(of))[:k - 1] + [of - 1])
+    else:
+        p = problem.select_ages(ages)
+    o = orc.Oracle(p)
+    P = np.vstack([p.base_params()[None], o.jitter_params(40, seed=3), o.uniform_params(23, seed=4)])
+    ref, st_ref, steps_ref, _ = o.eval_batch(P)
+    for math in (ev_mod.MATH_FAST, ev_mod.MATH_STRICT):
+        with ev_mod.BatchEvaluator(p, device=0, math=math) as ev:
+            ll, st, steps = ev.eval_batch(P, return_steps=True)
+            np.testing.assert_array_equal(st, st_ref)
+            assert _rel(ll, ref).max() < 1e-8
+            assert int((steps != steps_ref).any(axis=1).sum()) == 0
+            tr, _ = ev.simulate_batch(P[:9])
+            tr_ref, _ = o.simulate_batch(P[:9])
+            assert tr.shape == tr_ref.shape == (9, p.n_times, 11 * p.n_ages)
+            assert (np.abs(tr - tr_ref) / np.maximum(np.abs(tr_ref), 1.0)).max() < 1e-6
+            ob, _ = ev.simulate_batch(P[:5], what=1, stride=7)          # D, CumH, CumICU only, every 7th output time
+            ob_ref, _ = o.simulate_batch(P[:5], what=1, stride=7)
+            assert ob.shape == ob_ref.shape and (np.abs(ob - ob_ref) / np.maximum(np.abs(ob_ref), 1.0)).max() < 1e-6
+            # Simulator::run semantics: one state per set, and one shared state
+            states = tr_ref[:4, 30, :].copy()
+            fs, _ = ev.simulate_from_state(P[:4], states)
+            fs_ref, _ = o.simulate_from_state(P[:4], states)
+            assert (np.abs(fs - fs_ref) / np.maximum(np.abs(fs_ref), 1.0)).max() < 1e-6
+            if math == ev_mod.MATH_FAST:
+                probs = (0.05, 0.5, 0.95)
+                q, valid = ev.posterior_predictive(P[:32], p.data_initial_state, probs)
+                q_ref, n_ok = _ppc_reference(p, o, P[:32], p.data_initial_state, probs)
+                assert valid == n_ok == 32 and q.shape == q_ref.shape == (6, int((p.times >= 0).sum()), p.n_ages, 3)
+                assert (np.abs(q - q_ref) / np.maximum(np.abs(q_ref), 1e-6)).max() < 1e-8
+
+
 def test_concurrent_callers_are_serialised_and_merged_into_shared_launches(problem, oracle, ev_mod):
     """calculate() is called from OpenMP loops in the reference (ParticleSwarmOptimizer.cpp:368-424): many host threads on ONE ctx.
     Every thread must get its own vector's value, and calls that arrive while a launch is in flight share the next launch."""
