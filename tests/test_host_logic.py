@@ -158,3 +158,26 @@ def test_expand_ages_preserves_totals(problem):
     # contact structure: sum over the sub-classes of j reproduces M(i, j)
     np.testing.assert_allclose(p16.contact_matrix.reshape(4, 4, 4, 4)[:, 0].sum(-1), problem.contact_matrix)
     assert "h_infec_15" in p16.param_names and len(p16.param_names) == 62 + 3 * 32
+
+
+def test_select_ages_builds_consistent_sub_problems(problem, orc):
+    """Problem.select_ages (fixtures for the zero-padded kernel path): the identity selection is the problem itself, a
+    permutation leaves the likelihood unchanged up to summation order, and a sub-problem drops exactly the per-age parameters
+    of the removed classes."""
+    same = problem.select_ages([0, 1, 2, 3])
+    assert same.param_names == problem.param_names
+    np.testing.assert_array_equal(same.base_slots, problem.base_slots)
+    np.testing.assert_array_equal(same.contact_matrix, problem.contact_matrix)
+    x = problem.base_params()
+    ll = orc.Oracle(problem).eval_one(x)["ll"]
+    perm = problem.select_ages([3, 1, 0, 2])
+    xp = perm.base_params()
+    assert sorted(perm.param_names) == sorted(problem.param_names)
+    assert abs(orc.Oracle(perm).eval_one(xp)["ll"] - ll) <= 1e-9 * abs(ll)
+    sub = problem.select_ages([0, 3])
+    assert sub.n_ages == 2 and sub.n_params == problem.n_params - 2 * 8 and sub.layout.count == problem.layout.count - 2 * 8
+    assert "h_infec_1" in sub.param_names and "h_infec_2" not in sub.param_names
+    i_old, i_new = problem.param_names.index("h_infec_3"), sub.param_names.index("h_infec_1")
+    assert problem.base_params()[i_old] == sub.base_params()[i_new]
+    with pytest.raises(ValueError):
+        problem.select_ages([0, 4])
