@@ -16,6 +16,10 @@
 #include "sepaihrd_internal.h"
 #include "sepaihrd_kernels.cuh"
 
+#ifndef SEPAIHRD_E2E_DEFAULT_SPLIT
+#define SEPAIHRD_E2E_DEFAULT_SPLIT 85, 21, 5      // measured best on a B200 with PCIe 5 (tools/e2e_split.py); chunk ends of the host-buffer evaluation at B/d for each d listed (descending)
+#endif
+
 namespace {
 
 thread_local std::string g_last_error;
@@ -96,7 +100,7 @@ struct sepaihrd_ctx {
     unsigned* d_tile_counter = nullptr;
     cudaStream_t own_stream = nullptr;
     cudaStream_t copy_stream = nullptr;   // host-pointer entry points: H2D / early D2H next to the compute stream
-    cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_kernel = nullptr;
+    cudaEvent_t ev_copy[4] = {nullptr, nullptr, nullptr, nullptr}, ev_kernel = nullptr;
     cudaStream_t stream = nullptr;
     int num_sms = 0;
     // scratch for the host-pointer entry points (grown on demand)
@@ -492,7 +496,7 @@ sepaihrd_rc create_impl(const sepaihrd_problem* pb, int n_user, int n, int32_t d
     if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_tile_counter, sizeof(unsigned));
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
-    for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&ctx->ev_copy[i], cudaEventDisableTiming);
+    for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&ctx->ev_copy[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_kernel, cudaEventDisableTiming);
     if (e != cudaSuccess) {
         std::string msg = std::string("CUDA setup failed: ") + cudaGetErrorString(e);
@@ -524,7 +528,7 @@ void sepaihrd_destroy(sepaihrd_ctx* ctx) {
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
-    for (int i = 0; i < 2; ++i) if (ctx->ev_copy[i]) cudaEventDestroy(ctx->ev_copy[i]);
+    for (int i = 0; i < 4; ++i) if (ctx->ev_copy[i]) cudaEventDestroy(ctx->ev_copy[i]);
     if (ctx->ev_kernel) cudaEventDestroy(ctx->ev_kernel);
     delete ctx;
 }
@@ -631,12 +635,30 @@ sepaihrd_rc eval_batch_serial(sepaihrd_ctx* ctx, const double* params, int64_t B
     if ((rc = grow(&ctx->d_out, &ctx->cap_out, (size_t)B)) != SEPAIHRD_OK) return rc;
     if ((rc = grow(&ctx->d_status, &ctx->cap_status, (size_t)B)) != SEPAIHRD_OK) return rc;
     if (out_steps && (rc = grow(&ctx->d_steps, &ctx->cap_steps, (size_t)B * 2)) != SEPAIHRD_OK) return rc;
-    // Two chunks on two streams: while the kernel works on the first ~1/12 of the batch, the copy stream brings the
-    // rest over (H2D moves ~10x more sets per second than the kernel consumes), so only the first chunk's copy and the
-    // 12-byte-per-set results are exposed.  Small batches go as one piece.
-    const int64_t first = (B >= (1 << 16)) ? ((B / 12 + 255) / 256) * 256 : B;
-    const int64_t off[3] = {0, first, B};
-    const int n_chunks = (first < B) ? 2 : 1;
+    // Chunks on two streams: while the kernel works on a chunk, the copy stream brings the next ones over (H2D moves several
+    // times more sets per second than the kernel consumes), so only the FIRST chunk's copy and the last chunk's 12-byte-per-set
+    // results are exposed; the chunks grow geometrically so that each copy still finishes under the kernel before it.  Small
+    // batches go as one piece.  SEPAIHRD_E2E_SPLIT="d1,d2,..." (chunk ends at B/d1 < B/d2 < ...) overrides the default for
+    // experiments.
+    static const std::vector<int> split = [] {
+        std::vector<int> v;
+        if (const char* e = std::getenv("SEPAIHRD_E2E_SPLIT")) {
+            for (const char* p = e; *p;) { const long d = std::strtol(p, const_cast<char**>(&p), 10); if (d > 1) v.push_back((int)d); while (*p == ',' || *p == ' ') ++p; }
+        }
+        if (v.empty()) v = {SEPAIHRD_E2E_DEFAULT_SPLIT};
+        if (v.size() > 3) v.resize(3);
+        std::sort(v.begin(), v.end(), [](int a, int b) { return a > b; });
+        return v;
+    }();
+    int64_t off[5] = {0, B, B, B, B};
+    int n_chunks = 1;
+    if (B >= (1 << 16)) {
+        for (int d : split) {
+            const int64_t end = ((B / d + 255) / 256) * 256;
+            if (end > off[n_chunks - 1] && end < B) { off[n_chunks] = end; ++n_chunks; }
+        }
+        off[n_chunks] = B;
+    }
     for (int c = 0; c < n_chunks; ++c) {
         const int64_t b0 = off[c], nb = off[c + 1] - off[c];
         CUDA_TRY(cudaMemcpyAsync(ctx->d_params + b0 * ld, params + b0 * ld, sizeof(double) * (size_t)nb * ld, cudaMemcpyHostToDevice, ctx->copy_stream));
@@ -648,7 +670,7 @@ sepaihrd_rc eval_batch_serial(sepaihrd_ctx* ctx, const double* params, int64_t B
         rc = sepaihrd_eval_batch_device(ctx, ctx->d_params + b0 * ld, nb, ld, ctx->d_out + b0, ctx->d_status + b0,
                                         out_steps ? ctx->d_steps + 2 * b0 : nullptr);
         if (rc != SEPAIHRD_OK) return rc;
-        if (c + 1 < n_chunks) {      // results of the first chunk go back under the second kernel
+        if (c + 1 < n_chunks) {      // results of this chunk go back under the next kernel
             CUDA_TRY(cudaEventRecord(ctx->ev_kernel, ctx->stream));
             CUDA_TRY(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_kernel, 0));
             CUDA_TRY(cudaMemcpyAsync(out_ll + b0, ctx->d_out + b0, sizeof(double) * (size_t)nb, cudaMemcpyDeviceToHost, ctx->copy_stream));
