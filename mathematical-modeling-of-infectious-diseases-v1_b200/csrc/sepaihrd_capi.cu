@@ -17,7 +17,7 @@
 #include "sepaihrd_kernels.cuh"
 
 #ifndef SEPAIHRD_E2E_DEFAULT_SPLIT
-#define SEPAIHRD_E2E_DEFAULT_SPLIT 85, 21, 5      // measured best on a B200 with PCIe 5 (tools/e2e_split.py); chunk ends of the host-buffer evaluation at B/d for each d listed (descending)
+#define SEPAIHRD_E2E_DEFAULT_SPLIT 128, 32, 8      // measured best on a B200 with PCIe 5 (tools/e2e_split.py); chunk ends of the host-buffer evaluation at B/d for each d listed (descending)
 #endif
 
 namespace {
@@ -100,6 +100,8 @@ struct sepaihrd_ctx {
     unsigned* d_tile_counter = nullptr;
     cudaStream_t own_stream = nullptr;
     cudaStream_t copy_stream = nullptr;   // host-pointer entry points: H2D / early D2H next to the compute stream
+    cudaStream_t stream2 = nullptr;       // host-pointer evaluation: odd chunks run here, so a chunk's first blocks start while the previous chunk's last warps drain
+    cudaEvent_t ev_chunk[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_copy[4] = {nullptr, nullptr, nullptr, nullptr}, ev_kernel = nullptr;
     cudaStream_t stream = nullptr;
     int num_sms = 0;
@@ -493,9 +495,11 @@ sepaihrd_rc create_impl(const sepaihrd_problem* pb, int n_user, int n, int32_t d
     cudaError_t e = cudaGetDeviceProperties(&prop, device);
     if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_blob, kp.blob_bytes);
     if (e == cudaSuccess) e = cudaMemcpy(ctx->d_blob, B.data(), kp.blob_bytes, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_tile_counter, sizeof(unsigned));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_tile_counter, 4 * sizeof(unsigned));   // one per chunk in flight (host-pointer evaluation)
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking);
+    for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&ctx->ev_chunk[i], cudaEventDisableTiming);
     for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&ctx->ev_copy[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_kernel, cudaEventDisableTiming);
     if (e != cudaSuccess) {
@@ -528,6 +532,8 @@ void sepaihrd_destroy(sepaihrd_ctx* ctx) {
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+    for (int i = 0; i < 4; ++i) if (ctx->ev_chunk[i]) cudaEventDestroy(ctx->ev_chunk[i]);
     for (int i = 0; i < 4; ++i) if (ctx->ev_copy[i]) cudaEventDestroy(ctx->ev_copy[i]);
     if (ctx->ev_kernel) cudaEventDestroy(ctx->ev_kernel);
     delete ctx;
@@ -664,24 +670,31 @@ sepaihrd_rc eval_batch_serial(sepaihrd_ctx* ctx, const double* params, int64_t B
         CUDA_TRY(cudaMemcpyAsync(ctx->d_params + b0 * ld, params + b0 * ld, sizeof(double) * (size_t)nb * ld, cudaMemcpyHostToDevice, ctx->copy_stream));
         CUDA_TRY(cudaEventRecord(ctx->ev_copy[c], ctx->copy_stream));
     }
+    // Chunk c runs on the ctx stream (even c) or on a second compute stream (odd c) with its own tile counter: nothing orders
+    // the kernels among themselves, so the first blocks of chunk c + 1 start on the SMs the last warps of chunk c have left.
+    struct Restore {
+        sepaihrd_ctx* ctx; cudaStream_t stream; unsigned* counter;
+        ~Restore() { ctx->stream = stream; ctx->d_tile_counter = counter; }
+    } restore{ctx, ctx->stream, ctx->d_tile_counter};
+    static const bool two_streams = std::getenv("SEPAIHRD_E2E_ONE_STREAM") == nullptr;
     for (int c = 0; c < n_chunks; ++c) {
         const int64_t b0 = off[c], nb = off[c + 1] - off[c];
-        CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[c], 0));
+        cudaStream_t s = (two_streams && (c & 1)) ? ctx->stream2 : restore.stream;
+        ctx->stream = s;
+        ctx->d_tile_counter = restore.counter + c;
+        CUDA_TRY(cudaStreamWaitEvent(s, ctx->ev_copy[c], 0));
         rc = sepaihrd_eval_batch_device(ctx, ctx->d_params + b0 * ld, nb, ld, ctx->d_out + b0, ctx->d_status + b0,
                                         out_steps ? ctx->d_steps + 2 * b0 : nullptr);
         if (rc != SEPAIHRD_OK) return rc;
-        if (c + 1 < n_chunks) {      // results of this chunk go back under the next kernel
-            CUDA_TRY(cudaEventRecord(ctx->ev_kernel, ctx->stream));
-            CUDA_TRY(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_kernel, 0));
-            CUDA_TRY(cudaMemcpyAsync(out_ll + b0, ctx->d_out + b0, sizeof(double) * (size_t)nb, cudaMemcpyDeviceToHost, ctx->copy_stream));
-            if (out_status) CUDA_TRY(cudaMemcpyAsync(out_status + b0, ctx->d_status + b0, sizeof(unsigned) * (size_t)nb, cudaMemcpyDeviceToHost, ctx->copy_stream));
-            if (out_steps) CUDA_TRY(cudaMemcpyAsync(out_steps + 2 * b0, ctx->d_steps + 2 * b0, sizeof(int) * (size_t)nb * 2, cudaMemcpyDeviceToHost, ctx->copy_stream));
-        } else {
-            CUDA_TRY(cudaMemcpyAsync(out_ll + b0, ctx->d_out + b0, sizeof(double) * (size_t)nb, cudaMemcpyDeviceToHost, ctx->stream));
-            if (out_status) CUDA_TRY(cudaMemcpyAsync(out_status + b0, ctx->d_status + b0, sizeof(unsigned) * (size_t)nb, cudaMemcpyDeviceToHost, ctx->stream));
-            if (out_steps) CUDA_TRY(cudaMemcpyAsync(out_steps + 2 * b0, ctx->d_steps + 2 * b0, sizeof(int) * (size_t)nb * 2, cudaMemcpyDeviceToHost, ctx->stream));
-        }
+        // results go back on the copy stream as soon as their kernel is done (under the following kernels)
+        CUDA_TRY(cudaEventRecord(ctx->ev_chunk[c], s));
+        CUDA_TRY(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_chunk[c], 0));
+        CUDA_TRY(cudaMemcpyAsync(out_ll + b0, ctx->d_out + b0, sizeof(double) * (size_t)nb, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        if (out_status) CUDA_TRY(cudaMemcpyAsync(out_status + b0, ctx->d_status + b0, sizeof(unsigned) * (size_t)nb, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        if (out_steps) CUDA_TRY(cudaMemcpyAsync(out_steps + 2 * b0, ctx->d_steps + 2 * b0, sizeof(int) * (size_t)nb * 2, cudaMemcpyDeviceToHost, ctx->copy_stream));
     }
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream2));
+    ctx->stream = restore.stream;
     CUDA_TRY(cudaStreamSynchronize(ctx->copy_stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return SEPAIHRD_OK;
