@@ -102,7 +102,7 @@ struct sepaihrd_ctx {
     cudaStream_t copy_stream = nullptr;   // host-pointer entry points: H2D / early D2H next to the compute stream
     cudaStream_t stream2 = nullptr;       // host-pointer evaluation: odd chunks run here, so a chunk's first blocks start while the previous chunk's last warps drain
     cudaEvent_t ev_chunk[4] = {nullptr, nullptr, nullptr, nullptr};
-    cudaEvent_t ev_copy[4] = {nullptr, nullptr, nullptr, nullptr}, ev_kernel = nullptr;
+    cudaEvent_t ev_copy[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaStream_t stream = nullptr;
     int num_sms = 0;
     // scratch for the host-pointer entry points (grown on demand)
@@ -501,7 +501,6 @@ sepaihrd_rc create_impl(const sepaihrd_problem* pb, int n_user, int n, int32_t d
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking);
     for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&ctx->ev_chunk[i], cudaEventDisableTiming);
     for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&ctx->ev_copy[i], cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_kernel, cudaEventDisableTiming);
     if (e != cudaSuccess) {
         std::string msg = std::string("CUDA setup failed: ") + cudaGetErrorString(e);
         sepaihrd_destroy(ctx);
@@ -535,7 +534,6 @@ void sepaihrd_destroy(sepaihrd_ctx* ctx) {
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     for (int i = 0; i < 4; ++i) if (ctx->ev_chunk[i]) cudaEventDestroy(ctx->ev_chunk[i]);
     for (int i = 0; i < 4; ++i) if (ctx->ev_copy[i]) cudaEventDestroy(ctx->ev_copy[i]);
-    if (ctx->ev_kernel) cudaEventDestroy(ctx->ev_kernel);
     delete ctx;
 }
 
