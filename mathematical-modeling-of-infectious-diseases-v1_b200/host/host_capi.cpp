@@ -185,6 +185,9 @@ extern "C" {
 
 const char* sepaihrd_host_last_error(void) { return g_err.c_str(); }
 
+int32_t sepaihrd_host_set_trace_directory(const char* dir) {
+    return guarded([&] { MetropolisHastingsSampler::setDefaultOutputDirectory(dir ? dir : ""); });
+}
 int32_t sepaihrd_host_set_threads(int32_t n) {
     if (n > 0) omp_set_num_threads(n);
     return omp_get_max_threads();

@@ -26,6 +26,10 @@ const char* sepaihrd_host_last_error(void);
 /* OpenMP threads of the host-side sampler loops (proposal / particle updates).  torchrun exports OMP_NUM_THREADS=1 to
  * every rank; the drivers call this with (host cores / ranks per node).  n <= 0 leaves the setting alone; returns the
  * number of threads now in use. */
+/* Directory for the Metropolis-Hastings trace files of whole runs (posterior_trace_checkpoint.csv, posterior_trace_final.csv,
+ * posterior_trace.csv; MetropolisHastingsSampler.cpp:380-469).  NULL or "": back to the reference's rule (<project root>/data/
+ * mcmc_samples inside a reference-style tree, nothing elsewhere).                                                             */
+int32_t sepaihrd_host_set_trace_directory(const char* dir);
 int32_t sepaihrd_host_set_threads(int32_t n);
 
 /* B log-posteriors for B parameter rows ([B][ld] row-major).  Return non-zero to abort the run. */

@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <filesystem>
 #include <iostream>
 
 namespace epidemic {
@@ -48,6 +49,8 @@ void MetropolisHastingsSampler::configure(const std::map<std::string, double>& s
     target_acceptance_rate_ = setting(s, "target_acceptance_rate", 0.234);
     adapt_scale_ = setting(s, "adapt_scale", 1.0) != 0.0;
     store_samples_ = setting(s, "store_samples", 1.0) != 0.0;
+    write_checkpoints_ = setting(s, "write_checkpoints", 1.0) != 0.0;
+    write_trace_ = setting(s, "write_trace", 1.0) != 0.0;
     // batched / repeatable extensions
     n_chains_ = std::max(1, static_cast<int>(setting(s, "n_chains", 1.0)));
     chain_offset_ = static_cast<long>(setting(s, "chain_offset", 0.0));
@@ -264,12 +267,68 @@ OptimizationResult MetropolisHastingsSampler::optimize(const VectorXd& initial, 
     std::vector<double> lp(static_cast<size_t>(n_chains_), lp0);
     begin(initial, lp.data(), pm);
     std::vector<double> prop(static_cast<size_t>(n_chains_) * static_cast<size_t>(P));
+    const std::string dir = (store_samples_ && (write_checkpoints_ || write_trace_)) ? traceDirectory() : std::string();
     while (!done()) {
+        const int t = t_;
         propose(pm, prop.data());
         const std::vector<double> plp = evaluate_rows(f, prop, n_chains_, P);
         accept(plp.data());
+        if (!dir.empty() && write_checkpoints_ && (t + 1) % report_interval_ == 0) saveCheckpoint(result(), pm, false, dir);   // .cpp:380-382
     }
-    return result();
+    OptimizationResult r = result();
+    if (!dir.empty() && write_checkpoints_) saveCheckpoint(r, pm, true, dir);                                                  // .cpp:399-401
+    if (!dir.empty() && write_trace_ && !r.samples.empty())                                                                    // .cpp:403-409
+        saveSamplesToCSV(r.samples, r.sampleObjectiveValues, pm.getParameterNames(), dir + "/posterior_trace.csv");
+    return r;
+}
+
+namespace {
+std::string g_default_trace_dir;
+}
+void MetropolisHastingsSampler::setDefaultOutputDirectory(const std::string& dir) { g_default_trace_dir = dir; }
+
+std::string MetropolisHastingsSampler::traceDirectory() const {
+    namespace fs = std::filesystem;
+    std::string dir = !output_dir_.empty() ? output_dir_ : g_default_trace_dir;
+    if (dir.empty()) {
+        // FileUtils::getProjectRoot (src/utils/FileUtils.cpp:25-46): the working directory or one of its five ancestors that
+        // holds data/, include/ and src/
+        std::error_code ec;
+        fs::path cur = fs::current_path(ec);
+        for (int i = 0; i <= 5 && !ec && !cur.empty(); ++i) {
+            if (fs::exists(cur / "data") && fs::exists(cur / "include") && fs::exists(cur / "src")) { dir = (cur / "data" / "mcmc_samples").string(); break; }
+            if (!cur.has_parent_path() || cur.parent_path() == cur) break;
+            cur = cur.parent_path();
+        }
+    }
+    if (dir.empty()) return dir;
+    std::error_code ec;
+    fs::create_directories(dir, ec);
+    return ec ? std::string() : dir;
+}
+
+// iter, log_posterior, one column per parameter; everything after the index in %.6e (the reference sets std::scientific and
+// setprecision(6) on the stream before the objective value and never resets them, .cpp:429-433)
+void MetropolisHastingsSampler::saveSamplesToCSV(const std::vector<VectorXd>& samples, const std::vector<double>& values,
+                                                 const std::vector<std::string>& names, const std::string& filepath, size_t first) {
+    std::FILE* file = std::fopen(filepath.c_str(), "w");
+    if (!file) return;
+    std::fputs("iter,log_posterior", file);
+    for (const auto& n : names) std::fprintf(file, ",%s", n.c_str());
+    std::fputc('\n', file);
+    for (size_t i = first; i < samples.size(); ++i) {
+        std::fprintf(file, "%zu,%.6e", i, values[i]);
+        for (std::ptrdiff_t j = 0; j < samples[i].size(); ++j) std::fprintf(file, ",%.6e", samples[i](j));
+        std::fputc('\n', file);
+    }
+    std::fclose(file);
+}
+
+void MetropolisHastingsSampler::saveCheckpoint(const OptimizationResult& res, IParameterManager& pm, bool final, const std::string& dir) const {   // .cpp:440-469
+    if (res.samples.empty()) return;
+    const size_t first = final ? 0 : (res.samples.size() > 5000 ? res.samples.size() - 5000 : 0);
+    saveSamplesToCSV(res.samples, res.sampleObjectiveValues, pm.getParameterNames(),
+                     dir + (final ? "/posterior_trace_final.csv" : "/posterior_trace_checkpoint.csv"), first);
 }
 
 // =====================================================================================================================

@@ -21,6 +21,7 @@
 
 #include <deque>
 #include <random>
+#include <string>
 
 #include "epidemic_host.hpp"
 
@@ -33,6 +34,16 @@ public:
     OptimizationResult optimize(const VectorXd& initialParameters, IObjectiveFunction& objectiveFunction,
                                 IParameterManager& parameterManager) override;
     void setInitialCovariance(const MatrixXd& cov);
+    // Trace files of optimize() (.cpp:380-382, 399-409, 414-469): `posterior_trace_checkpoint.csv` (last 5000 samples, every
+    // report_interval), `posterior_trace_final.csv` and `posterior_trace.csv` (all samples) -- columns iter, log_posterior, one
+    // per parameter, written when the settings write_checkpoints / write_trace are on (default, like the reference) AND a
+    // directory is known: the one set here, else the process-wide default, else <project root>/data/mcmc_samples when the
+    // working directory lies in a reference-style tree (data/, include/, src/ -- FileUtils::getProjectRoot).  Outside such a
+    // tree and without a directory nothing is written (the reference would create ./data/mcmc_samples).
+    void setOutputDirectory(const std::string& dir) { output_dir_ = dir; }
+    static void setDefaultOutputDirectory(const std::string& dir);
+    static void saveSamplesToCSV(const std::vector<VectorXd>& samples, const std::vector<double>& objectiveValues,
+                                 const std::vector<std::string>& parameterNames, const std::string& filepath, size_t first = 0);
 
     // ---- step-wise form (used by optimize() and by the multi-GPU driver) --------------------------------------
     // begin(): chains start at `initial` ([P], shared) with log-posteriors `initial_logpost` ([n_chains]).
@@ -75,6 +86,10 @@ private:
     void ownKernel(Chain& c) const;
 
     int iterations_ = 10000, burn_in_ = 1000, adaptation_period_ = 100, report_interval_ = 100, thinning_ = 1;
+    bool write_checkpoints_ = true, write_trace_ = true;
+    std::string output_dir_;
+    std::string traceDirectory() const;
+    void saveCheckpoint(const OptimizationResult& res, IParameterManager& pm, bool final, const std::string& dir) const;
     double regularization_epsilon_ = 1e-6, target_acceptance_rate_ = 0.234;
     bool adapt_scale_ = true, store_samples_ = true;
     int n_chains_ = 1;

@@ -30,6 +30,7 @@ BATCH_FN = C.CFUNCTYPE(C.c_int32, C.c_void_p, _dp, C.c_int64, C.c_int64, _dp)
 SIGNATURES = {
     "sepaihrd_host_last_error": (C.c_char_p, []),
     "sepaihrd_host_set_threads": (C.c_int32, [C.c_int32]),
+    "sepaihrd_host_set_trace_directory": (C.c_int32, [C.c_char_p]),
     "sepaihrd_host_pm_create": (C.c_int32, [C.c_int32, _vp, _vp, _vp, C.c_int32, _vpp]),
     "sepaihrd_host_pm_set_mode": (C.c_int32, [_vp, C.c_int32]),
     "sepaihrd_host_pm_apply_constraints": (C.c_int32, [_vp, _vp, _vp]),
@@ -115,6 +116,11 @@ def load_library():
 def check(rc: int):
     if rc != 0:
         raise HostError((load_library().sepaihrd_host_last_error() or b"").decode())
+
+
+def set_trace_directory(path: Optional[str]):
+    """Where whole Metropolis-Hastings runs write posterior_trace*.csv (None: the reference's project-root rule)."""
+    check(load_library().sepaihrd_host_set_trace_directory(path.encode() if path else None))
 
 
 def set_threads(n: int) -> int:

@@ -227,3 +227,42 @@ def test_two_phase_model_calibrator_on_a_synthetic_posterior(host, problem):
         assert n_samples == 4 * (1 + 39 // 2)             # initial state + every 2nd iteration, per chain
         np.testing.assert_allclose(ev(best[None])[0], val, rtol=1e-12)
         assert np.all(best >= problem.lower_bound) and np.all(best <= problem.upper_bound)
+
+
+def test_metropolis_hastings_writes_the_reference_trace_files(host, problem, tmp_path):
+    """posterior_trace_checkpoint.csv / posterior_trace_final.csv / posterior_trace.csv of MetropolisHastingsSampler::optimize
+    (.cpp:380-382, 399-409, 414-469): iter, log_posterior and one column per parameter, %.6e, thinning applied."""
+    target = problem.base_params()
+    sc = np.maximum(problem.sigmas, 1e-9)
+    ev = lambda x: -0.5 * (((x - target) / sc) ** 2).sum(axis=1)
+    pm = host.ParameterManager(problem.sigmas, problem.lower_bound, problem.upper_bound, mode=1)
+    st = dict(mcmc_iterations=60, burn_in=10, adaptation_period=20, n_chains=1, report_interval=20, thinning=2, seed=1)
+    out = tmp_path / "traces"
+    host.set_trace_directory(str(out))
+    try:
+        best, val, nev = host.optimize("mh", pm, st, ev, target)
+        names = sorted(p.name for p in out.iterdir())
+        assert names == ["posterior_trace.csv", "posterior_trace_checkpoint.csv", "posterior_trace_final.csv"]
+        final = (out / "posterior_trace_final.csv").read_text().splitlines()
+        assert final[0].split(",")[:2] == ["iter", "log_posterior"] and len(final[0].split(",")) == 2 + problem.n_params
+        assert len(final) == 1 + 1 + 29                           # header, the initial sample, t = 2, 4, ..., 58
+        assert (out / "posterior_trace.csv").read_text().splitlines() == final
+        rows = np.array([[float(v) for v in ln.split(",")] for ln in final[1:]])
+        np.testing.assert_array_equal(rows[:, 0], np.arange(30))
+        np.testing.assert_allclose(rows[:, 1], ev(rows[:, 2:]), rtol=2e-5, atol=1e-6)      # six significant digits
+        assert rows[:, 1].max() == pytest.approx(val, rel=1e-6)
+        assert all(len(v.split("e")[0]) <= 9 for v in final[1].split(",")[1:])              # d.dddddde+xx
+        ckpt = (out / "posterior_trace_checkpoint.csv").read_text().splitlines()
+        assert ckpt[0] == final[0] and 1 < len(ckpt) <= len(final)                           # written at t + 1 = 20, 40, 60
+        # write_trace 0 / write_checkpoints 0, and no directory known outside a reference-style tree: nothing is written
+        for p in out.iterdir():
+            p.unlink()
+        host.optimize("mh", pm, dict(st, write_trace=0, write_checkpoints=0), ev, target)
+        assert list(out.iterdir()) == []
+        host.optimize("mh", pm, dict(st, write_trace=0), ev, target)
+        assert sorted(p.name for p in out.iterdir()) == ["posterior_trace_checkpoint.csv", "posterior_trace_final.csv"]
+    finally:
+        host.set_trace_directory(None)
+    before = set(os.listdir(ROOT))
+    host.optimize("mh", pm, st, ev, target)
+    assert set(os.listdir(ROOT)) == before and not os.path.exists(os.path.join(os.getcwd(), "data", "mcmc_samples"))
