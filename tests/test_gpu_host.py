@@ -82,6 +82,26 @@ def test_simulator_mirror_matches_oracle(host, problem, oracle):
     m.close()
 
 
+def test_host_mirror_runs_problems_with_other_age_class_counts(host, problem, orc):
+    """Three and seven age classes through the C++ mirror (objective, simulator, two-phase calibration, posterior predictive):
+    the library pads them to its 4- and 16-lane kernels, the mirror sees the caller's n everywhere."""
+    for p in (problem.select_ages([0, 1, 3]), problem.expand_ages(2).select_ages([0, 1, 2, 3, 4, 5, 7])):
+        o = orc.Oracle(p)
+        m = host.HostModel(p)
+        P = o.jitter_params(33, seed=2)
+        assert _rel(m.calculate_batch(P), o.eval_batch(P)[0]).max() < 1e-8
+        s0 = p.data_initial_state
+        ref, st = o.simulate_from_state(p.base_params()[None], s0)
+        got = m.simulate(s0, p.times)
+        assert got.shape == (p.n_times, 11 * p.n_ages) and (np.abs(got - ref[0]) / np.maximum(np.abs(ref[0]), 1.0)).max() < 1e-9
+        f0 = o.eval_batch(p.base_params()[None])[0][0]
+        best, val, ns = m.calibrate("hill", dict(iterations=2, cloud_size=16, seed=3), dict(mcmc_iterations=4, burn_in=4, n_chains=4, seed=5))
+        assert val >= f0 * (1 - 1e-12) and _rel(o.eval_batch(best[None])[0][0], val) < 1e-8
+        q, used = m.posterior_predictive(P[:16], s0)
+        assert used == 16 and q.shape[:3] == (6, int((p.times >= 0).sum()), p.n_ages) and np.isfinite(q).all()
+        m.close()
+
+
 def test_seeded_mcmc_accept_sequences_are_identical_on_gpu_and_oracle(problem, reflect_problem, orc, ev_mod, pkg):
     """BASELINE.json configs[2] at test size: every accept/reject decision of a seeded multi-chain run must agree."""
     from sepaihrd_b200 import drivers
