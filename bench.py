@@ -43,9 +43,9 @@ B_PER_GPU = 1 << 20
 DISTINCT = 1 << 20              # every set of the batch is its own draw
 FLOP_PER_ATTEMPT = 3750.0      # 6 RHS + stage/solution/error combinations + error norm, n = 4
 FLOP_PER_SET_FIXED = 22000.0   # 3672 likelihood terms * ~6
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch at B = 2^20 (ncu --set full, profiles/r01_v9_ncu_full_summary.txt):
-# 527.8 MB + 16.3 MB, i.e. the algorithmic 532.7 MB (62 doubles in, 12 bytes out per set) -- no re-reads.
-NCU_DRAM_BYTES_PER_LAUNCH_1M = 527.774976e6 + 16.291328e6
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch at B = 2^20 (ncu --set full, profiles/r01_v12_ncu_full_summary.txt):
+# 527.3 MB + 17.5 MB, i.e. the algorithmic 532.7 MB (62 doubles in, 12 bytes out per set) -- no re-reads.
+NCU_DRAM_BYTES_PER_LAUNCH_1M = 527.267328e6 + 17.500160e6
 
 
 def workload_config(n_gpus: int, batch: int) -> dict:
