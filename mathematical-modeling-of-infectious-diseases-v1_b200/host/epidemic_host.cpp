@@ -522,13 +522,21 @@ void SEPAIHRDObjectiveFunction::calculateBatch(const double* params, int64_t B, 
 }
 
 void SEPAIHRDObjectiveFunction::calculateBatch(const double* params, int64_t B, int64_t ld, double* out) const {
+    evaluateThroughCache(cache_, dev_->numParams(), params, B, ld, out,
+                         [this](const double* rows, int64_t M, int64_t rld, double* vals, uint32_t* st) { evaluateRows(rows, M, rld, vals, st, nullptr); });
+}
+
+// calculate() row by row as far as the cache is concerned (ObjectiveFunction.cpp:63-77): probe, remember the misses, evaluate
+// them as ONE batch, store what calculate() would have stored (.cpp:227-234).
+void evaluateThroughCache(ISimulationCache& cache_, std::ptrdiff_t P, const double* params, int64_t B, int64_t ld, double* out,
+                          const std::function<void(const double*, int64_t, int64_t, double*, uint32_t*)>& evaluate) {
     if (B <= 0) return;
     auto* fast = dynamic_cast<SimulationCache*>(&cache_);
     const bool uncached = dynamic_cast<NullSimulationCache*>(&cache_) != nullptr || (fast != nullptr && static_cast<size_t>(B) > fast->capacity());
-    if (uncached) return evaluateRows(params, B, ld, out, nullptr, nullptr);
-    // calculate() row by row as far as the cache is concerned (.cpp:63-77): probe, remember the misses, evaluate them as ONE
-    // batch, store what calculate() would have stored (.cpp:227-234).
-    const std::ptrdiff_t P = dev_->numParams();
+    if (uncached) {
+        std::vector<uint32_t> st(static_cast<size_t>(B));
+        return evaluate(params, B, ld, out, st.data());
+    }
     std::vector<size_t> fkey(fast ? static_cast<size_t>(B) : 0);
     std::vector<std::string> skey(fast ? 0 : static_cast<size_t>(B));
     std::vector<int64_t> miss, first_of(static_cast<size_t>(B), -1);
@@ -556,7 +564,7 @@ void SEPAIHRDObjectiveFunction::calculateBatch(const double* params, int64_t B, 
             for (int64_t j = 0; j < M; ++j) std::copy(params + miss[static_cast<size_t>(j)] * ld, params + miss[static_cast<size_t>(j)] * ld + P, rows.begin() + j * P);
             src = rows.data(); src_ld = P;
         }
-        evaluateRows(src, M, src_ld, vals.data(), st.data(), nullptr);
+        evaluate(src, M, src_ld, vals.data(), st.data());
         for (int64_t j = 0; j < M; ++j) {
             const int64_t i = miss[static_cast<size_t>(j)];
             out[i] = vals[static_cast<size_t>(j)];

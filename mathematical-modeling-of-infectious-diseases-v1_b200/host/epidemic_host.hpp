@@ -289,6 +289,12 @@ private:
     mutable std::atomic<size_t> get_calls_{0}, get_hits_{0}, store_calls_{0};
 };
 
+// B calls of calculate() as far as `cache` is concerned (probe per vector, ONE evaluate() call for the distinct misses, store
+// what calculate() stores: rows whose status word is 0 or SEPAIHRD_ST_NONFINITE); batches larger than a SimulationCache's
+// capacity and the NullSimulationCache go to evaluate() whole.  evaluate(rows, M, ld, values, status).
+void evaluateThroughCache(ISimulationCache& cache, std::ptrdiff_t P, const double* params, int64_t B, int64_t ld, double* out,
+                          const std::function<void(const double*, int64_t, int64_t, double*, uint32_t*)>& evaluate);
+
 struct OptimizationResult {                                          // IOptimizationAlgorithm.hpp:18-27
     VectorXd bestParameters;
     double bestObjectiveValue = -std::numeric_limits<double>::infinity();

@@ -561,6 +561,17 @@ int32_t sepaihrd_host_cache_get_vector(sepaihrd_host_cache* c, const double* par
     return v ? 1 : 0;
 }
 void sepaihrd_host_cache_set_vector(sepaihrd_host_cache* c, const double* params, int32_t n, double value) { c->c.set(VectorXd::FromPointer(params, n), value); }
+int32_t sepaihrd_host_cache_batch(sepaihrd_host_cache* c, int32_t n_params, const double* params, int64_t B, int64_t ld, double* out,
+                                  sepaihrd_host_batch_fn fn, void* user, const uint32_t* status_of_row) {
+    return guarded([&] {
+        if (!c || !fn || !params || !out) throw InvalidParameterException("sepaihrd_host_cache_batch", "bad argument");
+        evaluateThroughCache(c->c, n_params, params, B, ld, out, [&](const double* rows, int64_t M, int64_t rld, double* vals, uint32_t* st) {
+            if (fn(user, rows, M, rld, vals) != 0) throw SimulationException("sepaihrd_host_cache_batch", "the batch callback reported a failure");
+            // test hook: a status word per ORIGINAL row, looked up by the row's first coordinate used as an index
+            for (int64_t j = 0; j < M; ++j) st[j] = status_of_row ? status_of_row[static_cast<int64_t>(rows[j * rld])] : 0u;
+        });
+    });
+}
 int64_t sepaihrd_host_cache_size(const sepaihrd_host_cache* c) { return static_cast<int64_t>(c->c.size()); }
 void sepaihrd_host_cache_clear(sepaihrd_host_cache* c) { c->c.clear(); }
 void sepaihrd_host_cache_stats(const sepaihrd_host_cache* c, int64_t* out) {

@@ -156,6 +156,11 @@ int32_t  sepaihrd_host_cache_get(sepaihrd_host_cache* c, uint64_t key, double* o
 void     sepaihrd_host_cache_store(sepaihrd_host_cache* c, uint64_t key, double value);
 int32_t  sepaihrd_host_cache_get_vector(sepaihrd_host_cache* c, const double* params, int32_t n, double* out_value);
 void     sepaihrd_host_cache_set_vector(sepaihrd_host_cache* c, const double* params, int32_t n, double value);
+/* evaluateThroughCache (what SEPAIHRDObjectiveFunction::calculateBatch does with its cache) against a batch callback: probe per
+ * row, one callback for the distinct misses, store, repeats counted as hits.  status_of_row (or NULL): per-row status words,
+ * indexed by the row's FIRST coordinate -- rows with a failure status other than NONFINITE are not stored (test hook).          */
+int32_t  sepaihrd_host_cache_batch(sepaihrd_host_cache* c, int32_t n_params, const double* params, int64_t B, int64_t ld, double* out,
+                                   sepaihrd_host_batch_fn fn, void* user, const uint32_t* status_of_row);
 int64_t  sepaihrd_host_cache_size(const sepaihrd_host_cache* c);
 void     sepaihrd_host_cache_clear(sepaihrd_host_cache* c);
 void     sepaihrd_host_cache_stats(const sepaihrd_host_cache* c, int64_t* out_stats /* [3]: get calls, hits, store calls */);

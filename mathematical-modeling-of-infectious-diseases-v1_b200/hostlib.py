@@ -82,6 +82,7 @@ SIGNATURES = {
     "sepaihrd_host_cache_store": (None, [_vp, C.c_uint64, C.c_double]),
     "sepaihrd_host_cache_get_vector": (C.c_int32, [_vp, _vp, C.c_int32, _dp]),
     "sepaihrd_host_cache_set_vector": (None, [_vp, _vp, C.c_int32, C.c_double]),
+    "sepaihrd_host_cache_batch": (C.c_int32, [_vp, C.c_int32, _vp, C.c_int64, C.c_int64, _vp, BATCH_FN, _vp, _vp]),
     "sepaihrd_host_cache_size": (C.c_int64, [_vp]),
     "sepaihrd_host_cache_clear": (None, [_vp]),
     "sepaihrd_host_cache_stats": (None, [_vp, _vp]),
@@ -346,6 +347,17 @@ class Cache:
     def set_vector(self, params, value: float):
         x = _c64(params)
         self.L.sepaihrd_host_cache_set_vector(self._h, x.ctypes.data, len(x), float(value))
+
+    def batch(self, params, evaluate, status_of_row=None) -> np.ndarray:
+        """What SEPAIHRDObjectiveFunction::calculateBatch does with its cache, with ``evaluate`` ([M, P] -> [M]) as the device:
+        status_of_row (optional uint32 array) is indexed by each row's first coordinate."""
+        x = _c64(params)
+        out = np.empty(len(x))
+        cb = BATCH_FN(_batch_callback(evaluate, x.shape[1]))
+        st = None if status_of_row is None else np.ascontiguousarray(status_of_row, dtype=np.uint32)
+        check(self.L.sepaihrd_host_cache_batch(self._h, x.shape[1], x.ctypes.data, x.shape[0], x.shape[1], out.ctypes.data, cb, None,
+                                               None if st is None else st.ctypes.data))
+        return out
 
     def __len__(self) -> int:
         return int(self.L.sepaihrd_host_cache_size(self._h))

@@ -123,3 +123,36 @@ def test_least_frequently_used_goes_first_then_least_recently_used(host):
 def test_constructor_and_string_keys(host):
     with pytest.raises(host.HostError):
         host.Cache(0)                                               # "SimulationCache: max_size must be > 0."
+
+
+def test_batches_go_through_the_cache_like_a_sequence_of_calculate_calls(host):
+    """evaluateThroughCache (the body of SEPAIHRDObjectiveFunction::calculateBatch) on the CPU with a counting evaluator: probe
+    per row, ONE evaluation call for the distinct misses, repeats counted as hits, failures that calculate() returns before its
+    store are not stored, batches beyond the capacity evaluated whole."""
+    c = host.Cache(32)
+    calls = []
+
+    def ev(x):
+        calls.append(np.array(x))
+        return -np.sum(x * x, axis=1)
+    rows = np.array([[float(i), 0.5 * i, -1.0] for i in range(10)])
+    out = c.batch(rows[[1, 2, 1, 3, 2]], ev)
+    np.testing.assert_array_equal(out, ev(rows[[1, 2, 1, 3, 2]])); calls.pop()
+    assert len(calls) == 1 and len(calls[0]) == 3                   # rows 1, 2, 3 once, as one batch
+    np.testing.assert_array_equal(calls[0], rows[[1, 2, 3]])
+    assert len(c) == 3 and c.stats() == dict(get_calls=5 + 2, hits=2, store_calls=3)
+    out = c.batch(rows[[3, 4, 1]], ev)                              # two hits, one miss
+    assert len(calls) == 2 and len(calls[1]) == 1 and len(c) == 4
+    np.testing.assert_array_equal(out, -np.sum(rows[[3, 4, 1]] ** 2, axis=1))
+    out = c.batch(rows[[1, 2, 3, 4]], ev)                           # all hits: the evaluator is not called
+    assert len(calls) == 2
+    # status words: row 5 fails before calculate()'s store (S overflow = 1), row 6 is the non-finite sentinel (4, stored)
+    st = np.zeros(10, dtype=np.uint32); st[5] = 1; st[6] = 4
+    c.batch(rows[[5, 6, 7]], ev, status_of_row=st)
+    assert len(c) == 4 + 2 and c.get(c.hash(rows[5])) is None and c.get(c.hash(rows[6])) == -np.sum(rows[6] ** 2)
+    # a batch larger than the capacity is evaluated whole and leaves the cache alone
+    big = np.array([[100.0 + i, 1.0, 2.0] for i in range(40)])
+    n_before, s_before = len(c), c.stats()
+    out = c.batch(big, ev)
+    assert len(calls[-1]) == 40 and len(c) == n_before and c.stats() == s_before
+    np.testing.assert_array_equal(out, -np.sum(big * big, axis=1))
