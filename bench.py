@@ -46,6 +46,8 @@ FLOP_PER_SET_FIXED = 22000.0   # 3672 likelihood terms * ~6
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch at B = 2^20 (ncu --set full, profiles/r01_v12_ncu_full_summary.txt):
 # 527.3 MB + 17.5 MB, i.e. the algorithmic 532.7 MB (62 doubles in, 12 bytes out per set) -- no re-reads.
 NCU_DRAM_BYTES_PER_LAUNCH_1M = 527.267328e6 + 17.500160e6
+NCU_FP64_PIPE_PCT = 61.52        # sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active, same capture
+NCU_ISSUE_ACTIVE_PCT = 51.78     # smsp__issue_active.avg.pct_of_peak_sustained_active
 
 
 def workload_config(n_gpus: int, batch: int) -> dict:
@@ -300,7 +302,11 @@ def main():
                             "launch_ms": launch_s * 1e3,
                             "peak_source": "measured live: sepaihrd_measure_fp64_peak (dependent DFMA chains), x2 FLOP per DFMA; "
                                            "MEASURED_PEAKS.json has no FP64 entry",
-                            "hbm_bytes_per_launch_algorithmic": B * (P * 8 + 12)},
+                            "hbm_bytes_per_launch_algorithmic": B * (P * 8 + 12),
+                            # BASELINE.json's "% FP64 peak (ncu fp64-pipe utilisation and issue efficiency)": from the ncu --set full
+                            # capture of this kernel at this batch size (profiles/r01_v12_ncu_full_summary.txt), not measured live
+                            "ncu_fp64_pipe_pct": NCU_FP64_PIPE_PCT if B == (1 << 20) else None,
+                            "ncu_issue_active_pct": NCU_ISSUE_ACTIVE_PCT if B == (1 << 20) else None},
                "clocks": clocks, "logl_checksum": checksum}
         if world == 1:
             # SURVEY.md 8(d) names a second distribution: uniform in bounds (the PSO initialisation recipe), mt19937(2).  Not the
