@@ -34,6 +34,7 @@ def pytest_collection_modifyitems(config, items):
 
 @pytest.fixture(scope="session")
 def pkg():
+    entry.build()            # csrc/, host/ and oracle/ in-tree; a no-op when the libraries are newer than their sources
     return entry.load_package()
 
 
