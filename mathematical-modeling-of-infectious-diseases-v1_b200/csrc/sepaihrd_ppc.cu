@@ -15,6 +15,8 @@
 //   quantile gather --[6][T][n][Q]--> host
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
+#include <algorithm>
 #include <vector>
 
 #include <cub/device/device_segmented_radix_sort.cuh>
@@ -84,6 +86,185 @@ __global__ void ppc_quantile_kernel(const double* __restrict__ sorted, long long
     }
 }
 
+// ---- exact order statistics without sorting -------------------------------------------------------------------------------
+// A column needs the values at <= 2Q ranks (the two neighbours of every quantile position), not its full order.  One block per
+// column: a first sweep finds the count, minimum and maximum of the non-NaN keys (everything above their common bit prefix is
+// already decided); then most-significant-digit radix steps of 8 bits narrow, for ALL wanted ranks at once, the bucket each rank
+// lies in (one 256-bin histogram per distinct bucket prefix, <= 16 of them), until every bucket holds at most SEL_CAP keys or
+// the bits are used up; the survivors are gathered into shared memory and the wanted rank is picked by counting.  A column is
+// read 3-5 times (its later sweeps mostly from L2) instead of being read and written 8 times by the radix sort.
+// Keys: the usual order-preserving map of a double's bits to an unsigned integer; NaNs (failed draws) are left out.
+constexpr int SEL_THREADS = 512, SEL_MAXT = 16, SEL_CAP = 192;
+
+__device__ __forceinline__ unsigned long long sel_key(double x) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(x);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ULL);
+}
+__device__ __forceinline__ double sel_value(unsigned long long k) {
+    const unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffULL) : ~k;
+    return __longlong_as_double((long long)b);
+}
+
+__global__ void __launch_bounds__(SEL_THREADS) ppc_select_kernel(const double* __restrict__ series, long long B, long long n_cols, int Q,
+                                                                 const double* __restrict__ probs, double* __restrict__ out) {
+    __shared__ unsigned hist[SEL_MAXT][256];
+    __shared__ unsigned long long cand[SEL_MAXT][SEL_CAP];
+    __shared__ unsigned cand_n[SEL_MAXT];
+    __shared__ unsigned long long t_prefix[SEL_MAXT], t_value[SEL_MAXT], b_prefix[SEL_MAXT];
+    __shared__ long long t_want[SEL_MAXT], t_rank[SEL_MAXT];
+    __shared__ unsigned t_size[SEL_MAXT];
+    __shared__ int t_bucket[SEL_MAXT];
+    __shared__ unsigned long long s_min, s_max;
+    __shared__ unsigned long long s_cnt;
+    __shared__ int n_targets, n_buckets, s_shift, s_go;
+    const int tid = threadIdx.x;
+    for (long long col = blockIdx.x; col < n_cols; col += gridDim.x) {
+        const double* v = series + (size_t)col * B;
+        if (tid == 0) { s_min = ~0ULL; s_max = 0ULL; s_cnt = 0ULL; }
+        __syncthreads();
+        {   // sweep 0: how many non-NaN keys, and between which bounds
+            unsigned long long lo = ~0ULL, hi = 0ULL, c = 0ULL;
+            for (long long i = tid; i < B; i += SEL_THREADS) {
+                const double x = v[i];
+                if (x == x) { const unsigned long long k = sel_key(x); lo = (k < lo) ? k : lo; hi = (k > hi) ? k : hi; ++c; }
+            }
+            for (int o = 16; o >= 1; o >>= 1) {
+                const unsigned long long lo2 = __shfl_xor_sync(0xffffffffu, lo, o), hi2 = __shfl_xor_sync(0xffffffffu, hi, o);
+                lo = (lo2 < lo) ? lo2 : lo; hi = (hi2 > hi) ? hi2 : hi; c += __shfl_xor_sync(0xffffffffu, c, o);
+            }
+            if ((tid & 31) == 0) { atomicMin(&s_min, lo); atomicMax(&s_max, hi); atomicAdd(&s_cnt, c); }
+        }
+        __syncthreads();
+        const long long cnt = (long long)s_cnt;
+        if (cnt == 0) {                                            // no valid draw: every quantile is NaN
+            for (int q = tid; q < Q; q += SEL_THREADS) out[(size_t)col * Q + q] = nan("");
+            __syncthreads();
+            continue;
+        }
+        if (tid == 0) {
+            // the ranks wanted: floor((cnt - 1) p) and its right neighbour for every probability, without repeats
+            int nt = 0;
+            for (int q = 0; q < Q; ++q) {
+                const double h = (double)(cnt - 1) * probs[q];
+                long long i0 = (long long)floor(h);
+                if (i0 < 0) i0 = 0;
+                if (i0 > cnt - 1) i0 = cnt - 1;
+                const long long i1 = (i0 + 1 < cnt) ? i0 + 1 : i0;
+                for (int w = 0; w < 2; ++w) {
+                    const long long r = w ? i1 : i0;
+                    bool seen = false;
+                    for (int t = 0; t < nt; ++t) seen = seen || (t_want[t] == r);
+                    if (!seen) { t_want[nt] = r; ++nt; }
+                }
+            }
+            n_targets = nt;
+            const unsigned long long diff = s_min ^ s_max;
+            const int hb = diff ? (64 - __clzll((long long)diff)) : 0;     // low bits in which the keys differ at all
+            s_shift = hb;
+            for (int t = 0; t < nt; ++t) {
+                t_prefix[t] = (hb < 64) ? (s_min >> hb) : 0ULL;
+                t_rank[t] = t_want[t];
+                t_size[t] = (unsigned)((cnt > 0xffffffffLL) ? 0xffffffffLL : cnt);
+            }
+        }
+        __syncthreads();
+        while (true) {
+            if (tid == 0) {
+                // go on while some bucket is still too large for the gather and bits remain; buckets = distinct prefixes
+                int go = 0;
+                for (int t = 0; t < n_targets; ++t) go = go || (t_size[t] > (unsigned)SEL_CAP);
+                s_go = go && (s_shift > 0);
+                int nb = 0;
+                for (int t = 0; t < n_targets; ++t) {
+                    int a = -1;
+                    for (int j = 0; j < nb; ++j) if (b_prefix[j] == t_prefix[t]) a = j;
+                    if (a < 0) { a = nb; b_prefix[nb] = t_prefix[t]; ++nb; }
+                    t_bucket[t] = a;
+                }
+                n_buckets = nb;
+            }
+            __syncthreads();
+            if (!s_go) break;
+            const int shift = s_shift, nshift = (shift > 8) ? shift - 8 : 0, width = shift - nshift, nb = n_buckets;
+            for (int i = tid; i < nb * 256; i += SEL_THREADS) hist[i >> 8][i & 255] = 0u;
+            __syncthreads();
+            for (long long i = tid; i < B; i += SEL_THREADS) {
+                const double x = v[i];
+                if (x == x) {
+                    const unsigned long long k = sel_key(x);
+                    const unsigned long long hi = (shift < 64) ? (k >> shift) : 0ULL;
+                    const unsigned d = (unsigned)((k >> nshift) & ((1ULL << width) - 1ULL));
+                    for (int a = 0; a < nb; ++a) if (hi == b_prefix[a]) atomicAdd(&hist[a][d], 1u);
+                }
+            }
+            __syncthreads();
+            if (tid < n_targets) {
+                const int a = t_bucket[tid];
+                long long k = t_rank[tid];
+                unsigned d = 0;
+                for (; d < (1u << width) - 1u; ++d) {
+                    const unsigned hcount = hist[a][d];
+                    if (k < (long long)hcount) break;
+                    k -= hcount;
+                }
+                t_prefix[tid] = (t_prefix[tid] << width) | d;
+                t_rank[tid] = k;
+                t_size[tid] = hist[a][d];
+            }
+            __syncthreads();
+            if (tid == 0) s_shift = nshift;
+            __syncthreads();
+        }
+        const int shift = s_shift;
+        bool small = true;
+        for (int t = 0; t < n_targets; ++t) small = small && (t_size[t] <= (unsigned)SEL_CAP);
+        if (!small) {
+            // bits used up with a large bucket: all its keys are equal, the prefix IS the key
+            if (tid < n_targets) t_value[tid] = t_prefix[tid];
+        } else {
+            const int nb = n_buckets;
+            if (tid < nb) cand_n[tid] = 0u;
+            __syncthreads();
+            for (long long i = tid; i < B; i += SEL_THREADS) {
+                const double x = v[i];
+                if (x == x) {
+                    const unsigned long long k = sel_key(x);
+                    const unsigned long long hi = (shift < 64) ? (k >> shift) : 0ULL;
+                    for (int a = 0; a < nb; ++a)
+                        if (hi == b_prefix[a]) { const unsigned pos = atomicAdd(&cand_n[a], 1u); if (pos < (unsigned)SEL_CAP) cand[a][pos] = k; }
+                }
+            }
+            __syncthreads();
+            for (int t = 0; t < n_targets; ++t) {
+                const int a = t_bucket[t];
+                const unsigned m = (cand_n[a] < (unsigned)SEL_CAP) ? cand_n[a] : (unsigned)SEL_CAP;
+                const long long k = t_rank[t];
+                for (unsigned c = tid; c < m; c += SEL_THREADS) {
+                    const unsigned long long key = cand[a][c];
+                    long long less = 0, eq = 0;
+                    for (unsigned j = 0; j < m; ++j) { const unsigned long long o = cand[a][j]; less += (o < key); eq += (o == key); }
+                    if (less <= k && k < less + eq) t_value[t] = key;       // every candidate of that value writes the same bits
+                }
+            }
+        }
+        __syncthreads();
+        for (int q = tid; q < Q; q += SEL_THREADS) {
+            const double h = (double)(cnt - 1) * probs[q];
+            long long i0 = (long long)floor(h);
+            if (i0 < 0) i0 = 0;
+            if (i0 > cnt - 1) i0 = cnt - 1;
+            const long long i1 = (i0 + 1 < cnt) ? i0 + 1 : i0;
+            double a = 0.0, c = 0.0;
+            for (int t = 0; t < n_targets; ++t) {
+                if (t_want[t] == i0) a = sel_value(t_value[t]);
+                if (t_want[t] == i1) c = sel_value(t_value[t]);
+            }
+            out[(size_t)col * Q + q] = a + (h - (double)i0) * (c - a);
+        }
+        __syncthreads();
+    }
+}
+
 __global__ void ppc_offsets_kernel(long long* off, long long n_cols, long long B) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i <= n_cols) off[i] = i * B;
@@ -126,7 +307,9 @@ extern "C" sepaihrd_rc sepaihrd_posterior_predictive(sepaihrd_ctx* ctx, const do
     double* d_init = (double*)buf(sizeof(double) * SEPAIHRD_NUM_COMPARTMENTS * n);
     double* d_traj = (double*)buf(sizeof(double) * traj_elems);
     double* d_series = (double*)buf(sizeof(double) * 6 * col_elems);
-    double* d_sorted = (double*)buf(sizeof(double) * col_elems);
+    static const bool force_sort = std::getenv("SEPAIHRD_PPC_SORT") != nullptr;
+    const bool use_select = 2 * n_probs <= SEL_MAXT && !force_sort;
+    double* d_sorted = use_select ? nullptr : (double*)buf(sizeof(double) * col_elems);     // only the sort path needs a second copy of a series
     double* d_probs = (double*)buf(sizeof(double) * n_probs);
     double* d_q = (double*)buf(sizeof(double) * 6 * (size_t)n_cols * n_probs);
     unsigned* d_status = (unsigned*)buf(sizeof(unsigned) * (size_t)B);
@@ -161,6 +344,14 @@ extern "C" sepaihrd_rc sepaihrd_posterior_predictive(sepaihrd_ctx* ctx, const do
         ppc_offsets_kernel<<<(unsigned)((n_cols + 256) / 256), 256, 0, s>>>(d_off, n_cols, B);
         PPC_TRY(cudaGetLastError());
     }
+    // 3 + 4. the order statistics the quantiles need, column by column, without sorting (few probabilities: the usual case)
+    if (use_select) {
+        const long long all_cols = 6 * n_cols;
+        const unsigned grid = (unsigned)std::min<long long>(all_cols, 4 * 148);
+        ppc_select_kernel<<<grid, SEL_THREADS, 0, s>>>(d_series, B, all_cols, n_probs, d_probs, d_q);
+        PPC_TRY(cudaGetLastError());
+        count_launches(ctx, 1);
+    } else {
     // 3. sort every column (one segment per (day, age)), one series at a time; 4. gather the quantiles
     size_t tmp_bytes = 0;
     PPC_TRY(cub::DeviceSegmentedRadixSort::SortKeys(nullptr, tmp_bytes, d_series, d_sorted, (long long)col_elems, (long long)n_cols, d_off, d_off + 1,
@@ -172,6 +363,7 @@ extern "C" sepaihrd_rc sepaihrd_posterior_predictive(sepaihrd_ctx* ctx, const do
                                                          (long long)n_cols, d_off, d_off + 1, 0, 64, s));
         ppc_quantile_kernel<<<(unsigned)((n_cols + 127) / 128), 128, 0, s>>>(d_sorted, B, n_cols, n_probs, d_probs, d_q + (size_t)ser * n_cols * n_probs);
         PPC_TRY(cudaGetLastError());
+    }
     }
     unsigned long long cnt = 0;
     std::vector<double> wide_q;
