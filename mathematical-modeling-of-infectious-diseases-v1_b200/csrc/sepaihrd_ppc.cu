@@ -8,11 +8,12 @@
 //
 // Deliberate, documented difference: the reference feeds the draws through Boost's extended P-square streaming
 // estimator (.cpp:28-33), whose result depends on the order of the draws; here every quantile is the EXACT sample
-// quantile with linear interpolation between order statistics (numpy's default), from a full sort of the column.
+// quantile with linear interpolation between order statistics (numpy's default).
 //
 // Data flow (all in HBM, HBM-bound integer/byte-style work -- no tensor cores):
-//   trajectory kernel --[K][3n][B], draws fastest--> series kernel --[6][T][n][B]--> segmented radix sort (cub) -->
-//   quantile gather --[6][T][n][Q]--> host
+//   trajectory kernel --[K][3n][B], draws fastest--> series kernel --[6][T][n][B]--> per column: the <= 2Q order statistics
+//   the quantiles need, SELECTED by ppc_select_kernel (up to 8 probabilities) or read off a cub segmented radix sort (more)
+//   --[6][T][n][Q]--> host
 #include <cmath>
 #include <cstdint>
 #include <cstdlib>
