@@ -197,8 +197,9 @@ sepaihrd_rc sepaihrd_simulate_from_state_device(sepaihrd_ctx* ctx, const double*
  *   probs          [n_probs] in [0, 1]  (the reference uses 0.025, 0.05, 0.5, 0.95, 0.975, .cpp:233)
  *   out_quantiles  [6][T][n_ages][n_probs]; NaN where no valid draw exists
  *   out_valid_draws (optional) draws whose simulation succeeded (failed ones are skipped like .cpp:290)
- * Difference from the reference (documented in DESIGN.md): exact sample quantiles with linear interpolation from a full
- * sort, not Boost's order-dependent extended P-square estimate. */
+ * Difference from the reference (documented in DESIGN.md): EXACT sample quantiles with linear interpolation between order
+ * statistics (selected per column on the device; read off a full sort for more than 8 probabilities), not Boost's
+ * order-dependent extended P-square estimate. */
 sepaihrd_rc sepaihrd_posterior_predictive(sepaihrd_ctx* ctx, const double* params, int64_t B, int64_t ld,
                                           const double* initial_state, int32_t n_probs, const double* probs,
                                           double* out_quantiles, int64_t* out_valid_draws);
