@@ -101,6 +101,15 @@ __device__ __forceinline__ unsigned long long sel_key(double x) {
     const unsigned long long b = (unsigned long long)__double_as_longlong(x);
     return (b >> 63) ? ~b : (b | 0x8000000000000000ULL);
 }
+// SEL_UNROLL coalesced loads issued together (the sweeps are latency-bound otherwise); past the end: NaN, which every sweep skips
+constexpr int SEL_UNROLL = 4;
+__device__ __forceinline__ void sel_load(const double* __restrict__ v, long long i0, long long B, double (&xs)[SEL_UNROLL]) {
+#pragma unroll
+    for (int u = 0; u < SEL_UNROLL; ++u) {
+        const long long i = i0 + (long long)u * SEL_THREADS;
+        xs[u] = (i < B) ? __ldg(v + i) : __longlong_as_double(0x7ff8000000000000LL);
+    }
+}
 __device__ __forceinline__ double sel_value(unsigned long long k) {
     const unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffULL) : ~k;
     return __longlong_as_double((long long)b);
@@ -125,9 +134,14 @@ __global__ void __launch_bounds__(SEL_THREADS) ppc_select_kernel(const double* _
         __syncthreads();
         {   // sweep 0: how many non-NaN keys, and between which bounds
             unsigned long long lo = ~0ULL, hi = 0ULL, c = 0ULL;
-            for (long long i = tid; i < B; i += SEL_THREADS) {
-                const double x = v[i];
-                if (x == x) { const unsigned long long k = sel_key(x); lo = (k < lo) ? k : lo; hi = (k > hi) ? k : hi; ++c; }
+            for (long long i0 = tid; i0 < B; i0 += SEL_UNROLL * SEL_THREADS) {
+                double xs[SEL_UNROLL];
+                sel_load(v, i0, B, xs);
+#pragma unroll
+                for (int u = 0; u < SEL_UNROLL; ++u) {
+                    const double x = xs[u];
+                    if (x == x) { const unsigned long long k = sel_key(x); lo = (k < lo) ? k : lo; hi = (k > hi) ? k : hi; ++c; }
+                }
             }
             for (int o = 16; o >= 1; o >>= 1) {
                 const unsigned long long lo2 = __shfl_xor_sync(0xffffffffu, lo, o), hi2 = __shfl_xor_sync(0xffffffffu, hi, o);
@@ -189,13 +203,18 @@ __global__ void __launch_bounds__(SEL_THREADS) ppc_select_kernel(const double* _
             const int shift = s_shift, nshift = (shift > 8) ? shift - 8 : 0, width = shift - nshift, nb = n_buckets;
             for (int i = tid; i < nb * 256; i += SEL_THREADS) hist[i >> 8][i & 255] = 0u;
             __syncthreads();
-            for (long long i = tid; i < B; i += SEL_THREADS) {
-                const double x = v[i];
-                if (x == x) {
-                    const unsigned long long k = sel_key(x);
-                    const unsigned long long hi = (shift < 64) ? (k >> shift) : 0ULL;
-                    const unsigned d = (unsigned)((k >> nshift) & ((1ULL << width) - 1ULL));
-                    for (int a = 0; a < nb; ++a) if (hi == b_prefix[a]) atomicAdd(&hist[a][d], 1u);
+            for (long long i0 = tid; i0 < B; i0 += SEL_UNROLL * SEL_THREADS) {
+                double xs[SEL_UNROLL];
+                sel_load(v, i0, B, xs);
+#pragma unroll
+                for (int u = 0; u < SEL_UNROLL; ++u) {
+                    const double x = xs[u];
+                    if (x == x) {
+                        const unsigned long long k = sel_key(x);
+                        const unsigned long long hi = (shift < 64) ? (k >> shift) : 0ULL;
+                        const unsigned d = (unsigned)((k >> nshift) & ((1ULL << width) - 1ULL));
+                        for (int a = 0; a < nb; ++a) if (hi == b_prefix[a]) atomicAdd(&hist[a][d], 1u);
+                    }
                 }
             }
             __syncthreads();
@@ -226,13 +245,18 @@ __global__ void __launch_bounds__(SEL_THREADS) ppc_select_kernel(const double* _
             const int nb = n_buckets;
             if (tid < nb) cand_n[tid] = 0u;
             __syncthreads();
-            for (long long i = tid; i < B; i += SEL_THREADS) {
-                const double x = v[i];
-                if (x == x) {
-                    const unsigned long long k = sel_key(x);
-                    const unsigned long long hi = (shift < 64) ? (k >> shift) : 0ULL;
-                    for (int a = 0; a < nb; ++a)
-                        if (hi == b_prefix[a]) { const unsigned pos = atomicAdd(&cand_n[a], 1u); if (pos < (unsigned)SEL_CAP) cand[a][pos] = k; }
+            for (long long i0 = tid; i0 < B; i0 += SEL_UNROLL * SEL_THREADS) {
+                double xs[SEL_UNROLL];
+                sel_load(v, i0, B, xs);
+#pragma unroll
+                for (int u = 0; u < SEL_UNROLL; ++u) {
+                    const double x = xs[u];
+                    if (x == x) {
+                        const unsigned long long k = sel_key(x);
+                        const unsigned long long hi = (shift < 64) ? (k >> shift) : 0ULL;
+                        for (int a = 0; a < nb; ++a)
+                            if (hi == b_prefix[a]) { const unsigned pos = atomicAdd(&cand_n[a], 1u); if (pos < (unsigned)SEL_CAP) cand[a][pos] = k; }
+                    }
                 }
             }
             __syncthreads();
