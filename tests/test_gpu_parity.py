@@ -364,6 +364,14 @@ def test_posterior_predictive_quantiles_match_numpy_on_oracle_trajectories(probl
     assert err.max() < 1e-8, err.max()
     assert np.all(np.diff(got, axis=-1) >= 0)                                       # quantiles are ordered
     assert np.all(np.diff(got[3:], axis=1) >= -1e-9)                                # cumulative series are non-decreasing in time
+    # more than 8 probabilities take the full-sort path, up to 8 the multi-select: same numbers where they overlap
+    many = tuple(np.linspace(0.0, 1.0, 11))
+    ref11, _ = _ppc_reference(loose, o, P, s0, many)
+    with ev_mod.BatchEvaluator(loose, device=0) as ev:
+        got11, _ = ev.posterior_predictive(P, s0, many)
+        got3, _ = ev.posterior_predictive(P, s0, (0.0, 0.5, 1.0))
+    assert (np.abs(got11 - ref11) / np.maximum(np.abs(ref11), 1e-6)).max() < 1e-8
+    np.testing.assert_array_equal(got3, got11[..., [0, 5, 10]])
     # a single draw: every quantile is that draw's value
     with ev_mod.BatchEvaluator(loose, device=0) as ev:
         one, v1 = ev.posterior_predictive(P[:1], s0, (0.0, 0.5, 1.0))
