@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cmath>
 #include <fstream>
+#include <iomanip>
 #include <limits>
 
 namespace epidemic {
@@ -381,6 +382,80 @@ void PostCalibrationAnalyser::writeScenarioComparison(const std::string& filepat
              << m.seroprevalence_at_target_day;
         for (const auto& kv : m.kappa_values) file << ',' << kv.second;
         file << '\n';
+    }
+}
+
+// ---- AnalysisWriter -----------------------------------------------------------------------------------------------------
+void AnalysisWriter::savePosteriorPredictiveData(const std::string& output_dir, const PosteriorPredictiveData& ppd) const {
+    std::ptrdiff_t n_ages = 0;                                        // .cpp:288-299: from the data, else the default 4
+    if (ppd.daily_hospitalizations.median.cols() > 0) n_ages = ppd.daily_hospitalizations.median.cols();
+    else if (ppd.daily_deaths.median.cols() > 0) n_ages = ppd.daily_deaths.median.cols();
+    else n_ages = 4;
+    auto save_matrix = [&](const MatrixXd& m, const std::string& base, const char* suffix) {
+        std::ofstream file(output_dir + "/" + base + "_" + suffix + ".csv");
+        if (!file.is_open()) return;                                  // the reference logs and goes on
+        const std::ptrdiff_t cols = std::min(n_ages, m.cols());
+        file << "time";
+        for (std::ptrdiff_t a = 0; a < cols; ++a) file << ",age_" << a;
+        file << "\n";
+        for (size_t t = 0; t < ppd.time_points.size(); ++t) {
+            file << ppd.time_points[t];
+            for (std::ptrdiff_t a = 0; a < cols; ++a) file << "," << std::fixed << std::setprecision(6) << m(static_cast<std::ptrdiff_t>(t), a);
+            file << "\n";
+        }
+    };
+    auto save_series = [&](const PosteriorPredictiveData::IncidenceData& d, const std::string& base) {
+        save_matrix(d.median, base, "median");
+        save_matrix(d.lower_90, base, "lower90");
+        save_matrix(d.upper_90, base, "upper90");
+        save_matrix(d.lower_95, base, "lower95");
+        save_matrix(d.upper_95, base, "upper95");
+        save_matrix(d.observed, base, "observed");
+    };
+    save_series(ppd.daily_hospitalizations, "daily_hospitalizations");
+    save_series(ppd.daily_icu_admissions, "daily_icu_admissions");
+    save_series(ppd.daily_deaths, "daily_deaths");
+    save_series(ppd.cumulative_hospitalizations, "cumulative_hospitalizations");
+    save_series(ppd.cumulative_icu_admissions, "cumulative_icu_admissions");
+    save_series(ppd.cumulative_deaths, "cumulative_deaths");
+}
+
+void AnalysisWriter::saveParameterPosteriors(const std::string& output_dir, const std::vector<VectorXd>& samples,
+                                             const std::vector<std::string>& names, int burn_in, int thinning) const {
+    const size_t first = static_cast<size_t>(std::max(burn_in, 0)), step = static_cast<size_t>(std::max(thinning, 1));
+    {
+        std::ofstream sfile(output_dir + "/posterior_samples.csv");
+        if (!sfile.is_open()) return;
+        sfile << "sample_index";
+        for (const auto& nm : names) sfile << "," << nm;
+        sfile << "\n";
+        int saved = 0;
+        for (size_t i = first; i < samples.size(); i += step) {
+            sfile << saved++;
+            for (std::ptrdiff_t j = 0; j < samples[i].size(); ++j) sfile << "," << std::scientific << std::setprecision(8) << samples[i](j);
+            sfile << "\n";
+        }
+    }
+    std::ofstream sum(output_dir + "/posterior_summary.csv");
+    if (!sum.is_open()) return;
+    sum << "parameter,mean,median,std_dev,lower_95_ci,upper_95_ci\n";
+    sum << std::fixed << std::setprecision(8);
+    for (size_t p = 0; p < names.size(); ++p) {
+        std::vector<double> values;
+        for (size_t i = first; i < samples.size(); i += step)
+            if (static_cast<std::ptrdiff_t>(p) < samples[i].size()) values.push_back(samples[i](static_cast<std::ptrdiff_t>(p)));
+        if (values.empty()) continue;
+        std::sort(values.begin(), values.end());
+        double total = 0.0;
+        for (double v : values) total += v;                           // std::accumulate over the SORTED values (.cpp:258)
+        const double mean = total / static_cast<double>(values.size());
+        const double median = values[values.size() / 2];              // upper median, no interpolation (.cpp:259)
+        const double q025 = values[static_cast<size_t>(0.025 * static_cast<double>(values.size()))];
+        const double q975 = values[static_cast<size_t>(0.975 * static_cast<double>(values.size()))];
+        double ss = 0.0;
+        for (double v : values) ss += (v - mean) * (v - mean);
+        const double sd = std::sqrt(ss / static_cast<double>(values.size()));   // population form
+        sum << names[p] << "," << mean << "," << median << "," << sd << "," << q025 << "," << q975 << "\n";
     }
 }
 

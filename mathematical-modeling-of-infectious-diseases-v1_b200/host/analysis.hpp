@@ -125,4 +125,23 @@ private:
     MetricsCalculator metrics_;
 };
 
+// AnalysisWriter (src/model/AnalysisWriter.cpp): the report files the reference's plotting scripts read.  The reference queues
+// the writes on a worker thread; here they are written when the call is made (waitForCompletion() is kept and does nothing).
+//   savePosteriorPredictiveData  .cpp:283-347   <series>_{median,lower90,upper90,lower95,upper95,observed}.csv for the six series
+//   saveParameterPosteriors      .cpp:201-281   posterior_samples.csv, posterior_summary.csv
+//   saveScenarioComparison       .cpp:439-477   scenario_comparison.csv
+// Number formats are the reference's, stream state included: in the posterior-predictive files the time column of the FIRST row
+// is printed with the stream's default format and, once a value has switched the stream to fixed / 6 digits, every later one in
+// that format ("0", then "1.000000", ...).
+class AnalysisWriter {
+public:
+    void savePosteriorPredictiveData(const std::string& output_dir, const PosteriorPredictiveData& ppd_data) const;
+    void saveParameterPosteriors(const std::string& output_dir, const std::vector<VectorXd>& param_samples,
+                                 const std::vector<std::string>& param_names, int burn_in, int thinning) const;
+    void saveScenarioComparison(const std::string& filepath, const std::vector<PostCalibrationAnalyser::NamedMetrics>& scenarios) const {
+        PostCalibrationAnalyser::writeScenarioComparison(filepath, scenarios);
+    }
+    void waitForCompletion() const {}
+};
+
 }  // namespace epidemic

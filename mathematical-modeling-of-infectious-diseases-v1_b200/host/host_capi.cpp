@@ -519,6 +519,40 @@ int32_t sepaihrd_host_model_gradient(sepaihrd_host_model* m, const double* param
         std::copy(grad.data(), grad.data() + P, out_grad);
     });
 }
+// ---- AnalysisWriter files from plain arrays (host only) ---------------------------------------------------------------------
+int32_t sepaihrd_host_write_posterior_predictive(const char* output_dir, int32_t T, int32_t n_ages, const double* time_points,
+                                                 const double* quantiles, const double* observed) {
+    return guarded([&] {
+        if (!output_dir || !time_points || !quantiles || T < 0 || n_ages < 0) throw InvalidParameterException("sepaihrd_host_write_posterior_predictive", "bad argument");
+        PosteriorPredictiveData d;
+        d.time_points.assign(time_points, time_points + T);
+        PosteriorPredictiveData::IncidenceData* series[6] = {&d.daily_hospitalizations, &d.daily_icu_admissions, &d.daily_deaths,
+                                                             &d.cumulative_hospitalizations, &d.cumulative_icu_admissions, &d.cumulative_deaths};
+        for (int s = 0; s < 6; ++s) {
+            MatrixXd* q[5] = {&series[s]->lower_95, &series[s]->lower_90, &series[s]->median, &series[s]->upper_90, &series[s]->upper_95};
+            for (int k = 0; k < 5; ++k) {
+                *q[k] = MatrixXd::Zero(T, n_ages);
+                for (int t = 0; t < T; ++t) for (int a = 0; a < n_ages; ++a) (*q[k])(t, a) = quantiles[(((size_t)s * T + t) * n_ages + a) * 5 + k];
+            }
+            if (observed) {
+                series[s]->observed = MatrixXd::Zero(T, n_ages);
+                for (int t = 0; t < T; ++t) for (int a = 0; a < n_ages; ++a) series[s]->observed(t, a) = observed[((size_t)s * T + t) * n_ages + a];
+            }
+        }
+        AnalysisWriter().savePosteriorPredictiveData(output_dir, d);
+    });
+}
+int32_t sepaihrd_host_write_parameter_posteriors(const char* output_dir, const double* samples, int64_t S, int32_t P, const char* const* names,
+                                                 int32_t burn_in, int32_t thinning) {
+    return guarded([&] {
+        if (!output_dir || (S > 0 && !samples) || !names || P < 0) throw InvalidParameterException("sepaihrd_host_write_parameter_posteriors", "bad argument");
+        std::vector<VectorXd> sv;
+        for (int64_t i = 0; i < S; ++i) sv.push_back(VectorXd::FromPointer(samples + i * P, P));
+        std::vector<std::string> nm;
+        for (int32_t j = 0; j < P; ++j) nm.emplace_back(names[j]);
+        AnalysisWriter().saveParameterPosteriors(output_dir, sv, nm, burn_in, thinning);
+    });
+}
 int32_t sepaihrd_host_model_set_cache(sepaihrd_host_model* m, int64_t capacity) {
     return guarded([&] {
         if (!m || capacity < 0) throw InvalidParameterException("sepaihrd_host_model_set_cache", "bad argument");

@@ -139,6 +139,14 @@ int32_t sepaihrd_host_model_posterior_predictive(sepaihrd_host_model* m, const d
 /* SEPAIHRDGradientObjectiveFunction::evaluate_with_gradient: the objective at params and its forward-difference gradient
  * (step epsilon * max(|x_i|, epsilon), epsilon <= 0: the reference's 1e-4), the P perturbed vectors as one device batch.     */
 int32_t sepaihrd_host_model_gradient(sepaihrd_host_model* m, const double* params, double epsilon, double* out_value, double* out_grad /* [P] */);
+/* AnalysisWriter (src/model/AnalysisWriter.cpp) from plain arrays, host only.
+ * posterior predictive (.cpp:283-347): quantiles [6][T][n_ages][5] in the order lower_95, lower_90, median, upper_90, upper_95 (what
+ * sepaihrd_host_model_posterior_predictive returns), observed [6][T][n_ages] or NULL -> 36 files <series>_<what>.csv in output_dir.
+ * parameter posteriors (.cpp:201-281): samples [S][P] -> posterior_samples.csv, posterior_summary.csv.                          */
+int32_t sepaihrd_host_write_posterior_predictive(const char* output_dir, int32_t T, int32_t n_ages, const double* time_points,
+                                                 const double* quantiles, const double* observed_or_null);
+int32_t sepaihrd_host_write_parameter_posteriors(const char* output_dir, const double* samples, int64_t S, int32_t P,
+                                                 const char* const* names, int32_t burn_in, int32_t thinning);
 /* The model is built with the cache that caches nothing (parity runs).  capacity > 0: the objective and the
  * calibration are rebuilt over a SimulationCache of that capacity (src/model/main.cpp:371 uses 1000); 0: back to none.
  * stats[4] = entries, getLikelihood calls, hits, storeLikelihood calls.                                                     */

@@ -73,6 +73,8 @@ SIGNATURES = {
     "sepaihrd_host_model_calibrate": (C.c_int32, [_vp, C.c_char_p, C.c_int32, _keys, _vp, C.c_int32, _keys, _vp, _vp, _dp, _i64p]),
     "sepaihrd_host_model_posterior_predictive": (C.c_int32, [_vp, _vp, C.c_int64, C.c_int32, C.c_uint32, _vp, _vp, _i64p]),
     "sepaihrd_host_model_gradient": (C.c_int32, [_vp, _vp, C.c_double, _dp, _vp]),
+    "sepaihrd_host_write_posterior_predictive": (C.c_int32, [C.c_char_p, C.c_int32, C.c_int32, _vp, _vp, _vp]),
+    "sepaihrd_host_write_parameter_posteriors": (C.c_int32, [C.c_char_p, _vp, C.c_int64, C.c_int32, _keys, C.c_int32, C.c_int32]),
     "sepaihrd_host_model_set_cache": (C.c_int32, [_vp, C.c_int64]),
     "sepaihrd_host_model_cache_stats": (C.c_int32, [_vp, _vp]),
     "sepaihrd_host_model_destroy": (None, [_vp]),
@@ -374,6 +376,21 @@ class Cache:
         if getattr(self, "_h", None):
             self.L.sepaihrd_host_cache_destroy(self._h)
             self._h = None
+
+
+def write_posterior_predictive(output_dir: str, time_points, quantiles, observed=None):
+    """AnalysisWriter::savePosteriorPredictiveData: quantiles [6, T, n, 5] (HostModel.posterior_predictive), observed [6, T, n]."""
+    q = _c64(quantiles); t = _c64(time_points)
+    obs = None if observed is None else _c64(observed)
+    check(load_library().sepaihrd_host_write_posterior_predictive(output_dir.encode(), q.shape[1], q.shape[2], t.ctypes.data, q.ctypes.data,
+                                                                   None if obs is None else obs.ctypes.data))
+
+
+def write_parameter_posteriors(output_dir: str, samples, names: Sequence[str], burn_in: int = 0, thinning: int = 1):
+    """AnalysisWriter::saveParameterPosteriors: posterior_samples.csv and posterior_summary.csv."""
+    x = _c64(samples)
+    arr = (C.c_char_p * len(names))(*[n.encode() for n in names])
+    check(load_library().sepaihrd_host_write_parameter_posteriors(output_dir.encode(), x.ctypes.data, x.shape[0], x.shape[1], arr, int(burn_in), int(thinning)))
 
 
 def _batch_callback(evaluate, P):
