@@ -97,7 +97,9 @@ struct sepaihrd_ctx {
     std::vector<double> blob;   // host image
     sepaihrd::KParams kp{};     // offsets etc. (I/O fields filled per call)
     double* d_blob = nullptr;
-    unsigned* d_tile_counter = nullptr;
+    static constexpr unsigned N_TILE_COUNTERS = 64;
+    unsigned* d_tile_counter = nullptr;   // ring of N_TILE_COUNTERS work counters, one per launch in flight
+    unsigned launch_seq = 0;
     cudaStream_t own_stream = nullptr;
     cudaStream_t copy_stream = nullptr;   // host-pointer entry points: H2D / early D2H next to the compute stream
     cudaStream_t stream2 = nullptr;       // host-pointer evaluation: odd chunks run here, so a chunk's first blocks start while the previous chunk's last warps drain
@@ -111,6 +113,7 @@ struct sepaihrd_ctx {
     unsigned* d_status = nullptr; size_t cap_status = 0;
     int* d_steps = nullptr; size_t cap_steps = 0;
     long long launches = 0, sets = 0;
+    double* dbg_trace = nullptr;          // SEPAIHRD_DEBUG_INTERVALS builds only
 };
 
 namespace {
@@ -118,7 +121,7 @@ namespace {
 template <class T>
 sepaihrd_rc grow(T** ptr, size_t* cap, size_t need) {
     if (need <= *cap) return SEPAIHRD_OK;
-    if (*ptr) cudaFree(*ptr);
+    if (*ptr) { cudaDeviceSynchronize(); cudaFree(*ptr); }   // nothing queued on ANY stream may still use the old buffer
     *ptr = nullptr; *cap = 0;
     CUDA_TRY(cudaMalloc((void**)ptr, need * sizeof(T)));
     *cap = need;
@@ -135,14 +138,17 @@ sepaihrd_rc launch_t(sepaihrd_ctx* ctx, const sepaihrd::KParams& kp_in) {
     constexpr int WSETS = (32 / NA) > 0 ? (32 / NA) : 1;
     kp.tiles = (kp.B + WSETS - 1) / WSETS;
     if (kp.tiles > 0xffff0000LL) return fail(SEPAIHRD_ERR_UNSUPPORTED, "batch too large for one launch");
-    kp.tile_counter = ctx->d_tile_counter;
-    CUDA_TRY(cudaMemsetAsync(ctx->d_tile_counter, 0, sizeof(unsigned), ctx->stream));
+    // Every launch draws its tiles from its OWN counter (a ring of N_TILE_COUNTERS, zeroed on the launching stream right before
+    // the kernel): launches of one ctx that are in flight on different streams never share one.
+    kp.tile_counter = ctx->d_tile_counter + (ctx->launch_seq++ % sepaihrd_ctx::N_TILE_COUNTERS);
+    CUDA_TRY(cudaMemsetAsync(kp.tile_counter, 0, sizeof(unsigned), ctx->stream));
     auto kern = sepaihrd_batch_kernel<NA, STRICT, MODE, THREADS, MINBLOCKS, LOOP, ONGRID>;
     const size_t smem = (size_t)kp.blob_bytes + sizeof(double) * (SETS * (size_t)(kp.slot_stride + ((kp.seg_stride + 1) & ~1)) + 2 * THREADS + (size_t)NA * THREADS) + 16;
-    static bool attr_set[64] = {};   // per device
-    if (!attr_set[ctx->device & 63]) {
-        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set[ctx->device & 63] = true;
+    {   // once per device and instantiation, whichever thread / ctx gets here first
+        static std::once_flag attr_once[64];
+        cudaError_t attr_err = cudaSuccess;
+        std::call_once(attr_once[ctx->device & 63], [&] { attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); });
+        CUDA_TRY(attr_err);
     }
     if (smem > 200 * 1024) return fail(SEPAIHRD_ERR_UNSUPPORTED, "problem constants do not fit in shared memory");
     int occ = 0;
@@ -495,7 +501,7 @@ sepaihrd_rc create_impl(const sepaihrd_problem* pb, int n_user, int n, int32_t d
     cudaError_t e = cudaGetDeviceProperties(&prop, device);
     if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_blob, kp.blob_bytes);
     if (e == cudaSuccess) e = cudaMemcpy(ctx->d_blob, B.data(), kp.blob_bytes, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_tile_counter, 4 * sizeof(unsigned));   // one per chunk in flight (host-pointer evaluation)
+    if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_tile_counter, sepaihrd_ctx::N_TILE_COUNTERS * sizeof(unsigned));
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking);
@@ -559,6 +565,10 @@ sepaihrd_rc sepaihrd_set_stream(sepaihrd_ctx* ctx, void* cuda_stream) {
     return SEPAIHRD_OK;
 }
 
+#ifdef SEPAIHRD_DEBUG_INTERVALS
+sepaihrd_rc sepaihrd_debug_set_trace(sepaihrd_ctx* ctx, double* d_trace) { ctx->dbg_trace = d_trace; return SEPAIHRD_OK; }
+#endif
+
 sepaihrd_rc sepaihrd_release_scratch(sepaihrd_ctx* ctx) {
     if (!ctx) return fail(SEPAIHRD_ERR_INVALID_ARGUMENT, "null argument");
     std::lock_guard<std::recursive_mutex> lock(ctx->mu);
@@ -621,6 +631,9 @@ sepaihrd_rc sepaihrd_eval_batch_device(sepaihrd_ctx* ctx, const double* d_params
     kp.params = d_params; kp.B = B; kp.ld = ld;
     kp.out_ll = d_out_ll; kp.out_status = d_out_status; kp.out_steps = d_out_steps;
     kp.out_traj = nullptr; kp.traj_what = 0; kp.traj_stride = 1; kp.traj_rows = 0; kp.traj_draw_minor = 0;
+#ifdef SEPAIHRD_DEBUG_INTERVALS
+    kp.out_traj = ctx->dbg_trace;      // diagnostic build: [B][2048][3] (t, step, err) of every attempt
+#endif
     kp.init_states = nullptr; kp.init_stride = 0;
     return launch(ctx, kp, sepaihrd::MODE_LL);
 }
@@ -663,23 +676,31 @@ sepaihrd_rc eval_batch_serial(sepaihrd_ctx* ctx, const double* params, int64_t B
         }
         off[n_chunks] = B;
     }
+    struct DrainCopies {     // declared before the first copy is queued: an early return below must not leave one in flight
+        sepaihrd_ctx* ctx;
+        ~DrainCopies() { cudaStreamSynchronize(ctx->copy_stream); }
+    } drain_copies{ctx};
     for (int c = 0; c < n_chunks; ++c) {
         const int64_t b0 = off[c], nb = off[c + 1] - off[c];
         CUDA_TRY(cudaMemcpyAsync(ctx->d_params + b0 * ld, params + b0 * ld, sizeof(double) * (size_t)nb * ld, cudaMemcpyHostToDevice, ctx->copy_stream));
         CUDA_TRY(cudaEventRecord(ctx->ev_copy[c], ctx->copy_stream));
     }
-    // Chunk c runs on the ctx stream (even c) or on a second compute stream (odd c) with its own tile counter: nothing orders
+    // Chunk c runs on the ctx stream (even c) or on a second compute stream (odd c); every launch has its own tile counter: nothing orders
     // the kernels among themselves, so the first blocks of chunk c + 1 start on the SMs the last warps of chunk c have left.
+    // On EVERY way out -- error returns included -- the three streams are drained before the caller gets its buffers back:
+    // copies of earlier chunks may still be reading `params` or writing `out_*`.
     struct Restore {
-        sepaihrd_ctx* ctx; cudaStream_t stream; unsigned* counter;
-        ~Restore() { ctx->stream = stream; ctx->d_tile_counter = counter; }
-    } restore{ctx, ctx->stream, ctx->d_tile_counter};
+        sepaihrd_ctx* ctx; cudaStream_t stream;
+        ~Restore() {
+            ctx->stream = stream;
+            cudaStreamSynchronize(ctx->stream2); cudaStreamSynchronize(ctx->copy_stream); cudaStreamSynchronize(stream);
+        }
+    } restore{ctx, ctx->stream};
     static const bool two_streams = std::getenv("SEPAIHRD_E2E_ONE_STREAM") == nullptr;
     for (int c = 0; c < n_chunks; ++c) {
         const int64_t b0 = off[c], nb = off[c + 1] - off[c];
         cudaStream_t s = (two_streams && (c & 1)) ? ctx->stream2 : restore.stream;
         ctx->stream = s;
-        ctx->d_tile_counter = restore.counter + c;
         CUDA_TRY(cudaStreamWaitEvent(s, ctx->ev_copy[c], 0));
         rc = sepaihrd_eval_batch_device(ctx, ctx->d_params + b0 * ld, nb, ld, ctx->d_out + b0, ctx->d_status + b0,
                                         out_steps ? ctx->d_steps + 2 * b0 : nullptr);
@@ -942,8 +963,10 @@ std::unique_lock<std::recursive_mutex> lock(sepaihrd_ctx* ctx) { return std::uni
 void* scratch(sepaihrd_ctx* ctx, int slot, size_t bytes) {
     if (slot < 0 || slot >= sepaihrd_ctx::N_SCRATCH) return nullptr;
     if (ctx->scratch_bytes[slot] >= bytes && ctx->scratch[slot]) return ctx->scratch[slot];
-    cudaStreamSynchronize(ctx->stream);             // nothing in flight may still use the buffer that is replaced
-    if (ctx->scratch[slot]) cudaFree(ctx->scratch[slot]);
+    if (ctx->scratch[slot]) {
+        cudaDeviceSynchronize();                    // the ctx stream may have been re-pointed since the buffer was last used: drain the whole device
+        cudaFree(ctx->scratch[slot]);
+    }
     ctx->scratch[slot] = nullptr; ctx->scratch_bytes[slot] = 0;
     void* p = nullptr;
     if (cudaMalloc(&p, bytes ? bytes : 16) != cudaSuccess) { cudaGetLastError(); return nullptr; }
@@ -951,7 +974,7 @@ void* scratch(sepaihrd_ctx* ctx, int slot, size_t bytes) {
     return p;
 }
 void release_scratch(sepaihrd_ctx* ctx) {
-    cudaStreamSynchronize(ctx->stream);
+    cudaDeviceSynchronize();
     for (int i = 0; i < sepaihrd_ctx::N_SCRATCH; ++i) {
         if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
         ctx->scratch[i] = nullptr; ctx->scratch_bytes[i] = 0;

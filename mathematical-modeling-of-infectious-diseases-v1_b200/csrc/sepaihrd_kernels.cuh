@@ -692,6 +692,9 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) sepaihrd_batch_kernel(cons
         const unsigned lane_bit = 1u << (threadIdx.x & 31);
         for (int idx = 0; idx < K; ++idx) {
             t = s_times[idx];
+#ifdef SEPAIHRD_DEBUG_INTERVALS   // diagnostic build (tools/strict_parity_diag.py): out_steps is [B][K][2], running totals at every grid point
+            if (MODE == MODE_LL && have && age == 0 && kp.out_steps) { kp.out_steps[(b * K + idx) * 2] = n_acc; kp.out_steps[(b * K + idx) * 2 + 1] = n_rej; }
+#endif
             if (MODE == MODE_TRAJ) {
                 if (have && alive && (idx % kp.traj_stride == 0)) {
                     double* row = traj_out + (size_t)(idx / kp.traj_stride) * t_rs;
@@ -782,6 +785,12 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) sepaihrd_batch_kernel(cons
                     // The common day: every stepping group took the full step and accepted it.  dt >= hmax, so nothing about
                     // the error norm's value can matter: commit and leave the day.
                     if (active) {
+#ifdef SEPAIHRD_DEBUG_INTERVALS
+                        if (MODE == MODE_LL && have && age == 0 && kp.out_traj && n_acc + n_rej < 2048) {
+                            double* tr = kp.out_traj + ((size_t)b * 2048 + (n_acc + n_rej)) * 3;
+                            tr[0] = t; tr[1] = cur; tr[2] = -2.0;
+                        }
+#endif
                         t = t_end;
                         ++n_acc;
                         fail_steps = 0;
@@ -829,6 +838,12 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) sepaihrd_batch_kernel(cons
                     facv = 0.9 * pow_neg_inv(reject ? err : std_max(3.2e-4 /* pow(5,-5) */, err), reject);
                 }
                 unsigned m_dead = 0;
+#ifdef SEPAIHRD_DEBUG_INTERVALS
+                if (MODE == MODE_LL && active && have && age == 0 && kp.out_traj && n_acc + n_rej < 2048) {
+                    double* tr = kp.out_traj + ((size_t)b * 2048 + (n_acc + n_rej)) * 3;
+                    tr[0] = t; tr[1] = cur; tr[2] = (m_val != 0) ? err : (reject ? 1e300 : -1.0);
+                }
+#endif
                 if (reject) {
                     const double shrink = ((g_sb & lane_bit) || err > 128.0) ? 0.2 : std_max(facv, 0.2);   // 0.9 err^(-1/3) < 0.2 beyond 91.2
                     dt = cur * shrink;
@@ -868,6 +883,9 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) sepaihrd_batch_kernel(cons
         // Unfused IEEE mul/add in source order, libm pow/log, true divisions, likelihood summed row by row per stream.
         for (int idx = 0; idx < K; ++idx) {
             t = s_times[idx];
+#ifdef SEPAIHRD_DEBUG_INTERVALS
+            if (MODE == MODE_LL && have && age == 0 && kp.out_steps) { kp.out_steps[(b * K + idx) * 2] = n_acc; kp.out_steps[(b * K + idx) * 2 + 1] = n_rej; }
+#endif
             // ---- observer -----------------------------------------------------------------------------
             if (MODE == MODE_TRAJ) {
                 if (have && alive && (idx % kp.traj_stride == 0)) {
@@ -954,6 +972,12 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) sepaihrd_batch_kernel(cons
                     m = (m < v) ? v : m;
                 }
                 const double err = group_max<NA>(m);
+#ifdef SEPAIHRD_DEBUG_INTERVALS
+                if (MODE == MODE_LL && need && have && age == 0 && kp.out_traj && n_acc + n_rej < 2048) {
+                    double* tr = kp.out_traj + ((size_t)b * 2048 + (n_acc + n_rej)) * 3;
+                    tr[0] = t; tr[1] = cur; tr[2] = err;
+                }
+#endif
                 if (need) {
                     if (err > 1.0) {
                         // decrease_step (error_order 4): dt *= max(0.9 * err^(-1/3), 1/5)
@@ -999,7 +1023,9 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) sepaihrd_batch_kernel(cons
             if (have && age == 0) {
                 kp.out_ll[b] = total;
                 if (kp.out_status) kp.out_status[b] = status;
+#ifndef SEPAIHRD_DEBUG_INTERVALS
                 if (kp.out_steps) { kp.out_steps[2 * b] = n_acc; kp.out_steps[2 * b + 1] = n_rej; }
+#endif
             }
         } else {
             if (have && status != 0) {   // failed sets: NaN-fill every row

@@ -112,6 +112,17 @@ class Oracle:
         return dict(ll=ll, status=st.value, traj=traj, interval_steps=isteps,
                     accepted=int(counts[0]), rejected=int(counts[1]), rhs_calls=int(counts[2]))
 
+    def trace_one(self, params, cap: int = 8192):
+        """(t, dt, err) of every step attempt of one evaluation: [attempts, 3]."""
+        x = _c64(params)
+        out = np.zeros((cap, 3))
+        ll = C.c_double()
+        f = self.L.sepaihrd_oracle_trace_one
+        f.restype = C.c_int64
+        f.argtypes = [C.c_void_p, _dp, C.c_int64, _dp, C.POINTER(C.c_double)]
+        n = f(self._ref, _p(x), cap, _p(out), C.byref(ll))
+        return out[:min(n, cap)], ll.value
+
     def eval_batch(self, params, nthreads: int = 0):
         x = _c64(params)
         B, ld = x.shape

@@ -171,6 +171,7 @@ struct Dopri5 {
     int dim;
     double eps_abs, eps_rel;
     bool first_call = true;
+    double* trace = nullptr; long trace_cap = 0, trace_n = 0;   // diagnostics: (t, dt, err) of every attempt (sepaihrd_oracle_trace_one)
     double dxdt[MAXS], xnew[MAXS], dxdt_new[MAXS], xerr[MAXS];
     double xt[MAXS], k2[MAXS], k3[MAXS], k4[MAXS], k5[MAXS], k6[MAXS];
 
@@ -227,6 +228,8 @@ struct Dopri5 {
             double v = std::fabs(xerr[i]) / (eps_abs + eps_rel * (a_x * std::fabs(x[i]) + a_dxdt_dt * std::fabs(dxdt[i])));
             max_rel_err = std::max(max_rel_err, std::fabs(v));           // norm_inf: std::max(init, |v|) ignores NaN
         }
+        if (trace && trace_n < trace_cap) { trace[3 * trace_n] = t; trace[3 * trace_n + 1] = dt; trace[3 * trace_n + 2] = max_rel_err; }
+        ++trace_n;
         if (max_rel_err > 1.0) {
             // decrease_step(dt, err, error_order = 4): dt *= max(0.9 * err^(-1/(4-1)), 1/5)
             dt *= std::max(9.0 / 10.0 * std::pow(max_rel_err, -1.0 / (4 - 1)), 1.0 / 5.0);
@@ -371,6 +374,7 @@ double poisson_ll(const double* simulated, const double* observed, int rows, int
 
 struct EvalScratch {
     std::vector<double> slots, traj, inc_h, inc_icu, inc_d;
+    double* trace = nullptr; long trace_cap = 0;
 };
 
 // calculate() (.cpp:62-235) with a null cache. traj_out: [K][11n] (optional).
@@ -393,6 +397,7 @@ double eval_one(const sepaihrd_problem* pb, const double* params, uint32_t* stat
     double* traj = sc.traj.data();
     Model model; model.init(pb, sc.slots.data());
     Dopri5 stepper; stepper.dim = dim; stepper.eps_abs = pb->abs_tol; stepper.eps_rel = pb->rel_tol;
+    stepper.trace = sc.trace; stepper.trace_cap = sc.trace_cap;
     IntegrateStats stats;
     bool ok = integrate_times(model, stepper, x, pb->times, K, pb->dt_hint,
         [&](const double* xs, double, int idx) { std::memcpy(traj + (size_t)idx * dim, xs, sizeof(double) * dim); },
@@ -548,6 +553,16 @@ double sepaihrd_oracle_eval_one(const sepaihrd_problem* pb, const double* params
                                 double* out_traj, int32_t* out_interval_steps, int64_t* out_counts) {
     EvalScratch sc;
     return eval_one(pb, params, out_status, out_traj, out_interval_steps, out_counts, sc);
+}
+
+int64_t sepaihrd_oracle_trace_one(const sepaihrd_problem* pb, const double* params, int64_t cap, double* out_trace, double* out_ll) {
+    EvalScratch sc;
+    sc.trace = out_trace; sc.trace_cap = (long)cap;
+    int64_t counts[3] = {0, 0, 0};
+    uint32_t st = 0;
+    const double ll = eval_one(pb, params, &st, nullptr, nullptr, counts, sc);
+    if (out_ll) *out_ll = ll;
+    return counts[0] + counts[1];
 }
 
 int32_t sepaihrd_oracle_eval_batch(const sepaihrd_problem* pb, const double* params, int64_t B, int64_t ld,

@@ -68,6 +68,10 @@ void sepaihrd_oracle_initial_state_from_data(int32_t n, const double* population
 double sepaihrd_oracle_eval_one(const sepaihrd_problem* pb, const double* params, uint32_t* out_status,
                                 double* out_traj, int32_t* out_interval_steps, int64_t* out_counts);
 
+/* Diagnostics: one evaluation with (t, dt, err) of every step attempt written to out_trace[cap][3]; returns the number of
+ * attempts (which may exceed cap). */
+int64_t sepaihrd_oracle_trace_one(const sepaihrd_problem* pb, const double* params, int64_t cap, double* out_trace, double* out_ll);
+
 /* B evaluations, OpenMP over sets (schedule(dynamic)); nthreads <= 0 = all cores.
  * out_status / out_steps ([B][2]) may be NULL. Returns the number of threads used. */
 int32_t sepaihrd_oracle_eval_batch(const sepaihrd_problem* pb, const double* params, int64_t B, int64_t ld,
