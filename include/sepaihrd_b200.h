@@ -26,6 +26,10 @@
  *   - there is NO CPU fallback: if no CUDA device is usable, sepaihrd_create fails.
  *   - a ctx may be used from several host threads: every entry point takes the ctx's lock for its duration.  The
  *     `_device` variants only ENQUEUE on the ctx stream; ordering between threads that enqueue is the callers' business.
+ *   - streams: evaluation / simulation launches of one ctx may be in flight on DIFFERENT streams (sepaihrd_set_stream between
+ *     calls): every launch owns its work counter.  The host-pointer entry points, the posterior-predictive pass, the swarm
+ *     and the sampler reuse per-ctx staging / work buffers and therefore assume ONE stream at a time; buffers that have to
+ *     grow are replaced only after the whole device has drained.
  */
 #ifndef SEPAIHRD_B200_H
 #define SEPAIHRD_B200_H
@@ -230,6 +234,96 @@ sepaihrd_rc sepaihrd_swarm_step(sepaihrd_swarm* swarm, const uint32_t* seeds, do
                                 const double* global_best);
 /* Copy one of the swarm's arrays to the host: [local][P] or [local] (SEPAIHRD_SWARM_*).                                */
 sepaihrd_rc sepaihrd_swarm_read(sepaihrd_swarm* swarm, int32_t what, double* out);
+
+/* Fully asynchronous form of the swarm iteration (no host synchronisation, no host<->device copy per iteration): the seeds of
+ * every iteration are uploaded once, the global best stays on the device, and the per-rank best travels as ONE record
+ * [value, global particle index, position[P]] (2 + P doubles) that the caller all-gathers between the ranks -- with
+ * sepaihrd_exchange_all_gather below (NVLink peer memory) or any collective on device buffers (ncclAllGather).
+ *   upload_seeds     seeds [n_sets][swarm_size]: set 0 is consumed by sepaihrd_swarm_init_async, set 1 + it by step `it`
+ *   init_async       sepaihrd_swarm_init from seed set 0 (initial as for sepaihrd_swarm_init, host pointer or NULL)
+ *   evaluate_async   objective launch + personal bests + the shard's best record, all enqueued on the ctx stream
+ *   record_device    device pointer of this shard's record (valid until sepaihrd_swarm_destroy)
+ *   adopt_global_best  arg-max over `n_records` records (device, [n_records][record_stride]; ties: the lowest particle index,
+ *                    like a serial scan of the whole swarm) replaces the device-resident global best when STRICTLY better
+ *                    (ParticleSwarmOptimizer.cpp:149-156); the resulting best value is stored in trace[trace_slot]
+ *   step_async       sepaihrd_swarm_step with seed set 1 + iteration and the device-resident global best
+ *   read_trace       copies trace[0 .. n) to the host (synchronises the ctx stream)
+ *   read_global_best copies the device-resident global best (value, position[P]) to the host (synchronises)            */
+#define SEPAIHRD_SWARM_TRACE_CAPACITY 4096
+sepaihrd_rc sepaihrd_swarm_upload_seeds(sepaihrd_swarm* swarm, const uint32_t* seeds, int64_t n_sets);
+sepaihrd_rc sepaihrd_swarm_init_async(sepaihrd_swarm* swarm, const double* initial);
+sepaihrd_rc sepaihrd_swarm_evaluate_async(sepaihrd_swarm* swarm);
+sepaihrd_rc sepaihrd_swarm_record_device(sepaihrd_swarm* swarm, const double** d_record, int32_t* record_doubles);
+sepaihrd_rc sepaihrd_swarm_adopt_global_best(sepaihrd_swarm* swarm, const double* d_records, int32_t n_records,
+                                             int64_t record_stride, int32_t trace_slot);
+sepaihrd_rc sepaihrd_swarm_step_async(sepaihrd_swarm* swarm, int32_t iteration, double omega, double c1, double c2);
+sepaihrd_rc sepaihrd_swarm_read_trace(sepaihrd_swarm* swarm, double* out, int32_t n);
+sepaihrd_rc sepaihrd_swarm_read_global_best(sepaihrd_swarm* swarm, double* out_value, double* out_position);
+
+/* ---- device-resident Metropolis-Hastings chains ----------------------------------------------------------------------
+ * Replaces the per-iteration host work of MetropolisHastingsSampler (src/sir_age_structured/optimizers/
+ * MetropolisHastingsSampler.cpp: generateProposal :91-102, the accept test :318-330, adaptGlobalScale :104-152) for
+ * `local_count` of `n_chains` independent chains scored by this evaluator: chain states, generators, scales and accept
+ * history stay in HBM; one iteration = propose kernel -> fused likelihood kernel -> accept kernel on the ctx stream, no
+ * host work.  Chain c (GLOBAL index) draws from std::mt19937(std::seed_seq{seed, c}); arithmetic, generator and
+ * distributions reproduce the host sampler of this repository bit for bit (host/optimizers.cpp; log / exp of both are
+ * csrc/det_math.h), so a sharded device run makes the accept decisions of the single-process host run.
+ * Scope: the fixed-kernel phase (iterations - 1 <= burn_in); the covariance adaptation after burn-in (:154-199) is the host
+ * sampler's.  The ctx's constraint mode applies to the proposals (MCMC_REFLECT for the reference's sampler, :207-210).   */
+#define SEPAIHRD_MH_MAX_PARAMS 128
+typedef struct sepaihrd_mh sepaihrd_mh;
+typedef struct sepaihrd_mh_settings {
+    int32_t iterations;             /* mcmc_iterations: the loop runs t = 1 .. iterations - 1 (.cpp:283)            */
+    int32_t burn_in;                /* must be >= iterations - 1 here                                              */
+    int32_t adapt_scale;            /* 0 / 1: Robbins-Monro global scale (.cpp:104-152)                            */
+    int32_t record_accepts;         /* 0 / 1: keep the accept decision of every (iteration, chain) for parity checks */
+    double target_acceptance_rate;  /* 0.234                                                                       */
+} sepaihrd_mh_settings;
+enum { SEPAIHRD_MH_POSITIONS = 0, SEPAIHRD_MH_LOGPOST = 1, SEPAIHRD_MH_SCALES = 2, SEPAIHRD_MH_ACCEPTED_COUNTS = 3 /* int64 */,
+       SEPAIHRD_MH_BEST_LOGPOST = 4, SEPAIHRD_MH_BEST_POSITIONS = 5, SEPAIHRD_MH_ACCEPT_MATRIX = 6 /* uint8 [iterations done][local] */,
+       SEPAIHRD_MH_TRACE = 7 /* [iterations + 1] */, SEPAIHRD_MH_PROPOSALS = 8 };
+sepaihrd_rc sepaihrd_mh_create(sepaihrd_ctx* ctx, int64_t n_chains, int64_t chain_offset, int64_t local_count,
+                               const sepaihrd_mh_settings* settings, sepaihrd_mh** out);
+void sepaihrd_mh_destroy(sepaihrd_mh* mh);
+/* All chains start at initial [P] (its log-posterior is evaluated once on the device); chol_lower [P*P] column-major is the
+ * lower Cholesky factor of the proposal covariance (MetropolisHastingsSampler.cpp:216-240).  Enqueues; host buffers are
+ * consumed before the call returns. */
+sepaihrd_rc sepaihrd_mh_begin(sepaihrd_mh* mh, uint32_t seed, const double* initial, const double* chol_lower);
+/* Enqueue up to n_iterations iterations on the ctx stream (stops at settings.iterations). */
+sepaihrd_rc sepaihrd_mh_iterate(sepaihrd_mh* mh, int32_t n_iterations);
+int32_t sepaihrd_mh_iteration(const sepaihrd_mh* mh);    /* next iteration index, 1-based */
+/* Device pointer of the local chains' current log-posteriors [local_count]: the block a rank contributes to the
+ * per-iteration all-gather (north_star: "gather log-likelihoods for the MCMC accept step"). */
+sepaihrd_rc sepaihrd_mh_logpost_device(sepaihrd_mh* mh, const double** d_logpost);
+/* trace[trace_slot] = max over the gathered log-posteriors of all chains; d_all_logpost is [world][block_stride] with rank
+ * r's n_chains/world (+1 for the first n_chains % world ranks) values at the start of its block.  Enqueues. */
+sepaihrd_rc sepaihrd_mh_note_gathered(sepaihrd_mh* mh, const double* d_all_logpost, int32_t world, int64_t block_stride,
+                                      int32_t trace_slot);
+/* Copy one of the sampler's arrays to the host (SEPAIHRD_MH_*); synchronises the ctx stream. */
+sepaihrd_rc sepaihrd_mh_read(sepaihrd_mh* mh, int32_t what, void* out);
+
+/* ---- small-record all-gather between the GPUs of one node over NVLink peer memory --------------------------------------
+ * The callers of the hot path exchange KiB-scale records once per iteration: the ranks' log-likelihood blocks of a
+ * multi-chain Metropolis-Hastings run (MetropolisHastingsSampler.cpp:312-330), the per-rank best of a particle swarm
+ * (ParticleSwarmOptimizer.cpp:149-156, 417-421).  One process per GPU; every rank owns a mailbox in its HBM that its peers
+ * map through CUDA IPC.  sepaihrd_exchange_all_gather is ONE kernel on the ctx stream: block p stores this rank's record into
+ * peer p's mailbox (NVLink stores, then a system-scope release of a sequence flag), then waits (acquire, bounded spin) for
+ * rank p's record in its own mailbox and copies it out -- no host round trip, no NCCL launch latency.
+ *   create   allocates the mailbox (records of at most max_doubles doubles) and returns its 64-byte IPC handle
+ *   connect  handles [world][SEPAIHRD_EXCHANGE_HANDLE_BYTES] of all ranks (gathered by the caller through any channel,
+ *            e.g. torch.distributed.all_gather_object); rank r's own entry is ignored
+ *   all_gather  d_src [count] -> d_dst [world][count] on every rank (device pointers); all ranks must make the same
+ *            sequence of calls.  A peer that does not show up within timeout (default 10 s) raises the status flag
+ *            instead of hanging the GPU.
+ *   status   0 = fine; nonzero = a wait timed out (synchronises the ctx stream)                                          */
+#define SEPAIHRD_EXCHANGE_HANDLE_BYTES 64
+typedef struct sepaihrd_exchange sepaihrd_exchange;
+sepaihrd_rc sepaihrd_exchange_create(sepaihrd_ctx* ctx, int32_t world, int32_t rank, int64_t max_doubles,
+                                     sepaihrd_exchange** out, unsigned char* out_handle);
+sepaihrd_rc sepaihrd_exchange_connect(sepaihrd_exchange* ex, const unsigned char* handles);
+sepaihrd_rc sepaihrd_exchange_all_gather(sepaihrd_exchange* ex, const double* d_src, int64_t count, double* d_dst);
+sepaihrd_rc sepaihrd_exchange_status(sepaihrd_exchange* ex, int32_t* out_status);
+void sepaihrd_exchange_destroy(sepaihrd_exchange* ex);
 
 /* The aggregation passes (sepaihrd_posterior_predictive) keep their device work buffers in the ctx and reuse them across
  * calls; this frees them (they are also freed by sepaihrd_destroy). */

@@ -39,6 +39,27 @@ SIGNATURES = {
     "sepaihrd_swarm_evaluate": (C.c_int, [C.c_void_p, _dp, C.POINTER(C.c_int64), C.c_void_p]),
     "sepaihrd_swarm_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_void_p]),
     "sepaihrd_swarm_read": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
+    "sepaihrd_swarm_upload_seeds": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
+    "sepaihrd_swarm_init_async": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "sepaihrd_swarm_evaluate_async": (C.c_int, [C.c_void_p]),
+    "sepaihrd_swarm_record_device": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), _i32p]),
+    "sepaihrd_swarm_adopt_global_best": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int32]),
+    "sepaihrd_swarm_step_async": (C.c_int, [C.c_void_p, C.c_int32, C.c_double, C.c_double, C.c_double]),
+    "sepaihrd_swarm_read_trace": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32]),
+    "sepaihrd_swarm_read_global_best": (C.c_int, [C.c_void_p, _dp, C.c_void_p]),
+    "sepaihrd_mh_create": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "sepaihrd_mh_destroy": (None, [C.c_void_p]),
+    "sepaihrd_mh_begin": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]),
+    "sepaihrd_mh_iterate": (C.c_int, [C.c_void_p, C.c_int32]),
+    "sepaihrd_mh_iteration": (C.c_int32, [C.c_void_p]),
+    "sepaihrd_mh_logpost_device": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "sepaihrd_mh_note_gathered": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int32]),
+    "sepaihrd_mh_read": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
+    "sepaihrd_exchange_create": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.POINTER(C.c_void_p), C.c_void_p]),
+    "sepaihrd_exchange_connect": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "sepaihrd_exchange_all_gather": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "sepaihrd_exchange_status": (C.c_int, [C.c_void_p, _i32p]),
+    "sepaihrd_exchange_destroy": (None, [C.c_void_p]),
     "sepaihrd_release_scratch": (C.c_int, [C.c_void_p]),
     "sepaihrd_alloc_pinned": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
     "sepaihrd_free_pinned": (None, [C.c_void_p]),

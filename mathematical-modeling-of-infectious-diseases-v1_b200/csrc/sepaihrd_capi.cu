@@ -959,6 +959,7 @@ sepaihrd_rc fail_with(sepaihrd_rc rc, const char* msg) { return fail(rc, msg); }
 const double* lower_bounds(const sepaihrd_ctx* ctx) { return ctx->blob.data() + ctx->kp.o_lo; }
 const double* upper_bounds(const sepaihrd_ctx* ctx) { return ctx->blob.data() + ctx->kp.o_hi; }
 void count_launches(sepaihrd_ctx* ctx, int n) { ctx->launches += n; }
+int constraint_mode(const sepaihrd_ctx* ctx) { return ctx->constraint_mode; }
 std::unique_lock<std::recursive_mutex> lock(sepaihrd_ctx* ctx) { return std::unique_lock<std::recursive_mutex>(ctx->mu); }
 void* scratch(sepaihrd_ctx* ctx, int slot, size_t bytes) {
     if (slot < 0 || slot >= sepaihrd_ctx::N_SCRATCH) return nullptr;

@@ -16,6 +16,7 @@ sepaihrd_rc fail_with(sepaihrd_rc rc, const char* msg);
 const double* lower_bounds(const sepaihrd_ctx* ctx);   // host copies, [P], as given at creation
 const double* upper_bounds(const sepaihrd_ctx* ctx);
 void count_launches(sepaihrd_ctx* ctx, int n);
+int constraint_mode(const sepaihrd_ctx* ctx);         // 0 clamp, 1 reflect (sepaihrd_set_constraint_mode)
 // the ctx mutex (recursive): every entry point of another translation unit that touches the ctx holds it for its duration
 std::unique_lock<std::recursive_mutex> lock(sepaihrd_ctx* ctx);
 // Grow-only device work buffer `slot` (0..15) of at least `bytes`, owned by the ctx and reused across calls; nullptr when the

@@ -34,6 +34,7 @@
 #include <cuda_runtime.h>
 
 #include "sepaihrd_b200.h"
+#include "sepaihrd_constraints.cuh"
 
 namespace sepaihrd {
 
@@ -99,10 +100,6 @@ struct Ops<false> {
     static __device__ __forceinline__ double mad(double a, double b, double c) { return fma(a, b, c); }
 };
 
-// std::max(a, b) == (a < b) ? b : a   (NaN in b is ignored, NaN in a is returned)
-__device__ __forceinline__ double std_max(double a, double b) { return (a < b) ? b : a; }
-__device__ __forceinline__ double std_min(double a, double b) { return (b < a) ? b : a; }
-
 // ---- TMA bulk copy + mbarrier (PTX) ---------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -129,25 +126,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
         "r"(parity)
         : "memory");
-}
-
-// ---- constraints ------------------------------------------------------------------------------------
-// reflectBound, SEPAIHRDParameterManager.cpp:302-313
-__device__ __forceinline__ double reflect_bound(double value, double minb, double maxb) {
-    if (minb >= maxb) return minb;
-    const double width = maxb - minb;
-    double y = fmod(value - minb, 2.0 * width);
-    if (y < 0) y += 2.0 * width;
-    if (y <= width) return minb + y;
-    return maxb - (y - width);
-}
-// applyConstraints, .cpp:315-347
-__device__ __forceinline__ double constrain(double v, double lo, double hi, int mode) {
-    if (lo == lo) {   // has a bounds entry
-        if (lo > hi) { double t = lo; lo = hi; hi = t; }
-        return (mode == 0) ? std_min(std_max(v, lo), hi) : reflect_bound(v, lo, hi);
-    }
-    return (mode == 0) ? std_max(0.0, v) : fabs(v);
 }
 
 // ---- step-size controller powers (FAST) ---------------------------------------------------------------

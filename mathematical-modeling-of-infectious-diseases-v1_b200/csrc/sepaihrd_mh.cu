@@ -1,0 +1,469 @@
+// sepaihrd_mh.cu -- Metropolis-Hastings chains that LIVE ON THE DEVICE: chain states, their std::mt19937 generators, the
+// Robbins-Monro scales and the accept history never leave HBM; an iteration is three launches on the ctx stream
+// (propose -> the fused likelihood kernel -> accept) and needs no host work at all.
+//
+// Replaces, for chains scored by this evaluator, the per-iteration host work of the reference's sampler
+// (src/sir_age_structured/optimizers/MetropolisHastingsSampler.cpp), one instance per chain:
+//   generateProposal   :91-102    y = x + s L z, z ~ N(0, I) from std::normal_distribution over the chain's std::mt19937
+//   applyConstraints   src/model/parameters/SEPAIHRDParameterManager.cpp:302-347 (mirror reflection in MCMC mode)
+//   accept             :318-330   log-space test, the uniform drawn ONLY for downhill proposals
+//   adaptGlobalScale   :104-152   Robbins-Monro on the last <= 1000 accept decisions
+// Scope: the phase with a FIXED proposal kernel (t <= burn_in: the start kernel built from the proposal sigmas, or the
+// covariance handed over by phase 1); the Haario covariance adaptation after burn-in (:154-199) stays in the host sampler
+// (host/optimizers.cpp), and sepaihrd_mh_create refuses a run that would need it.
+//
+// Bit-compatibility with the host sampler (host/optimizers.cpp, itself pinned against a Python restatement of the reference):
+// chain c draws from std::mt19937(std::seed_seq{seed, c}) with c the GLOBAL chain index -- the device runs seed_seq::generate,
+// the MT19937 twist / tempering, libstdc++'s generate_canonical<double, 53> and its polar normal_distribution -- every FP64
+// operation is individually rounded in the host's order, and log / exp are csrc/det_math.h on both sides.  A device-resident
+// run therefore makes EXACTLY the host run's accept decisions and visits its states (tests/test_gpu_host.py).
+//
+// Mapping: one thread per chain (a few hundred to a few thousand chains per GPU: the sampler is latency-bound, ~30 us per
+// iteration against >= 550 us for the likelihood launch).  Generator states are word-major ([624][chains]), so the 32 chains of
+// a warp read word i as one coalesced line; tempered outputs are prefetched 112 at a time (state blocks twisted lazily, 16
+// words at a time, exactly in the reference order), which turns ~160 dependent loads per proposal into two batches.
+#include <cfloat>
+#include <cmath>
+#include <cstdint>
+#include <vector>
+
+#include "det_math.h"
+#include "sepaihrd_constraints.cuh"
+#include "sepaihrd_internal.h"
+
+struct sepaihrd_mh {
+    sepaihrd_ctx* ctx = nullptr;
+    int P = 0;
+    long long n_chains = 0, offset = 0, local = 0;
+    sepaihrd_mh_settings cfg{};
+    int t = 1;                                 // next iteration (1-based like the reference loop)
+    bool begun = false, diagonal = true;
+    char* d_arena = nullptr;
+    double *d_x = nullptr, *d_prop = nullptr, *d_lp = nullptr, *d_plp = nullptr, *d_log_scale = nullptr, *d_scale = nullptr;
+    double *d_best_lp = nullptr, *d_best_x = nullptr, *d_chol = nullptr, *d_lo = nullptr, *d_hi = nullptr, *d_init = nullptr;
+    double* d_trace = nullptr;                 // [trace_cap]: max over all chains' log-posteriors per iteration (sepaihrd_mh_note_gathered)
+    unsigned *d_mt = nullptr, *d_C = nullptr, *d_T = nullptr, *d_recent = nullptr, *d_status = nullptr;
+    int *d_recent_n = nullptr, *d_recent_sum = nullptr, *d_emergency = nullptr;
+    long long* d_accepted = nullptr;
+    unsigned char* d_accepts = nullptr;        // [iterations - 1][local] when record_accepts
+    int trace_cap = 0;
+};
+
+namespace {
+
+using sepaihrd_internal::fail_with;
+
+#define MH_TRY(expr)                                                                              \
+    do {                                                                                          \
+        cudaError_t e__ = (expr);                                                                 \
+        if (e__ != cudaSuccess) return fail_with(SEPAIHRD_ERR_CUDA, cudaGetErrorString(e__));     \
+    } while (0)
+
+constexpr int MT_N = 624, MT_M = 397;
+constexpr int MH_THREADS = 64;
+constexpr int RNG_BUF = 112;                   // tempered words fetched per batch (7 state blocks of 16)
+constexpr int RECENT_WORDS = 32;               // ring of the last 1000 accept decisions, one bit each
+
+// std::mt19937 whose 624-word state lives in global memory, word-major.  C = outputs consumed, T = state words twisted,
+// both counted from the seeding (they wrap at 2^32; only their difference and their residues mod 624 are used -- 2^32 is
+// NOT a multiple of 624, so a chain may draw at most 2^32 - 1 words: ~2.7e7 iterations of a 62-parameter chain).
+struct ChainRng {
+    unsigned* st;
+    long long stride;
+    unsigned C, T;
+    unsigned buf[RNG_BUF];
+    int have, at;
+    __device__ __forceinline__ unsigned& word(int i) { return st[(long long)i * stride]; }
+    __device__ void twist16(int k0) {
+        unsigned cur[17], far[16];
+#pragma unroll
+        for (int j = 0; j < 17; ++j) { const int k = k0 + j; cur[j] = word(k == MT_N ? 0 : k); }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { const int km = k0 + j + MT_M; far[j] = word(km >= MT_N ? km - MT_N : km); }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const unsigned y = (cur[j] & 0x80000000u) | (cur[j + 1] & 0x7fffffffu);
+            word(k0 + j) = far[j] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+        }
+    }
+    __device__ void fill(int want) {           // the buffer is exhausted: fetch outputs [C, C + want)
+        while ((unsigned)(T - C) < (unsigned)want) { twist16((int)(T % MT_N)); T += 16; }
+        const int i0 = (int)(C % MT_N);
+#pragma unroll 8
+        for (int i = 0; i < want; ++i) {
+            int k = i0 + i; if (k >= MT_N) k -= MT_N;
+            unsigned y = word(k);
+            y ^= (y >> 11);
+            y ^= (y << 7) & 0x9d2c5680u;
+            y ^= (y << 15) & 0xefc60000u;
+            y ^= (y >> 18);
+            buf[i] = y;
+        }
+        have = want; at = 0;
+    }
+    __device__ __forceinline__ unsigned next(int refill) {
+        if (at == have) fill(refill);
+        ++C;
+        return buf[at++];
+    }
+    // generate_canonical<double, 53>: (lo + hi 2^32) / 2^64, one rounding in the sum; 1.0 -> the largest double below 1
+    __device__ __forceinline__ double uniform01(int refill) {
+        const unsigned lo = next(refill), hi = next(refill);
+        const double sum = __dadd_rn((double)lo, __dmul_rn((double)hi, 4294967296.0));
+        const double r = __dmul_rn(sum, 1.0 / 18446744073709551616.0);
+        return (r >= 1.0) ? 0.99999999999999988898 : r;
+    }
+};
+
+// std::seed_seq{seed, chain}.generate over 624 words ([rand.util.seedseq]) = the state of std::mt19937 seeded from it;
+// the first output comes after a twist.  Local scratch (lane-interleaved, L1-resident), then one pass to the word-major state.
+__global__ void __launch_bounds__(MH_THREADS) mh_seed_kernel(long long local, long long offset, unsigned seed, unsigned* __restrict__ mt,
+                                                              unsigned* __restrict__ Cc, unsigned* __restrict__ Tt) {
+    const long long c = blockIdx.x * (long long)MH_THREADS + threadIdx.x;
+    if (c >= local) return;
+    const unsigned v[2] = {seed, (unsigned)(offset + c)};
+    constexpr int n = MT_N, s = 2, t = 11, p = (n - t) / 2, q = p + t, m = n;      // m = max(s + 1, n)
+    unsigned b[MT_N];
+    for (int i = 0; i < n; ++i) b[i] = 0x8b8b8b8bu;
+    for (int k = 0; k < m; ++k) {
+        const int kn = k % n, kp = (k + p) % n, kq = (k + q) % n, k1 = (k + n - 1) % n;
+        unsigned r1 = b[kn] ^ b[kp] ^ b[k1];
+        r1 = 1664525u * (r1 ^ (r1 >> 27));
+        const unsigned r2 = r1 + ((k == 0) ? (unsigned)s : (k <= s) ? (unsigned)kn + v[k - 1] : (unsigned)kn);
+        b[kp] += r1;
+        b[kq] += r2;
+        b[kn] = r2;
+    }
+    for (int k = m; k < m + n; ++k) {
+        const int kn = k % n, kp = (k + p) % n, kq = (k + q) % n, k1 = (k + n - 1) % n;
+        unsigned r3 = b[kn] + b[kp] + b[k1];
+        r3 = 1566083941u * (r3 ^ (r3 >> 27));
+        const unsigned r4 = r3 - (unsigned)kn;
+        b[kp] ^= r3;
+        b[kq] ^= r4;
+        b[kn] = r4;
+    }
+    // mersenne_twister_engine::seed(Sseq&): an all-zero state (upper bit of word 0, all of the others) becomes 2^31
+    bool zero = (b[0] & 0x80000000u) == 0u;
+    for (int i = 1; i < n && zero; ++i) zero = (b[i] == 0u);
+    if (zero) b[0] = 0x80000000u;
+    for (int i = 0; i < n; ++i) mt[(long long)i * local + c] = b[i];
+    Cc[c] = 0u; Tt[c] = 0u;
+}
+
+// every chain starts at `init` with the log-posterior of that point (evaluated once, d_plp[0]); safeValue like the host
+__global__ void mh_start_kernel(long long local, int P, const double* __restrict__ init, const double* __restrict__ lp0, double* __restrict__ x,
+                                double* __restrict__ lp, double* __restrict__ log_scale, double* __restrict__ scale, double* __restrict__ best_lp,
+                                double* __restrict__ best_x, unsigned* __restrict__ recent, int* __restrict__ recent_n, int* __restrict__ recent_sum,
+                                int* __restrict__ emergency, long long* __restrict__ accepted) {
+    const long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (c >= local) return;
+    double v = lp0[0];
+    if (isnan(v) || isinf(v)) v = -1e18;
+    for (int k = 0; k < P; ++k) { x[c * P + k] = init[k]; best_x[c * P + k] = init[k]; }
+    lp[c] = v; best_lp[c] = v;
+    log_scale[c] = 0.0; scale[c] = 1.0;
+    for (int w = 0; w < RECENT_WORDS; ++w) recent[(long long)w * local + c] = 0u;
+    recent_n[c] = 0; recent_sum[c] = 0; emergency[c] = 0; accepted[c] = 0;
+}
+
+// generateProposal + applyConstraints for every local chain
+__global__ void __launch_bounds__(MH_THREADS) mh_propose_kernel(long long local, int P, int diagonal, int mode, const double* __restrict__ chol,
+                                                                 const double* __restrict__ lo, const double* __restrict__ hi,
+                                                                 const double* __restrict__ x, const double* __restrict__ scale,
+                                                                 unsigned* __restrict__ mt, unsigned* __restrict__ Cc, unsigned* __restrict__ Tt,
+                                                                 double* __restrict__ prop) {
+    const long long c = blockIdx.x * (long long)MH_THREADS + threadIdx.x;
+    if (c >= local) return;
+    ChainRng g;
+    g.st = mt + c; g.stride = local; g.C = Cc[c]; g.T = Tt[c]; g.have = 0; g.at = 0;
+    double z[SEPAIHRD_MH_MAX_PARAMS];
+    // std::normal_distribution<double>(0, 1), a FRESH object per proposal (the reference declares it inside generateProposal):
+    // polar method, the second value of an accepted pair is returned by the next call
+    for (int i = 0; i < P; i += 2) {
+        double a, b, r2;
+        do {
+            a = __dsub_rn(__dmul_rn(2.0, g.uniform01(RNG_BUF)), 1.0);
+            b = __dsub_rn(__dmul_rn(2.0, g.uniform01(RNG_BUF)), 1.0);
+            r2 = __dadd_rn(__dmul_rn(a, a), __dmul_rn(b, b));
+        } while (r2 > 1.0 || r2 == 0.0);
+        const double mult = __dsqrt_rn(__ddiv_rn(__dmul_rn(-2.0, detm::log(r2)), r2));
+        z[i] = __dmul_rn(b, mult);                          // first call returns y * mult and saves x * mult
+        if (i + 1 < P) z[i + 1] = __dmul_rn(a, mult);
+    }
+    const double sc = scale[c];
+    const double* xc = x + c * P;
+    double* out = prop + c * P;
+    if (diagonal) {
+        for (int i = 0; i < P; ++i) {
+            const double step = __dmul_rn(chol[(long long)i * P + i], z[i]);
+            out[i] = sepaihrd::constrain(__dadd_rn(xc[i], __dmul_rn(sc, step)), lo[i], hi[i], mode);
+        }
+    } else {
+        // step = L z over the lower triangle, column by column like the host (the structural zeros add nothing)
+        double step[SEPAIHRD_MH_MAX_PARAMS];
+        for (int i = 0; i < P; ++i) step[i] = 0.0;
+        for (int j = 0; j < P; ++j) {
+            const double zj = z[j];
+            for (int i = j; i < P; ++i) step[i] = __dadd_rn(step[i], __dmul_rn(chol[(long long)j * P + i], zj));
+        }
+        for (int i = 0; i < P; ++i) out[i] = sepaihrd::constrain(__dadd_rn(xc[i], __dmul_rn(sc, step[i])), lo[i], hi[i], mode);
+    }
+    Cc[c] = g.C; Tt[c] = g.T;
+}
+
+// accept + adaptGlobalScale for every local chain; `step` is the reference's 1-based iteration index
+__global__ void __launch_bounds__(MH_THREADS) mh_accept_kernel(long long local, int P, int step, int adapt_scale, double target,
+                                                                const double* __restrict__ plp_in, const double* __restrict__ prop,
+                                                                double* __restrict__ x, double* __restrict__ lp, unsigned* __restrict__ mt,
+                                                                unsigned* __restrict__ Cc, unsigned* __restrict__ Tt, double* __restrict__ log_scale,
+                                                                double* __restrict__ scale, unsigned* __restrict__ recent, int* __restrict__ recent_n,
+                                                                int* __restrict__ recent_sum, int* __restrict__ emergency,
+                                                                long long* __restrict__ accepted, double* __restrict__ best_lp,
+                                                                double* __restrict__ best_x, unsigned char* __restrict__ accepts_row) {
+    const long long c = blockIdx.x * (long long)MH_THREADS + threadIdx.x;
+    if (c >= local) return;
+    double plp = plp_in[c];
+    if (isnan(plp) || isinf(plp)) plp = -1e18;                                  // safeEvaluate, .cpp:65-74
+    const double clp = lp[c];
+    const double log_ratio = __dsub_rn(plp, clp);
+    bool acc = false;
+    if (log_ratio >= 0.0) {
+        acc = true;
+    } else {
+        ChainRng g;
+        g.st = mt + c; g.stride = local; g.C = Cc[c]; g.T = Tt[c]; g.have = 0; g.at = 0;
+        const double u = g.uniform01(16);
+        if (detm::log(u) < log_ratio) acc = true;
+        Cc[c] = g.C; Tt[c] = g.T;
+    }
+    if (acc) {
+        for (int k = 0; k < P; ++k) x[c * P + k] = prop[c * P + k];
+        lp[c] = plp;
+        accepted[c] += 1;
+        if (plp > best_lp[c]) { best_lp[c] = plp; for (int k = 0; k < P; ++k) best_x[c * P + k] = prop[c * P + k]; }
+    }
+    if (accepts_row) accepts_row[c] = acc ? 1 : 0;
+    if (!adapt_scale) return;
+    // recent: the last <= 1000 decisions (the host pushes, then drops the oldest once there are more than 1000)
+    int n = recent_n[c], sum = recent_sum[c];
+    const int slot = n % 1000;
+    unsigned* wp = recent + (long long)(slot >> 5) * local + c;
+    unsigned w = *wp;
+    const unsigned bit = 1u << (slot & 31);
+    if (n >= 1000) sum -= (w & bit) ? 1 : 0;
+    w = acc ? (w | bit) : (w & ~bit);
+    *wp = w;
+    sum += acc ? 1 : 0;
+    n += 1;
+    recent_n[c] = n; recent_sum[c] = sum;
+    const int size = n < 1000 ? n : 1000;
+    const double rate = __ddiv_rn((double)sum, (double)size);
+    double ls = log_scale[c];
+    const double s1 = __dadd_rn((double)step, 1.0);
+    if (size >= 1000 && rate < 0.001) {
+        ls = __dsub_rn(ls, 0.7);
+        emergency[c] += 1;
+    } else if (rate < 0.02 && size >= 500) {
+        const double g5 = __ddiv_rn(5.0, __dsqrt_rn(s1));
+        const double gg = (0.3 < g5) ? 0.3 : g5;                                  // std::min(g5, 0.3)
+        ls = __dadd_rn(ls, __dmul_rn(gg, __dsub_rn(0.0, target)));
+    } else {
+        const double g1 = __ddiv_rn(1.0, __dsqrt_rn(s1));
+        const double gg = (0.1 < g1) ? 0.1 : g1;
+        ls = __dadd_rn(ls, __dmul_rn(gg, __dsub_rn(acc ? 1.0 : 0.0, target)));
+    }
+    if (scale[c] <= 0.011 && rate > 0.15 && rate < 0.30) ls = __dadd_rn(ls, 0.01);
+    {   // std::max(std::min(ls, 2.3), -6.9)
+        const double lo_c = (2.3 < ls) ? 2.3 : ls;
+        ls = (lo_c < -6.9) ? -6.9 : lo_c;
+    }
+    log_scale[c] = ls;
+    scale[c] = detm::exp(ls);
+}
+
+// trace[slot] = max over the gathered log-posteriors of ALL chains ([world][stride] blocks of counts[r] valid values each)
+__global__ void mh_trace_kernel(const double* __restrict__ all_lp, int world, long long stride, long long base, long long extra,
+                                double* __restrict__ trace, int slot) {
+    __shared__ double s[256];
+    double m = -INFINITY;
+    for (int r = 0; r < world; ++r) {
+        const long long cnt = base + (r < extra ? 1 : 0);
+        for (long long i = threadIdx.x; i < cnt; i += blockDim.x) { const double v = all_lp[r * stride + i]; if (v > m) m = v; }
+    }
+    s[threadIdx.x] = m;
+    __syncthreads();
+    for (int off = 128; off >= 1; off >>= 1) {
+        if (threadIdx.x < off && s[threadIdx.x + off] > s[threadIdx.x]) s[threadIdx.x] = s[threadIdx.x + off];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) trace[slot] = s[0];
+}
+
+}  // namespace
+
+extern "C" {
+
+sepaihrd_rc sepaihrd_mh_create(sepaihrd_ctx* ctx, int64_t n_chains, int64_t chain_offset, int64_t local_count,
+                               const sepaihrd_mh_settings* settings, sepaihrd_mh** out) {
+    if (!ctx || !out || !settings) return fail_with(SEPAIHRD_ERR_INVALID_ARGUMENT, "null argument");
+    if (n_chains <= 0 || chain_offset < 0 || local_count < 0 || chain_offset + local_count > n_chains)
+        return fail_with(SEPAIHRD_ERR_INVALID_ARGUMENT, "chain_offset/local_count outside the set of chains");
+    if (settings->iterations < 1) return fail_with(SEPAIHRD_ERR_INVALID_ARGUMENT, "iterations must be >= 1");
+    if (settings->iterations - 1 > settings->burn_in)
+        return fail_with(SEPAIHRD_ERR_UNSUPPORTED, "the device-resident sampler covers the fixed-kernel phase (iterations - 1 <= burn_in); the covariance "
+                                                   "adaptation after burn-in runs in the host sampler");
+    const sepaihrd_internal::Dims d = sepaihrd_internal::dims(ctx);
+    if (d.P > SEPAIHRD_MH_MAX_PARAMS) return fail_with(SEPAIHRD_ERR_UNSUPPORTED, "too many parameters for the device-resident sampler");
+    MH_TRY(cudaSetDevice(d.device));
+    auto* m = new sepaihrd_mh;
+    m->ctx = ctx; m->P = d.P; m->n_chains = n_chains; m->offset = chain_offset; m->local = local_count; m->cfg = *settings;
+    m->trace_cap = settings->iterations + 1;
+    const size_t L = (size_t)local_count, LP = L * (size_t)d.P;
+    size_t bytes = 0;
+    auto reserve = [&](size_t b) { const size_t at = bytes; bytes += (b + 255) & ~(size_t)255; return at; };
+    const size_t o_x = reserve(8 * LP), o_prop = reserve(8 * LP), o_lp = reserve(8 * L), o_plp = reserve(8 * (L + 1)), o_ls = reserve(8 * L),
+                 o_sc = reserve(8 * L), o_blp = reserve(8 * L), o_bx = reserve(8 * LP), o_chol = reserve(8 * (size_t)d.P * d.P),
+                 o_lo = reserve(8 * (size_t)d.P), o_hi = reserve(8 * (size_t)d.P), o_init = reserve(8 * (size_t)d.P),
+                 o_trace = reserve(8 * (size_t)m->trace_cap), o_mt = reserve(4 * L * MT_N), o_C = reserve(4 * L), o_T = reserve(4 * L),
+                 o_rec = reserve(4 * L * RECENT_WORDS), o_st = reserve(4 * (L + 1)), o_rn = reserve(4 * L), o_rs = reserve(4 * L),
+                 o_em = reserve(4 * L), o_acc = reserve(8 * L),
+                 o_accepts = reserve(settings->record_accepts ? L * (size_t)settings->iterations : 1);
+    cudaError_t e = cudaMalloc((void**)&m->d_arena, bytes);
+    if (e == cudaSuccess) {
+        char* D = m->d_arena;
+        m->d_x = (double*)(D + o_x); m->d_prop = (double*)(D + o_prop); m->d_lp = (double*)(D + o_lp); m->d_plp = (double*)(D + o_plp);
+        m->d_log_scale = (double*)(D + o_ls); m->d_scale = (double*)(D + o_sc); m->d_best_lp = (double*)(D + o_blp); m->d_best_x = (double*)(D + o_bx);
+        m->d_chol = (double*)(D + o_chol); m->d_lo = (double*)(D + o_lo); m->d_hi = (double*)(D + o_hi); m->d_init = (double*)(D + o_init);
+        m->d_trace = (double*)(D + o_trace); m->d_mt = (unsigned*)(D + o_mt); m->d_C = (unsigned*)(D + o_C); m->d_T = (unsigned*)(D + o_T);
+        m->d_recent = (unsigned*)(D + o_rec); m->d_status = (unsigned*)(D + o_st); m->d_recent_n = (int*)(D + o_rn); m->d_recent_sum = (int*)(D + o_rs);
+        m->d_emergency = (int*)(D + o_em); m->d_accepted = (long long*)(D + o_acc); m->d_accepts = (unsigned char*)(D + o_accepts);
+        e = cudaMemcpy(m->d_lo, sepaihrd_internal::lower_bounds(ctx), 8 * (size_t)d.P, cudaMemcpyHostToDevice);
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(m->d_hi, sepaihrd_internal::upper_bounds(ctx), 8 * (size_t)d.P, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        sepaihrd_mh_destroy(m);
+        return fail_with(e == cudaErrorMemoryAllocation ? SEPAIHRD_ERR_OUT_OF_MEMORY : SEPAIHRD_ERR_CUDA, cudaGetErrorString(e));
+    }
+    *out = m;
+    return SEPAIHRD_OK;
+}
+
+void sepaihrd_mh_destroy(sepaihrd_mh* m) {
+    if (!m) return;
+    if (m->d_arena) { cudaDeviceSynchronize(); cudaFree(m->d_arena); }
+    delete m;
+}
+
+sepaihrd_rc sepaihrd_mh_begin(sepaihrd_mh* m, uint32_t seed, const double* initial, const double* chol_lower) {
+    if (!m || !initial || !chol_lower) return fail_with(SEPAIHRD_ERR_INVALID_ARGUMENT, "null argument");
+    const auto ctx_lock = sepaihrd_internal::lock(m->ctx);
+    const sepaihrd_internal::Dims d = sepaihrd_internal::dims(m->ctx);
+    MH_TRY(cudaSetDevice(d.device));
+    cudaStream_t st = sepaihrd_internal::stream(m->ctx);
+    const int P = m->P;
+    m->diagonal = true;
+    for (int j = 0; j < P && m->diagonal; ++j)
+        for (int i = 0; i < P; ++i)
+            if (i != j && chol_lower[(size_t)j * P + i] != 0.0) { m->diagonal = false; break; }
+    MH_TRY(cudaStreamSynchronize(st));
+    MH_TRY(cudaMemcpyAsync(m->d_chol, chol_lower, 8 * (size_t)P * P, cudaMemcpyHostToDevice, st));
+    MH_TRY(cudaMemcpyAsync(m->d_init, initial, 8 * (size_t)P, cudaMemcpyHostToDevice, st));
+    MH_TRY(cudaStreamSynchronize(st));                      // the sources are the caller's pageable buffers
+    // log-posterior of the common start: ONE evaluation (like optimize(), host/optimizers.cpp), read by the start kernel
+    sepaihrd_rc rc = sepaihrd_eval_batch_device(m->ctx, m->d_init, 1, P, m->d_plp + m->local, m->d_status + m->local, nullptr);
+    if (rc != SEPAIHRD_OK) return rc;
+    if (m->local > 0) {
+        const unsigned blocks = (unsigned)((m->local + MH_THREADS - 1) / MH_THREADS);
+        mh_seed_kernel<<<blocks, MH_THREADS, 0, st>>>(m->local, m->offset, seed, m->d_mt, m->d_C, m->d_T);
+        MH_TRY(cudaGetLastError());
+        mh_start_kernel<<<blocks, MH_THREADS, 0, st>>>(m->local, P, m->d_init, m->d_plp + m->local, m->d_x, m->d_lp, m->d_log_scale, m->d_scale,
+                                                        m->d_best_lp, m->d_best_x, m->d_recent, m->d_recent_n, m->d_recent_sum, m->d_emergency,
+                                                        m->d_accepted);
+        MH_TRY(cudaGetLastError());
+        sepaihrd_internal::count_launches(m->ctx, 2);
+    }
+    m->t = 1;
+    m->begun = true;
+    return SEPAIHRD_OK;
+}
+
+sepaihrd_rc sepaihrd_mh_iterate(sepaihrd_mh* m, int32_t n_iterations) {
+    if (!m) return fail_with(SEPAIHRD_ERR_INVALID_ARGUMENT, "null argument");
+    if (!m->begun) return fail_with(SEPAIHRD_ERR_INVALID_ARGUMENT, "sepaihrd_mh_iterate before sepaihrd_mh_begin");
+    const auto ctx_lock = sepaihrd_internal::lock(m->ctx);
+    const sepaihrd_internal::Dims d = sepaihrd_internal::dims(m->ctx);
+    MH_TRY(cudaSetDevice(d.device));
+    cudaStream_t st = sepaihrd_internal::stream(m->ctx);
+    const int mode = sepaihrd_internal::constraint_mode(m->ctx);
+    for (int it = 0; it < n_iterations && m->t < m->cfg.iterations; ++it) {
+        if (m->local > 0) {
+            const unsigned blocks = (unsigned)((m->local + MH_THREADS - 1) / MH_THREADS);
+            mh_propose_kernel<<<blocks, MH_THREADS, 0, st>>>(m->local, m->P, m->diagonal ? 1 : 0, mode, m->d_chol, m->d_lo, m->d_hi, m->d_x, m->d_scale,
+                                                              m->d_mt, m->d_C, m->d_T, m->d_prop);
+            MH_TRY(cudaGetLastError());
+            sepaihrd_rc rc = sepaihrd_eval_batch_device(m->ctx, m->d_prop, m->local, m->P, m->d_plp, m->d_status, nullptr);
+            if (rc != SEPAIHRD_OK) return rc;
+            mh_accept_kernel<<<blocks, MH_THREADS, 0, st>>>(m->local, m->P, m->t, m->cfg.adapt_scale, m->cfg.target_acceptance_rate, m->d_plp, m->d_prop,
+                                                             m->d_x, m->d_lp, m->d_mt, m->d_C, m->d_T, m->d_log_scale, m->d_scale, m->d_recent,
+                                                             m->d_recent_n, m->d_recent_sum, m->d_emergency, m->d_accepted, m->d_best_lp, m->d_best_x,
+                                                             m->cfg.record_accepts ? m->d_accepts + (size_t)(m->t - 1) * m->local : nullptr);
+            MH_TRY(cudaGetLastError());
+            sepaihrd_internal::count_launches(m->ctx, 2);
+        }
+        m->t += 1;
+    }
+    return SEPAIHRD_OK;
+}
+
+int32_t sepaihrd_mh_iteration(const sepaihrd_mh* m) { return m ? m->t : 0; }
+
+sepaihrd_rc sepaihrd_mh_logpost_device(sepaihrd_mh* m, const double** d_logpost) {
+    if (!m || !d_logpost) return fail_with(SEPAIHRD_ERR_INVALID_ARGUMENT, "null argument");
+    *d_logpost = m->d_lp;
+    return SEPAIHRD_OK;
+}
+
+sepaihrd_rc sepaihrd_mh_note_gathered(sepaihrd_mh* m, const double* d_all_logpost, int32_t world, int64_t block_stride, int32_t trace_slot) {
+    if (!m || !d_all_logpost) return fail_with(SEPAIHRD_ERR_INVALID_ARGUMENT, "null argument");
+    if (world < 1 || trace_slot < 0 || trace_slot >= m->trace_cap) return fail_with(SEPAIHRD_ERR_INVALID_ARGUMENT, "bad world / trace slot");
+    const auto ctx_lock = sepaihrd_internal::lock(m->ctx);
+    const sepaihrd_internal::Dims d = sepaihrd_internal::dims(m->ctx);
+    MH_TRY(cudaSetDevice(d.device));
+    mh_trace_kernel<<<1, 256, 0, sepaihrd_internal::stream(m->ctx)>>>(d_all_logpost, world, block_stride, m->n_chains / world, m->n_chains % world,
+                                                                        m->d_trace, trace_slot);
+    MH_TRY(cudaGetLastError());
+    sepaihrd_internal::count_launches(m->ctx, 1);
+    return SEPAIHRD_OK;
+}
+
+sepaihrd_rc sepaihrd_mh_read(sepaihrd_mh* m, int32_t what, void* out) {
+    if (!m || !out) return fail_with(SEPAIHRD_ERR_INVALID_ARGUMENT, "null argument");
+    const auto ctx_lock = sepaihrd_internal::lock(m->ctx);
+    const sepaihrd_internal::Dims d = sepaihrd_internal::dims(m->ctx);
+    MH_TRY(cudaSetDevice(d.device));
+    cudaStream_t st = sepaihrd_internal::stream(m->ctx);
+    const void* src = nullptr;
+    size_t bytes = 0;
+    const size_t L = (size_t)m->local;
+    switch (what) {
+        case SEPAIHRD_MH_POSITIONS: src = m->d_x; bytes = 8 * L * m->P; break;
+        case SEPAIHRD_MH_LOGPOST: src = m->d_lp; bytes = 8 * L; break;
+        case SEPAIHRD_MH_SCALES: src = m->d_scale; bytes = 8 * L; break;
+        case SEPAIHRD_MH_ACCEPTED_COUNTS: src = m->d_accepted; bytes = 8 * L; break;
+        case SEPAIHRD_MH_BEST_LOGPOST: src = m->d_best_lp; bytes = 8 * L; break;
+        case SEPAIHRD_MH_BEST_POSITIONS: src = m->d_best_x; bytes = 8 * L * m->P; break;
+        case SEPAIHRD_MH_ACCEPT_MATRIX:
+            if (!m->cfg.record_accepts) return fail_with(SEPAIHRD_ERR_INVALID_ARGUMENT, "accept decisions were not recorded (settings.record_accepts)");
+            src = m->d_accepts; bytes = L * (size_t)(m->t - 1); break;
+        case SEPAIHRD_MH_TRACE: src = m->d_trace; bytes = 8 * (size_t)m->trace_cap; break;
+        case SEPAIHRD_MH_PROPOSALS: src = m->d_prop; bytes = 8 * L * m->P; break;
+        default: return fail_with(SEPAIHRD_ERR_INVALID_ARGUMENT, "bad sampler array selector");
+    }
+    if (bytes == 0) return SEPAIHRD_OK;
+    MH_TRY(cudaMemcpyAsync(out, src, bytes, cudaMemcpyDeviceToHost, st));
+    MH_TRY(cudaStreamSynchronize(st));
+    return SEPAIHRD_OK;
+}
+
+}  // extern "C"

@@ -40,6 +40,11 @@ struct sepaihrd_swarm {
     double* h_gbest = nullptr;
     bool evaluated_once = false;
     int blocks_tell = 0;
+    // asynchronous form: seeds of every iteration resident, global best and its trace on the device
+    unsigned* d_seed_sets = nullptr;    // [n_seed_sets][swarm_size], a separate allocation (sepaihrd_swarm_upload_seeds)
+    long long n_seed_sets = 0;
+    double* d_gbest_val = nullptr;      // [1]
+    double* d_trace = nullptr;          // [SEPAIHRD_SWARM_TRACE_CAPACITY]
     char* d_arena = nullptr;            // the one device allocation all d_* pointers point into
     char* h_arena = nullptr;            // the one pinned allocation all h_* pointers point into
 };
@@ -198,9 +203,11 @@ __global__ void __launch_bounds__(TELL_THREADS) swarm_tell_kernel(long long loca
         block_idx[blockIdx.x] = i;
     }
 }
+// best = [value, particle index + index_offset (-1: none), position[P]]: index_offset 0 gives the shard-local index of the
+// synchronous form, the shard's particle_offset the GLOBAL index of the record the ranks exchange
 __global__ void __launch_bounds__(TELL_THREADS) swarm_best_kernel(int blocks, int P, const double* __restrict__ block_val,
                                                                   const long long* __restrict__ block_idx, const double* __restrict__ pbest,
-                                                                  double* __restrict__ best) {
+                                                                  double* __restrict__ best, long long index_offset) {
     __shared__ double s_val[TELL_THREADS];
     __shared__ long long s_idx[TELL_THREADS];
     double v = 0.0;
@@ -217,10 +224,36 @@ __global__ void __launch_bounds__(TELL_THREADS) swarm_best_kernel(int blocks, in
         __syncthreads();
     }
     const long long bi = s_idx[0];
-    if (threadIdx.x == 0) { best[0] = (bi >= 0) ? s_val[0] : -INFINITY; best[1] = (double)bi; }
+    if (threadIdx.x == 0) { best[0] = (bi >= 0) ? s_val[0] : -INFINITY; best[1] = (bi >= 0) ? (double)(bi + index_offset) : -1.0; }
     if (bi >= 0)
         for (int k = threadIdx.x; k < P; k += TELL_THREADS) best[2 + k] = pbest[bi * P + k];
 }
+
+// Global best from one record per rank: the arg-max over the records (a NaN value never wins; ties go to the lowest particle
+// index, i.e. what a serial scan of the whole swarm finds first) replaces the resident global best when STRICTLY better
+// (ParticleSwarmOptimizer.cpp:149-156 / setGlobalBest of the host swarm); trace[slot] = the global best value after that.
+__global__ void swarm_adopt_kernel(const double* __restrict__ records, int n_records, long long stride, int P, double* __restrict__ gbest,
+                                   double* __restrict__ gbest_val, double* __restrict__ trace, int slot) {
+    __shared__ int s_owner;
+    if (threadIdx.x == 0) {
+        int owner = -1;
+        double best = -INFINITY, best_idx = 0.0;
+        for (int r = 0; r < n_records; ++r) {
+            const double v = records[r * stride], idx = records[r * stride + 1];
+            if (!(idx >= 0.0) || !(v == v)) continue;
+            if (owner < 0 || v > best || (v == best && idx < best_idx)) { owner = r; best = v; best_idx = idx; }
+        }
+        if (owner >= 0 && !(best > gbest_val[0])) owner = -1;
+        if (owner >= 0) gbest_val[0] = best;
+        if (trace) trace[slot] = gbest_val[0];
+        s_owner = owner;
+    }
+    __syncthreads();
+    const int owner = s_owner;
+    if (owner >= 0)
+        for (int k = threadIdx.x; k < P; k += blockDim.x) gbest[k] = records[owner * stride + 2 + k];
+}
+__global__ void swarm_reset_best_kernel(double* gbest_val) { gbest_val[0] = -INFINITY; }
 
 }  // namespace
 
@@ -254,7 +287,8 @@ sepaihrd_rc sepaihrd_swarm_create(sepaihrd_ctx* ctx, int64_t swarm_size, int64_t
                  o_seeds = reserve(dev_bytes, sizeof(unsigned) * (size_t)swarm_size),
                  o_bval = reserve(dev_bytes, sizeof(double) * (size_t)(s->blocks_tell + 1)),
                  o_bidx = reserve(dev_bytes, sizeof(long long) * (size_t)(s->blocks_tell + 1)),
-                 o_best = reserve(dev_bytes, sizeof(double) * ((size_t)d.P + 2));
+                 o_best = reserve(dev_bytes, sizeof(double) * ((size_t)d.P + 2)),
+                 o_gval = reserve(dev_bytes, sizeof(double)), o_trace = reserve(dev_bytes, sizeof(double) * SEPAIHRD_SWARM_TRACE_CAPACITY);
     const size_t h_best = reserve(host_bytes, sizeof(double) * ((size_t)d.P + 2)), h_seeds = reserve(host_bytes, sizeof(unsigned) * (size_t)swarm_size),
                  h_gbest = reserve(host_bytes, sizeof(double) * (size_t)d.P);
     e = cudaMalloc((void**)&s->d_arena, dev_bytes);
@@ -265,7 +299,7 @@ sepaihrd_rc sepaihrd_swarm_create(sepaihrd_ctx* ctx, int64_t swarm_size, int64_t
         s->d_pbest_val = (double*)(D + o_pval); s->d_fit = (double*)(D + o_fit); s->d_status = (unsigned*)(D + o_status);
         s->d_lb = (double*)(D + o_lb); s->d_ub = (double*)(D + o_ub); s->d_gbest = (double*)(D + o_gbest); s->d_init = (double*)(D + o_init);
         s->d_seeds = (unsigned*)(D + o_seeds); s->d_block_val = (double*)(D + o_bval); s->d_block_idx = (long long*)(D + o_bidx);
-        s->d_best = (double*)(D + o_best);
+        s->d_best = (double*)(D + o_best); s->d_gbest_val = (double*)(D + o_gval); s->d_trace = (double*)(D + o_trace);
         s->h_best = (double*)(H + h_best); s->h_seeds = (unsigned*)(H + h_seeds); s->h_gbest = (double*)(H + h_gbest);
     }
     if (e == cudaSuccess) e = cudaMemcpy(s->d_lb, lo, sizeof(double) * d.P, cudaMemcpyHostToDevice);
@@ -280,7 +314,8 @@ sepaihrd_rc sepaihrd_swarm_create(sepaihrd_ctx* ctx, int64_t swarm_size, int64_t
 
 void sepaihrd_swarm_destroy(sepaihrd_swarm* s) {
     if (!s) return;
-    if (s->d_arena) cudaFree(s->d_arena);
+    if (s->d_arena) { cudaDeviceSynchronize(); cudaFree(s->d_arena); }
+    if (s->d_seed_sets) cudaFree(s->d_seed_sets);
     if (s->h_arena) cudaFreeHost(s->h_arena);
     delete s;
 }
@@ -331,7 +366,7 @@ sepaihrd_rc sepaihrd_swarm_evaluate(sepaihrd_swarm* s, double* out_best_value, i
     swarm_tell_kernel<<<s->blocks_tell, TELL_THREADS, 0, st>>>(s->local, s->P, s->evaluated_once ? 0 : 1, s->d_fit, s->d_pos, s->d_pbest,
                                                               s->d_pbest_val, s->d_block_val, s->d_block_idx);
     SW_TRY(cudaGetLastError());
-    swarm_best_kernel<<<1, TELL_THREADS, 0, st>>>(s->blocks_tell, s->P, s->d_block_val, s->d_block_idx, s->d_pbest, s->d_best);
+    swarm_best_kernel<<<1, TELL_THREADS, 0, st>>>(s->blocks_tell, s->P, s->d_block_val, s->d_block_idx, s->d_pbest, s->d_best, 0);
     SW_TRY(cudaGetLastError());
     sepaihrd_internal::count_launches(s->ctx, 2);
     s->evaluated_once = true;
@@ -385,6 +420,130 @@ sepaihrd_rc sepaihrd_swarm_read(sepaihrd_swarm* s, int32_t what, double* out) {
     }
     if (count == 0) return SEPAIHRD_OK;
     SW_TRY(cudaMemcpyAsync(out, src, sizeof(double) * count, cudaMemcpyDeviceToHost, st));
+    SW_TRY(cudaStreamSynchronize(st));
+    return SEPAIHRD_OK;
+}
+
+// ---- asynchronous form: nothing below synchronises or copies per iteration -------------------------------------------------
+sepaihrd_rc sepaihrd_swarm_upload_seeds(sepaihrd_swarm* s, const uint32_t* seeds, int64_t n_sets) {
+    if (!s || !seeds || n_sets < 1) return fail_with(SEPAIHRD_ERR_INVALID_ARGUMENT, "null argument / no seed sets");
+    const auto ctx_lock = sepaihrd_internal::lock(s->ctx);
+    const sepaihrd_internal::Dims d = sepaihrd_internal::dims(s->ctx);
+    SW_TRY(cudaSetDevice(d.device));
+    cudaStream_t st = sepaihrd_internal::stream(s->ctx);
+    if (s->d_seed_sets) { SW_TRY(cudaDeviceSynchronize()); cudaFree(s->d_seed_sets); s->d_seed_sets = nullptr; s->n_seed_sets = 0; }
+    const size_t bytes = sizeof(unsigned) * (size_t)n_sets * (size_t)s->swarm_size;
+    SW_TRY(cudaMalloc((void**)&s->d_seed_sets, bytes));
+    SW_TRY(cudaMemcpyAsync(s->d_seed_sets, seeds, bytes, cudaMemcpyHostToDevice, st));
+    SW_TRY(cudaStreamSynchronize(st));                       // the source is the caller's buffer
+    s->n_seed_sets = n_sets;
+    return SEPAIHRD_OK;
+}
+
+sepaihrd_rc sepaihrd_swarm_init_async(sepaihrd_swarm* s, const double* initial) {
+    if (!s) return fail_with(SEPAIHRD_ERR_INVALID_ARGUMENT, "null argument");
+    if (s->n_seed_sets < 1) return fail_with(SEPAIHRD_ERR_INVALID_ARGUMENT, "sepaihrd_swarm_init_async before sepaihrd_swarm_upload_seeds");
+    const auto ctx_lock = sepaihrd_internal::lock(s->ctx);
+    const sepaihrd_internal::Dims d = sepaihrd_internal::dims(s->ctx);
+    SW_TRY(cudaSetDevice(d.device));
+    cudaStream_t st = sepaihrd_internal::stream(s->ctx);
+    if (initial) {
+        SW_TRY(cudaStreamSynchronize(st));                   // pinned staging reused
+        for (int k = 0; k < s->P; ++k) s->h_gbest[k] = initial[k];
+        SW_TRY(cudaMemcpyAsync(s->d_init, s->h_gbest, sizeof(double) * s->P, cudaMemcpyHostToDevice, st));
+    }
+    s->evaluated_once = false;
+    swarm_reset_best_kernel<<<1, 1, 0, st>>>(s->d_gbest_val);
+    SW_TRY(cudaGetLastError());
+    if (s->local > 0) {
+        const unsigned blocks = (unsigned)((s->local + RNG_THREADS - 1) / RNG_THREADS);
+        swarm_init_kernel<<<blocks, RNG_THREADS, 0, st>>>(s->local, s->offset, s->P, s->d_seed_sets, s->d_lb, s->d_ub,
+                                                                 initial ? s->d_init : nullptr, s->d_pos, s->d_vel);
+        SW_TRY(cudaGetLastError());
+    }
+    sepaihrd_internal::count_launches(s->ctx, 2);
+    return SEPAIHRD_OK;
+}
+
+sepaihrd_rc sepaihrd_swarm_evaluate_async(sepaihrd_swarm* s) {
+    if (!s) return fail_with(SEPAIHRD_ERR_INVALID_ARGUMENT, "null argument");
+    const auto ctx_lock = sepaihrd_internal::lock(s->ctx);
+    const sepaihrd_internal::Dims d = sepaihrd_internal::dims(s->ctx);
+    SW_TRY(cudaSetDevice(d.device));
+    cudaStream_t st = sepaihrd_internal::stream(s->ctx);
+    if (s->local > 0) {
+        sepaihrd_rc rc = sepaihrd_eval_batch_device(s->ctx, s->d_pos, s->local, s->P, s->d_fit, s->d_status, nullptr);
+        if (rc != SEPAIHRD_OK) return rc;
+        swarm_tell_kernel<<<s->blocks_tell, TELL_THREADS, 0, st>>>(s->local, s->P, s->evaluated_once ? 0 : 1, s->d_fit, s->d_pos, s->d_pbest,
+                                                                  s->d_pbest_val, s->d_block_val, s->d_block_idx);
+        SW_TRY(cudaGetLastError());
+    }
+    // an empty shard still publishes a record: (-inf, -1)
+    swarm_best_kernel<<<1, TELL_THREADS, 0, st>>>(s->blocks_tell, s->P, s->d_block_val, s->d_block_idx, s->d_pbest, s->d_best, s->offset);
+    SW_TRY(cudaGetLastError());
+    sepaihrd_internal::count_launches(s->ctx, 2);
+    s->evaluated_once = true;
+    return SEPAIHRD_OK;
+}
+
+sepaihrd_rc sepaihrd_swarm_record_device(sepaihrd_swarm* s, const double** d_record, int32_t* record_doubles) {
+    if (!s || !d_record) return fail_with(SEPAIHRD_ERR_INVALID_ARGUMENT, "null argument");
+    *d_record = s->d_best;
+    if (record_doubles) *record_doubles = s->P + 2;
+    return SEPAIHRD_OK;
+}
+
+sepaihrd_rc sepaihrd_swarm_adopt_global_best(sepaihrd_swarm* s, const double* d_records, int32_t n_records, int64_t record_stride,
+                                             int32_t trace_slot) {
+    if (!s || !d_records || n_records < 1 || record_stride < s->P + 2) return fail_with(SEPAIHRD_ERR_INVALID_ARGUMENT, "bad records");
+    if (trace_slot >= SEPAIHRD_SWARM_TRACE_CAPACITY) return fail_with(SEPAIHRD_ERR_INVALID_ARGUMENT, "trace slot beyond SEPAIHRD_SWARM_TRACE_CAPACITY");
+    const auto ctx_lock = sepaihrd_internal::lock(s->ctx);
+    const sepaihrd_internal::Dims d = sepaihrd_internal::dims(s->ctx);
+    SW_TRY(cudaSetDevice(d.device));
+    swarm_adopt_kernel<<<1, 64, 0, sepaihrd_internal::stream(s->ctx)>>>(d_records, n_records, record_stride, s->P, s->d_gbest, s->d_gbest_val,
+                                                                          trace_slot >= 0 ? s->d_trace : nullptr, trace_slot);
+    SW_TRY(cudaGetLastError());
+    sepaihrd_internal::count_launches(s->ctx, 1);
+    return SEPAIHRD_OK;
+}
+
+sepaihrd_rc sepaihrd_swarm_step_async(sepaihrd_swarm* s, int32_t iteration, double omega, double c1, double c2) {
+    if (!s) return fail_with(SEPAIHRD_ERR_INVALID_ARGUMENT, "null argument");
+    if (!s->evaluated_once) return fail_with(SEPAIHRD_ERR_INVALID_ARGUMENT, "sepaihrd_swarm_step_async before the first evaluation");
+    if (iteration < 0 || iteration + 1 >= s->n_seed_sets) return fail_with(SEPAIHRD_ERR_INVALID_ARGUMENT, "no seed set uploaded for this iteration");
+    const auto ctx_lock = sepaihrd_internal::lock(s->ctx);
+    const sepaihrd_internal::Dims d = sepaihrd_internal::dims(s->ctx);
+    SW_TRY(cudaSetDevice(d.device));
+    if (s->local > 0) {
+        const unsigned blocks = (unsigned)((s->local + RNG_THREADS - 1) / RNG_THREADS);
+        swarm_step_kernel<<<blocks, RNG_THREADS, 0, sepaihrd_internal::stream(s->ctx)>>>(
+            s->local, s->offset, s->P, s->d_seed_sets + (size_t)(iteration + 1) * (size_t)s->swarm_size, s->d_lb, s->d_ub, s->d_gbest, s->d_pbest,
+            omega, c1, c2, s->d_pos, s->d_vel);
+        SW_TRY(cudaGetLastError());
+        sepaihrd_internal::count_launches(s->ctx, 1);
+    }
+    return SEPAIHRD_OK;
+}
+
+sepaihrd_rc sepaihrd_swarm_read_trace(sepaihrd_swarm* s, double* out, int32_t n) {
+    if (!s || !out || n < 0 || n > SEPAIHRD_SWARM_TRACE_CAPACITY) return fail_with(SEPAIHRD_ERR_INVALID_ARGUMENT, "bad trace request");
+    const auto ctx_lock = sepaihrd_internal::lock(s->ctx);
+    const sepaihrd_internal::Dims d = sepaihrd_internal::dims(s->ctx);
+    SW_TRY(cudaSetDevice(d.device));
+    cudaStream_t st = sepaihrd_internal::stream(s->ctx);
+    if (n > 0) SW_TRY(cudaMemcpyAsync(out, s->d_trace, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    SW_TRY(cudaStreamSynchronize(st));
+    return SEPAIHRD_OK;
+}
+
+sepaihrd_rc sepaihrd_swarm_read_global_best(sepaihrd_swarm* s, double* out_value, double* out_position) {
+    if (!s) return fail_with(SEPAIHRD_ERR_INVALID_ARGUMENT, "null argument");
+    const auto ctx_lock = sepaihrd_internal::lock(s->ctx);
+    const sepaihrd_internal::Dims d = sepaihrd_internal::dims(s->ctx);
+    SW_TRY(cudaSetDevice(d.device));
+    cudaStream_t st = sepaihrd_internal::stream(s->ctx);
+    if (out_value) SW_TRY(cudaMemcpyAsync(out_value, s->d_gbest_val, sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (out_position) SW_TRY(cudaMemcpyAsync(out_position, s->d_gbest, sizeof(double) * (size_t)s->P, cudaMemcpyDeviceToHost, st));
     SW_TRY(cudaStreamSynchronize(st));
     return SEPAIHRD_OK;
 }

@@ -1,5 +1,6 @@
 // host_capi.cpp -- extern "C" wrappers over the C++ host layer.  See host_capi.h.
 #include "host_capi.h"
+#include "../csrc/det_math.h"
 
 #include <cmath>
 #include <omp.h>
@@ -249,6 +250,14 @@ int32_t sepaihrd_host_mh_best(const sepaihrd_host_mh* mh, double* x, double* val
         const OptimizationResult r = mh->s.result();
         if (x) std::copy(r.bestParameters.data(), r.bestParameters.data() + r.bestParameters.size(), x);
         if (value) *value = r.bestObjectiveValue;
+    });
+}
+double sepaihrd_host_det_log(double x) { return detm::log(x); }
+double sepaihrd_host_det_exp(double x) { return detm::exp(x); }
+int32_t sepaihrd_host_mh_shared_cholesky(const sepaihrd_host_mh* mh, double* out) {
+    return guarded([&] {
+        const MatrixXd& L = mh->s.sharedCholesky();
+        std::copy(L.data(), L.data() + L.rows() * L.cols(), out);
     });
 }
 void sepaihrd_host_mh_destroy(sepaihrd_host_mh* mh) { delete mh; }

@@ -59,6 +59,12 @@ int32_t sepaihrd_host_mh_accept(sepaihrd_host_mh* mh, const double* proposed_log
 int32_t sepaihrd_host_mh_state(const sepaihrd_host_mh* mh, double* out_x /* [n][P] */, double* out_logpost /* [n] */,
                                double* out_scale /* [n] */, int64_t* out_accepted /* [n] */);
 int32_t sepaihrd_host_mh_best(const sepaihrd_host_mh* mh, double* out_x /* [P] */, double* out_value);
+/* csrc/det_math.h on the host: the log / exp both Metropolis-Hastings samplers (host and device-resident) use */
+double sepaihrd_host_det_log(double x);
+double sepaihrd_host_det_exp(double x);
+/* lower Cholesky factor [P*P] column-major of the start kernel all chains share until they adapt (after begin): what a
+ * device-resident run of the same chains (sepaihrd_mh_begin) has to be given to reproduce them */
+int32_t sepaihrd_host_mh_shared_cholesky(const sepaihrd_host_mh* mh, double* out_chol);
 void    sepaihrd_host_mh_destroy(sepaihrd_host_mh* mh);
 
 /* ---- particle swarm (ParticleSwarmOptimization) ----------------------------------------------------------------- *

@@ -1,5 +1,6 @@
 // optimizers.cpp -- batched calibrators over IObjectiveFunction::calculateBatch.  See optimizers.hpp.
 #include "optimizers.hpp"
+#include "../csrc/det_math.h"      // log / exp with the same bits on the host and on the device (see there)
 
 #include <algorithm>
 #include <cmath>
@@ -23,6 +24,27 @@ std::vector<double> evaluate_rows(IObjectiveFunction& f, const std::vector<doubl
     for (double& v : out) v = MetropolisHastingsSampler::safeValue(v);
     return out;
 }
+
+// std::normal_distribution<double>(0, 1) as libstdc++ draws it (Marsaglia's polar method over generate_canonical<double, 53>;
+// the second value of a pair is kept for the next call), with det_math's logarithm in place of libm's and every product
+// rounded on its own: csrc/sepaihrd_mh.cu draws the same numbers from the same generator state on the device.
+struct PolarNormal {
+    bool has_saved = false;
+    double saved = 0.0;
+    double operator()(std::mt19937& gen) {
+        if (has_saved) { has_saved = false; return saved; }
+        double x, y, r2;
+        do {
+            x = 2.0 * std::generate_canonical<double, 53>(gen) - 1.0;
+            y = 2.0 * std::generate_canonical<double, 53>(gen) - 1.0;
+            r2 = detm::opaque(x * x) + detm::opaque(y * y);
+        } while (r2 > 1.0 || r2 == 0.0);
+        const double mult = std::sqrt(-2.0 * detm::log(r2) / r2);
+        saved = x * mult;
+        has_saved = true;
+        return y * mult;
+    }
+};
 
 MatrixXd outer(const VectorXd& d) {
     const auto n = d.size();
@@ -165,7 +187,7 @@ void MetropolisHastingsSampler::adaptGlobalScale(Chain& c, bool accepted, int st
     }
     if (c.global_scale <= 0.011 && rate > 0.15 && rate < 0.30) c.log_scale += 0.01;
     c.log_scale = std::max(std::min(c.log_scale, 2.3), -6.9);
-    c.global_scale = std::exp(c.log_scale);
+    c.global_scale = detm::exp(c.log_scale);
 }
 
 void MetropolisHastingsSampler::propose(IParameterManager& pm, double* out) {
@@ -186,7 +208,7 @@ void MetropolisHastingsSampler::propose(IParameterManager& pm, double* out) {
         }
         // 2. proposal  Y = X + scale * L z,  z ~ N(0, I)   (generateProposal, .cpp:91-102)
         VectorXd z(P);
-        std::normal_distribution<double> dist(0.0, 1.0);
+        PolarNormal dist;                                   // a fresh distribution per proposal, like the reference's local object
         for (std::ptrdiff_t i = 0; i < P; ++i) z(i) = dist(c.gen);
         // L is a lower Cholesky factor (diagonal for the start kernel): the structural zeros are skipped, which leaves every
         // sum unchanged (they would add +-0)
@@ -224,7 +246,7 @@ void MetropolisHastingsSampler::accept(const double* proposed_logpost, uint8_t* 
             acc = true;
         } else {
             std::uniform_real_distribution<double> u(0.0, 1.0);      // drawn ONLY for downhill proposals (.cpp:323-329)
-            if (std::log(u(c.gen)) < log_ratio) acc = true;
+            if (detm::log(u(c.gen)) < log_ratio) acc = true;
         }
         double* x = cur_x_.data() + static_cast<std::ptrdiff_t>(ci) * P;
         if (acc) {

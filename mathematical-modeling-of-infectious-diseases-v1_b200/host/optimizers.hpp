@@ -58,6 +58,7 @@ public:
     int numParams() const { return n_params_; }
     const double* currentPositions() const { return cur_x_.data(); }       // [n_chains][P]
     const double* currentLogPost() const { return cur_lp_.data(); }        // [n_chains]
+    const MatrixXd& sharedCholesky() const { return shared_chol_; }         // lower factor of the start kernel (after begin)
     double globalScale(int chain) const { return chains_[static_cast<size_t>(chain)].global_scale; }
     long acceptedCount(int chain) const { return chains_[static_cast<size_t>(chain)].accepted; }
     OptimizationResult result() const;

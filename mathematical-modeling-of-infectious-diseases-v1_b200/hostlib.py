@@ -44,6 +44,9 @@ SIGNATURES = {
     "sepaihrd_host_mh_accept": (C.c_int32, [_vp, _vp, _vp]),
     "sepaihrd_host_mh_state": (C.c_int32, [_vp, _vp, _vp, _vp, _vp]),
     "sepaihrd_host_mh_best": (C.c_int32, [_vp, _vp, _dp]),
+    "sepaihrd_host_mh_shared_cholesky": (C.c_int32, [_vp, _vp]),
+    "sepaihrd_host_det_log": (C.c_double, [C.c_double]),
+    "sepaihrd_host_det_exp": (C.c_double, [C.c_double]),
     "sepaihrd_host_mh_destroy": (None, [_vp]),
     "sepaihrd_host_pso_create": (C.c_int32, [_vp, C.c_int32, _keys, _vp, _vpp]),
     "sepaihrd_host_pso_begin": (C.c_int32, [_vp, _vp]),
@@ -216,6 +219,12 @@ class MultiChainMH:
         x = np.empty(self.pm.n); v = C.c_double()
         check(self.L.sepaihrd_host_mh_best(self._h, x.ctypes.data, C.byref(v)))
         return x, v.value
+
+    def shared_cholesky(self) -> np.ndarray:
+        """Lower Cholesky factor of the start kernel (after begin()), as the sampler factorised it."""
+        out = np.empty((self.pm.n, self.pm.n), order="F")
+        check(self.L.sepaihrd_host_mh_shared_cholesky(self._h, out.ctypes.data))
+        return out
 
     def __del__(self):
         if getattr(self, "_h", None):

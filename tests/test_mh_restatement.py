@@ -2,7 +2,9 @@
 of src/sir_age_structured/optimizers/MetropolisHastingsSampler.cpp:201-412 -- proposal x + s L z, mirror reflection, log-space
 accept with the uniform drawn only for downhill proposals, Robbins-Monro scale, rank-1 covariance updates, periodic full
 recomputation + Cholesky -- over Python versions of libstdc++'s seed_seq, mt19937, generate_canonical and the polar
-normal_distribution (a fresh distribution object per proposal, as the reference constructs it).  Proposals, accept decisions,
+normal_distribution (a fresh distribution object per proposal, as the reference constructs it).  The three libm calls of the
+algorithm (log in the polar method and in the accept test, exp in the scale) go through csrc/det_math.h on the host AND on the
+device (the device-resident sampler must reproduce the host's bits), restated here in tests/_det_math.py.  Proposals, accept decisions,
 chain states and scales must agree BIT FOR BIT for every chain and iteration, through burn-in and through the adaptive phase.
 
 "Seeded" is this build's extension (the reference seeds from std::random_device): chain c draws from
@@ -12,6 +14,7 @@ import math
 import numpy as np
 import pytest
 
+from _det_math import det_exp, det_log
 from test_nuts import StdNormal
 from test_pso_variants import StdMt19937
 
@@ -140,7 +143,7 @@ class PyChain:
         P = self.P
         if t > self.st["burn_in"]:
             self.adapt_covariance(t)
-        nrm = StdNormal()                                        # a fresh distribution per proposal (.cpp:94)
+        nrm = StdNormal(det_log)                                        # a fresh distribution per proposal (.cpp:94)
         z = [nrm(self.gen) for _ in range(P)]
         step = [0.0] * P
         for j in range(P):
@@ -155,7 +158,7 @@ class PyChain:
         if math.isnan(plp) or math.isinf(plp):
             plp = -1e18
         ratio = plp - self.lp
-        acc = True if ratio >= 0.0 else (math.log(self.gen.uniform()) < ratio)
+        acc = True if ratio >= 0.0 else (det_log(self.gen.uniform()) < ratio)
         if acc:
             self.x, self.lp = list(self.prop), plp
             self.accepted += 1
@@ -174,7 +177,7 @@ class PyChain:
         if self.scale <= 0.011 and 0.15 < rate < 0.30:
             self.log_scale += 0.01
         self.log_scale = max(min(self.log_scale, 2.3), -6.9)
-        self.scale = math.exp(self.log_scale)
+        self.scale = det_exp(self.log_scale)
         self.history.append(list(self.x))
         return acc
 
@@ -200,7 +203,7 @@ def test_seed_seq_and_engine_match_libstdcxx(host):
     y = mh.propose()
     for c in range(2):
         g = SeedSeqMt19937([42, c])
-        nrm = StdNormal()
+        nrm = StdNormal(det_log)
         z = [nrm(g) for _ in range(P)]
         L = [math.sqrt(sig[i] * sig[i] * ((2.38 * 2.38) / P) + 1e-6) for i in range(P)]
         want = [reflect(0.0 + 1.0 * (L[i] * z[i]), -1e6, 1e6) for i in range(P)]      # reflectBound rounds through fmod even inside the bounds

@@ -25,8 +25,9 @@ def host(pkg, cuda_lib):
 class StdNormal:
     """std::normal_distribution<double>(0, 1) of libstdc++: polar method, the second value of a pair is kept for the next call."""
 
-    def __init__(self):
+    def __init__(self, log=math.log):
         self.saved = None
+        self.log = log            # the Metropolis-Hastings sampler draws with csrc/det_math.h's logarithm (tests/_det_math.py)
 
     def __call__(self, g: StdMt19937) -> float:
         if self.saved is not None:
@@ -38,7 +39,7 @@ class StdNormal:
             r2 = x * x + y * y
             if not (r2 > 1.0 or r2 == 0.0):
                 break
-        mult = math.sqrt(-2.0 * math.log(r2) / r2)
+        mult = math.sqrt(-2.0 * self.log(r2) / r2)
         self.saved = x * mult
         return y * mult
 
