@@ -43,11 +43,33 @@ B_PER_GPU = 1 << 20
 DISTINCT = 1 << 20              # every set of the batch is its own draw
 FLOP_PER_ATTEMPT = 3750.0      # 6 RHS + stage/solution/error combinations + error norm, n = 4
 FLOP_PER_SET_FIXED = 22000.0   # 3672 likelihood terms * ~6
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch at B = 2^20 (ncu --set full, profiles/r01_v12_ncu_full_summary.txt):
-# 527.3 MB + 17.5 MB, i.e. the algorithmic 532.7 MB (62 doubles in, 12 bytes out per set) -- no re-reads.
-NCU_DRAM_BYTES_PER_LAUNCH_1M = 527.267328e6 + 17.500160e6
-NCU_FP64_PIPE_PCT = 61.52        # sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active, same capture
-NCU_ISSUE_ACTIVE_PCT = 51.78     # smsp__issue_active.avg.pct_of_peak_sustained_active
+NCU_CAPTURE_FILE = os.path.join(ROOT, "profiles", "current_ncu_capture.json")
+KERNEL_SOURCES = ("sepaihrd_kernels.cuh", "sepaihrd_constraints.cuh")
+
+
+def kernel_source_hash() -> str:
+    """sha256 over the kernel sources: ties a committed ncu capture to the build it was taken from."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in KERNEL_SOURCES:
+        with open(os.path.join(entry.CSRC, f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
+def ncu_capture(batch: int):
+    """The numbers of the committed `ncu --set full` capture of the headline kernel (profiles/current_ncu_capture.json, written
+    by tools/ncu_summary.py --json): DRAM traffic per launch, FP64-pipe utilisation, issue efficiency.  They are NOT measured by
+    this run; `stale` says whether the kernel sources have changed since the capture."""
+    try:
+        with open(NCU_CAPTURE_FILE) as f:
+            c = json.load(f)
+    except Exception:
+        return None
+    c = dict(c)
+    c["stale"] = c.get("kernel_source_hash") != kernel_source_hash()
+    c["same_batch"] = int(c.get("sets_per_launch", -1)) == int(batch)
+    return c
 
 
 def workload_config(n_gpus: int, batch: int) -> dict:
@@ -130,11 +152,11 @@ def cpu_baseline(oracle, params, target_seconds: float = 12.0):
     rate = len(probe) / (time.perf_counter() - t0)
     m = int(min(len(params), max(1024, rate * target_seconds)))
     t0 = time.perf_counter()
-    ll, _, _, used = oracle.eval_batch(params[:m], nthreads=nt)
+    ll, st, steps, used = oracle.eval_batch(params[:m], nthreads=nt)
     dt = time.perf_counter() - t0
     return {"value": m / dt, "unit": UNIT, "cores": int(used), "kind": "port",
             "sample": f"first {m} sets of the same batch, OpenMP schedule(dynamic) over sets, {dt:.1f} s; the oracle is the "
-                      "dependency-free restatement of the reference path (the reference needs Boost/Eigen, absent here)"}, ll
+                      "dependency-free restatement of the reference path (the reference needs Boost/Eigen, absent here)"}, ll, st, steps
 
 
 def run_reference(args, json_out):
@@ -170,6 +192,138 @@ def run_reference(args, json_out):
     json_out.flush()
 
 
+MH_CHAINS, MH_ITERATIONS = 4096, 30          # BASELINE configs[2]: 4096 seeded chains (strong scaling: the chains are split over the ranks)
+PSO_PARTICLES, PSO_ITERATIONS = 65536, 30     # BASELINE configs[3]: 65,536 particles, global-best topology (strong scaling)
+
+
+def _max_over_ranks(dist, world, dev, values):
+    import torch
+    t = torch.tensor(values, dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return [float(v) for v in t.cpu()]
+
+
+def _gather_bytes(dist, world, rank, dev, arr):
+    """Rank 0 gets the list of every rank's array (uint8 / float64 numpy), the others None."""
+    if world == 1:
+        return [arr]
+    out = [None] * world
+    dist.all_gather_object(out, arr)
+    return out if rank == 0 else None
+
+
+def run_caller_configs(pkg, prob, rank, world, local_rank, dist):
+    """BASELINE configs[2] (multi-chain Metropolis-Hastings) and configs[3] (particle swarm) with the callers RESIDENT ON THE
+    DEVICES and their per-iteration collective on device buffers; strong-scaled over the ranks of this job; outside the headline
+    timed region.  Each record carries wall time (max over ranks), the CUDA-event split of an iteration, the exchange transport
+    and its parity gate: the seeded accept matrix / global-best trace of the sharded run equals the ONE-rank run bit for bit."""
+    import torch
+    from sepaihrd_b200 import drivers, resident
+    from sepaihrd_b200.distributed import Comm
+    from sepaihrd_b200.evaluator import BatchEvaluator
+    dev = torch.device("cuda", local_rank)
+    out = {}
+    transports = ["p2p", "nccl"] if world > 1 else [None]
+    base = prob.base_params()
+
+    def summarise(r, n_iter, units):
+        wall, setup = _max_over_ranks(dist, world, dev, [r["run_seconds"], r["setup_seconds"]])
+        names = sorted(r["phase_seconds"])
+        phases = _max_over_ranks(dist, world, dev, [r["phase_seconds"][k] for k in names])
+        gpu = sum(phases)
+        rec = {"wall_s": wall, "setup_s": setup, "iterations": n_iter, "ms_per_iteration": wall / n_iter * 1e3,
+               "phase_ms_per_iteration": {k: v / n_iter * 1e3 for k, v in zip(names, phases)},
+               "exchange_us_per_iteration": dict(zip(names, phases)).get("exchange", 0.0) / n_iter * 1e6,
+               "host_share_of_wall": max(0.0, 1.0 - gpu / wall) if wall > 0 else None,
+               "evals_per_s": units / wall, "transport": r["transport"], "fallback_reason": r["fallback_reason"],
+               "exchange_status": r["exchange_status"]}
+        return rec
+
+    # ---- configs[2]: 4096 chains x 30 iterations, MCMC_REFLECT ----------------------------------------------------------
+    try:
+        rp = prob.__class__.from_json(dict(prob.to_json(), constraint_mode=1))
+        with BatchEvaluator(rp, device=local_rank) as ev:
+            ev.eval_batch(np.tile(base, (64, 1)))
+            rec = {"workload": f"{MH_CHAINS} seeded Metropolis-Hastings chains x {MH_ITERATIONS} iterations, reflect mode, chains sharded over "
+                               f"{world} rank(s); device-resident sampler (propose / accept kernels) + per-iteration all-gather of the log-likelihoods",
+                   "scaling": "strong"}
+            runs = {}
+            for tr in transports:
+                resident.run_mh_resident(ev, prob.sigmas, base, MH_CHAINS, 4, 1234, rank, world, transport=tr)       # warm-up (module load, IPC mapping)
+                r = resident.run_mh_resident(ev, prob.sigmas, base, MH_CHAINS, MH_ITERATIONS, 1234, rank, world, transport=tr)
+                runs[r["transport"]] = (r, summarise(r, MH_ITERATIONS - 1, MH_CHAINS * (MH_ITERATIONS - 1)))
+            first = runs[next(iter(runs))][0]
+            rec["transports"] = {k: v[1] for k, v in runs.items()}
+            rec.update(runs[next(iter(runs))][1])
+            parts = _gather_bytes(dist, world, rank, dev, first["accepts"])
+            xs = _gather_bytes(dist, world, rank, dev, first["x"])
+            if rank == 0:
+                acc = np.concatenate(parts, axis=1)
+                one = first if world == 1 else resident.run_mh_resident(ev, prob.sigmas, base, MH_CHAINS, MH_ITERATIONS, 1234, 0, 1)
+                rec["parity"] = {"accept_rate": float(acc.mean()), "accept_checksum": int(np.packbits(acc).astype(np.int64).sum()),
+                                 "accept_matrix_equals_one_rank_run": bool(np.array_equal(acc, one["accepts"])),
+                                 "states_equal_one_rank_run": bool(np.array_equal(np.concatenate(xs), one["x"])),
+                                 "best_trace_equals_one_rank_run": bool(np.array_equal(first["best_trace"], one["best_trace"])),
+                                 "best_logpost": float(first["best_trace"][-1])}
+            if world > 1:
+                dist.barrier()
+            # the round-1 path beside it: host sampler (C++) + numpy -> H2D -> all_gather on a list of tensors -> .cpu() per rank
+            comm = Comm()
+            comm.barrier(); t0 = time.perf_counter()
+            old = drivers.run_multichain_mh(ev.eval_batch, prob.sigmas, prob.lower_bound, prob.upper_bound, base, MH_CHAINS, MH_ITERATIONS,
+                                            seed=1234, comm=comm, record_accepts=True)
+            comm.barrier(); dt = time.perf_counter() - t0
+            old_parts = _gather_bytes(dist, world, rank, dev, old["accepts"])
+            w, e, c = _max_over_ranks(dist, world, dev, [dt, old["eval_seconds"], old["comm_seconds"]])
+            rec["host_staged_path"] = {"wall_s": w, "ms_per_iteration": w / (MH_ITERATIONS - 1) * 1e3, "eval_ms_per_iteration": e / (MH_ITERATIONS - 1) * 1e3,
+                                       "exchange_us_per_iteration": c / (MH_ITERATIONS - 1) * 1e6,
+                                       "host_sampler_share_of_wall": max(0.0, 1.0 - (e + c) / w)}
+            if rank == 0:
+                rec["parity"]["accept_matrix_equals_host_sampler"] = bool(np.array_equal(np.concatenate(old_parts, axis=1), np.concatenate(parts, axis=1)))
+            out["mh4096"] = rec
+    except Exception as exc:                                   # never lose the headline line over a caller configuration
+        out["mh4096"] = {"error": f"{type(exc).__name__}: {exc}"}
+
+    # ---- configs[3]: 65,536 particles x 30 iterations, global best --------------------------------------------------------
+    try:
+        with BatchEvaluator(prob, device=local_rank) as ev:
+            ev.eval_batch(np.tile(base, (64, 1)))
+            rec = {"workload": f"particle swarm of {PSO_PARTICLES} particles x {PSO_ITERATIONS} iterations (STANDARD update, global-best topology), "
+                               f"particles sharded over {world} rank(s); device-resident swarm + per-iteration all-gather of one 64-double record per rank",
+                   "scaling": "strong"}
+            runs = {}
+            for tr in transports:
+                resident.run_pso_resident(ev, PSO_PARTICLES, 2, 7, initial=base, rank=rank, world=world, transport=tr)
+                r = resident.run_pso_resident(ev, PSO_PARTICLES, PSO_ITERATIONS, 7, initial=base, rank=rank, world=world, transport=tr)
+                runs[r["transport"]] = (r, summarise(r, PSO_ITERATIONS + 1, PSO_PARTICLES * (PSO_ITERATIONS + 1)))
+            first = runs[next(iter(runs))][0]
+            rec["transports"] = {k: v[1] for k, v in runs.items()}
+            rec.update(runs[next(iter(runs))][1])
+            if rank == 0:
+                one = first if world == 1 else resident.run_pso_resident(ev, PSO_PARTICLES, PSO_ITERATIONS, 7, initial=base, rank=0, world=1)
+                rec["parity"] = {"global_best_trace_equals_one_rank_run": bool(np.array_equal(first["trace"], one["trace"])),
+                                 "best_position_equals_one_rank_run": bool(np.array_equal(first["best_position"], one["best_position"])),
+                                 "best_first": float(first["trace"][0]), "best_last": float(first["trace"][-1]),
+                                 "transports_agree": bool(all(np.array_equal(v[0]["trace"], first["trace"]) for v in runs.values()))}
+            if world > 1:
+                dist.barrier()
+            comm = Comm()
+            comm.barrier(); t0 = time.perf_counter()
+            old = drivers.run_pso(None, prob.sigmas, prob.lower_bound, prob.upper_bound, PSO_PARTICLES, PSO_ITERATIONS, seed=7, initial=base,
+                                  comm=comm, device_ctx=ev.handle)
+            comm.barrier(); dt = time.perf_counter() - t0
+            w, e, c = _max_over_ranks(dist, world, dev, [dt, old["eval_seconds"], old["comm_seconds"]])
+            rec["host_staged_path"] = {"wall_s": w, "ms_per_iteration": w / (PSO_ITERATIONS + 1) * 1e3, "eval_ms_per_iteration": e / (PSO_ITERATIONS + 1) * 1e3,
+                                       "exchange_us_per_iteration": c / (PSO_ITERATIONS + 1) * 1e6}
+            if rank == 0:
+                rec["parity"]["trace_equals_host_staged_path"] = bool(np.array_equal(old["trace"], first["trace"]))
+            out["pso65536"] = rec
+    except Exception as exc:
+        out["pso65536"] = {"error": f"{type(exc).__name__}: {exc}"}
+    return out
+
+
 def _claim_stdout():
     """Keep file descriptor 1 for the ONE JSON line: everything else that writes to stdout while the benchmark runs
     (NCCL prints its version banner there, libraries may log) is sent to stderr.  Returns the stream for the JSON line."""
@@ -188,6 +342,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=B_PER_GPU, help="parameter sets per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip BASELINE configs[2] / [3] (MH 4096 chains, PSO 65,536 particles)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args, json_out)
@@ -281,6 +436,11 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_kernel, ms_e2e = t[0].item(), t[1].item()
 
+    caller_configs = None
+    if not args.no_configs:
+        # free the sweep's 1 GB of parameter buffers first; the callers below allocate their own state
+        caller_configs = run_caller_configs(pkg, prob, rank, world, local_rank, dist if world > 1 else None)
+
     if rank == 0:
         value = world * args.steps * B / (ms_kernel * 1e-3)
         e2e_value = world * args.steps * B / (ms_e2e * 1e-3)
@@ -288,6 +448,8 @@ def main():
         launch_s = ms_kernel * 1e-3 / args.steps
         achieved = flop_per_launch / launch_s / 1e12
         peak = 2.0 * peak_dfma / 1e12
+        cap = ncu_capture(B)
+        sm_ghz = ((clocks or {}).get("sm_mhz") or 1965.0) / 1e3
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                "ms_per_step": ms_kernel / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                "dtype": "f64", "data": "synthetic", "config": workload_config(world, B),
@@ -296,18 +458,22 @@ def main():
                "gpu_launches": int(launches1 - launches0),
                "gpu_launches_e2e": int(launches2 - launches1),
                "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                            "traffic": NCU_DRAM_BYTES_PER_LAUNCH_1M if B == (1 << 20) else None,
+                            "traffic": (cap["dram_bytes_per_launch"] if cap and cap["same_batch"] and not cap["stale"] else None),
                             "kernel": "sepaihrd_batch_kernel<4,fast,LL>",
                             "flop_per_launch": flop_per_launch, "attempts_per_set": attempts_total / B,
                             "launch_ms": launch_s * 1e3,
                             "peak_source": "measured live: sepaihrd_measure_fp64_peak (dependent DFMA chains), x2 FLOP per DFMA; "
                                            "MEASURED_PEAKS.json has no FP64 entry",
                             "hbm_bytes_per_launch_algorithmic": B * (P * 8 + 12),
-                            # BASELINE.json's "% FP64 peak (ncu fp64-pipe utilisation and issue efficiency)": from the ncu --set full
-                            # capture of this kernel at this batch size (profiles/r01_v12_ncu_full_summary.txt), not measured live
-                            "ncu_fp64_pipe_pct": NCU_FP64_PIPE_PCT if B == (1 << 20) else None,
-                            "ncu_issue_active_pct": NCU_ISSUE_ACTIVE_PCT if B == (1 << 20) else None},
+                            # the datasheet-order denominator beside the measured one: 148 SMs x 64 FP64 lanes x 2 FLOP x SM clock
+                            "frac_of_datasheet_peak": achieved / (148 * 64 * 2 * sm_ghz / 1e3),
+                            "datasheet_peak": 148 * 64 * 2 * sm_ghz / 1e3, "datasheet_clock_ghz": sm_ghz,
+                            # BASELINE.json's "% FP64 peak (ncu fp64-pipe utilisation and issue efficiency)": the committed ncu --set full
+                            # capture of this kernel (NOT measured by this run; "stale" = kernel sources changed since the capture)
+                            "ncu_capture": cap},
                "clocks": clocks, "logl_checksum": checksum}
+        if caller_configs is not None:
+            out["configs"] = caller_configs
         if world == 1:
             # SURVEY.md 8(d) names a second distribution: uniform in bounds (the PSO initialisation recipe), mt19937(2).  Not the
             # headline (warps idle more when their 8 sets need different attempt counts); reported beside it, outside the
@@ -330,10 +496,15 @@ def main():
             except Exception as exc:           # informational only: never lose the headline line over it
                 out["second_distribution"] = {"error": str(exc)}
         if not args.no_cpu_baseline and world == 1:
-            base, ll_cpu = cpu_baseline(oracle, params)
+            base, ll_cpu, st_cpu, steps_cpu = cpu_baseline(oracle, params)
             m = len(ll_cpu)
             rel = np.abs(h_ll.numpy()[:m] - ll_cpu) / np.abs(ll_cpu)
             base["max_rel_logl_diff_vs_gpu"] = float(rel.max())
+            # parity gates in the same job: accept/reject path and status word of every set of the sample
+            step(0, True); torch.cuda.synchronize()
+            base["step_count_mismatches"] = int((d_steps[:m].cpu().numpy() != steps_cpu).any(axis=1).sum())
+            base["status_mismatches"] = int((d_st[:m].cpu().numpy().astype(np.uint32) != st_cpu).sum())
+            base["sets_compared"] = int(m)
             out["cpu_baseline"] = base
         json_out.write(json.dumps(out) + "\n")
         json_out.flush()

@@ -281,7 +281,8 @@ typedef struct sepaihrd_mh_settings {
 } sepaihrd_mh_settings;
 enum { SEPAIHRD_MH_POSITIONS = 0, SEPAIHRD_MH_LOGPOST = 1, SEPAIHRD_MH_SCALES = 2, SEPAIHRD_MH_ACCEPTED_COUNTS = 3 /* int64 */,
        SEPAIHRD_MH_BEST_LOGPOST = 4, SEPAIHRD_MH_BEST_POSITIONS = 5, SEPAIHRD_MH_ACCEPT_MATRIX = 6 /* uint8 [iterations done][local] */,
-       SEPAIHRD_MH_TRACE = 7 /* [iterations + 1] */, SEPAIHRD_MH_PROPOSALS = 8 };
+       SEPAIHRD_MH_TRACE = 7 /* [iterations + 1] */, SEPAIHRD_MH_PROPOSALS = 8,
+       SEPAIHRD_MH_FAULT = 9 /* uint32: nonzero if a proposal ever ran out of its 128 polar attempts (never in practice) */ };
 sepaihrd_rc sepaihrd_mh_create(sepaihrd_ctx* ctx, int64_t n_chains, int64_t chain_offset, int64_t local_count,
                                const sepaihrd_mh_settings* settings, sepaihrd_mh** out);
 void sepaihrd_mh_destroy(sepaihrd_mh* mh);
@@ -291,6 +292,11 @@ void sepaihrd_mh_destroy(sepaihrd_mh* mh);
 sepaihrd_rc sepaihrd_mh_begin(sepaihrd_mh* mh, uint32_t seed, const double* initial, const double* chol_lower);
 /* Enqueue up to n_iterations iterations on the ctx stream (stops at settings.iterations). */
 sepaihrd_rc sepaihrd_mh_iterate(sepaihrd_mh* mh, int32_t n_iterations);
+/* The three phases of ONE iteration as separate calls (propose kernel / fused likelihood kernel / accept kernel; accept
+ * advances the iteration index), for callers that time them with CUDA events between the calls. */
+sepaihrd_rc sepaihrd_mh_propose(sepaihrd_mh* mh);
+sepaihrd_rc sepaihrd_mh_evaluate(sepaihrd_mh* mh);
+sepaihrd_rc sepaihrd_mh_accept(sepaihrd_mh* mh);
 int32_t sepaihrd_mh_iteration(const sepaihrd_mh* mh);    /* next iteration index, 1-based */
 /* Device pointer of the local chains' current log-posteriors [local_count]: the block a rank contributes to the
  * per-iteration all-gather (north_star: "gather log-likelihoods for the MCMC accept step"). */

@@ -51,6 +51,9 @@ SIGNATURES = {
     "sepaihrd_mh_destroy": (None, [C.c_void_p]),
     "sepaihrd_mh_begin": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]),
     "sepaihrd_mh_iterate": (C.c_int, [C.c_void_p, C.c_int32]),
+    "sepaihrd_mh_propose": (C.c_int, [C.c_void_p]),
+    "sepaihrd_mh_evaluate": (C.c_int, [C.c_void_p]),
+    "sepaihrd_mh_accept": (C.c_int, [C.c_void_p]),
     "sepaihrd_mh_iteration": (C.c_int32, [C.c_void_p]),
     "sepaihrd_mh_logpost_device": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "sepaihrd_mh_note_gathered": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int32]),

@@ -18,10 +18,13 @@
 // operation is individually rounded in the host's order, and log / exp are csrc/det_math.h on both sides.  A device-resident
 // run therefore makes EXACTLY the host run's accept decisions and visits its states (tests/test_gpu_host.py).
 //
-// Mapping: one thread per chain (a few hundred to a few thousand chains per GPU: the sampler is latency-bound, ~30 us per
-// iteration against >= 550 us for the likelihood launch).  Generator states are word-major ([624][chains]), so the 32 chains of
-// a warp read word i as one coalesced line; tempered outputs are prefetched 112 at a time (state blocks twisted lazily, 16
-// words at a time, exactly in the reference order), which turns ~160 dependent loads per proposal into two batches.
+// Mapping: one WARP per chain.  The polar method consumes exactly four generator words per attempt, so the attempts of a
+// proposal are independent given their position in the stream: the 32 lanes evaluate 32 attempts at once (uniforms, r^2, log,
+// sqrt), a ballot + prefix count hands the accepted ones their place among the P normals, and the position of the last one
+// needed tells how many words the chain consumed -- the same numbers, in the same order, as the sequential host loop.  The
+// generator state is chain-major ([chains][624]); a warp twists 32 consecutive words per step (word k needs the old k, k + 1 and
+// the word 397 ahead or 227 behind: never one of the same step), loads before stores.  ~15 us per iteration for 4096 chains
+// against >= 550 us for the likelihood launch (the first version, one thread per chain, took 220 us).
 #include <cfloat>
 #include <cmath>
 #include <cstdint>
@@ -60,66 +63,45 @@ using sepaihrd_internal::fail_with;
     } while (0)
 
 constexpr int MT_N = 624, MT_M = 397;
-constexpr int MH_THREADS = 64;
-constexpr int RNG_BUF = 112;                   // tempered words fetched per batch (7 state blocks of 16)
+constexpr int MH_THREADS = 128;                // 4 chains per block
+constexpr int MH_WARPS = MH_THREADS / 32;
 constexpr int RECENT_WORDS = 32;               // ring of the last 1000 accept decisions, one bit each
+constexpr unsigned FULLM = 0xffffffffu;
 
-// std::mt19937 whose 624-word state lives in global memory, word-major.  C = outputs consumed, T = state words twisted,
-// both counted from the seeding (they wrap at 2^32; only their difference and their residues mod 624 are used -- 2^32 is
-// NOT a multiple of 624, so a chain may draw at most 2^32 - 1 words: ~2.7e7 iterations of a 62-parameter chain).
-struct ChainRng {
-    unsigned* st;
-    long long stride;
-    unsigned C, T;
-    unsigned buf[RNG_BUF];
-    int have, at;
-    __device__ __forceinline__ unsigned& word(int i) { return st[(long long)i * stride]; }
-    __device__ void twist16(int k0) {
-        unsigned cur[17], far[16];
-#pragma unroll
-        for (int j = 0; j < 17; ++j) { const int k = k0 + j; cur[j] = word(k == MT_N ? 0 : k); }
-#pragma unroll
-        for (int j = 0; j < 16; ++j) { const int km = k0 + j + MT_M; far[j] = word(km >= MT_N ? km - MT_N : km); }
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const unsigned y = (cur[j] & 0x80000000u) | (cur[j + 1] & 0x7fffffffu);
-            word(k0 + j) = far[j] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
-        }
-    }
-    __device__ void fill(int want) {           // the buffer is exhausted: fetch outputs [C, C + want)
-        while ((unsigned)(T - C) < (unsigned)want) { twist16((int)(T % MT_N)); T += 16; }
-        const int i0 = (int)(C % MT_N);
-#pragma unroll 8
-        for (int i = 0; i < want; ++i) {
-            int k = i0 + i; if (k >= MT_N) k -= MT_N;
-            unsigned y = word(k);
-            y ^= (y >> 11);
-            y ^= (y << 7) & 0x9d2c5680u;
-            y ^= (y << 15) & 0xefc60000u;
-            y ^= (y >> 18);
-            buf[i] = y;
-        }
-        have = want; at = 0;
-    }
-    __device__ __forceinline__ unsigned next(int refill) {
-        if (at == have) fill(refill);
-        ++C;
-        return buf[at++];
-    }
-    // generate_canonical<double, 53>: (lo + hi 2^32) / 2^64, one rounding in the sum; 1.0 -> the largest double below 1
-    __device__ __forceinline__ double uniform01(int refill) {
-        const unsigned lo = next(refill), hi = next(refill);
-        const double sum = __dadd_rn((double)lo, __dmul_rn((double)hi, 4294967296.0));
-        const double r = __dmul_rn(sum, 1.0 / 18446744073709551616.0);
-        return (r >= 1.0) ? 0.99999999999999988898 : r;
-    }
-};
+// std::mt19937 whose 624-word state lives in global memory ([chains][624]).  C = outputs consumed, T = state words twisted, both
+// counted from the seeding (T a multiple of 32; they wrap at 2^32 and only their difference and residues mod 624 are used --
+// 2^32 is not a multiple of 624, so a chain may draw at most 2^32 - 1 words: ~2.7e7 iterations of a 62-parameter chain).
+// Twisting [T, T + 32) overwrites the outputs T - 624 ..., which must have been consumed: T <= C + 592 (callers keep T - C <= 544).
+__device__ __forceinline__ void warp_twist32(unsigned* st, unsigned T, int lane) {
+    int k = (int)(T % MT_N) + lane; if (k >= MT_N) k -= MT_N;
+    const int k1 = (k + 1 == MT_N) ? 0 : k + 1;
+    const int km = (k + MT_M >= MT_N) ? k + MT_M - MT_N : k + MT_M;
+    const unsigned a = st[k], b = st[k1], f = st[km];
+    __syncwarp();                                                      // every lane has loaded before any lane stores
+    const unsigned y = (a & 0x80000000u) | (b & 0x7fffffffu);
+    st[k] = f ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+    __syncwarp();
+}
+__device__ __forceinline__ unsigned mt_output(const unsigned* st, unsigned pos) {      // tempered output number `pos`
+    unsigned y = st[pos % MT_N];
+    y ^= (y >> 11);
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= (y >> 18);
+    return y;
+}
+// generate_canonical<double, 53>: (lo + hi 2^32) / 2^64, one rounding in the sum; 1.0 -> the largest double below 1
+__device__ __forceinline__ double canonical(unsigned lo, unsigned hi) {
+    const double sum = __dadd_rn((double)lo, __dmul_rn((double)hi, 4294967296.0));
+    const double r = __dmul_rn(sum, 1.0 / 18446744073709551616.0);
+    return (r >= 1.0) ? 0.99999999999999988898 : r;
+}
 
 // std::seed_seq{seed, chain}.generate over 624 words ([rand.util.seedseq]) = the state of std::mt19937 seeded from it;
-// the first output comes after a twist.  Local scratch (lane-interleaved, L1-resident), then one pass to the word-major state.
-__global__ void __launch_bounds__(MH_THREADS) mh_seed_kernel(long long local, long long offset, unsigned seed, unsigned* __restrict__ mt,
-                                                              unsigned* __restrict__ Cc, unsigned* __restrict__ Tt) {
-    const long long c = blockIdx.x * (long long)MH_THREADS + threadIdx.x;
+// the first output comes after a twist.  Local scratch (lane-interleaved, L1-resident), then one pass to the state.
+__global__ void __launch_bounds__(64) mh_seed_kernel(long long local, long long offset, unsigned seed, unsigned* __restrict__ mt,
+                                                      unsigned* __restrict__ Cc, unsigned* __restrict__ Tt) {
+    const long long c = blockIdx.x * (long long)64 + threadIdx.x;
     if (c >= local) return;
     const unsigned v[2] = {seed, (unsigned)(offset + c)};
     constexpr int n = MT_N, s = 2, t = 11, p = (n - t) / 2, q = p + t, m = n;      // m = max(s + 1, n)
@@ -147,7 +129,7 @@ __global__ void __launch_bounds__(MH_THREADS) mh_seed_kernel(long long local, lo
     bool zero = (b[0] & 0x80000000u) == 0u;
     for (int i = 1; i < n && zero; ++i) zero = (b[i] == 0u);
     if (zero) b[0] = 0x80000000u;
-    for (int i = 0; i < n; ++i) mt[(long long)i * local + c] = b[i];
+    for (int i = 0; i < n; ++i) mt[c * MT_N + i] = b[i];
     Cc[c] = 0u; Tt[c] = 0u;
 }
 
@@ -163,56 +145,71 @@ __global__ void mh_start_kernel(long long local, int P, const double* __restrict
     for (int k = 0; k < P; ++k) { x[c * P + k] = init[k]; best_x[c * P + k] = init[k]; }
     lp[c] = v; best_lp[c] = v;
     log_scale[c] = 0.0; scale[c] = 1.0;
-    for (int w = 0; w < RECENT_WORDS; ++w) recent[(long long)w * local + c] = 0u;
+    for (int w = 0; w < RECENT_WORDS; ++w) recent[c * RECENT_WORDS + w] = 0u;
     recent_n[c] = 0; recent_sum[c] = 0; emergency[c] = 0; accepted[c] = 0;
 }
 
-// generateProposal + applyConstraints for every local chain
+// generateProposal + applyConstraints: one warp per local chain
 __global__ void __launch_bounds__(MH_THREADS) mh_propose_kernel(long long local, int P, int diagonal, int mode, const double* __restrict__ chol,
                                                                  const double* __restrict__ lo, const double* __restrict__ hi,
                                                                  const double* __restrict__ x, const double* __restrict__ scale,
                                                                  unsigned* __restrict__ mt, unsigned* __restrict__ Cc, unsigned* __restrict__ Tt,
-                                                                 double* __restrict__ prop) {
-    const long long c = blockIdx.x * (long long)MH_THREADS + threadIdx.x;
+                                                                 double* __restrict__ prop, unsigned* __restrict__ fault) {
+    __shared__ double zs[MH_WARPS][SEPAIHRD_MH_MAX_PARAMS];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const long long c = blockIdx.x * (long long)MH_WARPS + wib;
     if (c >= local) return;
-    ChainRng g;
-    g.st = mt + c; g.stride = local; g.C = Cc[c]; g.T = Tt[c]; g.have = 0; g.at = 0;
-    double z[SEPAIHRD_MH_MAX_PARAMS];
+    unsigned* st = mt + c * MT_N;
+    unsigned C = Cc[c], T = Tt[c];
+    double* z = zs[wib];
     // std::normal_distribution<double>(0, 1), a FRESH object per proposal (the reference declares it inside generateProposal):
-    // polar method, the second value of an accepted pair is returned by the next call
-    for (int i = 0; i < P; i += 2) {
-        double a, b, r2;
-        do {
-            a = __dsub_rn(__dmul_rn(2.0, g.uniform01(RNG_BUF)), 1.0);
-            b = __dsub_rn(__dmul_rn(2.0, g.uniform01(RNG_BUF)), 1.0);
-            r2 = __dadd_rn(__dmul_rn(a, a), __dmul_rn(b, b));
-        } while (r2 > 1.0 || r2 == 0.0);
-        const double mult = __dsqrt_rn(__ddiv_rn(__dmul_rn(-2.0, detm::log(r2)), r2));
-        z[i] = __dmul_rn(b, mult);                          // first call returns y * mult and saves x * mult
-        if (i + 1 < P) z[i + 1] = __dmul_rn(a, mult);
+    // polar method; the first value of an accepted pair is y * mult, the second (returned by the next call) x * mult.
+    // Attempt j of this proposal reads the outputs C + 4 j ... C + 4 j + 3 whatever happened to the attempts before it.
+    const int npairs = (P + 1) / 2;
+    int got = 0, consumed = -1;
+    for (int base = 0; base < 128 && consumed < 0; base += 32) {
+        while ((unsigned)(T - C) < (unsigned)(4 * (base + 32))) { warp_twist32(st, T, lane); T += 32; }
+        const unsigned w0 = C + 4u * (unsigned)(base + lane);
+        const double a = __dsub_rn(__dmul_rn(2.0, canonical(mt_output(st, w0), mt_output(st, w0 + 1))), 1.0);
+        const double b = __dsub_rn(__dmul_rn(2.0, canonical(mt_output(st, w0 + 2), mt_output(st, w0 + 3))), 1.0);
+        const double r2 = __dadd_rn(__dmul_rn(a, a), __dmul_rn(b, b));
+        const bool ok = !(r2 > 1.0 || r2 == 0.0);
+        const unsigned mask = __ballot_sync(FULLM, ok);
+        const int rank = got + __popc(mask & ((1u << lane) - 1u));
+        if (ok && rank < npairs) {
+            const double mult = __dsqrt_rn(__ddiv_rn(__dmul_rn(-2.0, detm::log(r2)), r2));
+            z[2 * rank] = __dmul_rn(b, mult);
+            if (2 * rank + 1 < P) z[2 * rank + 1] = __dmul_rn(a, mult);
+        }
+        const int cnt = __popc(mask);
+        if (got + cnt >= npairs) consumed = 4 * (base + (int)__fns(mask, 0, npairs - got) + 1);
+        got += cnt;
     }
+    if (consumed < 0) {                 // 128 attempts without P normals: probability ~1e-40; flagged, never silently wrong
+        if (lane == 0) atomicExch(fault, 1u);
+        consumed = 4 * 128;
+        for (int i = 2 * got + lane; i < P; i += 32) z[i] = 0.0;
+    }
+    C += (unsigned)consumed;
+    __syncwarp();
     const double sc = scale[c];
     const double* xc = x + c * P;
     double* out = prop + c * P;
-    if (diagonal) {
-        for (int i = 0; i < P; ++i) {
-            const double step = __dmul_rn(chol[(long long)i * P + i], z[i]);
-            out[i] = sepaihrd::constrain(__dadd_rn(xc[i], __dmul_rn(sc, step)), lo[i], hi[i], mode);
+    for (int i = lane; i < P; i += 32) {
+        double step;
+        if (diagonal) {
+            step = __dmul_rn(chol[(long long)i * P + i], z[i]);
+        } else {        // row i of L z: the host adds the columns j = 0 .. i in this order (the structural zeros add nothing)
+            step = 0.0;
+            for (int j = 0; j <= i; ++j) step = __dadd_rn(step, __dmul_rn(chol[(long long)j * P + i], z[j]));
         }
-    } else {
-        // step = L z over the lower triangle, column by column like the host (the structural zeros add nothing)
-        double step[SEPAIHRD_MH_MAX_PARAMS];
-        for (int i = 0; i < P; ++i) step[i] = 0.0;
-        for (int j = 0; j < P; ++j) {
-            const double zj = z[j];
-            for (int i = j; i < P; ++i) step[i] = __dadd_rn(step[i], __dmul_rn(chol[(long long)j * P + i], zj));
-        }
-        for (int i = 0; i < P; ++i) out[i] = sepaihrd::constrain(__dadd_rn(xc[i], __dmul_rn(sc, step[i])), lo[i], hi[i], mode);
+        out[i] = sepaihrd::constrain(__dadd_rn(xc[i], __dmul_rn(sc, step)), lo[i], hi[i], mode);
     }
-    Cc[c] = g.C; Tt[c] = g.T;
+    if (lane == 0) { Cc[c] = C; Tt[c] = T; }
 }
 
-// accept + adaptGlobalScale for every local chain; `step` is the reference's 1-based iteration index
+// accept + adaptGlobalScale: one warp per local chain (lane 0 decides and keeps the books, the warp moves the state);
+// `step` is the reference's 1-based iteration index
 __global__ void __launch_bounds__(MH_THREADS) mh_accept_kernel(long long local, int P, int step, int adapt_scale, double target,
                                                                 const double* __restrict__ plp_in, const double* __restrict__ prop,
                                                                 double* __restrict__ x, double* __restrict__ lp, unsigned* __restrict__ mt,
@@ -221,7 +218,8 @@ __global__ void __launch_bounds__(MH_THREADS) mh_accept_kernel(long long local, 
                                                                 int* __restrict__ recent_sum, int* __restrict__ emergency,
                                                                 long long* __restrict__ accepted, double* __restrict__ best_lp,
                                                                 double* __restrict__ best_x, unsigned char* __restrict__ accepts_row) {
-    const long long c = blockIdx.x * (long long)MH_THREADS + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const long long c = blockIdx.x * (long long)MH_WARPS + (threadIdx.x >> 5);
     if (c >= local) return;
     double plp = plp_in[c];
     if (isnan(plp) || isinf(plp)) plp = -1e18;                                  // safeEvaluate, .cpp:65-74
@@ -230,25 +228,35 @@ __global__ void __launch_bounds__(MH_THREADS) mh_accept_kernel(long long local, 
     bool acc = false;
     if (log_ratio >= 0.0) {
         acc = true;
-    } else {
-        ChainRng g;
-        g.st = mt + c; g.stride = local; g.C = Cc[c]; g.T = Tt[c]; g.have = 0; g.at = 0;
-        const double u = g.uniform01(16);
+    } else {                                                                    // the uniform is drawn ONLY for downhill proposals
+        unsigned* st = mt + c * MT_N;
+        unsigned C = Cc[c], T = Tt[c];
+        while ((unsigned)(T - C) < 2u) { warp_twist32(st, T, lane); T += 32; }
+        const double u = canonical(mt_output(st, C), mt_output(st, C + 1));
         if (detm::log(u) < log_ratio) acc = true;
-        Cc[c] = g.C; Tt[c] = g.T;
+        __syncwarp();
+        if (lane == 0) { Cc[c] = C + 2u; Tt[c] = T; }
     }
+    const bool better = acc && plp > best_lp[c];
+    __syncwarp();
+    if (acc)
+        for (int k = lane; k < P; k += 32) {
+            const double v = prop[c * P + k];
+            x[c * P + k] = v;
+            if (better) best_x[c * P + k] = v;
+        }
+    if (lane != 0) return;
     if (acc) {
-        for (int k = 0; k < P; ++k) x[c * P + k] = prop[c * P + k];
         lp[c] = plp;
         accepted[c] += 1;
-        if (plp > best_lp[c]) { best_lp[c] = plp; for (int k = 0; k < P; ++k) best_x[c * P + k] = prop[c * P + k]; }
+        if (better) best_lp[c] = plp;
     }
     if (accepts_row) accepts_row[c] = acc ? 1 : 0;
     if (!adapt_scale) return;
     // recent: the last <= 1000 decisions (the host pushes, then drops the oldest once there are more than 1000)
     int n = recent_n[c], sum = recent_sum[c];
     const int slot = n % 1000;
-    unsigned* wp = recent + (long long)(slot >> 5) * local + c;
+    unsigned* wp = recent + c * RECENT_WORDS + (slot >> 5);
     unsigned w = *wp;
     const unsigned bit = 1u << (slot & 31);
     if (n >= 1000) sum -= (w & bit) ? 1 : 0;
@@ -326,7 +334,7 @@ sepaihrd_rc sepaihrd_mh_create(sepaihrd_ctx* ctx, int64_t n_chains, int64_t chai
                  o_sc = reserve(8 * L), o_blp = reserve(8 * L), o_bx = reserve(8 * LP), o_chol = reserve(8 * (size_t)d.P * d.P),
                  o_lo = reserve(8 * (size_t)d.P), o_hi = reserve(8 * (size_t)d.P), o_init = reserve(8 * (size_t)d.P),
                  o_trace = reserve(8 * (size_t)m->trace_cap), o_mt = reserve(4 * L * MT_N), o_C = reserve(4 * L), o_T = reserve(4 * L),
-                 o_rec = reserve(4 * L * RECENT_WORDS), o_st = reserve(4 * (L + 1)), o_rn = reserve(4 * L), o_rs = reserve(4 * L),
+                 o_rec = reserve(4 * L * RECENT_WORDS), o_st = reserve(4 * (L + 2)), o_rn = reserve(4 * L), o_rs = reserve(4 * L),
                  o_em = reserve(4 * L), o_acc = reserve(8 * L),
                  o_accepts = reserve(settings->record_accepts ? L * (size_t)settings->iterations : 1);
     cudaError_t e = cudaMalloc((void**)&m->d_arena, bytes);
@@ -339,6 +347,7 @@ sepaihrd_rc sepaihrd_mh_create(sepaihrd_ctx* ctx, int64_t n_chains, int64_t chai
         m->d_recent = (unsigned*)(D + o_rec); m->d_status = (unsigned*)(D + o_st); m->d_recent_n = (int*)(D + o_rn); m->d_recent_sum = (int*)(D + o_rs);
         m->d_emergency = (int*)(D + o_em); m->d_accepted = (long long*)(D + o_acc); m->d_accepts = (unsigned char*)(D + o_accepts);
         e = cudaMemcpy(m->d_lo, sepaihrd_internal::lower_bounds(ctx), 8 * (size_t)d.P, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemset(m->d_status, 0, 4 * (L + 2));       // [L + 1] = the proposal kernel's fault flag
     }
     if (e == cudaSuccess) e = cudaMemcpy(m->d_hi, sepaihrd_internal::upper_bounds(ctx), 8 * (size_t)d.P, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
@@ -374,10 +383,10 @@ sepaihrd_rc sepaihrd_mh_begin(sepaihrd_mh* m, uint32_t seed, const double* initi
     sepaihrd_rc rc = sepaihrd_eval_batch_device(m->ctx, m->d_init, 1, P, m->d_plp + m->local, m->d_status + m->local, nullptr);
     if (rc != SEPAIHRD_OK) return rc;
     if (m->local > 0) {
-        const unsigned blocks = (unsigned)((m->local + MH_THREADS - 1) / MH_THREADS);
-        mh_seed_kernel<<<blocks, MH_THREADS, 0, st>>>(m->local, m->offset, seed, m->d_mt, m->d_C, m->d_T);
+        const unsigned blocks = (unsigned)((m->local + 63) / 64);
+        mh_seed_kernel<<<blocks, 64, 0, st>>>(m->local, m->offset, seed, m->d_mt, m->d_C, m->d_T);
         MH_TRY(cudaGetLastError());
-        mh_start_kernel<<<blocks, MH_THREADS, 0, st>>>(m->local, P, m->d_init, m->d_plp + m->local, m->d_x, m->d_lp, m->d_log_scale, m->d_scale,
+        mh_start_kernel<<<blocks, 64, 0, st>>>(m->local, P, m->d_init, m->d_plp + m->local, m->d_x, m->d_lp, m->d_log_scale, m->d_scale,
                                                         m->d_best_lp, m->d_best_x, m->d_recent, m->d_recent_n, m->d_recent_sum, m->d_emergency,
                                                         m->d_accepted);
         MH_TRY(cudaGetLastError());
@@ -388,31 +397,49 @@ sepaihrd_rc sepaihrd_mh_begin(sepaihrd_mh* m, uint32_t seed, const double* initi
     return SEPAIHRD_OK;
 }
 
-sepaihrd_rc sepaihrd_mh_iterate(sepaihrd_mh* m, int32_t n_iterations) {
+// the three phases of one iteration, each enqueued on the ctx stream (sepaihrd_mh_iterate = the three in a loop; the separate
+// entry points let a caller put CUDA events between them)
+static sepaihrd_rc mh_phase(sepaihrd_mh* m, int phase) {
     if (!m) return fail_with(SEPAIHRD_ERR_INVALID_ARGUMENT, "null argument");
-    if (!m->begun) return fail_with(SEPAIHRD_ERR_INVALID_ARGUMENT, "sepaihrd_mh_iterate before sepaihrd_mh_begin");
+    if (!m->begun) return fail_with(SEPAIHRD_ERR_INVALID_ARGUMENT, "sampler phase before sepaihrd_mh_begin");
+    if (m->t >= m->cfg.iterations) return fail_with(SEPAIHRD_ERR_INVALID_ARGUMENT, "all iterations have run");
     const auto ctx_lock = sepaihrd_internal::lock(m->ctx);
     const sepaihrd_internal::Dims d = sepaihrd_internal::dims(m->ctx);
     MH_TRY(cudaSetDevice(d.device));
     cudaStream_t st = sepaihrd_internal::stream(m->ctx);
-    const int mode = sepaihrd_internal::constraint_mode(m->ctx);
-    for (int it = 0; it < n_iterations && m->t < m->cfg.iterations; ++it) {
+    const unsigned blocks = (unsigned)((m->local + MH_WARPS - 1) / MH_WARPS);      // one warp per chain
+    if (phase == 0 && m->local > 0) {
+        mh_propose_kernel<<<blocks, MH_THREADS, 0, st>>>(m->local, m->P, m->diagonal ? 1 : 0, sepaihrd_internal::constraint_mode(m->ctx), m->d_chol,
+                                                          m->d_lo, m->d_hi, m->d_x, m->d_scale, m->d_mt, m->d_C, m->d_T, m->d_prop, m->d_status + m->local + 1);
+        MH_TRY(cudaGetLastError());
+        sepaihrd_internal::count_launches(m->ctx, 1);
+    } else if (phase == 1 && m->local > 0) {
+        return sepaihrd_eval_batch_device(m->ctx, m->d_prop, m->local, m->P, m->d_plp, m->d_status, nullptr);
+    } else if (phase == 2) {
         if (m->local > 0) {
-            const unsigned blocks = (unsigned)((m->local + MH_THREADS - 1) / MH_THREADS);
-            mh_propose_kernel<<<blocks, MH_THREADS, 0, st>>>(m->local, m->P, m->diagonal ? 1 : 0, mode, m->d_chol, m->d_lo, m->d_hi, m->d_x, m->d_scale,
-                                                              m->d_mt, m->d_C, m->d_T, m->d_prop);
-            MH_TRY(cudaGetLastError());
-            sepaihrd_rc rc = sepaihrd_eval_batch_device(m->ctx, m->d_prop, m->local, m->P, m->d_plp, m->d_status, nullptr);
-            if (rc != SEPAIHRD_OK) return rc;
             mh_accept_kernel<<<blocks, MH_THREADS, 0, st>>>(m->local, m->P, m->t, m->cfg.adapt_scale, m->cfg.target_acceptance_rate, m->d_plp, m->d_prop,
                                                              m->d_x, m->d_lp, m->d_mt, m->d_C, m->d_T, m->d_log_scale, m->d_scale, m->d_recent,
                                                              m->d_recent_n, m->d_recent_sum, m->d_emergency, m->d_accepted, m->d_best_lp, m->d_best_x,
                                                              m->cfg.record_accepts ? m->d_accepts + (size_t)(m->t - 1) * m->local : nullptr);
             MH_TRY(cudaGetLastError());
-            sepaihrd_internal::count_launches(m->ctx, 2);
+            sepaihrd_internal::count_launches(m->ctx, 1);
         }
         m->t += 1;
     }
+    return SEPAIHRD_OK;
+}
+sepaihrd_rc sepaihrd_mh_propose(sepaihrd_mh* m) { return mh_phase(m, 0); }
+sepaihrd_rc sepaihrd_mh_evaluate(sepaihrd_mh* m) { return mh_phase(m, 1); }
+sepaihrd_rc sepaihrd_mh_accept(sepaihrd_mh* m) { return mh_phase(m, 2); }
+
+sepaihrd_rc sepaihrd_mh_iterate(sepaihrd_mh* m, int32_t n_iterations) {
+    if (!m) return fail_with(SEPAIHRD_ERR_INVALID_ARGUMENT, "null argument");
+    if (!m->begun) return fail_with(SEPAIHRD_ERR_INVALID_ARGUMENT, "sepaihrd_mh_iterate before sepaihrd_mh_begin");
+    for (int it = 0; it < n_iterations && m->t < m->cfg.iterations; ++it)
+        for (int phase = 0; phase < 3; ++phase) {
+            const sepaihrd_rc rc = mh_phase(m, phase);
+            if (rc != SEPAIHRD_OK) return rc;
+        }
     return SEPAIHRD_OK;
 }
 
@@ -458,6 +485,7 @@ sepaihrd_rc sepaihrd_mh_read(sepaihrd_mh* m, int32_t what, void* out) {
             src = m->d_accepts; bytes = L * (size_t)(m->t - 1); break;
         case SEPAIHRD_MH_TRACE: src = m->d_trace; bytes = 8 * (size_t)m->trace_cap; break;
         case SEPAIHRD_MH_PROPOSALS: src = m->d_prop; bytes = 8 * L * m->P; break;
+        case SEPAIHRD_MH_FAULT: src = m->d_status + m->local + 1; bytes = 4; break;
         default: return fail_with(SEPAIHRD_ERR_INVALID_ARGUMENT, "bad sampler array selector");
     }
     if (bytes == 0) return SEPAIHRD_OK;

@@ -21,7 +21,7 @@ import numpy as np
 from . import capi
 from .distributed import shard_range
 
-MH_POSITIONS, MH_LOGPOST, MH_SCALES, MH_ACCEPTED, MH_BEST_LOGPOST, MH_BEST_POSITIONS, MH_ACCEPT_MATRIX, MH_TRACE, MH_PROPOSALS = range(9)
+MH_POSITIONS, MH_LOGPOST, MH_SCALES, MH_ACCEPTED, MH_BEST_LOGPOST, MH_BEST_POSITIONS, MH_ACCEPT_MATRIX, MH_TRACE, MH_PROPOSALS, MH_FAULT = range(10)
 HANDLE_BYTES = 64
 
 
@@ -200,6 +200,15 @@ class DeviceMH:
     def iterate(self, n: int = 1):
         capi.check(self.L.sepaihrd_mh_iterate(self._h, int(n)))
 
+    def propose(self):
+        capi.check(self.L.sepaihrd_mh_propose(self._h))
+
+    def evaluate(self):
+        capi.check(self.L.sepaihrd_mh_evaluate(self._h))
+
+    def accept(self):
+        capi.check(self.L.sepaihrd_mh_accept(self._h))
+
     @property
     def iteration(self) -> int:
         return int(self.L.sepaihrd_mh_iteration(self._h))
@@ -218,7 +227,7 @@ class DeviceMH:
                      MH_SCALES: ((self.local,), np.float64), MH_ACCEPTED: ((self.local,), np.int64),
                      MH_BEST_LOGPOST: ((self.local,), np.float64), MH_BEST_POSITIONS: ((self.local, self.P), np.float64),
                      MH_ACCEPT_MATRIX: ((done, self.local), np.uint8), MH_TRACE: ((self.iterations + 1,), np.float64),
-                     MH_PROPOSALS: ((self.local, self.P), np.float64)}[what]
+                     MH_PROPOSALS: ((self.local, self.P), np.float64), MH_FAULT: ((1,), np.uint32)}[what]
         out = np.zeros(shape, dtype=dt)
         if out.size:
             capi.check(self.L.sepaihrd_mh_read(self._h, int(what), out.ctypes.data))
@@ -349,13 +358,17 @@ def run_mh_resident(ev, sigmas, initial, n_chains: int, iterations: int, seed: i
     lp_ptr = mh.logpost_ptr()
     send = torch.zeros(block, dtype=torch.float64, device=dev) if (hi - lo) < block or ex.transport == "nccl" else None
     t_setup = time.perf_counter() - t0
-    ph = _Phases(stream, ["sample_eval", "exchange"])
+    ph = _Phases(stream, ["propose", "eval", "accept", "exchange"])
     torch.cuda.synchronize(dev)
     t1 = time.perf_counter()
     mh.begin(seed, initial, initial_cholesky(sigmas) if chol_lower is None else chol_lower)
     ph.mark()
     for it in range(1, iterations):
-        mh.iterate(1)
+        mh.propose()
+        ph.mark()
+        mh.evaluate()
+        ph.mark()
+        mh.accept()
         ph.mark()
         if send is not None:
             if hi > lo:
@@ -367,6 +380,8 @@ def run_mh_resident(ev, sigmas, initial, n_chains: int, iterations: int, seed: i
         ph.mark()
     trace = mh.read(MH_TRACE)[1:iterations]               # the one synchronisation of the run
     t_run = time.perf_counter() - t1
+    if int(mh.read(MH_FAULT)[0]) != 0:
+        raise RuntimeError("device-resident sampler: a proposal exhausted its polar attempts (generator fault)")
     out = dict(rank=rank, world=world, chains=(lo, hi), best_trace=trace, x=mh.read(MH_POSITIONS), logpost=mh.read(MH_LOGPOST),
                scale=mh.read(MH_SCALES), accepted=mh.read(MH_ACCEPTED), accepts=mh.read(MH_ACCEPT_MATRIX) if record_accepts else None,
                all_logpost=np.concatenate([gathered[r, :shard_range(n_chains, r, world)[1] - shard_range(n_chains, r, world)[0]].cpu().numpy()

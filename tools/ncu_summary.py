@@ -2,13 +2,17 @@
 """Summarise an .ncu-rep (one kernel) into the handful of numbers DESIGN.md / profiles/ cite.
 
     python tools/ncu_summary.py gpurun_out/prof.ncu-rep [launch_index] > profiles/rNN_<name>.txt
+    python tools/ncu_summary.py gpurun_out/prof.ncu-rep --json=profiles/current_ncu_capture.json --sets=1048576 --summary=profiles/rNN_<name>.txt
+        also writes the capture record bench.py reports under roofline.ncu_capture (with the hash of the kernel sources)
 """
 import csv
 import subprocess
 import sys
 
-rep = sys.argv[1]
-which = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+args = [a for a in sys.argv[1:] if not a.startswith("--")]
+opts = dict(a[2:].split("=", 1) for a in sys.argv[1:] if a.startswith("--") and "=" in a)
+rep = args[0]
+which = int(args[1]) if len(args) > 1 else 0
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 hdr, units, vals = rows[0], rows[1], rows[2 + which]
@@ -53,3 +57,25 @@ print("\n-- pc sampling totals --")
 ps = [(h, v) for h, (v, u) in m.items() if h.startswith("smsp__pcsamp_warps_issue_stalled") and not h.endswith("not_issued")]
 for h, v in sorted(ps, key=lambda kv: -float(kv[1].replace(",", "") or 0))[:14]:
     print(f"{h:90s} {v}")
+
+if "json" in opts:
+    import hashlib, json, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    csrc = os.path.join(root, "mathematical-modeling-of-infectious-diseases-v1_b200", "csrc")
+    h = hashlib.sha256()
+    for f in ("sepaihrd_kernels.cuh", "sepaihrd_constraints.cuh"):
+        h.update(open(os.path.join(csrc, f), "rb").read())
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+
+    def num(key):
+        v, u = m[key]
+        return float(v.replace(",", "")) * scale.get(u, 1.0)
+    rec = {"kernel": m.get("Kernel Name", ("?",))[0][:160], "summary_file": opts.get("summary"), "sets_per_launch": int(opts.get("sets", 0)),
+           "kernel_source_hash": h.hexdigest()[:16],
+           "dram_bytes_per_launch": num("dram__bytes_read.sum") + num("dram__bytes_write.sum"),
+           "fp64_pipe_pct": num("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"),
+           "issue_active_pct": num("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+           "duration_ms_under_ncu": num("gpu__time_duration.sum") * {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}.get(m["gpu__time_duration.sum"][1], 1.0),
+           "registers_per_thread": num("launch__registers_per_thread")}
+    with open(opts["json"], "w") as f:
+        json.dump(rec, f, indent=1)
