@@ -127,6 +127,11 @@ typedef struct sepaihrd_ctx sepaihrd_ctx; /* opaque: owns device copies of the p
 /* FAST arithmetic with the general kernel build even when every breakpoint sits on an output-grid point (the default then
  * picks the build without the mixed-segment attempt body): a verification switch, results are bit-identical to FAST. */
 #define SEPAIHRD_MATH_FAST_GENERAL 2
+/* EXPERIMENTAL builds only (-DSEPAIHRD_WITH_SPLIT; the shipped library answers SEPAIHRD_ERR_UNSUPPORTED): FAST arithmetic on
+ * the warp-pair kernel (csrc/experiments/sepaihrd_split.cuh: every set split over an upstream warp S E P A I and a downstream
+ * warp H ICU R D CumH CumICU).  Bit-identical to FAST but measured SLOWER at every batch size
+ * (profiles/r02_split_kernel_experiment.txt), so it is not part of the product. */
+#define SEPAIHRD_MATH_FAST_SPLIT 3
 
 /* Replaces: construction of AgeSEPAIHRDModel + PiecewiseConstantNpiStrategy + SEPAIHRDParameterManager
  * + SEPAIHRDObjectiveFunction + AgeSEPAIHRDSimulator + Dopri5SolverStrategy

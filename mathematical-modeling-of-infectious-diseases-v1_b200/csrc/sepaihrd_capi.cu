@@ -15,7 +15,13 @@
 
 #include "sepaihrd_internal.h"
 #include "sepaihrd_kernels.cuh"
+#ifdef SEPAIHRD_WITH_SPLIT      // experiment, not part of the shipped library (tools/build_variant.sh split -DSEPAIHRD_WITH_SPLIT)
+#include "experiments/sepaihrd_split.cuh"
+#endif
 
+#ifndef SEPAIHRD_SPLIT_THREADS
+#define SEPAIHRD_SPLIT_THREADS 384                 // 6 warp pairs per block, one block per SM: <= 170 registers per thread
+#endif
 #ifndef SEPAIHRD_E2E_DEFAULT_SPLIT
 #define SEPAIHRD_E2E_DEFAULT_SPLIT 128, 32, 8      // measured best on a B200 with PCIe 5 (tools/e2e_split.py); chunk ends of the host-buffer evaluation at B/d for each d listed (descending)
 #endif
@@ -179,7 +185,51 @@ sepaihrd_rc launch_na(sepaihrd_ctx* ctx, const sepaihrd::KParams& kp, int mode) 
                              : launch_t<NA, false, MODE_TRAJ, THREADS, MINBLOCKS, 6>(ctx, kp);
 }
 
+#ifdef SEPAIHRD_WITH_SPLIT
+// The warp-pair kernel (experiments/sepaihrd_split.cuh): same arithmetic, half the state per lane.
+template <int THREADS>
+sepaihrd_rc launch_split(sepaihrd_ctx* ctx, const sepaihrd::KParams& kp_in) {
+    using namespace sepaihrd;
+    KParams kp = kp_in;
+    constexpr int PAIRS = THREADS / 64, SETS = PAIRS * 8;
+    kp.tiles = (kp.B + 7) / 8;
+    if (kp.tiles > 0xffff0000LL) return fail(SEPAIHRD_ERR_UNSUPPORTED, "batch too large for one launch");
+    kp.tile_counter = ctx->d_tile_counter + (ctx->launch_seq++ % sepaihrd_ctx::N_TILE_COUNTERS);
+    CUDA_TRY(cudaMemsetAsync(kp.tile_counter, 0, sizeof(unsigned), ctx->stream));
+    auto kern = sepaihrd_split_kernel<THREADS>;
+    const size_t smem = (size_t)kp.blob_bytes + sizeof(double) * (SETS * (size_t)(kp.slot_stride + ((kp.seg_stride + 1) & ~1)) + 2 * THREADS + (size_t)4 * THREADS) +
+                        PAIRS * sizeof(PairBox) + 16;
+    {
+        static std::once_flag attr_once[64];
+        cudaError_t attr_err = cudaSuccess;
+        std::call_once(attr_once[ctx->device & 63], [&] { attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); });
+        CUDA_TRY(attr_err);
+    }
+    if (smem > 200 * 1024) return fail(SEPAIHRD_ERR_UNSUPPORTED, "problem constants do not fit in shared memory");
+    int occ = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, smem));
+    if (occ < 1) return fail(SEPAIHRD_ERR_CUDA, "kernel does not fit on an SM");
+    long long grid = std::min<long long>((kp.tiles + PAIRS - 1) / PAIRS, (long long)ctx->num_sms * occ);
+    if (grid < 1) grid = 1;
+    kern<<<(unsigned)grid, THREADS, smem, ctx->stream>>>(kp);
+    CUDA_TRY(cudaGetLastError());
+    ctx->launches += 1;
+    ctx->sets += kp.B;
+    return SEPAIHRD_OK;
+}
+
+#endif
+
 sepaihrd_rc launch(sepaihrd_ctx* ctx, const sepaihrd::KParams& kp, int mode) {
+    if (ctx->math_mode == SEPAIHRD_MATH_FAST_SPLIT) {
+#ifdef SEPAIHRD_WITH_SPLIT
+        if (!(ctx->n == 4 && mode == sepaihrd::MODE_LL && ctx->bp_on_grid))
+            return fail(SEPAIHRD_ERR_UNSUPPORTED, "the warp-pair kernel covers log-likelihoods of 4-age problems with breakpoints on grid days");
+        return launch_split<SEPAIHRD_SPLIT_THREADS>(ctx, kp);
+#else
+        return fail(SEPAIHRD_ERR_UNSUPPORTED, "SEPAIHRD_MATH_FAST_SPLIT needs an experimental build (-DSEPAIHRD_WITH_SPLIT): measured slower than FAST, not shipped");
+#endif
+    }
     switch (ctx->n) {
         case 4: return launch_na<4, 128, 2>(ctx, kp, mode);
         case 16: return launch_na<16, 256, 1>(ctx, kp, mode);   // the 16-age observation block (117 KB) allows one block per SM: make it 8 warps
@@ -551,7 +601,7 @@ sepaihrd_rc sepaihrd_set_constraint_mode(sepaihrd_ctx* ctx, int32_t mode) {
 }
 
 sepaihrd_rc sepaihrd_set_math_mode(sepaihrd_ctx* ctx, int32_t mode) {
-    if (!ctx || (mode != SEPAIHRD_MATH_FAST && mode != SEPAIHRD_MATH_STRICT && mode != SEPAIHRD_MATH_FAST_GENERAL)) return fail(SEPAIHRD_ERR_INVALID_ARGUMENT, "bad math mode");
+    if (!ctx || (mode != SEPAIHRD_MATH_FAST && mode != SEPAIHRD_MATH_STRICT && mode != SEPAIHRD_MATH_FAST_GENERAL && mode != SEPAIHRD_MATH_FAST_SPLIT)) return fail(SEPAIHRD_ERR_INVALID_ARGUMENT, "bad math mode");
     if (mode != SEPAIHRD_MATH_STRICT && (ctx->abs_tol <= 0.0 || ctx->rel_tol <= 0.0)) return fail(SEPAIHRD_ERR_UNSUPPORTED, "FAST math needs abs_tol > 0 and rel_tol > 0");
     std::lock_guard<std::recursive_mutex> lock(ctx->mu);
     ctx->math_mode = mode;

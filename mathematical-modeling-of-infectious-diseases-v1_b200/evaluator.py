@@ -17,6 +17,7 @@ from . import capi
 from .problem import Problem, TRAJ_FULL
 
 MATH_FAST, MATH_STRICT, MATH_FAST_GENERAL = 0, 1, 2   # FAST_GENERAL: FAST with the general kernel build (verification)
+MATH_FAST_SPLIT = 3                                   # FAST on the warp-pair kernel (csrc/sepaihrd_split.cuh), bit-identical
 PPC_PROBS = (0.025, 0.05, 0.5, 0.95, 0.975)     # ResultAggregator.cpp:233
 PPC_SERIES = ("daily_hospitalizations", "daily_icu_admissions", "daily_deaths",
               "cumulative_hospitalizations", "cumulative_icu_admissions", "cumulative_deaths")
