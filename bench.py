@@ -436,6 +436,22 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_kernel, ms_e2e = t[0].item(), t[1].item()
 
+    # H2D rate of every rank while ALL ranks copy at once (what the end-to-end path has to live with: at 4 and 8 GPUs the ranks
+    # share the host's memory system, and a rate below 520 MB / kernel time per rank exposes copy time the chunking cannot hide)
+    sync_all()
+    g0 = torch.cuda.Event(enable_timing=True); g1 = torch.cuda.Event(enable_timing=True)
+    g0.record(stream)
+    d_params[1].copy_(h_params, non_blocking=True)
+    g1.record(stream)
+    sync_all()
+    h2d_gbs = B * P * 8 / (g0.elapsed_time(g1) * 1e-3) / 1e9
+    if world > 1:
+        tt = torch.tensor([h2d_gbs, -h2d_gbs], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MIN)
+        h2d_min, h2d_max = tt[0].item(), -tt[1].item()
+    else:
+        h2d_min = h2d_max = h2d_gbs
+
     caller_configs = None
     if not args.no_configs:
         # free the sweep's 1 GB of parameter buffers first; the callers below allocate their own state
@@ -454,7 +470,9 @@ def main():
                "ms_per_step": ms_kernel / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                "dtype": "f64", "data": "synthetic", "config": workload_config(world, B),
                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * P * 8, "d2h_bytes_per_step": B * 12,
-                       "ms_per_step": ms_e2e / args.steps},
+                       "ms_per_step": ms_e2e / args.steps,
+                       "h2d_gbs_per_rank_all_ranks_copying": {"min": h2d_min, "max": h2d_max,
+                                                              "needed_to_hide_the_copy": B * P * 8 / (ms_kernel / args.steps * 1e-3) / 1e9}},
                "gpu_launches": int(launches1 - launches0),
                "gpu_launches_e2e": int(launches2 - launches1),
                "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,

@@ -23,7 +23,12 @@
 #define SEPAIHRD_SPLIT_THREADS 384                 // 6 warp pairs per block, one block per SM: <= 170 registers per thread
 #endif
 #ifndef SEPAIHRD_E2E_DEFAULT_SPLIT
-#define SEPAIHRD_E2E_DEFAULT_SPLIT 128, 32, 8      // measured best on a B200 with PCIe 5 (tools/e2e_split.py); chunk ends of the host-buffer evaluation at B/d for each d listed (descending)
+// Chunk ends of the host-buffer evaluation at B/d for each d listed (descending): every chunk is 3x the one before it.  The kernel
+// consumes a set in ~83 ns; a PCIe 5 x16 link alone delivers one in ~9 ns, but with 8 ranks copying at once a rank gets 23-35 GB/s
+// (~20 ns per set, measured: bench.py e2e.h2d_gbs_per_rank_all_ranks_copying), so a chunk's copy hides under the previous chunk's
+// kernel only if it is at most ~4x larger.  Round 1's split (128, 32, 8: last chunk 9x the one before) was right for one GPU and
+// exposed 5-10 ms of copy per step at 8 GPUs; this one measures 87.60 ms per 1M-set step on one GPU (87.76 before).
+#define SEPAIHRD_E2E_DEFAULT_SPLIT 243, 81, 27, 9, 3
 #endif
 
 namespace {
@@ -109,8 +114,9 @@ struct sepaihrd_ctx {
     cudaStream_t own_stream = nullptr;
     cudaStream_t copy_stream = nullptr;   // host-pointer entry points: H2D / early D2H next to the compute stream
     cudaStream_t stream2 = nullptr;       // host-pointer evaluation: odd chunks run here, so a chunk's first blocks start while the previous chunk's last warps drain
-    cudaEvent_t ev_chunk[4] = {nullptr, nullptr, nullptr, nullptr};
-    cudaEvent_t ev_copy[4] = {nullptr, nullptr, nullptr, nullptr};
+    static constexpr int MAX_CHUNKS = 8;
+    cudaEvent_t ev_chunk[MAX_CHUNKS] = {};
+    cudaEvent_t ev_copy[MAX_CHUNKS] = {};
     cudaStream_t stream = nullptr;
     int num_sms = 0;
     // scratch for the host-pointer entry points (grown on demand)
@@ -555,8 +561,8 @@ sepaihrd_rc create_impl(const sepaihrd_problem* pb, int n_user, int n, int32_t d
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking);
-    for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&ctx->ev_chunk[i], cudaEventDisableTiming);
-    for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&ctx->ev_copy[i], cudaEventDisableTiming);
+    for (int i = 0; i < sepaihrd_ctx::MAX_CHUNKS && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&ctx->ev_chunk[i], cudaEventDisableTiming);
+    for (int i = 0; i < sepaihrd_ctx::MAX_CHUNKS && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&ctx->ev_copy[i], cudaEventDisableTiming);
     if (e != cudaSuccess) {
         std::string msg = std::string("CUDA setup failed: ") + cudaGetErrorString(e);
         sepaihrd_destroy(ctx);
@@ -588,8 +594,8 @@ void sepaihrd_destroy(sepaihrd_ctx* ctx) {
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
-    for (int i = 0; i < 4; ++i) if (ctx->ev_chunk[i]) cudaEventDestroy(ctx->ev_chunk[i]);
-    for (int i = 0; i < 4; ++i) if (ctx->ev_copy[i]) cudaEventDestroy(ctx->ev_copy[i]);
+    for (int i = 0; i < sepaihrd_ctx::MAX_CHUNKS; ++i) if (ctx->ev_chunk[i]) cudaEventDestroy(ctx->ev_chunk[i]);
+    for (int i = 0; i < sepaihrd_ctx::MAX_CHUNKS; ++i) if (ctx->ev_copy[i]) cudaEventDestroy(ctx->ev_copy[i]);
     delete ctx;
 }
 
@@ -713,11 +719,13 @@ sepaihrd_rc eval_batch_serial(sepaihrd_ctx* ctx, const double* params, int64_t B
             for (const char* p = e; *p;) { const long d = std::strtol(p, const_cast<char**>(&p), 10); if (d > 1) v.push_back((int)d); while (*p == ',' || *p == ' ') ++p; }
         }
         if (v.empty()) v = {SEPAIHRD_E2E_DEFAULT_SPLIT};
-        if (v.size() > 3) v.resize(3);
+        if (v.size() > (size_t)sepaihrd_ctx::MAX_CHUNKS - 1) v.resize(sepaihrd_ctx::MAX_CHUNKS - 1);
         std::sort(v.begin(), v.end(), [](int a, int b) { return a > b; });
         return v;
     }();
-    int64_t off[5] = {0, B, B, B, B};
+    int64_t off[sepaihrd_ctx::MAX_CHUNKS + 1];
+    off[0] = 0;
+    for (int i = 1; i <= sepaihrd_ctx::MAX_CHUNKS; ++i) off[i] = B;
     int n_chunks = 1;
     if (B >= (1 << 16)) {
         for (int d : split) {

@@ -61,6 +61,10 @@ using sepaihrd_internal::fail_with;
 
 constexpr int MT_N = 624, MT_M = 397;
 constexpr int RNG_THREADS = 128;
+// Block size of the generator kernels: they are latency-bound (a 624-step seeding recurrence per particle), so a shard that
+// does not fill the GPU with 128-thread blocks is spread over more SMs with smaller ones (8,192 particles: 256 blocks of one
+// warp instead of 64 blocks of four -- every SM gets work and a block's generator states fit its L1).
+inline int rng_block(long long local) { return local <= 148LL * 32 * 4 ? 32 : (local <= 148LL * 64 * 4 ? 64 : RNG_THREADS); }
 
 // std::mt19937, one generator per thread.  The 624-word state is a per-thread array in LOCAL memory: the hardware interleaves
 // local memory by lane, so word i of the 32 generators of a warp is one coalesced 128-byte line, served from L1/L2.  (v10
@@ -118,7 +122,7 @@ __global__ void __launch_bounds__(RNG_THREADS) swarm_init_kernel(long long local
                                                                  const double* __restrict__ lb, const double* __restrict__ ub,
                                                                  const double* __restrict__ init, double* __restrict__ pos,
                                                                  double* __restrict__ vel) {
-    const long long li = blockIdx.x * (long long)RNG_THREADS + threadIdx.x;
+    const long long li = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (li >= local) return;
     const long long gi = offset + li;
     Mt19937 rng;
@@ -142,7 +146,7 @@ __global__ void __launch_bounds__(RNG_THREADS) swarm_step_kernel(long long local
                                                                  const double* __restrict__ gbest, const double* __restrict__ pbest,
                                                                  double omega, double c1, double c2, double* __restrict__ pos,
                                                                  double* __restrict__ vel) {
-    const long long li = blockIdx.x * (long long)RNG_THREADS + threadIdx.x;
+    const long long li = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (li >= local) return;
     Mt19937 rng;
     rng.seed(seeds[offset + li]);
@@ -341,8 +345,9 @@ sepaihrd_rc sepaihrd_swarm_init(sepaihrd_swarm* s, const uint32_t* seeds, const 
     }
     s->evaluated_once = false;
     if (s->local > 0) {
-        const unsigned blocks = (unsigned)((s->local + RNG_THREADS - 1) / RNG_THREADS);
-        swarm_init_kernel<<<blocks, RNG_THREADS, 0, st>>>(s->local, s->offset, s->P, s->d_seeds, s->d_lb, s->d_ub,
+        const int threads = rng_block(s->local);
+        const unsigned blocks = (unsigned)((s->local + threads - 1) / threads);
+        swarm_init_kernel<<<blocks, threads, 0, st>>>(s->local, s->offset, s->P, s->d_seeds, s->d_lb, s->d_ub,
                                                                  initial ? s->d_init : nullptr, s->d_pos, s->d_vel);
         SW_TRY(cudaGetLastError());
         sepaihrd_internal::count_launches(s->ctx, 1);
@@ -393,8 +398,9 @@ sepaihrd_rc sepaihrd_swarm_step(sepaihrd_swarm* s, const uint32_t* seeds, double
     for (int k = 0; k < s->P; ++k) s->h_gbest[k] = global_best[k];
     SW_TRY(cudaMemcpyAsync(s->d_gbest, s->h_gbest, sizeof(double) * s->P, cudaMemcpyHostToDevice, st));
     if (s->local > 0) {
-        const unsigned blocks = (unsigned)((s->local + RNG_THREADS - 1) / RNG_THREADS);
-        swarm_step_kernel<<<blocks, RNG_THREADS, 0, st>>>(s->local, s->offset, s->P, s->d_seeds, s->d_lb, s->d_ub, s->d_gbest, s->d_pbest,
+        const int threads = rng_block(s->local);
+        const unsigned blocks = (unsigned)((s->local + threads - 1) / threads);
+        swarm_step_kernel<<<blocks, threads, 0, st>>>(s->local, s->offset, s->P, s->d_seeds, s->d_lb, s->d_ub, s->d_gbest, s->d_pbest,
                                                                  omega, c1, c2, s->d_pos, s->d_vel);
         SW_TRY(cudaGetLastError());
         sepaihrd_internal::count_launches(s->ctx, 1);
@@ -456,8 +462,9 @@ sepaihrd_rc sepaihrd_swarm_init_async(sepaihrd_swarm* s, const double* initial) 
     swarm_reset_best_kernel<<<1, 1, 0, st>>>(s->d_gbest_val);
     SW_TRY(cudaGetLastError());
     if (s->local > 0) {
-        const unsigned blocks = (unsigned)((s->local + RNG_THREADS - 1) / RNG_THREADS);
-        swarm_init_kernel<<<blocks, RNG_THREADS, 0, st>>>(s->local, s->offset, s->P, s->d_seed_sets, s->d_lb, s->d_ub,
+        const int threads = rng_block(s->local);
+        const unsigned blocks = (unsigned)((s->local + threads - 1) / threads);
+        swarm_init_kernel<<<blocks, threads, 0, st>>>(s->local, s->offset, s->P, s->d_seed_sets, s->d_lb, s->d_ub,
                                                                  initial ? s->d_init : nullptr, s->d_pos, s->d_vel);
         SW_TRY(cudaGetLastError());
     }
@@ -515,8 +522,9 @@ sepaihrd_rc sepaihrd_swarm_step_async(sepaihrd_swarm* s, int32_t iteration, doub
     const sepaihrd_internal::Dims d = sepaihrd_internal::dims(s->ctx);
     SW_TRY(cudaSetDevice(d.device));
     if (s->local > 0) {
-        const unsigned blocks = (unsigned)((s->local + RNG_THREADS - 1) / RNG_THREADS);
-        swarm_step_kernel<<<blocks, RNG_THREADS, 0, sepaihrd_internal::stream(s->ctx)>>>(
+        const int threads = rng_block(s->local);
+        const unsigned blocks = (unsigned)((s->local + threads - 1) / threads);
+        swarm_step_kernel<<<blocks, threads, 0, sepaihrd_internal::stream(s->ctx)>>>(
             s->local, s->offset, s->P, s->d_seed_sets + (size_t)(iteration + 1) * (size_t)s->swarm_size, s->d_lb, s->d_ub, s->d_gbest, s->d_pbest,
             omega, c1, c2, s->d_pos, s->d_vel);
         SW_TRY(cudaGetLastError());
