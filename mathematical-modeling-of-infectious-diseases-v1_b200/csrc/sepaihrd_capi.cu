@@ -1013,6 +1013,9 @@ sepaihrd_rc sepaihrd_measure_fp64_peak(int32_t device, double* out_dfma_per_seco
 namespace sepaihrd_internal {
 Dims dims(const sepaihrd_ctx* ctx) { return Dims{ctx->n, ctx->K, ctx->runup_offset, ctx->n_nonneg, ctx->P, ctx->device, ctx->n_user}; }
 cudaStream_t stream(const sepaihrd_ctx* ctx) { return ctx->stream; }
+cudaStream_t copy_stream(const sepaihrd_ctx* ctx) { return ctx->copy_stream; }
+cudaEvent_t* copy_events(sepaihrd_ctx* ctx) { return ctx->ev_copy; }
+cudaEvent_t* chunk_events(sepaihrd_ctx* ctx) { return ctx->ev_chunk; }
 sepaihrd_rc fail_with(sepaihrd_rc rc, const char* msg) { return fail(rc, msg); }
 const double* lower_bounds(const sepaihrd_ctx* ctx) { return ctx->blob.data() + ctx->kp.o_lo; }
 const double* upper_bounds(const sepaihrd_ctx* ctx) { return ctx->blob.data() + ctx->kp.o_hi; }
@@ -1039,8 +1042,19 @@ void release_scratch(sepaihrd_ctx* ctx) {
         ctx->scratch[i] = nullptr; ctx->scratch_bytes[i] = 0;
     }
 }
-sepaihrd_rc simulate_observed_draw_minor(sepaihrd_ctx* ctx, const double* d_params, long long B, long long ld, const double* d_init,
-                                         double* d_out, unsigned* d_status) {
-    return simulate_device_impl(ctx, d_params, B, ld, d_init, 0, SEPAIHRD_TRAJ_OBSERVED, 1, d_out, d_status, true);
+sepaihrd_rc simulate_ppc_series(sepaihrd_ctx* ctx, const double* d_params, long long b0, long long nb, long long B_total, long long ld,
+                                const double* d_init, double* d_series, unsigned* d_status) {
+    if (!ctx || !d_series || !d_params || !d_init) return fail(SEPAIHRD_ERR_INVALID_ARGUMENT, "null argument");
+    std::lock_guard<std::recursive_mutex> lock(ctx->mu);
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    sepaihrd::KParams kp = ctx->kp;
+    kp.constraint_mode = ctx->constraint_mode;
+    kp.params = d_params + b0 * ld; kp.B = nb; kp.ld = ld;
+    kp.out_ll = nullptr; kp.out_status = d_status + b0; kp.out_steps = nullptr;
+    kp.out_traj = d_series; kp.traj_what = sepaihrd::TRAJ_PPC_SERIES; kp.traj_stride = 1; kp.traj_rows = ctx->n_nonneg;
+    kp.traj_draw_minor = 1;
+    kp.ppc_b0 = b0; kp.ppc_B = B_total;
+    kp.init_states = d_init; kp.init_stride = 0;
+    return launch(ctx, kp, sepaihrd::MODE_TRAJ);
 }
 }  // namespace sepaihrd_internal

@@ -12,6 +12,9 @@ namespace sepaihrd_internal {
 struct Dims { int n, K, runup_offset, n_nonneg, P, device, n_user; };   // n: age classes the kernels run with (n_user zero-padded to 4 or 16); n_nonneg: output times >= 0 (the last ones)
 Dims dims(const sepaihrd_ctx* ctx);
 cudaStream_t stream(const sepaihrd_ctx* ctx);
+cudaStream_t copy_stream(const sepaihrd_ctx* ctx);     // the ctx's H2D / D2H stream next to its compute stream
+cudaEvent_t* copy_events(sepaihrd_ctx* ctx);           // [8] timing-free events for chunked copies (callers hold the ctx lock)
+cudaEvent_t* chunk_events(sepaihrd_ctx* ctx);          // [8]
 sepaihrd_rc fail_with(sepaihrd_rc rc, const char* msg);
 const double* lower_bounds(const sepaihrd_ctx* ctx);   // host copies, [P], as given at creation
 const double* upper_bounds(const sepaihrd_ctx* ctx);
@@ -23,8 +26,11 @@ std::unique_lock<std::recursive_mutex> lock(sepaihrd_ctx* ctx);
 // allocation fails.  sepaihrd_release_scratch() drops them all.
 void* scratch(sepaihrd_ctx* ctx, int slot, size_t bytes);
 void release_scratch(sepaihrd_ctx* ctx);          // kernels another translation unit enqueued on the ctx stream
-// D, CumH, CumICU of B draws in the DRAW-MINOR layout [K][3n][B] (device pointers); d_init: one shared state or null
-sepaihrd_rc simulate_observed_draw_minor(sepaihrd_ctx* ctx, const double* d_params, long long B, long long ld, const double* d_init,
-                                         double* d_out, unsigned* d_status);
+// The six posterior-predictive series of B draws straight from the trajectory kernel: out[6][T][n][B] (T = output days t >= 0),
+// all draws from the one state d_init (quirk Q9).  Failed draws are NaN in every series.
+// One launch covers draws [b0, b0 + nb) of B_total (d_params, d_status and the columns of d_series are indexed by the GLOBAL draw),
+// so the caller can feed the draws in chunks while later ones are still on their way from the host.
+sepaihrd_rc simulate_ppc_series(sepaihrd_ctx* ctx, const double* d_params, long long b0, long long nb, long long B_total, long long ld,
+                                const double* d_init, double* d_series, unsigned* d_status);
 
 }  // namespace sepaihrd_internal

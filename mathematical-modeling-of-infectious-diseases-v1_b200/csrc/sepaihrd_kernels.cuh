@@ -43,6 +43,10 @@ constexpr int NDYN = 7;                            // S E P A I H ICU feed the R
 constexpr int NPAS = 4;                            // R D CumH CumICU do not
 
 enum { MODE_LL = 0, MODE_TRAJ = 1 };
+// internal trajectory selector (next to SEPAIHRD_TRAJ_FULL / _OBSERVED): the six posterior-predictive series on the output days
+// t >= 0, draws fastest -- out[6][T][n][B]: daily hospitalisations, ICU admissions, deaths (first differences of CumH / CumICU / D
+// clamped at 0, ResultAggregator.cpp:292-335) and their running sums (.cpp:337-351).  The quantile pass reads them column by column.
+constexpr int TRAJ_PPC_SERIES = 2;
 
 // Everything the kernel needs besides the staged blob; passed by value (constant bank).
 struct KParams {
@@ -74,6 +78,7 @@ struct KParams {
     double* out_traj;          // MODE_TRAJ: [B][traj_rows][W], or [traj_rows][W][B] when traj_draw_minor
     int traj_what, traj_stride, traj_rows;
     int traj_draw_minor;       // draws fastest: the layout the posterior-predictive quantile pass reads column by column
+    long long ppc_b0, ppc_B;   // TRAJ_PPC_SERIES: this launch holds draws [ppc_b0, ppc_b0 + B) of ppc_B (chunked launches overlap the H2D copy)
     const double* init_states; // optional [B][11n] (or one shared state when init_stride == 0): Simulator::run semantics
     long long init_stride;
     long long tiles;           // ceil(B / sets_per_warp)
@@ -626,7 +631,6 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) sepaihrd_batch_kernel(cons
             t_rs = kp.traj_draw_minor ? (size_t)W * (size_t)kp.B : (size_t)W;
             t_cs = kp.traj_draw_minor ? (size_t)kp.B : (size_t)1;
         }
-
         bool alive = (status == 0);
         // ---- integrate_times: observer at every grid point, adaptive steps in between ---------------------
         double dt = kp.dt_hint;
@@ -651,6 +655,28 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) sepaihrd_batch_kernel(cons
             for (int c = 0; c < NPAS; ++c) k1[NDYN + c] = p0[c];
         }
 
+        // TRAJ_PPC_SERIES: element (series s, day r, age) of this draw sits at ((s T + r) n + age) B + b
+        const size_t ppc_day = (size_t)n * (size_t)kp.ppc_B, ppc_series = (size_t)kp.traj_rows * ppc_day;
+        auto ppc_observe = [&](int idx, double& ph, double& pi, double& pd, double& rh, double& ri, double& rd) {
+            // ppc_series rule: d = max(0, v - prev), a NaN value stays NaN (kept out of the quantiles); run += d
+            const double vh = x[9], vi = x[10], vd = x[8];
+            double dh = vh - ph, di = vi - pi, dd = vd - pd;
+            dh = (0.0 < dh) ? dh : 0.0; di = (0.0 < di) ? di : 0.0; dd = (0.0 < dd) ? dd : 0.0;
+            if (vh != vh) dh = vh;
+            if (vi != vi) di = vi;
+            if (vd != vd) dd = vd;
+            ph = vh; pi = vi; pd = vd;
+            const int r = idx - kp.runup_offset;
+            if (r >= 0) {
+                rh += dh; ri += di; rd += dd;
+                if (have && alive) {
+                    double* o = kp.out_traj + ((size_t)r * n + age) * (size_t)kp.ppc_B + (size_t)(kp.ppc_b0 + b);
+                    o[0 * ppc_series] = dh; o[1 * ppc_series] = di; o[2 * ppc_series] = dd;
+                    o[3 * ppc_series] = rh; o[4 * ppc_series] = ri; o[5 * ppc_series] = rd;
+                }
+            }
+        };
+
         if constexpr (LOOP == 6 && !STRICT) {
         // ================= LOOP 6 (FAST): one short decision section per attempt ============================
         // Same arithmetic as the loop below; what changes is the control flow around the attempt body:
@@ -674,7 +700,9 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) sepaihrd_batch_kernel(cons
             if (MODE == MODE_LL && have && age == 0 && kp.out_steps) { kp.out_steps[(b * K + idx) * 2] = n_acc; kp.out_steps[(b * K + idx) * 2 + 1] = n_rej; }
 #endif
             if (MODE == MODE_TRAJ) {
-                if (have && alive && (idx % kp.traj_stride == 0)) {
+                if (kp.traj_what == TRAJ_PPC_SERIES) {
+                    ppc_observe(idx, prev_h, prev_i, prev_d, ll_acc_h, ll_acc_i, ll_acc_d);     // the likelihood accumulators are free here: running sums
+                } else if (have && alive && (idx % kp.traj_stride == 0)) {
                     double* row = traj_out + (size_t)(idx / kp.traj_stride) * t_rs;
                     if (kp.traj_what == SEPAIHRD_TRAJ_FULL) {
 #pragma unroll
@@ -866,7 +894,9 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) sepaihrd_batch_kernel(cons
 #endif
             // ---- observer -----------------------------------------------------------------------------
             if (MODE == MODE_TRAJ) {
-                if (have && alive && (idx % kp.traj_stride == 0)) {
+                if (kp.traj_what == TRAJ_PPC_SERIES) {
+                    ppc_observe(idx, prev_h, prev_i, prev_d, ll_acc_h, ll_acc_i, ll_acc_d);
+                } else if (have && alive && (idx % kp.traj_stride == 0)) {
                     double* row = traj_out + (size_t)(idx / kp.traj_stride) * t_rs;
                     if (kp.traj_what == SEPAIHRD_TRAJ_FULL) {
 #pragma unroll
@@ -1008,8 +1038,13 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) sepaihrd_batch_kernel(cons
         } else {
             if (have && status != 0) {   // failed sets: NaN-fill every row
                 const double qnan = __longlong_as_double(0x7ff8000000000000LL);
-                for (int r = 0; r < kp.traj_rows; ++r)
-                    for (int w = age; w < W; w += NA) traj_out[(size_t)r * t_rs + (size_t)w * t_cs] = qnan;
+                if (kp.traj_what == TRAJ_PPC_SERIES) {
+                    for (int r = 0; r < kp.traj_rows; ++r)
+                        for (int sidx = 0; sidx < 6; ++sidx) kp.out_traj[(size_t)sidx * ppc_series + ((size_t)r * n + age) * (size_t)kp.ppc_B + (size_t)(kp.ppc_b0 + b)] = qnan;
+                } else {
+                    for (int r = 0; r < kp.traj_rows; ++r)
+                        for (int w = age; w < W; w += NA) traj_out[(size_t)r * t_rs + (size_t)w * t_cs] = qnan;
+                }
             }
             if (have && age == 0) {
                 if (kp.out_status) kp.out_status[b] = status;

@@ -10,17 +10,18 @@
 // estimator (.cpp:28-33), whose result depends on the order of the draws; here every quantile is the EXACT sample
 // quantile with linear interpolation between order statistics (numpy's default).
 //
-// Data flow (all in HBM, HBM-bound integer/byte-style work -- no tensor cores):
-//   trajectory kernel --[K][3n][B], draws fastest--> series kernel --[6][T][n][B]--> per column: the <= 2Q order statistics
-//   the quantiles need, SELECTED by ppc_select_kernel (up to 8 probabilities) or read off a cub segmented radix sort (more)
-//   --[6][T][n][Q]--> host
+// Data flow (HBM-bound byte work -- no tensor cores): the trajectory kernel itself forms the six series while it integrates
+// (TRAJ_PPC_SERIES: the incidences and running sums are three subtractions and three additions per output day on values it
+// holds in registers anyway) and writes them draws-fastest, out[6][T][n][B]; ppc_select_kernel then SELECTS, per (series, day,
+// age) column, the <= 2Q order statistics the quantiles need -- 8 probabilities per sweep group, any number of probabilities
+// in groups -- and writes [6][T][n][Q].  Round 1 wrote D / CumH / CumICU trajectories (3.1 GB for 100 k draws x 4 ages), read
+// them back in a series kernel that wrote 5.9 GB, and fell back to cub's segmented radix sort above 8 probabilities; now the
+// trajectories are never materialised, the series are written once and no library sort is left.
 #include <cmath>
 #include <cstdint>
 #include <cstdlib>
 #include <algorithm>
 #include <vector>
-
-#include <cub/device/device_segmented_radix_sort.cuh>
 
 #include "sepaihrd_internal.h"
 
@@ -32,61 +33,6 @@ namespace {
         if (e__ != cudaSuccess) { cleanup(); return sepaihrd_internal::fail_with(SEPAIHRD_ERR_CUDA, cudaGetErrorString(e__)); } \
     } while (0)
 
-// One thread per (draw b, stream, age): walks the output days t >= 0 in order.  Reads and writes are coalesced over b.
-//   traj   [K][3n][B]: w = 0*n+age -> D, 1*n+age -> CumH, 2*n+age -> CumICU   (TRAJ_OBSERVED order)
-//   series [6][T][n][B]: daily hosp, daily icu, daily deaths, cumulative hosp, cumulative icu, cumulative deaths
-__global__ void ppc_series_kernel(const double* __restrict__ traj, const double* __restrict__ init_state, int n, int first_pos, int T,
-                                  long long B, double* __restrict__ series) {
-    const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (b >= B) return;
-    const int stream = blockIdx.y / n, age = blockIdx.y % n;      // stream: 0 hosp, 1 icu, 2 deaths
-    const int w = ((stream == 0) ? 1 : (stream == 1) ? 2 : 0) * n + age;
-    const int comp = (stream == 0) ? 9 : (stream == 1) ? 10 : 8;
-    const size_t W = (size_t)3 * n;
-    double prev = (first_pos > 0) ? traj[((size_t)(first_pos - 1) * W + w) * B + b] : init_state[comp * n + age];
-    double run = 0.0;
-    double* daily = series + (((size_t)stream * T) * n + age) * B + b;
-    double* cum = series + (((size_t)(3 + stream) * T) * n + age) * B + b;
-    const size_t step = (size_t)n * B;
-    for (int t = 0; t < T; ++t) {
-        const double v = traj[((size_t)(first_pos + t) * W + w) * B + b];
-        double d = v - prev;
-        d = (0.0 < d) ? d : 0.0;          // std::max(0.0, diff)
-        if (v != v) d = v;                // a failed draw is NaN-filled by the trajectory kernel: keep it out of the quantiles
-        prev = v;
-        run += d;
-        daily[(size_t)t * step] = d;
-        cum[(size_t)t * step] = run;
-    }
-}
-
-// One warp per sorted column: number of non-NaN entries by binary search (NaNs sort last), then linear interpolation.
-__global__ void ppc_quantile_kernel(const double* __restrict__ sorted, long long B, long long n_cols, int Q, const double* __restrict__ probs,
-                                    double* __restrict__ out) {
-    const long long col = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (col >= n_cols) return;
-    const double* v = sorted + (size_t)col * B;
-    long long lo = 0, hi = B;             // first index whose value is NaN
-    while (lo < hi) {
-        const long long mid = (lo + hi) >> 1;
-        if (v[mid] != v[mid]) hi = mid; else lo = mid + 1;
-    }
-    const long long cnt = lo;
-    for (int q = 0; q < Q; ++q) {
-        double r = nan("");
-        if (cnt > 0) {
-            const double h = (double)(cnt - 1) * probs[q];
-            long long i0 = (long long)floor(h);
-            if (i0 < 0) i0 = 0;
-            if (i0 > cnt - 1) i0 = cnt - 1;
-            const long long i1 = (i0 + 1 < cnt) ? i0 + 1 : i0;
-            const double a = v[i0], c = v[i1];
-            r = a + (h - (double)i0) * (c - a);
-        }
-        out[(size_t)col * Q + q] = r;
-    }
-}
-
 // ---- exact order statistics without sorting -------------------------------------------------------------------------------
 // A column needs the values at <= 2Q ranks (the two neighbours of every quantile position), not its full order.  One block per
 // column: a first sweep finds the count, minimum and maximum of the non-NaN keys (everything above their common bit prefix is
@@ -95,7 +41,8 @@ __global__ void ppc_quantile_kernel(const double* __restrict__ sorted, long long
 // the bits are used up; the survivors are gathered into shared memory and the wanted rank is picked by counting.  A column is
 // read 3-5 times (its later sweeps mostly from L2) instead of being read and written 8 times by the radix sort.
 // Keys: the usual order-preserving map of a double's bits to an unsigned integer; NaNs (failed draws) are left out.
-constexpr int SEL_THREADS = 512, SEL_MAXT = 16, SEL_CAP = 192;
+constexpr int SEL_MAXT = 16, SEL_CAP = 192;
+constexpr int PPC_DEFAULT_GRID = 4 * 148, PPC_DEFAULT_THREADS = 1024;
 
 __device__ __forceinline__ unsigned long long sel_key(double x) {
     const unsigned long long b = (unsigned long long)__double_as_longlong(x);
@@ -103,6 +50,7 @@ __device__ __forceinline__ unsigned long long sel_key(double x) {
 }
 // SEL_UNROLL coalesced loads issued together (the sweeps are latency-bound otherwise); past the end: NaN, which every sweep skips
 constexpr int SEL_UNROLL = 4;
+template <int SEL_THREADS>
 __device__ __forceinline__ void sel_load(const double* __restrict__ v, long long i0, long long B, double (&xs)[SEL_UNROLL]) {
 #pragma unroll
     for (int u = 0; u < SEL_UNROLL; ++u) {
@@ -115,8 +63,12 @@ __device__ __forceinline__ double sel_value(unsigned long long k) {
     return __longlong_as_double((long long)b);
 }
 
+// Q probabilities probs[0..Q) of this launch land in out[col * Q_total + q_first + q]
+template <int SEL_THREADS>
 __global__ void __launch_bounds__(SEL_THREADS) ppc_select_kernel(const double* __restrict__ series, long long B, long long n_cols, int Q,
-                                                                 const double* __restrict__ probs, double* __restrict__ out) {
+                                                                 const double* __restrict__ probs, double* __restrict__ out_all, int Q_total,
+                                                                 int q_first) {
+    probs += q_first;
     __shared__ unsigned hist[SEL_MAXT][256];
     __shared__ unsigned long long cand[SEL_MAXT][SEL_CAP];
     __shared__ unsigned cand_n[SEL_MAXT];
@@ -124,7 +76,8 @@ __global__ void __launch_bounds__(SEL_THREADS) ppc_select_kernel(const double* _
     __shared__ long long t_want[SEL_MAXT], t_rank[SEL_MAXT];
     __shared__ unsigned t_size[SEL_MAXT];
     __shared__ int t_bucket[SEL_MAXT];
-    __shared__ unsigned long long s_min, s_max;
+    __shared__ unsigned long long s_min, s_max;          // AND and OR of the column's keys
+    __shared__ unsigned s_bloom[128];                    // which 12-bit prefix tails belong to a live bucket (4096 bits)
     __shared__ unsigned long long s_cnt;
     __shared__ int n_targets, n_buckets, s_shift, s_go;
     const int tid = threadIdx.x;
@@ -132,27 +85,27 @@ __global__ void __launch_bounds__(SEL_THREADS) ppc_select_kernel(const double* _
         const double* v = series + (size_t)col * B;
         if (tid == 0) { s_min = ~0ULL; s_max = 0ULL; s_cnt = 0ULL; }
         __syncthreads();
-        {   // sweep 0: how many non-NaN keys, and between which bounds
+        {   // sweep 0: how many non-NaN keys, and which leading bits they all share (AND / OR of the keys: two logic ops per key,
+            // where a minimum and a maximum of 64-bit keys cost a dozen)
             unsigned long long lo = ~0ULL, hi = 0ULL, c = 0ULL;
             for (long long i0 = tid; i0 < B; i0 += SEL_UNROLL * SEL_THREADS) {
                 double xs[SEL_UNROLL];
-                sel_load(v, i0, B, xs);
+                sel_load<SEL_THREADS>(v, i0, B, xs);
 #pragma unroll
                 for (int u = 0; u < SEL_UNROLL; ++u) {
                     const double x = xs[u];
-                    if (x == x) { const unsigned long long k = sel_key(x); lo = (k < lo) ? k : lo; hi = (k > hi) ? k : hi; ++c; }
+                    if (x == x) { const unsigned long long k = sel_key(x); lo &= k; hi |= k; ++c; }
                 }
             }
             for (int o = 16; o >= 1; o >>= 1) {
-                const unsigned long long lo2 = __shfl_xor_sync(0xffffffffu, lo, o), hi2 = __shfl_xor_sync(0xffffffffu, hi, o);
-                lo = (lo2 < lo) ? lo2 : lo; hi = (hi2 > hi) ? hi2 : hi; c += __shfl_xor_sync(0xffffffffu, c, o);
+                lo &= __shfl_xor_sync(0xffffffffu, lo, o); hi |= __shfl_xor_sync(0xffffffffu, hi, o); c += __shfl_xor_sync(0xffffffffu, c, o);
             }
-            if ((tid & 31) == 0) { atomicMin(&s_min, lo); atomicMax(&s_max, hi); atomicAdd(&s_cnt, c); }
+            if ((tid & 31) == 0) { atomicAnd(&s_min, lo); atomicOr(&s_max, hi); atomicAdd(&s_cnt, c); }
         }
         __syncthreads();
         const long long cnt = (long long)s_cnt;
         if (cnt == 0) {                                            // no valid draw: every quantile is NaN
-            for (int q = tid; q < Q; q += SEL_THREADS) out[(size_t)col * Q + q] = nan("");
+            for (int q = tid; q < Q; q += SEL_THREADS) out_all[(size_t)col * Q_total + q_first + q] = nan("");
             __syncthreads();
             continue;
         }
@@ -183,6 +136,7 @@ __global__ void __launch_bounds__(SEL_THREADS) ppc_select_kernel(const double* _
             }
         }
         __syncthreads();
+        const int first_shift = s_shift;
         while (true) {
             if (tid == 0) {
                 // go on while some bucket is still too large for the gather and bits remain; buckets = distinct prefixes
@@ -200,36 +154,59 @@ __global__ void __launch_bounds__(SEL_THREADS) ppc_select_kernel(const double* _
             }
             __syncthreads();
             if (!s_go) break;
-            const int shift = s_shift, nshift = (shift > 8) ? shift - 8 : 0, width = shift - nshift, nb = n_buckets;
-            for (int i = tid; i < nb * 256; i += SEL_THREADS) hist[i >> 8][i & 255] = 0u;
+            // digit width: as many bits as the 4096 histogram cells allow for the buckets alive -- 12 bits while all ranks still
+            // share one bucket (the first step: 100 k keys fall to ~25 per cell, so the usual column needs no second step)
+            const int nb = n_buckets;
+            const int dig = (nb == 1) ? 12 : (nb <= 4) ? 10 : 8;
+            const int shift = s_shift, nshift = (shift > dig) ? shift - dig : 0, width = shift - nshift;
+            unsigned* hflat = &hist[0][0];
+            for (int i = tid; i < (nb << width); i += SEL_THREADS) hflat[i] = 0u;
+            if (tid < 128) s_bloom[tid] = 0u;
             __syncthreads();
+            if (tid < nb) atomicOr(&s_bloom[(unsigned)(b_prefix[tid] & 4095ULL) >> 5], 1u << (unsigned)(b_prefix[tid] & 31ULL));
+            __syncthreads();
+            const bool everyone = (shift == first_shift);      // first step: the prefix is the one ALL keys share, nothing to test
             for (long long i0 = tid; i0 < B; i0 += SEL_UNROLL * SEL_THREADS) {
                 double xs[SEL_UNROLL];
-                sel_load(v, i0, B, xs);
+                sel_load<SEL_THREADS>(v, i0, B, xs);
 #pragma unroll
                 for (int u = 0; u < SEL_UNROLL; ++u) {
                     const double x = xs[u];
                     if (x == x) {
                         const unsigned long long k = sel_key(x);
-                        const unsigned long long hi = (shift < 64) ? (k >> shift) : 0ULL;
-                        const unsigned d = (unsigned)((k >> nshift) & ((1ULL << width) - 1ULL));
-                        for (int a = 0; a < nb; ++a) if (hi == b_prefix[a]) atomicAdd(&hist[a][d], 1u);
+                        const unsigned d = (unsigned)(k >> nshift) & ((1u << width) - 1u);
+                        if (everyone) {
+                            atomicAdd(&hflat[d], 1u);
+                        } else {
+                            const unsigned long long hi = (shift < 64) ? (k >> shift) : 0ULL;
+                            const unsigned tail = (unsigned)hi & 4095u;
+                            if ((s_bloom[tail >> 5] >> (tail & 31u)) & 1u)
+                                for (int a = 0; a < nb; ++a) if (hi == b_prefix[a]) atomicAdd(&hflat[((unsigned)a << width) + d], 1u);
+                        }
                     }
                 }
             }
             __syncthreads();
-            if (tid < n_targets) {
-                const int a = t_bucket[tid];
-                long long k = t_rank[tid];
-                unsigned d = 0;
-                for (; d < (1u << width) - 1u; ++d) {
-                    const unsigned hcount = hist[a][d];
-                    if (k < (long long)hcount) break;
-                    k -= hcount;
+            // one warp per wanted rank: the cell that holds it (lanes sum 1/32 of the cells each, a shuffle scan finds the lane,
+            // the lane walks its cells)
+            for (int t = tid >> 5; t < n_targets; t += SEL_THREADS / 32) {
+                const int lane = tid & 31;
+                const unsigned* h = hflat + ((unsigned)t_bucket[t] << width);
+                const int cells = 1 << width, per = (cells + 31) / 32, c0 = lane * per, c1 = (c0 + per < cells) ? c0 + per : cells;
+                long long mine = 0;
+                for (int c = c0; c < c1; ++c) mine += h[c];
+                long long incl = mine;
+                for (int o = 1; o < 32; o <<= 1) { const long long up = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += up; }
+                const long long k = t_rank[t], before = incl - mine;
+                const bool owner = (k >= before && k < incl) || (lane == 31 && k >= incl);      // (a rank past the end cannot happen; the last lane would take it)
+                if (owner) {
+                    long long r = k - before;
+                    int d = c0;
+                    for (; d < c1 - 1; ++d) { const unsigned hc = h[d]; if (r < (long long)hc) break; r -= hc; }
+                    t_prefix[t] = (t_prefix[t] << width) | (unsigned long long)d;
+                    t_rank[t] = r;
+                    t_size[t] = h[d];
                 }
-                t_prefix[tid] = (t_prefix[tid] << width) | d;
-                t_rank[tid] = k;
-                t_size[tid] = hist[a][d];
             }
             __syncthreads();
             if (tid == 0) s_shift = nshift;
@@ -244,18 +221,23 @@ __global__ void __launch_bounds__(SEL_THREADS) ppc_select_kernel(const double* _
         } else {
             const int nb = n_buckets;
             if (tid < nb) cand_n[tid] = 0u;
+            if (tid < 128) s_bloom[tid] = 0u;
+            __syncthreads();
+            if (tid < nb) atomicOr(&s_bloom[(unsigned)(b_prefix[tid] & 4095ULL) >> 5], 1u << (unsigned)(b_prefix[tid] & 31ULL));
             __syncthreads();
             for (long long i0 = tid; i0 < B; i0 += SEL_UNROLL * SEL_THREADS) {
                 double xs[SEL_UNROLL];
-                sel_load(v, i0, B, xs);
+                sel_load<SEL_THREADS>(v, i0, B, xs);
 #pragma unroll
                 for (int u = 0; u < SEL_UNROLL; ++u) {
                     const double x = xs[u];
                     if (x == x) {
                         const unsigned long long k = sel_key(x);
                         const unsigned long long hi = (shift < 64) ? (k >> shift) : 0ULL;
-                        for (int a = 0; a < nb; ++a)
-                            if (hi == b_prefix[a]) { const unsigned pos = atomicAdd(&cand_n[a], 1u); if (pos < (unsigned)SEL_CAP) cand[a][pos] = k; }
+                        const unsigned tail = (unsigned)hi & 4095u;
+                        if ((s_bloom[tail >> 5] >> (tail & 31u)) & 1u)
+                            for (int a = 0; a < nb; ++a)
+                                if (hi == b_prefix[a]) { const unsigned pos = atomicAdd(&cand_n[a], 1u); if (pos < (unsigned)SEL_CAP) cand[a][pos] = k; }
                     }
                 }
             }
@@ -284,15 +266,10 @@ __global__ void __launch_bounds__(SEL_THREADS) ppc_select_kernel(const double* _
                 if (t_want[t] == i0) a = sel_value(t_value[t]);
                 if (t_want[t] == i1) c = sel_value(t_value[t]);
             }
-            out[(size_t)col * Q + q] = a + (h - (double)i0) * (c - a);
+            out_all[(size_t)col * Q_total + q_first + q] = a + (h - (double)i0) * (c - a);
         }
         __syncthreads();
     }
-}
-
-__global__ void ppc_offsets_kernel(long long* off, long long n_cols, long long B) {
-    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (i <= n_cols) off[i] = i * B;
 }
 
 __global__ void ppc_count_valid_kernel(const unsigned* st, long long B, unsigned long long* out) {
@@ -314,7 +291,7 @@ extern "C" sepaihrd_rc sepaihrd_posterior_predictive(sepaihrd_ctx* ctx, const do
     if (n_probs < 1 || n_probs > 64) return fail_with(SEPAIHRD_ERR_INVALID_ARGUMENT, "between 1 and 64 quantile probabilities");
     for (int q = 0; q < n_probs; ++q)
         if (!(probs[q] >= 0.0 && probs[q] <= 1.0)) return fail_with(SEPAIHRD_ERR_INVALID_ARGUMENT, "quantile probabilities must lie in [0, 1]");
-    const int n = d.n, K = d.K, T = d.n_nonneg, first_pos = K - T;
+    const int n = d.n, T = d.n_nonneg;
     if (T <= 0) return fail_with(SEPAIHRD_ERR_INVALID_ARGUMENT, "No non-negative time points for PPC.");   // ResultAggregator.cpp:197-200
     const long long n_cols = (long long)T * n;            // columns per series
     if ((double)n_cols * (double)B > 2.0e9) return fail_with(SEPAIHRD_ERR_UNSUPPORTED, "more than 2e9 values per series: split the draws");
@@ -324,25 +301,18 @@ extern "C" sepaihrd_rc sepaihrd_posterior_predictive(sepaihrd_ctx* ctx, const do
     cudaStream_t s = stream(ctx);
     // work buffers live in the ctx (grow-only scratch slots): repeated aggregations of the same size allocate nothing
     auto cleanup = [] {};
-    const size_t traj_elems = (size_t)K * 3 * n * (size_t)B, col_elems = (size_t)n_cols * (size_t)B;
+    const size_t col_elems = (size_t)n_cols * (size_t)B;
     int slot = 0;
     bool oom = false;
     auto buf = [&](size_t bytes) { void* p = scratch(ctx, slot++, bytes); oom = oom || (p == nullptr); return p; };
     double* d_params = (double*)buf(sizeof(double) * (size_t)B * ld);
     double* d_init = (double*)buf(sizeof(double) * SEPAIHRD_NUM_COMPARTMENTS * n);
-    double* d_traj = (double*)buf(sizeof(double) * traj_elems);
     double* d_series = (double*)buf(sizeof(double) * 6 * col_elems);
-    static const bool force_sort = std::getenv("SEPAIHRD_PPC_SORT") != nullptr;
-    const bool use_select = 2 * n_probs <= SEL_MAXT && !force_sort;
-    double* d_sorted = use_select ? nullptr : (double*)buf(sizeof(double) * col_elems);     // only the sort path needs a second copy of a series
     double* d_probs = (double*)buf(sizeof(double) * n_probs);
     double* d_q = (double*)buf(sizeof(double) * 6 * (size_t)n_cols * n_probs);
     unsigned* d_status = (unsigned*)buf(sizeof(unsigned) * (size_t)B);
-    long long* d_off = (long long*)buf(sizeof(long long) * (size_t)(n_cols + 1));
     unsigned long long* d_cnt = (unsigned long long*)buf(sizeof(unsigned long long));
     if (oom) return fail_with(SEPAIHRD_ERR_OUT_OF_MEMORY, "posterior-predictive work buffers do not fit: split the draws");
-    void* d_tmp = nullptr;
-    PPC_TRY(cudaMemcpyAsync(d_params, params, sizeof(double) * (size_t)B * ld, cudaMemcpyHostToDevice, s));
     // padded age classes (sepaihrd_create): the caller's state has d.n_user classes per compartment, the pass runs with n
     std::vector<double> wide_init;
     if (n != d.n_user) {
@@ -356,39 +326,53 @@ extern "C" sepaihrd_rc sepaihrd_posterior_predictive(sepaihrd_ctx* ctx, const do
     PPC_TRY(cudaMemcpyAsync(d_probs, probs, sizeof(double) * n_probs, cudaMemcpyHostToDevice, s));
     PPC_TRY(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), s));
 
-    // 1. trajectories of D, CumH, CumICU, draws fastest
-    sepaihrd_rc rc = simulate_observed_draw_minor(ctx, d_params, B, ld, d_init, d_traj, d_status);
-    if (rc != SEPAIHRD_OK) { cleanup(); return rc; }
-    // 2. daily incidence + cumulative-from-flows series
+    // 1. the six series, formed by the trajectory kernel while it integrates.  The draws go to the device in growing chunks on a
+    //    copy stream of their own: the kernel of chunk c runs while chunk c + 1 is copied (a draw costs the kernel ~90 ns and the
+    //    link ~10-40 ns, pinned or pageable), so only the first, small copy is exposed.
     {
-        const int threads = 256;
-        dim3 grid((unsigned)((B + threads - 1) / threads), (unsigned)(3 * n));
-        ppc_series_kernel<<<grid, threads, 0, s>>>(d_traj, d_init, n, first_pos, T, B, d_series);
-        PPC_TRY(cudaGetLastError());
-        ppc_count_valid_kernel<<<(unsigned)((B + 255) / 256), 256, 0, s>>>(d_status, B, d_cnt);
-        ppc_offsets_kernel<<<(unsigned)((n_cols + 256) / 256), 256, 0, s>>>(d_off, n_cols, B);
-        PPC_TRY(cudaGetLastError());
+        cudaStream_t copy_stream = sepaihrd_internal::copy_stream(ctx);      // the ctx's own copy stream and chunk events (the ctx lock is held)
+        cudaEvent_t* ev_copy = sepaihrd_internal::copy_events(ctx);          // [8]
+        cudaEvent_t ev_free = sepaihrd_internal::chunk_events(ctx)[0];
+        PPC_TRY(cudaEventRecord(ev_free, s));                         // the copy stream may not overwrite d_params while earlier work on s reads it
+        PPC_TRY(cudaStreamWaitEvent(copy_stream, ev_free, 0));
+        long long ends[8];
+        int nc = 0;
+        // chunk ends at 1, 4 and 16 waves of the trajectory kernel (a wave = every resident warp holding one tile: 148 SMs x 8 warps x
+        // 32 / n draws), so no chunk pays for a mostly empty last wave
+        const long long wave = 148LL * 8 * (32 / n);
+        for (long long w = 1; w <= 16; w *= 4) if (w * wave * 2 <= B) ends[nc++] = w * wave;
+        ends[nc++] = B;
+        long long b0 = 0;
+        for (int c = 0; c < nc; ++c) {
+            // copy and launch alternate: a copy from PAGEABLE memory blocks the host until it is staged, and it should block it
+            // while the previous chunk's kernel is already running
+            PPC_TRY(cudaMemcpyAsync(d_params + b0 * ld, params + b0 * ld, sizeof(double) * (size_t)(ends[c] - b0) * ld, cudaMemcpyHostToDevice, copy_stream));
+            PPC_TRY(cudaEventRecord(ev_copy[c], copy_stream));
+            PPC_TRY(cudaStreamWaitEvent(s, ev_copy[c], 0));
+            const sepaihrd_rc rc = simulate_ppc_series(ctx, d_params, b0, ends[c] - b0, B, ld, d_init, d_series, d_status);
+            if (rc != SEPAIHRD_OK) { cudaStreamSynchronize(copy_stream); cleanup(); return rc; }
+            b0 = ends[c];
+        }
     }
-    // 3 + 4. the order statistics the quantiles need, column by column, without sorting (few probabilities: the usual case)
-    if (use_select) {
+    ppc_count_valid_kernel<<<(unsigned)((B + 255) / 256), 256, 0, s>>>(d_status, B, d_cnt);
+    PPC_TRY(cudaGetLastError());
+    // 2. the order statistics the quantiles need, column by column, 8 probabilities (<= 16 ranks) per group
+    {
         const long long all_cols = 6 * n_cols;
-        const unsigned grid = (unsigned)std::min<long long>(all_cols, 4 * 148);
-        ppc_select_kernel<<<grid, SEL_THREADS, 0, s>>>(d_series, B, all_cols, n_probs, d_probs, d_q);
-        PPC_TRY(cudaGetLastError());
-        count_launches(ctx, 1);
-    } else {
-    // 3. sort every column (one segment per (day, age)), one series at a time; 4. gather the quantiles
-    size_t tmp_bytes = 0;
-    PPC_TRY(cub::DeviceSegmentedRadixSort::SortKeys(nullptr, tmp_bytes, d_series, d_sorted, (long long)col_elems, (long long)n_cols, d_off, d_off + 1,
-                                                     0, 64, s));
-    d_tmp = scratch(ctx, slot++, tmp_bytes ? tmp_bytes : 16);
-    if (!d_tmp) return fail_with(SEPAIHRD_ERR_OUT_OF_MEMORY, "posterior-predictive sort buffer does not fit: split the draws");
-    for (int ser = 0; ser < 6; ++ser) {
-        PPC_TRY(cub::DeviceSegmentedRadixSort::SortKeys(d_tmp, tmp_bytes, d_series + (size_t)ser * col_elems, d_sorted, (long long)col_elems,
-                                                         (long long)n_cols, d_off, d_off + 1, 0, 64, s));
-        ppc_quantile_kernel<<<(unsigned)((n_cols + 127) / 128), 128, 0, s>>>(d_sorted, B, n_cols, n_probs, d_probs, d_q + (size_t)ser * n_cols * n_probs);
-        PPC_TRY(cudaGetLastError());
-    }
+        // Columns in flight x column size is what the later sweeps of a column find in L2 (126 MB): one 1024-thread block per SM
+        // keeps 148 columns of 100 k draws (118 MB) resident, so only the first sweep of a column reads HBM.
+        static const int env_grid = std::getenv("SEPAIHRD_PPC_GRID") ? std::atoi(std::getenv("SEPAIHRD_PPC_GRID")) : 0;
+        static const int env_threads = std::getenv("SEPAIHRD_PPC_THREADS") ? std::atoi(std::getenv("SEPAIHRD_PPC_THREADS")) : 0;
+        const int threads = env_threads ? env_threads : PPC_DEFAULT_THREADS;
+        const unsigned grid = (unsigned)std::min<long long>(all_cols, env_grid ? env_grid : PPC_DEFAULT_GRID);
+        for (int q0 = 0; q0 < n_probs; q0 += SEL_MAXT / 2) {
+            const int qg = std::min(SEL_MAXT / 2, n_probs - q0);
+            if (threads == 1024) ppc_select_kernel<1024><<<grid, 1024, 0, s>>>(d_series, B, all_cols, qg, d_probs, d_q, n_probs, q0);
+            else if (threads == 256) ppc_select_kernel<256><<<grid, 256, 0, s>>>(d_series, B, all_cols, qg, d_probs, d_q, n_probs, q0);
+            else ppc_select_kernel<512><<<grid, 512, 0, s>>>(d_series, B, all_cols, qg, d_probs, d_q, n_probs, q0);
+            PPC_TRY(cudaGetLastError());
+            count_launches(ctx, 1);
+        }
     }
     unsigned long long cnt = 0;
     std::vector<double> wide_q;

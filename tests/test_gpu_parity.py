@@ -411,7 +411,7 @@ def _ppc_reference(problem, oracle_obj, P, s0, probs):
 
 
 def test_posterior_predictive_quantiles_match_numpy_on_oracle_trajectories(problem, orc, ev_mod, pkg):
-    """Device posterior-predictive aggregation (trajectory kernel -> series -> segmented sort -> quantiles) against the
+    """Device posterior-predictive aggregation (trajectory kernel forming the six series -> multi-select -> quantiles) against the
     reference's incidence rule applied to oracle trajectories; two draws are invalid (negative kappa) and must be skipped."""
     loose = problem.__class__.from_json(dict(problem.to_json()))
     k2 = loose.param_names.index("kappa_2")
@@ -430,7 +430,7 @@ def test_posterior_predictive_quantiles_match_numpy_on_oracle_trajectories(probl
     assert err.max() < 1e-8, err.max()
     assert np.all(np.diff(got, axis=-1) >= 0)                                       # quantiles are ordered
     assert np.all(np.diff(got[3:], axis=1) >= -1e-9)                                # cumulative series are non-decreasing in time
-    # more than 8 probabilities take the full-sort path, up to 8 the multi-select: same numbers where they overlap
+    # more than 8 probabilities run the multi-select in groups of 8 (no library sort): same numbers where they overlap
     many = tuple(np.linspace(0.0, 1.0, 11))
     ref11, _ = _ppc_reference(loose, o, P, s0, many)
     with ev_mod.BatchEvaluator(loose, device=0) as ev:

@@ -20,6 +20,7 @@ ap.add_argument("--iterations", type=int, default=30)
 ap.add_argument("--draws", type=int, default=100000)
 ap.add_argument("--chunk", type=int, default=8192)
 ap.add_argument("--host-swarm", action="store_true", help="pso: keep the swarm on the host (the pre-device-resident path)")
+ap.add_argument("--pageable", action="store_true", help="ppcq: pass the draws in ordinary (pageable) host memory instead of page-locked memory")
 ap.add_argument("--ages", type=int, default=4, help="ppcq: 4, or 16 for the synthetic many-age-group variant of BASELINE configs[4]")
 a = ap.parse_args()
 pkg = g.load_package(); orc = g.load_oracle()
@@ -62,6 +63,8 @@ elif a.what == "ppcq":
     oq = orc.Oracle(pq)
     draws = oq.jitter_params(4096, seed=11)
     draws = np.tile(draws, ((a.draws + 4095) // 4096, 1))[:a.draws]
+    if not a.pageable:          # page-locked draws, as include/sepaihrd_b200.h recommends for the host-buffer entry points (sepaihrd_alloc_pinned)
+        draws = torch.from_numpy(draws).pin_memory().numpy()
     with BatchEvaluator(pq, device=dev) as ev:
         ev.posterior_predictive(draws[:1024], pq.data_initial_state)
         t0 = time.perf_counter()
@@ -71,7 +74,7 @@ elif a.what == "ppcq":
         q, valid = ev.posterior_predictive(draws, pq.data_initial_state)     # steady state: the ctx reuses them
         dt = time.perf_counter() - t0
         free_b, total_b = torch.cuda.mem_get_info(dev)
-    out.update(draws=a.draws, ages=a.ages, seconds=dt, first_call_seconds=first, draws_per_s=a.draws / dt, valid=valid,
+    out.update(draws=a.draws, ages=a.ages, host_memory="pageable" if a.pageable else "pinned", seconds=dt, first_call_seconds=first, draws_per_s=a.draws / dt, valid=valid,
                device_gbytes_in_use=(total_b - free_b) / 1e9, median_deaths_last_day=[float(x) for x in q[2, -1, :, 2]])
 else:
     p16 = p.expand_ages(4)
