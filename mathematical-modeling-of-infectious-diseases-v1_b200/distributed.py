@@ -40,7 +40,10 @@ class Comm:
             import torch
             import torch.distributed as dist
             os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-            os.environ.setdefault("MASTER_PORT", "29533")
+            if "MASTER_PORT" not in os.environ:
+                # every rank has to agree on the port, so it cannot be picked here: launchers (torchrun, the tests) export it;
+                # SEPAIHRD_MASTER_PORT lets hand-started ranks of concurrent jobs on one node choose different ones
+                os.environ["MASTER_PORT"] = os.environ.get("SEPAIHRD_MASTER_PORT", "29533")
             if backend is None:
                 backend = "nccl" if torch.cuda.is_available() else "gloo"
             if backend == "nccl":

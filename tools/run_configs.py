@@ -20,6 +20,9 @@ ap.add_argument("--iterations", type=int, default=30)
 ap.add_argument("--draws", type=int, default=100000)
 ap.add_argument("--chunk", type=int, default=8192)
 ap.add_argument("--host-swarm", action="store_true", help="pso: keep the swarm on the host (the pre-device-resident path)")
+ap.add_argument("--host-staged", action="store_true", help="mh / pso: round 1's path (host sampler resp. per-iteration host round trips, host-staged collectives) "
+                                                           "instead of the device-resident callers with the peer-memory exchange")
+ap.add_argument("--transport", default=None, choices=[None, "p2p", "nccl"], help="mh / pso: exchange transport of the device-resident callers")
 ap.add_argument("--pageable", action="store_true", help="ppcq: pass the draws in ordinary (pageable) host memory instead of page-locked memory")
 ap.add_argument("--ages", type=int, default=4, help="ppcq: 4, or 16 for the synthetic many-age-group variant of BASELINE configs[4]")
 a = ap.parse_args()
@@ -34,7 +37,24 @@ dev = comm.local_rank if comm.world > 1 else 0
 torch.cuda.set_device(dev)
 p = pkg.load_default_problem()
 out = dict(what=a.what, world=comm.world)
-if a.what == "mh":
+if a.what in ("mh", "pso") and not (a.host_staged or a.host_swarm):
+    # the device-resident callers (csrc/sepaihrd_mh.cu, csrc/sepaihrd_swarm.cu) with the per-iteration exchange on device buffers
+    from sepaihrd_b200 import resident
+    prob = p.__class__.from_json(dict(p.to_json(), constraint_mode=1)) if a.what == "mh" else p
+    with BatchEvaluator(prob, device=dev) as ev:
+        ev.eval_batch(np.tile(p.base_params(), (64, 1)))
+        if a.what == "mh":
+            r = resident.run_mh_resident(ev, p.sigmas, p.base_params(), a.chains, a.iterations, 1234, comm.rank, comm.world, transport=a.transport)
+            out.update(chains=a.chains, iterations=a.iterations, seconds=r["run_seconds"], setup_seconds=r["setup_seconds"],
+                       evals_per_s=a.chains * (a.iterations - 1) / r["run_seconds"], phase_seconds=r["phase_seconds"], transport=r["transport"],
+                       accept_rate=float(r["accepts"].mean()), best=float(r["best_trace"][-1]),
+                       accept_checksum_local=int(np.packbits(r["accepts"]).astype(np.int64).sum()))
+        else:
+            r = resident.run_pso_resident(ev, a.particles, a.iterations, 7, initial=p.base_params(), rank=comm.rank, world=comm.world, transport=a.transport)
+            out.update(swarm="device, asynchronous", particles=a.particles, iterations=a.iterations, seconds=r["run_seconds"], setup_seconds=r["setup_seconds"],
+                       evals_per_s=a.particles * (a.iterations + 1) / r["run_seconds"], phase_seconds=r["phase_seconds"], transport=r["transport"],
+                       best_first=float(r["trace"][0]), best_last=float(r["trace"][-1]))
+elif a.what == "mh":
     rp = p.__class__.from_json(dict(p.to_json(), constraint_mode=1))
     with BatchEvaluator(rp, device=dev) as ev:
         ev.eval_batch(np.tile(p.base_params(), (64, 1)))
