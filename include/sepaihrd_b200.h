@@ -336,6 +336,23 @@ sepaihrd_rc sepaihrd_exchange_all_gather(sepaihrd_exchange* ex, const double* d_
 sepaihrd_rc sepaihrd_exchange_status(sepaihrd_exchange* ex, int32_t* out_status);
 void sepaihrd_exchange_destroy(sepaihrd_exchange* ex);
 
+/* ---- ordering pass in front of large launches (csrc/sepaihrd_order.cu) --------------------------------------------------
+ * The kernel steps the 8 sets of a warp in lockstep, so a warp pays the largest number of step attempts among its sets on
+ * every output day; on widely spread batches (uniform in the bounds: the swarm initialisation of ParticleSwarmOptimizer.cpp:291)
+ * that idles 22 % of the lane-attempts.  With a fitted model, evaluations of >= 32,768 sets hand the sets to the warps in an
+ * order that puts sets with alike predicted attempt profiles together (two linear predictors per set, a counting sort, an
+ * index list): results are bit-identical, a 1M-set uniform-in-bounds launch takes 100 ms instead of 113 ms.
+ *   sepaihrd_fit_ordering   fits the model on a pilot of 2048 rows spread over `params` (one extra launch of a profiling
+ *                           instantiation of the kernel + a small least-squares problem on the host, ~15 ms, synchronous).
+ *                           Call it once per distribution of parameter sets.  sepaihrd_eval_batch (host buffers) does so by
+ *                           itself: at its first large batch, and again when a batch is centred or spread differently than
+ *                           the pilot; the `_device` entry points never fit on their own (they only enqueue).
+ *   sepaihrd_set_ordering   0 = never reorder, 1 = reorder when a model exists (default).
+ * 4-age problems in FAST arithmetic; other configurations simply stay unordered.  No reference counterpart. */
+sepaihrd_rc sepaihrd_set_ordering(sepaihrd_ctx* ctx, int32_t mode);
+sepaihrd_rc sepaihrd_fit_ordering(sepaihrd_ctx* ctx, const double* params, int64_t B, int64_t ld, int32_t params_on_device);
+sepaihrd_rc sepaihrd_ordering_state(const sepaihrd_ctx* ctx, int32_t* out_fitted, int64_t* out_fits);
+
 /* The aggregation passes (sepaihrd_posterior_predictive) keep their device work buffers in the ctx and reuse them across
  * calls; this frees them (they are also freed by sepaihrd_destroy). */
 sepaihrd_rc sepaihrd_release_scratch(sepaihrd_ctx* ctx);

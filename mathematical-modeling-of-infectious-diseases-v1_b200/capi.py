@@ -63,6 +63,9 @@ SIGNATURES = {
     "sepaihrd_exchange_all_gather": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "sepaihrd_exchange_status": (C.c_int, [C.c_void_p, _i32p]),
     "sepaihrd_exchange_destroy": (None, [C.c_void_p]),
+    "sepaihrd_set_ordering": (C.c_int, [C.c_void_p, C.c_int32]),
+    "sepaihrd_fit_ordering": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32]),
+    "sepaihrd_ordering_state": (C.c_int, [C.c_void_p, _i32p, C.POINTER(C.c_int64)]),
     "sepaihrd_release_scratch": (C.c_int, [C.c_void_p]),
     "sepaihrd_alloc_pinned": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
     "sepaihrd_free_pinned": (None, [C.c_void_p]),

@@ -126,6 +126,8 @@ struct sepaihrd_ctx {
     int* d_steps = nullptr; size_t cap_steps = 0;
     long long launches = 0, sets = 0;
     double* dbg_trace = nullptr;          // SEPAIHRD_DEBUG_INTERVALS builds only
+    void* order_model = nullptr;          // sepaihrd_order.cu: the fitted predictor + work buffers of the ordering pass
+    int order_mode = 1;                   // 0 off, 1 on (when a model has been fitted and the batch is large enough)
 };
 
 namespace {
@@ -142,7 +144,7 @@ sepaihrd_rc grow(T** ptr, size_t* cap, size_t need) {
 
 struct LaunchCfg { int threads, minblocks; };
 
-template <int NA, bool STRICT, int MODE, int THREADS, int MINBLOCKS, int LOOP, bool ONGRID = false>
+template <int NA, bool STRICT, int MODE, int THREADS, int MINBLOCKS, int LOOP, bool ONGRID = false, bool PROFILE = false>
 sepaihrd_rc launch_t(sepaihrd_ctx* ctx, const sepaihrd::KParams& kp_in) {
     using namespace sepaihrd;
     KParams kp = kp_in;
@@ -154,7 +156,7 @@ sepaihrd_rc launch_t(sepaihrd_ctx* ctx, const sepaihrd::KParams& kp_in) {
     // the kernel): launches of one ctx that are in flight on different streams never share one.
     kp.tile_counter = ctx->d_tile_counter + (ctx->launch_seq++ % sepaihrd_ctx::N_TILE_COUNTERS);
     CUDA_TRY(cudaMemsetAsync(kp.tile_counter, 0, sizeof(unsigned), ctx->stream));
-    auto kern = sepaihrd_batch_kernel<NA, STRICT, MODE, THREADS, MINBLOCKS, LOOP, ONGRID>;
+    auto kern = sepaihrd_batch_kernel<NA, STRICT, MODE, THREADS, MINBLOCKS, LOOP, ONGRID, PROFILE>;
     const size_t smem = (size_t)kp.blob_bytes + sizeof(double) * (SETS * (size_t)(kp.slot_stride + ((kp.seg_stride + 1) & ~1)) + 2 * THREADS + (size_t)NA * THREADS) + 16;
     {   // once per device and instantiation, whichever thread / ctx gets here first
         static std::once_flag attr_once[64];
@@ -589,6 +591,7 @@ void sepaihrd_destroy(sepaihrd_ctx* ctx) {
     if (ctx->d_out) cudaFree(ctx->d_out);
     if (ctx->d_status) cudaFree(ctx->d_status);
     if (ctx->d_steps) cudaFree(ctx->d_steps);
+    sepaihrd_internal::order_release(ctx);
     for (void* p : ctx->scratch) if (p) cudaFree(p);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -668,8 +671,16 @@ sepaihrd_rc sepaihrd_get_merge_counters(const sepaihrd_ctx* ctx, int64_t* merged
     return SEPAIHRD_OK;
 }
 
+static sepaihrd_rc eval_device_impl(sepaihrd_ctx* ctx, const double* d_params, int64_t B, int64_t ld, double* d_out_ll, uint32_t* d_out_status,
+                                    int32_t* d_out_steps, bool allow_order);
+
 sepaihrd_rc sepaihrd_eval_batch_device(sepaihrd_ctx* ctx, const double* d_params, int64_t B, int64_t ld,
                                        double* d_out_ll, uint32_t* d_out_status, int32_t* d_out_steps) {
+    return eval_device_impl(ctx, d_params, B, ld, d_out_ll, d_out_status, d_out_steps, true);
+}
+
+static sepaihrd_rc eval_device_impl(sepaihrd_ctx* ctx, const double* d_params, int64_t B, int64_t ld, double* d_out_ll, uint32_t* d_out_status,
+                                    int32_t* d_out_steps, bool allow_order) {
     if (!ctx || !d_out_ll || (B > 0 && !d_params)) return fail(SEPAIHRD_ERR_INVALID_ARGUMENT, "null argument");
     if (B < 0 || ld < ctx->P) return fail(SEPAIHRD_ERR_INVALID_ARGUMENT, "Parameter vector size mismatch.");   // ParameterManager.cpp:165-167
     if (B == 0) return SEPAIHRD_OK;
@@ -691,6 +702,11 @@ sepaihrd_rc sepaihrd_eval_batch_device(sepaihrd_ctx* ctx, const double* d_params
     kp.out_traj = ctx->dbg_trace;      // diagnostic build: [B][2048][3] (t, step, err) of every attempt
 #endif
     kp.init_states = nullptr; kp.init_stride = 0;
+    kp.perm = nullptr; kp.out_profile = nullptr;
+    if (allow_order) {
+        const sepaihrd_rc orc = sepaihrd_internal::order_batch(ctx, d_params, B, ld, &kp.perm);      // no model / small batch: perm stays null
+        if (orc != SEPAIHRD_OK) return orc;
+    }
     return launch(ctx, kp, sepaihrd::MODE_LL);
 }
 
@@ -708,6 +724,7 @@ sepaihrd_rc eval_batch_serial(sepaihrd_ctx* ctx, const double* params, int64_t B
     if ((rc = grow(&ctx->d_out, &ctx->cap_out, (size_t)B)) != SEPAIHRD_OK) return rc;
     if ((rc = grow(&ctx->d_status, &ctx->cap_status, (size_t)B)) != SEPAIHRD_OK) return rc;
     if (out_steps && (rc = grow(&ctx->d_steps, &ctx->cap_steps, (size_t)B * 2)) != SEPAIHRD_OK) return rc;
+    if ((rc = sepaihrd_internal::order_autofit_host(ctx, params, B, ld)) != SEPAIHRD_OK) return rc;      // large batches: keep the ordering model current (sepaihrd_order.cu)
     // Chunks on two streams: while the kernel works on a chunk, the copy stream brings the next ones over (H2D moves several
     // times more sets per second than the kernel consumes), so only the FIRST chunk's copy and the last chunk's 12-byte-per-set
     // results are exposed; the chunks grow geometrically so that each copy still finishes under the kernel before it.  Small
@@ -901,6 +918,7 @@ static sepaihrd_rc simulate_device_impl(sepaihrd_ctx* ctx, const double* d_param
     kp.out_traj = d_kernel_out; kp.traj_what = what; kp.traj_stride = stride; kp.traj_rows = rows;
     kp.traj_draw_minor = draw_minor ? 1 : 0;
     kp.init_states = d_init; kp.init_stride = init_stride;
+    kp.perm = nullptr; kp.out_profile = nullptr;
     const sepaihrd_rc rc = launch(ctx, kp, sepaihrd::MODE_TRAJ);
     if (rc != SEPAIHRD_OK || !repack) return rc;
     const long long n_vec = (long long)B * rows, narrow = (long long)C * ctx->n_user;
@@ -1021,6 +1039,27 @@ const double* lower_bounds(const sepaihrd_ctx* ctx) { return ctx->blob.data() + 
 const double* upper_bounds(const sepaihrd_ctx* ctx) { return ctx->blob.data() + ctx->kp.o_hi; }
 void count_launches(sepaihrd_ctx* ctx, int n) { ctx->launches += n; }
 int constraint_mode(const sepaihrd_ctx* ctx) { return ctx->constraint_mode; }
+void** order_slot(sepaihrd_ctx* ctx) { return &ctx->order_model; }
+int order_mode(const sepaihrd_ctx* ctx) { return ctx->order_mode; }
+void set_order_mode(sepaihrd_ctx* ctx, int mode) { ctx->order_mode = mode; }
+int num_sms(const sepaihrd_ctx* ctx) { return ctx->num_sms; }
+sepaihrd_rc eval_batch_device_unordered(sepaihrd_ctx* ctx, const double* d_params, long long B, long long ld, double* d_ll, unsigned* d_status, int* d_steps) {
+    return eval_device_impl(ctx, d_params, B, ld, d_ll, d_status, d_steps, false);
+}
+// the pilot of the ordering pass: one launch of the PROFILE instantiation (FAST arithmetic, 4 lanes per set)
+sepaihrd_rc eval_profile(sepaihrd_ctx* ctx, const double* d_params, long long B, long long ld, double* d_ll, unsigned* d_status, int* d_profile) {
+    if (ctx->n != 4 || ctx->math_mode == SEPAIHRD_MATH_STRICT || ctx->obs_mismatch) return fail(SEPAIHRD_ERR_UNSUPPORTED, "no attempt profile for this configuration");
+    std::lock_guard<std::recursive_mutex> lock(ctx->mu);
+    sepaihrd::KParams kp = ctx->kp;
+    kp.constraint_mode = ctx->constraint_mode;
+    kp.params = d_params; kp.B = B; kp.ld = ld;
+    kp.out_ll = d_ll; kp.out_status = d_status; kp.out_steps = nullptr;
+    kp.out_traj = nullptr; kp.traj_what = 0; kp.traj_stride = 1; kp.traj_rows = 0; kp.traj_draw_minor = 0;
+    kp.init_states = nullptr; kp.init_stride = 0;
+    kp.perm = nullptr; kp.out_profile = d_profile;
+    if (ctx->bp_on_grid && ctx->math_mode != SEPAIHRD_MATH_FAST_GENERAL) return launch_t<4, false, sepaihrd::MODE_LL, 128, 2, 6, true, true>(ctx, kp);
+    return launch_t<4, false, sepaihrd::MODE_LL, 128, 2, 6, false, true>(ctx, kp);
+}
 std::unique_lock<std::recursive_mutex> lock(sepaihrd_ctx* ctx) { return std::unique_lock<std::recursive_mutex>(ctx->mu); }
 void* scratch(sepaihrd_ctx* ctx, int slot, size_t bytes) {
     if (slot < 0 || slot >= sepaihrd_ctx::N_SCRATCH) return nullptr;
@@ -1055,6 +1094,7 @@ sepaihrd_rc simulate_ppc_series(sepaihrd_ctx* ctx, const double* d_params, long 
     kp.traj_draw_minor = 1;
     kp.ppc_b0 = b0; kp.ppc_B = B_total;
     kp.init_states = d_init; kp.init_stride = 0;
+    kp.perm = nullptr; kp.out_profile = nullptr;
     return launch(ctx, kp, sepaihrd::MODE_TRAJ);
 }
 }  // namespace sepaihrd_internal

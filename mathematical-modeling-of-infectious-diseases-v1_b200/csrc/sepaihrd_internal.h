@@ -20,6 +20,20 @@ const double* lower_bounds(const sepaihrd_ctx* ctx);   // host copies, [P], as g
 const double* upper_bounds(const sepaihrd_ctx* ctx);
 void count_launches(sepaihrd_ctx* ctx, int n);
 int constraint_mode(const sepaihrd_ctx* ctx);         // 0 clamp, 1 reflect (sepaihrd_set_constraint_mode)
+int num_sms(const sepaihrd_ctx* ctx);
+// ---- ordering pass (sepaihrd_order.cu) ----------------------------------------------------------------------------------
+void** order_slot(sepaihrd_ctx* ctx);                 // where the ctx keeps the fitted model (owned by sepaihrd_order.cu)
+int order_mode(const sepaihrd_ctx* ctx);
+void set_order_mode(sepaihrd_ctx* ctx, int mode);
+sepaihrd_rc order_autofit_host(sepaihrd_ctx* ctx, const double* params, long long B, long long ld);   // host-pointer evaluations: fit when there is no model or the batch looks different
+void order_release(sepaihrd_ctx* ctx);
+// *perm = the order in which to hand the B sets to the warps (device, owned by the model), or left null (no model, batch too
+// small, ordering off); enqueues its kernels on the ctx stream
+sepaihrd_rc order_batch(sepaihrd_ctx* ctx, const double* d_params, long long B, long long ld, const int** perm);
+// one launch of the likelihood kernel that also records, per set, the attempts made before every grid point: d_profile [B][K]
+sepaihrd_rc eval_profile(sepaihrd_ctx* ctx, const double* d_params, long long B, long long ld, double* d_ll, unsigned* d_status, int* d_profile);
+// the evaluation as sepaihrd_eval_batch_device does it, but never reordered (callers whose batches change every iteration)
+sepaihrd_rc eval_batch_device_unordered(sepaihrd_ctx* ctx, const double* d_params, long long B, long long ld, double* d_ll, unsigned* d_status, int* d_steps);
 // the ctx mutex (recursive): every entry point of another translation unit that touches the ctx holds it for its duration
 std::unique_lock<std::recursive_mutex> lock(sepaihrd_ctx* ctx);
 // Grow-only device work buffer `slot` (0..15) of at least `bytes`, owned by the ctx and reused across calls; nullptr when the

@@ -81,6 +81,10 @@ struct KParams {
     long long ppc_b0, ppc_B;   // TRAJ_PPC_SERIES: this launch holds draws [ppc_b0, ppc_b0 + B) of ppc_B (chunked launches overlap the H2D copy)
     const double* init_states; // optional [B][11n] (or one shared state when init_stride == 0): Simulator::run semantics
     long long init_stride;
+    const int* perm;           // optional [B]: the order in which the sets are handed to the warps (position -> set index); results still go
+                               // to the set's own slot.  Built by the ordering pass (sepaihrd_order.cu) so that a warp holds sets that
+                               // need similar numbers of step attempts per day
+    int* out_profile;          // PROFILE instantiation only: [B][K] attempts (accepted + rejected) made before each grid point
     long long tiles;           // ceil(B / sets_per_warp)
     unsigned* tile_counter;    // zeroed before every launch (tiles < 2^32 - grid warps)
 };
@@ -468,7 +472,9 @@ __device__ __forceinline__ void dopri5_attempt(const LaneParams<NA>& q, const St
 // ONGRID (FAST only): every schedule breakpoint inside the integration window sits on an output-grid point, so no step can
 // have its stages in two segments and the mixed-segment attempt body is not instantiated (668 SASS instructions less to
 // keep in the instruction cache).  The host decides per problem (sepaihrd_create).
-template <int NA, bool STRICT, int MODE, int THREADS, int MINBLOCKS, int LOOP, bool ONGRID = false>
+// PROFILE (FAST, log-likelihood mode): additionally records the running attempt count at every grid point -- the pilot of the
+// ordering pass; a separate instantiation so that the production kernel carries none of it.
+template <int NA, bool STRICT, int MODE, int THREADS, int MINBLOCKS, int LOOP, bool ONGRID = false, bool PROFILE = false>
 __global__ void __launch_bounds__(THREADS, MINBLOCKS) sepaihrd_batch_kernel(const KParams kp) {
     static_assert(STRICT ? LOOP == 5 : LOOP == 6, "STRICT keeps the reference-order loop 5; FAST runs loop 6");
     using O = Ops<STRICT>;
@@ -529,7 +535,8 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) sepaihrd_batch_kernel(cons
         if ((long long)wt >= kp.tiles) break;
         const long long b_raw = (long long)wt * WSETS + grp_in_warp;
         const bool have = b_raw < kp.B;
-        const long long b = have ? b_raw : (kp.B - 1);   // idle groups shadow the last set; nothing is written for them
+        const long long b_pos = have ? b_raw : (kp.B - 1);   // idle groups shadow the last set; nothing is written for them
+        const long long b = kp.perm ? (long long)kp.perm[b_pos] : b_pos;
 
         // ---- updateModelParameters: base slots, then constrained calibrated values -------------------
         __syncwarp();
@@ -699,6 +706,7 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) sepaihrd_batch_kernel(cons
 #ifdef SEPAIHRD_DEBUG_INTERVALS   // diagnostic build (tools/strict_parity_diag.py): out_steps is [B][K][2], running totals at every grid point
             if (MODE == MODE_LL && have && age == 0 && kp.out_steps) { kp.out_steps[(b * K + idx) * 2] = n_acc; kp.out_steps[(b * K + idx) * 2 + 1] = n_rej; }
 #endif
+            if constexpr (PROFILE) { if (have && age == 0) kp.out_profile[b * K + idx] = n_acc + n_rej; }
             if (MODE == MODE_TRAJ) {
                 if (kp.traj_what == TRAJ_PPC_SERIES) {
                     ppc_observe(idx, prev_h, prev_i, prev_d, ll_acc_h, ll_acc_i, ll_acc_d);     // the likelihood accumulators are free here: running sums

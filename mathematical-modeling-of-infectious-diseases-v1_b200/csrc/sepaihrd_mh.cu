@@ -380,7 +380,7 @@ sepaihrd_rc sepaihrd_mh_begin(sepaihrd_mh* m, uint32_t seed, const double* initi
     MH_TRY(cudaMemcpyAsync(m->d_init, initial, 8 * (size_t)P, cudaMemcpyHostToDevice, st));
     MH_TRY(cudaStreamSynchronize(st));                      // the sources are the caller's pageable buffers
     // log-posterior of the common start: ONE evaluation (like optimize(), host/optimizers.cpp), read by the start kernel
-    sepaihrd_rc rc = sepaihrd_eval_batch_device(m->ctx, m->d_init, 1, P, m->d_plp + m->local, m->d_status + m->local, nullptr);
+    sepaihrd_rc rc = sepaihrd_internal::eval_batch_device_unordered(m->ctx, m->d_init, 1, P, m->d_plp + m->local, m->d_status + m->local, nullptr);
     if (rc != SEPAIHRD_OK) return rc;
     if (m->local > 0) {
         const unsigned blocks = (unsigned)((m->local + 63) / 64);
@@ -414,7 +414,7 @@ static sepaihrd_rc mh_phase(sepaihrd_mh* m, int phase) {
         MH_TRY(cudaGetLastError());
         sepaihrd_internal::count_launches(m->ctx, 1);
     } else if (phase == 1 && m->local > 0) {
-        return sepaihrd_eval_batch_device(m->ctx, m->d_prop, m->local, m->P, m->d_plp, m->d_status, nullptr);
+        return sepaihrd_internal::eval_batch_device_unordered(m->ctx, m->d_prop, m->local, m->P, m->d_plp, m->d_status, nullptr);
     } else if (phase == 2) {
         if (m->local > 0) {
             mh_accept_kernel<<<blocks, MH_THREADS, 0, st>>>(m->local, m->P, m->t, m->cfg.adapt_scale, m->cfg.target_acceptance_rate, m->d_plp, m->d_prop,

@@ -366,7 +366,7 @@ sepaihrd_rc sepaihrd_swarm_evaluate(sepaihrd_swarm* s, double* out_best_value, i
         if (out_best_local_index) *out_best_local_index = -1;
         return SEPAIHRD_OK;
     }
-    sepaihrd_rc rc = sepaihrd_eval_batch_device(s->ctx, s->d_pos, s->local, s->P, s->d_fit, s->d_status, nullptr);
+    sepaihrd_rc rc = sepaihrd_internal::eval_batch_device_unordered(s->ctx, s->d_pos, s->local, s->P, s->d_fit, s->d_status, nullptr);
     if (rc != SEPAIHRD_OK) return rc;
     swarm_tell_kernel<<<s->blocks_tell, TELL_THREADS, 0, st>>>(s->local, s->P, s->evaluated_once ? 0 : 1, s->d_fit, s->d_pos, s->d_pbest,
                                                               s->d_pbest_val, s->d_block_val, s->d_block_idx);
@@ -479,7 +479,7 @@ sepaihrd_rc sepaihrd_swarm_evaluate_async(sepaihrd_swarm* s) {
     SW_TRY(cudaSetDevice(d.device));
     cudaStream_t st = sepaihrd_internal::stream(s->ctx);
     if (s->local > 0) {
-        sepaihrd_rc rc = sepaihrd_eval_batch_device(s->ctx, s->d_pos, s->local, s->P, s->d_fit, s->d_status, nullptr);
+        sepaihrd_rc rc = sepaihrd_internal::eval_batch_device_unordered(s->ctx, s->d_pos, s->local, s->P, s->d_fit, s->d_status, nullptr);
         if (rc != SEPAIHRD_OK) return rc;
         swarm_tell_kernel<<<s->blocks_tell, TELL_THREADS, 0, st>>>(s->local, s->P, s->evaluated_once ? 0 : 1, s->d_fit, s->d_pos, s->d_pbest,
                                                                   s->d_pbest_val, s->d_block_val, s->d_block_idx);

@@ -74,6 +74,26 @@ class BatchEvaluator:
     def set_stream(self, cuda_stream_ptr: int):
         capi.check(self._lib.sepaihrd_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
 
+    def set_ordering(self, on: bool):
+        """Switch the ordering pass in front of large launches (csrc/sepaihrd_order.cu) on (default) or off."""
+        capi.check(self._lib.sepaihrd_set_ordering(self._h, 1 if on else 0))
+
+    def fit_ordering(self, params):
+        """Fit the ordering model on a representative batch ([B, P] numpy array or CUDA tensor); ~15 ms, synchronous."""
+        if _is_tensor(params):
+            assert params.is_cuda and params.dim() == 2 and params.is_contiguous()
+            self.set_stream(__import__("torch").cuda.current_stream(params.device).cuda_stream)
+            capi.check(self._lib.sepaihrd_fit_ordering(self._h, C.c_void_p(params.data_ptr()), params.shape[0], params.shape[1], 1))
+        else:
+            x = np.ascontiguousarray(params, dtype=np.float64)
+            capi.check(self._lib.sepaihrd_fit_ordering(self._h, x.ctypes.data, x.shape[0], x.shape[1], 0))
+
+    def ordering_state(self):
+        """(model fitted?, number of fits so far)."""
+        a, b = C.c_int32(), C.c_int64()
+        capi.check(self._lib.sepaihrd_ordering_state(self._h, C.byref(a), C.byref(b)))
+        return bool(a.value), b.value
+
     def synchronize(self):
         capi.check(self._lib.sepaihrd_synchronize(self._h))
 

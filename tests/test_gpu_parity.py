@@ -609,3 +609,54 @@ def test_ongrid_build_is_bit_identical_to_the_general_build(problem, oracle, ev_
         tr_a, _ = a.simulate_batch(P[:64])
         tr_b, _ = b.simulate_batch(P[:64])
         np.testing.assert_array_equal(tr_a, tr_b)
+
+
+def test_ordering_pass_changes_the_schedule_not_the_results(problem, oracle, ev_mod):
+    """csrc/sepaihrd_order.cu: with a fitted model, launches of >= 32,768 sets hand the sets to the warps through an index list
+    (alike predicted attempt profiles together).  Every result must be the one of the unordered launch, bit for bit -- logL,
+    status, step counts -- on uniform-in-bounds and on jittered sets, through the device and the host entry points; small
+    batches and switched-off ordering take the plain path; the host entry point fits by itself and refits when the batch
+    looks different."""
+    import torch
+    U = oracle.uniform_params(70000, seed=2)
+    J = oracle.jitter_params(40000, seed=1)
+    U[11] = problem.upper_bound * 40.0                       # clamped
+    with ev_mod.BatchEvaluator(problem, device=0) as ev:
+        assert ev.ordering_state() == (False, 0)
+        dU, dJ = torch.from_numpy(U).cuda(), torch.from_numpy(J).cuda()
+        ref_u = ev.eval_batch(dU, return_steps=True)
+        ref_j = ev.eval_batch(dJ, return_steps=True)
+        torch.cuda.synchronize()
+        l0 = ev.counters()[0]
+        ev.fit_ordering(dU)
+        assert ev.ordering_state() == (True, 1)
+        l1 = ev.counters()[0]
+        got_u = ev.eval_batch(dU, return_steps=True)
+        torch.cuda.synchronize()
+        assert ev.counters()[0] - l1 == 5                   # keys, buckets, scan, scatter + the likelihood kernel
+        got_j = ev.eval_batch(dJ, return_steps=True)         # a model fitted elsewhere still only reorders
+        small = ev.eval_batch(dU[:5000], return_steps=True)
+        torch.cuda.synchronize()
+        for a, b in zip(got_u, ref_u):
+            assert torch.equal(a, b)
+        for a, b in zip(got_j, ref_j):
+            assert torch.equal(a, b)
+        for a, b in zip(small, ref_u):
+            assert torch.equal(a, b[:5000])
+        ev.set_ordering(False)
+        l2 = ev.counters()[0]
+        off = ev.eval_batch(dU)
+        torch.cuda.synchronize()
+        assert ev.counters()[0] - l2 == 1 and torch.equal(off[0], ref_u[0])
+        ev.set_ordering(True)
+    with ev_mod.BatchEvaluator(problem, device=0) as ev:      # host buffers: the call keeps the model current by itself
+        ll_u, st_u, steps_u = ev.eval_batch(U, return_steps=True)
+        assert ev.ordering_state() == (True, 1)
+        ll_u2, _ = ev.eval_batch(U)
+        assert ev.ordering_state() == (True, 1)              # same distribution: no refit
+        ll_j, _ = ev.eval_batch(J)
+        assert ev.ordering_state() == (True, 2)              # jittered sets sit elsewhere and are 10x narrower: refit
+    np.testing.assert_array_equal(ll_u, ref_u[0].cpu().numpy())
+    np.testing.assert_array_equal(ll_u2, ll_u)
+    np.testing.assert_array_equal(steps_u, ref_u[2].cpu().numpy())
+    np.testing.assert_array_equal(ll_j, ref_j[0].cpu().numpy())
