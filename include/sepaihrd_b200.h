@@ -348,7 +348,9 @@ void sepaihrd_exchange_destroy(sepaihrd_exchange* ex);
  *                           itself: at its first large batch, and again when a batch is centred or spread differently than
  *                           the pilot; the `_device` entry points never fit on their own (they only enqueue).
  *   sepaihrd_set_ordering   0 = never reorder, 1 = reorder when a model exists (default).
- * 4-age problems in FAST arithmetic; other configurations simply stay unordered.  No reference counterpart. */
+ * 4-age problems in FAST arithmetic; other configurations simply stay unordered.  The swarm's and the sampler's own
+ * evaluations are never reordered (measured on the 65,536-particle swarm: no gain -- its particles are not spread like the
+ * uniform batch after the first update -- and their batches change every iteration).  No reference counterpart. */
 sepaihrd_rc sepaihrd_set_ordering(sepaihrd_ctx* ctx, int32_t mode);
 sepaihrd_rc sepaihrd_fit_ordering(sepaihrd_ctx* ctx, const double* params, int64_t B, int64_t ld, int32_t params_on_device);
 sepaihrd_rc sepaihrd_ordering_state(const sepaihrd_ctx* ctx, int32_t* out_fitted, int64_t* out_fits);

@@ -707,7 +707,9 @@ static sepaihrd_rc eval_device_impl(sepaihrd_ctx* ctx, const double* d_params, i
         const sepaihrd_rc orc = sepaihrd_internal::order_batch(ctx, d_params, B, ld, &kp.perm);      // no model / small batch: perm stays null
         if (orc != SEPAIHRD_OK) return orc;
     }
-    return launch(ctx, kp, sepaihrd::MODE_LL);
+    const sepaihrd_rc lrc = launch(ctx, kp, sepaihrd::MODE_LL);
+    if (kp.perm) { const sepaihrd_rc mrc = sepaihrd_internal::order_mark_done(ctx); if (lrc == SEPAIHRD_OK && mrc != SEPAIHRD_OK) return mrc; }
+    return lrc;
 }
 
 }  // extern "C"

@@ -30,6 +30,7 @@ void order_release(sepaihrd_ctx* ctx);
 // *perm = the order in which to hand the B sets to the warps (device, owned by the model), or left null (no model, batch too
 // small, ordering off); enqueues its kernels on the ctx stream
 sepaihrd_rc order_batch(sepaihrd_ctx* ctx, const double* d_params, long long B, long long ld, const int** perm);
+sepaihrd_rc order_mark_done(sepaihrd_ctx* ctx);      // call right after the launch that reads *perm has been enqueued (same stream)
 // one launch of the likelihood kernel that also records, per set, the attempts made before every grid point: d_profile [B][K]
 sepaihrd_rc eval_profile(sepaihrd_ctx* ctx, const double* d_params, long long B, long long ld, double* d_ll, unsigned* d_status, int* d_profile);
 // the evaluation as sepaihrd_eval_batch_device does it, but never reordered (callers whose batches change every iteration)

@@ -43,12 +43,21 @@ struct OrderModel {
     bool fitted = false;
     std::vector<double> mu, inv_sd, sd;             // standardisation of the parameters (pilot statistics)
     double* d_model = nullptr;                      // mu[P] | inv_sd[P] | w1[P + 1] | w2[P + 1]  (intercept last)
-    float2* d_keys = nullptr;                       // [cap] predicted components
-    int* d_perm = nullptr;                          // [cap]
-    unsigned* d_bucket = nullptr;                   // [cap]
-    unsigned* d_hist = nullptr;                     // [NBUCKETS + 1]
-    double* d_stats = nullptr;                      // [4]: sum1, sumsq1, sum2, sumsq2
-    long long cap = 0;
+    // Work buffers of one ordering pass.  TWO sets, used alternately: the host-buffer evaluation runs consecutive chunks on two
+    // streams so that they overlap, and a launch reads its index list until it ends -- a set is reused only after the launch
+    // that last read it has finished (its `done` event, awaited on the new launch's stream).
+    struct Work {
+        float2* d_keys = nullptr;                   // [cap] predicted components
+        int* d_perm = nullptr;                      // [cap]
+        unsigned* d_bucket = nullptr;               // [cap]
+        unsigned* d_hist = nullptr;                 // [NBUCKETS + 1]
+        double* d_stats = nullptr;                  // [4]: sum1, sumsq1, sum2, sumsq2
+        long long cap = 0;
+        cudaEvent_t done = nullptr;
+        bool pending = false;
+    } work[2];
+    unsigned seq = 0;
+    int last = -1;                                  // set handed out by the latest order_batch, until order_mark_done records its event
     long long fits = 0;
 };
 
@@ -137,19 +146,20 @@ __global__ void order_scatter_kernel(const unsigned* __restrict__ bucket, long l
     perm[atomicAdd(&cursor[bucket[b]], 1u)] = (int)b;
 }
 
-sepaihrd_rc ensure_buffers(OrderModel* m, long long B) {
-    if (B <= m->cap) return SEPAIHRD_OK;
+sepaihrd_rc ensure_buffers(OrderModel::Work& w, long long B) {
+    if (!w.done) ORD_TRY(cudaEventCreateWithFlags(&w.done, cudaEventDisableTiming));
+    if (!w.d_hist) ORD_TRY(cudaMalloc((void**)&w.d_hist, sizeof(unsigned) * (NBUCKETS + 1)));
+    if (!w.d_stats) ORD_TRY(cudaMalloc((void**)&w.d_stats, sizeof(double) * 4));
+    if (B <= w.cap) return SEPAIHRD_OK;
     ORD_TRY(cudaDeviceSynchronize());
-    if (m->d_keys) cudaFree(m->d_keys);
-    if (m->d_perm) cudaFree(m->d_perm);
-    if (m->d_bucket) cudaFree(m->d_bucket);
-    m->d_keys = nullptr; m->d_perm = nullptr; m->d_bucket = nullptr; m->cap = 0;
-    ORD_TRY(cudaMalloc((void**)&m->d_keys, sizeof(float2) * (size_t)B));
-    ORD_TRY(cudaMalloc((void**)&m->d_perm, sizeof(int) * (size_t)B));
-    ORD_TRY(cudaMalloc((void**)&m->d_bucket, sizeof(unsigned) * (size_t)B));
-    if (!m->d_hist) ORD_TRY(cudaMalloc((void**)&m->d_hist, sizeof(unsigned) * (NBUCKETS + 1)));
-    if (!m->d_stats) ORD_TRY(cudaMalloc((void**)&m->d_stats, sizeof(double) * 4));
-    m->cap = B;
+    if (w.d_keys) cudaFree(w.d_keys);
+    if (w.d_perm) cudaFree(w.d_perm);
+    if (w.d_bucket) cudaFree(w.d_bucket);
+    w.d_keys = nullptr; w.d_perm = nullptr; w.d_bucket = nullptr; w.cap = 0; w.pending = false;
+    ORD_TRY(cudaMalloc((void**)&w.d_keys, sizeof(float2) * (size_t)B));
+    ORD_TRY(cudaMalloc((void**)&w.d_perm, sizeof(int) * (size_t)B));
+    ORD_TRY(cudaMalloc((void**)&w.d_bucket, sizeof(unsigned) * (size_t)B));
+    w.cap = B;
     return SEPAIHRD_OK;
 }
 
@@ -276,7 +286,11 @@ void order_release(sepaihrd_ctx* ctx) {
     OrderModel* m = model_of(ctx, false);
     if (!m) return;
     cudaDeviceSynchronize();
-    for (void* p : {(void*)m->d_model, (void*)m->d_keys, (void*)m->d_perm, (void*)m->d_bucket, (void*)m->d_hist, (void*)m->d_stats}) if (p) cudaFree(p);
+    if (m->d_model) cudaFree(m->d_model);
+    for (OrderModel::Work& w : m->work) {
+        for (void* p : {(void*)w.d_keys, (void*)w.d_perm, (void*)w.d_bucket, (void*)w.d_hist, (void*)w.d_stats}) if (p) cudaFree(p);
+        if (w.done) cudaEventDestroy(w.done);
+    }
     delete m;
     *order_slot(ctx) = nullptr;
 }
@@ -286,18 +300,33 @@ sepaihrd_rc order_batch(sepaihrd_ctx* ctx, const double* d_params, long long B, 
     if (!m || !m->fitted || order_mode(ctx) == 0 || B < ORDER_MIN_BATCH || B > 0x7fffffffLL) return SEPAIHRD_OK;
     const Dims d = dims(ctx);
     if (m->P != d.P) return SEPAIHRD_OK;
-    sepaihrd_rc rc = ensure_buffers(m, B);
+    const int which = (int)(m->seq++ & 1u);
+    OrderModel::Work& w = m->work[which];
+    sepaihrd_rc rc = ensure_buffers(w, B);
     if (rc != SEPAIHRD_OK) return rc;
     cudaStream_t s = stream(ctx);
-    ORD_TRY(cudaMemsetAsync(m->d_stats, 0, sizeof(double) * 4, s));
-    ORD_TRY(cudaMemsetAsync(m->d_hist, 0, sizeof(unsigned) * (NBUCKETS + 1), s));
-    order_keys_kernel<<<(unsigned)((B + 7) / 8), 256, 0, s>>>(d_params, B, ld, d.P, m->d_model, m->d_keys, m->d_stats);
-    order_bucket_kernel<<<(unsigned)((B + 255) / 256), 256, 0, s>>>(m->d_keys, B, m->d_stats, m->d_bucket, m->d_hist);
-    order_scan_kernel<<<1, 1024, 0, s>>>(m->d_hist);
-    order_scatter_kernel<<<(unsigned)((B + 255) / 256), 256, 0, s>>>(m->d_bucket, B, m->d_hist, m->d_perm);
+    if (w.pending) ORD_TRY(cudaStreamWaitEvent(s, w.done, 0));        // the launch that last read this set's index list (maybe on another stream)
+    ORD_TRY(cudaMemsetAsync(w.d_stats, 0, sizeof(double) * 4, s));
+    ORD_TRY(cudaMemsetAsync(w.d_hist, 0, sizeof(unsigned) * (NBUCKETS + 1), s));
+    order_keys_kernel<<<(unsigned)((B + 7) / 8), 256, 0, s>>>(d_params, B, ld, d.P, m->d_model, w.d_keys, w.d_stats);
+    order_bucket_kernel<<<(unsigned)((B + 255) / 256), 256, 0, s>>>(w.d_keys, B, w.d_stats, w.d_bucket, w.d_hist);
+    order_scan_kernel<<<1, 1024, 0, s>>>(w.d_hist);
+    order_scatter_kernel<<<(unsigned)((B + 255) / 256), 256, 0, s>>>(w.d_bucket, B, w.d_hist, w.d_perm);
     ORD_TRY(cudaGetLastError());
     count_launches(ctx, 4);
-    *perm = m->d_perm;
+    *perm = w.d_perm;
+    m->last = which;
+    return SEPAIHRD_OK;
+}
+
+// the launch that reads the index list of the latest order_batch has been enqueued on the ctx stream
+sepaihrd_rc order_mark_done(sepaihrd_ctx* ctx) {
+    OrderModel* m = model_of(ctx, false);
+    if (!m || m->last < 0) return SEPAIHRD_OK;
+    OrderModel::Work& w = m->work[m->last];
+    m->last = -1;
+    ORD_TRY(cudaEventRecord(w.done, stream(ctx)));
+    w.pending = true;
     return SEPAIHRD_OK;
 }
 

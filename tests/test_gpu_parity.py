@@ -656,6 +656,16 @@ def test_ordering_pass_changes_the_schedule_not_the_results(problem, oracle, ev_
         assert ev.ordering_state() == (True, 1)              # same distribution: no refit
         ll_j, _ = ev.eval_batch(J)
         assert ev.ordering_state() == (True, 2)              # jittered sets sit elsewhere and are 10x narrower: refit
+    # the host-buffer call runs consecutive chunks on two streams: every chunk's index list must stay intact until its launch ends
+    big = np.vstack([U, oracle.uniform_params(230000, seed=5)])
+    with ev_mod.BatchEvaluator(problem, device=0) as ev:
+        ev.set_ordering(False)
+        want, _ = ev.eval_batch(big)
+        ev.set_ordering(True)
+        for _ in range(3):
+            got, _ = ev.eval_batch(big)
+            np.testing.assert_array_equal(got, want)
+        assert ev.ordering_state()[0]
     np.testing.assert_array_equal(ll_u, ref_u[0].cpu().numpy())
     np.testing.assert_array_equal(ll_u2, ll_u)
     np.testing.assert_array_equal(steps_u, ref_u[2].cpu().numpy())
