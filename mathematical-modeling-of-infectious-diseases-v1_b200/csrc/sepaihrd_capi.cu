@@ -1045,6 +1045,7 @@ void** order_slot(sepaihrd_ctx* ctx) { return &ctx->order_model; }
 int order_mode(const sepaihrd_ctx* ctx) { return ctx->order_mode; }
 void set_order_mode(sepaihrd_ctx* ctx, int mode) { ctx->order_mode = mode; }
 int num_sms(const sepaihrd_ctx* ctx) { return ctx->num_sms; }
+bool order_applicable(const sepaihrd_ctx* ctx) { return ctx->n == 4 && ctx->math_mode != SEPAIHRD_MATH_STRICT && !ctx->obs_mismatch; }
 sepaihrd_rc eval_batch_device_unordered(sepaihrd_ctx* ctx, const double* d_params, long long B, long long ld, double* d_ll, unsigned* d_status, int* d_steps) {
     return eval_device_impl(ctx, d_params, B, ld, d_ll, d_status, d_steps, false);
 }

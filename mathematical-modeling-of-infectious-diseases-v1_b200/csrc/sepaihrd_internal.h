@@ -24,6 +24,7 @@ int num_sms(const sepaihrd_ctx* ctx);
 // ---- ordering pass (sepaihrd_order.cu) ----------------------------------------------------------------------------------
 void** order_slot(sepaihrd_ctx* ctx);                 // where the ctx keeps the fitted model (owned by sepaihrd_order.cu)
 int order_mode(const sepaihrd_ctx* ctx);
+bool order_applicable(const sepaihrd_ctx* ctx);       // 4 lanes per set, FAST arithmetic, a scorable problem: where the profiling instantiation exists
 void set_order_mode(sepaihrd_ctx* ctx, int mode);
 sepaihrd_rc order_autofit_host(sepaihrd_ctx* ctx, const double* params, long long B, long long ld);   // host-pointer evaluations: fit when there is no model or the batch looks different
 void order_release(sepaihrd_ctx* ctx);

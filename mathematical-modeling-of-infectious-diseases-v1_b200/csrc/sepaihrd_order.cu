@@ -297,7 +297,7 @@ void order_release(sepaihrd_ctx* ctx) {
 
 sepaihrd_rc order_batch(sepaihrd_ctx* ctx, const double* d_params, long long B, long long ld, const int** perm) {
     OrderModel* m = model_of(ctx, false);
-    if (!m || !m->fitted || order_mode(ctx) == 0 || B < ORDER_MIN_BATCH || B > 0x7fffffffLL) return SEPAIHRD_OK;
+    if (!m || !m->fitted || order_mode(ctx) == 0 || !order_applicable(ctx) || B < ORDER_MIN_BATCH || B > 0x7fffffffLL) return SEPAIHRD_OK;
     const Dims d = dims(ctx);
     if (m->P != d.P) return SEPAIHRD_OK;
     const int which = (int)(m->seq++ & 1u);
@@ -347,7 +347,7 @@ sepaihrd_rc sepaihrd_fit_ordering(sepaihrd_ctx* ctx, const double* params, int64
     if (B < 1 || ld < d.P) return fail_with(SEPAIHRD_ERR_INVALID_ARGUMENT, "Parameter vector size mismatch.");
     const auto ctx_lock = sepaihrd_internal::lock(ctx);
     ORD_TRY(cudaSetDevice(d.device));
-    if (d.n != 4) return SEPAIHRD_OK;                                   // the profile instantiation exists for 4 lanes per set: other problems stay unordered
+    if (!sepaihrd_internal::order_applicable(ctx)) return SEPAIHRD_OK;   // no profiling instantiation (16 lanes per set, STRICT arithmetic): such launches stay unordered
     OrderModel* m = model_of(ctx, true);
     cudaStream_t s = sepaihrd_internal::stream(ctx);
     const int M = (int)std::min<int64_t>(PILOT, B);
@@ -385,7 +385,7 @@ namespace sepaihrd_internal {
 sepaihrd_rc order_autofit_host(sepaihrd_ctx* ctx, const double* params, long long B, long long ld) {
     if (order_mode(ctx) == 0 || B < ORDER_MIN_BATCH) return SEPAIHRD_OK;
     const Dims d = dims(ctx);
-    if (d.n != 4) return SEPAIHRD_OK;
+    if (!order_applicable(ctx)) return SEPAIHRD_OK;
     OrderModel* m = model_of(ctx, true);
     bool refit = !m->fitted && m->fits == 0;
     if (m->fitted) {

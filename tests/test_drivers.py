@@ -266,3 +266,18 @@ def test_metropolis_hastings_writes_the_reference_trace_files(host, problem, tmp
     before = set(os.listdir(ROOT))
     host.optimize("mh", pm, st, ev, target)
     assert set(os.listdir(ROOT)) == before and not os.path.exists(os.path.join(os.getcwd(), "data", "mcmc_samples"))
+
+
+def test_master_generator_draws_for_the_resident_swarm_are_std_mt19937():
+    """resident.std_mt19937_raw (numpy's MT19937 with init_genrand seeding) against the Python restatement of std::mt19937 the
+    sampler tests are built on: the device-resident swarm takes its per-particle seeds from these draws."""
+    import __graft_entry__ as entry
+    entry.load_package()
+    from sepaihrd_b200 import resident
+    from test_pso_variants import StdMt19937
+    for seed in (0, 1, 7, 5489, 2 ** 32 - 1):
+        g = StdMt19937(seed)
+        want = np.array([g.raw() for _ in range(1500)], dtype=np.uint32)
+        np.testing.assert_array_equal(resident.std_mt19937_raw(seed, 1500), want)
+    np.testing.assert_array_equal(resident.initial_cholesky([0.5, 0.0, 2.0]),
+                                  np.diag(np.sqrt(np.array([0.25, 1e-6, 4.0]) * (2.38 * 2.38 / 3.0) + 1e-6)))

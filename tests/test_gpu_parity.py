@@ -666,6 +666,10 @@ def test_ordering_pass_changes_the_schedule_not_the_results(problem, oracle, ev_
             got, _ = ev.eval_batch(big)
             np.testing.assert_array_equal(got, want)
         assert ev.ordering_state()[0]
+    # STRICT arithmetic and 16-age problems have no profiling instantiation: large host batches simply stay unordered
+    with ev_mod.BatchEvaluator(problem, device=0, math=ev_mod.MATH_STRICT) as ev:
+        ev.eval_batch(U[:40000])
+        assert ev.ordering_state() == (False, 0)
     np.testing.assert_array_equal(ll_u, ref_u[0].cpu().numpy())
     np.testing.assert_array_equal(ll_u2, ll_u)
     np.testing.assert_array_equal(steps_u, ref_u[2].cpu().numpy())

@@ -163,3 +163,33 @@ def test_two_processes_exchange_through_peer_memory_pso(problem, mods, tmp_path)
         np.testing.assert_array_equal(q["trace"], ref["trace"])
         np.testing.assert_array_equal(q["best_position"], ref["best_position"])
     np.testing.assert_array_equal(np.concatenate([q["positions"] for q in parts]), ref["final_positions"])
+
+
+def test_resident_sampler_refuses_what_it_does_not_cover(problem, reflect_problem, mods):
+    """No silent fallback: a run that needs the covariance adaptation after burn-in is the host sampler's, an exchange record larger
+    than its mailbox slots or an all-gather before connect are errors, a swarm step without its seed set is an error."""
+    import ctypes as C
+    import torch
+    _, evaluator, resident = mods
+    from sepaihrd_b200 import capi
+    with evaluator.BatchEvaluator(reflect_problem, device=0) as ev:
+        with pytest.raises(capi.SepaihrdError, match="covariance"):
+            resident.DeviceMH(ev, 16, 0, 16, iterations=50, burn_in=10)
+        mh = resident.DeviceMH(ev, 16, 0, 16, iterations=5)
+        with pytest.raises(capi.SepaihrdError, match="before sepaihrd_mh_begin"):
+            mh.iterate(1)
+        mh.close()
+        ev.set_stream(torch.cuda.current_stream().cuda_stream)
+        ex = resident.Exchange(ev, 64)
+        src = torch.zeros(4096, dtype=torch.float64, device="cuda"); dst = torch.zeros(4096, dtype=torch.float64, device="cuda")
+        with pytest.raises(capi.SepaihrdError, match="larger than the mailbox"):
+            ex.all_gather(src.data_ptr(), 4096, dst.data_ptr())
+        ex.close()
+        sw = resident.DeviceSwarm(ev, 100, 0, 100)
+        with pytest.raises(capi.SepaihrdError, match="upload_seeds"):
+            sw.init()
+        sw.upload_seeds(resident.std_mt19937_raw(3, 200).reshape(2, 100))
+        sw.init(); sw.evaluate(); sw.step(0, 0.9, 2.5, 0.5)
+        with pytest.raises(capi.SepaihrdError, match="no seed set"):
+            sw.step(1, 0.9, 2.5, 0.5)
+        sw.close()
