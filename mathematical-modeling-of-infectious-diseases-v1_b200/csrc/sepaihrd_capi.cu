@@ -157,7 +157,7 @@ sepaihrd_rc launch_t(sepaihrd_ctx* ctx, const sepaihrd::KParams& kp_in) {
     kp.tile_counter = ctx->d_tile_counter + (ctx->launch_seq++ % sepaihrd_ctx::N_TILE_COUNTERS);
     CUDA_TRY(cudaMemsetAsync(kp.tile_counter, 0, sizeof(unsigned), ctx->stream));
     auto kern = sepaihrd_batch_kernel<NA, STRICT, MODE, THREADS, MINBLOCKS, LOOP, ONGRID, PROFILE>;
-    const size_t smem = (size_t)kp.blob_bytes + sizeof(double) * (SETS * (size_t)(kp.slot_stride + ((kp.seg_stride + 1) & ~1)) + 2 * THREADS + (size_t)NA * THREADS) + 16;
+    const size_t smem = (size_t)kp.blob_bytes + sizeof(double) * (SETS * (size_t)(kp.slot_stride + ((kp.seg_stride + 1) & ~1)) + 2 * THREADS + (size_t)NA * THREADS) + 64;
     {   // once per device and instantiation, whichever thread / ctx gets here first
         static std::once_flag attr_once[64];
         cudaError_t attr_err = cudaSuccess;
@@ -239,7 +239,11 @@ sepaihrd_rc launch(sepaihrd_ctx* ctx, const sepaihrd::KParams& kp, int mode) {
 #endif
     }
     switch (ctx->n) {
-        case 4: return launch_na<4, 128, 2>(ctx, kp, mode);
+#ifdef SEPAIHRD_EXP_TWO_BLOCKS
+        case 4: return launch_na<4, 128, 2>(ctx, kp, mode);      // round 1's shape: two blocks of four warps per SM
+#else
+        case 4: return launch_na<4, 256, 1>(ctx, kp, mode);      // v16: ONE block of eight warps per SM (the constants are staged once per SM): -1.1 % time
+#endif
         case 16: return launch_na<16, 256, 1>(ctx, kp, mode);   // the 16-age observation block (117 KB) allows one block per SM: make it 8 warps
         default: return fail(SEPAIHRD_ERR_UNSUPPORTED, "GPU kernels are instantiated for 4 and 16 lanes per set (sepaihrd_create pads other age-class counts)");
     }
