@@ -168,8 +168,10 @@ sepaihrd_rc launch_t(sepaihrd_ctx* ctx, const sepaihrd::KParams& kp_in) {
     int occ = 0;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, smem));
     if (occ < 1) return fail(SEPAIHRD_ERR_CUDA, "kernel does not fit on an SM");
-    long long grid = std::min<long long>((kp.tiles * 32 + THREADS - 1) / THREADS, (long long)ctx->num_sms * occ);
+    // one block per tile until the machine is full; a launch smaller than the machine uses only as many warps per block as it needs
+    long long grid = std::min<long long>(kp.tiles, (long long)ctx->num_sms * occ);
     if (grid < 1) grid = 1;
+    kp.active_warps = (int)std::min<long long>(THREADS / 32, (kp.tiles + grid - 1) / grid);
     kern<<<(unsigned)grid, THREADS, smem, ctx->stream>>>(kp);
     CUDA_TRY(cudaGetLastError());
     ctx->launches += 1;

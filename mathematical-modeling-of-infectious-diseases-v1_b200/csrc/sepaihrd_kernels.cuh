@@ -86,6 +86,7 @@ struct KParams {
                                // need similar numbers of step attempts per day
     int* out_profile;          // PROFILE instantiation only: [B][K] attempts (accepted + rejected) made before each grid point
     long long tiles;           // ceil(B / sets_per_warp)
+    int active_warps;          // warps per block that take tiles (all of them unless the launch is smaller than the machine)
     unsigned* tile_counter;    // zeroed before every launch (tiles < 2^32 - grid warps)
 };
 
@@ -531,6 +532,11 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) sepaihrd_batch_kernel(cons
     // warps of their block and the tail of a launch is one warp-tile long.
     constexpr int WSETS = (32 / NA) > 0 ? (32 / NA) : 1;
     const int grp_in_warp = (threadIdx.x & 31) / NA;
+    // A launch with fewer tiles than resident warps (a few thousand sets: multi-chain samplers, line searches) is spread over the
+    // SMs and, inside an SM, over the schedulers: the host launches one block per tile until the machine is full and lets only
+    // the first `active_warps` warps of every block work (64 tiles: one warp on each of 64 SMs, not eight warps on eight SMs) --
+    // its attempts are latency-bound and want a scheduler of their own.
+    if ((int)(threadIdx.x >> 5) >= kp.active_warps) return;
     while (true) {
         unsigned wt = 0;
         if ((threadIdx.x & 31) == 0) wt = atomicAdd(kp.tile_counter, 1u);
