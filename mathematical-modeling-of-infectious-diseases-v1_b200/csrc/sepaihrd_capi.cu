@@ -183,14 +183,17 @@ template <int NA, int THREADS, int MINBLOCKS>
 sepaihrd_rc launch_na(sepaihrd_ctx* ctx, const sepaihrd::KParams& kp, int mode) {
     using namespace sepaihrd;
     const bool strict = ctx->math_mode == SEPAIHRD_MATH_STRICT;
-    if (strict)   // STRICT keeps the reference-order loop
+    if (strict)   // STRICT keeps the reference-order loop (the posterior-predictive series come out of its trajectory instantiation)
         return (mode == MODE_LL) ? launch_t<NA, true, MODE_LL, THREADS, MINBLOCKS, 5>(ctx, kp)
                                  : launch_t<NA, true, MODE_TRAJ, THREADS, MINBLOCKS, 5>(ctx, kp);
 #ifndef SEPAIHRD_EXP_NO_ONGRID
-    if (ctx->bp_on_grid && ctx->math_mode != SEPAIHRD_MATH_FAST_GENERAL)   // breakpoints on output-grid points (e.g. Spain 2020): the build without the mixed-segment attempt body
+    if (ctx->bp_on_grid && ctx->math_mode != SEPAIHRD_MATH_FAST_GENERAL) {   // breakpoints on output-grid points (e.g. Spain 2020): the build without the mixed-segment attempt body
+        if (mode == MODE_PPC) return launch_t<NA, false, MODE_PPC, THREADS, MINBLOCKS, 6, true>(ctx, kp);
         return (mode == MODE_LL) ? launch_t<NA, false, MODE_LL, THREADS, MINBLOCKS, 6, true>(ctx, kp)
                                  : launch_t<NA, false, MODE_TRAJ, THREADS, MINBLOCKS, 6, true>(ctx, kp);
+    }
 #endif
+    if (mode == MODE_PPC) return launch_t<NA, false, MODE_PPC, THREADS, MINBLOCKS, 6>(ctx, kp);
     return (mode == MODE_LL) ? launch_t<NA, false, MODE_LL, THREADS, MINBLOCKS, 6>(ctx, kp)
                              : launch_t<NA, false, MODE_TRAJ, THREADS, MINBLOCKS, 6>(ctx, kp);
 }
@@ -1104,6 +1107,6 @@ sepaihrd_rc simulate_ppc_series(sepaihrd_ctx* ctx, const double* d_params, long 
     kp.ppc_b0 = b0; kp.ppc_B = B_total;
     kp.init_states = d_init; kp.init_stride = 0;
     kp.perm = nullptr; kp.out_profile = nullptr;
-    return launch(ctx, kp, sepaihrd::MODE_TRAJ);
+    return launch(ctx, kp, sepaihrd::MODE_PPC);
 }
 }  // namespace sepaihrd_internal

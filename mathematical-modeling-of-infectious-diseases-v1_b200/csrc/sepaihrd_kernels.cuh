@@ -42,7 +42,7 @@ constexpr int NCOMP = SEPAIHRD_NUM_COMPARTMENTS;  // 11
 constexpr int NDYN = 7;                            // S E P A I H ICU feed the RHS
 constexpr int NPAS = 4;                            // R D CumH CumICU do not
 
-enum { MODE_LL = 0, MODE_TRAJ = 1 };
+enum { MODE_LL = 0, MODE_TRAJ = 1, MODE_PPC = 2 };   // MODE_PPC: FAST instantiation that writes TRAJ_PPC_SERIES and nothing else
 // internal trajectory selector (next to SEPAIHRD_TRAJ_FULL / _OBSERVED): the six posterior-predictive series on the output days
 // t >= 0, draws fastest -- out[6][T][n][B]: daily hospitalisations, ICU admissions, deaths (first differences of CumH / CumICU / D
 // clamped at 0, ResultAggregator.cpp:292-335) and their running sums (.cpp:337-351).  The quantile pass reads them column by column.
@@ -241,7 +241,14 @@ __device__ __forceinline__ void gather_pressure(double* spi, int slot_base, int 
 // runs in, so the lanes exchange u_j = P_j + A_j + theta I_j and lambda is one short dot product (two partial sums).
 // FOLDED=false (a step whose stages sit in different segments; never on the Spain-2020 grid) takes the unfolded
 // row M(age, j) h_infec_j / N_j from shared memory (`mb`, thread-strided) and multiplies by `ba`.
-template <int NA, bool STRICT, bool PASSIVE, bool FOLDED = true>
+// With 16 or more age classes the folded row lives in shared memory too (`mb` then points at it, same stride): 2 NA
+// registers per lane that the stage vectors need more (row_in_smem()).
+// Measured at 16 ages (profiles/r02_v17_16_ages_contact_row_in_smem.txt): it removes the spills everywhere, but only the
+// posterior-predictive instantiation gains (-10 %: its observer keeps six more doubles live); the others lose 5-8 % to the
+// 16 extra LDS.64 per right-hand side, so only MODE_PPC takes it.
+template <int NA, bool STRICT, int MODE>
+__host__ __device__ constexpr bool row_in_smem() { return NA >= 16 && !STRICT && MODE == 2; }
+template <int NA, bool STRICT, bool PASSIVE, bool FOLDED = true, bool MSM = false>
 __device__ __forceinline__ void rhs(const LaneParams<NA>& q, double ba, double* spi, int slot_base, int lane_in_block,
                                     const double (&y)[NDYN], double (&dyn)[NDYN], double (&pas)[NPAS],
                                     const double* mb = nullptr, int mb_stride = 0) {
@@ -267,7 +274,7 @@ __device__ __forceinline__ void rhs(const LaneParams<NA>& q, double ba, double* 
         double acc[NACC];
 #pragma unroll
         for (int j = 0; j < NA; ++j) {
-            const double m = FOLDED ? q.M[j] : mb[j * mb_stride];
+            const double m = (FOLDED && !MSM) ? q.M[j] : mb[j * mb_stride];
             acc[j % NACC] = (j < NACC) ? m * pall[j] : fma(m, pall[j], acc[j % NACC]);
         }
         lam = (NACC == 4) ? (acc[0] + acc[1]) + (acc[2] + acc[3]) : acc[0] + acc[1];
@@ -380,13 +387,14 @@ struct StepSched {
     int nseg;
     double a;
     const double* mb;     // FAST: this lane's unfolded row M(age, j) h_infec_j / N_j in shared memory, stride mb_stride
+    const double* mf;     // FAST, row_in_smem(): this lane's folded row, same stride
     int mb_stride;
 };
 
 // UNIT=true: every stepping lane group of the warp takes a step of exactly hmax (the usual case on a uniform output
 // grid: 48 % of the warp-attempts of the Spain-2020 jitter batch), so the 27 products step x coefficient are the
 // launch constants `hc` instead of 27 DMULs per lane.  hc[i] is computed on the host with the same single rounding.
-template <int NA, bool STRICT, bool MIXED, bool UNIT = false>
+template <int NA, bool STRICT, bool MIXED, bool UNIT = false, bool MSM = false>
 __device__ __forceinline__ void dopri5_attempt(const LaneParams<NA>& q, const StepSched& sc, double* spi, int& pi_slot,
                                                int pi_stride, int lane_in_block, double t, double cur, double t_end,
                                                const double (&x)[NCOMP], const double (&k1)[NCOMP], double (&xn)[NDYN],
@@ -404,18 +412,19 @@ __device__ __forceinline__ void dopri5_attempt(const LaneParams<NA>& q, const St
         return O::mul(sc.beff[s], sc.a);
     };
     auto next_slot = [&]() -> int { pi_slot ^= pi_stride; return pi_slot; };
+    const double* mrow = MIXED ? sc.mb : sc.mf;
     double k2[NDYN], k3[NDYN], k4[NDYN], k5[NDYN], k6[NDYN];
     double y[NDYN], kp_[NPAS], accE[NPAS];
     // stage 2
     { const double f1 = cf(T_B21);
 #pragma unroll
       for (int c = 0; c < NDYN; ++c) y[c] = O::mad(f1, k1[c], x[c]); }
-    rhs<NA, STRICT, false, !MIXED>(q, ba_at(T_A2), spi, next_slot(), lane_in_block, y, k2, kp_, sc.mb, sc.mb_stride);
+    rhs<NA, STRICT, false, !MIXED, MSM>(q, ba_at(T_A2), spi, next_slot(), lane_in_block, y, k2, kp_, mrow, sc.mb_stride);
     // stage 3
     { const double f1 = cf(T_B31), f2 = cf(T_B32);
 #pragma unroll
       for (int c = 0; c < NDYN; ++c) y[c] = O::mad(f2, k2[c], O::mad(f1, k1[c], x[c])); }
-    rhs<NA, STRICT, true, !MIXED>(q, ba_at(T_A3), spi, next_slot(), lane_in_block, y, k3, kp_, sc.mb, sc.mb_stride);
+    rhs<NA, STRICT, true, !MIXED, MSM>(q, ba_at(T_A3), spi, next_slot(), lane_in_block, y, k3, kp_, mrow, sc.mb_stride);
     { const double g1 = cf(T_C1), g3 = cf(T_C3);
       const double e1 = ef(T_DC1), e3 = ef(T_DC3);
 #pragma unroll
@@ -427,7 +436,7 @@ __device__ __forceinline__ void dopri5_attempt(const LaneParams<NA>& q, const St
     { const double f1 = cf(T_B41), f2 = cf(T_B42), f3 = cf(T_B43);
 #pragma unroll
       for (int c = 0; c < NDYN; ++c) y[c] = O::mad(f3, k3[c], O::mad(f2, k2[c], O::mad(f1, k1[c], x[c]))); }
-    rhs<NA, STRICT, true, !MIXED>(q, ba_at(T_A4), spi, next_slot(), lane_in_block, y, k4, kp_, sc.mb, sc.mb_stride);
+    rhs<NA, STRICT, true, !MIXED, MSM>(q, ba_at(T_A4), spi, next_slot(), lane_in_block, y, k4, kp_, mrow, sc.mb_stride);
     { const double g4 = cf(T_C4), e4 = ef(T_DC4);
 #pragma unroll
       for (int c = 0; c < NPAS; ++c) { accN[c] = O::mad(g4, kp_[c], accN[c]); accE[c] = O::mad(e4, kp_[c], accE[c]); } }
@@ -437,7 +446,7 @@ __device__ __forceinline__ void dopri5_attempt(const LaneParams<NA>& q, const St
 #pragma unroll
       for (int c = 0; c < NDYN; ++c)
           y[c] = O::mad(f4, k4[c], O::mad(f3, k3[c], O::mad(f2, k2[c], O::mad(f1, k1[c], x[c])))); }
-    rhs<NA, STRICT, true, !MIXED>(q, ba_at(T_A5), spi, next_slot(), lane_in_block, y, k5, kp_, sc.mb, sc.mb_stride);
+    rhs<NA, STRICT, true, !MIXED, MSM>(q, ba_at(T_A5), spi, next_slot(), lane_in_block, y, k5, kp_, mrow, sc.mb_stride);
     { const double g5 = cf(T_C5), e5 = ef(T_DC5);
 #pragma unroll
       for (int c = 0; c < NPAS; ++c) { accN[c] = O::mad(g5, kp_[c], accN[c]); accE[c] = O::mad(e5, kp_[c], accE[c]); } }
@@ -447,7 +456,7 @@ __device__ __forceinline__ void dopri5_attempt(const LaneParams<NA>& q, const St
 #pragma unroll
       for (int c = 0; c < NDYN; ++c)
           y[c] = O::mad(f5, k5[c], O::mad(f4, k4[c], O::mad(f3, k3[c], O::mad(f2, k2[c], O::mad(f1, k1[c], x[c]))))); }
-    rhs<NA, STRICT, true, !MIXED>(q, ba_at(-1), spi, next_slot(), lane_in_block, y, k6, kp_, sc.mb, sc.mb_stride);
+    rhs<NA, STRICT, true, !MIXED, MSM>(q, ba_at(-1), spi, next_slot(), lane_in_block, y, k6, kp_, mrow, sc.mb_stride);
     { const double g6 = cf(T_C6), e6 = ef(T_DC6);
 #pragma unroll
       for (int c = 0; c < NPAS; ++c) { accN[c] = O::mad(g6, kp_[c], accN[c]); accE[c] = O::mad(e6, kp_[c], accE[c]); } }
@@ -457,7 +466,7 @@ __device__ __forceinline__ void dopri5_attempt(const LaneParams<NA>& q, const St
 #pragma unroll
       for (int c = 0; c < NDYN; ++c)
           xn[c] = O::mad(g6, k6[c], O::mad(g5, k5[c], O::mad(g4, k4[c], O::mad(g3, k3[c], O::mad(g1, k1[c], x[c]))))); }
-    rhs<NA, STRICT, true, !MIXED>(q, ba_at(-1), spi, next_slot(), lane_in_block, xn, k7d, k7p, sc.mb, sc.mb_stride);
+    rhs<NA, STRICT, true, !MIXED, MSM>(q, ba_at(-1), spi, next_slot(), lane_in_block, xn, k7d, k7p, mrow, sc.mb_stride);
     // error estimate
     { const double e1 = ef(T_DC1), e3 = ef(T_DC3), e4 = ef(T_DC4),
                    e5 = ef(T_DC5), e6 = ef(T_DC6), e7 = ef(T_DC7);
@@ -481,6 +490,7 @@ __device__ __forceinline__ void dopri5_attempt(const LaneParams<NA>& q, const St
 template <int NA, bool STRICT, int MODE, int THREADS, int MINBLOCKS, int LOOP, bool ONGRID = false, bool PROFILE = false>
 __global__ void __launch_bounds__(THREADS, MINBLOCKS) sepaihrd_batch_kernel(const KParams kp) {
     static_assert(STRICT ? LOOP == 5 : LOOP == 6, "STRICT keeps the reference-order loop 5; FAST runs loop 6");
+    static_assert(!(STRICT && MODE == MODE_PPC), "STRICT writes the posterior-predictive series from its MODE_TRAJ instantiation");
     using O = Ops<STRICT>;
     constexpr int SETS = THREADS / NA;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -490,6 +500,8 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) sepaihrd_batch_kernel(cons
     double* sbeff = sslots + SETS * kp.slot_stride;
     double* spi = sbeff + SETS * ((kp.seg_stride + 1) & ~1);            // 2 x THREADS doubles, 16-byte aligned
     double* smb = spi + 2 * THREADS;                                    // NA x THREADS doubles: unfolded contact rows (FAST)
+    constexpr bool MSM = row_in_smem<NA, STRICT, MODE>();                     // the same array then holds the row the attempt reads:
+    double* smf = smb;                                                  // folded, or unfolded around a mixed-segment attempt
     uint64_t* bar = reinterpret_cast<uint64_t*>(smb + NA * THREADS);
 
     // ---- stage the constants blob once per block with one TMA bulk copy -----------------------------
@@ -595,15 +607,27 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) sepaihrd_batch_kernel(cons
 #pragma unroll
         for (int j = 0; j < NA; ++j) q.M[j] = sblob[kp.o_M + j * n + age];   // column-major M(age, j)
         int mseg = -1;                 // FAST: schedule segment q.M is currently folded for
-        if (!STRICT) {
+        // unfolded row element M(age, j) h_infec_j / N_j: kept in shared memory, or (MSM) formed again when it is needed
+        auto unfolded = [&](int j) -> double {
+            if (MSM) return sblob[kp.o_M + j * n + age] * (my_slots[sl_age0 + 1 * n + j] * sblob[kp.o_invN + j]);
+            return smb[j * THREADS + threadIdx.x];
+        };
+        if (!STRICT && !MSM) {
 #pragma unroll
             for (int j = 0; j < NA; ++j) smb[j * THREADS + threadIdx.x] = q.M[j] * __shfl_sync(FULL, q.hN, j, NA);
         }
-        auto refold = [&](int s) {     // q.M[j] = M(age, j) h_infec_j / N_j * (beta*kappa)(segment s) * a_age
+        auto refold = [&](int s) {     // row[j] = M(age, j) h_infec_j / N_j * (beta*kappa)(segment s) * a_age
             const double f = my_beff[s] * q.a;
 #pragma unroll
-            for (int j = 0; j < NA; ++j) q.M[j] = smb[j * THREADS + threadIdx.x] * f;
+            for (int j = 0; j < NA; ++j) {
+                const double v = unfolded(j) * f;
+                if (MSM) smf[j * THREADS + threadIdx.x] = v; else q.M[j] = v;
+            }
             mseg = s;
+        };
+        auto unfold = [&]() {          // MSM, around a mixed-segment attempt: the array holds the unfolded row
+#pragma unroll
+            for (int j = 0; j < NA; ++j) smf[j * THREADS + threadIdx.x] = unfolded(j);
         };
 
         // ---- initial state (ObjectiveFunction.cpp:124-163) -------------------------------------------
@@ -641,7 +665,9 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) sepaihrd_batch_kernel(cons
         double* traj_out = nullptr;
         size_t t_rs = 0, t_cs = 1;     // row / column strides of this set's trajectory block
         int W = 0;
-        if (MODE == MODE_TRAJ) {
+        // FAST: the series are MODE_PPC's only output; STRICT decides at run time inside its MODE_TRAJ instantiation
+        const bool is_ppc = STRICT ? (MODE == MODE_TRAJ && kp.traj_what == TRAJ_PPC_SERIES) : (MODE == MODE_PPC);
+        if (MODE != MODE_LL) {
             W = (kp.traj_what == SEPAIHRD_TRAJ_FULL) ? NCOMP * n : 3 * n;
             traj_out = kp.traj_draw_minor ? kp.out_traj + (size_t)b : kp.out_traj + (size_t)b * kp.traj_rows * W;
             t_rs = kp.traj_draw_minor ? (size_t)W * (size_t)kp.B : (size_t)W;
@@ -664,7 +690,7 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) sepaihrd_batch_kernel(cons
             for (int c = 0; c < NDYN; ++c) y0[c] = x[c];
             pi_slot ^= THREADS;
             if (!STRICT) refold(seg);
-            rhs<NA, STRICT, true>(q, ba, spi, pi_slot, threadIdx.x, y0, d0, p0);
+            rhs<NA, STRICT, true, true, MSM>(q, ba, spi, pi_slot, threadIdx.x, y0, d0, p0, smf + threadIdx.x, THREADS);
 #pragma unroll
             for (int c = 0; c < NDYN; ++c) k1[c] = d0[c];
 #pragma unroll
@@ -716,8 +742,8 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) sepaihrd_batch_kernel(cons
             if (MODE == MODE_LL && have && age == 0 && kp.out_steps) { kp.out_steps[(b * K + idx) * 2] = n_acc; kp.out_steps[(b * K + idx) * 2 + 1] = n_rej; }
 #endif
             if constexpr (PROFILE) { if (have && age == 0) kp.out_profile[b * K + idx] = n_acc + n_rej; }
-            if (MODE == MODE_TRAJ) {
-                if (kp.traj_what == TRAJ_PPC_SERIES) {
+            if (MODE != MODE_LL) {
+                if (is_ppc) {
                     ppc_observe(idx, prev_h, prev_i, prev_d, ll_acc_h, ll_acc_i, ll_acc_d);     // the likelihood accumulators are free here: running sums
                 } else if (have && alive && (idx % kp.traj_stride == 0)) {
                     double* row = traj_out + (size_t)(idx / kp.traj_stride) * t_rs;
@@ -761,7 +787,7 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) sepaihrd_batch_kernel(cons
                 const double t_end = t + cur;
                 StepSched sc;
                 sc.ba_step = ba; sc.s_lo = seg; sc.bp = s_bp; sc.beff = my_beff; sc.nseg = nseg; sc.a = q.a;
-                sc.mb = smb + threadIdx.x; sc.mb_stride = THREADS;
+                sc.mb = smb + threadIdx.x; sc.mf = smf + threadIdx.x; sc.mb_stride = THREADS;
                 int s_hi = seg;
                 bool run_mixed = false;
                 if (day_bp) {
@@ -787,11 +813,14 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) sepaihrd_batch_kernel(cons
                 const bool unit = first_of_day && !day_bp && __all_sync(FULL, !active || cur == hmax);
                 first_of_day = false;
                 if (unit)
-                    dopri5_attempt<NA, false, false, true>(q, sc, spi, pi_slot, THREADS, threadIdx.x, t, cur, t_end, x, k1, xn, k7d, k7p, accN, xe, ecur, kp.hc);
-                else if (!ONGRID && run_mixed)
-                    dopri5_attempt<NA, false, true>(q, sc, spi, pi_slot, THREADS, threadIdx.x, t, cur, t_end, x, k1, xn, k7d, k7p, accN, xe, ecur);
+                    dopri5_attempt<NA, false, false, true, MSM>(q, sc, spi, pi_slot, THREADS, threadIdx.x, t, cur, t_end, x, k1, xn, k7d, k7p, accN, xe, ecur, kp.hc);
+                else if (!ONGRID && run_mixed) {
+                    if (MSM) unfold();
+                    dopri5_attempt<NA, false, true, false, MSM>(q, sc, spi, pi_slot, THREADS, threadIdx.x, t, cur, t_end, x, k1, xn, k7d, k7p, accN, xe, ecur);
+                    if (MSM) refold(mseg);
+                }
                 else
-                    dopri5_attempt<NA, false, false>(q, sc, spi, pi_slot, THREADS, threadIdx.x, t, cur, t_end, x, k1, xn, k7d, k7p, accN, xe, ecur);
+                    dopri5_attempt<NA, false, false, false, MSM>(q, sc, spi, pi_slot, THREADS, threadIdx.x, t, cur, t_end, x, k1, xn, k7d, k7p, accN, xe, ecur);
                 // ---- decision: exact compares; coarse magnitude of the worst ratio from the high words ---------
                 double num[NCOMP], den[NCOMP];
                 bool big0 = false, big1 = false, big2 = false;
@@ -910,8 +939,8 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) sepaihrd_batch_kernel(cons
             if (MODE == MODE_LL && have && age == 0 && kp.out_steps) { kp.out_steps[(b * K + idx) * 2] = n_acc; kp.out_steps[(b * K + idx) * 2 + 1] = n_rej; }
 #endif
             // ---- observer -----------------------------------------------------------------------------
-            if (MODE == MODE_TRAJ) {
-                if (kp.traj_what == TRAJ_PPC_SERIES) {
+            if (MODE != MODE_LL) {
+                if (is_ppc) {
                     ppc_observe(idx, prev_h, prev_i, prev_d, ll_acc_h, ll_acc_i, ll_acc_d);
                 } else if (have && alive && (idx % kp.traj_stride == 0)) {
                     double* row = traj_out + (size_t)(idx / kp.traj_stride) * t_rs;
@@ -964,7 +993,7 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) sepaihrd_batch_kernel(cons
                 const double t_end = O::add(t, cur);
                 StepSched sc;
                 sc.ba_step = ba; sc.s_lo = seg; sc.bp = s_bp; sc.beff = my_beff; sc.nseg = nseg; sc.a = q.a;
-                sc.mb = nullptr; sc.mb_stride = 0;
+                sc.mb = nullptr; sc.mf = nullptr; sc.mb_stride = 0;
                 int s_hi = seg;
                 bool run_mixed = false;
                 if (__any_sync(FULL, !(t_end <= bp_next))) {
@@ -1055,7 +1084,7 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) sepaihrd_batch_kernel(cons
         } else {
             if (have && status != 0) {   // failed sets: NaN-fill every row
                 const double qnan = __longlong_as_double(0x7ff8000000000000LL);
-                if (kp.traj_what == TRAJ_PPC_SERIES) {
+                if (is_ppc) {
                     for (int r = 0; r < kp.traj_rows; ++r)
                         for (int sidx = 0; sidx < 6; ++sidx) kp.out_traj[(size_t)sidx * ppc_series + ((size_t)r * n + age) * (size_t)kp.ppc_B + (size_t)(kp.ppc_b0 + b)] = qnan;
                 } else {
