@@ -355,6 +355,16 @@ sepaihrd_rc sepaihrd_set_ordering(sepaihrd_ctx* ctx, int32_t mode);
 sepaihrd_rc sepaihrd_fit_ordering(sepaihrd_ctx* ctx, const double* params, int64_t B, int64_t ld, int32_t params_on_device);
 sepaihrd_rc sepaihrd_ordering_state(const sepaihrd_ctx* ctx, int32_t* out_fitted, int64_t* out_fits);
 
+/* Exact sample quantiles (linear interpolation between order statistics, numpy's default) of n_cols device-resident columns of
+ * B doubles each, columns contiguous: d_columns[col * B + draw].  NaNs are left out (a column of NaNs gives NaN).  This is the
+ * second half of sepaihrd_posterior_predictive, exposed for callers that hold their own series on the device (replaces the
+ * per-column accumulators of ResultAggregator.cpp:276-371 for any series, not only the six built-in ones).
+ *   probs   host, [n_probs], each in [0, 1];  d_out  device, [n_cols][n_probs];  enqueued on the ctx stream.
+ *   path    0: by size (a cluster of 4 or 8 thread blocks holds a column in shared memory up to ~208 k draws, one block per
+ *              column sweeping global memory beyond); 1: force the one-block-per-column kernel; 2: force the cluster kernel. */
+sepaihrd_rc sepaihrd_column_quantiles_device(sepaihrd_ctx* ctx, const double* d_columns, int64_t B, int64_t n_cols, int32_t n_probs,
+                                             const double* probs, double* d_out, int32_t path);
+
 /* The aggregation passes (sepaihrd_posterior_predictive) keep their device work buffers in the ctx and reuse them across
  * calls; this frees them (they are also freed by sepaihrd_destroy). */
 sepaihrd_rc sepaihrd_release_scratch(sepaihrd_ctx* ctx);

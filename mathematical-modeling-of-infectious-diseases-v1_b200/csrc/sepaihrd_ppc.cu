@@ -21,7 +21,10 @@
 #include <cstdint>
 #include <cstdlib>
 #include <algorithm>
+#include <mutex>
 #include <vector>
+
+#include <cooperative_groups.h>
 
 #include "sepaihrd_internal.h"
 
@@ -266,10 +269,407 @@ __global__ void __launch_bounds__(SEL_THREADS) ppc_select_kernel(const double* _
                 if (t_want[t] == i0) a = sel_value(t_value[t]);
                 if (t_want[t] == i1) c = sel_value(t_value[t]);
             }
-            out_all[(size_t)col * Q_total + q_first + q] = a + (h - (double)i0) * (c - a);
+            out_all[(size_t)col * Q_total + q_first + q] = __dadd_rn(a, __dmul_rn(h - (double)i0, c - a));   // unfused: the same bits as the host formula
         }
         __syncthreads();
     }
+}
+
+// ---- the same selection with the column held ON CHIP ---------------------------------------------------------------------
+// ppc_select_kernel above is instruction-bound (ncu, 100 k draws x 4 ages: 142 thread-instructions per key, 56 % issue slots
+// busy) and reads every column 3.6 x from DRAM, because 2 x 148 resident columns of 800 KB do not fit the L2.  Here a CLUSTER
+// of CL thread blocks owns a column: block r loads draws [r S, (r + 1) S) ONCE, as order-preserving keys (high and low words in
+// separate arrays), into its shared memory (CL = 4: 4 x 200 KB hold 100 k draws); every later sweep runs on shared memory.
+// The narrowing works on rel = key - (smallest high word << 32): its first 12-bit digit covers exactly the spread of the
+// column (2048-4096 cells in use whatever binade boundary the values straddle), so ~25-50 keys share a cell and one step is
+// enough for the usual column; while that digit lies in the high word a sweep reads 4 bytes per key.
+// The blocks exchange only small things through distributed shared memory:
+//   * after the load: min / max high word and count of each slice (every block combines all CL triples itself);
+//   * per narrowing step: each block histograms its slice, then every thread sums ITS four cells over the CL histograms
+//     (one 16-byte remote load per block), a block-wide scan finds the cell of every wanted rank -- redundantly and
+//     identically in every block, so no result has to be sent back;
+//   * the <= CS_CAP survivors of a rank's bucket are PUSHED (remote atomic + remote store) into the list of the block that
+//     owns the bucket (bucket a -> block a mod CL), which picks the rank by counting and writes the order statistic.
+// The linear interpolation between order statistics is a separate tiny kernel (ppc_finalize_kernel), so no block waits for
+// another one's pick.  Barriers per column: 3 cluster-wide (after load, after histogram, after push) + 2 per extra step.
+// The bookkeeping between sweeps (wanted ranks, distinct buckets) is done by one WARP with match / ballot, not by one thread.
+namespace cg = cooperative_groups;
+constexpr int CS_THREADS = 1024, CS_CELLS = 4096, CS_MAXT = 16, CS_CAP = 192, CS_LOADS = 8;
+constexpr unsigned CS_NAN_HI = 0xffffffffu;              // high word of the key NaNs are stored as (~0: no double maps to it)
+
+struct CsCtl {
+    unsigned st_min[2], st_max[2], st_cnt[2];            // this block's slice, double-buffered by column parity (read by the others)
+    unsigned long long t_prefix[CS_MAXT], b_prefix[CS_MAXT];
+    long long t_want[CS_MAXT];
+    unsigned t_rank[CS_MAXT], t_size[CS_MAXT], n_rank[CS_MAXT], n_size[CS_MAXT], n_digit[CS_MAXT], base[CS_MAXT], bucket_base[CS_MAXT];
+    int t_bucket[CS_MAXT];
+    unsigned own_n[CS_MAXT];                              // keys pushed into the lists this block owns
+    unsigned warp_tot[32];
+    unsigned cnt, base_hi;
+    int n_targets, n_buckets, shift, go;
+};
+constexpr size_t cs_ctl_bytes() { return (sizeof(CsCtl) + 15) & ~(size_t)15; }
+template <int CL> constexpr int cs_own_slots() { return (CS_MAXT + CL - 1) / CL; }
+// control block, histogram, first-digit -> bucket map, owned candidate lists; the keys follow
+template <int CL> constexpr size_t cs_fixed_bytes() {
+    return cs_ctl_bytes() + sizeof(unsigned) * CS_CELLS + CS_CELLS + sizeof(unsigned long long) * cs_own_slots<CL>() * CS_CAP;
+}
+
+__device__ __forceinline__ unsigned long long cs_rel(unsigned hi, unsigned lo, unsigned base_hi) {
+    return ((unsigned long long)(hi - base_hi) << 32) | (unsigned long long)lo;
+}
+
+template <int CL>
+__global__ void __launch_bounds__(CS_THREADS, 1) ppc_select_cluster_kernel(const double* __restrict__ series, long long B, long long n_cols, int Q,
+                                                                           const double* __restrict__ probs, double* __restrict__ tvals,
+                                                                           long long* __restrict__ col_cnt) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned cr = cluster.block_rank();
+    const long long cluster_id = blockIdx.x / CL, n_clusters = gridDim.x / CL;
+    extern __shared__ __align__(16) unsigned char cs_raw[];
+    CsCtl* ctl = reinterpret_cast<CsCtl*>(cs_raw);
+    unsigned* hist = reinterpret_cast<unsigned*>(cs_raw + cs_ctl_bytes());
+    unsigned char* cellmap = reinterpret_cast<unsigned char*>(hist + CS_CELLS);   // first digit -> 0 (no live bucket), bucket + 1, or 255 (several)
+    unsigned long long* lists = reinterpret_cast<unsigned long long*>(cellmap + CS_CELLS);
+    const int tid = threadIdx.x, lane = tid & 31;
+    const long long S = (B + CL - 1) / CL;
+    const long long s0 = (cr * S < B) ? cr * S : B, s1 = (s0 + S < B) ? s0 + S : B;
+    const int nl = (int)(s1 - s0);
+    unsigned* khi = reinterpret_cast<unsigned*>(lists + cs_own_slots<CL>() * CS_CAP);
+    unsigned* klo = khi + ((S + 3) & ~3LL);
+    for (int i = tid; i < CS_CELLS / 4; i += CS_THREADS) reinterpret_cast<unsigned*>(cellmap)[i] = 0u;
+    // the only read of a column: CS_LOADS coalesced loads in flight per thread, keys to shared memory, slice statistics
+    auto load_column = [&](long long col, int parity) {
+        const double* v = series + (size_t)col * B + s0;
+        if (tid == 0) { ctl->st_min[parity] = 0xffffffffu; ctl->st_max[parity] = 0u; ctl->st_cnt[parity] = 0u; }
+        __syncthreads();
+        unsigned lo_hi = 0xffffffffu, hi_hi = 0u, c = 0u;
+        auto take = [&](int i, double x) {
+            const unsigned long long b = (unsigned long long)__double_as_longlong(x);
+            unsigned h = (unsigned)(b >> 32), l = (unsigned)b;
+            const unsigned sgn = (unsigned)((int)h >> 31);          // all ones for a negative value
+            h ^= sgn | 0x80000000u; l ^= sgn;                          // sel_key, word by word
+            if (x != x) { h = CS_NAN_HI; l = 0xffffffffu; } else { lo_hi = min(lo_hi, h); hi_hi = max(hi_hi, h); ++c; }
+            khi[i] = h; klo[i] = l;
+        };
+        int i0 = tid;
+        for (; i0 + (CS_LOADS - 1) * CS_THREADS < nl; i0 += CS_LOADS * CS_THREADS) {
+            double xs[CS_LOADS];
+#pragma unroll
+            for (int u = 0; u < CS_LOADS; ++u) xs[u] = __ldg(v + i0 + u * CS_THREADS);
+#pragma unroll
+            for (int u = 0; u < CS_LOADS; ++u) take(i0 + u * CS_THREADS, xs[u]);
+        }
+        if (i0 < nl) {
+            double xs[CS_LOADS];
+#pragma unroll
+            for (int u = 0; u < CS_LOADS; ++u) { const int i = i0 + u * CS_THREADS; xs[u] = (i < nl) ? __ldg(v + i) : 0.0; }
+#pragma unroll
+            for (int u = 0; u < CS_LOADS; ++u) { const int i = i0 + u * CS_THREADS; if (i < nl) take(i, xs[u]); }
+        }
+        lo_hi = __reduce_min_sync(0xffffffffu, lo_hi); hi_hi = __reduce_max_sync(0xffffffffu, hi_hi); c = __reduce_add_sync(0xffffffffu, c);
+        if (lane == 0) { atomicMin(&ctl->st_min[parity], lo_hi); atomicMax(&ctl->st_max[parity], hi_hi); atomicAdd(&ctl->st_cnt[parity], c); }
+    };
+    if (tid < CS_MAXT) ctl->own_n[tid] = 0u;
+    int parity = 0;
+    if (cluster_id < n_cols) load_column(cluster_id, 0);
+    // Software pipeline: the keys of a column are dead once its survivors are pushed, so the NEXT column is loaded between the
+    // arrival at the "lists complete" barrier and the wait on it -- the load latency covers the barrier skew and vice versa.
+    for (long long col = cluster_id; col < n_cols; col += n_clusters, parity ^= 1) {
+        const long long next_col = col + n_clusters;
+        bool pushed = false;
+        cluster.sync();                                                                    // every slice is loaded and summarised
+        if (tid < 32) {                                                                    // one warp: column statistics, wanted ranks
+            unsigned mn = 0xffffffffu, mx = 0u, cn = 0u;
+            if (lane < CL) {
+                const CsCtl* rc = cluster.map_shared_rank(ctl, lane);
+                mn = rc->st_min[parity]; mx = rc->st_max[parity]; cn = rc->st_cnt[parity];
+            }
+            mn = __reduce_min_sync(0xffffffffu, mn); mx = __reduce_max_sync(0xffffffffu, mx); cn = __reduce_add_sync(0xffffffffu, cn);
+            const long long cnt = (long long)cn;
+            long long r = -1 - lane;                                                       // lanes without a rank: distinct, negative
+            const bool has = (cnt > 0) && (lane < 2 * Q);
+            if (has) {
+                const double h = (double)(cnt - 1) * probs[lane >> 1];
+                long long i0 = (long long)floor(h);
+                if (i0 < 0) i0 = 0;
+                if (i0 > cnt - 1) i0 = cnt - 1;
+                const long long i1 = (i0 + 1 < cnt) ? i0 + 1 : i0;
+                r = (lane & 1) ? i1 : i0;
+            }
+            const unsigned same = __match_any_sync(0xffffffffu, r);
+            const bool first = has && ((same & ((1u << lane) - 1u)) == 0u);               // ranks without repeats, in order of appearance
+            const unsigned fm = __ballot_sync(0xffffffffu, first);
+            if (first) {
+                const int t = __popc(fm & ((1u << lane) - 1u));
+                ctl->t_want[t] = r; ctl->t_rank[t] = (unsigned)r; ctl->t_prefix[t] = 0ULL; ctl->t_size[t] = cn;
+            }
+            if (lane == 0) {
+                ctl->n_targets = __popc(fm); ctl->cnt = cn; ctl->base_hi = mn;
+                ctl->shift = (cn > 0) ? 32 + (32 - __clz(mx - mn)) : 0;                    // rel < 2^shift
+                if (cr == 0) col_cnt[col] = cnt;
+            }
+        }
+        __syncthreads();
+        int first_nshift = 0;                                                              // where the first digit sits: what cellmap is keyed by
+        int round = 0;
+        if (ctl->cnt != 0u) {                                                              // (no valid draw: nothing to select; every block sees the same count)
+        const unsigned base_hi = ctl->base_hi;
+        while (true) {
+            if (tid < 32) {                                                                // one warp: go on?  distinct buckets
+                const int nt = ctl->n_targets;
+                const bool valid = lane < nt;
+                const unsigned long long p = valid ? ctl->t_prefix[lane] : 0ULL;
+                const bool large = valid && (ctl->t_size[lane] > (unsigned)CS_CAP);
+                const unsigned vm = __ballot_sync(0xffffffffu, valid);
+                const unsigned any_large = __ballot_sync(0xffffffffu, large);
+                unsigned same = 0u;
+                if (valid) same = __match_any_sync(vm, p);
+                const int leader = valid ? (__ffs(same) - 1) : 0;
+                const unsigned lm = __ballot_sync(0xffffffffu, valid && leader == lane);
+                if (valid) {
+                    const int a = __popc(lm & ((1u << leader) - 1u));
+                    ctl->t_bucket[lane] = a;
+                    if (leader == lane) ctl->b_prefix[a] = p;
+                }
+                if (lane == 0) { ctl->n_buckets = __popc(lm); ctl->go = (any_large != 0u) && (ctl->shift > 0); }
+            }
+            __syncthreads();
+            if (!ctl->go) break;
+            const int nb = ctl->n_buckets;
+            const int dig = (nb == 1) ? 12 : (nb <= 4) ? 10 : 8;
+            const int shift = ctl->shift, nshift = (shift > dig) ? shift - dig : 0, width = shift - nshift;
+            const int ncells = nb << width;
+            const unsigned dmask = (1u << width) - 1u;
+            if (round == 0) first_nshift = nshift;
+            else cluster.sync();                                                           // nobody reads the previous step's histograms any more
+            for (int i = tid; i < ncells; i += CS_THREADS) hist[i] = 0u;
+            if (round > 0 && tid == 0) {                                                   // first digit -> live bucket(s)
+                for (int a = 0; a < nb; ++a) {
+                    const unsigned d1 = (unsigned)(ctl->b_prefix[a] >> (first_nshift - shift));
+                    cellmap[d1] = (cellmap[d1] == 0) ? (unsigned char)(a + 1) : (unsigned char)255;
+                }
+            }
+            __syncthreads();
+            if (round == 0) {                                                              // every valid key: rel < 2^shift, one bucket
+                if (nshift >= 32) {
+                    const int sh = nshift - 32;
+#pragma unroll 4
+                    for (int i = tid; i < nl; i += CS_THREADS) {
+                        const unsigned h = khi[i];
+                        if (h != CS_NAN_HI) atomicAdd(&hist[(h - base_hi) >> sh], 1u);
+                    }
+                } else {
+#pragma unroll 4
+                    for (int i = tid; i < nl; i += CS_THREADS) {
+                        const unsigned h = khi[i];
+                        if (h != CS_NAN_HI) atomicAdd(&hist[(unsigned)(cs_rel(h, klo[i], base_hi) >> nshift)], 1u);
+                    }
+                }
+            } else {
+#pragma unroll 4
+                for (int i = tid; i < nl; i += CS_THREADS) {
+                    const unsigned h = khi[i];
+                    if (h == CS_NAN_HI) continue;
+                    const unsigned long long rel = cs_rel(h, klo[i], base_hi);
+                    const unsigned cm = cellmap[(unsigned)(rel >> first_nshift)];
+                    if (cm != 0u) {
+                        const unsigned long long hi = (shift < 64) ? (rel >> shift) : 0ULL;
+                        const unsigned d = (unsigned)(rel >> nshift) & dmask;
+                        if (cm != 255u) { if (hi == ctl->b_prefix[cm - 1]) atomicAdd(&hist[((cm - 1) << width) + d], 1u); }
+                        else for (int a = 0; a < nb; ++a) if (hi == ctl->b_prefix[a]) atomicAdd(&hist[((unsigned)a << width) + d], 1u);
+                    }
+                }
+            }
+            cluster.sync();                                                                // all CL histograms are complete
+            if (round > 0 && tid < nb) cellmap[(unsigned)(ctl->b_prefix[tid] >> (first_nshift - shift))] = 0;     // leave the map clean
+            // my four cells, summed over the blocks; exclusive scan over all cells
+            unsigned h4[4] = {0u, 0u, 0u, 0u};
+            const int c0 = 4 * tid;
+            if (c0 < ncells) {
+#pragma unroll
+                for (int r = 0; r < CL; ++r) {
+                    const uint4 hv = *reinterpret_cast<const uint4*>(cluster.map_shared_rank(hist, r) + c0);
+                    h4[0] += hv.x; h4[1] += hv.y; h4[2] += hv.z; h4[3] += hv.w;
+                }
+                if (c0 + 1 >= ncells) h4[1] = 0u;
+                if (c0 + 2 >= ncells) h4[2] = 0u;
+                if (c0 + 3 >= ncells) h4[3] = 0u;
+            }
+            const unsigned mine = h4[0] + h4[1] + h4[2] + h4[3];
+            unsigned incl = mine;
+            for (int o = 1; o < 32; o <<= 1) { const unsigned up = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += up; }
+            if (lane == 31) ctl->warp_tot[tid >> 5] = incl;
+            __syncthreads();
+            if (tid < 32) {
+                unsigned w = ctl->warp_tot[tid], wi = w;
+                for (int o = 1; o < 32; o <<= 1) { const unsigned up = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += up; }
+                ctl->warp_tot[tid] = wi - w;
+            }
+            __syncthreads();
+            const unsigned excl = ctl->warp_tot[tid >> 5] + (incl - mine);                  // counts fit 32 bits: a column has < 2^31 draws
+            // where every bucket starts in the scan: its first cell belongs to the thread that holds cell (a << width)
+            if (c0 < ncells) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int ci = c0 + j;
+                    if (ci < ncells && (ci & (int)dmask) == 0) {
+                        unsigned e = excl;
+                        for (int jj = 0; jj < j; ++jj) e += h4[jj];
+                        ctl->bucket_base[ci >> width] = e;
+                    }
+                }
+            }
+            __syncthreads();
+            const int nt = ctl->n_targets;
+            if (tid < CS_MAXT) ctl->base[tid] = (tid < nt) ? ctl->bucket_base[ctl->t_bucket[tid]] + ctl->t_rank[tid] : 0xffffffffu;
+            __syncthreads();
+            if (mine != 0u) {
+#pragma unroll
+                for (int t = 0; t < CS_MAXT; ++t) {
+                    const unsigned pos = ctl->base[t];
+                    if (pos - excl < mine) {                                               // excl <= pos < excl + mine (unsigned wrap-around)
+                        unsigned e = excl;
+                        int j = 0;
+                        for (; j < 3; ++j) { if (pos - e < h4[j]) break; e += h4[j]; }
+                        ctl->n_rank[t] = pos - e;
+                        ctl->n_size[t] = h4[j];
+                        ctl->n_digit[t] = (unsigned)(c0 + j) & dmask;
+                    }
+                }
+            }
+            __syncthreads();
+            if (tid < nt) {
+                ctl->t_prefix[tid] = (ctl->t_prefix[tid] << width) | (unsigned long long)ctl->n_digit[tid];
+                ctl->t_rank[tid] = ctl->n_rank[tid];
+                ctl->t_size[tid] = ctl->n_size[tid];
+            }
+            if (tid == 0) ctl->shift = nshift;
+            __syncthreads();
+            ++round;
+        }
+        const int shift = ctl->shift, nt = ctl->n_targets, nb = ctl->n_buckets;
+        bool small = true;
+        for (int t = 0; t < nt; ++t) small = small && (ctl->t_size[t] <= (unsigned)CS_CAP);
+        if (!small) {
+            // bits used up with a large bucket: all its keys are equal, the prefix IS rel
+            if (cr == 0 && tid < nt) tvals[(size_t)col * CS_MAXT + tid] = sel_value(ctl->t_prefix[tid] + ((unsigned long long)base_hi << 32));
+        } else {
+        if (round > 0) {                                                                   // first digit -> live bucket(s)
+            if (tid == 0) {
+                for (int a = 0; a < nb; ++a) {
+                    const unsigned d1 = (unsigned)(ctl->b_prefix[a] >> (first_nshift - shift));
+                    cellmap[d1] = (cellmap[d1] == 0) ? (unsigned char)(a + 1) : (unsigned char)255;
+                }
+            }
+            __syncthreads();
+        }
+        {   // push the survivors to the blocks that own their buckets
+            auto push = [&](int a, unsigned h, unsigned l) {
+                const int owner = a % CL, slot = a / CL;
+                const unsigned pos = atomicAdd(cluster.map_shared_rank(&ctl->own_n[slot], owner), 1u);
+                if (pos < (unsigned)CS_CAP) cluster.map_shared_rank(lists, owner)[slot * CS_CAP + pos] = ((unsigned long long)h << 32) | (unsigned long long)l;
+            };
+            if (round == 0) {                                                              // a column of <= CS_CAP valid draws, or of one value
+                for (int i = tid; i < nl; i += CS_THREADS) { const unsigned h = khi[i]; if (h != CS_NAN_HI) push(0, h, klo[i]); }
+            } else if (first_nshift >= 32) {
+                const int sh = first_nshift - 32;
+#pragma unroll 4
+                for (int i = tid; i < nl; i += CS_THREADS) {
+                    const unsigned h = khi[i];
+                    if (h == CS_NAN_HI) continue;
+                    const unsigned cm = cellmap[(h - base_hi) >> sh];
+                    if (cm != 0u) {
+                        const unsigned l = klo[i];
+                        const unsigned long long rel = cs_rel(h, l, base_hi);
+                        const unsigned long long hi = (shift < 64) ? (rel >> shift) : 0ULL;
+                        if (cm != 255u) { if (hi == ctl->b_prefix[cm - 1]) push((int)cm - 1, h, l); }
+                        else for (int a = 0; a < nb; ++a) if (hi == ctl->b_prefix[a]) push(a, h, l);
+                    }
+                }
+            } else {
+#pragma unroll 4
+                for (int i = tid; i < nl; i += CS_THREADS) {
+                    const unsigned h = khi[i];
+                    if (h == CS_NAN_HI) continue;
+                    const unsigned l = klo[i];
+                    const unsigned long long rel = cs_rel(h, l, base_hi);
+                    const unsigned cm = cellmap[(unsigned)(rel >> first_nshift)];
+                    if (cm != 0u) {
+                        const unsigned long long hi = (shift < 64) ? (rel >> shift) : 0ULL;
+                        if (cm != 255u) { if (hi == ctl->b_prefix[cm - 1]) push((int)cm - 1, h, l); }
+                        else for (int a = 0; a < nb; ++a) if (hi == ctl->b_prefix[a]) push(a, h, l);
+                    }
+                }
+            }
+        }
+        cluster.barrier_arrive();                                                          // my pushes are out (release)
+        pushed = true;
+        }   // small
+        }   // cnt != 0
+        if (next_col < n_cols) load_column(next_col, parity ^ 1);
+        if (pushed) {
+            cluster.barrier_wait();                                                        // every list is complete
+            const int shift = ctl->shift, nt = ctl->n_targets, nb = ctl->n_buckets;
+            if (round > 0 && tid < nb) cellmap[(unsigned)(ctl->b_prefix[tid] >> (first_nshift - shift))] = 0;     // leave the map clean
+            // every rank whose bucket this block owns is picked by its own group of CS_CAP threads, all groups at once
+            const int grp = tid / CS_CAP, c = tid % CS_CAP;
+            int seen = 0;
+            for (int t = 0; t < nt; ++t) {
+                const int a = ctl->t_bucket[t];
+                if (a % CL != (int)cr) continue;
+                if (seen++ % (CS_THREADS / CS_CAP) != grp) continue;
+                const unsigned long long* cand = lists + (a / CL) * CS_CAP;
+                const unsigned m = (ctl->own_n[a / CL] < (unsigned)CS_CAP) ? ctl->own_n[a / CL] : (unsigned)CS_CAP;
+                const unsigned k = ctl->t_rank[t];
+                if ((unsigned)c < m) {
+                    const unsigned long long key = cand[c];
+                    unsigned less = 0, eq = 0;
+                    for (unsigned j = 0; j < m; ++j) { const unsigned long long o = cand[j]; less += (o < key); eq += (o == key); }
+                    if (less <= k && k < less + eq) tvals[(size_t)col * CS_MAXT + t] = sel_value(key);   // every candidate of that value writes the same bits
+                }
+            }
+        }
+        __syncthreads();
+        if (tid < CS_MAXT) ctl->own_n[tid] = 0u;                                           // refilled only after the next column's barriers
+    }
+    cluster.sync();                                                                        // no block leaves while another may still read its shared memory
+}
+
+// quantile q of column col = linear interpolation between the two order statistics the select left in tvals (target order
+// rebuilt the way the select built it)
+__global__ void ppc_finalize_kernel(const double* __restrict__ tvals, const long long* __restrict__ col_cnt, long long n_cols, int Q,
+                                    const double* __restrict__ probs, double* __restrict__ out_all, int Q_total, int q_first) {
+    const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (idx >= n_cols * Q) return;
+    const long long col = idx / Q;
+    const int q = (int)(idx % Q);
+    const long long cnt = col_cnt[col];
+    if (cnt <= 0) { out_all[(size_t)col * Q_total + q_first + q] = nan(""); return; }
+    long long want[CS_MAXT];
+    int nt = 0;
+    double hq = 0.0;
+    long long q_i0 = 0, q_i1 = 0;
+    for (int qq = 0; qq <= q; ++qq) {
+        const double h = (double)(cnt - 1) * probs[qq];
+        long long i0 = (long long)floor(h);
+        if (i0 < 0) i0 = 0;
+        if (i0 > cnt - 1) i0 = cnt - 1;
+        const long long i1 = (i0 + 1 < cnt) ? i0 + 1 : i0;
+        for (int w = 0; w < 2; ++w) {
+            const long long r = w ? i1 : i0;
+            bool seen = false;
+            for (int t = 0; t < nt; ++t) seen = seen || (want[t] == r);
+            if (!seen) { want[nt] = r; ++nt; }
+        }
+        if (qq == q) { hq = h; q_i0 = i0; q_i1 = i1; }
+    }
+    double a = 0.0, c = 0.0;
+    for (int t = 0; t < nt; ++t) {
+        if (want[t] == q_i0) a = tvals[(size_t)col * CS_MAXT + t];
+        if (want[t] == q_i1) c = tvals[(size_t)col * CS_MAXT + t];
+    }
+    out_all[(size_t)col * Q_total + q_first + q] = __dadd_rn(a, __dmul_rn(hq - (double)q_i0, c - a));   // unfused: the same bits as the host formula
 }
 
 __global__ void ppc_count_valid_kernel(const unsigned* st, long long B, unsigned long long* out) {
@@ -277,6 +677,84 @@ __global__ void ppc_count_valid_kernel(const unsigned* st, long long B, unsigned
     const unsigned ok = (i < B && st[i] == 0u) ? 1u : 0u;
     const unsigned m = __ballot_sync(0xffffffffu, ok);
     if ((threadIdx.x & 31) == 0 && m) atomicAdd(out, (unsigned long long)__popc(m));
+}
+
+
+template <int CL>
+cudaError_t launch_cluster_select(cudaStream_t s, int device, long long B, long long n_cols, int Q, const double* d_series, const double* d_probs,
+                                  double* d_tvals, long long* d_colcnt) {
+    auto kern = ppc_select_cluster_kernel<CL>;
+    const size_t smem = cs_fixed_bytes<CL>() + 2 * sizeof(unsigned) * (size_t)((((B + CL - 1) / CL) + 3) & ~3LL);   // high and low key words
+    static std::once_flag attr_once[64];
+    cudaError_t err = cudaSuccess;
+    std::call_once(attr_once[device & 63], [&] {
+        int max_optin = 0;
+        err = cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+        if (err == cudaSuccess) err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin);
+    });
+    if (err != cudaSuccess) return err;
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cfg.blockDim = dim3(CS_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cfg.gridDim = dim3(CL);
+    int n_clusters = 0;
+    err = cudaOccupancyMaxActiveClusters(&n_clusters, kern, &cfg);
+    if (err != cudaSuccess) return err;
+    if (n_clusters < 1) return cudaErrorLaunchOutOfResources;
+    cfg.gridDim = dim3((unsigned)(std::min<long long>(n_cols, n_clusters) * CL));
+    return cudaLaunchKernelEx(&cfg, kern, d_series, B, n_cols, Q, d_probs, d_tvals, d_colcnt);
+}
+
+// how many draws a block of the cluster kernel can hold
+template <int CL>
+long long cluster_slice_cap(int device) {
+    int max_optin = 0;
+    if (cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device) != cudaSuccess) return 0;
+    const long long room = (long long)max_optin - (long long)cs_fixed_bytes<CL>();
+    return room > 0 ? (room / (long long)sizeof(unsigned long long)) & ~3LL : 0;
+}
+
+// Quantiles of n_cols device columns of B values each: d_q[col][n_probs].  path: 0 = by size (the cluster kernel while a column fits
+// the shared memory of 4 or 8 blocks, the one-block-per-column kernel beyond), 1 = one block per column, 2 = cluster kernel or fail.
+sepaihrd_rc select_quantiles(sepaihrd_ctx* ctx, cudaStream_t s, int device, const double* d_series, long long B, long long all_cols, int n_probs,
+                             const double* d_probs, double* d_q, double* d_tvals, long long* d_colcnt, int path) {
+    using sepaihrd_internal::fail_with;
+    static const char* env_path = std::getenv("SEPAIHRD_PPC_SELECT");
+    if (path == 0 && env_path) path = (env_path[0] == 'b') ? 1 : (env_path[0] == 'c') ? 2 : 0;
+    int cl = 0;
+    if (path != 1) {
+        if ((B + 3) / 4 <= cluster_slice_cap<4>(device)) cl = 4;
+        else if ((B + 7) / 8 <= cluster_slice_cap<8>(device)) cl = 8;
+        if (cl == 0 && path == 2) return fail_with(SEPAIHRD_ERR_UNSUPPORTED, "a column of this many draws does not fit the shared memory of 8 thread blocks");
+    }
+    static const int env_grid = std::getenv("SEPAIHRD_PPC_GRID") ? std::atoi(std::getenv("SEPAIHRD_PPC_GRID")) : 0;
+    static const int env_threads = std::getenv("SEPAIHRD_PPC_THREADS") ? std::atoi(std::getenv("SEPAIHRD_PPC_THREADS")) : 0;
+    for (int q0 = 0; q0 < n_probs; q0 += SEL_MAXT / 2) {
+        const int qg = std::min(SEL_MAXT / 2, n_probs - q0);
+        if (cl != 0) {
+            const cudaError_t e = (cl == 4) ? launch_cluster_select<4>(s, device, B, all_cols, qg, d_series, d_probs + q0, d_tvals, d_colcnt)
+                                            : launch_cluster_select<8>(s, device, B, all_cols, qg, d_series, d_probs + q0, d_tvals, d_colcnt);
+            if (e != cudaSuccess) return fail_with(SEPAIHRD_ERR_CUDA, cudaGetErrorString(e));
+            const long long work = all_cols * qg;
+            ppc_finalize_kernel<<<(unsigned)((work + 255) / 256), 256, 0, s>>>(d_tvals, d_colcnt, all_cols, qg, d_probs + q0, d_q, n_probs, q0);
+            if (cudaGetLastError() != cudaSuccess) return fail_with(SEPAIHRD_ERR_CUDA, "ppc_finalize_kernel launch failed");
+            sepaihrd_internal::count_launches(ctx, 2);
+        } else {
+            // Columns in flight x column size is what the later sweeps of a column find in L2 (126 MB)
+            const int threads = env_threads ? env_threads : PPC_DEFAULT_THREADS;
+            const unsigned grid = (unsigned)std::min<long long>(all_cols, env_grid ? env_grid : PPC_DEFAULT_GRID);
+            if (threads == 1024) ppc_select_kernel<1024><<<grid, 1024, 0, s>>>(d_series, B, all_cols, qg, d_probs, d_q, n_probs, q0);
+            else if (threads == 256) ppc_select_kernel<256><<<grid, 256, 0, s>>>(d_series, B, all_cols, qg, d_probs, d_q, n_probs, q0);
+            else ppc_select_kernel<512><<<grid, 512, 0, s>>>(d_series, B, all_cols, qg, d_probs, d_q, n_probs, q0);
+            const cudaError_t e = cudaGetLastError();
+            if (e != cudaSuccess) return fail_with(SEPAIHRD_ERR_CUDA, cudaGetErrorString(e));
+            sepaihrd_internal::count_launches(ctx, 1);
+        }
+    }
+    return SEPAIHRD_OK;
 }
 
 }  // namespace
@@ -312,6 +790,8 @@ extern "C" sepaihrd_rc sepaihrd_posterior_predictive(sepaihrd_ctx* ctx, const do
     double* d_q = (double*)buf(sizeof(double) * 6 * (size_t)n_cols * n_probs);
     unsigned* d_status = (unsigned*)buf(sizeof(unsigned) * (size_t)B);
     unsigned long long* d_cnt = (unsigned long long*)buf(sizeof(unsigned long long));
+    double* d_tvals = (double*)buf(sizeof(double) * CS_MAXT * 6 * (size_t)n_cols);      // order statistics per column (cluster select)
+    long long* d_colcnt = (long long*)buf(sizeof(long long) * 6 * (size_t)n_cols);
     if (oom) return fail_with(SEPAIHRD_ERR_OUT_OF_MEMORY, "posterior-predictive work buffers do not fit: split the draws");
     // padded age classes (sepaihrd_create): the caller's state has d.n_user classes per compartment, the pass runs with n
     std::vector<double> wide_init;
@@ -358,21 +838,8 @@ extern "C" sepaihrd_rc sepaihrd_posterior_predictive(sepaihrd_ctx* ctx, const do
     PPC_TRY(cudaGetLastError());
     // 2. the order statistics the quantiles need, column by column, 8 probabilities (<= 16 ranks) per group
     {
-        const long long all_cols = 6 * n_cols;
-        // Columns in flight x column size is what the later sweeps of a column find in L2 (126 MB): one 1024-thread block per SM
-        // keeps 148 columns of 100 k draws (118 MB) resident, so only the first sweep of a column reads HBM.
-        static const int env_grid = std::getenv("SEPAIHRD_PPC_GRID") ? std::atoi(std::getenv("SEPAIHRD_PPC_GRID")) : 0;
-        static const int env_threads = std::getenv("SEPAIHRD_PPC_THREADS") ? std::atoi(std::getenv("SEPAIHRD_PPC_THREADS")) : 0;
-        const int threads = env_threads ? env_threads : PPC_DEFAULT_THREADS;
-        const unsigned grid = (unsigned)std::min<long long>(all_cols, env_grid ? env_grid : PPC_DEFAULT_GRID);
-        for (int q0 = 0; q0 < n_probs; q0 += SEL_MAXT / 2) {
-            const int qg = std::min(SEL_MAXT / 2, n_probs - q0);
-            if (threads == 1024) ppc_select_kernel<1024><<<grid, 1024, 0, s>>>(d_series, B, all_cols, qg, d_probs, d_q, n_probs, q0);
-            else if (threads == 256) ppc_select_kernel<256><<<grid, 256, 0, s>>>(d_series, B, all_cols, qg, d_probs, d_q, n_probs, q0);
-            else ppc_select_kernel<512><<<grid, 512, 0, s>>>(d_series, B, all_cols, qg, d_probs, d_q, n_probs, q0);
-            PPC_TRY(cudaGetLastError());
-            count_launches(ctx, 1);
-        }
+        const sepaihrd_rc rc = select_quantiles(ctx, s, d.device, d_series, B, 6 * n_cols, n_probs, d_probs, d_q, d_tvals, d_colcnt, 0);
+        if (rc != SEPAIHRD_OK) { cleanup(); return rc; }
     }
     unsigned long long cnt = 0;
     std::vector<double> wide_q;
@@ -388,4 +855,28 @@ extern "C" sepaihrd_rc sepaihrd_posterior_predictive(sepaihrd_ctx* ctx, const do
     if (out_valid_draws) *out_valid_draws = (int64_t)cnt;
     cleanup();
     return SEPAIHRD_OK;
+}
+
+extern "C" sepaihrd_rc sepaihrd_column_quantiles_device(sepaihrd_ctx* ctx, const double* d_columns, int64_t B, int64_t n_cols, int32_t n_probs,
+                                                        const double* probs, double* d_out, int32_t path) {
+    using namespace sepaihrd_internal;
+    if (!ctx || !d_columns || !probs || !d_out) return fail_with(SEPAIHRD_ERR_INVALID_ARGUMENT, "null argument");
+    if (B <= 0 || n_cols <= 0) return fail_with(SEPAIHRD_ERR_INVALID_ARGUMENT, "empty columns");
+    if (n_probs < 1 || n_probs > 64) return fail_with(SEPAIHRD_ERR_INVALID_ARGUMENT, "between 1 and 64 quantile probabilities");
+    for (int q = 0; q < n_probs; ++q)
+        if (!(probs[q] >= 0.0 && probs[q] <= 1.0)) return fail_with(SEPAIHRD_ERR_INVALID_ARGUMENT, "quantile probabilities must lie in [0, 1]");
+    if (path < 0 || path > 2) return fail_with(SEPAIHRD_ERR_INVALID_ARGUMENT, "path: 0 by size, 1 one block per column, 2 cluster");
+    const Dims d = dims(ctx);
+    const auto ctx_lock = lock(ctx);
+    cudaSetDevice(d.device);
+    cudaStream_t s = stream(ctx);
+    // scratch slots 9..11: the aggregation pass above uses 0..8 and may be called with the same ctx in between
+    double* d_probs = (double*)scratch(ctx, 9, sizeof(double) * 64);
+    double* d_tvals = (double*)scratch(ctx, 10, sizeof(double) * CS_MAXT * (size_t)n_cols);
+    long long* d_colcnt = (long long*)scratch(ctx, 11, sizeof(long long) * (size_t)n_cols);
+    if (!d_probs || !d_tvals || !d_colcnt) return fail_with(SEPAIHRD_ERR_OUT_OF_MEMORY, "work buffers of the column quantiles do not fit");
+    auto cleanup = [] {};
+    PPC_TRY(cudaMemcpyAsync(d_probs, probs, sizeof(double) * n_probs, cudaMemcpyHostToDevice, s));
+    PPC_TRY(cudaStreamSynchronize(s));                                   // probs may be a temporary of the caller
+    return select_quantiles(ctx, s, d.device, d_columns, B, n_cols, n_probs, d_probs, d_out, d_tvals, d_colcnt, path);
 }

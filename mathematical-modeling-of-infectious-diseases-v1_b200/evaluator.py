@@ -207,6 +207,21 @@ class BatchEvaluator:
                                                            out.ctypes.data, C.byref(valid)))
         return out, valid.value
 
+    SELECT_BY_SIZE, SELECT_BLOCK, SELECT_CLUSTER = 0, 1, 2
+
+    def column_quantiles(self, columns, probs, path=0):
+        """Exact quantiles (numpy's default interpolation, NaNs left out) of device-resident columns: ``columns`` is a CUDA float64
+        tensor [n_cols, B] (contiguous); returns a CUDA tensor [n_cols, len(probs)].  ``path`` picks the kernel (SELECT_*)."""
+        import torch
+        if columns.dtype != torch.float64 or not columns.is_cuda or not columns.is_contiguous() or columns.dim() != 2:
+            raise ValueError("columns: contiguous CUDA float64 tensor [n_cols, B]")
+        self.set_stream(torch.cuda.current_stream(columns.device).cuda_stream)
+        pr = np.ascontiguousarray(probs, dtype=np.float64)
+        out = torch.empty((columns.shape[0], len(pr)), dtype=torch.float64, device=columns.device)
+        capi.check(self._lib.sepaihrd_column_quantiles_device(self._h, columns.data_ptr(), columns.shape[1], columns.shape[0], len(pr),
+                                                              pr.ctypes.data, out.data_ptr(), int(path)))
+        return out
+
 
 def measure_fp64_peak(device: int = 0) -> float:
     """Measured FP64 pipe peak in DFMA instructions per second (lane-ops): roofline denominator."""

@@ -444,6 +444,68 @@ def test_posterior_predictive_quantiles_match_numpy_on_oracle_trajectories(probl
     assert v1 == 1 and np.all(one[..., 0] == one[..., 2])
 
 
+def _awkward_columns(B, rng):
+    """Columns that are hard for a radix multi-select: ties, mixed signs, NaNs, outliers that stretch the common prefix, values
+    that differ only in their last bits, denormals."""
+    cols = {
+        "gamma": rng.gamma(2.0, 30.0, B),
+        "all equal": np.full(B, 7.25),
+        "all zero": np.zeros(B),
+        "half zero, half continuous": np.where(rng.random(B) < 0.5, 0.0, rng.random(B) * 1e-3),
+        "big tie + outliers": np.concatenate([np.full(B - min(50, B // 2), 3.0), rng.random(min(50, B // 2)) * 1e6]),
+        "mixed signs": rng.normal(size=B) * 1e3,
+        "10 % NaN": np.where(rng.random(B) < 0.1, np.nan, rng.lognormal(0, 3, B)),
+        "all NaN": np.full(B, np.nan),
+        "one valid": np.concatenate([[4.5], np.full(B - 1, np.nan)]),
+        "last bits": 1.0 + rng.integers(0, 1 << 20, B) * 2.0 ** -52,
+        "denormals and huge": np.concatenate([rng.random(B // 2) * 1e-310, rng.random(B - B // 2) * 1e300]),
+        "lognormal, 30 decades": rng.lognormal(0, 12, B),
+        "few distinct values": rng.integers(0, 7, B).astype(np.float64),
+        "negative zero and zero": np.where(rng.random(B) < 0.5, -0.0, 0.0),
+        "infinities": np.where(rng.random(B) < 0.01, np.inf, rng.normal(size=B)),
+    }
+    for v in cols.values():
+        rng.shuffle(v)
+    return cols
+
+
+@pytest.mark.parametrize("B", [1, 2, 193, 4099, 100000, 150001])
+def test_column_quantiles_both_kernels_against_numpy(problem, ev_mod, B):
+    """sepaihrd_column_quantiles_device (the selection half of the posterior-predictive pass) on awkward columns: the cluster
+    kernel (column in the shared memory of 4 or 8 blocks) and the one-block-per-column kernel give the order statistics numpy's
+    sort gives, bit for bit, for 5 and for 11 probabilities (two groups of <= 8)."""
+    import torch
+    rng = np.random.default_rng(1000 + B)
+    cols = _awkward_columns(B, rng)
+    X = np.stack(list(cols.values()))
+    dX = torch.from_numpy(X).cuda()
+    with ev_mod.BatchEvaluator(problem, device=0) as ev:
+        for probs in ((0.025, 0.05, 0.5, 0.95, 0.975), tuple(np.linspace(0.0, 1.0, 11))):
+            ref = np.full((len(X), len(probs)), np.nan)
+            for i, x in enumerate(X):
+                v = np.sort(x[x == x])
+                if len(v):
+                    h = (len(v) - 1) * np.asarray(probs)
+                    i0 = np.clip(np.floor(h).astype(np.int64), 0, len(v) - 1)
+                    i1 = np.minimum(i0 + 1, len(v) - 1)
+                    with np.errstate(invalid="ignore"):
+                        ref[i] = v[i0] + (h - i0) * (v[i1] - v[i0])
+            got = {}
+            for name, path in (("cluster", ev.SELECT_CLUSTER), ("block", ev.SELECT_BLOCK), ("by size", ev.SELECT_BY_SIZE)):
+                got[name] = ev.column_quantiles(dX, probs, path).cpu().numpy()
+                for i, cname in enumerate(cols):
+                    np.testing.assert_array_equal(got[name][i], ref[i], err_msg=f"{name} kernel, column '{cname}', B={B}")
+    # a column larger than 8 blocks can hold: the cluster kernel says so, the size rule takes the other kernel
+    if B == 150001:
+        big = torch.from_numpy(rng.normal(size=(2, 250000))).cuda()
+        with ev_mod.BatchEvaluator(problem, device=0) as ev:
+            with pytest.raises(Exception, match="does not fit"):
+                ev.column_quantiles(big, (0.5,), ev.SELECT_CLUSTER)
+            srt = np.sort(big.cpu().numpy(), axis=1)
+            lo_, hi_ = srt[:, 124999], srt[:, 125000]                       # (250000 - 1) * 0.5 = 124999.5
+            np.testing.assert_array_equal(ev.column_quantiles(big, (0.5,), ev.SELECT_BY_SIZE).cpu().numpy()[:, 0], lo_ + 0.5 * (hi_ - lo_))
+
+
 @pytest.mark.parametrize("ages", [[2], [1, 0], [0, 1, 3], "5 of 8", "7 of 8", "11 of 16"])
 def test_any_number_of_age_classes_runs_zero_padded(problem, orc, ev_mod, ages):
     """The kernels run with 4 or 16 lanes per set; sepaihrd_create pads any other age-class count with empty classes
