@@ -2,6 +2,7 @@
 #include "host_capi.h"
 #include "../csrc/det_math.h"
 
+#include <chrono>
 #include <cmath>
 #include <omp.h>
 #include <cstring>
@@ -492,6 +493,31 @@ int32_t sepaihrd_host_model_calibrate(sepaihrd_host_model* m, const char* phase1
         if (out_best) std::copy(b.data(), b.data() + b.size(), out_best);
         if (out_value) *out_value = c.getBestObjectiveValue();
         if (out_samples) *out_samples = static_cast<int64_t>(c.getMCMCSamples().size());
+    });
+}
+int32_t sepaihrd_host_model_metropolis(sepaihrd_host_model* m, int32_t n, const char* const* keys, const double* values, const double* initial,
+                                       double* out_best, double* out_value, double* out_last, double* out_stats) {
+    return guarded([&] {
+        const auto P = static_cast<std::ptrdiff_t>(m->pm->getParameterCount());
+        MetropolisHastingsSampler mh;
+        mh.configure(settings_map(n, keys, values));
+        int64_t l0 = 0, s0 = 0, l1 = 0, s1 = 0;
+        sepaihrd_get_counters(m->objective->device().get(), &l0, &s0);
+        const auto t0 = std::chrono::steady_clock::now();
+        const OptimizationResult r = mh.optimize(VectorXd::FromPointer(initial, P), *m->objective, *m->pm);
+        const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        sepaihrd_get_counters(m->objective->device().get(), &l1, &s1);
+        if (out_best) std::copy(r.bestParameters.data(), r.bestParameters.data() + P, out_best);
+        if (out_value) *out_value = r.bestObjectiveValue;
+        if (out_last) { std::copy(mh.currentPositions(), mh.currentPositions() + P, out_last); out_last[P] = mh.currentLogPost()[0]; }
+        if (out_stats) {
+            out_stats[0] = ms;
+            out_stats[1] = static_cast<double>(s1 - s0);                               // parameter sets the device evaluated
+            out_stats[2] = static_cast<double>(l1 - l0);                               // kernel launches
+            out_stats[3] = r.additionalStats.at("acceptance_rate");
+            out_stats[4] = r.additionalStats.at("final_scale");
+            out_stats[5] = static_cast<double>(mh.iteration());
+        }
     });
 }
 int32_t sepaihrd_host_model_posterior_predictive(sepaihrd_host_model* m, const double* samples, int64_t S, int32_t num_samples, uint32_t seed,

@@ -138,6 +138,12 @@ int32_t sepaihrd_host_model_simulate(sepaihrd_host_model* m, const double* initi
 int32_t sepaihrd_host_model_calibrate(sepaihrd_host_model* m, const char* phase1, int32_t n1, const char* const* keys1, const double* values1,
                                       int32_t n2, const char* const* keys2, const double* values2, double* out_best /* [P] */,
                                       double* out_best_value, int64_t* out_n_samples);
+/* MetropolisHastingsSampler::optimize (MetropolisHastingsSampler.cpp:201-412) on the model's device objective, timed as a
+ * whole: the reference's phase-2 sampler as shipped (one chain; setting "lookahead" != 1 evaluates the next K iterations'
+ * proposals in one launch, see optimizers.hpp) or n_chains in lockstep.  out_last [P + 1]: final state of chain 0 and its
+ * log-posterior; out_stats [6]: wall ms, parameter sets evaluated, kernel launches, acceptance rate, final scale, iterations. */
+int32_t sepaihrd_host_model_metropolis(sepaihrd_host_model* m, int32_t n, const char* const* keys, const double* values, const double* initial,
+                                       double* out_best /* [P] */, double* out_best_value, double* out_last, double* out_stats);
 /* ResultAggregator::aggregatePosteriorPredictives over `samples` ([S][P]); out [6][T][n][5] in the order
  * lower_95, lower_90, median, upper_90, upper_95 (probabilities 0.025, 0.05, 0.5, 0.95, 0.975) */
 int32_t sepaihrd_host_model_posterior_predictive(sepaihrd_host_model* m, const double* samples, int64_t S, int32_t num_samples_for_ppc,

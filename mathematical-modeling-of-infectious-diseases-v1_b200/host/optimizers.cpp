@@ -75,6 +75,7 @@ void MetropolisHastingsSampler::configure(const std::map<std::string, double>& s
     write_trace_ = setting(s, "write_trace", 1.0) != 0.0;
     // batched / repeatable extensions
     n_chains_ = std::max(1, static_cast<int>(setting(s, "n_chains", 1.0)));
+    lookahead_ = std::max(0, static_cast<int>(setting(s, "lookahead", 0.0)));
     chain_offset_ = static_cast<long>(setting(s, "chain_offset", 0.0));
     has_seed_ = s.count("seed") != 0;
     seed_ = static_cast<unsigned>(setting(s, "seed", 0.0));
@@ -169,7 +170,7 @@ void MetropolisHastingsSampler::recomputeFullCovariance(Chain& c) const {
     if (linalg::cholesky_lower(c.cov, L)) c.chol = L;
 }
 
-void MetropolisHastingsSampler::adaptGlobalScale(Chain& c, bool accepted, int step) const {
+void MetropolisHastingsSampler::adaptGlobalScale(ScaleState& c, bool accepted, int step) const {
     if (!adapt_scale_) return;
     c.recent.push_back(accepted ? 1 : 0);
     c.recent_sum += accepted ? 1 : 0;
@@ -190,44 +191,53 @@ void MetropolisHastingsSampler::adaptGlobalScale(Chain& c, bool accepted, int st
     c.global_scale = detm::exp(c.log_scale);
 }
 
+// 1. adaptation (only after burn-in), .cpp:286-303
+void MetropolisHastingsSampler::adaptKernel(Chain& c, int t) const {
+    if (t <= burn_in_) return;
+    const auto P = static_cast<std::ptrdiff_t>(n_params_);
+    ownKernel(c);
+    updateCovarianceRank1(c, t);
+    if (t % adaptation_period_ == 0) {
+        recomputeFullCovariance(c);
+        MatrixXd L;
+        if (linalg::cholesky_lower(c.cov + regularization_epsilon_ * MatrixXd::Identity(P, P), L)) c.chol = L;
+    }
+}
+
+// 2. proposal  Y = X + scale * L z,  z ~ N(0, I)   (generateProposal, .cpp:91-102), 2b. constraints (reflection in MCMC mode, .cpp:308)
+void MetropolisHastingsSampler::drawProposal(std::mt19937& gen, const Chain& c, double scale, const double* x, IParameterManager& pm,
+                                             double* out) const {
+    const auto P = static_cast<std::ptrdiff_t>(n_params_);
+    VectorXd z(P);
+    PolarNormal dist;                                   // a fresh distribution per proposal, like the reference's local object
+    for (std::ptrdiff_t i = 0; i < P; ++i) z(i) = dist(gen);
+    // L is a lower Cholesky factor (diagonal for the start kernel): the structural zeros are skipped, which leaves every
+    // sum unchanged (they would add +-0)
+    const MatrixXd& L = c.own_kernel ? c.chol : shared_chol_;
+    VectorXd step = VectorXd::Zero(P);
+    if (!c.own_kernel && shared_diagonal_) {
+        for (std::ptrdiff_t i = 0; i < P; ++i) step(i) = L(i, i) * z(i);
+    } else {
+        for (std::ptrdiff_t j = 0; j < P; ++j) {
+            const double zj = z(j);
+            for (std::ptrdiff_t i = j; i < P; ++i) step(i) += L(i, j) * zj;
+        }
+    }
+    VectorXd y(P);
+    for (std::ptrdiff_t i = 0; i < P; ++i) y(i) = x[i] + scale * step(i);
+    const VectorXd yc = pm.applyConstraints(y);
+    std::copy(yc.data(), yc.data() + P, out);
+}
+
 void MetropolisHastingsSampler::propose(IParameterManager& pm, double* out) {
     const auto P = static_cast<std::ptrdiff_t>(n_params_);
     const int t = t_;
 #pragma omp parallel for schedule(static)
     for (int ci = 0; ci < n_chains_; ++ci) {
         Chain& c = chains_[static_cast<size_t>(ci)];
-        // 1. adaptation (only after burn-in), .cpp:286-303
-        if (t > burn_in_) {
-            ownKernel(c);
-            updateCovarianceRank1(c, t);
-            if (t % adaptation_period_ == 0) {
-                recomputeFullCovariance(c);
-                MatrixXd L;
-                if (linalg::cholesky_lower(c.cov + regularization_epsilon_ * MatrixXd::Identity(P, P), L)) c.chol = L;
-            }
-        }
-        // 2. proposal  Y = X + scale * L z,  z ~ N(0, I)   (generateProposal, .cpp:91-102)
-        VectorXd z(P);
-        PolarNormal dist;                                   // a fresh distribution per proposal, like the reference's local object
-        for (std::ptrdiff_t i = 0; i < P; ++i) z(i) = dist(c.gen);
-        // L is a lower Cholesky factor (diagonal for the start kernel): the structural zeros are skipped, which leaves every
-        // sum unchanged (they would add +-0)
-        const MatrixXd& L = c.own_kernel ? c.chol : shared_chol_;
-        VectorXd step = VectorXd::Zero(P);
-        if (!c.own_kernel && shared_diagonal_) {
-            for (std::ptrdiff_t i = 0; i < P; ++i) step(i) = L(i, i) * z(i);
-        } else {
-            for (std::ptrdiff_t j = 0; j < P; ++j) {
-                const double zj = z(j);
-                for (std::ptrdiff_t i = j; i < P; ++i) step(i) += L(i, j) * zj;
-            }
-        }
-        VectorXd y(P);
-        const double* x = cur_x_.data() + static_cast<std::ptrdiff_t>(ci) * P;
-        for (std::ptrdiff_t i = 0; i < P; ++i) y(i) = x[i] + c.global_scale * step(i);
-        // 2b. constraints (reflection in MCMC mode)
-        const VectorXd yc = pm.applyConstraints(y);
-        std::copy(yc.data(), yc.data() + P, prop_x_.begin() + static_cast<std::ptrdiff_t>(ci) * P);
+        adaptKernel(c, t);
+        drawProposal(c.gen, c, c.global_scale, cur_x_.data() + static_cast<std::ptrdiff_t>(ci) * P, pm,
+                     prop_x_.data() + static_cast<std::ptrdiff_t>(ci) * P);
     }
     std::copy(prop_x_.begin(), prop_x_.end(), out);
 }
@@ -281,6 +291,59 @@ OptimizationResult MetropolisHastingsSampler::result() const {
     return r;
 }
 
+// How many iterations ahead to evaluate: the smallest K with (1 - rate)^K < 1 % -- the chance that all K are rejected and a
+// longer window would have been used -- from the acceptance rate over the last <= 1000 iterations (the window the scale
+// adaptation keeps anyway).  A launch costs the same from 1 to ~4 000 sets, so the only price of a long window is the host's
+// proposal arithmetic (~4 us each).
+int MetropolisHastingsSampler::windowLength(const Chain& c) const {
+    if (lookahead_ > 1) return lookahead_;
+    if (c.recent.size() < 50) return 16;
+    const double rate = std::max(static_cast<double>(c.recent_sum) / static_cast<double>(c.recent.size()), 0.02);
+    const int k = static_cast<int>(std::ceil(std::log(0.01) / std::log1p(-std::min(rate, 0.9))));
+    return std::min(std::max(k, 4), 128);
+}
+
+// One chain, K iterations per device launch (see optimizers.hpp).  The chain object only ever changes through the calls the
+// sequential loop makes -- adaptKernel, the generator draws, accept() -- in the sequential order; the speculation works on
+// copies of the generator and of the scale state.
+void MetropolisHastingsSampler::runLookahead(IObjectiveFunction& f, IParameterManager& pm, const std::string& dir) {
+    const auto P = static_cast<std::ptrdiff_t>(n_params_);
+    Chain& c = chains_.front();
+    std::vector<double> props;
+    std::uniform_real_distribution<double> u01(0.0, 1.0);
+    while (!done()) {
+        const int t0 = t_;
+        int K = std::min(windowLength(c), iterations_ - t0);
+        // the proposal kernel L must not change inside the window: an iteration that refactors it (.cpp:292-302) may open
+        // a window (its adaptation runs before anything is drawn), it may not sit inside one
+        for (int j = 1; j < K; ++j)
+            if (t0 + j > burn_in_ && (t0 + j) % adaptation_period_ == 0) { K = j; break; }
+        adaptKernel(c, t0);
+        std::mt19937 gen = c.gen;
+        ScaleState sc = c;
+        props.resize(static_cast<size_t>(K) * static_cast<size_t>(P));
+        for (int j = 0; j < K; ++j) {
+            drawProposal(gen, c, sc.global_scale, cur_x_.data(), pm, props.data() + static_cast<std::ptrdiff_t>(j) * P);
+            (void)u01(gen);                                          // a rejected proposal was a downhill one: its uniform is drawn
+            if (adapt_scale_) adaptGlobalScale(sc, false, t0 + j);
+        }
+        const std::vector<double> plp = evaluate_rows(f, props, K, P);
+        speculated_ += K;
+        for (int j = 0; j < K; ++j) {
+            const int t = t_;
+            if (j > 0) adaptKernel(c, t);                            // rank-1 update of the covariance only (no refactoring, see above)
+            PolarNormal dist;                                        // the generator makes the draws of this iteration's proposal
+            for (std::ptrdiff_t i = 0; i < P; ++i) (void)dist(c.gen);
+            std::copy(props.begin() + static_cast<std::ptrdiff_t>(j) * P, props.begin() + static_cast<std::ptrdiff_t>(j + 1) * P, prop_x_.begin());
+            uint8_t acc = 0;
+            accept(&plp[static_cast<size_t>(j)], &acc);              // the uniform (if the proposal is downhill), state, scale, history, samples; ++t_
+            ++committed_;
+            if (!dir.empty() && write_checkpoints_ && (t + 1) % report_interval_ == 0) saveCheckpoint(result(), pm, false, dir);   // .cpp:380-382
+            if (acc) break;
+        }
+    }
+}
+
 OptimizationResult MetropolisHastingsSampler::optimize(const VectorXd& initial, IObjectiveFunction& f, IParameterManager& pm) {
     if (auto* spm = dynamic_cast<SEPAIHRDParameterManager*>(&pm)) spm->setConstraintMode(ConstraintMode::MCMC_REFLECT);   // .cpp:207-210
     const int64_t P = initial.size();
@@ -290,6 +353,8 @@ OptimizationResult MetropolisHastingsSampler::optimize(const VectorXd& initial, 
     begin(initial, lp.data(), pm);
     std::vector<double> prop(static_cast<size_t>(n_chains_) * static_cast<size_t>(P));
     const std::string dir = (store_samples_ && (write_checkpoints_ || write_trace_)) ? traceDirectory() : std::string();
+    speculated_ = committed_ = 0;
+    if (n_chains_ == 1 && lookahead_ != 1) runLookahead(f, pm, dir);
     while (!done()) {
         const int t = t_;
         propose(pm, prop.data());

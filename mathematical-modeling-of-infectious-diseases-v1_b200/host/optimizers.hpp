@@ -64,13 +64,27 @@ public:
     OptimizationResult result() const;
     static double safeValue(double v) { return (std::isnan(v) || std::isinf(v)) ? -1e18 : v; }   // safeEvaluate, .cpp:65-74
 
+    // Look-ahead (setting "lookahead": 0 = sized from the recent acceptance rate, 1 = off, K = that many; one chain only).
+    // The reference's shipped run is ONE chain of 100 000 sequential iterations (data/configuration/mcmc_settings.txt,
+    // .cpp:283-384): one evaluation per device launch, and a launch costs ~0.5 ms whatever it holds.  Between two accepted
+    // proposals the chain does not move, so the proposals of the next K iterations ARE known before any of them is evaluated:
+    // iteration t + j proposes x + s_j L z_j with z_j the next normals of the generator (a rejected iteration has consumed its
+    // uniform, .cpp:323-329) and s_j the scale after j more rejections (.cpp:104-152).  optimize() evaluates those K as one
+    // batch, commits iterations up to and including the first accepted one and throws the rest away.  The chain, its
+    // generator, scale, covariance and trace files are bit for bit those of the sequential run (tests/test_mh_lookahead.py).
+    int lookahead() const { return lookahead_; }
+    long speculatedEvaluations() const { return speculated_; }          // evaluations made / iterations they committed
+    long committedIterations() const { return committed_; }
+
 private:
-    struct Chain {
-        std::mt19937 gen;
+    struct ScaleState {                   // what adaptGlobalScale reads and writes
         double log_scale = 0.0, global_scale = 1.0;
         std::deque<uint8_t> recent;
         int recent_sum = 0;
         int emergency_shrink_count = 0;
+    };
+    struct Chain : ScaleState {
+        std::mt19937 gen;
         long accepted = 0;
         bool own_kernel = false;          // false: shares the initial Cholesky factor
         MatrixXd cov, chol;
@@ -81,7 +95,11 @@ private:
         std::vector<VectorXd> samples;
         std::vector<double> sample_lp;
     };
-    void adaptGlobalScale(Chain& c, bool accepted, int step) const;     // .cpp:104-152
+    void adaptGlobalScale(ScaleState& c, bool accepted, int step) const;   // .cpp:104-152
+    void adaptKernel(Chain& c, int step) const;                          // .cpp:286-303
+    void drawProposal(std::mt19937& gen, const Chain& c, double scale, const double* x, IParameterManager& pm, double* out) const;   // .cpp:91-102, 308
+    int windowLength(const Chain& c) const;
+    void runLookahead(IObjectiveFunction& f, IParameterManager& pm, const std::string& dir);
     void updateCovarianceRank1(Chain& c, int step) const;               // .cpp:154-168
     void recomputeFullCovariance(Chain& c) const;                       // .cpp:170-199
     void ownKernel(Chain& c) const;
@@ -94,6 +112,8 @@ private:
     double regularization_epsilon_ = 1e-6, target_acceptance_rate_ = 0.234;
     bool adapt_scale_ = true, store_samples_ = true;
     int n_chains_ = 1;
+    int lookahead_ = 0;
+    long speculated_ = 0, committed_ = 0;
     long chain_offset_ = 0;
     bool shared_diagonal_ = false;
     bool has_seed_ = false;

@@ -74,6 +74,7 @@ SIGNATURES = {
     "sepaihrd_host_model_update_parameters": (C.c_int32, [_vp, _vp]),
     "sepaihrd_host_model_simulate": (C.c_int32, [_vp, _vp, _vp, C.c_int32, _vp]),
     "sepaihrd_host_model_calibrate": (C.c_int32, [_vp, C.c_char_p, C.c_int32, _keys, _vp, C.c_int32, _keys, _vp, _vp, _dp, _i64p]),
+    "sepaihrd_host_model_metropolis": (C.c_int32, [_vp, C.c_int32, _keys, _vp, _vp, _vp, _dp, _vp, _vp]),
     "sepaihrd_host_model_posterior_predictive": (C.c_int32, [_vp, _vp, C.c_int64, C.c_int32, C.c_uint32, _vp, _vp, _i64p]),
     "sepaihrd_host_model_gradient": (C.c_int32, [_vp, _vp, C.c_double, _dp, _vp]),
     "sepaihrd_host_write_posterior_predictive": (C.c_int32, [C.c_char_p, C.c_int32, C.c_int32, _vp, _vp, _vp]),
@@ -533,6 +534,17 @@ class HostModel:
         check(self.L.sepaihrd_host_model_calibrate(self._h, phase1.encode(), n1, k1, v1.ctypes.data, n2, k2, v2.ctypes.data,
                                                    best.ctypes.data, C.byref(val), C.byref(ns)))
         return best, val.value, ns.value
+
+    def metropolis(self, settings: Dict[str, float], initial):
+        """MetropolisHastingsSampler::optimize on the device objective, timed in C++.  Returns dict(best, best_value, last,
+        last_logpost, ms, evaluations, launches, acceptance_rate, final_scale, iterations)."""
+        n, k, v = _settings(settings)
+        x0 = _c64(initial); P = self.problem.n_params
+        best = np.empty(P); last = np.empty(P + 1); val = C.c_double(); st = np.zeros(6)
+        check(self.L.sepaihrd_host_model_metropolis(self._h, n, k, v.ctypes.data, x0.ctypes.data, best.ctypes.data, C.byref(val),
+                                                    last.ctypes.data, st.ctypes.data))
+        return dict(best=best, best_value=val.value, last=last[:P].copy(), last_logpost=float(last[P]), ms=float(st[0]), evaluations=int(st[1]),
+                    launches=int(st[2]), acceptance_rate=float(st[3]), final_scale=float(st[4]), iterations=int(st[5]))
 
     def posterior_predictive(self, samples, initial_state, num_samples: int = 0, seed: int = 0):
         """ResultAggregator::aggregatePosteriorPredictives: [6, T, n, 5] (lower_95, lower_90, median, upper_90, upper_95)."""

@@ -441,3 +441,24 @@ def test_objective_benchmark_harness_runs_from_a_project_tree(host, problem, ora
     assert rep["threads_launches"] < 2048 / 4
     bad = subprocess.run([exe, "--project-root", str(tmp_path / "nowhere")], capture_output=True, text=True)
     assert bad.returncode == 1 and "unable to open" in bad.stderr
+
+
+def test_single_chain_lookahead_is_the_sequential_chain_on_the_device_objective(host, problem, oracle):
+    """The reference's shipped phase 2 -- one chain (MetropolisHastingsSampler.cpp:283-384) -- on the device objective: with look-ahead
+    (the next K iterations' proposals in ONE launch, host/optimizers.cpp runLookahead) the chain ends in the state, with the
+    log-posterior, scale, acceptance rate and best value of the one-evaluation-per-launch run, in a fraction of the launches;
+    through the burn-in, rank-1 covariance updates and two refactorisations of the proposal kernel."""
+    m = host.HostModel(problem)
+    x0 = problem.base_params()
+    st = dict(mcmc_iterations=260, burn_in=100, adaptation_period=60, n_chains=1, seed=8, store_samples=0, write_trace=0, write_checkpoints=0)
+    seq = m.metropolis(dict(st, lookahead=1), x0)
+    assert seq["launches"] == 260 and seq["evaluations"] == 260 and seq["iterations"] == 260
+    for la in (0, 5, 48):
+        r = m.metropolis(dict(st, lookahead=la), x0)
+        np.testing.assert_array_equal(r["last"], seq["last"])
+        assert (r["last_logpost"], r["best_value"], r["final_scale"], r["acceptance_rate"]) == \
+               (seq["last_logpost"], seq["best_value"], seq["final_scale"], seq["acceptance_rate"])
+        np.testing.assert_array_equal(r["best"], seq["best"])
+        assert r["launches"] < seq["launches"] and r["evaluations"] > seq["evaluations"]
+    assert _rel(oracle.eval_batch(seq["last"][None])[0][0], seq["last_logpost"]) < 1e-8
+    m.close()

@@ -1,0 +1,102 @@
+"""Look-ahead Metropolis-Hastings (host/optimizers.cpp `runLookahead`): the reference's shipped configuration is ONE chain of
+sequential iterations (data/configuration/mcmc_settings.txt, MetropolisHastingsSampler.cpp:283-384), one objective evaluation
+per iteration.  With setting ``lookahead`` != 1 the sampler evaluates the proposals of the next K iterations -- all known in
+advance as long as the chain keeps rejecting -- as ONE batch and commits up to the first accepted one.  The chain must be the
+sequential chain bit for bit: every visited state, every log-posterior, the generator (a misaligned draw would change every
+later state), the scale, the adapted covariance, and the trace / checkpoint files; only the shape of the evaluation batches
+differs."""
+import numpy as np
+import pytest
+
+
+@pytest.fixture(scope="module")
+def host(pkg, cuda_lib):
+    import __graft_entry__ as entry
+    entry.build()
+    from sepaihrd_b200 import hostlib
+    hostlib.load_library()
+    return hostlib
+
+
+def _objective(problem, kind):
+    target = problem.base_params()
+    sc = np.maximum(problem.sigmas, 1e-9)
+    if kind == "gauss":                      # smooth: acceptance near the target rate once the scale has adapted
+        return lambda x: -0.5 * (((x - target) / (3.0 * sc)) ** 2).sum(axis=1)
+    if kind == "steep":                      # almost everything is rejected: long windows, the emergency / fast-shrink branches
+        return lambda x: -0.5 * (((x - target) / (1e-3 * sc)) ** 2).sum(axis=1)
+    if kind == "plateau":                    # ties: log_ratio == 0 accepts WITHOUT drawing a uniform (.cpp:323-329)
+        return lambda x: -np.floor(np.abs((x - target) / sc).sum(axis=1))
+    if kind == "nan":                        # non-finite values go through safeEvaluate's -1e18 (.cpp:65-74)
+        def f(x):
+            v = -0.5 * (((x - target) / (3.0 * sc)) ** 2).sum(axis=1)
+            v[(np.abs(x[:, 0] - target[0]) / sc[0]) > 1.0] = np.nan
+            return v
+        return f
+    raise ValueError(kind)
+
+
+def _run(host, problem, tmp_path, tag, kind, settings):
+    calls = []
+    inner = _objective(problem, kind)
+
+    def ev(x):
+        calls.append(x.copy())
+        return inner(x)
+
+    pm = host.ParameterManager(problem.sigmas, problem.lower_bound, problem.upper_bound, mode=1)
+    out = tmp_path / tag
+    host.set_trace_directory(str(out))
+    try:
+        best, val, nev = host.optimize("mh", pm, settings, ev, problem.base_params())
+    finally:
+        host.set_trace_directory(None)
+    files = {p.name: p.read_text() for p in out.iterdir()} if out.exists() else {}
+    return dict(best=best, val=val, nev=nev, files=files, calls=calls)
+
+
+@pytest.mark.parametrize("kind", ["gauss", "steep", "plateau", "nan"])
+@pytest.mark.parametrize("lookahead", [0, 2, 7, 64])
+def test_lookahead_chain_is_the_sequential_chain(host, problem, tmp_path, kind, lookahead):
+    # 330 iterations: through the burn-in (rank-1 updates from t = 121), three refactorisations of the proposal kernel
+    # (t = 150, 200, ... : windows must stop in front of them), checkpoints every 40, thinning 1 so that every state is written
+    st = dict(mcmc_iterations=330, burn_in=120, adaptation_period=50, n_chains=1, report_interval=40, thinning=1, seed=11)
+    seq = _run(host, problem, tmp_path, "seq", kind, dict(st, lookahead=1))
+    la = _run(host, problem, tmp_path, f"la{lookahead}", kind, dict(st, lookahead=lookahead))
+    assert all(len(c) == 1 for c in seq["calls"]) and seq["nev"] == 330             # 1 initial + 329 proposals, one per call
+    assert sorted(la["files"]) == sorted(seq["files"]) == ["posterior_trace.csv", "posterior_trace_checkpoint.csv", "posterior_trace_final.csv"]
+    for name in seq["files"]:
+        assert la["files"][name] == seq["files"][name], f"{name} differs (lookahead {lookahead}, {kind})"
+    np.testing.assert_array_equal(la["best"], seq["best"])
+    assert la["val"] == seq["val"]
+    # every proposal the sequential run evaluated appears, bit for bit and in order, among the look-ahead evaluations
+    # (the first row of every window is the sequential proposal of that iteration)
+    flat = np.concatenate(la["calls"])
+    want = np.concatenate(seq["calls"])
+    pos = 0
+    for row in want:
+        while pos < len(flat) and not np.array_equal(flat[pos], row):
+            pos += 1
+        assert pos < len(flat), "a sequential proposal was never evaluated by the look-ahead run"
+        pos += 1
+    assert len(la["calls"]) < len(seq["calls"])                                       # fewer launches
+    if lookahead > 1:
+        assert max(len(c) for c in la["calls"]) <= lookahead
+
+
+def test_lookahead_cuts_the_number_of_launches(host, problem, tmp_path):
+    """On a smooth target with the scale adapted to ~23 % acceptance a window commits ~4 iterations: the number of objective
+    calls (device launches behind the drop-in) falls accordingly, at the price of evaluations thrown away."""
+    st = dict(mcmc_iterations=3000, burn_in=3000, n_chains=1, seed=5, write_trace=0, write_checkpoints=0)
+    la = _run(host, problem, tmp_path, "la", "gauss", dict(st, lookahead=0))
+    launches = len(la["calls"]) - 1
+    assert 2999 / launches > 2.5, (launches, la["nev"])
+    assert la["nev"] < 25 * launches
+
+
+def test_multichain_runs_ignore_lookahead(host, problem, tmp_path):
+    st = dict(mcmc_iterations=40, burn_in=40, n_chains=3, seed=2, write_trace=0, write_checkpoints=0)
+    a = _run(host, problem, tmp_path, "a", "gauss", dict(st, lookahead=1))
+    b = _run(host, problem, tmp_path, "b", "gauss", dict(st, lookahead=0))
+    assert a["nev"] == b["nev"] == 1 + 3 * 39 and all(len(c) == 3 for c in b["calls"][1:])
+    np.testing.assert_array_equal(a["best"], b["best"])
