@@ -94,6 +94,7 @@ struct sepaihrd_ctx {
     std::vector<EvalRequest*> queue;
     bool leader = false;
     double* h_stage = nullptr; size_t cap_stage = 0;          // pinned: packed rows | logL | status | steps of a merged launch
+    double* h_small = nullptr; size_t cap_small = 0;          // pinned: the same four pieces of ONE small request with pageable buffers
     long long merged_launches = 0, merged_requests = 0;
     int device = 0;
     int n_user = 0;                // the caller's age-class count; n below is what the kernels run with (4 or 16, zero-padded classes)
@@ -150,7 +151,11 @@ sepaihrd_rc launch_t(sepaihrd_ctx* ctx, const sepaihrd::KParams& kp_in) {
     KParams kp = kp_in;
     constexpr int SETS = THREADS / NA;
     constexpr int WSETS = (32 / NA) > 0 ? (32 / NA) : 1;
-    kp.tiles = (kp.B + WSETS - 1) / WSETS;
+    // A warp pays the day-by-day MAXIMUM of its sets' attempts.  While there are fewer sets than warp slots with a scheduler of
+    // their own (4 per SM), a warp takes fewer sets per tile, down to one: 8 sets cost what 1 set costs (0.51 ms, not 0.57).
+    kp.sets_per_tile = (int)std::min<long long>(WSETS, std::max<long long>(1, (kp.B + 4LL * ctx->num_sms - 1) / (4LL * ctx->num_sms)));
+    if (PROFILE || kp.perm) kp.sets_per_tile = WSETS;
+    kp.tiles = (kp.B + kp.sets_per_tile - 1) / kp.sets_per_tile;
     if (kp.tiles > 0xffff0000LL) return fail(SEPAIHRD_ERR_UNSUPPORTED, "batch too large for one launch");
     // Every launch draws its tiles from its OWN counter (a ring of N_TILE_COUNTERS, zeroed on the launching stream right before
     // the kernel): launches of one ctx that are in flight on different streams never share one.
@@ -603,6 +608,7 @@ void sepaihrd_destroy(sepaihrd_ctx* ctx) {
     sepaihrd_internal::order_release(ctx);
     for (void* p : ctx->scratch) if (p) cudaFree(p);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    if (ctx->h_small) cudaFreeHost(ctx->h_small);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
@@ -805,6 +811,71 @@ sepaihrd_rc eval_batch_serial(sepaihrd_ctx* ctx, const double* params, int64_t B
     return SEPAIHRD_OK;
 }
 
+constexpr int64_t COALESCE_MAX_SETS = 4096;      // larger requests fill the machine on their own
+
+bool page_locked(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+// A small request (<= COALESCE_MAX_SETS: a look-ahead window of the one-chain sampler, a line search, a few thousand chains) is
+// latency, not throughput: ONE piece on the ctx stream -- copy in, launch, copy out, one synchronisation -- without the copy
+// stream, the chunk events and the three stream synchronisations of the large path.  Pageable caller buffers (an
+// Eigen::VectorXd, a std::vector) are staged through a page-locked buffer of the ctx: a cudaMemcpyAsync on pageable memory
+// is a synchronous, driver-staged copy, three of them per call cost more than the rest of the call's overhead together
+// (measured through the C++ host layer: 0.606 ms per calculate() against 0.538 ms from page-locked buffers).
+sepaihrd_rc eval_batch_small(sepaihrd_ctx* ctx, const double* params, int64_t B, int64_t ld, double* out_ll,
+                             uint32_t* out_status, int32_t* out_steps) {
+    std::lock_guard<std::recursive_mutex> lock(ctx->mu);
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const int P = ctx->P;
+    sepaihrd_rc rc;
+    if ((rc = grow(&ctx->d_params, &ctx->cap_params, (size_t)B * ld)) != SEPAIHRD_OK) return rc;
+    if ((rc = grow(&ctx->d_out, &ctx->cap_out, (size_t)B)) != SEPAIHRD_OK) return rc;
+    if ((rc = grow(&ctx->d_status, &ctx->cap_status, (size_t)B)) != SEPAIHRD_OK) return rc;
+    if (out_steps && (rc = grow(&ctx->d_steps, &ctx->cap_steps, (size_t)B * 2)) != SEPAIHRD_OK) return rc;
+    const bool stage_in = !page_locked(params);
+    const bool stage_out = !(page_locked(out_ll) && (!out_status || page_locked(out_status)) && (!out_steps || page_locked(out_steps)));
+    const size_t doubles = (size_t)B * P + (size_t)B /* logL */ + (size_t)(B + 1) / 2 /* status */ + (size_t)B /* steps */;
+    if ((stage_in || stage_out) && doubles > ctx->cap_small) {
+        if (ctx->h_small) cudaFreeHost(ctx->h_small);
+        ctx->h_small = nullptr; ctx->cap_small = 0;
+        const size_t want = std::max<size_t>(doubles * 2, 1 << 14);
+        CUDA_TRY(cudaMallocHost((void**)&ctx->h_small, want * sizeof(double)));
+        ctx->cap_small = want;
+    }
+    double* h_rows = ctx->h_small;
+    double* h_ll = stage_out ? h_rows + (size_t)B * P : out_ll;
+    uint32_t* h_st = stage_out ? reinterpret_cast<uint32_t*>(ctx->h_small + (size_t)B * P + B) : out_status;
+    int32_t* h_steps = stage_out ? reinterpret_cast<int32_t*>(ctx->h_small + (size_t)B * P + B + (B + 1) / 2) : out_steps;
+    cudaStream_t s = ctx->stream;
+    struct Drain {           // an early return must not leave a copy from / into the caller's buffers in flight
+        cudaStream_t s;
+        ~Drain() { cudaStreamSynchronize(s); }
+    } drain{s};
+    int64_t dev_ld = ld;
+    if (stage_in) {          // rows packed to P doubles
+        for (int64_t b = 0; b < B; ++b) std::memcpy(h_rows + b * P, params + b * ld, sizeof(double) * (size_t)P);
+        dev_ld = P;
+        CUDA_TRY(cudaMemcpyAsync(ctx->d_params, h_rows, sizeof(double) * (size_t)B * P, cudaMemcpyHostToDevice, s));
+    } else {
+        CUDA_TRY(cudaMemcpyAsync(ctx->d_params, params, sizeof(double) * (size_t)B * ld, cudaMemcpyHostToDevice, s));
+    }
+    rc = sepaihrd_eval_batch_device(ctx, ctx->d_params, B, dev_ld, ctx->d_out, ctx->d_status, out_steps ? ctx->d_steps : nullptr);
+    if (rc != SEPAIHRD_OK) return rc;
+    CUDA_TRY(cudaMemcpyAsync(h_ll, ctx->d_out, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost, s));
+    if (out_status) CUDA_TRY(cudaMemcpyAsync(h_st, ctx->d_status, sizeof(unsigned) * (size_t)B, cudaMemcpyDeviceToHost, s));
+    if (out_steps) CUDA_TRY(cudaMemcpyAsync(h_steps, ctx->d_steps, sizeof(int) * (size_t)B * 2, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    if (stage_out) {
+        std::memcpy(out_ll, h_ll, sizeof(double) * (size_t)B);
+        if (out_status) std::memcpy(out_status, h_st, sizeof(uint32_t) * (size_t)B);
+        if (out_steps) std::memcpy(out_steps, h_steps, sizeof(int32_t) * 2 * (size_t)B);
+    }
+    return SEPAIHRD_OK;
+}
+
 // Serve the requests of `batch` (>= 2) with ONE launch: rows packed into a page-locked staging buffer (leading dimension P),
 // results scattered back.
 sepaihrd_rc eval_merged(sepaihrd_ctx* ctx, const std::vector<EvalRequest*>& batch) {
@@ -831,7 +902,8 @@ sepaihrd_rc eval_merged(sepaihrd_ctx* ctx, const std::vector<EvalRequest*>& batc
     int64_t at = 0;
     for (const EvalRequest* r : batch)
         for (int64_t b = 0; b < r->B; ++b, ++at) std::memcpy(rows + at * P, r->params + b * r->ld, sizeof(double) * (size_t)P);
-    const sepaihrd_rc rc = eval_batch_serial(ctx, rows, total, P, ll, want_status ? st : nullptr, want_steps ? steps : nullptr);
+    const sepaihrd_rc rc = (total <= COALESCE_MAX_SETS) ? eval_batch_small(ctx, rows, total, P, ll, want_status ? st : nullptr, want_steps ? steps : nullptr)
+                                                        : eval_batch_serial(ctx, rows, total, P, ll, want_status ? st : nullptr, want_steps ? steps : nullptr);
     if (rc != SEPAIHRD_OK) return rc;
     at = 0;
     for (EvalRequest* r : batch) {
@@ -844,8 +916,6 @@ sepaihrd_rc eval_merged(sepaihrd_ctx* ctx, const std::vector<EvalRequest*>& batc
     ctx->merged_requests += (long long)batch.size();
     return SEPAIHRD_OK;
 }
-
-constexpr int64_t COALESCE_MAX_SETS = 4096;      // larger requests fill the machine on their own
 
 }  // namespace
 
@@ -873,7 +943,7 @@ sepaihrd_rc sepaihrd_eval_batch(sepaihrd_ctx* ctx, const double* params, int64_t
         batch.swap(ctx->queue);
         ql.unlock();
         sepaihrd_rc rc;
-        if (batch.size() == 1) rc = eval_batch_serial(ctx, params, B, ld, out_ll, out_status, out_steps);   // nobody else: no staging copy
+        if (batch.size() == 1) rc = eval_batch_small(ctx, params, B, ld, out_ll, out_status, out_steps);    // nobody else
         else rc = eval_merged(ctx, batch);
         const std::string err = (rc != SEPAIHRD_OK) ? g_last_error : std::string();
         ql.lock();

@@ -85,7 +85,8 @@ struct KParams {
                                // to the set's own slot.  Built by the ordering pass (sepaihrd_order.cu) so that a warp holds sets that
                                // need similar numbers of step attempts per day
     int* out_profile;          // PROFILE instantiation only: [B][K] attempts (accepted + rejected) made before each grid point
-    long long tiles;           // ceil(B / sets_per_warp)
+    long long tiles;           // ceil(B / sets_per_tile)
+    int sets_per_tile;         // sets a warp takes at a time: 32 / NA, fewer (down to one) when the launch is smaller than the machine
     int active_warps;          // warps per block that take tiles (all of them unless the launch is smaller than the machine)
     unsigned* tile_counter;    // zeroed before every launch (tiles < 2^32 - grid warps)
 };
@@ -554,9 +555,12 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) sepaihrd_batch_kernel(cons
         if ((threadIdx.x & 31) == 0) wt = atomicAdd(kp.tile_counter, 1u);
         wt = __shfl_sync(FULL, wt, 0);
         if ((long long)wt >= kp.tiles) break;
-        const long long b_raw = (long long)wt * WSETS + grp_in_warp;
-        const bool have = b_raw < kp.B;
-        const long long b_pos = have ? b_raw : (kp.B - 1);   // idle groups shadow the last set; nothing is written for them
+        // a small launch hands out fewer than WSETS sets per tile (a warp then pays for its own sets' attempts only, not for the
+        // day-by-day maximum over eight); idle groups shadow the tile's first set, nothing is written for them
+        const long long b_first = (long long)wt * kp.sets_per_tile;
+        const long long b_raw = b_first + grp_in_warp;
+        const bool have = grp_in_warp < kp.sets_per_tile && b_raw < kp.B;
+        const long long b_pos = have ? b_raw : b_first;
         const long long b = kp.perm ? (long long)kp.perm[b_pos] : b_pos;
 
         // ---- updateModelParameters: base slots, then constrained calibrated values -------------------

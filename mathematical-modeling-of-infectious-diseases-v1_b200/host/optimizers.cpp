@@ -145,25 +145,76 @@ void MetropolisHastingsSampler::ownKernel(Chain& c) const {
 
 void MetropolisHastingsSampler::updateCovarianceRank1(Chain& c, int step) const {
     if (c.history.empty()) return;
+    const auto P = static_cast<std::ptrdiff_t>(n_params_);
     const double gamma = 10.0 / (step + 100.0);
     const VectorXd diff = c.history.back() - c.running_mean;
     c.running_mean += gamma * diff;
-    c.cov = (1.0 - gamma) * c.cov + gamma * outer(diff);
+    // cov = (1 - gamma) cov + gamma diff diff^T, element by element in place (the same three products and one sum per element
+    // as the matrix expression, without its four P x P temporaries)
+    const double keep = 1.0 - gamma;
+    double* cov = c.cov.data();
+    const double* d = diff.data();
+    for (std::ptrdiff_t j = 0; j < P; ++j) {
+        const double dj = d[j];
+        double* col = cov + j * P;
+        for (std::ptrdiff_t i = 0; i < P; ++i) col[i] = keep * col[i] + gamma * (d[i] * dj);
+    }
 }
 
+// .cpp:170-199.  The reference recomputes mean and covariance over the WHOLE chain history every adaptation_period
+// iterations (O(t P^2) each; Eigen's GEMM there).  Same here, every sum in history order: the centred history is laid out
+// once, the lower triangle is accumulated column by column (d_i d_j == d_j d_i bit for bit, so the upper triangle is a copy),
+// and for a long history the columns are shared among the host threads -- a column's sums never leave their thread, so the
+// result does not depend on the thread count.
 void MetropolisHastingsSampler::recomputeFullCovariance(Chain& c) const {
     const auto P = static_cast<std::ptrdiff_t>(n_params_);
     if (c.history.size() < static_cast<size_t>(n_params_) + 10) return;
+    const std::ptrdiff_t n = static_cast<std::ptrdiff_t>(c.history.size());
     VectorXd mean = VectorXd::Zero(P);
     for (const auto& v : c.history) mean += v;
     mean /= static_cast<double>(c.history.size());
     c.running_mean = mean;
-    MatrixXd cov = MatrixXd::Zero(P, P);
-    for (const auto& v : c.history) {
-        const VectorXd d = v - mean;
-        for (std::ptrdiff_t j = 0; j < P; ++j)
-            for (std::ptrdiff_t i = 0; i < P; ++i) cov(i, j) += d(i) * d(j);
+    std::vector<double> centred(static_cast<size_t>(n) * static_cast<size_t>(P));
+    const double* m = mean.data();
+    for (std::ptrdiff_t t = 0; t < n; ++t) {
+        const double* v = c.history[static_cast<size_t>(t)].data();
+        double* row = centred.data() + t * P;
+        for (std::ptrdiff_t i = 0; i < P; ++i) row[i] = v[i] - m[i];
     }
+    MatrixXd cov = MatrixXd::Zero(P, P);
+    double* cv = cov.data();
+    const double* D = centred.data();
+    auto accumulate = [&](std::ptrdiff_t j0, std::ptrdiff_t j1) {       // columns [j0, j1) of the lower triangle, ONE pass over the history
+        std::ptrdiff_t t = 0;
+        for (; t + 4 <= n; t += 4) {                                     // four states per pass over a column, added in history order
+            const double* __restrict r0 = D + t * P;
+            const double* __restrict r1 = r0 + P;
+            const double* __restrict r2 = r1 + P;
+            const double* __restrict r3 = r2 + P;
+            for (std::ptrdiff_t j = j0; j < j1; ++j) {
+                const double d0 = r0[j], d1 = r1[j], d2 = r2[j], d3 = r3[j];
+                double* __restrict col = cv + j * P;
+                for (std::ptrdiff_t i = j; i < P; ++i) col[i] = (((col[i] + r0[i] * d0) + r1[i] * d1) + r2[i] * d2) + r3[i] * d3;
+            }
+        }
+        for (; t < n; ++t) {
+            const double* __restrict row = D + t * P;
+            for (std::ptrdiff_t j = j0; j < j1; ++j) {
+                const double dj = row[j];
+                double* __restrict col = cv + j * P;
+                for (std::ptrdiff_t i = j; i < P; ++i) col[i] += row[i] * dj;
+            }
+        }
+    };
+    if (n_chains_ == 1 && n * P * P > (1 << 22)) {                       // a long history: column pairs shared among the host threads
+        const std::ptrdiff_t blocks = (P + 1) / 2;
+#pragma omp parallel for schedule(dynamic, 1)
+        for (std::ptrdiff_t b = 0; b < blocks; ++b) accumulate(2 * b, std::min<std::ptrdiff_t>(2 * b + 2, P));
+    } else {
+        accumulate(0, P);
+    }
+    for (std::ptrdiff_t j = 0; j < P; ++j)
+        for (std::ptrdiff_t i = j + 1; i < P; ++i) cv[i * P + j] = cv[j * P + i];
     cov *= 1.0 / static_cast<double>(c.history.size() - 1);
     c.cov = ((2.38 * 2.38) / static_cast<double>(n_params_)) * cov + regularization_epsilon_ * MatrixXd::Identity(P, P);
     MatrixXd L;
@@ -232,7 +283,7 @@ void MetropolisHastingsSampler::drawProposal(std::mt19937& gen, const Chain& c, 
 void MetropolisHastingsSampler::propose(IParameterManager& pm, double* out) {
     const auto P = static_cast<std::ptrdiff_t>(n_params_);
     const int t = t_;
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (n_chains_ >= 8)      // one chain (the reference's run): no thread team to wake per iteration
     for (int ci = 0; ci < n_chains_; ++ci) {
         Chain& c = chains_[static_cast<size_t>(ci)];
         adaptKernel(c, t);
@@ -245,7 +296,7 @@ void MetropolisHastingsSampler::propose(IParameterManager& pm, double* out) {
 void MetropolisHastingsSampler::accept(const double* proposed_logpost, uint8_t* accepted_out) {
     const auto P = static_cast<std::ptrdiff_t>(n_params_);
     const int t = t_;
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (n_chains_ >= 8)
     for (int ci = 0; ci < n_chains_; ++ci) {
         Chain& c = chains_[static_cast<size_t>(ci)];
         const double plp = safeValue(proposed_logpost[ci]);
@@ -291,15 +342,16 @@ OptimizationResult MetropolisHastingsSampler::result() const {
     return r;
 }
 
-// How many iterations ahead to evaluate: the smallest K with (1 - rate)^K < 1 % -- the chance that all K are rejected and a
-// longer window would have been used -- from the acceptance rate over the last <= 1000 iterations (the window the scale
-// adaptation keeps anyway).  A launch costs the same from 1 to ~4 000 sets, so the only price of a long window is the host's
-// proposal arithmetic (~4 us each).
+// How many iterations ahead to evaluate.  Proposal k of a window is reached with probability (1 - rate)^(k-1) and then commits
+// exactly one iteration; it costs the host ~6 us of arithmetic (normals, L z, reflection) against ~600 us for the launch that
+// commits ~4 iterations, so it pays while (1 - rate)^(k-1) > ~0.03: K = log(0.025) / log(1 - rate), from the acceptance rate
+// over the last <= 1000 iterations (the window the scale adaptation keeps anyway).  Measured on the device objective at 21 %
+// acceptance: K = 8 5.7 k, 16 6.2 k, 32 5.9 k, 128 5.0 k iterations/s.
 int MetropolisHastingsSampler::windowLength(const Chain& c) const {
     if (lookahead_ > 1) return lookahead_;
     if (c.recent.size() < 50) return 16;
     const double rate = std::max(static_cast<double>(c.recent_sum) / static_cast<double>(c.recent.size()), 0.02);
-    const int k = static_cast<int>(std::ceil(std::log(0.01) / std::log1p(-std::min(rate, 0.9))));
+    const int k = static_cast<int>(std::ceil(std::log(0.025) / std::log1p(-std::min(rate, 0.9))));
     return std::min(std::max(k, 4), 128);
 }
 
