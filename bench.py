@@ -323,7 +323,48 @@ def run_caller_configs(pkg, prob, rank, world, local_rank, dist):
             out["pso65536"] = rec
     except Exception as exc:
         out["pso65536"] = {"error": f"{type(exc).__name__}: {exc}"}
+    if world == 1:
+        out["mh_one_chain"] = run_one_chain(pkg, prob)
     return out
+
+
+ONE_CHAIN_ITERATIONS, ONE_CHAIN_BURN_IN = 2000, 1000
+
+
+def run_one_chain(pkg, prob):
+    """The reference's SHIPPED phase 2: ONE Metropolis-Hastings chain of sequential iterations (data/configuration/mcmc_settings.txt;
+    MetropolisHastingsSampler.cpp:283-384), through the C++ host mirror on the device objective -- one evaluation per launch (what a
+    drop-in behind calculate() gives) against the look-ahead sampler (host/optimizers.cpp runLookahead: the next K iterations'
+    proposals in ONE launch), with the gate that both runs end in the same state, log-posterior, scale and acceptance count, and one
+    host core running the CPU oracle beside them.  2000 iterations, the second 1000 with covariance adaptation."""
+    try:
+        import __graft_entry__ as entry
+        from sepaihrd_b200 import hostlib
+        x0 = prob.base_params()
+        m = hostlib.HostModel(prob)
+        m.calculate(x0)
+        st = dict(mcmc_iterations=ONE_CHAIN_ITERATIONS, burn_in=ONE_CHAIN_BURN_IN, adaptation_period=100, n_chains=1, seed=3, store_samples=0,
+                  write_trace=0, write_checkpoints=0)
+        seq = m.metropolis(dict(st, lookahead=1), x0)
+        la = m.metropolis(dict(st, lookahead=0), x0)
+        m.close()
+        same = bool(np.array_equal(la["last"], seq["last"]) and la["last_logpost"] == seq["last_logpost"] and la["best_value"] == seq["best_value"]
+                    and la["final_scale"] == seq["final_scale"] and la["acceptance_rate"] == seq["acceptance_rate"])
+        orc = entry.load_oracle()
+        o = orc.Oracle(prob)
+        P = o.jitter_params(192, seed=9)
+        o.eval_batch(P[:8], nthreads=1)
+        t0 = time.perf_counter(); o.eval_batch(P, nthreads=1); dt = time.perf_counter() - t0
+        n = ONE_CHAIN_ITERATIONS - 1
+        return {"iterations": ONE_CHAIN_ITERATIONS, "burn_in": ONE_CHAIN_BURN_IN,
+                "sequential": {"iterations_per_s": n / seq["ms"] * 1e3, "launches": seq["launches"], "evaluations": seq["evaluations"]},
+                "lookahead": {"iterations_per_s": n / la["ms"] * 1e3, "launches": la["launches"], "evaluations": la["evaluations"],
+                              "iterations_per_launch": n / max(la["launches"], 1)},
+                "acceptance_rate": seq["acceptance_rate"],
+                "one_host_core_oracle_evals_per_s": len(P) / dt,
+                "parity": {"lookahead_chain_equals_sequential_chain": same}}
+    except Exception as exc:
+        return {"error": f"{type(exc).__name__}: {exc}"}
 
 
 def _claim_stdout():
