@@ -325,6 +325,62 @@ def run_caller_configs(pkg, prob, rank, world, local_rank, dist):
         out["pso65536"] = {"error": f"{type(exc).__name__}: {exc}"}
     if world == 1:
         out["mh_one_chain"] = run_one_chain(pkg, prob)
+        out["ppc100k"] = run_posterior_predictive(pkg, prob)
+    return out
+
+
+PPC_DRAWS = 100000
+
+
+def _ppc_numpy(problem, oracle_obj, P, s0, probs):
+    """ResultAggregator::aggregatePosteriorPredictives (.cpp:276-371) in numpy on ORACLE trajectories: daily increments clamped at 0,
+    their running sums, exact linear-interpolation quantiles over the valid draws -> [6][T][n][Q]."""
+    tr, st = oracle_obj.simulate_from_state(P, s0, what=1)          # [B][K][3n]: D | CumH | CumICU
+    n = problem.n_ages
+    T = int((problem.times >= 0).sum()); first = problem.n_times - T
+    tr = tr[st == 0]
+    blocks = (tr[:, :, n:2 * n], tr[:, :, 2 * n:3 * n], tr[:, :, 0:n])
+    init = (s0[9 * n:10 * n], s0[10 * n:11 * n], s0[8 * n:9 * n])
+    daily = []
+    for X, x0 in zip(blocks, init):
+        prev = X[:, first - 1] if first > 0 else np.broadcast_to(x0, X[:, 0].shape)
+        daily.append(np.maximum(0.0, np.diff(np.concatenate([prev[:, None, :], X[:, first:]], axis=1), axis=1)))
+    series = daily + [np.cumsum(d, axis=1) for d in daily]
+    return np.stack([np.moveaxis(np.quantile(S, probs, axis=0), 0, -1) for S in series])
+
+
+def run_posterior_predictive(pkg, prob):
+    """BASELINE configs[4]: 100 000 posterior draws -> trajectories -> the six posterior-predictive series -> five quantiles per
+    (series, day, age class), ONE C-ABI call from page-locked host draws (sepaihrd_posterior_predictive), for the Spain problem (4 age
+    classes) and the synthetic 16-age-class variant.  Gate in the same job: the quantiles of a 384-draw subsample equal numpy's on
+    oracle trajectories within 1e-8."""
+    import torch
+    from sepaihrd_b200.evaluator import BatchEvaluator
+    orc = entry.load_oracle()
+    out = {}
+    probs = (0.025, 0.05, 0.5, 0.95, 0.975)
+    for ages in (4, 16):
+        try:
+            pq = prob if ages == 4 else prob.expand_ages(ages // 4)
+            oq = orc.Oracle(pq)
+            base = oq.jitter_params(4096, seed=11)
+            draws = torch.from_numpy(np.tile(base, ((PPC_DRAWS + 4095) // 4096, 1))[:PPC_DRAWS].copy()).pin_memory().numpy()
+            s0 = pq.data_initial_state
+            with BatchEvaluator(pq, device=torch.cuda.current_device()) as ev:
+                ev.posterior_predictive(draws, s0, probs)                       # allocates the work buffers
+                ts = []
+                for _ in range(3):
+                    t0 = time.perf_counter(); q, valid = ev.posterior_predictive(draws, s0, probs); ts.append(time.perf_counter() - t0)
+                sub, _ = ev.posterior_predictive(draws[:384], s0, probs)
+            ref = _ppc_numpy(pq, oq, draws[:384], s0, probs)
+            err = float((np.abs(sub - ref) / np.maximum(np.abs(ref), 1e-6)).max())
+            dt = sorted(ts)[1]
+            out[f"{ages}_ages"] = {"draws": PPC_DRAWS, "valid": int(valid), "seconds": dt, "draws_per_s": PPC_DRAWS / dt,
+                                   "quantile_cells": int(q.size), "h2d_bytes": int(draws.nbytes), "d2h_bytes": int(q.nbytes),
+                                   "series_gbytes_on_device": 6 * q.shape[1] * q.shape[2] * PPC_DRAWS * 8 / 1e9,
+                                   "parity": {"subsample_draws": 384, "max_rel_quantile_diff_vs_numpy_on_oracle_trajectories": err, "within_1e-8": err < 1e-8}}
+        except Exception as exc:
+            out[f"{ages}_ages"] = {"error": f"{type(exc).__name__}: {exc}"}
     return out
 
 

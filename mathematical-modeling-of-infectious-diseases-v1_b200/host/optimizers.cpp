@@ -127,6 +127,7 @@ void MetropolisHastingsSampler::begin(const VectorXd& initial, const double* ini
         }
         std::copy(initial.data(), initial.data() + n_params_, cur_x_.begin() + static_cast<std::ptrdiff_t>(c) * n_params_);
         cur_lp_[static_cast<size_t>(c)] = safeValue(initial_logpost[c]);
+        ch.t = 1;
         ch.running_mean = initial;
         ch.best_x = initial;
         ch.best_lp = cur_lp_[static_cast<size_t>(c)];
@@ -282,56 +283,65 @@ void MetropolisHastingsSampler::drawProposal(std::mt19937& gen, const Chain& c, 
 
 void MetropolisHastingsSampler::propose(IParameterManager& pm, double* out) {
     const auto P = static_cast<std::ptrdiff_t>(n_params_);
-    const int t = t_;
 #pragma omp parallel for schedule(static) if (n_chains_ >= 8)      // one chain (the reference's run): no thread team to wake per iteration
     for (int ci = 0; ci < n_chains_; ++ci) {
         Chain& c = chains_[static_cast<size_t>(ci)];
-        adaptKernel(c, t);
+        adaptKernel(c, c.t);
         drawProposal(c.gen, c, c.global_scale, cur_x_.data() + static_cast<std::ptrdiff_t>(ci) * P, pm,
                      prop_x_.data() + static_cast<std::ptrdiff_t>(ci) * P);
     }
     std::copy(prop_x_.begin(), prop_x_.end(), out);
 }
 
-void MetropolisHastingsSampler::accept(const double* proposed_logpost, uint8_t* accepted_out) {
+// Steps 4-7 of the loop for ONE chain at ITS iteration c.t (.cpp:310-367): log-space accept test, state, MAP estimate, scale
+// adaptation, history, thinned samples.  The proposal is row ci of prop_x_.
+bool MetropolisHastingsSampler::acceptOne(Chain& c, int ci, double proposed_logpost) {
     const auto P = static_cast<std::ptrdiff_t>(n_params_);
-    const int t = t_;
+    const int t = c.t;
+    const double plp = safeValue(proposed_logpost);
+    double& clp = cur_lp_[static_cast<size_t>(ci)];
+    const double log_ratio = plp - clp;
+    bool acc = false;
+    if (log_ratio >= 0.0) {
+        acc = true;
+    } else {
+        std::uniform_real_distribution<double> u(0.0, 1.0);      // drawn ONLY for downhill proposals (.cpp:323-329)
+        if (detm::log(u(c.gen)) < log_ratio) acc = true;
+    }
+    double* x = cur_x_.data() + static_cast<std::ptrdiff_t>(ci) * P;
+    if (acc) {
+        std::copy(prop_x_.begin() + static_cast<std::ptrdiff_t>(ci) * P, prop_x_.begin() + static_cast<std::ptrdiff_t>(ci + 1) * P, x);
+        clp = plp;
+        c.accepted++;
+        if (clp > c.best_lp) { c.best_lp = clp; c.best_x = VectorXd::FromPointer(x, P); }
+    }
+    if (adapt_scale_) adaptGlobalScale(c, acc, t);
+    if (keep_history_) c.history.push_back(VectorXd::FromPointer(x, P));
+    if (store_samples_ && (t % thinning_ == 0)) { c.samples.push_back(VectorXd::FromPointer(x, P)); c.sample_lp.push_back(clp); }
+    ++c.t;
+    return acc;
+}
+
+void MetropolisHastingsSampler::accept(const double* proposed_logpost, uint8_t* accepted_out) {
 #pragma omp parallel for schedule(static) if (n_chains_ >= 8)
     for (int ci = 0; ci < n_chains_; ++ci) {
-        Chain& c = chains_[static_cast<size_t>(ci)];
-        const double plp = safeValue(proposed_logpost[ci]);
-        double& clp = cur_lp_[static_cast<size_t>(ci)];
-        const double log_ratio = plp - clp;
-        bool acc = false;
-        if (log_ratio >= 0.0) {
-            acc = true;
-        } else {
-            std::uniform_real_distribution<double> u(0.0, 1.0);      // drawn ONLY for downhill proposals (.cpp:323-329)
-            if (detm::log(u(c.gen)) < log_ratio) acc = true;
-        }
-        double* x = cur_x_.data() + static_cast<std::ptrdiff_t>(ci) * P;
-        if (acc) {
-            std::copy(prop_x_.begin() + static_cast<std::ptrdiff_t>(ci) * P, prop_x_.begin() + static_cast<std::ptrdiff_t>(ci + 1) * P, x);
-            clp = plp;
-            c.accepted++;
-            if (clp > c.best_lp) { c.best_lp = clp; c.best_x = VectorXd::FromPointer(x, P); }
-        }
-        if (adapt_scale_) adaptGlobalScale(c, acc, t);
-        if (keep_history_) c.history.push_back(VectorXd::FromPointer(x, P));
-        if (store_samples_ && (t % thinning_ == 0)) { c.samples.push_back(VectorXd::FromPointer(x, P)); c.sample_lp.push_back(clp); }
+        const bool acc = acceptOne(chains_[static_cast<size_t>(ci)], ci, proposed_logpost[ci]);
         if (accepted_out) accepted_out[ci] = acc ? 1 : 0;
     }
     ++t_;
 }
 
-OptimizationResult MetropolisHastingsSampler::result() const {
+// upto >= 0: only the samples of iterations <= upto (a look-ahead run writes its checkpoints with every chain cut at the
+// reporting iteration, although some chains are already past it)
+OptimizationResult MetropolisHastingsSampler::result(int upto) const {
     OptimizationResult r;
     long accepted = 0;
     for (const Chain& c : chains_) {
         if (c.best_lp > r.bestObjectiveValue || r.bestParameters.size() == 0) { r.bestObjectiveValue = c.best_lp; r.bestParameters = c.best_x; }
         accepted += c.accepted;
-        r.samples.insert(r.samples.end(), c.samples.begin(), c.samples.end());                 // chain-major
-        r.sampleObjectiveValues.insert(r.sampleObjectiveValues.end(), c.sample_lp.begin(), c.sample_lp.end());
+        const size_t keep = upto < 0 ? c.samples.size() : std::min(c.samples.size(), static_cast<size_t>(1 + upto / thinning_));
+        r.samples.insert(r.samples.end(), c.samples.begin(), c.samples.begin() + static_cast<std::ptrdiff_t>(keep));     // chain-major
+        r.sampleObjectiveValues.insert(r.sampleObjectiveValues.end(), c.sample_lp.begin(), c.sample_lp.begin() + static_cast<std::ptrdiff_t>(keep));
     }
     r.finalCovariance = chains_.empty() || !chains_.front().own_kernel ? shared_cov_ : chains_.front().cov;
     r.additionalStats["acceptance_rate"] = static_cast<double>(accepted) / (static_cast<double>(iterations_) * std::max(1, n_chains_));
@@ -355,43 +365,76 @@ int MetropolisHastingsSampler::windowLength(const Chain& c) const {
     return std::min(std::max(k, 4), 128);
 }
 
-// One chain, K iterations per device launch (see optimizers.hpp).  The chain object only ever changes through the calls the
-// sequential loop makes -- adaptKernel, the generator draws, accept() -- in the sequential order; the speculation works on
-// copies of the generator and of the scale state.
+// K iterations of every chain per device launch (see optimizers.hpp).  A chain object only ever changes through the calls the
+// sequential loop makes -- adaptKernel, the generator draws, acceptOne -- in the sequential order; the speculation works on
+// copies of the generator and of the scale state.  Chains advance by different amounts per launch (each up to its first
+// accepted proposal), so every chain carries its own iteration counter; a launch holds at most LOOKAHEAD_SETS proposals
+// (the range in which its cost does not depend on their number), shared evenly among the chains still running.
 void MetropolisHastingsSampler::runLookahead(IObjectiveFunction& f, IParameterManager& pm, const std::string& dir) {
     const auto P = static_cast<std::ptrdiff_t>(n_params_);
-    Chain& c = chains_.front();
+    const int n = n_chains_;
+    std::vector<int> K(static_cast<size_t>(n));
+    std::vector<std::ptrdiff_t> first(static_cast<size_t>(n) + 1);
     std::vector<double> props;
-    std::uniform_real_distribution<double> u01(0.0, 1.0);
     while (!done()) {
-        const int t0 = t_;
-        int K = std::min(windowLength(c), iterations_ - t0);
-        // the proposal kernel L must not change inside the window: an iteration that refactors it (.cpp:292-302) may open
-        // a window (its adaptation runs before anything is drawn), it may not sit inside one
-        for (int j = 1; j < K; ++j)
-            if (t0 + j > burn_in_ && (t0 + j) % adaptation_period_ == 0) { K = j; break; }
-        adaptKernel(c, t0);
-        std::mt19937 gen = c.gen;
-        ScaleState sc = c;
-        props.resize(static_cast<size_t>(K) * static_cast<size_t>(P));
-        for (int j = 0; j < K; ++j) {
-            drawProposal(gen, c, sc.global_scale, cur_x_.data(), pm, props.data() + static_cast<std::ptrdiff_t>(j) * P);
-            (void)u01(gen);                                          // a rejected proposal was a downhill one: its uniform is drawn
-            if (adapt_scale_) adaptGlobalScale(sc, false, t0 + j);
+        int running = 0;
+        for (const Chain& c : chains_) running += c.t < iterations_;
+        const int share = std::max(1, LOOKAHEAD_SETS / std::max(running, 1));
+        first[0] = 0;
+        for (int ci = 0; ci < n; ++ci) {
+            const Chain& c = chains_[static_cast<size_t>(ci)];
+            int k = std::min(std::min(windowLength(c), share), iterations_ - c.t);
+            // the proposal kernel L must not change inside the window: an iteration that refactors it (.cpp:292-302) may open
+            // a window (its adaptation runs before anything is drawn), it may not sit inside one
+            for (int j = 1; j < k; ++j)
+                if (c.t + j > burn_in_ && (c.t + j) % adaptation_period_ == 0) { k = j; break; }
+            K[static_cast<size_t>(ci)] = std::max(k, 0);
+            first[static_cast<size_t>(ci) + 1] = first[static_cast<size_t>(ci)] + K[static_cast<size_t>(ci)];
         }
-        const std::vector<double> plp = evaluate_rows(f, props, K, P);
-        speculated_ += K;
-        for (int j = 0; j < K; ++j) {
-            const int t = t_;
-            if (j > 0) adaptKernel(c, t);                            // rank-1 update of the covariance only (no refactoring, see above)
-            PolarNormal dist;                                        // the generator makes the draws of this iteration's proposal
-            for (std::ptrdiff_t i = 0; i < P; ++i) (void)dist(c.gen);
-            std::copy(props.begin() + static_cast<std::ptrdiff_t>(j) * P, props.begin() + static_cast<std::ptrdiff_t>(j + 1) * P, prop_x_.begin());
-            uint8_t acc = 0;
-            accept(&plp[static_cast<size_t>(j)], &acc);              // the uniform (if the proposal is downhill), state, scale, history, samples; ++t_
-            ++committed_;
-            if (!dir.empty() && write_checkpoints_ && (t + 1) % report_interval_ == 0) saveCheckpoint(result(), pm, false, dir);   // .cpp:380-382
-            if (acc) break;
+        const int64_t total = first[static_cast<size_t>(n)];
+        props.resize(static_cast<size_t>(total) * static_cast<size_t>(P));
+#pragma omp parallel for schedule(static) if (n >= 8)
+        for (int ci = 0; ci < n; ++ci) {
+            Chain& c = chains_[static_cast<size_t>(ci)];
+            const int k = K[static_cast<size_t>(ci)];
+            if (k == 0) continue;
+            adaptKernel(c, c.t);
+            std::mt19937 gen = c.gen;
+            ScaleState sc = c;
+            std::uniform_real_distribution<double> u01(0.0, 1.0);
+            for (int j = 0; j < k; ++j) {
+                drawProposal(gen, c, sc.global_scale, cur_x_.data() + static_cast<std::ptrdiff_t>(ci) * P, pm,
+                             props.data() + (first[static_cast<size_t>(ci)] + j) * P);
+                (void)u01(gen);                                      // a rejected proposal was a downhill one: its uniform is drawn
+                if (adapt_scale_) adaptGlobalScale(sc, false, c.t + j);
+            }
+        }
+        const std::vector<double> plp = evaluate_rows(f, props, total, P);
+        speculated_ += total;
+        long committed = 0;
+#pragma omp parallel for schedule(static) reduction(+ : committed) if (n >= 8)
+        for (int ci = 0; ci < n; ++ci) {
+            Chain& c = chains_[static_cast<size_t>(ci)];
+            for (int j = 0; j < K[static_cast<size_t>(ci)]; ++j) {
+                if (j > 0) adaptKernel(c, c.t);                      // rank-1 update of the covariance only (no refactoring, see above)
+                PolarNormal dist;                                    // the generator makes the draws of this iteration's proposal
+                for (std::ptrdiff_t i = 0; i < P; ++i) (void)dist(c.gen);
+                const double* row = props.data() + (first[static_cast<size_t>(ci)] + j) * P;
+                std::copy(row, row + P, prop_x_.begin() + static_cast<std::ptrdiff_t>(ci) * P);
+                ++committed;
+                if (acceptOne(c, ci, plp[static_cast<size_t>(first[static_cast<size_t>(ci)] + j)])) break;   // the uniform (if downhill), state, scale, history, samples
+            }
+        }
+        committed_ += committed;
+        // the lockstep loop writes a checkpoint after iteration t when (t + 1) % report_interval == 0 (.cpp:380-382): here once ALL
+        // chains have completed such an iteration, with every chain cut at it
+        const int t_before = t_;
+        t_ = iterations_;
+        for (const Chain& c : chains_) t_ = std::min(t_, c.t);
+        if (!dir.empty() && write_checkpoints_) {
+            int last = -1;
+            for (int t = t_before; t < t_; ++t) if ((t + 1) % report_interval_ == 0) last = t;
+            if (last >= 0) saveCheckpoint(result(last), pm, false, dir);
         }
     }
 }
@@ -406,7 +449,7 @@ OptimizationResult MetropolisHastingsSampler::optimize(const VectorXd& initial, 
     std::vector<double> prop(static_cast<size_t>(n_chains_) * static_cast<size_t>(P));
     const std::string dir = (store_samples_ && (write_checkpoints_ || write_trace_)) ? traceDirectory() : std::string();
     speculated_ = committed_ = 0;
-    if (n_chains_ == 1 && lookahead_ != 1) runLookahead(f, pm, dir);
+    if (lookahead_ != 1 && 2 * n_chains_ <= LOOKAHEAD_SETS) runLookahead(f, pm, dir);
     while (!done()) {
         const int t = t_;
         propose(pm, prop.data());

@@ -61,10 +61,10 @@ public:
     const MatrixXd& sharedCholesky() const { return shared_chol_; }         // lower factor of the start kernel (after begin)
     double globalScale(int chain) const { return chains_[static_cast<size_t>(chain)].global_scale; }
     long acceptedCount(int chain) const { return chains_[static_cast<size_t>(chain)].accepted; }
-    OptimizationResult result() const;
+    OptimizationResult result(int upto_iteration = -1) const;
     static double safeValue(double v) { return (std::isnan(v) || std::isinf(v)) ? -1e18 : v; }   // safeEvaluate, .cpp:65-74
 
-    // Look-ahead (setting "lookahead": 0 = sized from the recent acceptance rate, 1 = off, K = that many; one chain only).
+    // Look-ahead (setting "lookahead": 0 = sized from the recent acceptance rate, 1 = off, K = that many; up to 2048 chains).
     // The reference's shipped run is ONE chain of 100 000 sequential iterations (data/configuration/mcmc_settings.txt,
     // .cpp:283-384): one evaluation per device launch, and a launch costs ~0.5 ms whatever it holds.  Between two accepted
     // proposals the chain does not move, so the proposals of the next K iterations ARE known before any of them is evaluated:
@@ -72,6 +72,8 @@ public:
     // uniform, .cpp:323-329) and s_j the scale after j more rejections (.cpp:104-152).  optimize() evaluates those K as one
     // batch, commits iterations up to and including the first accepted one and throws the rest away.  The chain, its
     // generator, scale, covariance and trace files are bit for bit those of the sequential run (tests/test_mh_lookahead.py).
+    // With several chains every chain looks ahead on its own (the chains then run apart by a few iterations between launches;
+    // a launch holds at most 4096 proposals, so the windows shrink as the chain count grows: 256 chains x 16, 2048 x 2).
     int lookahead() const { return lookahead_; }
     long speculatedEvaluations() const { return speculated_; }          // evaluations made / iterations they committed
     long committedIterations() const { return committed_; }
@@ -85,6 +87,7 @@ private:
     };
     struct Chain : ScaleState {
         std::mt19937 gen;
+        int t = 1;                        // next iteration of THIS chain (== iteration() in the lockstep loop; look-ahead lets chains run apart)
         long accepted = 0;
         bool own_kernel = false;          // false: shares the initial Cholesky factor
         MatrixXd cov, chol;
@@ -97,6 +100,7 @@ private:
     };
     void adaptGlobalScale(ScaleState& c, bool accepted, int step) const;   // .cpp:104-152
     void adaptKernel(Chain& c, int step) const;                          // .cpp:286-303
+    bool acceptOne(Chain& c, int ci, double proposed_logpost);           // .cpp:310-367
     void drawProposal(std::mt19937& gen, const Chain& c, double scale, const double* x, IParameterManager& pm, double* out) const;   // .cpp:91-102, 308
     int windowLength(const Chain& c) const;
     void runLookahead(IObjectiveFunction& f, IParameterManager& pm, const std::string& dir);
@@ -113,6 +117,7 @@ private:
     bool adapt_scale_ = true, store_samples_ = true;
     int n_chains_ = 1;
     int lookahead_ = 0;
+    static constexpr int LOOKAHEAD_SETS = 4096;          // proposals per launch: up to here a launch costs what one set costs
     long speculated_ = 0, committed_ = 0;
     long chain_offset_ = 0;
     bool shared_diagonal_ = false;

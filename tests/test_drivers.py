@@ -173,8 +173,10 @@ def test_whole_run_optimizers_improve_the_oracle_likelihood(host, problem, oracl
     best, val, nev = host.optimize("pso", pm, dict(iterations=3, swarm_size=12, seed=4), ev, x0)
     assert val >= f0 and nev == 12 * 2 + 3 * 12 + 3
     pm.set_mode(1)
-    best, val, nev = host.optimize("mh", pm, dict(mcmc_iterations=6, burn_in=6, n_chains=3, seed=4), ev, x0)
+    best, val, nev = host.optimize("mh", pm, dict(mcmc_iterations=6, burn_in=6, n_chains=3, seed=4, lookahead=1), ev, x0)
     assert val >= f0 and nev == 1 + 5 * 3
+    best2, val2, nev2 = host.optimize("mh", pm, dict(mcmc_iterations=6, burn_in=6, n_chains=3, seed=4), ev, x0)      # look-ahead (the default)
+    assert val2 == val and np.array_equal(best2, best) and nev2 > nev
     with pytest.raises(host.HostError):
         host.optimize("pso", pm, dict(iterations=1, swarm_size=4, variant=5), ev, x0)      # "variant must be between 0 and 4"
 

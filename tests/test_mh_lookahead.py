@@ -94,9 +94,32 @@ def test_lookahead_cuts_the_number_of_launches(host, problem, tmp_path):
     assert la["nev"] < 25 * launches
 
 
-def test_multichain_runs_ignore_lookahead(host, problem, tmp_path):
-    st = dict(mcmc_iterations=40, burn_in=40, n_chains=3, seed=2, write_trace=0, write_checkpoints=0)
-    a = _run(host, problem, tmp_path, "a", "gauss", dict(st, lookahead=1))
-    b = _run(host, problem, tmp_path, "b", "gauss", dict(st, lookahead=0))
-    assert a["nev"] == b["nev"] == 1 + 3 * 39 and all(len(c) == 3 for c in b["calls"][1:])
-    np.testing.assert_array_equal(a["best"], b["best"])
+@pytest.mark.parametrize("n_chains", [3, 12])
+@pytest.mark.parametrize("kind", ["gauss", "plateau"])
+def test_multichain_lookahead_equals_the_lockstep_run(host, problem, tmp_path, n_chains, kind):
+    """Several chains: every chain looks ahead on its own (its own iteration counter; the chains run apart between launches).
+    Samples of all chains, checkpoints (every chain cut at the reporting iteration) and best value equal the lockstep run's."""
+    st = dict(mcmc_iterations=230, burn_in=90, adaptation_period=40, n_chains=n_chains, report_interval=50, thinning=3, seed=21)
+    lock = _run(host, problem, tmp_path, "lock", kind, dict(st, lookahead=1))
+    assert lock["nev"] == 1 + n_chains * 229 and all(len(c) == n_chains for c in lock["calls"][1:])
+    for la in (0, 5):
+        r = _run(host, problem, tmp_path, f"la{la}", kind, dict(st, lookahead=la))
+        assert sorted(r["files"]) == sorted(lock["files"]) == ["posterior_trace.csv", "posterior_trace_checkpoint.csv", "posterior_trace_final.csv"]
+        for name in lock["files"]:
+            assert r["files"][name] == lock["files"][name], f"{name} differs ({n_chains} chains, lookahead {la}, {kind})"
+        np.testing.assert_array_equal(r["best"], lock["best"])
+        assert r["val"] == lock["val"]
+        assert len(r["calls"]) < len(lock["calls"]) / 2                                  # fewer launches
+        assert max(len(c) for c in r["calls"]) <= 4096
+
+
+def test_many_chains_share_the_launch_budget(host, problem, tmp_path):
+    """A launch holds at most 4096 proposals: 1500 chains look 2 ahead, 3000 chains run in lockstep."""
+    st = dict(mcmc_iterations=6, burn_in=6, seed=2, write_trace=0, write_checkpoints=0, store_samples=0)
+    a = _run(host, problem, tmp_path, "a", "gauss", dict(st, n_chains=1500))
+    assert max(len(c) for c in a["calls"]) <= 4096 and any(len(c) > 1500 for c in a["calls"])
+    b = _run(host, problem, tmp_path, "b", "gauss", dict(st, n_chains=3000))
+    assert all(len(c) == 3000 for c in b["calls"][1:]) and b["nev"] == 1 + 3000 * 5
+    c = _run(host, problem, tmp_path, "c", "gauss", dict(st, n_chains=1500, lookahead=1))
+    np.testing.assert_array_equal(a["best"], c["best"])
+    assert a["val"] == c["val"]

@@ -40,6 +40,16 @@ for name, la in (("sequential", 1), ("lookahead auto", 0), ("lookahead 8", 8), (
                      acceptance_rate=r["acceptance_rate"], final_scale=r["final_scale"], best=r["best_value"], last_logpost=r["last_logpost"],
                      identical_to_sequential=same))
     print(json.dumps(rows[-1]), flush=True)
+# a few chains: every chain looks ahead on its own (a launch holds at most 4096 proposals)
+multi = []
+for nc in (4, 64, 512):
+    stc = dict(st, n_chains=nc, mcmc_iterations=600, burn_in=300)
+    a0 = m.metropolis(dict(stc, lookahead=1), x0)
+    a1 = m.metropolis(dict(stc, lookahead=0), x0)
+    same = bool(np.array_equal(a0["last"], a1["last"]) and a0["best_value"] == a1["best_value"] and a0["acceptance_rate"] == a1["acceptance_rate"])
+    multi.append(dict(chains=nc, iterations=600, lockstep_chain_iterations_per_s=nc * 599 / a0["ms"] * 1e3, lookahead_chain_iterations_per_s=nc * 599 / a1["ms"] * 1e3,
+                      lockstep_launches=a0["launches"], lookahead_launches=a1["launches"], lookahead_evaluations=a1["evaluations"], identical=same))
+    print(json.dumps(multi[-1]), flush=True)
 # one host core, the oracle (== the reference's arithmetic for one calculate(); BASELINE.md: the port is faster than the reference build)
 o = orc.Oracle(p)
 P = o.jitter_params(256, seed=9)
@@ -48,6 +58,7 @@ t0 = time.perf_counter(); o.eval_batch(P, nthreads=1); dt = time.perf_counter() 
 cpu = dict(run="one host core, CPU oracle", evals_per_s=len(P) / dt, sample="256 jittered sets, 1 thread")
 print(json.dumps(cpu), flush=True)
 assert all(r["identical_to_sequential"] for r in rows), "look-ahead chain differs from the sequential chain"
+assert all(r["identical"] for r in multi), "multi-chain look-ahead differs from the lockstep run"
 if a.json:
     with open(a.json, "w") as f:
-        json.dump(dict(runs=rows, cpu=cpu, iterations=a.iterations, burn_in=a.burn_in), f, indent=1)
+        json.dump(dict(runs=rows, multi=multi, cpu=cpu, iterations=a.iterations, burn_in=a.burn_in), f, indent=1)
