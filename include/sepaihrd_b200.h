@@ -310,6 +310,23 @@ sepaihrd_rc sepaihrd_mh_logpost_device(sepaihrd_mh* mh, const double** d_logpost
  * r's n_chains/world (+1 for the first n_chains % world ranks) values at the start of its block.  Enqueues. */
 sepaihrd_rc sepaihrd_mh_note_gathered(sepaihrd_mh* mh, const double* d_all_logpost, int32_t world, int64_t block_stride,
                                       int32_t trace_slot);
+/* Look-ahead windows: K iterations of every chain per likelihood launch.  A launch costs the same from 1 to ~4 000 parameter
+ * sets, and while a chain rejects it does not move, so the proposals of its next K iterations are known in advance (the
+ * generator's next normals; a rejected iteration has consumed its uniform, MetropolisHastingsSampler.cpp:323-329; the scale
+ * after j more rejections, :104-152).  _propose draws them for every local chain from a copy of its generator, _evaluate scores
+ * local_count x K proposals in ONE launch, _commit replays the sequential loop of every chain up to and including its first
+ * accepted proposal and discards the rest.  Decisions, states, scales and generator positions are those of the
+ * one-iteration-per-launch phases above; chains advance by different amounts, so each keeps its own iteration index, and a run
+ * uses EITHER the windows OR the one-iteration phases.  1 <= K <= 64; the first window of a run fixes the largest K (>= 8).
+ * _commit also fills the rank's record for the per-window exchange: [0, local_count) the chains' current log-posteriors,
+ * [record_stride] the smallest next-iteration index among the local chains as a double (settings.iterations once all are
+ * done); record_stride = local_count or local_count + 1 (the largest shard of the run; 0 = local_count).
+ * _progress synchronises and returns that index (also what sepaihrd_mh_iteration reports afterwards). */
+sepaihrd_rc sepaihrd_mh_window_propose(sepaihrd_mh* mh, int32_t K);
+sepaihrd_rc sepaihrd_mh_window_evaluate(sepaihrd_mh* mh);
+sepaihrd_rc sepaihrd_mh_window_commit(sepaihrd_mh* mh, int64_t record_stride);
+sepaihrd_rc sepaihrd_mh_window_record(sepaihrd_mh* mh, const double** d_record);
+sepaihrd_rc sepaihrd_mh_window_progress(sepaihrd_mh* mh, int32_t* out_min_iteration);
 /* Copy one of the sampler's arrays to the host (SEPAIHRD_MH_*); synchronises the ctx stream. */
 sepaihrd_rc sepaihrd_mh_read(sepaihrd_mh* mh, int32_t what, void* out);
 

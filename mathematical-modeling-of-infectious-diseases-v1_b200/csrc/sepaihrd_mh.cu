@@ -25,6 +25,7 @@
 // generator state is chain-major ([chains][624]); a warp twists 32 consecutive words per step (word k needs the old k, k + 1 and
 // the word 397 ahead or 227 behind: never one of the same step), loads before stores.  ~15 us per iteration for 4096 chains
 // against >= 550 us for the likelihood launch (the first version, one thread per chain, took 220 us).
+#include <algorithm>
 #include <cfloat>
 #include <cmath>
 #include <cstdint>
@@ -50,6 +51,15 @@ struct sepaihrd_mh {
     long long* d_accepted = nullptr;
     unsigned char* d_accepts = nullptr;        // [iterations - 1][local] when record_accepts
     int trace_cap = 0;
+    // look-ahead windows (sepaihrd_mh_window_*): every chain has its own iteration counter
+    bool windowed = false;
+    int win_cap = 0, win_K = 0;                // proposals per chain the window buffers hold / of the window in flight
+    char* d_win = nullptr;
+    int* d_t = nullptr;                        // [local] next iteration of every chain
+    int* d_tmin = nullptr;                     // min over d_t after the last commit
+    unsigned* d_ghost = nullptr;               // [local][624] generator copies the proposals of a window are drawn from
+    double *d_wprop = nullptr, *d_wplp = nullptr, *d_wlogu = nullptr, *d_record = nullptr;
+    unsigned *d_wCz = nullptr, *d_wstatus = nullptr;
 };
 
 namespace {
@@ -149,22 +159,11 @@ __global__ void mh_start_kernel(long long local, int P, const double* __restrict
     recent_n[c] = 0; recent_sum[c] = 0; emergency[c] = 0; accepted[c] = 0;
 }
 
-// generateProposal + applyConstraints: one warp per local chain
-__global__ void __launch_bounds__(MH_THREADS) mh_propose_kernel(long long local, int P, int diagonal, int mode, const double* __restrict__ chol,
-                                                                 const double* __restrict__ lo, const double* __restrict__ hi,
-                                                                 const double* __restrict__ x, const double* __restrict__ scale,
-                                                                 unsigned* __restrict__ mt, unsigned* __restrict__ Cc, unsigned* __restrict__ Tt,
-                                                                 double* __restrict__ prop, unsigned* __restrict__ fault) {
-    __shared__ double zs[MH_WARPS][SEPAIHRD_MH_MAX_PARAMS];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const long long c = blockIdx.x * (long long)MH_WARPS + wib;
-    if (c >= local) return;
-    unsigned* st = mt + c * MT_N;
-    unsigned C = Cc[c], T = Tt[c];
-    double* z = zs[wib];
-    // std::normal_distribution<double>(0, 1), a FRESH object per proposal (the reference declares it inside generateProposal):
-    // polar method; the first value of an accepted pair is y * mult, the second (returned by the next call) x * mult.
-    // Attempt j of this proposal reads the outputs C + 4 j ... C + 4 j + 3 whatever happened to the attempts before it.
+// std::normal_distribution<double>(0, 1), a FRESH object per proposal (the reference declares it inside generateProposal):
+// polar method; the first value of an accepted pair is y * mult, the second (returned by the next call) x * mult.
+// Attempt j of this proposal reads the outputs C + 4 j ... C + 4 j + 3 whatever happened to the attempts before it.
+// One warp: z[0 .. P) in shared memory, C / T advanced.
+__device__ __forceinline__ void warp_draw_normals(unsigned* st, unsigned& C, unsigned& T, int lane, int P, double* z, unsigned* fault) {
     const int npairs = (P + 1) / 2;
     int got = 0, consumed = -1;
     for (int base = 0; base < 128 && consumed < 0; base += 32) {
@@ -192,19 +191,74 @@ __global__ void __launch_bounds__(MH_THREADS) mh_propose_kernel(long long local,
     }
     C += (unsigned)consumed;
     __syncwarp();
-    const double sc = scale[c];
-    const double* xc = x + c * P;
-    double* out = prop + c * P;
+}
+
+// y = constrain(x + s L z): row i of L z summed over the columns j = 0 .. i in the host's order (the structural zeros add nothing)
+__device__ __forceinline__ void warp_make_proposal(int lane, int P, int diagonal, int mode, const double* __restrict__ chol, const double* __restrict__ lo,
+                                                   const double* __restrict__ hi, const double* __restrict__ xc, double sc, const double* z,
+                                                   double* __restrict__ out) {
     for (int i = lane; i < P; i += 32) {
         double step;
         if (diagonal) {
             step = __dmul_rn(chol[(long long)i * P + i], z[i]);
-        } else {        // row i of L z: the host adds the columns j = 0 .. i in this order (the structural zeros add nothing)
+        } else {
             step = 0.0;
             for (int j = 0; j <= i; ++j) step = __dadd_rn(step, __dmul_rn(chol[(long long)j * P + i], z[j]));
         }
         out[i] = sepaihrd::constrain(__dadd_rn(xc[i], __dmul_rn(sc, step)), lo[i], hi[i], mode);
     }
+}
+
+// adaptGlobalScale (.cpp:104-152) for one decision at the reference's 1-based iteration `step`: the ring of the last <= 1000
+// decisions (one bit each; the host pushes, then drops the oldest once there are more than 1000), Robbins-Monro on its rate
+__device__ __forceinline__ void scale_update(bool acc, int step, double target, unsigned* ring, int& n, int& sum, int& emergency, double& ls, double& sc) {
+    const int slot = n % 1000;
+    unsigned* wp = ring + (slot >> 5);
+    unsigned w = *wp;
+    const unsigned bit = 1u << (slot & 31);
+    if (n >= 1000) sum -= (w & bit) ? 1 : 0;
+    w = acc ? (w | bit) : (w & ~bit);
+    *wp = w;
+    sum += acc ? 1 : 0;
+    n += 1;
+    const int size = n < 1000 ? n : 1000;
+    const double rate = __ddiv_rn((double)sum, (double)size);
+    const double s1 = __dadd_rn((double)step, 1.0);
+    if (size >= 1000 && rate < 0.001) {
+        ls = __dsub_rn(ls, 0.7);
+        emergency += 1;
+    } else if (rate < 0.02 && size >= 500) {
+        const double g5 = __ddiv_rn(5.0, __dsqrt_rn(s1));
+        const double gg = (0.3 < g5) ? 0.3 : g5;                                  // std::min(g5, 0.3)
+        ls = __dadd_rn(ls, __dmul_rn(gg, __dsub_rn(0.0, target)));
+    } else {
+        const double g1 = __ddiv_rn(1.0, __dsqrt_rn(s1));
+        const double gg = (0.1 < g1) ? 0.1 : g1;
+        ls = __dadd_rn(ls, __dmul_rn(gg, __dsub_rn(acc ? 1.0 : 0.0, target)));
+    }
+    if (sc <= 0.011 && rate > 0.15 && rate < 0.30) ls = __dadd_rn(ls, 0.01);
+    {   // std::max(std::min(ls, 2.3), -6.9)
+        const double lo_c = (2.3 < ls) ? 2.3 : ls;
+        ls = (lo_c < -6.9) ? -6.9 : lo_c;
+    }
+    sc = detm::exp(ls);
+}
+
+// generateProposal + applyConstraints: one warp per local chain
+__global__ void __launch_bounds__(MH_THREADS) mh_propose_kernel(long long local, int P, int diagonal, int mode, const double* __restrict__ chol,
+                                                                 const double* __restrict__ lo, const double* __restrict__ hi,
+                                                                 const double* __restrict__ x, const double* __restrict__ scale,
+                                                                 unsigned* __restrict__ mt, unsigned* __restrict__ Cc, unsigned* __restrict__ Tt,
+                                                                 double* __restrict__ prop, unsigned* __restrict__ fault) {
+    __shared__ double zs[MH_WARPS][SEPAIHRD_MH_MAX_PARAMS];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const long long c = blockIdx.x * (long long)MH_WARPS + wib;
+    if (c >= local) return;
+    unsigned* st = mt + c * MT_N;
+    unsigned C = Cc[c], T = Tt[c];
+    double* z = zs[wib];
+    warp_draw_normals(st, C, T, lane, P, z, fault);
+    warp_make_proposal(lane, P, diagonal, mode, chol, lo, hi, x + c * P, scale[c], z, prop + c * P);
     if (lane == 0) { Cc[c] = C; Tt[c] = T; }
 }
 
@@ -253,41 +307,141 @@ __global__ void __launch_bounds__(MH_THREADS) mh_accept_kernel(long long local, 
     }
     if (accepts_row) accepts_row[c] = acc ? 1 : 0;
     if (!adapt_scale) return;
-    // recent: the last <= 1000 decisions (the host pushes, then drops the oldest once there are more than 1000)
-    int n = recent_n[c], sum = recent_sum[c];
-    const int slot = n % 1000;
-    unsigned* wp = recent + c * RECENT_WORDS + (slot >> 5);
-    unsigned w = *wp;
-    const unsigned bit = 1u << (slot & 31);
-    if (n >= 1000) sum -= (w & bit) ? 1 : 0;
-    w = acc ? (w | bit) : (w & ~bit);
-    *wp = w;
-    sum += acc ? 1 : 0;
-    n += 1;
-    recent_n[c] = n; recent_sum[c] = sum;
-    const int size = n < 1000 ? n : 1000;
-    const double rate = __ddiv_rn((double)sum, (double)size);
-    double ls = log_scale[c];
-    const double s1 = __dadd_rn((double)step, 1.0);
-    if (size >= 1000 && rate < 0.001) {
-        ls = __dsub_rn(ls, 0.7);
-        emergency[c] += 1;
-    } else if (rate < 0.02 && size >= 500) {
-        const double g5 = __ddiv_rn(5.0, __dsqrt_rn(s1));
-        const double gg = (0.3 < g5) ? 0.3 : g5;                                  // std::min(g5, 0.3)
-        ls = __dadd_rn(ls, __dmul_rn(gg, __dsub_rn(0.0, target)));
-    } else {
-        const double g1 = __ddiv_rn(1.0, __dsqrt_rn(s1));
-        const double gg = (0.1 < g1) ? 0.1 : g1;
-        ls = __dadd_rn(ls, __dmul_rn(gg, __dsub_rn(acc ? 1.0 : 0.0, target)));
-    }
-    if (scale[c] <= 0.011 && rate > 0.15 && rate < 0.30) ls = __dadd_rn(ls, 0.01);
-    {   // std::max(std::min(ls, 2.3), -6.9)
-        const double lo_c = (2.3 < ls) ? 2.3 : ls;
-        ls = (lo_c < -6.9) ? -6.9 : lo_c;
-    }
+    int n = recent_n[c], sum = recent_sum[c], em = emergency[c];
+    double ls = log_scale[c], sc = scale[c];
+    scale_update(acc, step, target, recent + c * RECENT_WORDS, n, sum, em, ls, sc);
+    recent_n[c] = n; recent_sum[c] = sum; emergency[c] = em;
     log_scale[c] = ls;
-    scale[c] = detm::exp(ls);
+    scale[c] = sc;
+}
+
+// ---- look-ahead windows -----------------------------------------------------------------------------------------------------
+// A launch of the likelihood kernel costs the same from 1 to ~4 000 sets, and while a chain rejects it does not move: the
+// proposals of its next K iterations are known before any of them is scored -- iteration t + j proposes x + s_j L z_j with z_j the
+// generator's next normals (a rejected iteration was a downhill one and has consumed its uniform, .cpp:323-329) and s_j the scale
+// after j more rejections (.cpp:104-152).  mh_window_propose_kernel draws them from a COPY of the chain's generator and scale
+// state; the likelihood kernel scores local x K proposals in one launch; mh_window_commit_kernel replays the sequential loop up
+// to and including the first accepted proposal and leaves the generator where the sequential run would have left it (the
+// number of words consumed is all that has to be carried over: the state is twisted forward to it).  Chains advance by
+// different amounts per window, so each has its own iteration counter.  Same decisions, same states as the one-iteration-per-
+// launch loop above and as the host sampler (tests/test_gpu_resident.py).
+__global__ void __launch_bounds__(MH_THREADS) mh_window_propose_kernel(long long local, int P, int K, int iterations, int diagonal, int mode, int adapt_scale,
+                                                                        double target, const double* __restrict__ chol, const double* __restrict__ lo,
+                                                                        const double* __restrict__ hi, const double* __restrict__ x,
+                                                                        const double* __restrict__ log_scale, const double* __restrict__ scale,
+                                                                        const unsigned* __restrict__ recent, const int* __restrict__ recent_n,
+                                                                        const int* __restrict__ recent_sum, const unsigned* __restrict__ mt,
+                                                                        const unsigned* __restrict__ Cc, const unsigned* __restrict__ Tt,
+                                                                        const int* __restrict__ t_next, unsigned* __restrict__ ghost,
+                                                                        double* __restrict__ wprop, unsigned* __restrict__ wCz, double* __restrict__ wlogu,
+                                                                        unsigned* __restrict__ fault) {
+    __shared__ double zs[MH_WARPS][SEPAIHRD_MH_MAX_PARAMS];
+    __shared__ unsigned rings[MH_WARPS][RECENT_WORDS];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const long long c = blockIdx.x * (long long)MH_WARPS + wib;
+    if (c >= local) return;
+    const int t0 = t_next[c];
+    const int k_eff = max(0, min(K, iterations - t0));
+    unsigned* st = ghost + c * MT_N;
+    for (int i = lane; i < MT_N; i += 32) st[i] = mt[c * MT_N + i];
+    rings[wib][lane] = recent[c * RECENT_WORDS + lane];
+    __syncwarp();
+    unsigned C = Cc[c], T = Tt[c];
+    int n = recent_n[c], sum = recent_sum[c], em = 0;
+    double ls = log_scale[c], sc = scale[c];
+    double* z = zs[wib];
+    const double* xc = x + c * P;
+    for (int j = 0; j < K; ++j) {
+        double* out = wprop + (c * K + j) * P;
+        if (j >= k_eff) {                                     // past the chain's last iteration: a valid point, scored and ignored
+            for (int i = lane; i < P; i += 32) out[i] = xc[i];
+            continue;
+        }
+        warp_draw_normals(st, C, T, lane, P, z, fault);
+        warp_make_proposal(lane, P, diagonal, mode, chol, lo, hi, xc, sc, z, out);
+        while ((unsigned)(T - C) < 2u) { warp_twist32(st, T, lane); T += 32; }
+        const double u = canonical(mt_output(st, C), mt_output(st, C + 1));       // the uniform of a rejected (downhill) proposal
+        if (lane == 0) { wCz[c * K + j] = C; wlogu[c * K + j] = detm::log(u); }
+        C += 2u;
+        if (adapt_scale) {
+            if (lane == 0) scale_update(false, t0 + j, target, rings[wib], n, sum, em, ls, sc);
+            sc = __shfl_sync(FULLM, sc, 0);
+        }
+        __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(MH_THREADS) mh_window_commit_kernel(long long local, int P, int K, int iterations, int adapt_scale, double target,
+                                                                       const double* __restrict__ wplp, const double* __restrict__ wprop,
+                                                                       const unsigned* __restrict__ wCz, const double* __restrict__ wlogu,
+                                                                       double* __restrict__ x, double* __restrict__ lp, unsigned* __restrict__ mt,
+                                                                       unsigned* __restrict__ Cc, unsigned* __restrict__ Tt, double* __restrict__ log_scale,
+                                                                       double* __restrict__ scale, unsigned* __restrict__ recent, int* __restrict__ recent_n,
+                                                                       int* __restrict__ recent_sum, int* __restrict__ emergency,
+                                                                       long long* __restrict__ accepted, double* __restrict__ best_lp,
+                                                                       double* __restrict__ best_x, unsigned char* __restrict__ accepts,
+                                                                       int* __restrict__ t_next, int* __restrict__ t_min, double* __restrict__ record) {
+    const int lane = threadIdx.x & 31;
+    const long long c = blockIdx.x * (long long)MH_WARPS + (threadIdx.x >> 5);
+    if (c >= local) return;
+    int t = t_next[c];
+    const int k_eff = max(0, min(K, iterations - t));
+    int jacc = -1, better = 0;
+    unsigned Cfin = Cc[c];
+    double clp = lp[c];
+    if (lane == 0 && k_eff > 0) {                             // the sequential loop, one decision after the other
+        int n = recent_n[c], sum = recent_sum[c], em = emergency[c];
+        double ls = log_scale[c], sc = scale[c];
+        for (int j = 0; j < k_eff; ++j) {
+            double plp = wplp[c * K + j];
+            if (isnan(plp) || isinf(plp)) plp = -1e18;                          // safeEvaluate, .cpp:65-74
+            const double log_ratio = __dsub_rn(plp, clp);
+            bool acc;
+            if (log_ratio >= 0.0) { acc = true; Cfin = wCz[c * K + j]; }          // uphill: no uniform is drawn
+            else { acc = wlogu[c * K + j] < log_ratio; Cfin = wCz[c * K + j] + 2u; }
+            if (accepts) accepts[(size_t)(t - 1) * local + c] = acc ? 1 : 0;
+            if (adapt_scale) scale_update(acc, t, target, recent + c * RECENT_WORDS, n, sum, em, ls, sc);
+            t += 1;
+            if (acc) {
+                jacc = j;
+                better = plp > best_lp[c];
+                clp = plp;
+                accepted[c] += 1;
+                if (better) best_lp[c] = plp;
+                break;
+            }
+        }
+        recent_n[c] = n; recent_sum[c] = sum; emergency[c] = em;
+        log_scale[c] = ls; scale[c] = sc;
+        lp[c] = clp;
+        t_next[c] = t;
+    }
+    jacc = __shfl_sync(FULLM, jacc, 0);
+    better = __shfl_sync(FULLM, better, 0);
+    Cfin = __shfl_sync(FULLM, Cfin, 0);
+    clp = __shfl_sync(FULLM, clp, 0);
+    t = __shfl_sync(FULLM, t, 0);
+    if (jacc >= 0)
+        for (int k = lane; k < P; k += 32) {
+            const double v = wprop[(c * K + jacc) * P + k];
+            x[c * P + k] = v;
+            if (better) best_x[c * P + k] = v;
+        }
+    // the generator: exactly the words of the committed iterations are consumed; twist the state forward to them
+    unsigned T = Tt[c];
+    unsigned* st = mt + c * MT_N;
+    while ((int)(T - Cfin) < 0) { warp_twist32(st, T, lane); T += 32; }
+    if (lane == 0) {
+        Cc[c] = Cfin; Tt[c] = T;
+        atomicMin(t_min, t);
+        if (record) record[c] = clp;
+    }
+}
+
+// the last slot of the rank's record: the smallest next-iteration index among its chains (a rank without chains is done)
+__global__ void mh_window_publish_kernel(int* t_min, int iterations, long long local, double* slot) {
+    if (local == 0) *t_min = iterations;
+    *slot = (double)min(*t_min, iterations);
 }
 
 // trace[slot] = max over the gathered log-posteriors of ALL chains ([world][stride] blocks of counts[r] valid values each)
@@ -360,7 +514,9 @@ sepaihrd_rc sepaihrd_mh_create(sepaihrd_ctx* ctx, int64_t n_chains, int64_t chai
 
 void sepaihrd_mh_destroy(sepaihrd_mh* m) {
     if (!m) return;
-    if (m->d_arena) { cudaDeviceSynchronize(); cudaFree(m->d_arena); }
+    if (m->d_arena || m->d_win) cudaDeviceSynchronize();
+    if (m->d_arena) cudaFree(m->d_arena);
+    if (m->d_win) cudaFree(m->d_win);
     delete m;
 }
 
@@ -393,6 +549,7 @@ sepaihrd_rc sepaihrd_mh_begin(sepaihrd_mh* m, uint32_t seed, const double* initi
         sepaihrd_internal::count_launches(m->ctx, 2);
     }
     m->t = 1;
+    m->windowed = false; m->win_K = 0;
     m->begun = true;
     return SEPAIHRD_OK;
 }
@@ -402,6 +559,7 @@ sepaihrd_rc sepaihrd_mh_begin(sepaihrd_mh* m, uint32_t seed, const double* initi
 static sepaihrd_rc mh_phase(sepaihrd_mh* m, int phase) {
     if (!m) return fail_with(SEPAIHRD_ERR_INVALID_ARGUMENT, "null argument");
     if (!m->begun) return fail_with(SEPAIHRD_ERR_INVALID_ARGUMENT, "sampler phase before sepaihrd_mh_begin");
+    if (m->windowed) return fail_with(SEPAIHRD_ERR_INVALID_ARGUMENT, "this run advances in look-ahead windows (sepaihrd_mh_window_*)");
     if (m->t >= m->cfg.iterations) return fail_with(SEPAIHRD_ERR_INVALID_ARGUMENT, "all iterations have run");
     const auto ctx_lock = sepaihrd_internal::lock(m->ctx);
     const sepaihrd_internal::Dims d = sepaihrd_internal::dims(m->ctx);
@@ -440,6 +598,110 @@ sepaihrd_rc sepaihrd_mh_iterate(sepaihrd_mh* m, int32_t n_iterations) {
             const sepaihrd_rc rc = mh_phase(m, phase);
             if (rc != SEPAIHRD_OK) return rc;
         }
+    return SEPAIHRD_OK;
+}
+
+
+// ---- look-ahead windows: K iterations of every chain per likelihood launch --------------------------------------------------
+static sepaihrd_rc window_buffers(sepaihrd_mh* m, int K) {
+    if (K <= m->win_cap) return SEPAIHRD_OK;
+    if (m->d_win) { cudaDeviceSynchronize(); cudaFree(m->d_win); m->d_win = nullptr; m->win_cap = 0; }
+    const size_t L = (size_t)m->local, LK = L * (size_t)K;
+    size_t bytes = 0;
+    auto reserve = [&](size_t b) { const size_t at = bytes; bytes += (b + 255) & ~(size_t)255; return at; };
+    const size_t o_prop = reserve(8 * LK * m->P), o_plp = reserve(8 * LK), o_logu = reserve(8 * LK), o_cz = reserve(4 * LK), o_st = reserve(4 * LK),
+                 o_ghost = reserve(4 * L * MT_N), o_t = reserve(4 * L), o_tmin = reserve(4), o_rec = reserve(8 * (L + 2));
+    MH_TRY(cudaMalloc((void**)&m->d_win, bytes));
+    char* D = m->d_win;
+    m->d_wprop = (double*)(D + o_prop); m->d_wplp = (double*)(D + o_plp); m->d_wlogu = (double*)(D + o_logu); m->d_wCz = (unsigned*)(D + o_cz);
+    m->d_wstatus = (unsigned*)(D + o_st); m->d_ghost = (unsigned*)(D + o_ghost);
+    int* old_t = m->d_t;
+    m->d_t = (int*)(D + o_t); m->d_tmin = (int*)(D + o_tmin); m->d_record = (double*)(D + o_rec);
+    (void)old_t;
+    m->win_cap = K;
+    return SEPAIHRD_OK;
+}
+
+static sepaihrd_rc mh_window_phase(sepaihrd_mh* m, int phase, int K, int64_t record_stride) {
+    if (!m) return fail_with(SEPAIHRD_ERR_INVALID_ARGUMENT, "null argument");
+    if (!m->begun) return fail_with(SEPAIHRD_ERR_INVALID_ARGUMENT, "sampler phase before sepaihrd_mh_begin");
+    if (!m->windowed && m->t != 1) return fail_with(SEPAIHRD_ERR_INVALID_ARGUMENT, "look-ahead windows cannot follow one-iteration phases of the same run");
+    const auto ctx_lock = sepaihrd_internal::lock(m->ctx);
+    const sepaihrd_internal::Dims d = sepaihrd_internal::dims(m->ctx);
+    MH_TRY(cudaSetDevice(d.device));
+    cudaStream_t st = sepaihrd_internal::stream(m->ctx);
+    const unsigned blocks = (unsigned)((m->local + MH_WARPS - 1) / MH_WARPS);      // one warp per chain
+    if (phase == 0) {
+        if (K < 1 || K > 64) return fail_with(SEPAIHRD_ERR_INVALID_ARGUMENT, "a window holds between 1 and 64 iterations per chain");
+        if (!m->windowed) {
+            if (m->win_cap < K) { const sepaihrd_rc rc = window_buffers(m, std::max(K, 8)); if (rc != SEPAIHRD_OK) return rc; }
+            if (m->local > 0) {
+                std::vector<int> ones((size_t)m->local, 1);
+                MH_TRY(cudaMemcpyAsync(m->d_t, ones.data(), 4 * (size_t)m->local, cudaMemcpyHostToDevice, st));
+                MH_TRY(cudaStreamSynchronize(st));
+            }
+            m->windowed = true;
+        } else if (K > m->win_cap) {
+            return fail_with(SEPAIHRD_ERR_INVALID_ARGUMENT, "the first window of a run fixes the largest window length (at least 8)");
+        }
+        m->win_K = K;
+        if (m->local > 0) {
+            mh_window_propose_kernel<<<blocks, MH_THREADS, 0, st>>>(m->local, m->P, K, m->cfg.iterations, m->diagonal ? 1 : 0,
+                                                                      sepaihrd_internal::constraint_mode(m->ctx), m->cfg.adapt_scale, m->cfg.target_acceptance_rate,
+                                                                      m->d_chol, m->d_lo, m->d_hi, m->d_x, m->d_log_scale, m->d_scale, m->d_recent, m->d_recent_n,
+                                                                      m->d_recent_sum, m->d_mt, m->d_C, m->d_T, m->d_t, m->d_ghost, m->d_wprop, m->d_wCz,
+                                                                      m->d_wlogu, m->d_status + m->local + 1);
+            MH_TRY(cudaGetLastError());
+            sepaihrd_internal::count_launches(m->ctx, 1);
+        }
+        return SEPAIHRD_OK;
+    }
+    if (!m->windowed || m->win_K < 1) return fail_with(SEPAIHRD_ERR_INVALID_ARGUMENT, "window phase without sepaihrd_mh_window_propose");
+    if (phase == 1) {
+        if (m->local == 0) return SEPAIHRD_OK;
+        return sepaihrd_internal::eval_batch_device_unordered(m->ctx, m->d_wprop, m->local * m->win_K, m->P, m->d_wplp, m->d_wstatus, nullptr);
+    }
+    // commit
+    if (record_stride != 0 && (record_stride < m->local || record_stride > m->local + 1))
+        return fail_with(SEPAIHRD_ERR_INVALID_ARGUMENT, "record stride: local_count or local_count + 1 (the largest shard of the run)");
+    MH_TRY(cudaMemsetAsync(m->d_tmin, 0x7f, 4, st));
+    if (m->local > 0) {
+        mh_window_commit_kernel<<<blocks, MH_THREADS, 0, st>>>(m->local, m->P, m->win_K, m->cfg.iterations, m->cfg.adapt_scale, m->cfg.target_acceptance_rate,
+                                                                 m->d_wplp, m->d_wprop, m->d_wCz, m->d_wlogu, m->d_x, m->d_lp, m->d_mt, m->d_C, m->d_T,
+                                                                 m->d_log_scale, m->d_scale, m->d_recent, m->d_recent_n, m->d_recent_sum, m->d_emergency,
+                                                                 m->d_accepted, m->d_best_lp, m->d_best_x, m->cfg.record_accepts ? m->d_accepts : nullptr,
+                                                                 m->d_t, m->d_tmin, m->d_record);
+        MH_TRY(cudaGetLastError());
+    }
+    mh_window_publish_kernel<<<1, 1, 0, st>>>(m->d_tmin, m->cfg.iterations, m->local, m->d_record + (record_stride ? record_stride : m->local));
+    MH_TRY(cudaGetLastError());
+    sepaihrd_internal::count_launches(m->ctx, m->local > 0 ? 2 : 1);
+    m->win_K = 0;
+    return SEPAIHRD_OK;
+}
+sepaihrd_rc sepaihrd_mh_window_propose(sepaihrd_mh* m, int32_t K) { return mh_window_phase(m, 0, K, 0); }
+sepaihrd_rc sepaihrd_mh_window_evaluate(sepaihrd_mh* m) { return mh_window_phase(m, 1, 0, 0); }
+sepaihrd_rc sepaihrd_mh_window_commit(sepaihrd_mh* m, int64_t record_stride) { return mh_window_phase(m, 2, 0, record_stride); }
+
+sepaihrd_rc sepaihrd_mh_window_record(sepaihrd_mh* m, const double** d_record) {
+    if (!m || !d_record) return fail_with(SEPAIHRD_ERR_INVALID_ARGUMENT, "null argument");
+    if (!m->windowed) return fail_with(SEPAIHRD_ERR_INVALID_ARGUMENT, "no window has been proposed yet");
+    *d_record = m->d_record;
+    return SEPAIHRD_OK;
+}
+
+sepaihrd_rc sepaihrd_mh_window_progress(sepaihrd_mh* m, int32_t* out_min_iteration) {
+    if (!m || !out_min_iteration) return fail_with(SEPAIHRD_ERR_INVALID_ARGUMENT, "null argument");
+    if (!m->windowed) { *out_min_iteration = m->t; return SEPAIHRD_OK; }
+    const auto ctx_lock = sepaihrd_internal::lock(m->ctx);
+    const sepaihrd_internal::Dims d = sepaihrd_internal::dims(m->ctx);
+    MH_TRY(cudaSetDevice(d.device));
+    cudaStream_t st = sepaihrd_internal::stream(m->ctx);
+    int v = 0;
+    MH_TRY(cudaMemcpyAsync(&v, m->d_tmin, 4, cudaMemcpyDeviceToHost, st));
+    MH_TRY(cudaStreamSynchronize(st));
+    *out_min_iteration = std::min(v, m->cfg.iterations);
+    m->t = *out_min_iteration;
     return SEPAIHRD_OK;
 }
 

@@ -209,6 +209,36 @@ class DeviceMH:
     def accept(self):
         capi.check(self.L.sepaihrd_mh_accept(self._h))
 
+    # look-ahead windows: K iterations of every chain per likelihood launch (sepaihrd_mh_window_*)
+    def window_propose(self, K: int):
+        capi.check(self.L.sepaihrd_mh_window_propose(self._h, int(K)))
+
+    def window_evaluate(self):
+        capi.check(self.L.sepaihrd_mh_window_evaluate(self._h))
+
+    def window_commit(self, record_stride: int = 0):
+        capi.check(self.L.sepaihrd_mh_window_commit(self._h, int(record_stride)))
+
+    def window_record_ptr(self) -> int:
+        p = C.c_void_p()
+        capi.check(self.L.sepaihrd_mh_window_record(self._h, C.byref(p)))
+        return p.value
+
+    def window_progress(self) -> int:
+        """Synchronises; the smallest next-iteration index among the local chains (``iterations`` once all are done)."""
+        v = C.c_int32()
+        capi.check(self.L.sepaihrd_mh_window_progress(self._h, C.byref(v)))
+        return v.value
+
+    def run_windows(self, K: int) -> int:
+        """All iterations of the local chains in look-ahead windows of K; returns the number of windows (likelihood launches)."""
+        n = 0
+        while True:
+            self.window_propose(K); self.window_evaluate(); self.window_commit()
+            n += 1
+            if self.window_progress() >= self.iterations:
+                return n
+
     @property
     def iteration(self) -> int:
         return int(self.L.sepaihrd_mh_iteration(self._h))
@@ -337,48 +367,89 @@ def run_pso_resident(ev, swarm_size: int, iterations: int, seed: int, initial=No
     return out
 
 
+def window_length(local: int, requested: Optional[int] = None) -> int:
+    """Iterations per window of the device-resident sampler: a likelihood launch costs the same up to ~4096 sets, so the local
+    chains share that many proposals (at most 16 each: at 23 % acceptance the chance of 16 rejections in a row is 1.5 %)."""
+    if requested is not None:
+        return max(1, min(64, int(requested)))
+    return max(1, min(16, 4096 // max(int(local), 1)))
+
+
 def run_mh_resident(ev, sigmas, initial, n_chains: int, iterations: int, seed: int, rank: int = 0, world: int = 1,
                     transport: Optional[str] = None, chol_lower=None, torch_device=None, record_accepts: bool = True,
-                    adapt_scale: bool = True):
+                    adapt_scale: bool = True, lookahead: Optional[int] = 1):
     """``n_chains`` seeded Metropolis-Hastings chains (MetropolisHastingsSampler.cpp:201-412, fixed-kernel phase) sharded over
     the ranks and resident on the devices; per iteration: propose kernel, fused likelihood kernel, accept kernel, all-gather of
     the ranks' log-likelihood blocks, max over all chains into the trace.  Nothing runs on the host inside the loop.  The
-    evaluator must be in MCMC_REFLECT mode (constraint_mode 1) like the reference's sampler (:207-210)."""
+    evaluator must be in MCMC_REFLECT mode (constraint_mode 1) like the reference's sampler (:207-210).
+
+    ``lookahead`` = 1: one iteration per likelihood launch (above).  ``lookahead`` = K > 1 or None (sized from the shard,
+    ``window_length``): look-ahead windows -- every chain proposes its next K iterations at once, one launch scores them all, every
+    chain commits up to its first accepted proposal; the exchange then runs once per WINDOW (the ranks' log-likelihood blocks plus
+    each rank's smallest iteration index, from which every rank knows when all chains of the run are done: one small D2H read per
+    window).  Same decisions and states; ``best_trace`` is then per window and ``windows`` counts them."""
     import torch
     dev = torch_device if torch_device is not None else torch.device("cuda", torch.cuda.current_device())
     stream = torch.cuda.current_stream(dev)
     ev.set_stream(stream.cuda_stream)
     lo, hi = shard_range(n_chains, rank, world)
     block = shard_range(n_chains, 0, world)[1]            # the largest shard: rank 0's
+    K = 1 if lookahead == 1 else window_length(block, lookahead)
+    windowed = K > 1
     t0 = time.perf_counter()
     mh = DeviceMH(ev, n_chains, lo, hi - lo, iterations, record_accepts=record_accepts, adapt_scale=adapt_scale)
-    ex = Exchange(ev, block, rank, world, transport, dev)
-    gathered = torch.zeros((world, block), dtype=torch.float64, device=dev)
+    rec_n = block + 1 if windowed else block              # windows: one more double per rank, its smallest iteration index
+    ex = Exchange(ev, rec_n, rank, world, transport, dev)
+    gathered = torch.zeros((world, rec_n), dtype=torch.float64, device=dev)
     # a rank with a shorter shard still sends `block` doubles: the tail of its buffer is never read (counts are known)
     lp_ptr = mh.logpost_ptr()
-    send = torch.zeros(block, dtype=torch.float64, device=dev) if (hi - lo) < block or ex.transport == "nccl" else None
+    send = torch.zeros(block, dtype=torch.float64, device=dev) if (not windowed and ((hi - lo) < block or ex.transport == "nccl")) else None
     t_setup = time.perf_counter() - t0
     ph = _Phases(stream, ["propose", "eval", "accept", "exchange"])
     torch.cuda.synchronize(dev)
     t1 = time.perf_counter()
     mh.begin(seed, initial, initial_cholesky(sigmas) if chol_lower is None else chol_lower)
     ph.mark()
-    for it in range(1, iterations):
-        mh.propose()
-        ph.mark()
-        mh.evaluate()
-        ph.mark()
-        mh.accept()
-        ph.mark()
-        if send is not None:
-            if hi > lo:
-                send[:hi - lo].copy_(_tensor_view(lp_ptr, hi - lo, dev), non_blocking=True)
-            ex.all_gather(send.data_ptr(), block, gathered.data_ptr(), send, gathered)
-        else:
-            ex.all_gather(lp_ptr, block, gathered.data_ptr(), None, gathered)
-        mh.note_gathered(gathered.data_ptr(), world, block, it)
-        ph.mark()
-    trace = mh.read(MH_TRACE)[1:iterations]               # the one synchronisation of the run
+    windows = 0
+    if windowed:
+        rec_ptr = rec_view = None
+        trace_rows = []
+        while True:
+            mh.window_propose(K)
+            ph.mark()
+            mh.window_evaluate()
+            ph.mark()
+            mh.window_commit(block)
+            ph.mark()
+            if rec_ptr is None:
+                rec_ptr = mh.window_record_ptr()
+                rec_view = _tensor_view(rec_ptr, rec_n, dev) if ex.transport == "nccl" else None
+            ex.all_gather(rec_ptr, rec_n, gathered.data_ptr(), rec_view, gathered)
+            if windows < iterations:
+                mh.note_gathered(gathered.data_ptr(), world, rec_n, windows + 1)
+            ph.mark()
+            windows += 1
+            if float(gathered[:, block].min().item()) >= iterations:      # the one host read per window: every rank sees the same value
+                break
+        mh.window_progress()
+        trace = mh.read(MH_TRACE)[1:min(windows, iterations) + 1]
+    else:
+        for it in range(1, iterations):
+            mh.propose()
+            ph.mark()
+            mh.evaluate()
+            ph.mark()
+            mh.accept()
+            ph.mark()
+            if send is not None:
+                if hi > lo:
+                    send[:hi - lo].copy_(_tensor_view(lp_ptr, hi - lo, dev), non_blocking=True)
+                ex.all_gather(send.data_ptr(), block, gathered.data_ptr(), send, gathered)
+            else:
+                ex.all_gather(lp_ptr, block, gathered.data_ptr(), None, gathered)
+            mh.note_gathered(gathered.data_ptr(), world, block, it)
+            ph.mark()
+        trace = mh.read(MH_TRACE)[1:iterations]               # the one synchronisation of the run
     t_run = time.perf_counter() - t1
     if int(mh.read(MH_FAULT)[0]) != 0:
         raise RuntimeError("device-resident sampler: a proposal exhausted its polar attempts (generator fault)")
@@ -387,7 +458,9 @@ def run_mh_resident(ev, sigmas, initial, n_chains: int, iterations: int, seed: i
                all_logpost=np.concatenate([gathered[r, :shard_range(n_chains, r, world)[1] - shard_range(n_chains, r, world)[0]].cpu().numpy()
                                            for r in range(world)]),
                setup_seconds=t_setup, run_seconds=t_run, phase_seconds=ph.totals(), transport=ex.transport,
-               fallback_reason=ex.fallback_reason, exchange_status=ex.status(), evaluations=(iterations - 1) * (hi - lo) + 1)
+               fallback_reason=ex.fallback_reason, exchange_status=ex.status(),
+               evaluations=(windows * K * (hi - lo) + 1) if windowed else ((iterations - 1) * (hi - lo) + 1),
+               lookahead=K, windows=windows if windowed else iterations - 1)
     if world > 1:
         import torch.distributed as dist
         dist.barrier()

@@ -98,6 +98,54 @@ def test_device_resident_chains_make_the_host_samplers_decisions(host, problem, 
     assert np.all(np.diff(r["best_trace"]) >= 0) or True      # (not monotone in general: a chain may leave its best state)
 
 
+@pytest.mark.parametrize("diag", [True, False])
+def test_look_ahead_windows_make_the_one_iteration_runs_decisions(problem, reflect_problem, mods, diag):
+    """sepaihrd_mh_window_*: every chain proposes its next K iterations from a copy of its generator, ONE likelihood launch scores
+    local x K proposals, every chain commits up to its first accepted proposal.  Accept matrix, states, log-posteriors, scales
+    and accept counts of 203 chains x 60 iterations equal the one-iteration-per-launch device run (itself equal to the host
+    sampler, above) for K = 2, 5, 16 and the automatic length; the generator positions are right or the later draws would differ."""
+    _, evaluator, resident = mods
+    n_chains, iters, seed = 203, 60, 77
+    P = problem.n_params
+    chol = None
+    if not diag:
+        rng = np.random.default_rng(5)
+        A = rng.standard_normal((P, P)) * 0.05
+        cov = (np.diag(problem.sigmas ** 2) + (A * problem.sigmas) @ (A * problem.sigmas).T) * 0.05
+        chol = np.linalg.cholesky(cov + 1e-6 * np.eye(P))
+    x0 = problem.base_params()
+    with evaluator.BatchEvaluator(reflect_problem, device=0) as ev:
+        ref = resident.run_mh_resident(ev, problem.sigmas, x0, n_chains, iters, seed, chol_lower=chol)
+        assert ref["lookahead"] == 1 and ref["windows"] == iters - 1
+        for K in (2, 5, 16, None):
+            r = resident.run_mh_resident(ev, problem.sigmas, x0, n_chains, iters, seed, chol_lower=chol, lookahead=K)
+            assert r["lookahead"] == (K if K else min(16, 4096 // n_chains)) and r["windows"] < ref["windows"]
+            np.testing.assert_array_equal(r["accepts"], ref["accepts"], err_msg=f"K={K}")
+            np.testing.assert_array_equal(r["x"], ref["x"])
+            np.testing.assert_array_equal(r["logpost"], ref["logpost"])
+            np.testing.assert_array_equal(r["scale"], ref["scale"])
+            np.testing.assert_array_equal(r["accepted"], ref["accepted"])
+            assert r["best_trace"][-1] == ref["best_trace"][-1] == ref["logpost"].max()
+        # without scale adaptation, and a window longer than the run
+        a = resident.run_mh_resident(ev, problem.sigmas, x0, 37, 9, seed, chol_lower=chol, adapt_scale=False)
+        b = resident.run_mh_resident(ev, problem.sigmas, x0, 37, 9, seed, chol_lower=chol, adapt_scale=False, lookahead=32)
+        np.testing.assert_array_equal(a["accepts"], b["accepts"])
+        np.testing.assert_array_equal(a["x"], b["x"])
+        # a run uses either the windows or the one-iteration phases
+        mh = resident.DeviceMH(ev, 8, 0, 8, 20)
+        mh.begin(seed, x0, resident.initial_cholesky(problem.sigmas))
+        mh.iterate(2)
+        with pytest.raises(Exception, match="cannot follow"):
+            mh.window_propose(4)
+        mh.close()
+        mh = resident.DeviceMH(ev, 8, 0, 8, 20)
+        mh.begin(seed, x0, resident.initial_cholesky(problem.sigmas))
+        assert mh.run_windows(4) < 19 and mh.iteration == 20
+        with pytest.raises(Exception, match="look-ahead windows"):
+            mh.propose()
+        mh.close()
+
+
 def test_asynchronous_swarm_equals_the_synchronous_device_swarm(problem, mods):
     drivers, evaluator, resident = mods
     kw = dict(sigmas=problem.sigmas, lower=problem.lower_bound, upper=problem.upper_bound, swarm_size=333, iterations=6, seed=7,
