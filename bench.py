@@ -270,6 +270,26 @@ def run_caller_configs(pkg, prob, rank, world, local_rank, dist):
                                  "best_logpost": float(first["best_trace"][-1])}
             if world > 1:
                 dist.barrier()
+            # the same run in LOOK-AHEAD WINDOWS (sepaihrd_mh_window_*): every chain proposes its next K iterations at once, one
+            # likelihood launch scores them, every chain commits up to its first accept; K from the shard size (4096 proposals per launch)
+            try:
+                tr0 = transports[0]
+                resident.run_mh_resident(ev, prob.sigmas, base, MH_CHAINS, 4, 1234, rank, world, transport=tr0, lookahead=None)
+                la = resident.run_mh_resident(ev, prob.sigmas, base, MH_CHAINS, MH_ITERATIONS, 1234, rank, world, transport=tr0, lookahead=None)
+                la_rec = summarise(la, MH_ITERATIONS - 1, MH_CHAINS * (MH_ITERATIONS - 1))
+                la_rec.update({"window_length": la["lookahead"], "windows": la["windows"], "ms_per_window": la_rec["wall_s"] / max(la["windows"], 1) * 1e3,
+                               "proposals_scored_per_rank": la["evaluations"],
+                               "speedup_over_one_iteration_per_launch": rec["wall_s"] / la_rec["wall_s"] if la_rec["wall_s"] > 0 else None})
+                la_parts = _gather_bytes(dist, world, rank, dev, la["accepts"])
+                la_xs = _gather_bytes(dist, world, rank, dev, la["x"])
+                if rank == 0:
+                    la_rec["parity"] = {"accept_matrix_equals_one_iteration_run": bool(np.array_equal(np.concatenate(la_parts, axis=1), acc)),
+                                        "states_equal_one_iteration_run": bool(np.array_equal(np.concatenate(la_xs), np.concatenate(xs)))}
+                rec["lookahead"] = la_rec
+            except Exception as exc:
+                rec["lookahead"] = {"error": f"{type(exc).__name__}: {exc}"}
+            if world > 1:
+                dist.barrier()
             # the round-1 path beside it: host sampler (C++) + numpy -> H2D -> all_gather on a list of tensors -> .cpu() per rank
             comm = Comm()
             comm.barrier(); t0 = time.perf_counter()

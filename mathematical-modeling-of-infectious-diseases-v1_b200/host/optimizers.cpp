@@ -3,6 +3,7 @@
 #include "../csrc/det_math.h"      // log / exp with the same bits on the host and on the device (see there)
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -353,16 +354,24 @@ OptimizationResult MetropolisHastingsSampler::result(int upto) const {
 }
 
 // How many iterations ahead to evaluate.  Proposal k of a window is reached with probability (1 - rate)^(k-1) and then commits
-// exactly one iteration; it costs the host ~6 us of arithmetic (normals, L z, reflection) against ~600 us for the launch that
-// commits ~4 iterations, so it pays while (1 - rate)^(k-1) > ~0.03: K = log(0.025) / log(1 - rate), from the acceptance rate
-// over the last <= 1000 iterations (the window the scale adaptation keeps anyway).  Measured on the device objective at 21 %
-// acceptance: K = 8 5.7 k, 16 6.2 k, 32 5.9 k, 128 5.0 k iterations/s.
-int MetropolisHastingsSampler::windowLength(const Chain& c) const {
-    if (lookahead_ > 1) return lookahead_;
-    if (c.recent.size() < 50) return 16;
-    const double rate = std::max(static_cast<double>(c.recent_sum) / static_cast<double>(c.recent.size()), 0.02);
-    const int k = static_cast<int>(std::ceil(std::log(0.025) / std::log1p(-std::min(rate, 0.9))));
-    return std::min(std::max(k, 4), 128);
+// exactly one iteration, so K proposals commit g(K) = (1 - (1 - rate)^K) / rate iterations on average; they cost the host
+// n_chains * K * c of arithmetic (normals, L z, reflection; c measured per window, ~6 us on one thread, less when the chains are
+// shared among the threads) on top of the launch time L (measured, ~0.6 ms whatever the launch holds up to ~4 000 sets).
+// K = argmax g(K) / (L + n K c), with the acceptance rate of the last <= 1000 iterations (the window the scale adaptation keeps
+// anyway).  Measured on the device objective at 21 % acceptance, one chain: K = 8 5.7 k, 16 6.2 k, 32 5.9 k, 128 5.0 k iterations/s.
+int MetropolisHastingsSampler::windowLength(const Chain& c, int running, int share) const {
+    if (lookahead_ > 1) return std::min(lookahead_, share);
+    const double rate = c.recent.size() < 50 ? 0.234
+                                             : std::min(std::max(static_cast<double>(c.recent_sum) / static_cast<double>(c.recent.size()), 0.02), 0.9);
+    const double launch = launch_seconds_ > 0 ? launch_seconds_ : 6e-4, per = proposal_seconds_ > 0 ? proposal_seconds_ : 6e-6;
+    int best = 1;
+    double best_rate = 0.0, miss = 1.0;
+    for (int k = 1; k <= std::min(share, 128); ++k) {
+        miss *= 1.0 - rate;
+        const double r = (1.0 - miss) / rate / (launch + static_cast<double>(running) * k * per);
+        if (r > best_rate) { best_rate = r; best = k; }
+    }
+    return best;
 }
 
 // K iterations of every chain per device launch (see optimizers.hpp).  A chain object only ever changes through the calls the
@@ -383,7 +392,7 @@ void MetropolisHastingsSampler::runLookahead(IObjectiveFunction& f, IParameterMa
         first[0] = 0;
         for (int ci = 0; ci < n; ++ci) {
             const Chain& c = chains_[static_cast<size_t>(ci)];
-            int k = std::min(std::min(windowLength(c), share), iterations_ - c.t);
+            int k = std::min(windowLength(c, running, share), iterations_ - c.t);
             // the proposal kernel L must not change inside the window: an iteration that refactors it (.cpp:292-302) may open
             // a window (its adaptation runs before anything is drawn), it may not sit inside one
             for (int j = 1; j < k; ++j)
@@ -393,6 +402,7 @@ void MetropolisHastingsSampler::runLookahead(IObjectiveFunction& f, IParameterMa
         }
         const int64_t total = first[static_cast<size_t>(n)];
         props.resize(static_cast<size_t>(total) * static_cast<size_t>(P));
+        const auto clock0 = std::chrono::steady_clock::now();
 #pragma omp parallel for schedule(static) if (n >= 8)
         for (int ci = 0; ci < n; ++ci) {
             Chain& c = chains_[static_cast<size_t>(ci)];
@@ -409,7 +419,9 @@ void MetropolisHastingsSampler::runLookahead(IObjectiveFunction& f, IParameterMa
                 if (adapt_scale_) adaptGlobalScale(sc, false, c.t + j);
             }
         }
+        const auto clock1 = std::chrono::steady_clock::now();
         const std::vector<double> plp = evaluate_rows(f, props, total, P);
+        const auto clock2 = std::chrono::steady_clock::now();
         speculated_ += total;
         long committed = 0;
 #pragma omp parallel for schedule(static) reduction(+ : committed) if (n >= 8)
@@ -426,6 +438,12 @@ void MetropolisHastingsSampler::runLookahead(IObjectiveFunction& f, IParameterMa
             }
         }
         committed_ += committed;
+        {   // what a proposal costs the host (drawing + its share of the commit) and what a launch costs: running means for windowLength
+            const double host_s = std::chrono::duration<double>(clock1 - clock0).count() + std::chrono::duration<double>(std::chrono::steady_clock::now() - clock2).count();
+            const double per = host_s / static_cast<double>(std::max<int64_t>(total, 1)), launch = std::chrono::duration<double>(clock2 - clock1).count();
+            proposal_seconds_ = proposal_seconds_ > 0 ? 0.8 * proposal_seconds_ + 0.2 * per : per;
+            launch_seconds_ = launch_seconds_ > 0 ? 0.8 * launch_seconds_ + 0.2 * launch : launch;
+        }
         // the lockstep loop writes a checkpoint after iteration t when (t + 1) % report_interval == 0 (.cpp:380-382): here once ALL
         // chains have completed such an iteration, with every chain cut at it
         const int t_before = t_;
@@ -449,6 +467,7 @@ OptimizationResult MetropolisHastingsSampler::optimize(const VectorXd& initial, 
     std::vector<double> prop(static_cast<size_t>(n_chains_) * static_cast<size_t>(P));
     const std::string dir = (store_samples_ && (write_checkpoints_ || write_trace_)) ? traceDirectory() : std::string();
     speculated_ = committed_ = 0;
+    launch_seconds_ = proposal_seconds_ = 0.0;
     if (lookahead_ != 1 && 2 * n_chains_ <= LOOKAHEAD_SETS) runLookahead(f, pm, dir);
     while (!done()) {
         const int t = t_;

@@ -102,7 +102,7 @@ private:
     void adaptKernel(Chain& c, int step) const;                          // .cpp:286-303
     bool acceptOne(Chain& c, int ci, double proposed_logpost);           // .cpp:310-367
     void drawProposal(std::mt19937& gen, const Chain& c, double scale, const double* x, IParameterManager& pm, double* out) const;   // .cpp:91-102, 308
-    int windowLength(const Chain& c) const;
+    int windowLength(const Chain& c, int running_chains, int share) const;
     void runLookahead(IObjectiveFunction& f, IParameterManager& pm, const std::string& dir);
     void updateCovarianceRank1(Chain& c, int step) const;               // .cpp:154-168
     void recomputeFullCovariance(Chain& c) const;                       // .cpp:170-199
@@ -119,6 +119,7 @@ private:
     int lookahead_ = 0;
     static constexpr int LOOKAHEAD_SETS = 4096;          // proposals per launch: up to here a launch costs what one set costs
     long speculated_ = 0, committed_ = 0;
+    double launch_seconds_ = 0.0, proposal_seconds_ = 0.0;     // running means: one objective call; host arithmetic per proposal
     long chain_offset_ = 0;
     bool shared_diagonal_ = false;
     bool has_seed_ = false;

@@ -90,7 +90,7 @@ def test_lookahead_cuts_the_number_of_launches(host, problem, tmp_path):
     st = dict(mcmc_iterations=3000, burn_in=3000, n_chains=1, seed=5, write_trace=0, write_checkpoints=0)
     la = _run(host, problem, tmp_path, "la", "gauss", dict(st, lookahead=0))
     launches = len(la["calls"]) - 1
-    assert 2999 / launches > 2.5, (launches, la["nev"])
+    assert 2999 / launches > 1.5, (launches, la["nev"])            # (a device launch costs ~0.6 ms: ~4.5 iterations per launch there)
     assert la["nev"] < 25 * launches
 
 
@@ -109,7 +109,8 @@ def test_multichain_lookahead_equals_the_lockstep_run(host, problem, tmp_path, n
             assert r["files"][name] == lock["files"][name], f"{name} differs ({n_chains} chains, lookahead {la}, {kind})"
         np.testing.assert_array_equal(r["best"], lock["best"])
         assert r["val"] == lock["val"]
-        assert len(r["calls"]) < len(lock["calls"]) / 2                                  # fewer launches
+        # fewer launches (with lookahead 0 the window follows the measured cost of a call: this objective is cheap, the windows short)
+        assert len(r["calls"]) < len(lock["calls"]) / (2 if la else 1)
         assert max(len(c) for c in r["calls"]) <= 4096
 
 
