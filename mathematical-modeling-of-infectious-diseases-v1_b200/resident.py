@@ -367,12 +367,22 @@ def run_pso_resident(ev, swarm_size: int, iterations: int, seed: int, initial=No
     return out
 
 
-def window_length(local: int, requested: Optional[int] = None) -> int:
-    """Iterations per window of the device-resident sampler: a likelihood launch costs the same up to ~4096 sets, so the local
-    chains share that many proposals (at most 16 each: at 23 % acceptance the chance of 16 rejections in a row is 1.5 %)."""
+def window_length(local: int, requested: Optional[int] = None, rate: float = 0.234) -> int:
+    """Iterations per window of the device-resident sampler.  K proposals per chain commit g(K) = (1 - (1 - rate)^K) / rate
+    iterations on average; a likelihood launch costs ~0.55 ms up to 4096 sets and ~0.095 ms per further 1024 (measured,
+    profiles/r02_v17_small_batch_latency.txt), a proposal ~4 us of a warp's time.  K = argmax g(K) / cost(local * K):
+    16 for <= 256 chains per GPU, 8 for 512, 4 for 1024, 3 for 2048, 2 for 4096."""
     if requested is not None:
         return max(1, min(64, int(requested)))
-    return max(1, min(16, 4096 // max(int(local), 1)))
+    best, best_rate, miss = 1, 0.0, 1.0
+    for k in range(1, 17):
+        miss *= 1.0 - rate
+        sets = max(int(local), 1) * k
+        cost = 0.55 + max(0, sets - 4096) * (0.095 / 1024) + 0.004 * k + 0.05
+        r = (1.0 - miss) / rate / cost
+        if r > best_rate * 1.02:               # a longer window has to pay by more than the noise
+            best, best_rate = k, r
+    return best
 
 
 def run_mh_resident(ev, sigmas, initial, n_chains: int, iterations: int, seed: int, rank: int = 0, world: int = 1,

@@ -119,7 +119,7 @@ def test_look_ahead_windows_make_the_one_iteration_runs_decisions(problem, refle
         assert ref["lookahead"] == 1 and ref["windows"] == iters - 1
         for K in (2, 5, 16, None):
             r = resident.run_mh_resident(ev, problem.sigmas, x0, n_chains, iters, seed, chol_lower=chol, lookahead=K)
-            assert r["lookahead"] == (K if K else min(16, 4096 // n_chains)) and r["windows"] < ref["windows"]
+            assert r["lookahead"] == (K if K else resident.window_length(n_chains)) and r["windows"] < ref["windows"]
             np.testing.assert_array_equal(r["accepts"], ref["accepts"], err_msg=f"K={K}")
             np.testing.assert_array_equal(r["x"], ref["x"])
             np.testing.assert_array_equal(r["logpost"], ref["logpost"])
