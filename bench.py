@@ -194,6 +194,7 @@ def run_reference(args, json_out):
     json_out.flush()
 
 
+MH_LONG_ITERATIONS = 300
 MH_CHAINS, MH_ITERATIONS = 4096, 30          # BASELINE configs[2]: 4096 seeded chains (strong scaling: the chains are split over the ranks)
 PSO_PARTICLES, PSO_ITERATIONS = 65536, 30     # BASELINE configs[3]: 65,536 particles, global-best topology (strong scaling)
 
@@ -285,6 +286,16 @@ def run_caller_configs(pkg, prob, rank, world, local_rank, dist):
                 if rank == 0:
                     la_rec["parity"] = {"accept_matrix_equals_one_iteration_run": bool(np.array_equal(np.concatenate(la_parts, axis=1), acc)),
                                         "states_equal_one_iteration_run": bool(np.array_equal(np.concatenate(la_xs), np.concatenate(xs)))}
+                # a window ends for the RUN when its slowest chain is done, so 30 iterations show little of it; 300 iterations beside them
+                lk = resident.run_mh_resident(ev, prob.sigmas, base, MH_CHAINS, MH_LONG_ITERATIONS, 1234, rank, world, transport=tr0)
+                lw = resident.run_mh_resident(ev, prob.sigmas, base, MH_CHAINS, MH_LONG_ITERATIONS, 1234, rank, world, transport=tr0, lookahead=None)
+                w_lock, w_win = _max_over_ranks(dist, world, dev, [lk["run_seconds"], lw["run_seconds"]])
+                same = float(np.array_equal(lk["accepts"], lw["accepts"]) and np.array_equal(lk["x"], lw["x"]))
+                (all_same,) = _max_over_ranks(dist, world, dev, [1.0 - same])
+                la_rec["long_run"] = {"iterations": MH_LONG_ITERATIONS, "one_iteration_per_launch_wall_s": w_lock, "lookahead_wall_s": w_win,
+                                      "windows": lw["windows"], "speedup": w_lock / w_win if w_win > 0 else None,
+                                      "chain_iterations_per_s": MH_CHAINS * (MH_LONG_ITERATIONS - 1) / w_win if w_win > 0 else None,
+                                      "accept_matrix_and_states_equal_on_every_rank": all_same == 0.0}
                 rec["lookahead"] = la_rec
             except Exception as exc:
                 rec["lookahead"] = {"error": f"{type(exc).__name__}: {exc}"}

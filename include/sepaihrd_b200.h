@@ -317,11 +317,13 @@ sepaihrd_rc sepaihrd_mh_note_gathered(sepaihrd_mh* mh, const double* d_all_logpo
  * local_count x K proposals in ONE launch, _commit replays the sequential loop of every chain up to and including its first
  * accepted proposal and discards the rest.  Decisions, states, scales and generator positions are those of the
  * one-iteration-per-launch phases above; chains advance by different amounts, so each keeps its own iteration index, and a run
- * uses EITHER the windows OR the one-iteration phases.  1 <= K <= 64; the first window of a run fixes the largest K (>= 8).
+ * uses EITHER the windows OR the one-iteration phases.  1 <= K <= 64; the first window of a run fixes the largest K, unless
+ * _reserve has allocated the window buffers for a larger one beforehand (it keeps the allocation out of the run).
  * _commit also fills the rank's record for the per-window exchange: [0, local_count) the chains' current log-posteriors,
  * [record_stride] the smallest next-iteration index among the local chains as a double (settings.iterations once all are
  * done); record_stride = local_count or local_count + 1 (the largest shard of the run; 0 = local_count).
  * _progress synchronises and returns that index (also what sepaihrd_mh_iteration reports afterwards). */
+sepaihrd_rc sepaihrd_mh_window_reserve(sepaihrd_mh* mh, int32_t K);
 sepaihrd_rc sepaihrd_mh_window_propose(sepaihrd_mh* mh, int32_t K);
 sepaihrd_rc sepaihrd_mh_window_evaluate(sepaihrd_mh* mh);
 sepaihrd_rc sepaihrd_mh_window_commit(sepaihrd_mh* mh, int64_t record_stride);

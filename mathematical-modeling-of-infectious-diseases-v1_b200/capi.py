@@ -59,6 +59,7 @@ SIGNATURES = {
     "sepaihrd_mh_logpost_device": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "sepaihrd_mh_note_gathered": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int32]),
     "sepaihrd_mh_read": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
+    "sepaihrd_mh_window_reserve": (C.c_int, [C.c_void_p, C.c_int32]),
     "sepaihrd_mh_window_propose": (C.c_int, [C.c_void_p, C.c_int32]),
     "sepaihrd_mh_window_evaluate": (C.c_int, [C.c_void_p]),
     "sepaihrd_mh_window_commit": (C.c_int, [C.c_void_p, C.c_int64]),

@@ -634,7 +634,7 @@ static sepaihrd_rc mh_window_phase(sepaihrd_mh* m, int phase, int K, int64_t rec
     if (phase == 0) {
         if (K < 1 || K > 64) return fail_with(SEPAIHRD_ERR_INVALID_ARGUMENT, "a window holds between 1 and 64 iterations per chain");
         if (!m->windowed) {
-            if (m->win_cap < K) { const sepaihrd_rc rc = window_buffers(m, std::max(K, 8)); if (rc != SEPAIHRD_OK) return rc; }
+            if (m->win_cap < K) { const sepaihrd_rc rc = window_buffers(m, K); if (rc != SEPAIHRD_OK) return rc; }
             if (m->local > 0) {
                 std::vector<int> ones((size_t)m->local, 1);
                 MH_TRY(cudaMemcpyAsync(m->d_t, ones.data(), 4 * (size_t)m->local, cudaMemcpyHostToDevice, st));
@@ -642,7 +642,7 @@ static sepaihrd_rc mh_window_phase(sepaihrd_mh* m, int phase, int K, int64_t rec
             }
             m->windowed = true;
         } else if (K > m->win_cap) {
-            return fail_with(SEPAIHRD_ERR_INVALID_ARGUMENT, "the first window of a run fixes the largest window length (at least 8)");
+            return fail_with(SEPAIHRD_ERR_INVALID_ARGUMENT, "the first window of a run (or sepaihrd_mh_window_reserve) fixes the largest window length");
         }
         m->win_K = K;
         if (m->local > 0) {
@@ -678,6 +678,14 @@ static sepaihrd_rc mh_window_phase(sepaihrd_mh* m, int phase, int K, int64_t rec
     sepaihrd_internal::count_launches(m->ctx, m->local > 0 ? 2 : 1);
     m->win_K = 0;
     return SEPAIHRD_OK;
+}
+sepaihrd_rc sepaihrd_mh_window_reserve(sepaihrd_mh* m, int32_t K) {
+    if (!m) return fail_with(SEPAIHRD_ERR_INVALID_ARGUMENT, "null argument");
+    if (K < 1 || K > 64) return fail_with(SEPAIHRD_ERR_INVALID_ARGUMENT, "a window holds between 1 and 64 iterations per chain");
+    if (m->windowed) return fail_with(SEPAIHRD_ERR_INVALID_ARGUMENT, "the window buffers of a run in progress cannot be replaced");
+    const auto ctx_lock = sepaihrd_internal::lock(m->ctx);
+    MH_TRY(cudaSetDevice(sepaihrd_internal::dims(m->ctx).device));
+    return window_buffers(m, K);
 }
 sepaihrd_rc sepaihrd_mh_window_propose(sepaihrd_mh* m, int32_t K) { return mh_window_phase(m, 0, K, 0); }
 sepaihrd_rc sepaihrd_mh_window_evaluate(sepaihrd_mh* m) { return mh_window_phase(m, 1, 0, 0); }

@@ -210,6 +210,9 @@ class DeviceMH:
         capi.check(self.L.sepaihrd_mh_accept(self._h))
 
     # look-ahead windows: K iterations of every chain per likelihood launch (sepaihrd_mh_window_*)
+    def window_reserve(self, K: int):
+        capi.check(self.L.sepaihrd_mh_window_reserve(self._h, int(K)))
+
     def window_propose(self, K: int):
         capi.check(self.L.sepaihrd_mh_window_propose(self._h, int(K)))
 
@@ -396,8 +399,8 @@ def run_mh_resident(ev, sigmas, initial, n_chains: int, iterations: int, seed: i
     ``lookahead`` = 1: one iteration per likelihood launch (above).  ``lookahead`` = K > 1 or None (sized from the shard,
     ``window_length``): look-ahead windows -- every chain proposes its next K iterations at once, one launch scores them all, every
     chain commits up to its first accepted proposal; the exchange then runs once per WINDOW (the ranks' log-likelihood blocks plus
-    each rank's smallest iteration index, from which every rank knows when all chains of the run are done: one small D2H read per
-    window).  Same decisions and states; ``best_trace`` is then per window and ``windows`` counts them."""
+    each rank's smallest iteration index, from which every rank knows when all chains of the run are done: a small D2H read after
+    every second window once the run could be over).  Same decisions and states; ``best_trace`` is then per window and ``windows`` counts them."""
     import torch
     dev = torch_device if torch_device is not None else torch.device("cuda", torch.cuda.current_device())
     stream = torch.cuda.current_stream(dev)
@@ -408,6 +411,8 @@ def run_mh_resident(ev, sigmas, initial, n_chains: int, iterations: int, seed: i
     windowed = K > 1
     t0 = time.perf_counter()
     mh = DeviceMH(ev, n_chains, lo, hi - lo, iterations, record_accepts=record_accepts, adapt_scale=adapt_scale)
+    if windowed:
+        mh.window_reserve(K)
     rec_n = block + 1 if windowed else block              # windows: one more double per rank, its smallest iteration index
     ex = Exchange(ev, rec_n, rank, world, transport, dev)
     gathered = torch.zeros((world, rec_n), dtype=torch.float64, device=dev)
@@ -423,7 +428,7 @@ def run_mh_resident(ev, sigmas, initial, n_chains: int, iterations: int, seed: i
     windows = 0
     if windowed:
         rec_ptr = rec_view = None
-        trace_rows = []
+        first_check = max(1, -(-(iterations - 1) // K))
         while True:
             mh.window_propose(K)
             ph.mark()
@@ -439,7 +444,9 @@ def run_mh_resident(ev, sigmas, initial, n_chains: int, iterations: int, seed: i
                 mh.note_gathered(gathered.data_ptr(), world, rec_n, windows + 1)
             ph.mark()
             windows += 1
-            if float(gathered[:, block].min().item()) >= iterations:      # the one host read per window: every rank sees the same value
+            # the host reads the ranks' smallest iteration indices (every rank sees the same values) once the fastest possible
+            # run could be over, then after every second window: a window past the end is harmless (nothing left to commit)
+            if windows >= first_check and (windows - first_check) % 2 == 0 and float(gathered[:, block].min().item()) >= iterations:
                 break
         mh.window_progress()
         trace = mh.read(MH_TRACE)[1:min(windows, iterations) + 1]
