@@ -23,10 +23,11 @@ os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
 dist.init_process_group("gloo", rank=rank, world_size=world)
 torch.cuda.set_device(0)
 p = pkg.load_default_problem()
-if what == "mh":
+if what in ("mh", "mhw"):
     rp = p.__class__.from_json(dict(p.to_json(), constraint_mode=1))
     with BatchEvaluator(rp, device=0) as ev:
-        r = resident.run_mh_resident(ev, p.sigmas, p.base_params(), n_chains=203, iterations=12, seed=1234, rank=rank, world=world, transport="p2p")
+        r = resident.run_mh_resident(ev, p.sigmas, p.base_params(), n_chains=203, iterations=12 if what == "mh" else 40, seed=1234, rank=rank,
+                                     world=world, transport="p2p", lookahead=1 if what == "mh" else 6)
     np.savez(f"{out}.rank{rank}.npz", lo=r["chains"][0], hi=r["chains"][1], x=r["x"], logpost=r["logpost"], accepts=r["accepts"],
              all_logpost=r["all_logpost"], scale=r["scale"], trace=r["best_trace"], status=r["exchange_status"])
 else:

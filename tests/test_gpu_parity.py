@@ -736,3 +736,38 @@ def test_ordering_pass_changes_the_schedule_not_the_results(problem, oracle, ev_
     np.testing.assert_array_equal(ll_u2, ll_u)
     np.testing.assert_array_equal(steps_u, ref_u[2].cpu().numpy())
     np.testing.assert_array_equal(ll_j, ref_j[0].cpu().numpy())
+
+
+def test_small_host_requests_through_pageable_and_page_locked_buffers(problem, oracle, ev_mod):
+    """sepaihrd_eval_batch for <= 4096 sets takes one stream and stages pageable caller buffers through a page-locked buffer of
+    the ctx: the same logL / status / step counts whatever memory the caller passes, with a leading dimension larger than P, and
+    for sizes either side of the 4096-set switch to the chunked path."""
+    import ctypes as C
+    import torch
+    from sepaihrd_b200 import capi
+    P = problem.n_params
+    ld = P + 3
+    for B in (1, 7, 333, 4096, 4097):
+        params = oracle.jitter_params(B, seed=100 + B)
+        wide = np.full((B, ld), np.nan); wide[:, :P] = params
+        ll_ref, st_ref, steps_ref, _ = oracle.eval_batch(params)
+        with ev_mod.BatchEvaluator(problem, device=0) as ev:
+            got = {}
+            for kind in ("pageable", "pinned", "mixed"):
+                if kind == "pageable":
+                    x = wide.copy(); ll = np.empty(B); st = np.empty(B, dtype=np.uint32); sp = np.empty((B, 2), dtype=np.int32)
+                    keep = (x, ll, st, sp)
+                else:
+                    tx = torch.from_numpy(wide.copy()).pin_memory(); tl = torch.empty(B, dtype=torch.float64).pin_memory()
+                    tsp = torch.empty((B, 2), dtype=torch.int32).pin_memory()
+                    x, ll, sp = tx.numpy(), tl.numpy(), tsp.numpy()
+                    st = np.empty(B, dtype=np.uint32) if kind == "mixed" else torch.empty(B, dtype=torch.int32).pin_memory().numpy().view(np.uint32)
+                    keep = (tx, tl, tsp, st)
+                capi.check(ev._lib.sepaihrd_eval_batch(ev._h, x.ctypes.data, B, ld, ll.ctypes.data, st.ctypes.data, sp.ctypes.data))
+                got[kind] = (ll.copy(), st.copy(), sp.copy())
+                del keep
+            for kind, (ll, st, sp) in got.items():
+                np.testing.assert_array_equal(st, st_ref, err_msg=kind)
+                np.testing.assert_array_equal(sp, steps_ref, err_msg=kind)
+                assert (np.abs(ll - ll_ref) / np.abs(ll_ref)).max() < 1e-8
+                np.testing.assert_array_equal(ll, got["pageable"][0])

@@ -201,6 +201,23 @@ def test_two_processes_exchange_through_peer_memory_mh(problem, reflect_problem,
         np.testing.assert_array_equal(q["trace"], ref["best_trace"])
 
 
+def test_two_processes_run_look_ahead_windows_over_peer_memory(problem, reflect_problem, mods, tmp_path):
+    """The windowed run sharded 102 + 101 over two processes: the per-window record (log-likelihood block + the rank's smallest
+    iteration index at the stride of the larger shard) crosses the mailboxes, both ranks stop after the same window, and the
+    decisions are the single-process one-iteration-per-launch run's."""
+    _, evaluator, resident = mods
+    with evaluator.BatchEvaluator(reflect_problem, device=0) as ev:
+        ref = resident.run_mh_resident(ev, problem.sigmas, problem.base_params(), 203, 40, 1234)
+    parts = _launch("mhw", str(tmp_path / "mhw"))
+    assert [int(q["status"]) for q in parts] == [0, 0]
+    np.testing.assert_array_equal(np.concatenate([q["accepts"] for q in parts], axis=1), ref["accepts"])
+    np.testing.assert_array_equal(np.concatenate([q["x"] for q in parts]), ref["x"])
+    np.testing.assert_array_equal(np.concatenate([q["scale"] for q in parts]), ref["scale"])
+    for q in parts:
+        np.testing.assert_array_equal(q["all_logpost"], ref["logpost"])
+        assert q["trace"][-1] == ref["best_trace"][-1] and len(q["trace"]) == len(parts[0]["trace"]) < 39
+
+
 def test_two_processes_exchange_through_peer_memory_pso(problem, mods, tmp_path):
     _, evaluator, resident = mods
     with evaluator.BatchEvaluator(problem, device=0) as ev:
