@@ -143,7 +143,6 @@ void MetropolisHastingsSampler::ownKernel(Chain& c) const {
     c.cov = shared_cov_;
     c.chol = shared_chol_;
     c.own_kernel = true;
-    ++c.kernel_version;
 }
 
 void MetropolisHastingsSampler::updateCovarianceRank1(Chain& c, int step) const {
@@ -221,7 +220,7 @@ void MetropolisHastingsSampler::recomputeFullCovariance(Chain& c) const {
     cov *= 1.0 / static_cast<double>(c.history.size() - 1);
     c.cov = ((2.38 * 2.38) / static_cast<double>(n_params_)) * cov + regularization_epsilon_ * MatrixXd::Identity(P, P);
     MatrixXd L;
-    if (linalg::cholesky_lower(c.cov, L)) { c.chol = L; ++c.kernel_version; }
+    if (linalg::cholesky_lower(c.cov, L)) c.chol = L;
 }
 
 void MetropolisHastingsSampler::adaptGlobalScale(ScaleState& c, bool accepted, int step) const {
@@ -254,12 +253,13 @@ void MetropolisHastingsSampler::adaptKernel(Chain& c, int t) const {
     if (t % adaptation_period_ == 0) {
         recomputeFullCovariance(c);
         MatrixXd L;
-        if (linalg::cholesky_lower(c.cov + regularization_epsilon_ * MatrixXd::Identity(P, P), L)) { c.chol = L; ++c.kernel_version; }
+        if (linalg::cholesky_lower(c.cov + regularization_epsilon_ * MatrixXd::Identity(P, P), L)) c.chol = L;
     }
 }
 
-// 2. proposal  Y = X + scale * L z,  z ~ N(0, I)   (generateProposal, .cpp:91-102): the step L z ...
-VectorXd MetropolisHastingsSampler::drawStep(std::mt19937& gen, const Chain& c) const {
+// 2. proposal  Y = X + scale * L z,  z ~ N(0, I)   (generateProposal, .cpp:91-102), 2b. constraints (reflection in MCMC mode, .cpp:308)
+void MetropolisHastingsSampler::drawProposal(std::mt19937& gen, const Chain& c, double scale, const double* x, IParameterManager& pm,
+                                             double* out) const {
     const auto P = static_cast<std::ptrdiff_t>(n_params_);
     VectorXd z(P);
     PolarNormal dist;                                   // a fresh distribution per proposal, like the reference's local object
@@ -276,21 +276,10 @@ VectorXd MetropolisHastingsSampler::drawStep(std::mt19937& gen, const Chain& c) 
             for (std::ptrdiff_t i = j; i < P; ++i) step(i) += L(i, j) * zj;
         }
     }
-    return step;
-}
-
-// ... and 2b. the constrained point (reflection in MCMC mode, .cpp:308)
-void MetropolisHastingsSampler::makeProposal(const VectorXd& step, double scale, const double* x, IParameterManager& pm, double* out) const {
-    const auto P = static_cast<std::ptrdiff_t>(n_params_);
     VectorXd y(P);
     for (std::ptrdiff_t i = 0; i < P; ++i) y(i) = x[i] + scale * step(i);
     const VectorXd yc = pm.applyConstraints(y);
     std::copy(yc.data(), yc.data() + P, out);
-}
-
-void MetropolisHastingsSampler::drawProposal(std::mt19937& gen, const Chain& c, double scale, const double* x, IParameterManager& pm,
-                                             double* out) const {
-    makeProposal(drawStep(gen, c), scale, x, pm, out);
 }
 
 void MetropolisHastingsSampler::propose(IParameterManager& pm, double* out) {
@@ -420,24 +409,13 @@ void MetropolisHastingsSampler::runLookahead(IObjectiveFunction& f, IParameterMa
             const int k = K[static_cast<size_t>(ci)];
             if (k == 0) continue;
             adaptKernel(c, c.t);
-            // The draws of the all-reject path -- per iteration P normals and one uniform, whatever the state and the scale are -- stay
-            // valid across windows as long as the chain keeps consuming exactly them (rejections, and accepts that drew their
-            // uniform): the steps L z already drawn for iterations BEHIND the first accept of the last window are this window's
-            // first ones.  The cache is keyed by the generator itself: it is used only while the chain's generator equals the state
-            // the cached draws start from (an uphill accept, which draws no uniform, shifts the stream and empties it) and while L
-            // is the one the steps were formed with.
-            if (c.ahead_kernel != c.kernel_version || !(c.ahead_base == c.gen)) { c.ahead.clear(); c.ahead_base = c.gen; c.ahead_kernel = c.kernel_version; }
+            std::mt19937 gen = c.gen;
             ScaleState sc = c;
             std::uniform_real_distribution<double> u01(0.0, 1.0);
             for (int j = 0; j < k; ++j) {
-                if (static_cast<size_t>(j) >= c.ahead.size()) {
-                    std::mt19937 gen = c.ahead.empty() ? c.gen : c.ahead.back().after;
-                    VectorXd step = drawStep(gen, c);
-                    (void)u01(gen);                                  // a rejected proposal was a downhill one: its uniform is drawn
-                    c.ahead.push_back(Chain::Ahead{std::move(step), gen});
-                }
-                makeProposal(c.ahead[static_cast<size_t>(j)].step, sc.global_scale, cur_x_.data() + static_cast<std::ptrdiff_t>(ci) * P, pm,
+                drawProposal(gen, c, sc.global_scale, cur_x_.data() + static_cast<std::ptrdiff_t>(ci) * P, pm,
                              props.data() + (first[static_cast<size_t>(ci)] + j) * P);
+                (void)u01(gen);                                      // a rejected proposal was a downhill one: its uniform is drawn
                 if (adapt_scale_) adaptGlobalScale(sc, false, c.t + j);
             }
         }
@@ -449,7 +427,6 @@ void MetropolisHastingsSampler::runLookahead(IObjectiveFunction& f, IParameterMa
 #pragma omp parallel for schedule(static) reduction(+ : committed) if (n >= 8)
         for (int ci = 0; ci < n; ++ci) {
             Chain& c = chains_[static_cast<size_t>(ci)];
-            int done_here = 0;
             for (int j = 0; j < K[static_cast<size_t>(ci)]; ++j) {
                 if (j > 0) adaptKernel(c, c.t);                      // rank-1 update of the covariance only (no refactoring, see above)
                 PolarNormal dist;                                    // the generator makes the draws of this iteration's proposal
@@ -457,15 +434,7 @@ void MetropolisHastingsSampler::runLookahead(IObjectiveFunction& f, IParameterMa
                 const double* row = props.data() + (first[static_cast<size_t>(ci)] + j) * P;
                 std::copy(row, row + P, prop_x_.begin() + static_cast<std::ptrdiff_t>(ci) * P);
                 ++committed;
-                ++done_here;
                 if (acceptOne(c, ci, plp[static_cast<size_t>(first[static_cast<size_t>(ci)] + j)])) break;   // the uniform (if downhill), state, scale, history, samples
-            }
-            // the cached draws behind the committed iterations stay, if the generator stands exactly where they start
-            if (done_here > 0 && static_cast<size_t>(done_here) <= c.ahead.size() && c.ahead[static_cast<size_t>(done_here) - 1].after == c.gen) {
-                c.ahead.erase(c.ahead.begin(), c.ahead.begin() + done_here);
-                c.ahead_base = c.gen;
-            } else {
-                c.ahead.clear();
             }
         }
         committed_ += committed;

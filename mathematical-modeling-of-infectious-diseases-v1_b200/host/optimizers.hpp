@@ -88,11 +88,6 @@ private:
     struct Chain : ScaleState {
         std::mt19937 gen;
         int t = 1;                        // next iteration of THIS chain (== iteration() in the lockstep loop; look-ahead lets chains run apart)
-        // look-ahead: steps L z already drawn for the iterations ahead, with the generator state after each (its normals + uniform)
-        struct Ahead { VectorXd step; std::mt19937 after; };
-        std::deque<Ahead> ahead;
-        std::mt19937 ahead_base;          // the generator state the first cached draw starts from
-        long ahead_kernel = -1, kernel_version = 0;      // L the steps were formed with / bumped whenever the chain's L changes
         long accepted = 0;
         bool own_kernel = false;          // false: shares the initial Cholesky factor
         MatrixXd cov, chol;
@@ -107,8 +102,6 @@ private:
     void adaptKernel(Chain& c, int step) const;                          // .cpp:286-303
     bool acceptOne(Chain& c, int ci, double proposed_logpost);           // .cpp:310-367
     void drawProposal(std::mt19937& gen, const Chain& c, double scale, const double* x, IParameterManager& pm, double* out) const;   // .cpp:91-102, 308
-    VectorXd drawStep(std::mt19937& gen, const Chain& c) const;                                                        // ... its L z
-    void makeProposal(const VectorXd& step, double scale, const double* x, IParameterManager& pm, double* out) const;  // ... x + s L z, constrained
     int windowLength(const Chain& c, int running_chains, int share) const;
     void runLookahead(IObjectiveFunction& f, IParameterManager& pm, const std::string& dir);
     void updateCovarianceRank1(Chain& c, int step) const;               // .cpp:154-168
