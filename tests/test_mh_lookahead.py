@@ -117,7 +117,7 @@ def test_multichain_lookahead_equals_the_lockstep_run(host, problem, tmp_path, n
 def test_many_chains_share_the_launch_budget(host, problem, tmp_path):
     """A launch holds at most 4096 proposals: 1500 chains look 2 ahead, 3000 chains run in lockstep."""
     st = dict(mcmc_iterations=6, burn_in=6, seed=2, write_trace=0, write_checkpoints=0, store_samples=0)
-    a = _run(host, problem, tmp_path, "a", "gauss", dict(st, n_chains=1500))
+    a = _run(host, problem, tmp_path, "a", "gauss", dict(st, n_chains=1500, lookahead=8))      # 8 asked for, 2 fit (automatic lengths follow measured costs)
     assert max(len(c) for c in a["calls"]) <= 4096 and any(len(c) > 1500 for c in a["calls"])
     b = _run(host, problem, tmp_path, "b", "gauss", dict(st, n_chains=3000))
     assert all(len(c) == 3000 for c in b["calls"][1:]) and b["nev"] == 1 + 3000 * 5
