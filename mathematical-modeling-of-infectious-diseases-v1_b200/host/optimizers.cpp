@@ -132,7 +132,8 @@ void MetropolisHastingsSampler::begin(const VectorXd& initial, const double* ini
         ch.running_mean = initial;
         ch.best_x = initial;
         ch.best_lp = cur_lp_[static_cast<size_t>(c)];
-        if (keep_history_) ch.history.push_back(initial);
+        ch.hist.clear(); ch.hist_sum = VectorXd::Zero(static_cast<std::ptrdiff_t>(n_params_));
+        if (keep_history_) pushHistory(ch, initial.data());
         if (store_samples_) { ch.samples.push_back(initial); ch.sample_lp.push_back(ch.best_lp); }
     }
     t_ = 1;
@@ -145,11 +146,20 @@ void MetropolisHastingsSampler::ownKernel(Chain& c) const {
     c.own_kernel = true;
 }
 
+// chain_history_.push_back (.cpp:369): the states in one contiguous buffer, and their running sum (the mean the full
+// recomputation needs is this sum: the same additions in the same order as summing the history again)
+void MetropolisHastingsSampler::pushHistory(Chain& c, const double* x) const {
+    const auto P = static_cast<std::ptrdiff_t>(n_params_);
+    c.hist.insert(c.hist.end(), x, x + P);
+    double* s = c.hist_sum.data();
+    for (std::ptrdiff_t i = 0; i < P; ++i) s[i] += x[i];
+}
+
 void MetropolisHastingsSampler::updateCovarianceRank1(Chain& c, int step) const {
-    if (c.history.empty()) return;
+    if (c.hist.empty()) return;
     const auto P = static_cast<std::ptrdiff_t>(n_params_);
     const double gamma = 10.0 / (step + 100.0);
-    const VectorXd diff = c.history.back() - c.running_mean;
+    const VectorXd diff = VectorXd::FromPointer(c.hist.data() + c.hist.size() - static_cast<size_t>(P), P) - c.running_mean;
     c.running_mean += gamma * diff;
     // cov = (1 - gamma) cov + gamma diff diff^T, element by element in place (the same three products and one sum per element
     // as the matrix expression, without its four P x P temporaries)
@@ -163,6 +173,40 @@ void MetropolisHastingsSampler::updateCovarianceRank1(Chain& c, int step) const 
     }
 }
 
+namespace {
+// cv(i, j) += sum over the rows t of D of D(t, i) D(t, j) for the columns [j0, j1) of the lower triangle, in row order, ONE pass
+// over D; four rows per pass over a column (added one after the other, so every element sees the additions of the plain loop).
+// Compiled a second time for AVX2 (four elements per instruction; no fused multiply-add: the products are rounded on their own
+// on every path) and picked at load time.
+#if defined(__x86_64__) && defined(__GNUC__) && !defined(__clang__)
+__attribute__((target_clones("avx2", "default")))
+#endif
+void accumulate_lower(const double* D, std::ptrdiff_t n, std::ptrdiff_t P, std::ptrdiff_t j0, std::ptrdiff_t j1, double* cv) {
+    std::ptrdiff_t t = 0;
+    for (; t + 4 <= n; t += 4) {
+        const double* __restrict r0 = D + t * P;
+        const double* __restrict r1 = r0 + P;
+        const double* __restrict r2 = r1 + P;
+        const double* __restrict r3 = r2 + P;
+        for (std::ptrdiff_t j = j0; j < j1; ++j) {
+            const double d0 = r0[j], d1 = r1[j], d2 = r2[j], d3 = r3[j];
+            double* __restrict col = cv + j * P;
+#pragma omp simd
+            for (std::ptrdiff_t i = j; i < P; ++i) col[i] = (((col[i] + r0[i] * d0) + r1[i] * d1) + r2[i] * d2) + r3[i] * d3;
+        }
+    }
+    for (; t < n; ++t) {
+        const double* __restrict row = D + t * P;
+        for (std::ptrdiff_t j = j0; j < j1; ++j) {
+            const double dj = row[j];
+            double* __restrict col = cv + j * P;
+#pragma omp simd
+            for (std::ptrdiff_t i = j; i < P; ++i) col[i] += row[i] * dj;
+        }
+    }
+}
+}  // namespace
+
 // .cpp:170-199.  The reference recomputes mean and covariance over the WHOLE chain history every adaptation_period
 // iterations (O(t P^2) each; Eigen's GEMM there).  Same here, every sum in history order: the centred history is laid out
 // once, the lower triangle is accumulated column by column (d_i d_j == d_j d_i bit for bit, so the upper triangle is a copy),
@@ -170,45 +214,27 @@ void MetropolisHastingsSampler::updateCovarianceRank1(Chain& c, int step) const 
 // result does not depend on the thread count.
 void MetropolisHastingsSampler::recomputeFullCovariance(Chain& c) const {
     const auto P = static_cast<std::ptrdiff_t>(n_params_);
-    if (c.history.size() < static_cast<size_t>(n_params_) + 10) return;
-    const std::ptrdiff_t n = static_cast<std::ptrdiff_t>(c.history.size());
-    VectorXd mean = VectorXd::Zero(P);
-    for (const auto& v : c.history) mean += v;
-    mean /= static_cast<double>(c.history.size());
+    const std::ptrdiff_t n = static_cast<std::ptrdiff_t>(c.hist.size()) / P;
+    if (static_cast<size_t>(n) < static_cast<size_t>(n_params_) + 10) return;
+    // the mean: the history summed in order -- which is what the running sum kept by pushHistory holds, addition by addition
+    VectorXd mean = c.hist_sum;
+    mean /= static_cast<double>(n);
     c.running_mean = mean;
-    std::vector<double> centred(static_cast<size_t>(n) * static_cast<size_t>(P));
+    std::vector<double>& centred = c.centred;                            // work buffer kept with the chain (50 MB at 100 000 states)
+    centred.resize(static_cast<size_t>(n) * static_cast<size_t>(P));
     const double* m = mean.data();
+    const bool threads = n_chains_ == 1 && n * P * P > (1 << 22);        // a long history: rows / column pairs shared among the host threads
+#pragma omp parallel for schedule(static) if (threads)
     for (std::ptrdiff_t t = 0; t < n; ++t) {
-        const double* v = c.history[static_cast<size_t>(t)].data();
+        const double* v = c.hist.data() + t * P;
         double* row = centred.data() + t * P;
         for (std::ptrdiff_t i = 0; i < P; ++i) row[i] = v[i] - m[i];
     }
     MatrixXd cov = MatrixXd::Zero(P, P);
     double* cv = cov.data();
     const double* D = centred.data();
-    auto accumulate = [&](std::ptrdiff_t j0, std::ptrdiff_t j1) {       // columns [j0, j1) of the lower triangle, ONE pass over the history
-        std::ptrdiff_t t = 0;
-        for (; t + 4 <= n; t += 4) {                                     // four states per pass over a column, added in history order
-            const double* __restrict r0 = D + t * P;
-            const double* __restrict r1 = r0 + P;
-            const double* __restrict r2 = r1 + P;
-            const double* __restrict r3 = r2 + P;
-            for (std::ptrdiff_t j = j0; j < j1; ++j) {
-                const double d0 = r0[j], d1 = r1[j], d2 = r2[j], d3 = r3[j];
-                double* __restrict col = cv + j * P;
-                for (std::ptrdiff_t i = j; i < P; ++i) col[i] = (((col[i] + r0[i] * d0) + r1[i] * d1) + r2[i] * d2) + r3[i] * d3;
-            }
-        }
-        for (; t < n; ++t) {
-            const double* __restrict row = D + t * P;
-            for (std::ptrdiff_t j = j0; j < j1; ++j) {
-                const double dj = row[j];
-                double* __restrict col = cv + j * P;
-                for (std::ptrdiff_t i = j; i < P; ++i) col[i] += row[i] * dj;
-            }
-        }
-    };
-    if (n_chains_ == 1 && n * P * P > (1 << 22)) {                       // a long history: column pairs shared among the host threads
+    auto accumulate = [&](std::ptrdiff_t j0, std::ptrdiff_t j1) { accumulate_lower(D, n, P, j0, j1, cv); };
+    if (threads) {
         const std::ptrdiff_t blocks = (P + 1) / 2;
 #pragma omp parallel for schedule(dynamic, 1)
         for (std::ptrdiff_t b = 0; b < blocks; ++b) accumulate(2 * b, std::min<std::ptrdiff_t>(2 * b + 2, P));
@@ -217,7 +243,7 @@ void MetropolisHastingsSampler::recomputeFullCovariance(Chain& c) const {
     }
     for (std::ptrdiff_t j = 0; j < P; ++j)
         for (std::ptrdiff_t i = j + 1; i < P; ++i) cv[i * P + j] = cv[j * P + i];
-    cov *= 1.0 / static_cast<double>(c.history.size() - 1);
+    cov *= 1.0 / static_cast<double>(n - 1);
     c.cov = ((2.38 * 2.38) / static_cast<double>(n_params_)) * cov + regularization_epsilon_ * MatrixXd::Identity(P, P);
     MatrixXd L;
     if (linalg::cholesky_lower(c.cov, L)) c.chol = L;
@@ -317,7 +343,7 @@ bool MetropolisHastingsSampler::acceptOne(Chain& c, int ci, double proposed_logp
         if (clp > c.best_lp) { c.best_lp = clp; c.best_x = VectorXd::FromPointer(x, P); }
     }
     if (adapt_scale_) adaptGlobalScale(c, acc, t);
-    if (keep_history_) c.history.push_back(VectorXd::FromPointer(x, P));
+    if (keep_history_) pushHistory(c, x);
     if (store_samples_ && (t % thinning_ == 0)) { c.samples.push_back(VectorXd::FromPointer(x, P)); c.sample_lp.push_back(clp); }
     ++c.t;
     return acc;

@@ -92,7 +92,9 @@ private:
         bool own_kernel = false;          // false: shares the initial Cholesky factor
         MatrixXd cov, chol;
         VectorXd running_mean;
-        std::vector<VectorXd> history;
+        std::vector<double> hist;         // chain_history_: [states][P], contiguous
+        VectorXd hist_sum;                // sum of the history in order (the mean of the full recomputation)
+        std::vector<double> centred;      // work buffer of recomputeFullCovariance
         double best_lp = -std::numeric_limits<double>::infinity();
         VectorXd best_x;
         std::vector<VectorXd> samples;
@@ -107,6 +109,7 @@ private:
     void updateCovarianceRank1(Chain& c, int step) const;               // .cpp:154-168
     void recomputeFullCovariance(Chain& c) const;                       // .cpp:170-199
     void ownKernel(Chain& c) const;
+    void pushHistory(Chain& c, const double* x) const;
 
     int iterations_ = 10000, burn_in_ = 1000, adaptation_period_ = 100, report_interval_ = 100, thinning_ = 1;
     bool write_checkpoints_ = true, write_trace_ = true;
