@@ -160,7 +160,12 @@ sepaihrd_rc sepaihrd_set_stream(sepaihrd_ctx* ctx, void* cuda_stream);
  * Thread-safe like calculate() has to be (the reference calls it from OpenMP loops, ParticleSwarmOptimizer.cpp:368-424,
  * HillClimbingOptimizer.cpp:228-234), and concurrent calls of at most 4096 sets each are MERGED: a caller that finds no
  * launch in flight takes every request queued so far (its own included) to the device as one launch.  The reference's
- * optimizers, unchanged, therefore cost one launch per round of their threads, not one per calculate(). */
+ * optimizers, unchanged, therefore cost one launch per round of their threads, not one per calculate().
+ * Requests of at most 4096 sets are latency, not throughput: one stream, one synchronisation, and pageable buffers (an
+ * Eigen::VectorXd, a std::vector) staged through a page-locked buffer of the ctx, so page-locked caller buffers
+ * (sepaihrd_alloc_pinned) save one small copy, no more.  Larger requests overlap their copies with the kernel in growing
+ * chunks and want page-locked memory.  A launch of up to ~4 000 sets costs what one set costs (~0.5 ms): callers with a
+ * sequential loop over calculate() should look ahead (host/optimizers.hpp: the one-chain sampler, the line search). */
 sepaihrd_rc sepaihrd_eval_batch(sepaihrd_ctx* ctx, const double* params, int64_t B, int64_t ld,
                                 double* out_ll, uint32_t* out_status, int32_t* out_steps);
 
