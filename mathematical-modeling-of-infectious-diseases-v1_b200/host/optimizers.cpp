@@ -77,7 +77,6 @@ void MetropolisHastingsSampler::configure(const std::map<std::string, double>& s
     // batched / repeatable extensions
     n_chains_ = std::max(1, static_cast<int>(setting(s, "n_chains", 1.0)));
     lookahead_ = std::max(0, static_cast<int>(setting(s, "lookahead", 0.0)));
-    lookahead_depth_ = std::max(1, static_cast<int>(setting(s, "lookahead_depth", 2.0)));
     chain_offset_ = static_cast<long>(setting(s, "chain_offset", 0.0));
     has_seed_ = s.count("seed") != 0;
     seed_ = static_cast<unsigned>(setting(s, "seed", 0.0));
@@ -284,8 +283,9 @@ void MetropolisHastingsSampler::adaptKernel(Chain& c, int t) const {
     }
 }
 
-// 2. proposal  Y = X + scale * L z,  z ~ N(0, I)   (generateProposal, .cpp:91-102): the step L z ...
-VectorXd MetropolisHastingsSampler::drawStep(std::mt19937& gen, const Chain& c) const {
+// 2. proposal  Y = X + scale * L z,  z ~ N(0, I)   (generateProposal, .cpp:91-102), 2b. constraints (reflection in MCMC mode, .cpp:308)
+void MetropolisHastingsSampler::drawProposal(std::mt19937& gen, const Chain& c, double scale, const double* x, IParameterManager& pm,
+                                             double* out) const {
     const auto P = static_cast<std::ptrdiff_t>(n_params_);
     VectorXd z(P);
     PolarNormal dist;                                   // a fresh distribution per proposal, like the reference's local object
@@ -302,21 +302,10 @@ VectorXd MetropolisHastingsSampler::drawStep(std::mt19937& gen, const Chain& c) 
             for (std::ptrdiff_t i = j; i < P; ++i) step(i) += L(i, j) * zj;
         }
     }
-    return step;
-}
-
-// ... and 2b. the constrained point (reflection in MCMC mode, .cpp:308)
-void MetropolisHastingsSampler::makeProposal(const VectorXd& step, double scale, const double* x, IParameterManager& pm, double* out) const {
-    const auto P = static_cast<std::ptrdiff_t>(n_params_);
     VectorXd y(P);
     for (std::ptrdiff_t i = 0; i < P; ++i) y(i) = x[i] + scale * step(i);
     const VectorXd yc = pm.applyConstraints(y);
     std::copy(yc.data(), yc.data() + P, out);
-}
-
-void MetropolisHastingsSampler::drawProposal(std::mt19937& gen, const Chain& c, double scale, const double* x, IParameterManager& pm,
-                                             double* out) const {
-    makeProposal(drawStep(gen, c), scale, x, pm, out);
 }
 
 void MetropolisHastingsSampler::propose(IParameterManager& pm, double* out) {
@@ -419,74 +408,40 @@ int MetropolisHastingsSampler::windowLength(const Chain& c, int running, int sha
 void MetropolisHastingsSampler::runLookahead(IObjectiveFunction& f, IParameterManager& pm, const std::string& dir) {
     const auto P = static_cast<std::ptrdiff_t>(n_params_);
     const int n = n_chains_;
-    // per chain and window: K proposals of the first level (all-reject path), then for j < J a second level of K2[j] proposals that
-    // continue from "proposal j accepted after drawing its uniform" (rows: [K first-level][K2[0]][K2[1]] ...)
-    struct Plan { int K = 0, J = 0; std::vector<int> K2; std::ptrdiff_t first = 0, rows = 0; };
-    std::vector<Plan> plan(static_cast<size_t>(n));
+    std::vector<int> K(static_cast<size_t>(n));
+    std::vector<std::ptrdiff_t> first(static_cast<size_t>(n) + 1);
     std::vector<double> props;
-    auto refactors = [&](int t) { return t > burn_in_ && t % adaptation_period_ == 0; };
     while (!done()) {
         int running = 0;
         for (const Chain& c : chains_) running += c.t < iterations_;
         const int share = std::max(1, LOOKAHEAD_SETS / std::max(running, 1));
-        const bool second_level = lookahead_depth_ >= 2 && running <= 16;
-        std::ptrdiff_t total = 0;
+        first[0] = 0;
         for (int ci = 0; ci < n; ++ci) {
             const Chain& c = chains_[static_cast<size_t>(ci)];
-            Plan& pl = plan[static_cast<size_t>(ci)];
             int k = std::min(windowLength(c, running, share), iterations_ - c.t);
             // the proposal kernel L must not change inside the window: an iteration that refactors it (.cpp:292-302) may open
             // a window (its adaptation runs before anything is drawn), it may not sit inside one
             for (int j = 1; j < k; ++j)
-                if (refactors(c.t + j)) { k = j; break; }
-            pl.K = std::max(k, 0);
-            pl.J = second_level ? std::min(pl.K, 8) : 0;
-            pl.K2.assign(static_cast<size_t>(pl.J), 0);
-            pl.rows = pl.K;
-            for (int j = 0; j < pl.J; ++j) {
-                int k2 = std::min(std::min(pl.K, 12), iterations_ - (c.t + j + 1));
-                for (int q = 0; q < k2; ++q)
-                    if (refactors(c.t + j + 1 + q)) { k2 = q; break; }
-                pl.K2[static_cast<size_t>(j)] = std::max(k2, 0);
-                pl.rows += pl.K2[static_cast<size_t>(j)];
-            }
-            pl.first = total;
-            total += pl.rows;
+                if (c.t + j > burn_in_ && (c.t + j) % adaptation_period_ == 0) { k = j; break; }
+            K[static_cast<size_t>(ci)] = std::max(k, 0);
+            first[static_cast<size_t>(ci) + 1] = first[static_cast<size_t>(ci)] + K[static_cast<size_t>(ci)];
         }
+        const int64_t total = first[static_cast<size_t>(n)];
         props.resize(static_cast<size_t>(total) * static_cast<size_t>(P));
         const auto clock0 = std::chrono::steady_clock::now();
 #pragma omp parallel for schedule(static) if (n >= 8)
         for (int ci = 0; ci < n; ++ci) {
             Chain& c = chains_[static_cast<size_t>(ci)];
-            const Plan& pl = plan[static_cast<size_t>(ci)];
-            if (pl.K == 0) continue;
+            const int k = K[static_cast<size_t>(ci)];
+            if (k == 0) continue;
             adaptKernel(c, c.t);
-            // the draws of the all-reject path: per iteration P normals (-> the step L z) and one uniform, whatever the state and
-            // the scale are; a second-level branch consumes the SAME draws (its accept drew its uniform), so one stream serves all
-            int need = pl.K;
-            for (int j = 0; j < pl.J; ++j) need = std::max(need, j + 1 + pl.K2[static_cast<size_t>(j)]);
-            std::vector<VectorXd> steps;
-            steps.reserve(static_cast<size_t>(need));
             std::mt19937 gen = c.gen;
-            std::uniform_real_distribution<double> u01(0.0, 1.0);
-            for (int e = 0; e < need; ++e) {
-                steps.push_back(drawStep(gen, c));
-                (void)u01(gen);                                      // a rejected proposal was a downhill one: its uniform is drawn
-            }
-            const double* x = cur_x_.data() + static_cast<std::ptrdiff_t>(ci) * P;
-            double* rows = props.data() + pl.first * P;
             ScaleState sc = c;
-            std::ptrdiff_t child = pl.K;
-            for (int j = 0; j < pl.K; ++j) {
-                makeProposal(steps[static_cast<size_t>(j)], sc.global_scale, x, pm, rows + j * P);
-                if (j < pl.J && pl.K2[static_cast<size_t>(j)] > 0) {   // the branch "proposal j accepted": state = that proposal, scale after the accept
-                    ScaleState sb = sc;
-                    if (adapt_scale_) adaptGlobalScale(sb, true, c.t + j);
-                    for (int q = 0; q < pl.K2[static_cast<size_t>(j)]; ++q, ++child) {
-                        makeProposal(steps[static_cast<size_t>(j + 1 + q)], sb.global_scale, rows + j * P, pm, rows + child * P);
-                        if (adapt_scale_) adaptGlobalScale(sb, false, c.t + j + 1 + q);
-                    }
-                }
+            std::uniform_real_distribution<double> u01(0.0, 1.0);
+            for (int j = 0; j < k; ++j) {
+                drawProposal(gen, c, sc.global_scale, cur_x_.data() + static_cast<std::ptrdiff_t>(ci) * P, pm,
+                             props.data() + (first[static_cast<size_t>(ci)] + j) * P);
+                (void)u01(gen);                                      // a rejected proposal was a downhill one: its uniform is drawn
                 if (adapt_scale_) adaptGlobalScale(sc, false, c.t + j);
             }
         }
@@ -498,30 +453,14 @@ void MetropolisHastingsSampler::runLookahead(IObjectiveFunction& f, IParameterMa
 #pragma omp parallel for schedule(static) reduction(+ : committed) if (n >= 8)
         for (int ci = 0; ci < n; ++ci) {
             Chain& c = chains_[static_cast<size_t>(ci)];
-            const Plan& pl = plan[static_cast<size_t>(ci)];
-            // one iteration of the sequential loop with a proposal that is already scored: the generator makes the proposal's
-            // draws, acceptOne the rest (the uniform if downhill, state, scale, history, samples)
-            auto step_with = [&](std::ptrdiff_t row, bool rank1) {
-                if (rank1) adaptKernel(c, c.t);                      // rank-1 update of the covariance only (no refactoring, see above)
-                PolarNormal dist;
+            for (int j = 0; j < K[static_cast<size_t>(ci)]; ++j) {
+                if (j > 0) adaptKernel(c, c.t);                      // rank-1 update of the covariance only (no refactoring, see above)
+                PolarNormal dist;                                    // the generator makes the draws of this iteration's proposal
                 for (std::ptrdiff_t i = 0; i < P; ++i) (void)dist(c.gen);
-                const double* r = props.data() + (pl.first + row) * P;
-                std::copy(r, r + P, prop_x_.begin() + static_cast<std::ptrdiff_t>(ci) * P);
+                const double* row = props.data() + (first[static_cast<size_t>(ci)] + j) * P;
+                std::copy(row, row + P, prop_x_.begin() + static_cast<std::ptrdiff_t>(ci) * P);
                 ++committed;
-                return acceptOne(c, ci, plp[static_cast<size_t>(pl.first + row)]);
-            };
-            std::ptrdiff_t child = pl.K;
-            for (int j = 0; j < pl.K; ++j) {
-                const int k2 = j < pl.J ? pl.K2[static_cast<size_t>(j)] : 0;
-                const bool uphill = safeValue(plp[static_cast<size_t>(pl.first + j)]) - cur_lp_[static_cast<size_t>(ci)] >= 0.0;   // accepts without a uniform
-                if (step_with(j, j > 0)) {
-                    // accepted after drawing its uniform: the generator stands where the second-level draws start
-                    if (!uphill)
-                        for (int q = 0; q < k2; ++q)
-                            if (step_with(child + q, true)) break;
-                    break;
-                }
-                child += k2;
+                if (acceptOne(c, ci, plp[static_cast<size_t>(first[static_cast<size_t>(ci)] + j)])) break;   // the uniform (if downhill), state, scale, history, samples
             }
         }
         committed_ += committed;

@@ -72,11 +72,6 @@ public:
     // uniform, .cpp:323-329) and s_j the scale after j more rejections (.cpp:104-152).  optimize() evaluates those K as one
     // batch, commits iterations up to and including the first accepted one and throws the rest away.  The chain, its
     // generator, scale, covariance and trace files are bit for bit those of the sequential run (tests/test_mh_lookahead.py).
-    // Second level (setting "lookahead_depth", default 2, used for up to 16 chains): the first accept of a window usually drew its
-    // uniform (a downhill proposal), and then the generator goes on with exactly the draws the all-reject path would have made --
-    // so for the first 8 positions j the window also holds the proposals of the <= 12 iterations AFTER "proposal j accepted":
-    // state = that proposal, scale after j rejections and one accept, the same steps L z.  The commit walks into that branch when
-    // proposal j is accepted downhill: ~7 instead of ~4.4 iterations per launch at 23 % acceptance, for ~100 more cheap proposals.
     // With several chains every chain looks ahead on its own (the chains then run apart by a few iterations between launches;
     // a launch holds at most 4096 proposals, so the windows shrink as the chain count grows: 256 chains x 16, 2048 x 2).
     int lookahead() const { return lookahead_; }
@@ -109,8 +104,6 @@ private:
     void adaptKernel(Chain& c, int step) const;                          // .cpp:286-303
     bool acceptOne(Chain& c, int ci, double proposed_logpost);           // .cpp:310-367
     void drawProposal(std::mt19937& gen, const Chain& c, double scale, const double* x, IParameterManager& pm, double* out) const;   // .cpp:91-102, 308
-    VectorXd drawStep(std::mt19937& gen, const Chain& c) const;                                                        // ... its L z
-    void makeProposal(const VectorXd& step, double scale, const double* x, IParameterManager& pm, double* out) const;  // ... x + s L z, constrained
     int windowLength(const Chain& c, int running_chains, int share) const;
     void runLookahead(IObjectiveFunction& f, IParameterManager& pm, const std::string& dir);
     void updateCovarianceRank1(Chain& c, int step) const;               // .cpp:154-168
@@ -126,7 +119,7 @@ private:
     double regularization_epsilon_ = 1e-6, target_acceptance_rate_ = 0.234;
     bool adapt_scale_ = true, store_samples_ = true;
     int n_chains_ = 1;
-    int lookahead_ = 0, lookahead_depth_ = 2;
+    int lookahead_ = 0;
     static constexpr int LOOKAHEAD_SETS = 4096;          // proposals per launch: up to here a launch costs what one set costs
     long speculated_ = 0, committed_ = 0;
     double launch_seconds_ = 0.0, proposal_seconds_ = 0.0;     // running means: one objective call; host arithmetic per proposal

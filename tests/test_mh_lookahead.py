@@ -4,8 +4,7 @@ per iteration.  With setting ``lookahead`` != 1 the sampler evaluates the propos
 advance as long as the chain keeps rejecting -- as ONE batch and commits up to the first accepted one.  The chain must be the
 sequential chain bit for bit: every visited state, every log-posterior, the generator (a misaligned draw would change every
 later state), the scale, the adapted covariance, and the trace / checkpoint files; only the shape of the evaluation batches
-differs.  The same for the two-level window (setting ``lookahead_depth``, default 2): the first accept of a window usually drew its
-uniform, the generator then goes on with the draws of the all-reject path, and the window holds the proposals of that branch too."""
+differs."""
 import numpy as np
 import pytest
 
@@ -57,14 +56,13 @@ def _run(host, problem, tmp_path, tag, kind, settings):
 
 
 @pytest.mark.parametrize("kind", ["gauss", "steep", "plateau", "nan"])
-@pytest.mark.parametrize("lookahead,depth", [(0, 2), (2, 2), (7, 2), (64, 2), (0, 1), (7, 1)])
-def test_lookahead_chain_is_the_sequential_chain(host, problem, tmp_path, kind, lookahead, depth):
+@pytest.mark.parametrize("lookahead", [0, 2, 7, 64])
+def test_lookahead_chain_is_the_sequential_chain(host, problem, tmp_path, kind, lookahead):
     # 330 iterations: through the burn-in (rank-1 updates from t = 121), three refactorisations of the proposal kernel
     # (t = 150, 200, ... : windows must stop in front of them), checkpoints every 40, thinning 1 so that every state is written
     st = dict(mcmc_iterations=330, burn_in=120, adaptation_period=50, n_chains=1, report_interval=40, thinning=1, seed=11)
     seq = _run(host, problem, tmp_path, "seq", kind, dict(st, lookahead=1))
-    # depth 2: the window also holds, for its first 8 positions, the <= 12 iterations after "this proposal accepted downhill"
-    la = _run(host, problem, tmp_path, f"la{lookahead}", kind, dict(st, lookahead=lookahead, lookahead_depth=depth))
+    la = _run(host, problem, tmp_path, f"la{lookahead}", kind, dict(st, lookahead=lookahead))
     assert all(len(c) == 1 for c in seq["calls"]) and seq["nev"] == 330             # 1 initial + 329 proposals, one per call
     assert sorted(la["files"]) == sorted(seq["files"]) == ["posterior_trace.csv", "posterior_trace_checkpoint.csv", "posterior_trace_final.csv"]
     for name in seq["files"]:
@@ -83,9 +81,7 @@ def test_lookahead_chain_is_the_sequential_chain(host, problem, tmp_path, kind, 
         pos += 1
     assert len(la["calls"]) < len(seq["calls"])                                       # fewer launches
     if lookahead > 1:
-        assert max(len(c) for c in la["calls"]) <= lookahead + (min(lookahead, 8) * min(lookahead, 12) if depth == 2 else 0)
-    if depth == 2 and lookahead == 7 and kind == "gauss":
-        assert max(len(c) for c in la["calls"]) > 7                                   # the second level is there
+        assert max(len(c) for c in la["calls"]) <= lookahead
 
 
 def test_lookahead_cuts_the_number_of_launches(host, problem, tmp_path):
@@ -95,7 +91,7 @@ def test_lookahead_cuts_the_number_of_launches(host, problem, tmp_path):
     la = _run(host, problem, tmp_path, "la", "gauss", dict(st, lookahead=0))
     launches = len(la["calls"]) - 1
     assert 2999 / launches > 1.5, (launches, la["nev"])            # (a device launch costs ~0.6 ms: ~4.5 iterations per launch there)
-    assert la["nev"] < 130 * launches                              # at most 16 + 8 x 12 proposals per launch
+    assert la["nev"] < 25 * launches
 
 
 @pytest.mark.parametrize("n_chains", [3, 12])
