@@ -23,6 +23,7 @@ ap.add_argument("--host-swarm", action="store_true", help="pso: keep the swarm o
 ap.add_argument("--host-staged", action="store_true", help="mh / pso: round 1's path (host sampler resp. per-iteration host round trips, host-staged collectives) "
                                                            "instead of the device-resident callers with the peer-memory exchange")
 ap.add_argument("--transport", default=None, choices=[None, "p2p", "nccl"], help="mh / pso: exchange transport of the device-resident callers")
+ap.add_argument("--lookahead", type=int, default=1, help="mh: iterations per look-ahead window of the device-resident chains (1: one iteration per launch, 0: from the shard size)")
 ap.add_argument("--pageable", action="store_true", help="ppcq: pass the draws in ordinary (pageable) host memory instead of page-locked memory")
 ap.add_argument("--ages", type=int, default=4, help="ppcq: 4, or 16 for the synthetic many-age-group variant of BASELINE configs[4]")
 a = ap.parse_args()
@@ -44,8 +45,9 @@ if a.what in ("mh", "pso") and not (a.host_staged or a.host_swarm):
     with BatchEvaluator(prob, device=dev) as ev:
         ev.eval_batch(np.tile(p.base_params(), (64, 1)))
         if a.what == "mh":
-            r = resident.run_mh_resident(ev, p.sigmas, p.base_params(), a.chains, a.iterations, 1234, comm.rank, comm.world, transport=a.transport)
-            out.update(chains=a.chains, iterations=a.iterations, seconds=r["run_seconds"], setup_seconds=r["setup_seconds"],
+            r = resident.run_mh_resident(ev, p.sigmas, p.base_params(), a.chains, a.iterations, 1234, comm.rank, comm.world, transport=a.transport,
+                                         lookahead=None if a.lookahead == 0 else a.lookahead)
+            out.update(chains=a.chains, iterations=a.iterations, seconds=r["run_seconds"], setup_seconds=r["setup_seconds"], window_length=r["lookahead"], windows=r["windows"],
                        evals_per_s=a.chains * (a.iterations - 1) / r["run_seconds"], phase_seconds=r["phase_seconds"], transport=r["transport"],
                        accept_rate=float(r["accepts"].mean()), best=float(r["best_trace"][-1]),
                        accept_checksum_local=int(np.packbits(r["accepts"]).astype(np.int64).sum()))
