@@ -541,9 +541,8 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) sepaihrd_batch_kernel(cons
     const int sl_beta0 = 0, sl_kappa0 = kp.nb, sl_scal0 = kp.nb + kp.nk, sl_age0 = sl_scal0 + 7;
     const int sl_mult0 = sl_age0 + 8 * n, sl_seed = sl_mult0 + 8, sl_runup = sl_mult0 + 9, sl_beta = sl_mult0 + 10;
 
-    // Work is handed out per WARP (32 / NA sets at a time) from a global counter: warps never wait for the other
-    // warps of their block and the tail of a launch is one warp-tile long.
-    constexpr int WSETS = (32 / NA) > 0 ? (32 / NA) : 1;
+    // Work is handed out per WARP (kp.sets_per_tile <= 32 / NA sets at a time) from a global counter: warps never wait for the
+    // other warps of their block and the tail of a launch is one warp-tile long.
     const int grp_in_warp = (threadIdx.x & 31) / NA;
     // A launch with fewer tiles than resident warps (a few thousand sets: multi-chain samplers, line searches) is spread over the
     // SMs and, inside an SM, over the schedulers: the host launches one block per tile until the machine is full and lets only

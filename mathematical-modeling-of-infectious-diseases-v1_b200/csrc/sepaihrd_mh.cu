@@ -615,9 +615,7 @@ static sepaihrd_rc window_buffers(sepaihrd_mh* m, int K) {
     char* D = m->d_win;
     m->d_wprop = (double*)(D + o_prop); m->d_wplp = (double*)(D + o_plp); m->d_wlogu = (double*)(D + o_logu); m->d_wCz = (unsigned*)(D + o_cz);
     m->d_wstatus = (unsigned*)(D + o_st); m->d_ghost = (unsigned*)(D + o_ghost);
-    int* old_t = m->d_t;
     m->d_t = (int*)(D + o_t); m->d_tmin = (int*)(D + o_tmin); m->d_record = (double*)(D + o_rec);
-    (void)old_t;
     m->win_cap = K;
     return SEPAIHRD_OK;
 }
