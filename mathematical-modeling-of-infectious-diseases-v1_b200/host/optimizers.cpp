@@ -389,7 +389,10 @@ int MetropolisHastingsSampler::windowLength(const Chain& c, int running, int sha
     if (lookahead_ > 1) return std::min(lookahead_, share);
     const double rate = c.recent.size() < 50 ? 0.234
                                              : std::min(std::max(static_cast<double>(c.recent_sum) / static_cast<double>(c.recent.size()), 0.02), 0.9);
-    const double launch = launch_seconds_ > 0 ? launch_seconds_ : 6e-4, per = proposal_seconds_ > 0 ? proposal_seconds_ : 6e-6;
+    // a call of the objective over B rows is taken to cost launch + B * row: the device objective is all `launch` (~0.6 ms, ~2 us per
+    // row), an objective that scores its rows one after the other on the host is all `row` -- and then looking ahead only wastes
+    // evaluations, K comes out as 1 and the run is the sequential one
+    const double launch = launch_seconds_ > 0 ? launch_seconds_ : 6e-4, per = (proposal_seconds_ > 0 ? proposal_seconds_ : 6e-6) + row_seconds_;
     int best = 1;
     double best_rate = 0.0, miss = 1.0;
     for (int k = 1; k <= std::min(share, 128); ++k) {
@@ -466,9 +469,16 @@ void MetropolisHastingsSampler::runLookahead(IObjectiveFunction& f, IParameterMa
         committed_ += committed;
         {   // what a proposal costs the host (drawing + its share of the commit) and what a launch costs: running means for windowLength
             const double host_s = std::chrono::duration<double>(clock1 - clock0).count() + std::chrono::duration<double>(std::chrono::steady_clock::now() - clock2).count();
-            const double per = host_s / static_cast<double>(std::max<int64_t>(total, 1)), launch = std::chrono::duration<double>(clock2 - clock1).count();
+            const double per = host_s / static_cast<double>(std::max<int64_t>(total, 1)), call = std::chrono::duration<double>(clock2 - clock1).count();
             proposal_seconds_ = proposal_seconds_ > 0 ? 0.8 * proposal_seconds_ + 0.2 * per : per;
+            // split the call into its fixed part and its per-row part with the cheapest one-row call seen so far as the anchor
+            if (total == 1) one_row_seconds_ = one_row_seconds_ > 0 ? std::min(one_row_seconds_, call) : call;
+            double row = 0.0;
+            if (total > 1 && one_row_seconds_ > 0) row = std::max(0.0, (call - one_row_seconds_) / static_cast<double>(total - 1));
+            const double launch = std::max(call - row * static_cast<double>(total), 0.05 * call);
+            row_seconds_ = calls_seen_ > 0 ? 0.8 * row_seconds_ + 0.2 * row : row;
             launch_seconds_ = launch_seconds_ > 0 ? 0.8 * launch_seconds_ + 0.2 * launch : launch;
+            ++calls_seen_;
         }
         // the lockstep loop writes a checkpoint after iteration t when (t + 1) % report_interval == 0 (.cpp:380-382): here once ALL
         // chains have completed such an iteration, with every chain cut at it
@@ -487,13 +497,16 @@ OptimizationResult MetropolisHastingsSampler::optimize(const VectorXd& initial, 
     if (auto* spm = dynamic_cast<SEPAIHRDParameterManager*>(&pm)) spm->setConstraintMode(ConstraintMode::MCMC_REFLECT);   // .cpp:207-210
     const int64_t P = initial.size();
     // every chain starts from the same point: one evaluation, replicated
+    const auto first0 = std::chrono::steady_clock::now();
     const double lp0 = safeValue(f.calculate(initial));
+    one_row_seconds_ = std::chrono::duration<double>(std::chrono::steady_clock::now() - first0).count();     // (may include a warm-up: only ever lowered)
     std::vector<double> lp(static_cast<size_t>(n_chains_), lp0);
     begin(initial, lp.data(), pm);
     std::vector<double> prop(static_cast<size_t>(n_chains_) * static_cast<size_t>(P));
     const std::string dir = (store_samples_ && (write_checkpoints_ || write_trace_)) ? traceDirectory() : std::string();
     speculated_ = committed_ = 0;
-    launch_seconds_ = proposal_seconds_ = 0.0;
+    launch_seconds_ = proposal_seconds_ = row_seconds_ = 0.0;
+    calls_seen_ = 0;
     if (lookahead_ != 1 && 2 * n_chains_ <= LOOKAHEAD_SETS) runLookahead(f, pm, dir);
     while (!done()) {
         const int t = t_;

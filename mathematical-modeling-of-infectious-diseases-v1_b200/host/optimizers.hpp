@@ -122,7 +122,9 @@ private:
     int lookahead_ = 0;
     static constexpr int LOOKAHEAD_SETS = 4096;          // proposals per launch: up to here a launch costs what one set costs
     long speculated_ = 0, committed_ = 0;
-    double launch_seconds_ = 0.0, proposal_seconds_ = 0.0;     // running means: one objective call; host arithmetic per proposal
+    double launch_seconds_ = 0.0, proposal_seconds_ = 0.0;     // running means: fixed part of an objective call; host arithmetic per proposal
+    double row_seconds_ = 0.0, one_row_seconds_ = 0.0;         // per-row part of an objective call; the cheapest one-row call seen
+    long calls_seen_ = 0;
     long chain_offset_ = 0;
     bool shared_diagonal_ = false;
     bool has_seed_ = false;
