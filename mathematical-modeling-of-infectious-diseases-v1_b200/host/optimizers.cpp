@@ -387,6 +387,7 @@ OptimizationResult MetropolisHastingsSampler::result(int upto) const {
 // anyway).  Measured on the device objective at 21 % acceptance, one chain: K = 8 5.7 k, 16 6.2 k, 32 5.9 k, 128 5.0 k iterations/s.
 int MetropolisHastingsSampler::windowLength(const Chain& c, int running, int share) const {
     if (lookahead_ > 1) return std::min(lookahead_, share);
+    if (calls_seen_ < 2) return std::min(calls_seen_ == 0 ? 4 : 16, share);      // the two probe windows (see runLookahead)
     const double rate = c.recent.size() < 50 ? 0.234
                                              : std::min(std::max(static_cast<double>(c.recent_sum) / static_cast<double>(c.recent.size()), 0.02), 0.9);
     // a call of the objective over B rows is taken to cost launch + B * row: the device objective is all `launch` (~0.6 ms, ~2 us per
@@ -471,13 +472,13 @@ void MetropolisHastingsSampler::runLookahead(IObjectiveFunction& f, IParameterMa
             const double host_s = std::chrono::duration<double>(clock1 - clock0).count() + std::chrono::duration<double>(std::chrono::steady_clock::now() - clock2).count();
             const double per = host_s / static_cast<double>(std::max<int64_t>(total, 1)), call = std::chrono::duration<double>(clock2 - clock1).count();
             proposal_seconds_ = proposal_seconds_ > 0 ? 0.8 * proposal_seconds_ + 0.2 * per : per;
-            // split the call into its fixed part and its per-row part with the cheapest one-row call seen so far as the anchor
-            if (total == 1) one_row_seconds_ = one_row_seconds_ > 0 ? std::min(one_row_seconds_, call) : call;
-            double row = 0.0;
-            if (total > 1 && one_row_seconds_ > 0) row = std::max(0.0, (call - one_row_seconds_) / static_cast<double>(total - 1));
-            const double launch = std::max(call - row * static_cast<double>(total), 0.05 * call);
-            row_seconds_ = calls_seen_ > 0 ? 0.8 * row_seconds_ + 0.2 * row : row;
-            launch_seconds_ = launch_seconds_ > 0 ? 0.8 * launch_seconds_ + 0.2 * launch : launch;
+            // split the call into its fixed part and its per-row part from the first two windows, which are given different lengths
+            // on purpose (4 and 16 proposals per chain: fresh proposals, so a likelihood cache cannot fake a cheap call)
+            if (calls_seen_ == 0) { probe_rows_ = static_cast<double>(total); probe_seconds_ = call; }
+            else if (calls_seen_ == 1 && static_cast<double>(total) > probe_rows_)
+                row_seconds_ = std::max(0.0, (call - probe_seconds_) / (static_cast<double>(total) - probe_rows_));
+            const double launch = std::max(call - row_seconds_ * static_cast<double>(total), 0.05 * call);
+            launch_seconds_ = launch_seconds_ > 0 && calls_seen_ > 1 ? 0.8 * launch_seconds_ + 0.2 * launch : launch;
             ++calls_seen_;
         }
         // the lockstep loop writes a checkpoint after iteration t when (t + 1) % report_interval == 0 (.cpp:380-382): here once ALL
@@ -497,9 +498,7 @@ OptimizationResult MetropolisHastingsSampler::optimize(const VectorXd& initial, 
     if (auto* spm = dynamic_cast<SEPAIHRDParameterManager*>(&pm)) spm->setConstraintMode(ConstraintMode::MCMC_REFLECT);   // .cpp:207-210
     const int64_t P = initial.size();
     // every chain starts from the same point: one evaluation, replicated
-    const auto first0 = std::chrono::steady_clock::now();
     const double lp0 = safeValue(f.calculate(initial));
-    one_row_seconds_ = std::chrono::duration<double>(std::chrono::steady_clock::now() - first0).count();     // (may include a warm-up: only ever lowered)
     std::vector<double> lp(static_cast<size_t>(n_chains_), lp0);
     begin(initial, lp.data(), pm);
     std::vector<double> prop(static_cast<size_t>(n_chains_) * static_cast<size_t>(P));

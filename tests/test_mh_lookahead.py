@@ -124,3 +124,41 @@ def test_many_chains_share_the_launch_budget(host, problem, tmp_path):
     c = _run(host, problem, tmp_path, "c", "gauss", dict(st, n_chains=1500, lookahead=1))
     np.testing.assert_array_equal(a["best"], c["best"])
     assert a["val"] == c["val"]
+
+
+def test_window_length_follows_the_cost_structure_of_the_objective(host, problem, tmp_path):
+    """The automatic window length comes from measured costs: the first two windows (4 and 16 proposals) split an objective call
+    into a fixed and a per-row part.  An objective that scores its rows one after the other gains nothing from looking ahead and
+    gets the sequential call pattern back (one row per call); an objective with a fixed cost per call -- a device launch -- gets
+    long windows.  The chain is the same chain either way."""
+    import time
+    inner = _objective(problem, "gauss")
+    calls = []
+
+    def serial(x):                       # 0.3 ms per row
+        calls.append(len(x))
+        t0 = time.perf_counter()
+        while time.perf_counter() - t0 < 3e-4 * len(x):
+            pass
+        return inner(x)
+
+    def fixed(x):                        # 0.6 ms per call
+        calls.append(len(x))
+        t0 = time.perf_counter()
+        while time.perf_counter() - t0 < 6e-4:
+            pass
+        return inner(x)
+
+    pm = host.ParameterManager(problem.sigmas, problem.lower_bound, problem.upper_bound, mode=1)
+    st = dict(mcmc_iterations=400, burn_in=400, n_chains=1, seed=9, write_trace=0, write_checkpoints=0, store_samples=0)
+    best = {}
+    for name, f in (("serial", serial), ("fixed", fixed)):
+        calls.clear()
+        best[name] = host.optimize("mh", pm, dict(st, lookahead=0), f, problem.base_params())[:2]
+        rows, n_calls = sum(calls), len(calls)
+        if name == "serial":
+            assert rows < 1.25 * 400, (rows, n_calls)              # the two probe windows, then (nearly) one row per call
+        else:
+            assert n_calls < 400 / 2 and rows > 2 * 400, (rows, n_calls)
+    np.testing.assert_array_equal(best["serial"][0], best["fixed"][0])
+    assert best["serial"][1] == best["fixed"][1]
