@@ -394,11 +394,13 @@ int MetropolisHastingsSampler::windowLength(const Chain& c, int running, int sha
     // row), an objective that scores its rows one after the other on the host is all `row` -- and then looking ahead only wastes
     // evaluations, K comes out as 1 and the run is the sequential one
     const double launch = launch_seconds_ > 0 ? launch_seconds_ : 6e-4, per = (proposal_seconds_ > 0 ? proposal_seconds_ : 6e-6) + row_seconds_;
+    const double commit = commit_seconds_ > 0 ? commit_seconds_ : 3e-6;       // host time per COMMITTED iteration (draws replayed, accept, adaptation)
     int best = 1;
     double best_rate = 0.0, miss = 1.0;
     for (int k = 1; k <= std::min(share, 128); ++k) {
         miss *= 1.0 - rate;
-        const double r = (1.0 - miss) / rate / (launch + static_cast<double>(running) * k * per);
+        const double g = (1.0 - miss) / rate;
+        const double r = g / (launch + static_cast<double>(running) * (k * per + g * commit));
         if (r > best_rate) { best_rate = r; best = k; }
     }
     return best;
@@ -439,6 +441,10 @@ void MetropolisHastingsSampler::runLookahead(IObjectiveFunction& f, IParameterMa
             const int k = K[static_cast<size_t>(ci)];
             if (k == 0) continue;
             adaptKernel(c, c.t);
+            if (k == 1) {                                            // nothing to look ahead to: the sequential iteration, drawn from the chain's own generator
+                drawProposal(c.gen, c, c.global_scale, cur_x_.data() + static_cast<std::ptrdiff_t>(ci) * P, pm, props.data() + first[static_cast<size_t>(ci)] * P);
+                continue;
+            }
             std::mt19937 gen = c.gen;
             ScaleState sc = c;
             std::uniform_real_distribution<double> u01(0.0, 1.0);
@@ -459,8 +465,10 @@ void MetropolisHastingsSampler::runLookahead(IObjectiveFunction& f, IParameterMa
             Chain& c = chains_[static_cast<size_t>(ci)];
             for (int j = 0; j < K[static_cast<size_t>(ci)]; ++j) {
                 if (j > 0) adaptKernel(c, c.t);                      // rank-1 update of the covariance only (no refactoring, see above)
-                PolarNormal dist;                                    // the generator makes the draws of this iteration's proposal
-                for (std::ptrdiff_t i = 0; i < P; ++i) (void)dist(c.gen);
+                if (K[static_cast<size_t>(ci)] > 1) {                // the generator makes the draws of this iteration's proposal (a window of one drew them itself)
+                    PolarNormal dist;
+                    for (std::ptrdiff_t i = 0; i < P; ++i) (void)dist(c.gen);
+                }
                 const double* row = props.data() + (first[static_cast<size_t>(ci)] + j) * P;
                 std::copy(row, row + P, prop_x_.begin() + static_cast<std::ptrdiff_t>(ci) * P);
                 ++committed;
@@ -469,9 +477,11 @@ void MetropolisHastingsSampler::runLookahead(IObjectiveFunction& f, IParameterMa
         }
         committed_ += committed;
         {   // what a proposal costs the host (drawing + its share of the commit) and what a launch costs: running means for windowLength
-            const double host_s = std::chrono::duration<double>(clock1 - clock0).count() + std::chrono::duration<double>(std::chrono::steady_clock::now() - clock2).count();
-            const double per = host_s / static_cast<double>(std::max<int64_t>(total, 1)), call = std::chrono::duration<double>(clock2 - clock1).count();
+            const double per = std::chrono::duration<double>(clock1 - clock0).count() / static_cast<double>(std::max<int64_t>(total, 1));
+            const double com = std::chrono::duration<double>(std::chrono::steady_clock::now() - clock2).count() / static_cast<double>(std::max<long>(committed, 1));
+            const double call = std::chrono::duration<double>(clock2 - clock1).count();
             proposal_seconds_ = proposal_seconds_ > 0 ? 0.8 * proposal_seconds_ + 0.2 * per : per;
+            commit_seconds_ = commit_seconds_ > 0 ? 0.8 * commit_seconds_ + 0.2 * com : com;
             // split the call into its fixed part and its per-row part from the first two windows, which are given different lengths
             // on purpose (4 and 16 proposals per chain: fresh proposals, so a likelihood cache cannot fake a cheap call)
             if (calls_seen_ == 0) { probe_rows_ = static_cast<double>(total); probe_seconds_ = call; }
@@ -504,7 +514,7 @@ OptimizationResult MetropolisHastingsSampler::optimize(const VectorXd& initial, 
     std::vector<double> prop(static_cast<size_t>(n_chains_) * static_cast<size_t>(P));
     const std::string dir = (store_samples_ && (write_checkpoints_ || write_trace_)) ? traceDirectory() : std::string();
     speculated_ = committed_ = 0;
-    launch_seconds_ = proposal_seconds_ = row_seconds_ = 0.0;
+    launch_seconds_ = proposal_seconds_ = row_seconds_ = commit_seconds_ = 0.0;
     calls_seen_ = 0;
     if (lookahead_ != 1 && 2 * n_chains_ <= LOOKAHEAD_SETS) runLookahead(f, pm, dir);
     while (!done()) {
