@@ -387,7 +387,7 @@ OptimizationResult MetropolisHastingsSampler::result(int upto) const {
 // anyway).  Measured on the device objective at 21 % acceptance, one chain: K = 8 5.7 k, 16 6.2 k, 32 5.9 k, 128 5.0 k iterations/s.
 int MetropolisHastingsSampler::windowLength(const Chain& c, int running, int share) const {
     if (lookahead_ > 1) return std::min(lookahead_, share);
-    if (calls_seen_ < 2) return std::min(calls_seen_ == 0 ? 4 : 16, share);      // the two probe windows (see runLookahead)
+    if (calls_seen_ < 4) return std::min(calls_seen_ % 2 == 0 ? 4 : 16, share);      // the probe windows (see runLookahead)
     const double rate = c.recent.size() < 50 ? 0.234
                                              : std::min(std::max(static_cast<double>(c.recent_sum) / static_cast<double>(c.recent.size()), 0.02), 0.9);
     // a call of the objective over B rows is taken to cost launch + B * row: the device objective is all `launch` (~0.6 ms, ~2 us per
@@ -417,7 +417,15 @@ void MetropolisHastingsSampler::runLookahead(IObjectiveFunction& f, IParameterMa
     std::vector<int> K(static_cast<size_t>(n));
     std::vector<std::ptrdiff_t> first(static_cast<size_t>(n) + 1);
     std::vector<double> props;
+    static const bool debug_timing = std::getenv("SEPAIHRD_HOST_DEBUG_TIMING") != nullptr;
+    double dbg[5] = {0, 0, 0, 0, 0};
+    long dbg_windows = 0;
+    struct DebugReport {
+        const double* d; const long* w; bool on;
+        ~DebugReport() { if (on) std::fprintf(stderr, "look-ahead windows %ld: plan %.3f s, propose %.3f s, objective %.3f s, commit %.3f s, tail %.3f s\n", *w, d[0], d[1], d[2], d[3], d[4]); }
+    } debug_report{dbg, &dbg_windows, debug_timing};
     while (!done()) {
+        const auto clock_plan = std::chrono::steady_clock::now();
         int running = 0;
         for (const Chain& c : chains_) running += c.t < iterations_;
         const int share = std::max(1, LOOKAHEAD_SETS / std::max(running, 1));
@@ -476,19 +484,28 @@ void MetropolisHastingsSampler::runLookahead(IObjectiveFunction& f, IParameterMa
             }
         }
         committed_ += committed;
+        const auto clock3 = std::chrono::steady_clock::now();
         {   // what a proposal costs the host (drawing + its share of the commit) and what a launch costs: running means for windowLength
             const double per = std::chrono::duration<double>(clock1 - clock0).count() / static_cast<double>(std::max<int64_t>(total, 1));
             const double com = std::chrono::duration<double>(std::chrono::steady_clock::now() - clock2).count() / static_cast<double>(std::max<long>(committed, 1));
             const double call = std::chrono::duration<double>(clock2 - clock1).count();
             proposal_seconds_ = proposal_seconds_ > 0 ? 0.8 * proposal_seconds_ + 0.2 * per : per;
             commit_seconds_ = commit_seconds_ > 0 ? 0.8 * commit_seconds_ + 0.2 * com : com;
-            // split the call into its fixed part and its per-row part from the first two windows, which are given different lengths
-            // on purpose (4 and 16 proposals per chain: fresh proposals, so a likelihood cache cannot fake a cheap call)
-            if (calls_seen_ == 0) { probe_rows_ = static_cast<double>(total); probe_seconds_ = call; }
-            else if (calls_seen_ == 1 && static_cast<double>(total) > probe_rows_)
-                row_seconds_ = std::max(0.0, (call - probe_seconds_) / (static_cast<double>(total) - probe_rows_));
+            // Split the call into its fixed part and its per-row part from the first four windows, which are given the lengths 4, 16,
+            // 4, 16 on purpose (fresh proposals, so a likelihood cache cannot fake a cheap call); the cheaper call of each pair counts
+            // (the first call of a size may pay for buffers that grow), and a per-row part below 30 % of the call is taken as zero:
+            // the split only has to tell an objective that scores its rows one after the other from one launch for all of them.
+            if (calls_seen_ < 4) {
+                double& rows = (calls_seen_ % 2 == 0) ? probe_rows_[0] : probe_rows_[1];
+                double& secs = (calls_seen_ % 2 == 0) ? probe_seconds_[0] : probe_seconds_[1];
+                if (calls_seen_ < 2 || call / static_cast<double>(total) < secs / rows) { rows = static_cast<double>(total); secs = call; }
+                if (calls_seen_ == 3 && probe_rows_[1] > probe_rows_[0]) {
+                    const double row = std::max(0.0, (probe_seconds_[1] - probe_seconds_[0]) / (probe_rows_[1] - probe_rows_[0]));
+                    row_seconds_ = row * probe_rows_[1] < 0.3 * probe_seconds_[1] ? 0.0 : row;
+                }
+            }
             const double launch = std::max(call - row_seconds_ * static_cast<double>(total), 0.05 * call);
-            launch_seconds_ = launch_seconds_ > 0 && calls_seen_ > 1 ? 0.8 * launch_seconds_ + 0.2 * launch : launch;
+            launch_seconds_ = launch_seconds_ > 0 && calls_seen_ > 3 ? 0.8 * launch_seconds_ + 0.2 * launch : launch;
             ++calls_seen_;
         }
         // the lockstep loop writes a checkpoint after iteration t when (t + 1) % report_interval == 0 (.cpp:380-382): here once ALL
@@ -500,6 +517,12 @@ void MetropolisHastingsSampler::runLookahead(IObjectiveFunction& f, IParameterMa
             int last = -1;
             for (int t = t_before; t < t_; ++t) if ((t + 1) % report_interval_ == 0) last = t;
             if (last >= 0) saveCheckpoint(result(last), pm, false, dir);
+        }
+        if (debug_timing) {
+            auto sec = [](auto a, auto b) { return std::chrono::duration<double>(b - a).count(); };
+            dbg[0] += sec(clock_plan, clock0); dbg[1] += sec(clock0, clock1); dbg[2] += sec(clock1, clock2); dbg[3] += sec(clock2, clock3);
+            dbg[4] += sec(clock3, std::chrono::steady_clock::now());
+            ++dbg_windows;
         }
     }
 }

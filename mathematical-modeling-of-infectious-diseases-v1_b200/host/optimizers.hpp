@@ -123,7 +123,7 @@ private:
     static constexpr int LOOKAHEAD_SETS = 4096;          // proposals per launch: up to here a launch costs what one set costs
     long speculated_ = 0, committed_ = 0;
     double launch_seconds_ = 0.0, proposal_seconds_ = 0.0;     // running means: fixed part of an objective call; host arithmetic per proposal
-    double row_seconds_ = 0.0, probe_rows_ = 0.0, probe_seconds_ = 0.0;   // per-row part of an objective call, from the two probe windows
+    double row_seconds_ = 0.0, probe_rows_[2] = {0.0, 0.0}, probe_seconds_[2] = {0.0, 0.0};   // per-row part of an objective call, from the probe windows
     double commit_seconds_ = 0.0;                              // host time per committed iteration
     long calls_seen_ = 0;
     long chain_offset_ = 0;
