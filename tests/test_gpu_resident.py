@@ -146,6 +146,23 @@ def test_look_ahead_windows_make_the_one_iteration_runs_decisions(problem, refle
         mh.close()
 
 
+def test_look_ahead_windows_over_a_long_run(problem, reflect_problem, mods):
+    """400 iterations of 16 chains: ~65 000 generator words per chain (over a hundred wrap-arounds of the 624-word state), windows of
+    7 and of 64 iterations -- a window of 64 draws ~10 000 words ahead on the copy and the commit twists the real state forward by
+    whatever was consumed.  Decisions, states and scales equal the one-iteration-per-launch run."""
+    _, evaluator, resident = mods
+    x0 = problem.base_params()
+    with evaluator.BatchEvaluator(reflect_problem, device=0) as ev:
+        ref = resident.run_mh_resident(ev, problem.sigmas, x0, 16, 400, 4242)
+        for K in (7, 64):
+            r = resident.run_mh_resident(ev, problem.sigmas, x0, 16, 400, 4242, lookahead=K)
+            np.testing.assert_array_equal(r["accepts"], ref["accepts"], err_msg=f"K={K}")
+            np.testing.assert_array_equal(r["x"], ref["x"])
+            np.testing.assert_array_equal(r["scale"], ref["scale"])
+            np.testing.assert_array_equal(r["logpost"], ref["logpost"])
+            assert r["windows"] < 399 / 2
+
+
 def test_asynchronous_swarm_equals_the_synchronous_device_swarm(problem, mods):
     drivers, evaluator, resident = mods
     kw = dict(sigmas=problem.sigmas, lower=problem.lower_bound, upper=problem.upper_bound, swarm_size=333, iterations=6, seed=7,
