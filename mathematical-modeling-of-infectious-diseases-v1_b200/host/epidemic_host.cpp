@@ -251,6 +251,8 @@ SEPAIHRDParameterManager::SEPAIHRDParameterManager(std::shared_ptr<AgeSEPAIHRDMo
         const int32_t slot = sepaihrd_slot_for_name(n, nb, nk, name.c_str());   // same dispatch order as .cpp:197-267
         if (slot == -2) throw InvalidParameterException(src, "Parameter '" + name + "' is not a calibratable parameter of this model (fixed baseline kappa or index out of range).");
         slots_.push_back(slot);     // -1: a name updateModelParameters would only warn about (.cpp:265-267)
+        const auto& b = param_bounds_.at(name);                // resolved once: applyConstraints runs per proposal (.cpp:321-335 looks the name up every time)
+        lower_.push_back(b.first); upper_.push_back(b.second);
     }
 }
 
@@ -315,16 +317,11 @@ VectorXd SEPAIHRDParameterManager::applyConstraints(const VectorXd& parameters) 
     if (static_cast<size_t>(parameters.size()) != param_names_.size())
         throw InvalidParameterException("SEPAIHRDParameterManager::applyConstraints", "Parameter vector size mismatch.");
     VectorXd out = parameters;
-    for (size_t i = 0; i < param_names_.size(); ++i) {
+    for (size_t i = 0; i < param_names_.size(); ++i) {       // every calibrated name has bounds (checked by the constructor)
         const auto k = static_cast<std::ptrdiff_t>(i);
-        auto it = param_bounds_.find(param_names_[i]);
-        if (it != param_bounds_.end()) {
-            double lo = it->second.first, hi = it->second.second;
-            if (lo > hi) std::swap(lo, hi);
-            out(k) = (mode_ == ConstraintMode::OPTIMIZATION_CLAMP) ? std::min(std::max(parameters(k), lo), hi) : reflectBound(parameters(k), lo, hi);
-        } else {
-            out(k) = (mode_ == ConstraintMode::OPTIMIZATION_CLAMP) ? std::max(0.0, parameters(k)) : std::abs(parameters(k));
-        }
+        double lo = lower_[i], hi = upper_[i];
+        if (lo > hi) std::swap(lo, hi);
+        out(k) = (mode_ == ConstraintMode::OPTIMIZATION_CLAMP) ? std::min(std::max(parameters(k), lo), hi) : reflectBound(parameters(k), lo, hi);
     }
     return out;
 }
@@ -336,11 +333,11 @@ int SEPAIHRDParameterManager::getIndexForParam(const std::string& name) const {
 
 double SEPAIHRDParameterManager::getLowerBoundForParamIndex(int idx) const {
     if (idx < 0 || static_cast<size_t>(idx) >= param_names_.size()) throw OutOfRangeException("SEPAIHRDParameterManager::getLowerBoundForParamIndex", "Index out of bounds.");
-    return param_bounds_.at(param_names_[static_cast<size_t>(idx)]).first;
+    return lower_[static_cast<size_t>(idx)];
 }
 double SEPAIHRDParameterManager::getUpperBoundForParamIndex(int idx) const {
     if (idx < 0 || static_cast<size_t>(idx) >= param_names_.size()) throw OutOfRangeException("SEPAIHRDParameterManager::getUpperBoundForParamIndex", "Index out of bounds.");
-    return param_bounds_.at(param_names_[static_cast<size_t>(idx)]).second;
+    return upper_[static_cast<size_t>(idx)];
 }
 
 void SEPAIHRDParameterManager::setConstraintMode(ConstraintMode mode) {

@@ -348,6 +348,7 @@ private:
     std::vector<std::string> param_names_;
     std::map<std::string, double> proposal_sigmas_;
     std::map<std::string, std::pair<double, double>> param_bounds_;
+    std::vector<double> lower_, upper_;       // param_bounds_ by parameter index
     std::vector<int32_t> slots_;
     std::vector<std::function<void(ConstraintMode)>> mode_listeners_;
 };
