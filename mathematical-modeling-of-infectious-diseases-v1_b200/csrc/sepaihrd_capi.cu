@@ -154,6 +154,10 @@ sepaihrd_rc launch_t(sepaihrd_ctx* ctx, const sepaihrd::KParams& kp_in) {
     // A warp pays the day-by-day MAXIMUM of its sets' attempts.  While there are fewer sets than warp slots with a scheduler of
     // their own (4 per SM), a warp takes fewer sets per tile, down to one: 8 sets cost what 1 set costs (0.51 ms, not 0.57).
     kp.sets_per_tile = (int)std::min<long long>(WSETS, std::max<long long>(1, (kp.B + 4LL * ctx->num_sms - 1) / (4LL * ctx->num_sms)));
+    {   // experiments: SEPAIHRD_SETS_PER_TILE=n forces the tile width of launches without an index list
+        static const int forced = std::getenv("SEPAIHRD_SETS_PER_TILE") ? std::atoi(std::getenv("SEPAIHRD_SETS_PER_TILE")) : 0;
+        if (forced > 0) kp.sets_per_tile = std::min(forced, WSETS);
+    }
     if (PROFILE || kp.perm) kp.sets_per_tile = WSETS;
     kp.tiles = (kp.B + kp.sets_per_tile - 1) / kp.sets_per_tile;
     if (kp.tiles > 0xffff0000LL) return fail(SEPAIHRD_ERR_UNSUPPORTED, "batch too large for one launch");
