@@ -372,17 +372,18 @@ def run_pso_resident(ev, swarm_size: int, iterations: int, seed: int, initial=No
 
 def window_length(local: int, requested: Optional[int] = None, rate: float = 0.234) -> int:
     """Iterations per window of the device-resident sampler.  K proposals per chain commit g(K) = (1 - (1 - rate)^K) / rate
-    iterations on average; a likelihood launch costs ~0.55 ms up to 4096 sets and ~0.095 ms per further 1024 (measured,
-    profiles/r02_v17_small_batch_latency.txt), a proposal ~4 us of a warp's time.  K = argmax g(K) / cost(local * K):
-    16 for <= 256 chains per GPU, 8 for 512, 4 for 1024, 3 for 2048, 2 for 4096."""
+    iterations on average; a likelihood launch costs ~0.59 ms while every warp has a scheduler to itself (592 warps of 8 sets:
+    4736 sets), ~0.81 ms while two share one (9472 sets), and a further ~0.8 ms per wave of 9472 sets beyond
+    (profiles/r02_v17_sets_per_tile_ab.txt); a proposal costs ~5 us of a warp's time, the rest of a window ~0.06 ms.
+    K = argmax g(K) / cost(local * K): 11 up to 256 chains per GPU, 9 for 512, 4 for 1024 and for 2048, 2 for 4096."""
     if requested is not None:
         return max(1, min(64, int(requested)))
     best, best_rate, miss = 1, 0.0, 1.0
     for k in range(1, 17):
         miss *= 1.0 - rate
         sets = max(int(local), 1) * k
-        cost = 0.55 + max(0, sets - 4096) * (0.095 / 1024) + 0.004 * k + 0.05
-        r = (1.0 - miss) / rate / cost
+        launch = 0.59 if sets <= 4736 else 0.81 if sets <= 9472 else 0.81 + 0.8 * -(-(sets - 9472) // 9472)
+        r = (1.0 - miss) / rate / (launch + 0.005 * k + 0.06)
         if r > best_rate * 1.02:               # a longer window has to pay by more than the noise
             best, best_rate = k, r
     return best
