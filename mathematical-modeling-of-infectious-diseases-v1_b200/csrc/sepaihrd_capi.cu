@@ -175,7 +175,16 @@ sepaihrd_rc launch_t(sepaihrd_ctx* ctx, const sepaihrd::KParams& kp_in) {
     }
     if (smem > 200 * 1024) return fail(SEPAIHRD_ERR_UNSUPPORTED, "problem constants do not fit in shared memory");
     int occ = 0;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, smem));
+    {   // asked once per (instantiation, device, shared-memory size): a small launch should not pay for the query every time
+        struct OccCache { int device = -1; size_t smem = 0; int occ = 0; };
+        static thread_local OccCache cache;
+        if (cache.device != ctx->device || cache.smem != smem) {
+            int o = 0;
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, THREADS, smem));
+            cache.device = ctx->device; cache.smem = smem; cache.occ = o;
+        }
+        occ = cache.occ;
+    }
     if (occ < 1) return fail(SEPAIHRD_ERR_CUDA, "kernel does not fit on an SM");
     // one block per tile until the machine is full; a launch smaller than the machine uses only as many warps per block as it needs
     long long grid = std::min<long long>(kp.tiles, (long long)ctx->num_sms * occ);
