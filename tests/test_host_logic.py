@@ -181,3 +181,15 @@ def test_select_ages_builds_consistent_sub_problems(problem, orc):
     assert problem.base_params()[i_old] == sub.base_params()[i_new]
     with pytest.raises(ValueError):
         problem.select_ages([0, 4])
+
+
+def test_device_window_length_follows_the_launch_cost_steps(pkg):
+    """resident.window_length: iterations per look-ahead window of the device-resident chains from the measured steps of the launch
+    cost (592 warp tiles of 8 sets at one warp per scheduler, 1184 at two): more chains per GPU -> shorter windows, never more
+    proposals than a second wave would start for, an explicit request is clamped to 1 .. 64."""
+    from sepaihrd_b200 import resident
+    ks = [resident.window_length(n) for n in (1, 64, 256, 512, 1024, 2048, 4096, 8192, 65536)]
+    assert ks == sorted(ks, reverse=True) and ks[0] >= 8 and ks[-1] == 1
+    assert resident.window_length(512) * 512 <= 4736 and resident.window_length(2048) * 2048 <= 9472 and resident.window_length(4096) == 2
+    assert resident.window_length(100, 0) == 1 and resident.window_length(100, 1000) == 64 and resident.window_length(100, 7) == 7
+    assert resident.window_length(512, rate=0.05) >= resident.window_length(512, rate=0.5)          # rare accepts: longer windows pay
